@@ -1,0 +1,150 @@
+"""The C oracle (built-in loops and OpenBLAS-backed) against dense long-double arithmetic --
+the oracle pattern of the reference's own tests ("structured ~= dense")."""
+import numpy as np
+import pytest
+
+from oracle import cpu as O
+from oracle import formats as F
+from tests.helpers import BBB_CASES, dense_mul_ld, random_bbb, random_sky, relerr, tol
+
+
+@pytest.fixture(params=["builtin", "openblas"])
+def blas(request):
+    if request.param == "openblas":
+        if not O.use_openblas(threads=1):
+            pytest.skip("OpenBLAS not found")
+    else:
+        O.use_builtin()
+    yield request.param
+    O.use_builtin()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", BBB_CASES, ids=lambda c: f"r{len(c[0])}c{len(c[1])}_l{c[2]}u{c[3]}_lam{c[4]}mu{c[5]}")
+def test_bbb_mul_vs_dense(case, dtype, blas):
+    rows, cols, l, u, lam, mu = case
+    rng = np.random.default_rng(1234)
+    data = random_bbb(rng, rows, cols, l, u, lam, mu, dtype)
+    A = F.bbb_to_dense(data, rows, cols, l, u, lam, mu)
+    assert not np.isnan(A).any()
+    m, n = A.shape
+    for nrhs, alpha, beta in [(None, 1.0, 0.0), (None, 2.5, -0.5), (3, 1.0, 1.0)]:
+        shape_x = (n,) if nrhs is None else (n, nrhs)
+        shape_y = (m,) if nrhs is None else (m, nrhs)
+        X = np.asfortranarray(rng.standard_normal(shape_x).astype(dtype))
+        Y0 = np.asfortranarray(rng.standard_normal(shape_y).astype(dtype))
+        Y = Y0.copy(order="F")
+        if beta == 0.0:
+            Y[...] = np.nan  # beta == 0 must overwrite, never read (test/test_blockskyline.jl:34-39)
+        O.bbb_mul(rows, cols, l, u, lam, mu, alpha, data, X, beta, Y)
+        ref = alpha * dense_mul_ld(A, X) + (beta * Y0.astype(np.longdouble) if beta != 0 else 0)
+        assert relerr(Y, ref) <= tol(dtype, F.bbb_nnz_per_row_max(l, u, lam, mu) + 1)
+
+
+def test_bbb_laplacian_is_the_five_point_stencil(blas):
+    n = 24
+    data = F.laplacian_bbb_data(n)
+    x = np.random.default_rng(0).standard_normal(n * n)
+    y = np.full(n * n, np.nan)
+    O.bbb_mul([n] * n, [n] * n, 1, 1, 1, 1, 1.0, data, x, 0.0, y)
+    assert relerr(y, F.laplacian_apply(x, n)) <= tol(np.float64, 9)
+
+
+def test_bbb_dimension_mismatch():
+    data = np.zeros(F.bbb_data_shape([2, 2], 1, 1, 1, 1), order="F")
+    with pytest.raises(ValueError):
+        O.bbb_mul([2, 2], [2, 2], 1, 1, 1, 1, 1.0, data, np.zeros(5), 0.0, np.zeros(4))
+
+
+SKY_CASES = [
+    (list(range(1, 5)), list(range(1, 5)), 1, 1),                       # test/test_linalg.jl:35-57
+    ([3, 4, 5], [2, 3, 4, 3], 0, 1),                                    # test/test_triblockbanded.jl:101-107
+    ([3, 1, 2, 1, 2, 1, 2, 1, 2, 1, 3], [3, 1, 2, 1, 2, 1, 2, 1, 2, 1, 3],
+     [1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1], [1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1]),  # test/test_blockskyline.jl:43-44
+    ([9, 4, 1, 10, 6], [9, 4, 1, 10, 6], [-2, 2, 0, 2, -1], [-1, 2, 1, 0, -1]),  # :75-76 ragged negative
+    ([16] * 8, [16] * 8, 2, 2),                                         # cfg4-like
+    ([40, 7, 130, 3], [20, 50, 9, 64], 1, 2),
+    ([], [], 0, 0),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", SKY_CASES, ids=lambda c: f"r{len(c[0])}c{len(c[1])}")
+def test_sky_mul_vs_dense(case, dtype, blas):
+    rows, cols, l, u = case
+    rng = np.random.default_rng(7)
+    data = random_sky(rng, rows, cols, l, u, dtype)
+    A = F.sky_to_dense(data, rows, cols, l, u)
+    m, n = A.shape
+    for nrhs, alpha, beta in [(None, 1.0, 0.0), (4, -1.5, 0.75)]:
+        X = np.asfortranarray(rng.standard_normal((n,) if nrhs is None else (n, nrhs)).astype(dtype))
+        Y0 = np.asfortranarray(rng.standard_normal((m,) if nrhs is None else (m, nrhs)).astype(dtype))
+        Y = Y0.copy(order="F")
+        if beta == 0.0:
+            Y[...] = np.nan
+        O.sky_mul(rows, cols, l, u, alpha, data, X, beta, Y)
+        ref = alpha * dense_mul_ld(A, X) + (beta * Y0.astype(np.longdouble) if beta != 0 else 0)
+        assert relerr(Y, ref) <= tol(dtype, n + 1)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sky_matmul_vs_dense(dtype, blas):
+    rng = np.random.default_rng(11)
+    for rows, l, u, const in [([16] * 8, 2, 2, True), ([3, 1, 2, 1, 2, 1, 2], [1, 2, 1, 2, 1, 2, 1], [1, 2, 1, 2, 1, 2, 1], False),
+                              ([5, 9, 2, 7], 1, 0, True)]:
+        Ad = random_sky(rng, rows, rows, l, u, dtype)
+        Bd = random_sky(rng, rows, rows, l, u, dtype)
+        lv = np.full(len(rows), l) if np.isscalar(l) else np.array(l)
+        uv = np.full(len(rows), u) if np.isscalar(u) else np.array(u)
+        Cl, Cu = F.add_bandwidths(lv, uv, lv, uv, constant=const)
+        n = F.sky_numentries(rows, rows, Cl, Cu)
+        C0 = rng.standard_normal(n).astype(dtype)
+        for alpha, beta in [(1.0, 0.0), (2.0, -1.0)]:
+            Cd = C0.copy()
+            if beta == 0:
+                Cd[:] = np.nan
+            O.sky_matmul((rows, rows, l, u), (rows, rows, l, u), (rows, rows, Cl, Cu), alpha, Ad, Bd, beta, Cd)
+            A = F.sky_to_dense(Ad, rows, rows, l, u).astype(np.longdouble)
+            B = F.sky_to_dense(Bd, rows, rows, l, u).astype(np.longdouble)
+            ref = alpha * (A @ B) + (beta * F.sky_to_dense(C0, rows, rows, Cl, Cu).astype(np.longdouble) if beta else 0)
+            got = F.sky_to_dense(Cd, rows, rows, Cl, Cu)
+            assert relerr(got, ref) <= tol(dtype, sum(rows))
+            # nothing outside the product's band was needed: the stored part holds the full product
+            assert np.count_nonzero(np.isnan(Cd)) == 0
+
+
+def test_sky_matmul_band_violation_and_dims():
+    rows = [2, 2, 2]
+    Ad = np.ones(F.sky_numentries(rows, rows, 1, 1))
+    Cd = np.zeros(F.sky_numentries(rows, rows, 1, 1))
+    with pytest.raises(IndexError):  # C (1,1) too narrow for a (2,2) product
+        O.sky_matmul((rows, rows, 1, 1), (rows, rows, 1, 1), (rows, rows, 1, 1), 1.0, Ad, Ad, 0.0, Cd)
+    with pytest.raises(ValueError):
+        O.sky_matmul((rows, rows, 1, 1), ([2, 2], [2, 2], 1, 1), (rows, [2, 2], 2, 2), 1.0, Ad, Ad, 0.0, Cd)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
+def test_sky_trsm_vs_dense(dtype, uplo, unit, blas):
+    rng = np.random.default_rng(5)
+    for rows, l, u in [(list(range(1, 5)), 1, 1), ([8] * 6, 0, 3), ([8] * 6, 2, 0), ([3, 7, 1, 12, 5], 2, 1), ([6], 0, 0)]:
+        m = sum(rows)
+        data = random_sky(rng, rows, rows, l, u, dtype, scale=1.0 / np.sqrt(max(m, 1)))
+        A = F.sky_to_dense(data, rows, rows, l, u)
+        A += 10 * np.eye(m, dtype=dtype)  # well conditioned, cf. test/test_triblockbanded.jl:83
+        data = F.sky_from_dense(A, rows, rows, l, u)
+        T = np.triu(A) if uplo == "U" else np.tril(A)
+        if unit:
+            np.fill_diagonal(T, 1)
+        for nrhs in (None, 3):
+            B0 = np.asfortranarray(rng.standard_normal((m,) if nrhs is None else (m, nrhs)).astype(dtype))
+            B = B0.copy(order="F")
+            out = O.sky_trsm(rows, l, u, uplo, unit, data, B)
+            assert out is B  # in place (test/test_linalg.jl:65,75)
+            ref = np.linalg.solve(T.astype(np.float64), B0.astype(np.float64))
+            assert relerr(B, ref) <= tol(dtype, m)
+
+
+def test_sky_trsm_needs_diagonal_blocks():
+    with pytest.raises(IndexError):
+        O.sky_trsm([2, 2, 2], -1, 2, "U", False, np.ones(F.sky_numentries([2, 2, 2], [2, 2, 2], -1, 2)), np.ones(6))
