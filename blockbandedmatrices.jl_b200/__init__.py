@@ -1,0 +1,15 @@
+"""bbm_b200 -- B200-native block-banded ``mul!`` / ``ldiv!`` (the hot path of
+BlockBandedMatrices.jl) behind the reference's container / lazy-op interface.
+
+The arithmetic lives in ``lib/libbbm_b200.so`` (hand-written CUDA for sm_100a, C ABI declared in
+``include/bbm_b200.h``); this package is the host-side mirror of the reference interface used by
+the tests and the benchmark (Julia is not available in the build image; INTEGRATION.md shows the
+equivalent Julia package extension).
+"""
+from ._lib import BandError, BBMError, DimensionMismatch, build_library, LIB_PATH, SIGNATURES  # noqa: F401
+from .device import DeviceArray, Handle, PinnedArray  # noqa: F401
+from .linalg import mul, mul_, muladd_  # noqa: F401
+from .matrices import BandedBlockBandedMatrix  # noqa: F401
+
+__all__ = ["BandedBlockBandedMatrix", "Handle", "DeviceArray", "PinnedArray", "mul", "mul_", "muladd_",
+           "DimensionMismatch", "BandError", "BBMError", "build_library"]

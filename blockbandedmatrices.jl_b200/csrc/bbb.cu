@@ -1,0 +1,601 @@
+// BandedBlockBandedMatrix * vector(s): descriptor, work partition and the two kernels.
+//
+//   bbb_walk_kernel     the fused band-walk kernel (hot path).  One CTA owns a tile of T in-block
+//                       rows k in [k0,k0+T) and a segment of block rows [Ka,Kb).  It walks the
+//                       block columns J = Ka-l .. Kb-1+u once; at step J it bulk-copies (TMA 1-D,
+//                       cp.async.bulk + mbarrier ring) the *whole* contiguous P x (T+lam+mu) column
+//                       chunk of block column J plus the matching x chunk into shared memory, and
+//                       every thread (one output row each) gathers its l+u+1 slabs x lam+mu+1 band
+//                       entries from it.  Partial sums for the l+u+1 block rows that block column
+//                       J touches live in a register window that shifts by one per step; block row
+//                       J-u is complete after step J and is written exactly once.
+//                       => every byte of `data` is read from HBM once, in large contiguous pieces;
+//                       y is written once; no atomics; summation order per entry is ascending
+//                       global column, like the reference's per-block gbmv sweep.
+//   bbb_generic_kernel  one thread per output row, direct global loads.  Takes every case the
+//                       walk kernel does not (more than 8 block bands, P too large for shared
+//                       memory, tiny blocks, empty bands).
+//
+// Reference behaviour being replaced: SURVEY.md 3.1 ([upstream] BlockArrays block loop + BLAS
+// gbmv per block, operands from src/BandedBlockBandedMatrix.jl:503-545, bounds from
+// src/AbstractBlockBandedMatrix.jl:90-104).
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "bbm_internal.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kMaxNS = 8;  // block bands (l+u+1) the walk kernel keeps in registers
+
+struct BbbItem {
+    int32_t Ka, Kb;  // block-row segment [Ka,Kb)
+    int32_t k0;      // first in-block row of the tile
+    int32_t pad;
+};
+
+struct Partition {
+    int tile = 0;
+    int maxseg = 0;  // longest segment (block rows)
+    int nitems = 0;
+    BbbItem* d_items = nullptr;
+};
+
+}  // namespace
+
+struct bbm_bbb_desc {
+    uint32_t magic = 0xBBBDE5C0u;
+    bbm_handle_t h = nullptr;
+    i64 Nr = 0, Nc = 0, l = 0, u = 0, lam = 0, mu = 0;
+    i64 m = 0, n = 0, P = 0, maxr = 0;
+    std::vector<i64> r, c, R, C;
+    i64* dR = nullptr;
+    i64* dC = nullptr;
+    std::map<std::pair<int, int>, Partition> parts;  // (tile, target items) -> partition
+};
+
+namespace {
+
+inline bool desc_valid(bbm_bbb_desc_t d) { return d && d->magic == 0xBBBDE5C0u && bbm_valid(d->h); }
+
+template <typename T>
+struct BbbParams {
+    const T* data;
+    const T* X;
+    T* Y;
+    i64 ldx, ldy;
+    T alpha, beta;
+    const i64* R;
+    const i64* C;
+    const BbbItem* items;
+    i64 Nr, Nc, m;
+    int l, u, lam, mu, w, P;
+    int stages;
+    int maxseg;
+    int stage_data_bytes;  // per-stage bytes reserved for the matrix chunk
+    int stage_x_bytes;     // per-stage bytes reserved for the x chunk
+    int l2hint;
+};
+
+// ------------------------------------------------------------------------------------------------
+// band-walk kernel
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct StepGeom {
+    int jlo, jhi, cJ;  // loaded in-block column range [jlo,jhi), block-column width
+    i64 cbeg;          // first global column of block column J
+};
+
+template <typename T>
+__device__ __forceinline__ StepGeom<T> step_geom(const i64* Ctab, int it, int k0, int tile, int lam, int mu) {
+    StepGeom<T> g;
+    g.cbeg = Ctab[it];
+    g.cJ = static_cast<int>(Ctab[it + 1] - g.cbeg);
+    g.jlo = max(0, k0 - lam);
+    g.jhi = min(g.cJ, k0 + tile + mu);
+    return g;
+}
+
+template <typename T, int NS, int W>
+__global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int tile = blockDim.x;
+    const int w = (W > 0) ? W : p.w;
+    const int P = p.P;
+    const int S = p.stages;
+
+    const BbbItem item = p.items[blockIdx.x];
+    const int Ka = item.Ka, Kb = item.Kb, k0 = item.k0;
+    const int Jfirst = Ka - p.l;
+    const int nsteps = (Kb - Ka) + NS - 1;
+
+    // shared memory carve-up
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                       // S barriers (<= 16)
+    i64* Rtab = reinterpret_cast<i64*>(smem + 128);                           // maxseg+1
+    i64* Ctab = Rtab + (p.maxseg + 1);                                        // maxseg+NS+1
+    size_t tab_bytes = 128 + sizeof(i64) * (size_t)(2 * p.maxseg + NS + 2);
+    tab_bytes = (tab_bytes + 127) & ~size_t(127);
+    unsigned char* stage0 = smem + tab_bytes;
+    const int stage_bytes = p.stage_data_bytes + p.stage_x_bytes;
+
+    const T* __restrict__ Xq = p.X + (i64)blockIdx.y * p.ldx;
+    T* __restrict__ Yq = p.Y + (i64)blockIdx.y * p.ldy;
+
+    for (int i = tid; i <= Kb - Ka; i += tile) Rtab[i] = p.R[Ka + i];
+    for (int i = tid; i <= nsteps; i += tile) {
+        i64 J = (i64)Jfirst + i;
+        J = J < 0 ? 0 : (J > p.Nc ? p.Nc : J);
+        Ctab[i] = p.C[J];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) ptx::mbar_init(&bars[s], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint64_t pol_stream = 0, pol_keep = 0;
+    if (tid == 0 && p.l2hint) {
+        pol_stream = ptx::policy_evict_first();
+        pol_keep = ptx::policy_evict_last();
+    }
+
+    // producer: one thread issues the bulk copies of a step and arms its barrier
+    auto issue = [&](int it) {
+        const int st = it % S;
+        const StepGeom<T> g = step_geom<T>(Ctab, it, k0, tile, p.lam, p.mu);
+        if (g.jlo >= g.jhi) {
+            ptx::mbar_arrive(&bars[st]);  // nothing to load for this step
+            return;
+        }
+        unsigned char* sd = stage0 + (size_t)st * stage_bytes;
+        unsigned char* sx = sd + p.stage_data_bytes;
+        const uintptr_t d0 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jlo) * (i64)P);
+        const uintptr_t d1 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jhi) * (i64)P);
+        const uintptr_t x0 = reinterpret_cast<uintptr_t>(Xq + g.cbeg + g.jlo);
+        const uintptr_t x1 = reinterpret_cast<uintptr_t>(Xq + g.cbeg + g.jhi);
+        const uintptr_t dg0 = d0 & ~uintptr_t(15), dg1 = (d1 + 15) & ~uintptr_t(15);
+        const uintptr_t xg0 = x0 & ~uintptr_t(15), xg1 = (x1 + 15) & ~uintptr_t(15);
+        const uint32_t dbytes = static_cast<uint32_t>(dg1 - dg0);
+        const uint32_t xbytes = static_cast<uint32_t>(xg1 - xg0);
+        ptx::mbar_arrive_expect_tx(&bars[st], dbytes + xbytes);
+        if (p.l2hint) {
+            ptx::bulk_g2s_hint(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st], pol_stream);
+            ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
+        } else {
+            ptx::bulk_g2s(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st]);
+            ptx::bulk_g2s(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st]);
+        }
+    };
+
+    if (tid == 0) {
+        for (int it = 0; it < S - 1 && it < nsteps; ++it) issue(it);
+    }
+
+    T acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = T(0);
+
+    const int k = k0 + tid;
+    const T alpha = p.alpha, beta = p.beta;
+
+    for (int it = 0; it < nsteps; ++it) {
+        // every thread has finished reading the stage that step it+S-1 will overwrite
+        __syncthreads();
+        if (tid == 0 && it + S - 1 < nsteps) issue(it + S - 1);
+
+        const int st = it % S;
+        const int J = Jfirst + it;
+        const StepGeom<T> g = step_geom<T>(Ctab, it, k0, tile, p.lam, p.mu);
+        ptx::mbar_wait(&bars[st], (uint32_t)((it / S) & 1));
+
+        if (g.jlo < g.jhi) {
+            const unsigned char* sd = stage0 + (size_t)st * stage_bytes;
+            const unsigned char* sx = sd + p.stage_data_bytes;
+            const uintptr_t d0 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jlo) * (i64)P);
+            const uintptr_t x0 = reinterpret_cast<uintptr_t>(Xq + g.cbeg + g.jlo);
+            // Ds[(j-jlo)*P + row] = data[row, cbeg+j];  Xs[j-jlo] = x[cbeg+j]
+            const T* Ds = reinterpret_cast<const T*>(sd + (d0 & 15));
+            const T* Xs = reinterpret_cast<const T*>(sx + (x0 & 15));
+            const int cJ = g.cJ, jlo = g.jlo;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int K = J + s - p.u;
+                if (K >= Ka && K < Kb) {  // block-uniform
+                    const int rK = static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]);
+                    if (k < rK) {
+                        if (W > 0) {
+#pragma unroll
+                            for (int ii = (W > 0 ? W : 1) - 1; ii >= 0; --ii) {  // ascending column j
+                                const int j = k + p.mu - ii;
+                                if (j >= 0 && j < cJ) acc[s] = fma(Ds[(j - jlo) * P + s * w + ii], Xs[j - jlo], acc[s]);
+                            }
+                        } else {
+                            for (int ii = w - 1; ii >= 0; --ii) {
+                                const int j = k + p.mu - ii;
+                                if (j >= 0 && j < cJ) acc[s] = fma(Ds[(j - jlo) * P + s * w + ii], Xs[j - jlo], acc[s]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // block row J-u has now received every block column it overlaps: write it out once
+        const int Kdone = J - p.u;
+        if (Kdone >= Ka && Kdone < Kb) {
+            const i64 r0 = Rtab[Kdone - Ka];
+            const int rK = static_cast<int>(Rtab[Kdone - Ka + 1] - r0);
+            if (k < rK) {
+                T y = alpha * acc[0];
+                if (beta != T(0)) y = fma(beta, Yq[r0 + k], y);
+                Yq[r0 + k] = y;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s + 1 < NS; ++s) acc[s] = acc[s + 1];
+        acc[NS - 1] = T(0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: one thread per output row
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bbb_generic_kernel(const BbbParams<T> p) {
+    const T* __restrict__ Xq = p.X + (i64)blockIdx.y * p.ldx;
+    T* __restrict__ Yq = p.Y + (i64)blockIdx.y * p.ldy;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < p.m; row += stride) {
+        // K = last block with R[K] <= row (zero-size blocks share a start; take the non-empty one)
+        i64 lo = 0, hi = p.Nr;  // invariant: R[lo] <= row < R[hi]
+        while (hi - lo > 1) {
+            const i64 mid = (lo + hi) >> 1;
+            if (p.R[mid] <= row) lo = mid; else hi = mid;
+        }
+        const i64 K = lo;
+        const i64 k = row - p.R[K];
+        T acc = T(0);
+        if (p.P > 0) {
+            const i64 Jlo = max((i64)0, K - p.l), Jhi = min(p.Nc - 1, K + p.u);
+            for (i64 J = Jlo; J <= Jhi; ++J) {
+                const i64 cbeg = p.C[J];
+                const i64 cJ = p.C[J + 1] - cbeg;
+                const T* slab = p.data + (i64)(p.u + K - J) * p.w;
+                for (int ii = p.w - 1; ii >= 0; --ii) {
+                    const i64 j = k + p.mu - ii;
+                    if (j >= 0 && j < cJ) acc = fma(slab[ii + (i64)p.P * (cbeg + j)], Xq[cbeg + j], acc);
+                }
+            }
+        }
+        T y = p.alpha * acc;
+        if (p.beta != T(0)) y = fma(p.beta, Yq[row], y);
+        Yq[row] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: partition + dispatch
+// ------------------------------------------------------------------------------------------------
+size_t walk_tab_bytes(int maxseg, int NS) {
+    size_t b = 128 + sizeof(i64) * (size_t)(2 * maxseg + NS + 2);
+    return (b + 127) & ~size_t(127);
+}
+
+template <typename T>
+void walk_stage_bytes(int tile, int w, i64 P, int* dbytes, int* xbytes) {
+    size_t d = (size_t)(tile + w - 1) * (size_t)P * sizeof(T) + 32;
+    size_t x = (size_t)(tile + w - 1) * sizeof(T) + 32;
+    *dbytes = (int)((d + 15) & ~size_t(15));
+    *xbytes = (int)((x + 15) & ~size_t(15));
+}
+
+// Split the (tile, block-row) work into items of about equal weight.  A tile t covers in-block
+// rows [t*T, (t+1)*T); only block rows with r[K] > t*T take part, in maximal runs.
+int32_t build_partition(bbm_bbb_desc_t d, int tile, int target_items, int maxseg_cap, Partition* out) {
+    bbm_handle_t h = d->h;
+    const i64 Nr = d->Nr;
+    const int NS = (int)(d->l + d->u + 1);
+    const i64 ovh = 16;
+    struct Run { int t; i64 Ka, Kb; double wt; };
+    std::vector<Run> runs;
+    const i64 ntiles = (d->maxr + tile - 1) / tile;
+    double total = 0;
+    for (i64 t = 0; t < ntiles; ++t) {
+        const i64 k0 = t * tile;
+        i64 K = 0;
+        while (K < Nr) {
+            if (d->r[K] <= k0) { ++K; continue; }
+            Run run{(int)t, K, K, 0.0};
+            while (K < Nr && d->r[K] > k0) { run.wt += (double)(std::min<i64>(tile, d->r[K] - k0) + ovh); ++K; }
+            run.Kb = K;
+            total += run.wt;
+            runs.push_back(run);
+        }
+    }
+    std::vector<BbbItem> items;
+    const double target = std::max(total / std::max(1, target_items), 1.0);
+    const i64 minlen = std::max<i64>(1, 8 * (NS - 1));  // keep the (NS-1)-step ramp under ~12%
+    int maxseg = 1;
+    for (const Run& run : runs) {
+        i64 Ka = run.Ka;
+        while (Ka < run.Kb) {
+            double acc = 0;
+            i64 Kb = Ka;
+            const i64 k0 = (i64)run.t * tile;
+            while (Kb < run.Kb && (Kb - Ka) < maxseg_cap && (acc < target || (Kb - Ka) < minlen)) {
+                acc += (double)(std::min<i64>(tile, d->r[Kb] - k0) + ovh);
+                ++Kb;
+            }
+            // do not leave a sliver behind
+            if (run.Kb - Kb < minlen / 2 && (run.Kb - Ka) <= maxseg_cap) Kb = run.Kb;
+            items.push_back(BbbItem{(int32_t)Ka, (int32_t)Kb, (int32_t)k0, 0});
+            maxseg = std::max<int>(maxseg, (int)(Kb - Ka));
+            Ka = Kb;
+        }
+    }
+    // adjacent tiles of the same segment read adjacent memory: order by (Ka, tile)
+    std::stable_sort(items.begin(), items.end(), [](const BbbItem& a, const BbbItem& b) {
+        return a.Ka != b.Ka ? a.Ka < b.Ka : a.k0 < b.k0;
+    });
+    out->tile = tile;
+    out->maxseg = maxseg;
+    out->nitems = (int)items.size();
+    out->d_items = nullptr;
+    if (!items.empty()) {
+        cudaError_t e = cudaMalloc(&out->d_items, items.size() * sizeof(BbbItem));
+        if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(items): %s", cudaGetErrorString(e)); }
+        BBM_CUDA(h, cudaMemcpy(out->d_items, items.data(), items.size() * sizeof(BbbItem), cudaMemcpyHostToDevice));
+    }
+    return BBM_OK;
+}
+
+template <typename T, int NS>
+cudaError_t launch_walk_w(const BbbParams<T>& p, int w, dim3 grid, int tile, size_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, tile, smem, st>>>(p);
+        return cudaGetLastError();
+    };
+    if (w == 3) return go(bbb_walk_kernel<T, NS, 3>);
+    if (w == 5) return go(bbb_walk_kernel<T, NS, 5>);
+    return go(bbb_walk_kernel<T, NS, 0>);
+}
+
+template <typename T>
+cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, dim3 grid, int tile, size_t smem, cudaStream_t st) {
+    switch (NS) {
+        case 1: return launch_walk_w<T, 1>(p, w, grid, tile, smem, st);
+        case 2: return launch_walk_w<T, 2>(p, w, grid, tile, smem, st);
+        case 3: return launch_walk_w<T, 3>(p, w, grid, tile, smem, st);
+        case 4: return launch_walk_w<T, 4>(p, w, grid, tile, smem, st);
+        case 5: return launch_walk_w<T, 5>(p, w, grid, tile, smem, st);
+        case 6: return launch_walk_w<T, 6>(p, w, grid, tile, smem, st);
+        case 7: return launch_walk_w<T, 7>(p, w, grid, tile, smem, st);
+        case 8: return launch_walk_w<T, 8>(p, w, grid, tile, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename T>
+int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs,
+                     T beta, T* d_Y, i64 ldy) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!desc_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BandedBlockBandedMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && (ldx < std::max<i64>(1, d->n) || ldy < std::max<i64>(1, d->m)))
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: A is %lld x %lld, ldx=%lld, ldy=%lld", (long long)d->m,
+                        (long long)d->n, (long long)ldx, (long long)ldy);
+    if (d->m == 0 || nrhs == 0) return BBM_OK;
+    if (!d_Y || (d->n > 0 && !d_X) || (d->P > 0 && d->n > 0 && !d_data))
+        return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (nrhs > 65535) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "nrhs > 65535");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+
+    BbbParams<T> p{};
+    p.data = d_data; p.X = d_X; p.Y = d_Y; p.ldx = ldx; p.ldy = ldy; p.alpha = alpha; p.beta = beta;
+    p.R = d->dR; p.C = d->dC; p.Nr = d->Nr; p.Nc = d->Nc; p.m = d->m;
+    p.l = (int)d->l; p.u = (int)d->u; p.lam = (int)d->lam; p.mu = (int)d->mu;
+    p.w = (int)(d->lam + d->mu + 1); p.P = (int)d->P;
+    p.l2hint = (int)bbm_opt(h, "bbb.l2hint", 1);
+
+    const i64 NS = d->l + d->u + 1;
+    const int w = p.w;
+    const i64 force = bbm_opt(h, "bbb.kernel", 0);
+    bool walk = d->P > 0 && NS >= 1 && NS <= kMaxNS && force != 2;
+    // tiny blocks leave the 32..256-row tiles mostly idle: use the per-row kernel
+    if (walk && force != 1 && d->m < 16 * d->Nr) walk = false;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_data) % sizeof(T) == 0) && (reinterpret_cast<uintptr_t>(d_X) % sizeof(T) == 0);
+    if (!aligned) return bbm_fail(h, BBM_ERR_ARG, "device pointers must be aligned to the element size");
+
+    int tile = 0, stages = 0, dbytes = 0, xbytes = 0;
+    if (walk) {
+        const int want_stages = (int)std::min<i64>(8, std::max<i64>(2, bbm_opt(h, "bbb.stages", 4)));
+        const i64 forced_tile = bbm_opt(h, "bbb.tile", 0);
+        if (forced_tile && (forced_tile < 32 || forced_tile > 256 || forced_tile % 32))
+            return bbm_fail(h, BBM_ERR_ARG, "bbb.tile must be a multiple of 32 in [32,256]");
+        const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
+        const size_t soft = 100 * 1024;  // leaves room for two CTAs per SM
+        const int cands[4] = {forced_tile ? (int)forced_tile : 256, 128, 64, 32};
+        const int ncand = forced_tile ? 1 : 4;
+        const size_t tabs = walk_tab_bytes(512, (int)NS);
+        // pass 0: >= 3 stages within the two-CTA budget; pass 1: >= 2 stages within the opt-in limit
+        for (int pass = 0; pass < 2 && !tile; ++pass) {
+            const size_t limit = pass == 0 ? soft : budget;
+            const int min_stages = pass == 0 ? 3 : 2;
+            for (int ci = 0; ci < ncand && !tile; ++ci) {
+                const int t = cands[ci];
+                if (!forced_tile && t > 32 && t / 2 >= d->maxr) continue;  // tile twice the largest block: mostly idle
+                walk_stage_bytes<T>(t, w, d->P, &dbytes, &xbytes);
+                const size_t per = (size_t)dbytes + xbytes;
+                if (limit <= tabs) continue;
+                const int s = (int)std::min<size_t>(want_stages, (limit - tabs) / per);
+                if (s >= min_stages) { tile = t; stages = s; }
+            }
+        }
+        if (!tile) walk = false;  // P too large for shared memory staging
+    }
+
+    if (walk) {
+        const int target_items = h->num_sms * (int)std::max<i64>(1, bbm_opt(h, "bbb.items_per_sm", 6));
+        const int maxseg_cap = (int)std::min<i64>(512, std::max<i64>(1, bbm_opt(h, "bbb.maxseg", 512)));
+        auto key = std::make_pair(tile, target_items * 1024 + maxseg_cap);
+        auto it = d->parts.find(key);
+        if (it == d->parts.end()) {
+            Partition part;
+            int32_t rc = build_partition(d, tile, target_items, maxseg_cap, &part);
+            if (rc != BBM_OK) return rc;
+            it = d->parts.emplace(key, part).first;
+        }
+        const Partition& part = it->second;
+        if (part.nitems > 0) {
+            walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
+            p.items = part.d_items;
+            p.stages = stages;
+            p.maxseg = part.maxseg;
+            p.stage_data_bytes = dbytes;
+            p.stage_x_bytes = xbytes;
+            const size_t smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + xbytes);
+            dim3 grid((unsigned)part.nitems, (unsigned)nrhs, 1);
+            cudaError_t e = launch_walk<T>(p, (int)NS, w, grid, tile, smem, h->stream);
+            if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_walk_kernel launch: %s", cudaGetErrorString(e));
+            h->launches += 1;
+            return BBM_OK;
+        }
+    }
+    {
+        const int threads = 256;
+        const i64 blocks = std::min<i64>((d->m + threads - 1) / threads, (i64)h->num_sms * 32);
+        dim3 grid((unsigned)std::max<i64>(1, blocks), (unsigned)nrhs, 1);
+        bbb_generic_kernel<T><<<grid, threads, 0, h->stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_generic_kernel launch: %s", cudaGetErrorString(e));
+        h->launches += 1;
+    }
+    return BBM_OK;
+}
+
+template <typename T>
+int32_t bbb_mul_host_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data, const T* h_X, i64 ldx, i64 nrhs,
+                          T beta, T* h_Y, i64 ldy) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!desc_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BandedBlockBandedMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && (ldx < std::max<i64>(1, d->n) || ldy < std::max<i64>(1, d->m)))
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: A is %lld x %lld, ldx=%lld, ldy=%lld", (long long)d->m,
+                        (long long)d->n, (long long)ldx, (long long)ldy);
+    if (d->m == 0 || nrhs == 0) return BBM_OK;
+    if (!h_Y || (d->n > 0 && !h_X)) return bbm_fail(h, BBM_ERR_ARG, "null host pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const i64 n1 = std::max<i64>(1, d->n), m1 = std::max<i64>(1, d->m);
+    int32_t rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, (size_t)(n1 * nrhs) * sizeof(T) + 64);
+    if (rc != BBM_OK) return rc;
+    rc = bbm_ws_reserve(h, &h->ws_y, &h->ws_y_bytes, (size_t)(m1 * nrhs) * sizeof(T) + 64);
+    if (rc != BBM_OK) return rc;
+    T* dX = static_cast<T*>(h->ws_x);
+    T* dY = static_cast<T*>(h->ws_y);
+    if (d->n > 0)
+        BBM_CUDA(h, cudaMemcpy2DAsync(dX, n1 * sizeof(T), h_X, ldx * sizeof(T), d->n * sizeof(T), nrhs, cudaMemcpyHostToDevice, h->stream));
+    if (beta != T(0))
+        BBM_CUDA(h, cudaMemcpy2DAsync(dY, m1 * sizeof(T), h_Y, ldy * sizeof(T), d->m * sizeof(T), nrhs, cudaMemcpyHostToDevice, h->stream));
+    rc = bbb_mul_impl<T>(h, d, alpha, d_data, dX, n1, nrhs, beta, dY, m1);
+    if (rc != BBM_OK) return rc;
+    BBM_CUDA(h, cudaMemcpy2DAsync(h_Y, ldy * sizeof(T), dY, m1 * sizeof(T), d->m * sizeof(T), nrhs, cudaMemcpyDeviceToHost, h->stream));
+    BBM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bbm_bbb_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, int64_t l,
+                            int64_t u, int64_t lam, int64_t mu, bbm_bbb_desc_t* out) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!out) return bbm_fail(h, BBM_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (Nr < 0 || Nc < 0 || (Nr > 0 && !r) || (Nc > 0 && !c)) return bbm_fail(h, BBM_ERR_ARG, "bad block axes");
+    if (Nr > INT32_MAX - 1024 || Nc > INT32_MAX - 1024) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "too many blocks");
+    const i64 big = i64(1) << 30;
+    if (l < -big || l > big || u < -big || u > big || lam < -big || lam > big || mu < -big || mu > big)
+        return bbm_fail(h, BBM_ERR_ARG, "bandwidth out of range");
+    bbm_bbb_desc* d = new (std::nothrow) bbm_bbb_desc();
+    if (!d) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
+    d->h = h; d->Nr = Nr; d->Nc = Nc; d->l = l; d->u = u; d->lam = lam; d->mu = mu;
+    d->r.assign(r, r + Nr); d->c.assign(c, c + Nc);
+    d->R.assign(Nr + 1, 0); d->C.assign(Nc + 1, 0);
+    for (i64 K = 0; K < Nr; ++K) {
+        if (r[K] < 0 || r[K] > INT32_MAX / 2) { delete d; return bbm_fail(h, BBM_ERR_ARG, "bad row block size"); }
+        d->R[K + 1] = d->R[K] + r[K];
+        d->maxr = std::max(d->maxr, r[K]);
+    }
+    for (i64 J = 0; J < Nc; ++J) {
+        if (c[J] < 0 || c[J] > INT32_MAX / 2) { delete d; return bbm_fail(h, BBM_ERR_ARG, "bad column block size"); }
+        d->C[J + 1] = d->C[J] + c[J];
+    }
+    d->m = d->R[Nr]; d->n = d->C[Nc];
+    // rows of `data`: max(0,l+u+1)*max(0,lam+mu+1)  (src/BandedBlockBandedMatrix.jl:50)
+    const i64 nb = std::max<i64>(0, l + u + 1), w = std::max<i64>(0, lam + mu + 1);
+    if (nb > 0 && w > 0 && nb > (i64(1) << 30) / w) { delete d; return bbm_fail(h, BBM_ERR_UNSUPPORTED, "band storage too tall"); }
+    d->P = nb * w;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaMalloc(&d->dR, sizeof(i64) * (size_t)(Nr + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d->dC, sizeof(i64) * (size_t)(Nc + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(d->dR, d->R.data(), sizeof(i64) * (size_t)(Nr + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d->dC, d->C.data(), sizeof(i64) * (size_t)(Nc + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (d->dR) cudaFree(d->dR);
+        if (d->dC) cudaFree(d->dC);
+        delete d;
+        return bbm_fail(h, BBM_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e));
+    }
+    *out = d;
+    return BBM_OK;
+}
+
+int32_t bbm_bbb_desc_destroy(bbm_bbb_desc_t d) {
+    if (!d || d->magic != 0xBBBDE5C0u) return BBM_ERR_HANDLE;
+    if (bbm_valid(d->h)) cudaSetDevice(d->h->device);
+    for (auto& kv : d->parts)
+        if (kv.second.d_items) cudaFree(kv.second.d_items);
+    if (d->dR) cudaFree(d->dR);
+    if (d->dC) cudaFree(d->dC);
+    d->magic = 0;
+    delete d;
+    return BBM_OK;
+}
+
+int32_t bbm_bbb_desc_info(bbm_bbb_desc_t d, int64_t* m, int64_t* n, int64_t* P, int64_t* work_items) {
+    if (!desc_valid(d)) return BBM_ERR_HANDLE;
+    if (m) *m = d->m;
+    if (n) *n = d->n;
+    if (P) *P = d->P;
+    if (work_items) {
+        *work_items = 0;
+        for (auto& kv : d->parts) *work_items = std::max<i64>(*work_items, kv.second.nitems);
+    }
+    return BBM_OK;
+}
+
+int32_t bbm_bbb_mul_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data, const double* d_X,
+                        int64_t ldx, int64_t nrhs, double beta, double* d_Y, int64_t ldy) {
+    return bbb_mul_impl<double>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_bbb_mul_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data, const float* d_X,
+                        int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
+    return bbb_mul_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_bbb_mul_host_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data, const double* h_X,
+                             int64_t ldx, int64_t nrhs, double beta, double* h_Y, int64_t ldy) {
+    return bbb_mul_host_impl<double>(h, d, alpha, d_data, h_X, ldx, nrhs, beta, h_Y, ldy);
+}
+int32_t bbm_bbb_mul_host_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data, const float* h_X,
+                             int64_t ldx, int64_t nrhs, float beta, float* h_Y, int64_t ldy) {
+    return bbb_mul_host_impl<float>(h, d, alpha, d_data, h_X, ldx, nrhs, beta, h_Y, ldy);
+}
+
+}  // extern "C"

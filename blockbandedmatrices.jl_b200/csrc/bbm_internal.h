@@ -1,0 +1,61 @@
+// Internal declarations shared by the translation units of libbbm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bbm_b200.h"
+
+using i64 = int64_t;
+
+struct bbm_context {
+    uint32_t magic = 0xBB200C0Du;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    std::string err;
+    std::map<std::string, i64> opts;
+    i64 launches = 0;
+    // workspace for the *_host_* calls (device copies of X and Y)
+    void* ws_x = nullptr; size_t ws_x_bytes = 0;
+    void* ws_y = nullptr; size_t ws_y_bytes = 0;
+};
+
+inline bool bbm_valid(bbm_handle_t h) { return h != nullptr && h->magic == 0xBB200C0Du; }
+
+inline int32_t bbm_fail(bbm_handle_t h, int32_t code, const char* fmt, ...) {
+    if (bbm_valid(h)) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+
+#define BBM_CUDA(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return bbm_fail((h), BBM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define BBM_REQUIRE_HANDLE(h) \
+    do { if (!bbm_valid(h)) return BBM_ERR_HANDLE; } while (0)
+
+inline i64 bbm_opt(bbm_handle_t h, const char* key, i64 dflt) {
+    auto it = h->opts.find(key);
+    return it == h->opts.end() ? dflt : it->second;
+}
+
+// grow-only device workspace
+int32_t bbm_ws_reserve(bbm_handle_t h, void** ws, size_t* have, size_t need);

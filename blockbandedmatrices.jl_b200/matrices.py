@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's two containers.
+
+The reference keeps constructors, block axes and bandwidth queries in host Julia and only the
+``data`` buffer moves to the device (a package extension keyed on the buffer type).  These classes
+play that role for the Python harness: same field names, same storage shapes, same queries
+(0-based where Julia is 1-based).  ``data`` is either a numpy array (host matrix; only
+construction / indexing / densification work) or a :class:`DeviceArray` (device-resident; the
+products run through the C ABI).
+
+Reference: src/BandedBlockBandedMatrix.jl:25-50 (struct, data axes), :277-304 (bandwidth getters),
+:503-506 (block accessor); src/BlockSkylineMatrix.jl:47-53,158-173 (sizes + struct),
+:6-43,93-104 (starts/strides/numentries); src/AbstractBlockBandedMatrix.jl:90-104 (supports).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .device import DeviceArray, Handle
+
+
+def _sizes(v) -> np.ndarray:
+    a = np.asarray(v, dtype=np.int64).reshape(-1)
+    if (a < 0).any():
+        raise ValueError("block sizes must be non-negative")
+    return np.ascontiguousarray(a)
+
+
+def _cum(sz: np.ndarray) -> np.ndarray:
+    out = np.zeros(len(sz) + 1, dtype=np.int64)
+    np.cumsum(sz, out=out[1:])
+    return out
+
+
+class _BlockAxes:
+    """Block axes shared by both containers (``axes(A)`` / ``blocksize`` in the reference)."""
+
+    def _init_axes(self, rows, cols):
+        self.rows, self.cols = _sizes(rows), _sizes(cols)
+        self.R, self.C = _cum(self.rows), _cum(self.cols)
+
+    @property
+    def shape(self):
+        return (int(self.R[-1]), int(self.C[-1]))
+
+    @property
+    def blockshape(self):
+        """``blocksize(A)``: number of row / column blocks."""
+        return (len(self.rows), len(self.cols))
+
+    def _find(self, prefix, i):
+        if not (0 <= i < prefix[-1]):
+            raise IndexError(f"index {i} out of bounds")
+        return int(np.searchsorted(prefix, i, side="right") - 1)
+
+    @property
+    def on_device(self) -> bool:
+        return isinstance(self.data, DeviceArray)
+
+
+# ==================================================================================================
+class BandedBlockBandedMatrix(_BlockAxes):
+    """``_BandedBlockBandedMatrix(data, rows, cols, (l,u), (lam,mu))``.
+
+    ``data`` is the dense column-major ``P x n`` band-of-bands array, ``P = (l+u+1)(lam+mu+1)``
+    (0 rows when ``-l > u`` or ``-lam > mu``), exactly the parent array of the reference's
+    ``BlockedMatrix``; entry ``A[R[K]+k, C[J]+j]`` is ``data[(u+K-J)*w + (mu+k-j), C[J]+j]``.
+    """
+
+    def __init__(self, data, rows, cols, lu, lm):
+        self._init_axes(rows, cols)
+        self.l, self.u = int(lu[0]), int(lu[1])
+        self.lam, self.mu = int(lm[0]), int(lm[1])
+        exp = self.data_shape(self.cols, lu, lm)
+        if tuple(data.shape) != exp:  # check_data_sizes, src/BandedBlockBandedMatrix.jl:1-10
+            raise ValueError(f"Data matrix must be {exp[0]} x {exp[1]} (number of block bands x sub-block bands), got {tuple(data.shape)}")
+        if isinstance(data, np.ndarray) and data.size and not data.flags.f_contiguous:
+            data = np.asfortranarray(data)
+        self.data = data
+        self._desc = None
+
+    # ---- constructors ------------------------------------------------------------------------
+    @staticmethod
+    def data_shape(cols, lu, lm):
+        nb, w = max(0, lu[0] + lu[1] + 1), max(0, lm[0] + lm[1] + 1)
+        return (nb * w, int(np.sum(np.asarray(cols, dtype=np.int64))))
+
+    @classmethod
+    def undef(cls, dtype, rows, cols, lu, lm):
+        """``BandedBlockBandedMatrix{T}(undef, rows, cols, (l,u), (lam,mu))``."""
+        return cls(np.empty(cls.data_shape(cols, lu, lm), dtype=dtype, order="F"), rows, cols, lu, lm)
+
+    @classmethod
+    def zeros(cls, dtype, rows, cols, lu, lm):
+        return cls(np.zeros(cls.data_shape(cols, lu, lm), dtype=dtype, order="F"), rows, cols, lu, lm)
+
+    @classmethod
+    def from_dense(cls, A, rows, cols, lu, lm, fill=0.0):
+        """``BandedBlockBandedMatrix(A, rows, cols, (l,u), (lam,mu))``: keep the in-band entries of A.
+        Unused storage slots get ``fill`` (the reference leaves them undefined)."""
+        A = np.asarray(A)
+        out = cls(np.full(cls.data_shape(cols, lu, lm), fill, dtype=A.dtype, order="F"), rows, cols, lu, lm)
+        if A.shape != out.shape:
+            raise L.DimensionMismatch(f"dense matrix {A.shape} vs block axes {out.shape}")
+        for rho, gi, gj in out._slot_map():
+            out.data[rho, gj] = A[gi, gj]
+        return out
+
+    # ---- queries -----------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return np.dtype(self.data.dtype)
+
+    @property
+    def blockbandwidths(self):
+        return (self.l, self.u)
+
+    @property
+    def subblockbandwidths(self):
+        return (self.lam, self.mu)
+
+    def blockcolsupport(self, J: int) -> range:
+        Nr = len(self.rows)
+        return range(max(J - self.u, 0), max(min(J + self.l, Nr - 1), -1) + 1)
+
+    def blockrowsupport(self, K: int) -> range:
+        Nc = len(self.cols)
+        return range(max(K - self.l, 0), max(min(K + self.u, Nc - 1), -1) + 1)
+
+    def _slot_map(self):
+        """Yield (data row, global rows, global cols) index arrays, one per row of ``data``, for
+        the slots that encode a matrix entry."""
+        w, nb = self.lam + self.mu + 1, self.l + self.u + 1
+        if w <= 0 or nb <= 0 or self.shape[1] == 0:
+            return
+        Nr = len(self.rows)
+        gcol = np.arange(self.shape[1], dtype=np.int64)
+        Jc = np.repeat(np.arange(len(self.cols), dtype=np.int64), self.cols)
+        jc = gcol - self.C[Jc]
+        for s in range(nb):
+            K = Jc + s - self.u
+            okK = (K >= 0) & (K < Nr)
+            Kc = np.clip(K, 0, max(Nr - 1, 0))
+            rK = self.rows[Kc] if Nr else np.zeros_like(Kc)
+            for i in range(w):
+                k = jc + i - self.mu
+                ok = okK & (k >= 0) & (k < rK)
+                yield s * w + i, (self.R[Kc] + k)[ok], gcol[ok]
+
+    def valid_mask(self) -> np.ndarray:
+        mask = np.zeros(self.data_shape(self.cols, (self.l, self.u), (self.lam, self.mu)), dtype=bool, order="F")
+        for rho, gi, gj in self._slot_map():
+            mask[rho, gj] = True
+        return mask
+
+    def _host_data(self) -> np.ndarray:
+        return self.data.to_host() if self.on_device else self.data
+
+    def to_dense(self) -> np.ndarray:
+        """``Matrix(A)``."""
+        data = self._host_data()
+        A = np.zeros(self.shape, dtype=self.dtype)
+        for rho, gi, gj in self._slot_map():
+            A[gi, gj] = data[rho, gj]
+        return A
+
+    def __getitem__(self, ij):
+        i, j = ij
+        K, J = self._find(self.R, i), self._find(self.C, j)
+        k, jj = i - int(self.R[K]), j - int(self.C[J])
+        if not (-self.l <= J - K <= self.u) or not (-self.lam <= jj - k <= self.mu):
+            return self.dtype.type(0)
+        w = self.lam + self.mu + 1
+        return self._host_data()[(self.u + K - J) * w + (self.mu + k - jj), j]
+
+    def block(self, K: int, J: int) -> np.ndarray:
+        """``A[Block(K), Block(J)]`` as a dense array (zeros outside the block band)."""
+        out = np.zeros((int(self.rows[K]), int(self.cols[J])), dtype=self.dtype)
+        if not (-self.l <= J - K <= self.u) or self.lam + self.mu + 1 <= 0:
+            return out
+        w = self.lam + self.mu + 1
+        band = self._host_data()[(self.u + K - J) * w:(self.u + K - J + 1) * w, self.C[J]:self.C[J + 1]]
+        for jj in range(out.shape[1]):
+            for k in range(max(0, jj - self.mu), min(out.shape[0] - 1, jj + self.lam) + 1):
+                out[k, jj] = band[self.mu + k - jj, jj]
+        return out
+
+    # ---- device residency ----------------------------------------------------------------------
+    def to_device(self, handle: Handle) -> "BandedBlockBandedMatrix":
+        """Device-resident copy: one memcpy of the parent array, shape unchanged."""
+        if self.on_device:
+            return self
+        d = handle.to_device(self.data) if self.data.size else handle.empty(self.data.shape, self.dtype)
+        out = BandedBlockBandedMatrix(d, self.rows, self.cols, (self.l, self.u), (self.lam, self.mu))
+        return out
+
+    def descriptor(self, handle: Handle):
+        if self._desc is None or self._desc[0] is not handle:
+            d = C.c_void_p()
+            L.check(handle._lib.bbm_bbb_desc_create(
+                handle.h, len(self.rows), len(self.cols), self.rows.ctypes.data_as(C.c_void_p),
+                self.cols.ctypes.data_as(C.c_void_p), self.l, self.u, self.lam, self.mu, C.byref(d)), handle.h,
+                "bbm_bbb_desc_create")
+            self._desc = (handle, d)
+        return self._desc[1]
+
+    def __del__(self):
+        try:
+            if self._desc is not None and self._desc[0].h:
+                self._desc[0]._lib.bbm_bbb_desc_destroy(self._desc[1])
+        except Exception:
+            pass
+
+    def __matmul__(self, x):
+        from .linalg import mul
+        return mul(self, x)

@@ -1,0 +1,114 @@
+/*
+ * bbm_b200.h -- C ABI of libbbm_b200.so: hand-written sm_100a CUDA kernels for the data-parallel
+ * hot path of BlockBandedMatrices.jl (mul!/muladd! for BandedBlockBandedMatrix and
+ * BlockBandedMatrix/BlockSkylineMatrix, block-banded triangular ldiv!).
+ *
+ * This is what a Julia package extension `ccall`s (INTEGRATION.md shows the binding): plain
+ * pointers and sizes, no CUDA.jl / torch types.  All matrices keep the reference's storage
+ * formats with shapes unchanged (citations are relative to the reference repository):
+ *
+ *   BandedBlockBandedMatrix  `data` = dense column-major P x n array, P = (l+u+1)(lam+mu+1),
+ *       A[R[K]+k, C[J]+j] = data[(u+K-J)(lam+mu+1) + (mu+k-j) + P*(C[J]+j)]
+ *       (src/BandedBlockBandedMatrix.jl:25-50, 503-506, 538-545; docs/src/index.md:53-84)
+ *   BlockSkylineMatrix       `data` = vector of column-block-contiguous dense panels
+ *       (src/BlockSkylineMatrix.jl:6-43, 93-104, 459-479; docs/src/index.md:28-50)
+ *
+ * Conventions
+ *   - every entry point returns an int32 status (bbm_status); 0 = success.  The message of the
+ *     last failure on a handle is bbm_last_error(h).  Nothing throws or aborts across the ABI.
+ *     Julia maps BBM_ERR_DIM -> DimensionMismatch (where [upstream] BlockArrays' block loop and
+ *     src/linalg.jl:42,61 throw), BBM_ERR_BAND -> BandError (src/BlockSkylineMatrix.jl:491).
+ *   - block sizes / indices are int64 and 0-based; block sizes may be 0, bandwidths negative.
+ *   - device pointers named d_* must be device memory of the handle's device; the caller owns
+ *     every buffer; descriptors own only their index tables.
+ *   - work is enqueued on the handle's stream and the call returns (asynchronous), except the
+ *     *_host_* convenience calls and bbm_synchronize.
+ *   - a handle is not thread-safe; distinct handles are independent.  Every call does its own
+ *     cudaSetDevice, so calls may come from any host thread / Julia task.
+ *   - there is NO CPU fallback: without a usable CUDA device bbm_create fails with BBM_ERR_CUDA.
+ */
+#ifndef BBM_B200_H
+#define BBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bbm_context* bbm_handle_t;
+typedef struct bbm_bbb_desc* bbm_bbb_desc_t;
+typedef struct bbm_sky_desc* bbm_sky_desc_t;
+
+typedef enum bbm_status {
+    BBM_OK = 0,
+    BBM_ERR_HANDLE = 1,      /* null / destroyed handle or descriptor                          */
+    BBM_ERR_DIM = 2,         /* DimensionMismatch: vector lengths, leading dims, block axes     */
+    BBM_ERR_BAND = 3,        /* BandError: result structure too narrow, missing diagonal block  */
+    BBM_ERR_ARG = 4,         /* invalid argument (null pointer, negative size, bad enum)        */
+    BBM_ERR_CUDA = 5,        /* CUDA runtime error (message has the CUDA error string)          */
+    BBM_ERR_NCCL = 6,        /* peer / collective setup error                                   */
+    BBM_ERR_ALLOC = 7,       /* host or device allocation failed                                */
+    BBM_ERR_UNSUPPORTED = 8  /* valid in the reference but not taken by the device path         */
+} bbm_status;
+
+/* ---- library / handle ------------------------------------------------------------------- */
+int32_t bbm_version(void);                       /* major*10000 + minor*100 + patch             */
+const char* bbm_status_string(int32_t status);
+int32_t bbm_create(int32_t device, bbm_handle_t* out);
+int32_t bbm_destroy(bbm_handle_t h);
+int32_t bbm_set_stream(bbm_handle_t h, void* cuda_stream /* cudaStream_t, NULL = default */);
+int32_t bbm_synchronize(bbm_handle_t h);
+const char* bbm_last_error(bbm_handle_t h);
+/* tuning / diagnostics knobs ("bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel":
+ * 0 auto, 1 band-walk, 2 generic); unknown keys -> BBM_ERR_ARG.                                */
+int32_t bbm_set_option(bbm_handle_t h, const char* key, int64_t value);
+int32_t bbm_get_option(bbm_handle_t h, const char* key, int64_t* value);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches)         */
+int32_t bbm_launch_count(bbm_handle_t h, int64_t* count);
+
+/* ---- memory utilities (so the Julia side needs no CUDA.jl) ------------------------------- */
+int32_t bbm_malloc(bbm_handle_t h, void** d_ptr, size_t bytes);
+int32_t bbm_free(bbm_handle_t h, void* d_ptr);
+int32_t bbm_host_alloc(bbm_handle_t h, void** h_ptr, size_t bytes);   /* pinned host memory    */
+int32_t bbm_host_free(bbm_handle_t h, void* h_ptr);
+int32_t bbm_memcpy_h2d(bbm_handle_t h, void* d_dst, const void* h_src, size_t bytes);
+int32_t bbm_memcpy_d2h(bbm_handle_t h, void* h_dst, const void* d_src, size_t bytes);
+int32_t bbm_memcpy_d2d(bbm_handle_t h, void* d_dst, const void* d_src, size_t bytes);
+int32_t bbm_memset(bbm_handle_t h, void* d_ptr, int32_t byte_value, size_t bytes);
+
+/* ---- BandedBlockBandedMatrix -------------------------------------------------------------
+ * Descriptor = the host-side fields of the reference struct (raxis, column axis, l, u, lam, mu;
+ * src/BandedBlockBandedMatrix.jl:25-40) plus cached device index tables and the work
+ * partition of the band-walk kernel.  r[Nr], c[Nc] are block sizes.                           */
+int32_t bbm_bbb_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c,
+                            int64_t l, int64_t u, int64_t lam, int64_t mu, bbm_bbb_desc_t* out);
+int32_t bbm_bbb_desc_destroy(bbm_bbb_desc_t d);
+/* m = sum r, n = sum c, P = rows of `data` (0 if -l>u or -lam>mu), work items of the partition */
+int32_t bbm_bbb_desc_info(bbm_bbb_desc_t d, int64_t* m, int64_t* n, int64_t* P, int64_t* work_items);
+
+/* Y <- alpha*A*X + beta*Y  (replaces [upstream BlockArrays] materialize!(::MatMulVecAdd/
+ * ::MatMulMatAdd{<:AbstractBlockLayout,...}) + one BLAS gbmv per block, reached through
+ * src/BandedBlockBandedMatrix.jl:263-269,405,514-545 and src/AbstractBlockBandedMatrix.jl:90-104;
+ * in-repo rendering examples/cuarrays.jl:105-127).
+ * d_data: P x n column-major, ld = P.  d_X: n x nrhs (ldx >= n), d_Y: m x nrhs (ldy >= m).
+ * beta == 0 overwrites Y without reading it (test/test_blockskyline.jl:34-39).  Unused slots
+ * of d_data are never read into the arithmetic (they may hold NaN).  Y must not alias X/data.  */
+int32_t bbm_bbb_mul_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data,
+                        const double* d_X, int64_t ldx, int64_t nrhs, double beta, double* d_Y, int64_t ldy);
+int32_t bbm_bbb_mul_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data,
+                        const float* d_X, int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
+
+/* Same product with HOST vectors (the reference-facing call when x, y live in Julia Arrays and
+ * the matrix is device-resident): copies X host->device, runs the kernel, copies Y back and
+ * synchronises.  h_X / h_Y should be pinned (bbm_host_alloc) for full PCIe speed.             */
+int32_t bbm_bbb_mul_host_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data,
+                             const double* h_X, int64_t ldx, int64_t nrhs, double beta, double* h_Y, int64_t ldy);
+int32_t bbm_bbb_mul_host_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data,
+                             const float* h_X, int64_t ldx, int64_t nrhs, float beta, float* h_Y, int64_t ldy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBM_B200_H */
