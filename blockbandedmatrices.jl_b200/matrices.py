@@ -108,6 +108,22 @@ class BandedBlockBandedMatrix(_BlockAxes):
             out.data[rho, gj] = A[gi, gj]
         return out
 
+    @classmethod
+    def finitedifference_2d(cls, n: int, dtype=np.float64, nblocks: int | None = None):
+        """``finitedifference_2d(n)`` of examples/finitedifference_2d.jl:9-15: the 5-point Laplacian
+        ``Kron(D2, I) + Kron(I, D2)`` with h = 1/n as a BandedBlockBandedMatrix, n blocks of size n
+        (``nblocks`` block rows/columns of size n when given), (l,u) = (lam,mu) = (1,1).
+
+        Band storage: every column holds n^2*[0,1,0, 1,-4,1, 0,1,0] (slab 0 = super-diagonal block
+        = identity, slab 1 = diagonal block = tridiag(1,-4,1), slab 2 = sub-diagonal block).  Slots
+        that fall outside a block are unused; like examples/cuarrays.jl:6-24 they keep the value."""
+        nb = n if nblocks is None else int(nblocks)
+        dtype = np.dtype(dtype)
+        col = (np.array([0, 1, 0, 1, -4, 1, 0, 1, 0], dtype=np.float64) * float(n) ** 2).astype(dtype)
+        data = np.empty((9, n * nb), dtype=dtype, order="F")
+        data[:, :] = col[:, None]
+        return cls(data, [n] * nb, [n] * nb, (1, 1), (1, 1))
+
     # ---- queries -----------------------------------------------------------------------------
     @property
     def dtype(self):
