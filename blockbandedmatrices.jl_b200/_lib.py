@@ -55,7 +55,26 @@ SIGNATURES = {
     "bbm_bbb_mul_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
     "bbm_bbb_mul_host_f64": (i32, [vp, vp, f64, vp, vp, i64, i64, f64, vp, i64]),
     "bbm_bbb_mul_host_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
+    "bbm_bbb_partition_rows": (i32, [i64, vp, i32, vp]),
+    "bbm_bbb_dist_layout": (i32, [i64, i64, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp]),
+    "bbm_comm_unique_id": (i32, [vp]),
+    "bbm_comm_create": (i32, [vp, vp, i32, i32, pp]),
+    "bbm_comm_destroy": (i32, [vp]),
+    "bbm_dist_bbb_plan_create": (i32, [vp, i64, i64, vp, vp, i64, i64, i64, i64, vp, pp]),
+    "bbm_dist_bbb_plan_destroy": (i32, [vp]),
+    "bbm_dist_bbb_plan_layout": (i32, [vp, vp]),
+    "bbm_dist_bbb_mul_f64": (i32, [vp, f64, vp, vp, i64, f64, vp]),
+    "bbm_dist_bbb_mul_f32": (i32, [vp, f32, vp, vp, i64, f32, vp]),
 }
+
+
+class DistLayout(C.Structure):
+    """``bbm_dist_layout`` of include/bbm_b200.h."""
+    _fields_ = [(k, C.c_int64) for k in ("K0", "K1", "J0", "J1", "Jlo", "Jhi", "Ka", "Kb", "m_own", "n_own", "n_local",
+                                         "col_offset", "own_offset", "row_offset", "nsend", "nrecv")]
+
+    def asdict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 _lib = None
 

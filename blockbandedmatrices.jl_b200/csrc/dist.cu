@@ -1,0 +1,379 @@
+// Row-block-partitioned BandedBlockBandedMatrix matvec over several B200s (one process per GPU).
+//
+// Reference precedent: the row-block data parallelism of examples/shared_array_backend.jl:92-122
+// (balanced contiguous block-row ranges, read-only shared x).  Here x is distributed too, so the
+// x block-columns inside the l+u block halo are exchanged: NCCL send/recv between the owners,
+// overlapped with the product of the interior block rows, which need no halo.
+//
+// A contiguous block-row range of a BandedBlockBandedMatrix is itself banded-block-banded with
+// shifted block bandwidths (l-s, u+s) over a column range of the same band storage
+// (src/BandedBlockBandedMatrix.jl:450-456 sub-view bandwidths, :416-420 sub-view data), so every
+// rank -- and the interior / boundary pieces inside a rank -- runs the single-GPU band-walk kernel
+// on a column slab of the parent `data`, unchanged.
+//
+// The layout planning (bbm_bbb_partition_rows / bbm_bbb_dist_layout) is pure host code: it needs
+// no GPU and is what the world_size-2 gloo tests exercise on CPU.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "bbm_internal.h"
+
+namespace {
+
+// ---- NCCL, bound at run time (libnccl.so.2 is only needed once a communicator is created) -------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclSuccess = 0 };
+enum { ncclChar = 0 };
+
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    std::string err;
+};
+
+Nccl& nccl() {
+    static Nccl n;
+    return n;
+}
+
+bool nccl_load() {
+    Nccl& n = nccl();
+    if (n.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    void* lib = nullptr;
+    for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { n.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define BIND(field, sym)                                             \
+    n.field = reinterpret_cast<decltype(n.field)>(dlsym(lib, sym)); \
+    if (!n.field) { n.err = std::string("missing NCCL symbol ") + sym; return false; }
+    BIND(GetUniqueId, "ncclGetUniqueId")
+    BIND(CommInitRank, "ncclCommInitRank")
+    BIND(CommDestroy, "ncclCommDestroy")
+    BIND(Send, "ncclSend")
+    BIND(Recv, "ncclRecv")
+    BIND(GroupStart, "ncclGroupStart")
+    BIND(GroupEnd, "ncclGroupEnd")
+    BIND(GetErrorString, "ncclGetErrorString")
+    BIND(GetVersion, "ncclGetVersion")
+#undef BIND
+    n.lib = lib;
+    return true;
+}
+
+inline i64 clampi(i64 v, i64 lo, i64 hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+struct RankRanges {
+    i64 K0, K1;      // owned block rows
+    i64 J0, J1;      // owned block columns (x ownership)
+    i64 Nlo, Nhi;    // block columns the owned rows touch ("needed"), empty if K0 == K1
+};
+
+RankRanges rank_ranges(i64 Nr, i64 Nc, i64 l, i64 u, int nranks, int p, const i64* Kb) {
+    RankRanges g;
+    g.K0 = Kb[p]; g.K1 = Kb[p + 1];
+    g.J0 = std::min(g.K0, Nc);
+    g.J1 = (p == nranks - 1) ? Nc : std::min(g.K1, Nc);
+    if (g.J1 < g.J0) g.J1 = g.J0;
+    if (g.K1 > g.K0 && l + u + 1 > 0) {
+        g.Nlo = clampi(g.K0 - l, 0, Nc);
+        g.Nhi = clampi(g.K1 - 1 + u + 1, 0, Nc);
+        if (g.Nhi < g.Nlo) g.Nhi = g.Nlo;
+    } else {
+        g.Nlo = g.Nhi = g.J0;
+    }
+    return g;
+}
+
+}  // namespace
+
+struct bbm_comm {
+    uint32_t magic = 0xC0221234u;
+    bbm_handle_t h = nullptr;
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;   // exchange stream
+    cudaEvent_t ev_ready = nullptr;  // x ready on the compute stream
+    cudaEvent_t ev_halo = nullptr;   // halo landed on the exchange stream
+};
+
+struct bbm_dist_bbb_plan {
+    uint32_t magic = 0xD157B200u;
+    bbm_comm* comm = nullptr;
+    bbm_handle_t h = nullptr;
+    bbm_dist_layout lay{};
+    i64 P = 0;
+    std::vector<i64> sends, recvs;  // triples (peer, local column offset, count)
+    // sub-problems: 0 interior, 1 left boundary, 2 right boundary; each (desc, data col offset, y row offset)
+    bbm_bbb_desc_t desc[3] = {nullptr, nullptr, nullptr};
+    i64 coloff[3] = {0, 0, 0}, rowoff[3] = {0, 0, 0};
+};
+
+namespace {
+inline bool comm_valid(bbm_comm* c) { return c && c->magic == 0xC0221234u && bbm_valid(c->h); }
+inline bool plan_valid(bbm_dist_bbb_plan* p) { return p && p->magic == 0xD157B200u && bbm_valid(p->h); }
+
+int32_t layout_impl(i64 Nr, i64 Nc, const i64* r, const i64* c, i64 l, i64 u, int nranks, int rank, const i64* Kb,
+                    bbm_dist_layout* out, std::vector<i64>* sends, std::vector<i64>* recvs) {
+    if (Nr < 0 || Nc < 0 || nranks < 1 || rank < 0 || rank >= nranks || !Kb || !out) return BBM_ERR_ARG;
+    if (Kb[0] != 0 || Kb[nranks] != Nr) return BBM_ERR_ARG;
+    for (int p = 0; p < nranks; ++p)
+        if (Kb[p + 1] < Kb[p]) return BBM_ERR_ARG;
+    std::vector<i64> R(Nr + 1, 0), C(Nc + 1, 0);
+    for (i64 K = 0; K < Nr; ++K) R[K + 1] = R[K] + r[K];
+    for (i64 J = 0; J < Nc; ++J) C[J + 1] = C[J] + c[J];
+    const RankRanges me = rank_ranges(Nr, Nc, l, u, nranks, rank, Kb);
+    bbm_dist_layout L{};
+    L.K0 = me.K0; L.K1 = me.K1; L.J0 = me.J0; L.J1 = me.J1;
+    L.Jlo = std::min(me.J0, me.Nlo);
+    L.Jhi = std::max(me.J1, me.Nhi);
+    if (me.Nlo == me.Nhi) { L.Jlo = me.J0; L.Jhi = me.J1; }
+    L.m_own = R[me.K1] - R[me.K0];
+    L.n_own = C[me.J1] - C[me.J0];
+    L.n_local = C[L.Jhi] - C[L.Jlo];
+    L.col_offset = C[L.Jlo];
+    L.own_offset = C[me.J0] - C[L.Jlo];
+    L.row_offset = R[me.K0];
+    // interior block rows: every touched block column is owned by this rank
+    i64 Ka = me.K0, Kbnd = me.K1;
+    if (me.K1 > me.K0 && l + u + 1 > 0) {
+        if (me.Nlo < me.J0) Ka = clampi(me.J0 + l, me.K0, me.K1);
+        if (me.Nhi > me.J1) Kbnd = clampi(me.J1 - u, Ka, me.K1);
+        // rows whose support leaves the owned range on the far side (only with very negative bandwidths)
+        if (me.Nlo >= me.J1 || me.Nhi <= me.J0) { Ka = me.K0; Kbnd = me.K0; }
+    }
+    L.Ka = Ka; L.Kb = Kbnd;
+    // exchange lists: what I need from q / what q needs from me, as local-column ranges
+    if (sends) sends->clear();
+    if (recvs) recvs->clear();
+    i64 ns = 0, nr_ = 0;
+    for (int q = 0; q < nranks; ++q) {
+        if (q == rank) continue;
+        const RankRanges o = rank_ranges(Nr, Nc, l, u, nranks, q, Kb);
+        const i64 rlo = std::max(me.Nlo, o.J0), rhi = std::min(me.Nhi, o.J1);  // I need, q owns
+        if (rhi > rlo && C[rhi] > C[rlo]) {
+            ++nr_;
+            if (recvs) { recvs->push_back(q); recvs->push_back(C[rlo] - C[L.Jlo]); recvs->push_back(C[rhi] - C[rlo]); }
+        }
+        const i64 slo = std::max(o.Nlo, me.J0), shi = std::min(o.Nhi, me.J1);  // q needs, I own
+        if (shi > slo && C[shi] > C[slo]) {
+            ++ns;
+            if (sends) { sends->push_back(q); sends->push_back(C[slo] - C[L.Jlo]); sends->push_back(C[shi] - C[slo]); }
+        }
+    }
+    L.nsend = ns; L.nrecv = nr_;
+    *out = L;
+    return BBM_OK;
+}
+
+template <typename T>
+int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* d_x_local, i64 nrhs, T beta, T* d_y_own) {
+    if (!plan_valid(pl)) return BBM_ERR_HANDLE;
+    bbm_handle_t h = pl->h;
+    bbm_comm* cm = pl->comm;
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs == 0) return BBM_OK;
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const bbm_dist_layout& L = pl->lay;
+    const i64 ldx = std::max<i64>(1, L.n_local), ldy = std::max<i64>(1, L.m_own);
+    const bool exchange = cm && cm->comm && cm->nranks > 1 && (!pl->sends.empty() || !pl->recvs.empty());
+    auto run = [&](int which) -> int32_t {
+        if (!pl->desc[which]) return BBM_OK;
+        const T* data = d_data_local + pl->P * pl->coloff[which];
+        const T* x = d_x_local + pl->coloff[which];
+        T* y = d_y_own + pl->rowoff[which];
+        if (sizeof(T) == 8)
+            return bbm_bbb_mul_f64(h, pl->desc[which], (double)alpha, (const double*)data, (const double*)x, ldx, nrhs,
+                                   (double)beta, (double*)y, ldy);
+        return bbm_bbb_mul_f32(h, pl->desc[which], (float)alpha, (const float*)data, (const float*)x, ldx, nrhs,
+                               (float)beta, (float*)y, ldy);
+    };
+    if (exchange) {
+        Nccl& n = nccl();
+        // the exchange may start once everything queued on the compute stream so far (the producer
+        // of x, and the previous call's readers of the halo) has finished
+        BBM_CUDA(h, cudaEventRecord(cm->ev_ready, h->stream));
+        BBM_CUDA(h, cudaStreamWaitEvent(cm->stream, cm->ev_ready, 0));
+        ncclResult_t rc = n.GroupStart();
+        for (i64 q = 0; q < nrhs && rc == ncclSuccess; ++q) {
+            T* xq = d_x_local + q * ldx;
+            for (size_t i = 0; i + 2 < pl->recvs.size() && rc == ncclSuccess; i += 3)
+                rc = n.Recv(xq + pl->recvs[i + 1], (size_t)pl->recvs[i + 2] * sizeof(T), ncclChar, (int)pl->recvs[i], cm->comm, cm->stream);
+            for (size_t i = 0; i + 2 < pl->sends.size() && rc == ncclSuccess; i += 3)
+                rc = n.Send(xq + pl->sends[i + 1], (size_t)pl->sends[i + 2] * sizeof(T), ncclChar, (int)pl->sends[i], cm->comm, cm->stream);
+        }
+        ncclResult_t rc2 = n.GroupEnd();
+        if (rc == ncclSuccess) rc = rc2;
+        if (rc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "halo exchange: %s", n.GetErrorString(rc));
+        BBM_CUDA(h, cudaEventRecord(cm->ev_halo, cm->stream));
+    }
+    int32_t rc = run(0);  // interior rows: overlap the exchange
+    if (rc != BBM_OK) return rc;
+    if (exchange) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, cm->ev_halo, 0));
+    rc = run(1);
+    if (rc != BBM_OK) return rc;
+    return run(2);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bbm_bbb_partition_rows(int64_t Nr, const int64_t* r, int32_t nranks, int64_t* Kbounds) {
+    if (Nr < 0 || nranks < 1 || !Kbounds || (Nr > 0 && !r)) return BBM_ERR_ARG;
+    // contiguous block-row ranges balanced by rows (stored entries per block row are proportional
+    // to its height); cf. the balanced-remainder split of examples/shared_array_backend.jl:106-107
+    std::vector<i64> R(Nr + 1, 0);
+    for (i64 K = 0; K < Nr; ++K) { if (r[K] < 0) return BBM_ERR_ARG; R[K + 1] = R[K] + r[K]; }
+    const i64 m = R[Nr];
+    Kbounds[0] = 0;
+    for (int p = 1; p < nranks; ++p) {
+        i64 K;
+        if (m == 0) {
+            K = (Nr * p) / nranks;
+        } else {
+            const double target = (double)m * p / nranks;
+            K = std::lower_bound(R.begin(), R.end(), (i64)(target + 0.5)) - R.begin();
+            if (K > 0 && (double)R[K] - target > target - (double)R[K - 1]) --K;  // nearer boundary
+        }
+        Kbounds[p] = clampi(K, Kbounds[p - 1], Nr);
+    }
+    Kbounds[nranks] = Nr;
+    return BBM_OK;
+}
+
+int32_t bbm_bbb_dist_layout(int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, int64_t l, int64_t u,
+                            int32_t nranks, int32_t rank, const int64_t* Kbounds, bbm_dist_layout* out,
+                            int64_t* sendlist, int64_t* recvlist) {
+    std::vector<i64> s, v;
+    int32_t rc = layout_impl(Nr, Nc, r, c, l, u, nranks, rank, Kbounds, out, &s, &v);
+    if (rc != BBM_OK) return rc;
+    if (sendlist) std::copy(s.begin(), s.end(), sendlist);
+    if (recvlist) std::copy(v.begin(), v.end(), recvlist);
+    return BBM_OK;
+}
+
+int32_t bbm_comm_unique_id(uint8_t* id128) {
+    if (!id128) return BBM_ERR_ARG;
+    if (!nccl_load()) return BBM_ERR_NCCL;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return BBM_ERR_NCCL;
+    memcpy(id128, id.internal, 128);
+    return BBM_OK;
+}
+
+int32_t bbm_comm_create(bbm_handle_t h, const uint8_t* id128, int32_t nranks, int32_t rank, bbm_comm_t* out) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return bbm_fail(h, BBM_ERR_ARG, "bad communicator arguments");
+    *out = nullptr;
+    bbm_comm* c = new (std::nothrow) bbm_comm();
+    if (!c) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
+    c->h = h; c->nranks = nranks; c->rank = rank;
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    // id128 == NULL with nranks > 1: a communicator without NCCL -- the caller moves the halo itself
+    // (its own MPI / Distributed exchange) and bbm_dist_bbb_mul_* only multiplies.
+    if (nranks > 1 && id128) {
+        if (!nccl_load()) { delete c; return bbm_fail(h, BBM_ERR_NCCL, "%s", nccl().err.c_str()); }
+        ncclUniqueId id;
+        memcpy(id.internal, id128, 128);
+        ncclResult_t rc = nccl().CommInitRank(&c->comm, nranks, id, rank);
+        if (rc != ncclSuccess) { delete c; return bbm_fail(h, BBM_ERR_NCCL, "ncclCommInitRank: %s", nccl().GetErrorString(rc)); }
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
+    if (e != cudaSuccess) { bbm_comm_destroy(c); return bbm_fail(h, BBM_ERR_CUDA, "communicator streams: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return BBM_OK;
+}
+
+int32_t bbm_comm_destroy(bbm_comm_t c) {
+    if (!c || c->magic != 0xC0221234u) return BBM_ERR_HANDLE;
+    if (bbm_valid(c->h)) cudaSetDevice(c->h->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->magic = 0;
+    delete c;
+    return BBM_OK;
+}
+
+int32_t bbm_dist_bbb_plan_create(bbm_comm_t cm, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, int64_t l,
+                                 int64_t u, int64_t lam, int64_t mu, const int64_t* Kbounds, bbm_dist_bbb_plan_t* out) {
+    if (!comm_valid(cm)) return BBM_ERR_HANDLE;
+    bbm_handle_t h = cm->h;
+    if (!out) return bbm_fail(h, BBM_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    std::vector<i64> kb(cm->nranks + 1);
+    if (Kbounds) std::copy(Kbounds, Kbounds + cm->nranks + 1, kb.begin());
+    else {
+        int32_t rc = bbm_bbb_partition_rows(Nr, r, cm->nranks, kb.data());
+        if (rc != BBM_OK) return bbm_fail(h, rc, "bad block sizes");
+    }
+    bbm_dist_bbb_plan* pl = new (std::nothrow) bbm_dist_bbb_plan();
+    if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
+    pl->comm = cm; pl->h = h;
+    int32_t rc = layout_impl(Nr, Nc, r, c, l, u, cm->nranks, cm->rank, kb.data(), &pl->lay, &pl->sends, &pl->recvs);
+    if (rc != BBM_OK) { delete pl; return bbm_fail(h, rc, "bad partition"); }
+    const i64 nb = std::max<i64>(0, l + u + 1), w = std::max<i64>(0, lam + mu + 1);
+    pl->P = nb * w;
+    const bbm_dist_layout& L = pl->lay;
+    std::vector<i64> C(Nc + 1, 0), R(Nr + 1, 0);
+    for (i64 J = 0; J < Nc; ++J) C[J + 1] = C[J] + c[J];
+    for (i64 K = 0; K < Nr; ++K) R[K + 1] = R[K] + r[K];
+    // pieces: interior [Ka,Kb), left boundary [K0,Ka), right boundary [Kb,K1)
+    const i64 lo[3] = {L.Ka, L.K0, L.Kb}, hi[3] = {L.Kb, L.Ka, L.K1};
+    for (int i = 0; i < 3; ++i) {
+        if (hi[i] <= lo[i]) continue;
+        // block columns of the piece, kept inside the local column range
+        i64 Jl = clampi(lo[i] - l, L.Jlo, L.Jhi), Jh = clampi(hi[i] + u, Jl, L.Jhi);
+        if (pl->P == 0) { Jl = L.Jlo; Jh = L.Jlo; }
+        const i64 s = lo[i] - Jl;  // sub-view shift: (l,u) -> (l-s, u+s)
+        rc = bbm_bbb_desc_create(h, hi[i] - lo[i], Jh - Jl, r + lo[i], c + Jl, l - s, u + s, lam, mu, &pl->desc[i]);
+        if (rc != BBM_OK) { bbm_dist_bbb_plan_destroy(pl); return rc; }
+        pl->coloff[i] = C[Jl] - C[L.Jlo];
+        pl->rowoff[i] = R[lo[i]] - R[L.K0];
+    }
+    *out = pl;
+    return BBM_OK;
+}
+
+int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
+    if (!pl || pl->magic != 0xD157B200u) return BBM_ERR_HANDLE;
+    for (int i = 0; i < 3; ++i)
+        if (pl->desc[i]) bbm_bbb_desc_destroy(pl->desc[i]);
+    pl->magic = 0;
+    delete pl;
+    return BBM_OK;
+}
+
+int32_t bbm_dist_bbb_plan_layout(bbm_dist_bbb_plan_t pl, bbm_dist_layout* out) {
+    if (!plan_valid(pl) || !out) return BBM_ERR_HANDLE;
+    *out = pl->lay;
+    return BBM_OK;
+}
+
+int32_t bbm_dist_bbb_mul_f64(bbm_dist_bbb_plan_t pl, double alpha, const double* d_data_local, double* d_x_local,
+                             int64_t nrhs, double beta, double* d_y_own) {
+    return dist_mul_impl<double>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+}
+int32_t bbm_dist_bbb_mul_f32(bbm_dist_bbb_plan_t pl, float alpha, const float* d_data_local, float* d_x_local,
+                             int64_t nrhs, float beta, float* d_y_own) {
+    return dist_mul_impl<float>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+}
+
+}  // extern "C"

@@ -108,6 +108,65 @@ int32_t bbm_bbb_mul_host_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, con
 int32_t bbm_bbb_mul_host_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data,
                              const float* h_X, int64_t ldx, int64_t nrhs, float beta, float* h_Y, int64_t ldy);
 
+/* ---- several GPUs: row-block partition + halo exchange ------------------------------------
+ * One process per GPU.  Block rows are split into contiguous ranges (the reference's one
+ * data-parallel strategy, examples/shared_array_backend.jl:92-122, partition :106-107); rank p owns
+ * y[K0:K1) and x[J0:J1) and holds the column slab [Jlo,Jhi) of `data` that its rows touch -- a
+ * block-row range of a BandedBlockBandedMatrix is banded-block-banded with bandwidths
+ * (l-s, u+s) over a column range of the same storage (src/BandedBlockBandedMatrix.jl:416-420,
+ * 450-456).  Only the x block-columns inside the l+u block halo move between GPUs.           */
+typedef struct bbm_comm* bbm_comm_t;
+typedef struct bbm_dist_bbb_plan* bbm_dist_bbb_plan_t;
+
+typedef struct bbm_dist_layout {
+    int64_t K0, K1;        /* owned block rows [K0,K1)                                           */
+    int64_t J0, J1;        /* owned block columns (the part of x this rank owns)                 */
+    int64_t Jlo, Jhi;      /* local block columns: hull of owned and touched columns             */
+    int64_t Ka, Kb;        /* interior block rows [Ka,Kb): touch owned columns only              */
+    int64_t m_own, n_own;  /* rows of y / entries of x owned                                      */
+    int64_t n_local;       /* length of x_local = columns of the local data slab                 */
+    int64_t col_offset;    /* first global column of the local slab (= C[Jlo])                   */
+    int64_t own_offset;    /* offset of the owned x inside x_local                               */
+    int64_t row_offset;    /* first global row owned (= R[K0])                                   */
+    int64_t nsend, nrecv;  /* halo messages per exchange                                          */
+} bbm_dist_layout;
+
+/* Host-only planning (no GPU, no handle): balanced contiguous block-row ranges, Kbounds[nranks+1]. */
+int32_t bbm_bbb_partition_rows(int64_t Nr, const int64_t* r, int32_t nranks, int64_t* Kbounds);
+/* Host-only: layout of `rank`; sendlist / recvlist (may be NULL) receive nsend / nrecv triples
+ * (peer, offset into x_local, element count); each needs room for 3*(nranks-1) entries.          */
+int32_t bbm_bbb_dist_layout(int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, int64_t l, int64_t u,
+                            int32_t nranks, int32_t rank, const int64_t* Kbounds, bbm_dist_layout* out,
+                            int64_t* sendlist, int64_t* recvlist);
+
+/* NCCL communicator over the ranks (libnccl.so.2 is bound at run time).  Rank 0 calls
+ * bbm_comm_unique_id and ships the 128 bytes to the others by any means (MPI.jl, Distributed,
+ * torch.distributed, a file), then every rank calls bbm_comm_create (collective).
+ * id128 == NULL with nranks > 1 makes a communicator without NCCL: the caller fills the halo
+ * parts of x_local itself (its own MPI exchange) and bbm_dist_bbb_mul_* only multiplies.        */
+int32_t bbm_comm_unique_id(uint8_t* id128);
+int32_t bbm_comm_create(bbm_handle_t h, const uint8_t* id128, int32_t nranks, int32_t rank, bbm_comm_t* out);
+int32_t bbm_comm_destroy(bbm_comm_t c);
+
+/* Plan for one global matrix structure; Kbounds == NULL takes bbm_bbb_partition_rows.           */
+int32_t bbm_dist_bbb_plan_create(bbm_comm_t c, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* cols,
+                                 int64_t l, int64_t u, int64_t lam, int64_t mu, const int64_t* Kbounds,
+                                 bbm_dist_bbb_plan_t* out);
+int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t p);
+int32_t bbm_dist_bbb_plan_layout(bbm_dist_bbb_plan_t p, bbm_dist_layout* out);
+
+/* y_own <- alpha * A[K0:K1, :] * x + beta * y_own.
+ * d_data_local: P x n_local column slab (global columns col_offset ... ) of `data`.
+ * d_x_local:    n_local x nrhs (ld = max(1,n_local)); the caller fills the owned part at
+ *               own_offset, the halo parts are overwritten by the exchange.
+ * d_y_own:      m_own x nrhs (ld = max(1,m_own)).
+ * The halo exchange (grouped ncclSend/ncclRecv on the communicator's stream) overlaps the
+ * product of the interior block rows; boundary rows follow.  Collective over the ranks.        */
+int32_t bbm_dist_bbb_mul_f64(bbm_dist_bbb_plan_t p, double alpha, const double* d_data_local, double* d_x_local,
+                             int64_t nrhs, double beta, double* d_y_own);
+int32_t bbm_dist_bbb_mul_f32(bbm_dist_bbb_plan_t p, float alpha, const float* d_data_local, float* d_x_local,
+                             int64_t nrhs, float beta, float* d_y_own);
+
 #ifdef __cplusplus
 }
 #endif

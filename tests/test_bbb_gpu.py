@@ -137,3 +137,34 @@ def test_bbb_linearity_large(handle):
     x1, x2 = rng.standard_normal(n * 64), rng.standard_normal(n * 64)
     y1, y2, y12 = Ad @ x1, Ad @ x2, Ad @ (2.0 * x1 - 3.0 * x2)
     assert relerr(y12, 2.0 * y1 - 3.0 * y2) <= tol(np.float64, 9) * 4
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_dist_plan_virtual_ranks(handle, world):
+    """The multi-GPU plan on ONE device: every virtual rank multiplies its interior / boundary
+    sub-views (communicator without NCCL, halos filled by hand); assembled result == oracle."""
+    from bbm_b200 import distributed as D
+    for ci, (rows, cols, l, u, lam, mu) in enumerate([([64] * 24, [64] * 24, 1, 1, 1, 1),
+                                                     (list(range(1, 40)), list(range(1, 40)), 2, 2, 2, 2),
+                                                     ([5, 3, 7, 2, 6, 4, 5], [4, 6, 2, 5, 3, 7, 2, 4], 1, 2, 2, 1),
+                                                     ([300] * 9, [300] * 9, 2, 1, 3, 2)]):
+        rng = np.random.default_rng(40 + ci)
+        data = random_bbb(rng, rows, cols, l, u, lam, mu)
+        x = rng.standard_normal(sum(cols))
+        y0 = rng.standard_normal(sum(rows))
+        ref = y0.copy()
+        O.bbb_mul(rows, cols, l, u, lam, mu, 1.5, data, x, 0.5, ref)
+        y = np.full(sum(rows), np.nan)
+        for rank in range(world):
+            comm = D.Communicator(handle, None, world, rank)
+            A = D.DistBandedBlockBandedMatrix(comm, rows, cols, (l, u), (lam, mu))
+            lay = A.layout
+            A.set_local_data(A.local_data(data))
+            c0 = lay["col_offset"]
+            dx = handle.to_device(np.ascontiguousarray(x[c0:c0 + lay["n_local"]]))
+            dy = handle.to_device(np.ascontiguousarray(y0[lay["row_offset"]:lay["row_offset"] + lay["m_own"]]))
+            A.mul_(dy, dx, 1.5, 0.5)
+            y[lay["row_offset"]:lay["row_offset"] + lay["m_own"]] = dy.to_host()
+            A.close()
+            comm.close()
+        assert relerr(y, ref) <= tol(np.float64, F.bbb_nnz_per_row_max(l, u, lam, mu) + 1)
