@@ -209,6 +209,9 @@ def run_ours(args):
     n = BLOCK * nb
     stream = torch.cuda.Stream(device=local_rank)
     h = B.Handle(local_rank, stream=stream.cuda_stream)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        h.set_option(k, int(v))
 
     if world == 1:
         result = bench_single(args, torch, B, h, stream, nb, n, rank)
@@ -434,6 +437,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=BLOCK, help="number of blocks (default 4096 = cfg2; smaller only for debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments), e.g. dist.graph=0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

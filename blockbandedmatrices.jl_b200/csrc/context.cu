@@ -5,7 +5,7 @@
 
 static const char* const kOptionKeys[] = {
     "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint",
-    "sky.kernel", "sky.mm_kernel", "trsm.kernel", nullptr};
+    "sky.kernel", "sky.mm_kernel", "trsm.kernel", "dist.graph", nullptr};
 
 extern "C" {
 

@@ -109,8 +109,21 @@ struct bbm_comm {
     cudaEvent_t ev_halo = nullptr;   // halo landed on the exchange stream
 };
 
+struct GraphKey {
+    const void* data = nullptr; void* x = nullptr; void* y = nullptr;
+    double alpha = 0, beta = 0; i64 nrhs = 0; int ts = 0; cudaStream_t stream = nullptr;
+    bool operator==(const GraphKey& o) const {
+        return data == o.data && x == o.x && y == o.y && alpha == o.alpha && beta == o.beta && nrhs == o.nrhs &&
+               ts == o.ts && stream == o.stream;
+    }
+};
+
 struct bbm_dist_bbb_plan {
     uint32_t magic = 0xD157B200u;
+    cudaGraphExec_t gexec = nullptr;  // cached CUDA graph of one whole step
+    GraphKey gkey;
+    i64 glaunches = 0;
+    bool gfailed = false;
     bbm_comm* comm = nullptr;
     bbm_handle_t h = nullptr;
     bbm_dist_layout lay{};
@@ -178,14 +191,15 @@ int32_t layout_impl(i64 Nr, i64 Nc, const i64* r, const i64* c, i64 l, i64 u, in
     return BBM_OK;
 }
 
+// Enqueue one distributed product.  Stream plan:
+//   compute stream : [x ready] ------------------ interior rows ------------------ [join]
+//   exchange stream:      wait -> NCCL send/recv -> boundary rows (high priority) --^
+// The boundary pieces write disjoint rows of y, so they run concurrently with the interior kernel
+// and are absorbed into its tail instead of adding two serial launches per step.
 template <typename T>
-int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* d_x_local, i64 nrhs, T beta, T* d_y_own) {
-    if (!plan_valid(pl)) return BBM_ERR_HANDLE;
+int32_t dist_enqueue(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* d_x_local, i64 nrhs, T beta, T* d_y_own) {
     bbm_handle_t h = pl->h;
     bbm_comm* cm = pl->comm;
-    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
-    if (nrhs == 0) return BBM_OK;
-    BBM_CUDA(h, cudaSetDevice(h->device));
     const bbm_dist_layout& L = pl->lay;
     const i64 ldx = std::max<i64>(1, L.n_local), ldy = std::max<i64>(1, L.m_own);
     const bool exchange = cm && cm->comm && cm->nranks > 1 && (!pl->sends.empty() || !pl->recvs.empty());
@@ -200,31 +214,96 @@ int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* 
         return bbm_bbb_mul_f32(h, pl->desc[which], (float)alpha, (const float*)data, (const float*)x, ldx, nrhs,
                                (float)beta, (float*)y, ldy);
     };
-    if (exchange) {
-        Nccl& n = nccl();
-        // the exchange may start once everything queued on the compute stream so far (the producer
-        // of x, and the previous call's readers of the halo) has finished
-        BBM_CUDA(h, cudaEventRecord(cm->ev_ready, h->stream));
-        BBM_CUDA(h, cudaStreamWaitEvent(cm->stream, cm->ev_ready, 0));
-        ncclResult_t rc = n.GroupStart();
-        for (i64 q = 0; q < nrhs && rc == ncclSuccess; ++q) {
-            T* xq = d_x_local + q * ldx;
-            for (size_t i = 0; i + 2 < pl->recvs.size() && rc == ncclSuccess; i += 3)
-                rc = n.Recv(xq + pl->recvs[i + 1], (size_t)pl->recvs[i + 2] * sizeof(T), ncclChar, (int)pl->recvs[i], cm->comm, cm->stream);
-            for (size_t i = 0; i + 2 < pl->sends.size() && rc == ncclSuccess; i += 3)
-                rc = n.Send(xq + pl->sends[i + 1], (size_t)pl->sends[i + 2] * sizeof(T), ncclChar, (int)pl->sends[i], cm->comm, cm->stream);
-        }
-        ncclResult_t rc2 = n.GroupEnd();
-        if (rc == ncclSuccess) rc = rc2;
-        if (rc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "halo exchange: %s", n.GetErrorString(rc));
-        BBM_CUDA(h, cudaEventRecord(cm->ev_halo, cm->stream));
+    if (!exchange) {
+        int32_t rc = run(0);
+        if (rc == BBM_OK) rc = run(1);
+        if (rc == BBM_OK) rc = run(2);
+        return rc;
     }
-    int32_t rc = run(0);  // interior rows: overlap the exchange
+    Nccl& n = nccl();
+    // the exchange may start once everything queued on the compute stream so far (the producer of
+    // x, and the previous call's readers of the halo) has finished
+    BBM_CUDA(h, cudaEventRecord(cm->ev_ready, h->stream));
+    BBM_CUDA(h, cudaStreamWaitEvent(cm->stream, cm->ev_ready, 0));
+    ncclResult_t nrc = n.GroupStart();
+    for (i64 q = 0; q < nrhs && nrc == ncclSuccess; ++q) {
+        T* xq = d_x_local + q * ldx;
+        for (size_t i = 0; i + 2 < pl->recvs.size() && nrc == ncclSuccess; i += 3)
+            nrc = n.Recv(xq + pl->recvs[i + 1], (size_t)pl->recvs[i + 2] * sizeof(T), ncclChar, (int)pl->recvs[i], cm->comm, cm->stream);
+        for (size_t i = 0; i + 2 < pl->sends.size() && nrc == ncclSuccess; i += 3)
+            nrc = n.Send(xq + pl->sends[i + 1], (size_t)pl->sends[i + 2] * sizeof(T), ncclChar, (int)pl->sends[i], cm->comm, cm->stream);
+    }
+    ncclResult_t nrc2 = n.GroupEnd();
+    if (nrc == ncclSuccess) nrc = nrc2;
+    if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "halo exchange: %s", n.GetErrorString(nrc));
+    // boundary rows behind the exchange, on its (high-priority) stream
+    cudaStream_t compute = h->stream;
+    h->stream = cm->stream;
+    int32_t rc = run(1);
+    if (rc == BBM_OK) rc = run(2);
+    h->stream = compute;
     if (rc != BBM_OK) return rc;
-    if (exchange) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, cm->ev_halo, 0));
-    rc = run(1);
+    BBM_CUDA(h, cudaEventRecord(cm->ev_halo, cm->stream));
+    rc = run(0);  // interior rows: need no halo
     if (rc != BBM_OK) return rc;
-    return run(2);
+    BBM_CUDA(h, cudaStreamWaitEvent(h->stream, cm->ev_halo, 0));
+    return BBM_OK;
+}
+
+template <typename T>
+int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* d_x_local, i64 nrhs, T beta, T* d_y_own) {
+    if (!plan_valid(pl)) return BBM_ERR_HANDLE;
+    bbm_handle_t h = pl->h;
+    bbm_comm* cm = pl->comm;
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs == 0) return BBM_OK;
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const bool exchange = cm && cm->comm && cm->nranks > 1 && (!pl->sends.empty() || !pl->recvs.empty());
+    const bool want_graph = exchange && bbm_opt(h, "dist.graph", 1) != 0;
+    if (!want_graph) return dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+
+    // Repeated products with the same buffers (every iterative solver) replay one CUDA graph of the
+    // whole step -- exchange, boundary and interior kernels, cross-stream edges -- so the host
+    // issues one launch per step.  First call with a new argument set runs eagerly (it may allocate
+    // the work partition), the second captures, later ones replay.
+    GraphKey key{d_data_local, d_x_local, d_y_own, (double)alpha, (double)beta, nrhs, (int)sizeof(T), h->stream};
+    if (pl->gexec && key == pl->gkey) {
+        BBM_CUDA(h, cudaGraphLaunch(pl->gexec, h->stream));
+        h->launches += pl->glaunches;
+        return BBM_OK;
+    }
+    if (!(key == pl->gkey) || pl->gfailed) {
+        if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = nullptr; }
+        if (!(key == pl->gkey)) pl->gfailed = false;
+        pl->gkey = key;
+        return dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+    }
+    const i64 l0 = h->launches;
+    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGetLastError(); pl->gfailed = true; return dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own); }
+    int32_t rc = dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(h->stream, &graph);
+    const i64 captured = h->launches - l0;
+    h->launches = l0;
+    if (rc != BBM_OK || e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        pl->gfailed = true;
+        if (rc != BBM_OK) return rc;
+        return dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+    }
+    e = cudaGraphInstantiate(&pl->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pl->gexec = nullptr; pl->gfailed = true;
+        return dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
+    }
+    pl->glaunches = captured;
+    BBM_CUDA(h, cudaGraphLaunch(pl->gexec, h->stream));
+    h->launches += pl->glaunches;
+    return BBM_OK;
 }
 
 }  // namespace
@@ -291,7 +370,9 @@ int32_t bbm_comm_create(bbm_handle_t h, const uint8_t* id128, int32_t nranks, in
         ncclResult_t rc = nccl().CommInitRank(&c->comm, nranks, id, rank);
         if (rc != ncclSuccess) { delete c; return bbm_fail(h, BBM_ERR_NCCL, "ncclCommInitRank: %s", nccl().GetErrorString(rc)); }
     }
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
     if (e != cudaSuccess) { bbm_comm_destroy(c); return bbm_fail(h, BBM_ERR_CUDA, "communicator streams: %s", cudaGetErrorString(e)); }
@@ -356,6 +437,7 @@ int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
     if (!pl || pl->magic != 0xD157B200u) return BBM_ERR_HANDLE;
     for (int i = 0; i < 3; ++i)
         if (pl->desc[i]) bbm_bbb_desc_destroy(pl->desc[i]);
+    if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
     pl->magic = 0;
     delete pl;
     return BBM_OK;
