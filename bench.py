@@ -202,6 +202,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO banners go to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

@@ -55,6 +55,16 @@ SIGNATURES = {
     "bbm_bbb_mul_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
     "bbm_bbb_mul_host_f64": (i32, [vp, vp, f64, vp, vp, i64, i64, f64, vp, i64]),
     "bbm_bbb_mul_host_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
+    "bbm_sky_desc_create": (i32, [vp, i64, i64, vp, vp, vp, vp, pp]),
+    "bbm_sky_desc_destroy": (i32, [vp]),
+    "bbm_sky_desc_info": (i32, [vp, pi64, pi64, pi64, pi64]),
+    "bbm_sky_desc_layout": (i32, [vp, vp, vp, vp, vp]),
+    "bbm_sky_mul_f64": (i32, [vp, vp, f64, vp, vp, i64, i64, f64, vp, i64]),
+    "bbm_sky_mul_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
+    "bbm_sky_matmul_f64": (i32, [vp, vp, vp, vp, f64, vp, vp, f64, vp]),
+    "bbm_sky_matmul_f32": (i32, [vp, vp, vp, vp, f32, vp, vp, f32, vp]),
+    "bbm_sky_trsm_f64": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
+    "bbm_sky_trsm_f32": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_bbb_partition_rows": (i32, [i64, vp, i32, vp]),
     "bbm_bbb_dist_layout": (i32, [i64, i64, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp]),
     "bbm_comm_unique_id": (i32, [vp]),

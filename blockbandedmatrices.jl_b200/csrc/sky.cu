@@ -1,0 +1,886 @@
+// BlockSkylineMatrix / BlockBandedMatrix: descriptor, matvec (panel GEMV), block-banded x
+// block-banded product (FP64 tensor-core DMMA tiles) and block triangular solve.
+//
+// Storage (src/BlockSkylineMatrix.jl:6-43, 93-104, 459-479; docs/src/index.md:28-50): for block
+// column J the in-band block rows klo[J]..khi[J] form ONE dense column-major panel of
+// S_J = R[khi+1]-R[klo] rows x c[J] columns; panels are concatenated in J order.  Block (K,J)
+// starts at off[J] + R[K]-R[klo[J]] with leading dimension S_J.  Every stored slot is a matrix
+// entry (no unused slots, unlike the banded-block-banded storage).
+//
+// Reference behaviour being replaced: the [upstream] BlockArrays block loops
+// calling one BLAS gemv / gemm / trsv per block on the (ptr, ld) operands above.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <new>
+
+#include "bbm_internal.h"
+
+namespace {
+
+struct SkyEnt {      // one (block or panel piece) operand of a tall-skinny product
+    i64 start;       // offset of its first row/column in `data`
+    i64 ld;          // leading dimension
+    i64 xoff;        // first row of X it multiplies
+    i64 ncols;       // columns
+};
+
+struct SkyItem {     // one CTA of the panel-GEMV kernel: up to 128 consecutive output rows
+    i64 yrow0;       // first output row
+    i64 koff;        // row offset added to every entry's start
+    int32_t nrows;
+    int32_t ent_begin, ent_end;
+    int32_t pad;
+};
+
+constexpr int kGemvRows = 128;
+constexpr int kGemvChunk = 64;
+
+std::atomic<uint64_t> g_serial{1};
+
+}  // namespace
+
+struct bbm_sky_desc {
+    uint32_t magic = 0x5C71DE5Cu;
+    uint64_t serial = 0;
+    bbm_handle_t h = nullptr;
+    i64 Nr = 0, Nc = 0, m = 0, n = 0, numel = 0, nblocks = 0;
+    std::vector<i64> r, c, R, C, l, u, klo, khi, off, S;
+    // matvec tables
+    SkyEnt* d_ents = nullptr;
+    SkyItem* d_items = nullptr;
+    int nitems = 0;
+    // triangular-solve tables, built on first use, per uplo (0 lower, 1 upper)
+    struct Tri {
+        bool built = false;
+        SkyEnt* d_ents = nullptr;      // one panel entry per block column K
+        SkyItem* d_items = nullptr;    // update row tiles, grouped by K
+        std::vector<int> item_ptr;     // Nr+1
+        std::vector<i64> sub_ptr;      // prefix of 32-row sub-blocks per diagonal block
+        i64* d_sub = nullptr;          // per sub-block: (data offset of its top-left, ld, size)
+        i64 nsub = 0;
+    } tri[2];
+    // product plans keyed by the serials of (A, B), owned by the C descriptor
+    struct MmPlan;
+    std::map<std::pair<uint64_t, uint64_t>, MmPlan*> plans;
+};
+
+namespace {
+
+inline bool sky_valid(bbm_sky_desc_t d) { return d && d->magic == 0x5C71DE5Cu && bbm_valid(d->h); }
+inline bool sky_has(const bbm_sky_desc* d, i64 K, i64 J) { return K >= d->klo[J] && K <= d->khi[J]; }
+inline i64 sky_start(const bbm_sky_desc* d, i64 K, i64 J) { return d->off[J] + d->R[K] - d->R[d->klo[J]]; }
+
+template <typename V>
+int32_t upload(bbm_handle_t h, const std::vector<V>& v, V** out) {
+    *out = nullptr;
+    if (v.empty()) return BBM_OK;
+    cudaError_t e = cudaMalloc(out, v.size() * sizeof(V));
+    if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(%zu): %s", v.size() * sizeof(V), cudaGetErrorString(e)); }
+    BBM_CUDA(h, cudaMemcpy(*out, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+    return BBM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// panel GEMV:  Y[rows] <- alpha * sum_e A_e[rows, :] * X[xoff_e .. , q] + beta * Y[rows]
+// One thread per output row (consecutive rows of a column-major panel are contiguous, so every
+// column read is a coalesced 1 KB line per CTA), NR right-hand sides per CTA in registers, the X
+// chunk staged through shared memory, 8 independent loads in flight per thread.
+// Summation order per entry: ascending global column, like the reference's gemv-per-block sweep.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct GemvParams {
+    const T* data;
+    const T* X;
+    T* Y;
+    i64 ldx, ldy;
+    const SkyItem* items;
+    const SkyEnt* ents;
+    T alpha, beta;
+    int nrhs;
+};
+
+template <typename T, int NR>
+__global__ void __launch_bounds__(kGemvRows) sky_gemv_kernel(const GemvParams<T> p) {
+    __shared__ T xs[NR][kGemvChunk];
+    const SkyItem it = p.items[blockIdx.x];
+    const int q0 = blockIdx.y * NR;
+    const int nq = min(NR, p.nrhs - q0);
+    const int tid = threadIdx.x;
+    const bool active = tid < it.nrows;
+    T acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = T(0);
+
+    for (int e = it.ent_begin; e < it.ent_end; ++e) {
+        const SkyEnt en = p.ents[e];
+        const T* __restrict__ a = p.data + en.start + it.koff + tid;
+        for (i64 j0 = 0; j0 < en.ncols; j0 += kGemvChunk) {
+            const int nj = (int)min((i64)kGemvChunk, en.ncols - j0);
+            __syncthreads();
+            for (int idx = tid; idx < NR * kGemvChunk; idx += kGemvRows) {
+                const int q = idx / kGemvChunk, jj = idx % kGemvChunk;
+                xs[q][jj] = (q < nq && jj < nj) ? p.X[(i64)(q0 + q) * p.ldx + en.xoff + j0 + jj] : T(0);
+            }
+            __syncthreads();
+            if (active) {
+                const T* __restrict__ aj = a + j0 * en.ld;
+                int jj = 0;
+                for (; jj + 8 <= nj; jj += 8) {
+                    T v[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[t] = __ldg(aj + (i64)(jj + t) * en.ld);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) acc[q] = fma(v[t], xs[q][jj + t], acc[q]);
+                }
+                for (; jj < nj; ++jj) {
+                    const T v = __ldg(aj + (i64)jj * en.ld);
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) acc[q] = fma(v, xs[q][jj], acc[q]);
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            if (q < nq) {
+                T* yp = p.Y + (i64)(q0 + q) * p.ldy + it.yrow0 + tid;
+                T y = p.alpha * acc[q];
+                if (p.beta != T(0)) y = fma(p.beta, *yp, y);
+                *yp = y;
+            }
+        }
+    }
+}
+
+template <typename T>
+int32_t launch_gemv(bbm_handle_t h, const GemvParams<T>& p, int nitems, int nrhs) {
+    if (nitems <= 0 || nrhs <= 0) return BBM_OK;
+    cudaError_t e;
+    if (nrhs == 1) {
+        sky_gemv_kernel<T, 1><<<dim3(nitems, 1), kGemvRows, 0, h->stream>>>(p);
+    } else if (nrhs <= 4) {
+        sky_gemv_kernel<T, 4><<<dim3(nitems, 1), kGemvRows, 0, h->stream>>>(p);
+    } else {
+        sky_gemv_kernel<T, 8><<<dim3(nitems, (nrhs + 7) / 8), kGemvRows, 0, h->stream>>>(p);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_gemv_kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return BBM_OK;
+}
+
+template <typename T>
+int32_t sky_mul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs, T beta,
+                     T* d_Y, i64 ldy) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && (ldx < std::max<i64>(1, d->n) || ldy < std::max<i64>(1, d->m)))
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: A is %lld x %lld, ldx=%lld, ldy=%lld", (long long)d->m,
+                        (long long)d->n, (long long)ldx, (long long)ldy);
+    if (d->m == 0 || nrhs == 0) return BBM_OK;
+    if (!d_Y || (d->n > 0 && !d_X) || (d->numel > 0 && !d_data)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (nrhs > 8 * 65535) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "too many right-hand sides");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    GemvParams<T> p{d_data, d_X, d_Y, ldx, ldy, d->d_items, d->d_ents, alpha, beta, (int)nrhs};
+    return launch_gemv<T>(h, p, d->nitems, (int)nrhs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-banded x block-banded product:  C <- alpha*A*B + beta*C
+// Work item = one BM x BN tile of one stored block (K,J) of C; its inner dimension is the
+// concatenation of the segments N in colsupport(B,J) with K in colsupport(A,N)
+// ([upstream] _block_muladd! triple loop; result structure src/linalg.jl:27-48).  Every tile of C
+// is produced by exactly one CTA and written once: no atomics, no beta pre-pass.
+// FP64 runs on the tensor cores: mma.sync.m8n8k4.f64 (SASS DMMA) fed from a 3-stage cp.async
+// shared-memory ring -- tcgen05 has no f64 kind, so this is the sm_100a tensor path for doubles.
+// ------------------------------------------------------------------------------------------------
+struct MmCBlk {
+    i64 cstart, ldc;
+    int32_t rK, cJ;
+    int32_t seg_begin, seg_end;
+};
+struct MmSeg {
+    i64 astart, lda, bstart, ldb, kc;
+};
+struct MmTile {
+    int32_t cblk, ti, tj, pad;
+};
+
+template <typename T>
+struct MmParams {
+    const T* A;
+    const T* B;
+    T* C;
+    const MmCBlk* cblks;
+    const MmSeg* segs;
+    const MmTile* tiles;
+    T alpha, beta;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int kMmBK = 16;
+constexpr int kMmStages = 3;
+
+template <int BM, int BN>
+constexpr size_t mm_smem_bytes() {
+    return (size_t)kMmStages * ((size_t)kMmBK * (BM + 4) + (size_t)BN * (kMmBK + 4)) * sizeof(double);
+}
+
+template <int BM, int BN, int WM, int WN, bool ALIGNED>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_kernel(const MmParams<double> p) {
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int LDA = BM + 4;     // As[k][m]: 4 k-rows of a fragment land in distinct bank groups
+    constexpr int LDB = kMmBK + 4;  // Bs[n][k]
+    constexpr int MF = WM / 8, NF = WN / 8;
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    double* As = reinterpret_cast<double*>(mm_smem);
+    double* Bs = As + (size_t)kMmStages * kMmBK * LDA;
+
+    const MmTile tile = p.tiles[blockIdx.x];
+    const MmCBlk cb = p.cblks[tile.cblk];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+    const int row0 = tile.ti * BM, col0 = tile.tj * BN;
+
+    // flattened k-chunk iterator of the producer
+    int pseg = cb.seg_begin;
+    i64 pk0 = 0;
+    int total = 0;
+    for (int s = cb.seg_begin; s < cb.seg_end; ++s) total += (int)((p.segs[s].kc + kMmBK - 1) / kMmBK);
+
+    auto load_chunk = [&](int stage) {
+        const MmSeg sg = p.segs[pseg];
+        double* as = As + (size_t)stage * kMmBK * LDA;
+        double* bs = Bs + (size_t)stage * BN * LDB;
+        if (ALIGNED) {
+            for (int v = tid; v < (BM / 2) * kMmBK; v += NT) {
+                const int kk = v / (BM / 2), i = 2 * (v % (BM / 2));
+                const int row = row0 + i;
+                int nv = cb.rK - row; nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+                const bool kv = pk0 + kk < sg.kc;
+                const int bytes = kv ? 8 * nv : 0;
+                const double* src = bytes ? p.A + sg.astart + row + (pk0 + kk) * sg.lda : p.A;
+                cp_async16(as + kk * LDA + i, src, bytes);
+            }
+            for (int v = tid; v < BN * (kMmBK / 2); v += NT) {
+                const int j = v / (kMmBK / 2), kk = 2 * (v % (kMmBK / 2));
+                const int col = col0 + j;
+                i64 nv = sg.kc - (pk0 + kk); nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+                const int bytes = col < cb.cJ ? 8 * (int)nv : 0;
+                const double* src = bytes ? p.B + sg.bstart + (pk0 + kk) + (i64)col * sg.ldb : p.B;
+                cp_async16(bs + j * LDB + kk, src, bytes);
+            }
+        } else {
+            for (int v = tid; v < BM * kMmBK; v += NT) {
+                const int kk = v / BM, i = v % BM;
+                const int row = row0 + i;
+                const int bytes = (row < cb.rK && pk0 + kk < sg.kc) ? 8 : 0;
+                const double* src = bytes ? p.A + sg.astart + row + (pk0 + kk) * sg.lda : p.A;
+                cp_async8(as + kk * LDA + i, src, bytes);
+            }
+            for (int v = tid; v < BN * kMmBK; v += NT) {
+                const int j = v / kMmBK, kk = v % kMmBK;
+                const int col = col0 + j;
+                const int bytes = (col < cb.cJ && pk0 + kk < sg.kc) ? 8 : 0;
+                const double* src = bytes ? p.B + sg.bstart + (pk0 + kk) + (i64)col * sg.ldb : p.B;
+                cp_async8(bs + j * LDB + kk, src, bytes);
+            }
+        }
+        pk0 += kMmBK;
+        if (pk0 >= sg.kc) { pk0 = 0; ++pseg; }
+    };
+
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    int issued = 0;
+    for (; issued < kMmStages - 1; ++issued) {
+        if (issued < total) load_chunk(issued % kMmStages);
+        cp_async_commit();
+    }
+    const int ar = lane >> 2, ac = lane & 3;  // fragment coordinates of this lane
+    for (int c = 0; c < total; ++c) {
+        cp_async_wait<kMmStages - 2>();
+        __syncthreads();
+        if (issued < total) load_chunk(issued % kMmStages);
+        cp_async_commit();
+        ++issued;
+        const double* as = As + (size_t)(c % kMmStages) * kMmBK * LDA;
+        const double* bs = Bs + (size_t)(c % kMmStages) * BN * LDB;
+#pragma unroll
+        for (int k4 = 0; k4 < kMmBK; k4 += 4) {
+            double af[MF], bf[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) af[i] = as[(k4 + ac) * LDA + wm0 + i * 8 + ar];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) bf[j] = bs[(wn0 + j * 8 + ar) * LDB + k4 + ac];
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: accumulator (row = lane/4, cols = 2*(lane%4)+{0,1}) -> C, written once
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+        const int row = row0 + wm0 + i * 8 + ar;
+        if (row >= cb.rK) continue;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int col = col0 + wn0 + j * 8 + 2 * ac + t;
+                if (col < cb.cJ) {
+                    double* cp = p.C + cb.cstart + row + (i64)col * cb.ldc;
+                    double v = alpha * acc[i][j][t];
+                    if (beta != 0.0) v = fma(beta, *cp, v);
+                    *cp = v;
+                }
+            }
+        }
+    }
+}
+
+// SIMT tile kernel: Float32 (tcgen05 kind::tf32 would drop 13 mantissa bits, outside the
+// 64*eps tolerance) and a cross-check path for Float64 ("sky.mm_kernel" = 2).
+template <typename T>
+__global__ void __launch_bounds__(256) sky_gemm_simt_kernel(const MmParams<T> p) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ T As[BK][BM + 1];
+    __shared__ T Bs[BK][BN + 1];
+    const MmTile tile = p.tiles[blockIdx.x];
+    const MmCBlk cb = p.cblks[tile.cblk];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int row0 = tile.ti * BM, col0 = tile.tj * BN;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int s = cb.seg_begin; s < cb.seg_end; ++s) {
+        const MmSeg sg = p.segs[s];
+        for (i64 k0 = 0; k0 < sg.kc; k0 += BK) {
+            __syncthreads();
+            for (int v = tid; v < BM * BK; v += 256) {
+                const int kk = v / BM, i = v % BM;
+                const int row = row0 + i;
+                As[kk][i] = (row < cb.rK && k0 + kk < sg.kc) ? p.A[sg.astart + row + (k0 + kk) * sg.lda] : T(0);
+            }
+            for (int v = tid; v < BN * BK; v += 256) {
+                const int j = v / BK, kk = v % BK;
+                const int col = col0 + j;
+                Bs[kk][j] = (col < cb.cJ && k0 + kk < sg.kc) ? p.B[sg.bstart + (k0 + kk) + (i64)col * sg.ldb] : T(0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                T a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = row0 + tx + 16 * i;
+        if (row >= cb.rK) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = col0 + ty + 16 * j;
+            if (col < cb.cJ) {
+                T* cp = p.C + cb.cstart + row + (i64)col * cb.ldc;
+                T v = p.alpha * acc[i][j];
+                if (p.beta != T(0)) v = fma(p.beta, *cp, v);
+                *cp = v;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct bbm_sky_desc::MmPlan {
+    MmCBlk* d_cblks = nullptr;
+    MmSeg* d_segs = nullptr;
+    MmTile* d_tiles[2] = {nullptr, nullptr};  // [0] 128x128 DMMA tiles, [1] 64x64 tiles
+    int ntiles[2] = {0, 0};
+    bool aligned = false;
+    double flops = 0;
+};
+
+namespace {
+
+void free_plan(bbm_sky_desc::MmPlan* pl) {
+    if (!pl) return;
+    if (pl->d_cblks) cudaFree(pl->d_cblks);
+    if (pl->d_segs) cudaFree(pl->d_segs);
+    for (int i = 0; i < 2; ++i)
+        if (pl->d_tiles[i]) cudaFree(pl->d_tiles[i]);
+    delete pl;
+}
+
+// structure checks + plan construction for C <- A*B
+int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t Cd, bbm_sky_desc::MmPlan** out) {
+    // block axes must be compatible ([upstream] DimensionMismatch)
+    if (A->Nc != B->Nr || Cd->Nr != A->Nr || Cd->Nc != B->Nc || A->c != B->r || A->r != Cd->r || B->c != Cd->c)
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: block axes of A (%lldx%lld blocks), B (%lldx%lld) and C (%lldx%lld) are incompatible",
+                        (long long)A->Nr, (long long)A->Nc, (long long)B->Nr, (long long)B->Nc, (long long)Cd->Nr, (long long)Cd->Nc);
+    // every product block must be stored in C (BandError, src/BlockSkylineMatrix.jl:491)
+    for (i64 J = 0; J < B->Nc; ++J)
+        for (i64 N = B->klo[J]; N <= B->khi[J]; ++N)
+            for (i64 K = A->klo[N]; K <= A->khi[N]; ++K)
+                if (!sky_has(Cd, K, J) && A->r[K] > 0 && B->c[J] > 0 && A->c[N] > 0)
+                    return bbm_fail(h, BBM_ERR_BAND, "BandError: product block (%lld,%lld) lies outside the block band of C", (long long)K, (long long)J);
+    std::vector<MmCBlk> cblks;
+    std::vector<MmSeg> segs;
+    std::vector<MmTile> tiles[2];
+    const int tsz[2] = {128, 64};
+    bool aligned = true;
+    double flops = 0;
+    for (i64 J = 0; J < Cd->Nc; ++J) {
+        if (Cd->c[J] == 0) continue;
+        for (i64 K = Cd->klo[J]; K <= Cd->khi[J]; ++K) {
+            if (Cd->r[K] == 0) continue;
+            MmCBlk cb;
+            cb.cstart = sky_start(Cd, K, J); cb.ldc = Cd->S[J];
+            cb.rK = (int32_t)Cd->r[K]; cb.cJ = (int32_t)Cd->c[J];
+            cb.seg_begin = (int32_t)segs.size();
+            for (i64 N = B->klo[J]; N <= B->khi[J]; ++N) {
+                if (A->c[N] == 0 || !sky_has(A, K, N)) continue;
+                MmSeg sg{sky_start(A, K, N), A->S[N], sky_start(B, N, J), B->S[J], A->c[N]};
+                aligned = aligned && !(sg.astart & 1) && !(sg.lda & 1) && !(sg.bstart & 1) && !(sg.ldb & 1);
+                flops += 2.0 * (double)cb.rK * (double)cb.cJ * (double)sg.kc;
+                segs.push_back(sg);
+            }
+            cb.seg_end = (int32_t)segs.size();
+            const int32_t ci = (int32_t)cblks.size();
+            cblks.push_back(cb);
+            for (int t = 0; t < 2; ++t)
+                for (int tj = 0; tj * tsz[t] < cb.cJ; ++tj)
+                    for (int ti = 0; ti * tsz[t] < cb.rK; ++ti) tiles[t].push_back(MmTile{ci, ti, tj, 0});
+        }
+    }
+    if (segs.size() > (size_t)INT32_MAX / 2 || tiles[1].size() > (size_t)INT32_MAX / 2)
+        return bbm_fail(h, BBM_ERR_UNSUPPORTED, "product plan too large");
+    auto* pl = new (std::nothrow) bbm_sky_desc::MmPlan();
+    if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
+    pl->aligned = aligned; pl->flops = flops;
+    int32_t rc = upload(h, cblks, &pl->d_cblks);
+    if (rc == BBM_OK) rc = upload(h, segs, &pl->d_segs);
+    for (int t = 0; t < 2 && rc == BBM_OK; ++t) { rc = upload(h, tiles[t], &pl->d_tiles[t]); pl->ntiles[t] = (int)tiles[t].size(); }
+    if (rc != BBM_OK) { free_plan(pl); return rc; }
+    *out = pl;
+    return BBM_OK;
+}
+
+template <typename T>
+int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t Cd, T alpha, const T* dA,
+                        const T* dB, T beta, T* dC) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(A) || !sky_valid(B) || !sky_valid(Cd)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    auto key = std::make_pair(A->serial, B->serial);
+    auto it = Cd->plans.find(key);
+    if (it == Cd->plans.end()) {
+        bbm_sky_desc::MmPlan* pl = nullptr;
+        int32_t rc = build_mm_plan(h, A, B, Cd, &pl);
+        if (rc != BBM_OK) return rc;
+        it = Cd->plans.emplace(key, pl).first;
+    }
+    const bbm_sky_desc::MmPlan* pl = it->second;
+    if (pl->ntiles[1] == 0) return BBM_OK;
+    if (!dC || (A->numel > 0 && !dA) || (B->numel > 0 && !dB)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (dC == dA || dC == dB) return bbm_fail(h, BBM_ERR_ARG, "mul!: destination must not alias an operand");
+    MmParams<T> p{dA, dB, dC, pl->d_cblks, pl->d_segs, nullptr, alpha, beta};
+    const i64 force = bbm_opt(h, "sky.mm_kernel", 0);
+    cudaError_t e = cudaSuccess;
+    if (sizeof(T) == 8 && force != 2) {
+        const bool al = pl->aligned && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % 16 == 0);
+        MmParams<double> pd{(const double*)dA, (const double*)dB, (double*)dC, pl->d_cblks, pl->d_segs, pl->d_tiles[0], (double)alpha, (double)beta};
+        constexpr size_t smem = mm_smem_bytes<128, 128>();
+        auto go = [&](auto kern) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { kern<<<pl->ntiles[0], 256, smem, h->stream>>>(pd); e = cudaGetLastError(); }
+        };
+        if (al) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, true>);
+        else go(sky_dgemm_dmma_kernel<128, 128, 64, 32, false>);
+    } else {
+        p.tiles = pl->d_tiles[1];
+        sky_gemm_simt_kernel<T><<<pl->ntiles[1], 256, 0, h->stream>>>(p);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "block-banded product launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return BBM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block triangular solve  B <- T^-1 B,  T = Upper/LowerTriangular (unit or not) of a block-banded
+// matrix with square diagonal blocks ([upstream] BlockArrays block substitution; bounds
+// src/triblockbanded.jl:10-25, panel operand src/linalg.jl:93-115).
+//   pass 0 (parallel):   invert every 32x32 diagonal sub-block of every diagonal block
+//   per block K (sequential, as in the reference):
+//       diag kernel   x_K <- T_KK^-1 b_K by blocked substitution over 32-row sub-blocks, each step
+//                     a small product with the pre-inverted sub-block; right-hand sides split
+//                     over CTAs, b_K kept in shared memory
+//       panel update  b_KR <- b_KR - A[KR,K] x_K: the panel GEMV kernel on the contiguous
+//                     off-diagonal panel (all right-hand sides at once, the matrix read once
+//                     instead of once per column as on the CPU)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) sky_tri_invdiag_kernel(const T* __restrict__ data, const i64* __restrict__ sub, i64 nsub,
+                                                              int upper, int unit, T* __restrict__ W) {
+    __shared__ T Ts[4][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 sb = (i64)blockIdx.x * 4 + warp;
+    if (sb >= nsub) return;
+    const i64 start = sub[3 * sb], ld = sub[3 * sb + 1];
+    const int nb = (int)sub[3 * sb + 2];
+    for (int j = 0; j < nb; ++j)
+        if (lane < nb) Ts[warp][lane][j] = data[start + lane + (i64)j * ld];
+    __syncwarp();
+    // lane j computes column j of the inverse:  T x = e_j
+    T x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = T(0);
+    const int j = lane;
+    if (j < nb) {
+        if (upper) {
+#pragma unroll
+            for (int i = 31; i >= 0; --i) {
+                if (i <= j && i < nb) {
+                    T s = (i == j) ? T(1) : T(0);
+#pragma unroll
+                    for (int k = 31; k > 0; --k)
+                        if (k > i && k <= j) s = fma(-Ts[warp][i][k], x[k], s);
+                    x[i] = unit ? s : s / Ts[warp][i][i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i >= j && i < nb) {
+                    T s = (i == j) ? T(1) : T(0);
+#pragma unroll
+                    for (int k = 0; k < 31; ++k)
+                        if (k < i && k >= j) s = fma(-Ts[warp][i][k], x[k], s);
+                    x[i] = unit ? s : s / Ts[warp][i][i];
+                }
+            }
+        }
+    }
+    T* w = W + sb * 1024;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i + 32 * j] = x[i];
+}
+
+template <typename T, int RC>
+__global__ void __launch_bounds__(256) sky_tri_diag_kernel(const T* __restrict__ data, i64 dstart, i64 ld, int rK, int upper,
+                                                           const T* __restrict__ W, T* __restrict__ Bk, i64 ldb, int nrhs) {
+    extern __shared__ __align__(16) unsigned char tri_smem[];
+    T* bs = reinterpret_cast<T*>(tri_smem);  // bs[q * rK + i]
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * RC;
+    const int nq = min(RC, nrhs - q0);
+    for (int idx = tid; idx < RC * rK; idx += 256) {
+        const int q = idx / rK, i = idx % rK;
+        bs[idx] = q < nq ? Bk[(i64)(q0 + q) * ldb + i] : T(0);
+    }
+    __syncthreads();
+    const int nsb = (rK + 31) / 32;
+    const T* __restrict__ A = data + dstart;
+    for (int s = 0; s < nsb; ++s) {
+        const int ib = upper ? nsb - 1 - s : s;
+        const int i0 = ib * 32, nb = min(32, rK - i0);
+        const T* __restrict__ w = W + (i64)ib * 1024;
+        // x_ib = inv(T_ib,ib) * b_ib
+        T xv = T(0);
+        const int i = tid & 31, q = tid >> 5;
+        if (q < RC) {
+#pragma unroll 8
+            for (int j = 0; j < nb; ++j) xv = fma(w[i + 32 * j], bs[q * rK + i0 + j], xv);
+        }
+        __syncthreads();
+        if (q < RC && i < nb) {
+            bs[q * rK + i0 + i] = xv;
+            if (q < nq) Bk[(i64)(q0 + q) * ldb + i0 + i] = xv;
+        }
+        __syncthreads();
+        // remaining rows of the diagonal block: b -= T[rows, ib] * x_ib
+        const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
+        for (int row = rlo + tid; row < rhi; row += 256) {
+            T acc[RC];
+#pragma unroll
+            for (int qq = 0; qq < RC; ++qq) acc[qq] = T(0);
+            const T* __restrict__ a = A + row + (i64)i0 * ld;
+            for (int j = 0; j < nb; ++j) {
+                const T v = a[(i64)j * ld];
+#pragma unroll
+                for (int qq = 0; qq < RC; ++qq) acc[qq] = fma(v, bs[qq * rK + i0 + j], acc[qq]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < RC; ++qq) bs[qq * rK + row] -= acc[qq];
+        }
+        __syncthreads();
+    }
+}
+
+int32_t build_tri(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    if (t.built) return BBM_OK;
+    const i64 N = d->Nr;
+    std::vector<SkyEnt> ents(N);
+    std::vector<SkyItem> items;
+    std::vector<i64> sub;
+    t.item_ptr.assign(N + 1, 0);
+    t.sub_ptr.assign(N + 1, 0);
+    for (i64 K = 0; K < N; ++K) {
+        t.item_ptr[K] = (int)items.size();
+        t.sub_ptr[K + 1] = t.sub_ptr[K] + (d->r[K] + 31) / 32;
+        ents[K] = SkyEnt{0, 1, d->R[K], d->r[K]};
+        if (d->r[K] == 0) continue;
+        const i64 dstart = sky_start(d, K, K);
+        for (i64 i0 = 0; i0 < d->r[K]; i0 += 32) {
+            sub.push_back(dstart + i0 + i0 * d->S[K]);
+            sub.push_back(d->S[K]);
+            sub.push_back(std::min<i64>(32, d->r[K] - i0));
+        }
+        // off-diagonal panel of block column K: rows of block rows klo..K-1 (upper) / K+1..khi (lower)
+        i64 prow0, prows, yrow0;
+        if (upper) { prow0 = 0; prows = d->R[K] - d->R[d->klo[K]]; yrow0 = d->R[d->klo[K]]; }
+        else { prow0 = d->R[K + 1] - d->R[d->klo[K]]; prows = d->R[d->khi[K] + 1] - d->R[K + 1]; yrow0 = d->R[K + 1]; }
+        ents[K] = SkyEnt{d->off[K] + prow0, d->S[K], d->R[K], d->r[K]};
+        for (i64 r0 = 0; r0 < prows; r0 += kGemvRows)
+            items.push_back(SkyItem{yrow0 + r0, r0, (int32_t)std::min<i64>(kGemvRows, prows - r0), (int32_t)K, (int32_t)K + 1, 0});
+    }
+    t.item_ptr[N] = (int)items.size();
+    t.nsub = (i64)sub.size() / 3;
+    int32_t rc = upload(h, ents, &t.d_ents);
+    if (rc == BBM_OK) rc = upload(h, items, &t.d_items);
+    if (rc == BBM_OK) rc = upload(h, sub, &t.d_sub);
+    if (rc != BBM_OK) return rc;
+    t.built = true;
+    return BBM_OK;
+}
+
+template <typename T>
+int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (uplo != 'U' && uplo != 'L' && uplo != 'u' && uplo != 'l') return bbm_fail(h, BBM_ERR_ARG, "uplo must be 'U' or 'L'");
+    const int upper = (uplo == 'U' || uplo == 'u') ? 1 : 0;
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    // hasmatchingblocks (src/triblockbanded.jl:12,20): square diagonal blocks
+    if (d->Nr != d->Nc || d->r != d->c)
+        return bbm_fail(h, BBM_ERR_UNSUPPORTED, "triangular solve needs matching square diagonal blocks (the reference falls back to a generic solve)");
+    if (nrhs > 0 && ldb < std::max<i64>(1, d->m)) return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: T is %lld x %lld, ldb=%lld", (long long)d->m, (long long)d->m, (long long)ldb);
+    for (i64 K = 0; K < d->Nr; ++K)
+        if (d->r[K] > 0 && !sky_has(d, K, K)) return bbm_fail(h, BBM_ERR_BAND, "BandError: diagonal block %lld is outside the block band", (long long)K);
+    if (d->m == 0 || nrhs == 0) return BBM_OK;
+    if (!d_data || !d_B) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (nrhs > 8 * 65535) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "too many right-hand sides");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    int32_t rc = build_tri(h, d, upper);
+    if (rc != BBM_OK) return rc;
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    // pass 0: inverses of the 32x32 diagonal sub-blocks (workspace: 1024 entries per sub-block)
+    rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, (size_t)t.nsub * 1024 * sizeof(T));
+    if (rc != BBM_OK) return rc;
+    T* W = static_cast<T*>(h->ws_x);
+    sky_tri_invdiag_kernel<T><<<(unsigned)((t.nsub + 3) / 4), 128, 0, h->stream>>>(d_data, t.d_sub, t.nsub, upper, unit ? 1 : 0, W);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_tri_invdiag_kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    // right-hand sides per diag CTA: as many as keep b_K in shared memory, at most 8
+    i64 maxr = 0;
+    for (i64 K = 0; K < d->Nr; ++K) maxr = std::max(maxr, d->r[K]);
+    const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
+    int RC = 8;
+    while (RC > 1 && (size_t)RC * maxr * sizeof(T) > budget) RC /= 2;
+    if ((size_t)RC * maxr * sizeof(T) > budget) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "diagonal block of %lld rows does not fit the shared-memory solve", (long long)maxr);
+    if (nrhs < RC) RC = nrhs >= 4 ? 4 : (nrhs >= 2 ? 2 : 1);
+    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)RC * maxr * sizeof(T))); };
+    if (RC == 8) e = set_attr(sky_tri_diag_kernel<T, 8>);
+    else if (RC == 4) e = set_attr(sky_tri_diag_kernel<T, 4>);
+    else if (RC == 2) e = set_attr(sky_tri_diag_kernel<T, 2>);
+    else e = set_attr(sky_tri_diag_kernel<T, 1>);
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const unsigned gq = (unsigned)((nrhs + RC - 1) / RC);
+    for (i64 s = 0; s < d->Nr; ++s) {
+        const i64 K = upper ? d->Nr - 1 - s : s;
+        const int rK = (int)d->r[K];
+        if (rK == 0) continue;
+        const i64 dstart = sky_start(d, K, K);
+        const size_t smem = (size_t)RC * rK * sizeof(T);
+        const T* Wk = W + t.sub_ptr[K] * 1024;
+        T* Bk = d_B + d->R[K];
+        if (RC == 8) sky_tri_diag_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+        else if (RC == 4) sky_tri_diag_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+        else if (RC == 2) sky_tri_diag_kernel<T, 2><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+        else sky_tri_diag_kernel<T, 1><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_tri_diag_kernel launch: %s", cudaGetErrorString(e));
+        h->launches += 1;
+        const int ni = t.item_ptr[K + 1] - t.item_ptr[K];
+        if (ni > 0) {
+            GemvParams<T> p{d_data, d_B, d_B, ldb, ldb, t.d_items + t.item_ptr[K], t.d_ents, T(-1), T(1), (int)nrhs};
+            rc = launch_gemv<T>(h, p, ni, (int)nrhs);
+            if (rc != BBM_OK) return rc;
+        }
+    }
+    return BBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bbm_sky_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, const int64_t* lvec,
+                            const int64_t* uvec, bbm_sky_desc_t* out) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!out) return bbm_fail(h, BBM_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (Nr < 0 || Nc < 0 || (Nr > 0 && !r) || (Nc > 0 && (!c || !lvec || !uvec))) return bbm_fail(h, BBM_ERR_ARG, "bad block axes");
+    if (Nr > INT32_MAX / 4 || Nc > INT32_MAX / 4) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "too many blocks");
+    bbm_sky_desc* d = new (std::nothrow) bbm_sky_desc();
+    if (!d) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
+    d->h = h; d->serial = g_serial.fetch_add(1); d->Nr = Nr; d->Nc = Nc;
+    d->r.assign(r, r + Nr); d->c.assign(c, c + Nc);
+    d->l.assign(lvec, lvec + Nc); d->u.assign(uvec, uvec + Nc);
+    d->R.assign(Nr + 1, 0); d->C.assign(Nc + 1, 0);
+    for (i64 K = 0; K < Nr; ++K) {
+        if (r[K] < 0 || r[K] > INT32_MAX / 2) { delete d; return bbm_fail(h, BBM_ERR_ARG, "bad row block size"); }
+        d->R[K + 1] = d->R[K] + r[K];
+    }
+    for (i64 J = 0; J < Nc; ++J) {
+        if (c[J] < 0 || c[J] > INT32_MAX / 2) { delete d; return bbm_fail(h, BBM_ERR_ARG, "bad column block size"); }
+        d->C[J + 1] = d->C[J] + c[J];
+    }
+    d->m = d->R[Nr]; d->n = d->C[Nc];
+    // panels: bb_blockstarts / bb_blockstrides / bb_numentries (src/BlockSkylineMatrix.jl:6-43, 93-104)
+    d->klo.assign(Nc, 0); d->khi.assign(Nc, -1); d->S.assign(Nc, 0); d->off.assign(Nc + 1, 0);
+    for (i64 J = 0; J < Nc; ++J) {
+        // KR = max(1,J-u[J]):min(J+l[J],N), possibly empty (src/BlockSkylineMatrix.jl:16, 35, 91)
+        const i64 lo = std::max<i64>(0, J - uvec[J]), hi = std::min<i64>(Nr - 1, J + lvec[J]);
+        d->klo[J] = lo;
+        d->khi[J] = hi >= lo ? hi : lo - 1;
+        d->S[J] = hi >= lo ? d->R[hi + 1] - d->R[lo] : 0;
+        d->off[J + 1] = d->off[J] + d->S[J] * c[J];
+        d->nblocks += std::max<i64>(0, d->khi[J] - d->klo[J] + 1);
+    }
+    d->numel = d->off[Nc];
+    // matvec tables: per block row K the blocks (K,J) in ascending J; items = 128-row tiles
+    std::vector<std::vector<i64>> rowJ(Nr);
+    for (i64 J = 0; J < Nc; ++J)
+        for (i64 K = d->klo[J]; K <= d->khi[J]; ++K)
+            if (c[J] > 0) rowJ[K].push_back(J);
+    std::vector<SkyEnt> ents;
+    std::vector<SkyItem> items;
+    for (i64 K = 0; K < Nr; ++K) {
+        if (r[K] == 0) continue;
+        const int32_t e0 = (int32_t)ents.size();
+        for (i64 J : rowJ[K]) ents.push_back(SkyEnt{sky_start(d, K, J), d->S[J], d->C[J], c[J]});
+        const int32_t e1 = (int32_t)ents.size();
+        for (i64 k0 = 0; k0 < r[K]; k0 += kGemvRows)
+            items.push_back(SkyItem{d->R[K] + k0, k0, (int32_t)std::min<i64>(kGemvRows, r[K] - k0), e0, e1, 0});
+    }
+    d->nitems = (int)items.size();
+    cudaError_t e = cudaSetDevice(h->device);
+    int32_t rc = e == cudaSuccess ? BBM_OK : bbm_fail(h, BBM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (rc == BBM_OK) rc = upload(h, ents, &d->d_ents);
+    if (rc == BBM_OK) rc = upload(h, items, &d->d_items);
+    if (rc != BBM_OK) { bbm_sky_desc_destroy(d); return rc; }
+    *out = d;
+    return BBM_OK;
+}
+
+int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
+    if (!d || d->magic != 0x5C71DE5Cu) return BBM_ERR_HANDLE;
+    if (bbm_valid(d->h)) cudaSetDevice(d->h->device);
+    if (d->d_ents) cudaFree(d->d_ents);
+    if (d->d_items) cudaFree(d->d_items);
+    for (int t = 0; t < 2; ++t) {
+        if (d->tri[t].d_ents) cudaFree(d->tri[t].d_ents);
+        if (d->tri[t].d_items) cudaFree(d->tri[t].d_items);
+        if (d->tri[t].d_sub) cudaFree(d->tri[t].d_sub);
+    }
+    for (auto& kv : d->plans) free_plan(kv.second);
+    d->magic = 0;
+    delete d;
+    return BBM_OK;
+}
+
+int32_t bbm_sky_desc_info(bbm_sky_desc_t d, int64_t* m, int64_t* n, int64_t* numentries, int64_t* nblocks) {
+    if (!sky_valid(d)) return BBM_ERR_HANDLE;
+    if (m) *m = d->m;
+    if (n) *n = d->n;
+    if (numentries) *numentries = d->numel;
+    if (nblocks) *nblocks = d->nblocks;
+    return BBM_OK;
+}
+
+int32_t bbm_sky_desc_layout(bbm_sky_desc_t d, int64_t* panel_offsets, int64_t* panel_strides, int64_t* klo, int64_t* khi) {
+    if (!sky_valid(d)) return BBM_ERR_HANDLE;
+    if (panel_offsets) std::copy(d->off.begin(), d->off.end(), panel_offsets);
+    if (panel_strides) std::copy(d->S.begin(), d->S.end(), panel_strides);
+    if (klo) std::copy(d->klo.begin(), d->klo.end(), klo);
+    if (khi) std::copy(d->khi.begin(), d->khi.end(), khi);
+    return BBM_OK;
+}
+
+int32_t bbm_sky_mul_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_data, const double* d_X, int64_t ldx,
+                        int64_t nrhs, double beta, double* d_Y, int64_t ldy) {
+    return sky_mul_impl<double>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_sky_mul_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X, int64_t ldx,
+                        int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
+    return sky_mul_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_sky_matmul_f64(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, double alpha, const double* dA,
+                           const double* dB, double beta, double* dC) {
+    return sky_matmul_impl<double>(h, A, B, C, alpha, dA, dB, beta, dC);
+}
+int32_t bbm_sky_matmul_f32(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, float alpha, const float* dA,
+                           const float* dB, float beta, float* dC) {
+    return sky_matmul_impl<float>(h, A, B, C, alpha, dA, dB, beta, dC);
+}
+int32_t bbm_sky_trsm_f64(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const double* d_data, double* d_B,
+                         int64_t ldb, int64_t nrhs) {
+    return sky_trsm_impl<double>(h, d, uplo, unit, d_data, d_B, ldb, nrhs);
+}
+int32_t bbm_sky_trsm_f32(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const float* d_data, float* d_B,
+                         int64_t ldb, int64_t nrhs) {
+    return sky_trsm_impl<float>(h, d, uplo, unit, d_data, d_B, ldb, nrhs);
+}
+
+}  // extern "C"

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from .device import DeviceArray
-from .matrices import BandedBlockBandedMatrix
+from .matrices import BandedBlockBandedMatrix, BlockSkylineMatrix, _Triangular
 
 _SUF = {np.dtype(np.float64): ("f64", C.c_double), np.dtype(np.float32): ("f32", C.c_float)}
 
@@ -51,8 +51,11 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
 
     x, y are both DeviceArrays (asynchronous, on the handle's stream) or both numpy arrays
     (host vectors: copied through the C ABI's *_host_* call, synchronous)."""
-    if not isinstance(A, BandedBlockBandedMatrix):
+    if isinstance(A, BlockSkylineMatrix) and isinstance(x, BlockSkylineMatrix):
+        return _sky_matmul_(y, A, x, alpha, beta)
+    if not isinstance(A, (BandedBlockBandedMatrix, BlockSkylineMatrix)):
         raise TypeError(f"unsupported matrix type {type(A).__name__}")
+    kind = "bbb" if isinstance(A, BandedBlockBandedMatrix) else "sky"
     h = _require_device(A)
     m, n = A.shape
     xr, xc = _vec_dims(x, "x")
@@ -72,10 +75,13 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
     if dev[0]:
         if y.ptr == x.ptr and m and n:
             raise ValueError("mul!: destination must not alias the source")
-        fn = getattr(h._lib, f"bbm_bbb_mul_{suf}")
+        fn = getattr(h._lib, f"bbm_{kind}_mul_{suf}")
         rc = fn(h.h, desc, ct(alpha), C.c_void_p(A.data.ptr), C.c_void_p(x.ptr), _ld(x), xc, ct(beta),
                 C.c_void_p(y.ptr), _ld(y))
     else:
+        if kind != "bbb":
+            raise TypeError("host vectors are taken by the BandedBlockBandedMatrix product only; "
+                            "move x and y to the device for a BlockSkylineMatrix")
         if not y.flags.writeable:
             raise ValueError("y is read-only")
         fn = getattr(h._lib, f"bbm_bbb_mul_host_{suf}")
@@ -90,9 +96,82 @@ def muladd_(alpha, A, B, beta, Cdest):
     return mul_(Cdest, A, B, alpha, beta)
 
 
-def mul(A, x):
-    """``A*x``: allocates the result where x lives (``similar`` + ``mul!``)."""
+def add_bandwidths(A: BlockSkylineMatrix, B: BlockSkylineMatrix):
+    """Column block-bandwidths of ``A*B`` (src/linalg.jl:8-30): ``Fill(lA+lB), Fill(uA+uB)`` for two
+    BlockBandedMatrix operands, else per column ``v[i] = Bv[i] + maximum(Av[sel])`` with
+    ``sel = max(i-Bu[i],1):min(i+Bl[i],length(Av))`` (skipped when empty)."""
+    if A.constant_bandwidths and B.constant_bandwidths:
+        lA, uA = (int(A.l[0]), int(A.u[0])) if len(A.l) else (0, 0)
+        lB, uB = (int(B.l[0]), int(B.u[0])) if len(B.l) else (0, 0)
+        return lA + lB, uA + uB
+    l, u = B.l.copy(), B.u.copy()
+    for v, Av in ((l, A.l), (u, A.u)):
+        for i in range(len(v)):
+            lo, hi = max(i - int(B.u[i]), 0), min(i + int(B.l[i]), len(Av) - 1)
+            if hi >= lo:
+                v[i] += int(np.max(Av[lo:hi + 1]))
+    return l, u
+
+
+def _sky_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
+    """``mul!(C, A, B, alpha, beta)`` for three BlockSkylineMatrix operands."""
+    if not isinstance(Cm, BlockSkylineMatrix):
+        raise TypeError("the destination of a block-banded product must be a BlockSkylineMatrix")
     h = _require_device(A)
+    _require_device(B)
+    _require_device(Cm)
+    if A.shape[1] != B.shape[0] or Cm.shape != (A.shape[0], B.shape[1]):
+        raise L.DimensionMismatch(f"A is {A.shape}, B is {B.shape}, C is {Cm.shape}")
+    dt = A.dtype
+    if dt not in _SUF or B.dtype != dt or Cm.dtype != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, ct = _SUF[dt]
+    fn = getattr(h._lib, f"bbm_sky_matmul_{suf}")
+    rc = fn(h.h, A.descriptor(h), B.descriptor(h), Cm.descriptor(h), ct(alpha), C.c_void_p(A.data.ptr),
+            C.c_void_p(B.data.ptr), ct(beta), C.c_void_p(Cm.data.ptr))
+    L.check(rc, h.h, "mul!")
+    return Cm
+
+
+def ldiv_(T, B):
+    """``ldiv!(UpperTriangular(A), B)`` etc.: B <- T^-1 B in place on the device, returns B."""
+    if not isinstance(T, _Triangular) or not isinstance(T.parent, BlockSkylineMatrix):
+        raise TypeError("ldiv! takes Upper/LowerTriangular wrappers of a BlockSkylineMatrix")
+    A = T.parent
+    h = _require_device(A)
+    if not isinstance(B, DeviceArray):
+        raise TypeError("the right-hand side must be a device array")
+    br, bc = _vec_dims(B, "B")
+    if br != A.shape[0] or A.shape[0] != A.shape[1]:
+        raise L.DimensionMismatch(f"T is {A.shape}, B is {B.shape}")
+    dt = A.dtype
+    if dt not in _SUF or np.dtype(B.dtype) != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, _ = _SUF[dt]
+    fn = getattr(h._lib, f"bbm_sky_trsm_{suf}")
+    rc = fn(h.h, A.descriptor(h), ord(T.uplo), 1 if T.unit else 0, C.c_void_p(A.data.ptr), C.c_void_p(B.ptr), _ld(B), bc)
+    L.check(rc, h.h, "ldiv!")
+    return B
+
+
+def ldiv(T, B):
+    """``T \\ B``: solves into a copy of B."""
+    h = _require_device(T.parent)
+    X = h.empty(B.shape, B.dtype)
+    L.check(h._lib.bbm_memcpy_d2d(h.h, C.c_void_p(X.ptr), C.c_void_p(B.ptr), B.nbytes), h.h)
+    return ldiv_(T, X)
+
+
+def mul(A, x):
+    """``A*x``: allocates the result where x lives (``similar`` + ``mul!``).  For two
+    BlockSkylineMatrix operands the result structure is ``similar(::MulAdd)`` of src/linalg.jl:32-48."""
+    h = _require_device(A)
+    if isinstance(A, BlockSkylineMatrix) and isinstance(x, BlockSkylineMatrix):
+        if len(A.cols) != len(x.rows) or (A.cols != x.rows).any():
+            raise L.DimensionMismatch("*")
+        l, u = add_bandwidths(A, x)
+        n = BlockSkylineMatrix._numentries(A.rows, x.cols, l, u)
+        return _sky_matmul_(BlockSkylineMatrix(h.empty(n, A.dtype), A.rows, x.cols, l, u), A, x, 1.0, 0.0)
     m = A.shape[0]
     shape = (m,) if len(x.shape) == 1 else (m, x.shape[1])
     if isinstance(x, DeviceArray):

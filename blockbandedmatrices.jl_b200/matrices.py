@@ -232,3 +232,212 @@ class BandedBlockBandedMatrix(_BlockAxes):
     def __matmul__(self, x):
         from .linalg import mul
         return mul(self, x)
+
+
+# ==================================================================================================
+def _bwvec(b, Nc) -> np.ndarray:
+    b = np.asarray(b, dtype=np.int64)
+    if b.ndim == 0:
+        b = np.full(Nc, int(b), dtype=np.int64)
+    b = np.ascontiguousarray(b.reshape(-1))
+    if len(b) != Nc:  # checkbandwidths, src/BlockSkylineMatrix.jl:1-3
+        raise L.DimensionMismatch(f"{Nc} lower and upper column bandwidths are required, got {len(b)}")
+    return b
+
+
+class BlockSkylineMatrix(_BlockAxes):
+    """``_BlockSkylineMatrix(data, BlockSkylineSizes(rows, cols, l, u))``; a ``BlockBandedMatrix`` when
+    ``l``, ``u`` are scalars (``Fill`` bandwidths, src/BlockSkylineMatrix.jl:55-56, 173).
+
+    ``data`` is the flat vector of column-block-contiguous panels: block column J stores block
+    rows ``max(J-u[J],0) .. min(J+l[J],Nr-1)`` as one dense column-major panel of
+    ``block_strides[J]`` rows (src/BlockSkylineMatrix.jl:6-43, 93-104)."""
+
+    def __init__(self, data, rows, cols, l, u):
+        self._init_axes(rows, cols)
+        Nr, Nc = len(self.rows), len(self.cols)
+        self.constant_bandwidths = np.ndim(l) == 0 and np.ndim(u) == 0
+        self.l, self.u = _bwvec(l, Nc), _bwvec(u, Nc)
+        J = np.arange(Nc, dtype=np.int64)
+        self.klo = np.maximum(J - self.u, 0)
+        hi = np.minimum(J + self.l, Nr - 1)
+        self.khi = np.where(hi >= self.klo, hi, self.klo - 1)
+        Rhi = self.R[np.clip(self.khi + 1, 0, Nr)]
+        Rlo = self.R[np.clip(self.klo, 0, Nr)]
+        self.block_strides = np.where(self.khi >= self.klo, Rhi - Rlo, 0).astype(np.int64)
+        self.panel_offsets = np.zeros(Nc + 1, dtype=np.int64)
+        np.cumsum(self.block_strides * self.cols, out=self.panel_offsets[1:])
+        n = int(self.panel_offsets[-1])
+        if int(np.prod(data.shape)) != n or len(data.shape) != 1:
+            raise ValueError(f"data must be a vector of bb_numentries = {n} entries, got shape {tuple(data.shape)}")
+        self.data = data
+        self._desc = None
+
+    # ---- constructors ------------------------------------------------------------------------
+    @staticmethod
+    def _numentries(rows, cols, l, u) -> int:
+        """``bb_numentries`` (src/BlockSkylineMatrix.jl:93-104)."""
+        r, c = _sizes(rows), _sizes(cols)
+        R = _cum(r)
+        Nr, Nc = len(r), len(c)
+        lv, uv = _bwvec(l, Nc), _bwvec(u, Nc)
+        J = np.arange(Nc, dtype=np.int64)
+        lo = np.maximum(J - uv, 0)
+        hi = np.minimum(J + lv, Nr - 1)
+        S = np.where(hi >= lo, R[np.clip(hi + 1, 0, Nr)] - R[np.clip(lo, 0, Nr)], 0)
+        return int(np.sum(S * c))
+
+    numentries = _numentries
+
+    @classmethod
+    def undef(cls, dtype, rows, cols, l, u):
+        """``BlockSkylineMatrix{T}(undef, rows, cols, (l,u))`` / ``BlockBandedMatrix{T}(undef, ...)``."""
+        return cls(np.empty(cls._numentries(rows, cols, l, u), dtype=dtype), rows, cols, l, u)
+
+    @classmethod
+    def zeros(cls, dtype, rows, cols, l, u):
+        return cls(np.zeros(cls._numentries(rows, cols, l, u), dtype=dtype), rows, cols, l, u)
+
+    @classmethod
+    def from_dense(cls, A, rows, cols, l, u):
+        A = np.asarray(A)
+        out = cls.zeros(A.dtype, rows, cols, l, u)
+        if A.shape != out.shape:
+            raise L.DimensionMismatch(f"dense matrix {A.shape} vs block axes {out.shape}")
+        for J in range(len(out.cols)):
+            S = int(out.block_strides[J])
+            if S == 0 or out.cols[J] == 0:
+                continue
+            r0 = int(out.R[out.klo[J]])
+            out.data[out.panel_offsets[J]:out.panel_offsets[J + 1]] = \
+                A[r0:r0 + S, out.C[J]:out.C[J + 1]].reshape(-1, order="F")
+        return out
+
+    # ---- queries -----------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return np.dtype(self.data.dtype)
+
+    @property
+    def blockbandwidths(self):
+        """(max l, max u) (src/BlockSkylineMatrix.jl:371-372 ``blockbandwidths`` of a skyline)."""
+        if len(self.l) == 0:
+            return (0, 0)
+        return (int(self.l.max()), int(self.u.max()))
+
+    @property
+    def colblockbandwidths(self):
+        return self.l.copy(), self.u.copy()
+
+    def blockcolsupport(self, J: int) -> range:
+        return range(int(self.klo[J]), int(self.khi[J]) + 1)
+
+    def has_block(self, K: int, J: int) -> bool:
+        return self.klo[J] <= K <= self.khi[J]
+
+    def block_start(self, K: int, J: int) -> int:
+        """0-based offset of block (K,J) in ``data`` (``block_starts[K,J]-1`` of the reference)."""
+        if not self.has_block(K, J):
+            raise L.BandError(f"block ({K},{J}) is outside the block band")
+        return int(self.panel_offsets[J] + self.R[K] - self.R[self.klo[J]])
+
+    def _host_data(self) -> np.ndarray:
+        return self.data.to_host() if self.on_device else self.data
+
+    def block(self, K: int, J: int) -> np.ndarray:
+        out = np.zeros((int(self.rows[K]), int(self.cols[J])), dtype=self.dtype)
+        if not self.has_block(K, J) or out.size == 0:
+            return out
+        S = int(self.block_strides[J])
+        panel = self._host_data()[self.panel_offsets[J]:self.panel_offsets[J + 1]].reshape((S, int(self.cols[J])), order="F")
+        k0 = int(self.R[K] - self.R[self.klo[J]])
+        return panel[k0:k0 + out.shape[0], :].copy()
+
+    def __getitem__(self, ij):
+        i, j = ij
+        K, J = self._find(self.R, i), self._find(self.C, j)
+        if not self.has_block(K, J):
+            return self.dtype.type(0)
+        return self._host_data()[self.block_start(K, J) + (i - int(self.R[K])) + (j - int(self.C[J])) * int(self.block_strides[J])]
+
+    def to_dense(self) -> np.ndarray:
+        data = self._host_data()
+        A = np.zeros(self.shape, dtype=self.dtype)
+        for J in range(len(self.cols)):
+            S = int(self.block_strides[J])
+            if S == 0 or self.cols[J] == 0:
+                continue
+            r0 = int(self.R[self.klo[J]])
+            A[r0:r0 + S, self.C[J]:self.C[J + 1]] = data[self.panel_offsets[J]:self.panel_offsets[J + 1]].reshape(
+                (S, int(self.cols[J])), order="F")
+        return A
+
+    # ---- device residency ----------------------------------------------------------------------
+    def to_device(self, handle: Handle) -> "BlockSkylineMatrix":
+        if self.on_device:
+            return self
+        d = handle.to_device(self.data) if self.data.size else handle.empty(self.data.shape, self.dtype)
+        return self._like(d)
+
+    def _like(self, data):
+        l = int(self.l[0]) if self.constant_bandwidths and len(self.l) else (0 if self.constant_bandwidths else self.l)
+        u = int(self.u[0]) if self.constant_bandwidths and len(self.u) else (0 if self.constant_bandwidths else self.u)
+        return BlockSkylineMatrix(data, self.rows, self.cols, l, u)
+
+    def descriptor(self, handle: Handle):
+        if self._desc is None or self._desc[0] is not handle:
+            d = C.c_void_p()
+            L.check(handle._lib.bbm_sky_desc_create(
+                handle.h, len(self.rows), len(self.cols), self.rows.ctypes.data_as(C.c_void_p),
+                self.cols.ctypes.data_as(C.c_void_p), self.l.ctypes.data_as(C.c_void_p),
+                self.u.ctypes.data_as(C.c_void_p), C.byref(d)), handle.h, "bbm_sky_desc_create")
+            self._desc = (handle, d)
+        return self._desc[1]
+
+    def __del__(self):
+        try:
+            if self._desc is not None and self._desc[0].h:
+                self._desc[0]._lib.bbm_sky_desc_destroy(self._desc[1])
+        except Exception:
+            pass
+
+    def __matmul__(self, x):
+        from .linalg import mul
+        return mul(self, x)
+
+
+def BlockBandedMatrix(data, rows, cols, lu):
+    """``_BlockBandedMatrix(data, rows, cols, (l,u))``: a BlockSkylineMatrix with constant bandwidths."""
+    return BlockSkylineMatrix(data, rows, cols, int(lu[0]), int(lu[1]))
+
+
+class _Triangular:
+    """``UpperTriangular(A)`` / ``UnitUpperTriangular(A)`` / ``LowerTriangular(A)`` / ``UnitLowerTriangular(A)``."""
+
+    def __init__(self, parent, uplo: str, unit: bool):
+        self.parent, self.uplo, self.unit = parent, uplo, bool(unit)
+
+    @property
+    def blockbandwidths(self):
+        """src/triblockbanded.jl:10-25: clip to (min(0,l),u) / (l,min(0,u)) when the blocks match."""
+        l, u = self.parent.blockbandwidths
+        P = self.parent
+        if len(P.rows) == len(P.cols) and (P.rows == P.cols).all():
+            return (min(0, l), u) if self.uplo == "U" else (l, min(0, u))
+        return (l, u)
+
+
+def UpperTriangular(A):
+    return _Triangular(A, "U", False)
+
+
+def UnitUpperTriangular(A):
+    return _Triangular(A, "U", True)
+
+
+def LowerTriangular(A):
+    return _Triangular(A, "L", False)
+
+
+def UnitLowerTriangular(A):
+    return _Triangular(A, "L", True)

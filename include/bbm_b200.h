@@ -109,6 +109,52 @@ int32_t bbm_bbb_mul_host_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, con
 int32_t bbm_bbb_mul_host_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data,
                              const float* h_X, int64_t ldx, int64_t nrhs, float beta, float* h_Y, int64_t ldy);
 
+/* ---- BlockSkylineMatrix / BlockBandedMatrix ------------------------------------------------
+ * Descriptor = BlockSkylineSizes (src/BlockSkylineMatrix.jl:47-53): block axes and per-column
+ * block bandwidths lvec[Nc], uvec[Nc] (constant vectors for BlockBandedMatrix); it computes the
+ * panel offsets / strides exactly as bb_blockstarts / bb_blockstrides / bb_numentries
+ * (src/BlockSkylineMatrix.jl:6-43, 93-104) and caches the device work lists.                    */
+typedef struct bbm_sky_desc* bbm_sky_desc_t;
+int32_t bbm_sky_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c,
+                            const int64_t* lvec, const int64_t* uvec, bbm_sky_desc_t* out);
+int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d);
+int32_t bbm_sky_desc_info(bbm_sky_desc_t d, int64_t* m, int64_t* n, int64_t* numentries, int64_t* nblocks);
+/* panel_offsets[Nc+1] (0-based offset of panel J in `data`), panel_strides[Nc] (= block_strides),
+ * klo[Nc], khi[Nc] (0-based inclusive block-row range of column J; khi < klo if empty); any may
+ * be NULL.  For cross-checking against the host container's block_starts / block_strides.        */
+int32_t bbm_sky_desc_layout(bbm_sky_desc_t d, int64_t* panel_offsets, int64_t* panel_strides, int64_t* klo, int64_t* khi);
+
+/* Y <- alpha*A*X + beta*Y, A block-skyline (replaces [upstream] materialize!(::MatMulVecAdd /
+ * ::MatMulMatAdd{<:AbstractBlockLayout,...}) + one BLAS gemv/gemm per block on the operands of
+ * src/BlockSkylineMatrix.jl:442-465; pinned by test/test_linalg.jl:49-57,
+ * test/test_blockskyline.jl:28-39).  d_data: the skyline `data` vector.                          */
+int32_t bbm_sky_mul_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_data, const double* d_X,
+                        int64_t ldx, int64_t nrhs, double beta, double* d_Y, int64_t ldy);
+int32_t bbm_sky_mul_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X,
+                        int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
+
+/* C <- alpha*A*B + beta*C, all three block-skyline (replaces [upstream] _block_muladd! + one BLAS
+ * gemm per block triple; C's structure is the caller's: src/linalg.jl:27-48 for A*B, a wider C is
+ * allowed, test/test_blockbanded.jl:213-221).  BBM_ERR_DIM if the block axes are incompatible,
+ * BBM_ERR_BAND if a product block is not stored in C.  Float64 runs on the FP64 tensor cores
+ * (DMMA); "sky.mm_kernel" = 2 forces the SIMT kernel.  C must not alias A or B.                  */
+int32_t bbm_sky_matmul_f64(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, double alpha,
+                           const double* d_A, const double* d_B, double beta, double* d_C);
+int32_t bbm_sky_matmul_f32(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, float alpha,
+                           const float* d_A, const float* d_B, float beta, float* d_C);
+
+/* B <- T^-1 B in place, T = UpperTriangular ('U') / LowerTriangular ('L') of A, unit != 0 for the
+ * Unit variants (replaces [upstream] materialize!(::Ldiv{<:TriangularLayout{..,<:AbstractBlockLayout}})
+ * block substitution: BLAS trsv on the diagonal block + gemv on the off-diagonal panel of
+ * src/linalg.jl:93-115, bounds src/triblockbanded.jl:10-25; callers src/blockskylineqr.jl:136-155).
+ * Needs matching square diagonal blocks (hasmatchingblocks), else BBM_ERR_UNSUPPORTED -- the
+ * reference takes a generic fallback there; BBM_ERR_BAND if a diagonal block is not stored.
+ * d_B: m x nrhs, ldb >= m.  All right-hand sides are solved together.                            */
+int32_t bbm_sky_trsm_f64(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const double* d_data,
+                         double* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_sky_trsm_f32(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const float* d_data,
+                         float* d_B, int64_t ldb, int64_t nrhs);
+
 /* ---- several GPUs: row-block partition + halo exchange ------------------------------------
  * One process per GPU.  Block rows are split into contiguous ranges (the reference's one
  * data-parallel strategy, examples/shared_array_backend.jl:92-122, partition :106-107); rank p owns

@@ -1,0 +1,220 @@
+"""Parity of the CUDA BlockSkylineMatrix paths (matvec, block-banded x block-banded product on the
+FP64 tensor cores, block triangular solve) with the CPU oracle, through the C ABI.
+
+Tolerance (BASELINE.json north_star): normwise relative error <= 64*eps(T)*(nonzeros per row)."""
+import numpy as np
+import pytest
+
+import bbm_b200 as B
+from oracle import cpu as O
+from oracle import formats as F
+from tests.helpers import random_sky, relerr, tol
+
+pytestmark = pytest.mark.gpu
+
+SKY_CASES = [
+    # rows, cols, l, u   (scalars = BlockBandedMatrix, vectors = ragged BlockSkylineMatrix)
+    (list(range(1, 11)), list(range(1, 11)), 1, 1),                               # test/test_linalg.jl:35-57
+    ([256] * 6, [256] * 6, 2, 2),                                                 # cfg4-like
+    ([1, 2, 3, 4], [1, 2, 3, 4], 1, 1),                                           # test/test_blockbanded.jl:59-90
+    ([5, 3, 7, 2, 6], [4, 6, 2, 5, 3, 7], 1, 2),                                  # rectangular
+    ([3] * 7, [3] * 7, [2, 1, 2, 3, 1, 0, 0], [0, 1, 1, 2, 3, 1, 2]),             # ragged (test/test_blockskyline.jl:17-19)
+    ([3] * 7, [3] * 7, [-1, 1, 2, 0, 1, 0, 0], [1, 1, 0, 2, -1, 1, 2]),           # ragged with negative entries
+    ([2, 2], [2, 2, 2], 0, 1),                                                    # test/test_blockbanded.jl:213-221
+    ([], [], 1, 1),
+    ([4, 0, 5, 3], [4, 0, 5, 3], 1, 1),                                           # empty blocks
+    ([130, 7, 260, 129], [64, 200, 31, 150], 2, 1),                               # blocks spanning several tiles
+    ([6] * 5, [6] * 5, -1, 2),                                                    # band above the diagonal
+]
+
+
+@pytest.fixture(scope="module")
+def handle():
+    h = B.Handle(0)
+    yield h
+    h.close()
+
+
+def ids(c):
+    return f"r{len(c[0])}c{len(c[1])}"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", SKY_CASES, ids=ids)
+def test_sky_mul_matches_oracle(handle, case, dtype):
+    rows, cols, l, u = case
+    rng = np.random.default_rng(3)
+    data = random_sky(rng, rows, cols, l, u, dtype)
+    A = B.BlockSkylineMatrix(data, rows, cols, l, u)
+    Ad = A.to_device(handle)
+    m, n = A.shape
+    nnz = int(max(A.block_strides.max() if len(A.cols) else 0, 1)) * 3
+    for nrhs, alpha, beta in [(None, 1.0, 0.0), (None, 2.5, -0.5), (3, 1.0, 1.0), (11, -1.0, 0.0)]:
+        xs = (n,) if nrhs is None else (n, nrhs)
+        ys = (m,) if nrhs is None else (m, nrhs)
+        X = np.asfortranarray(rng.standard_normal(xs).astype(dtype))
+        Y0 = np.asfortranarray(rng.standard_normal(ys).astype(dtype))
+        Yin = Y0.copy(order="F")
+        if beta == 0:
+            Yin[...] = np.nan  # test/test_blockskyline.jl:34-39
+        dX, dY = handle.to_device(X), handle.to_device(Yin)
+        B.mul_(dY, Ad, dX, alpha, beta)
+        got = dY.to_host()
+        ref = Y0.copy(order="F")
+        O.sky_mul(rows, cols, l, u, alpha, data, X, beta, ref)
+        assert not np.isnan(got).any()
+        assert relerr(got, ref) <= tol(dtype, nnz)
+
+
+def product_structure(A, Bm):
+    l, u = B.add_bandwidths(A, Bm)
+    return l, u
+
+
+@pytest.mark.parametrize("kernel", [0, 2], ids=["dmma", "simt"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", [c for c in SKY_CASES if len(c[0]) == len(c[1])], ids=ids)
+def test_sky_matmul_matches_oracle(handle, case, dtype, kernel):
+    rows, cols, l, u = case
+    if list(rows) != list(cols):
+        pytest.skip("A*A needs matching axes")
+    handle.set_option("sky.mm_kernel", kernel)
+    try:
+        rng = np.random.default_rng(4)
+        adata = random_sky(rng, rows, cols, l, u, dtype)
+        bdata = random_sky(rng, rows, cols, l, u, dtype)
+        A = B.BlockSkylineMatrix(adata, rows, cols, l, u)
+        Bm = B.BlockSkylineMatrix(bdata, rows, cols, l, u)
+        Ad, Bd = A.to_device(handle), Bm.to_device(handle)
+        # A*B allocates the result with the reference's structure rule (src/linalg.jl:8-48)
+        Cd = B.mul(Ad, Bd)
+        cl, cu = product_structure(A, Bm)
+        ol, ou = F.add_bandwidths(A.l, A.u, Bm.l, Bm.u, constant=A.constant_bandwidths and Bm.constant_bandwidths)
+        assert list(np.broadcast_to(cl, len(cols))) == list(ol) and list(np.broadcast_to(cu, len(cols))) == list(ou)
+        got = Cd.data.to_host()
+        ref = np.zeros_like(got)
+        O.sky_matmul((rows, cols, l, u), (rows, cols, l, u), (rows, cols, ol, ou), 1.0, adata, bdata, 0.0, ref)
+        inner = int(max(A.block_strides.max() if len(cols) else 0, 1)) * 2
+        assert not np.isnan(got).any()
+        assert relerr(got, ref) <= tol(dtype, inner)
+        # dense cross-check (independent of the oracle's loops)
+        if A.shape[0] and A.shape[0] <= 600:
+            dense = A.to_dense().astype(np.longdouble) @ Bm.to_dense().astype(np.longdouble)
+            assert relerr(Cd.to_dense(), dense) <= tol(dtype, inner)
+        # mul! with alpha, beta into the existing C
+        c0 = rng.standard_normal(got.shape).astype(dtype)
+        Cd2 = B.BlockSkylineMatrix(handle.to_device(c0), rows, cols, ol, ou)
+        B.mul_(Cd2, Ad, Bd, -1.5, 0.75)
+        ref2 = c0.copy()
+        O.sky_matmul((rows, cols, l, u), (rows, cols, l, u), (rows, cols, ol, ou), -1.5, adata, bdata, 0.75, ref2)
+        assert relerr(Cd2.data.to_host(), ref2) <= tol(dtype, inner)
+    finally:
+        handle.set_option("sky.mm_kernel", 0)
+
+
+def test_sky_matmul_into_wider_c_and_band_error(handle):
+    """test/test_blockbanded.jl:213-221: mul!(C, A, B) into a preallocated wider-banded C; a C that is
+    too narrow is a BandError (src/BlockSkylineMatrix.jl:491)."""
+    rows, cols = [2, 2], [2, 2]
+    A = B.BlockSkylineMatrix(np.ones(B.BlockSkylineMatrix.numentries(rows, cols, 0, 1)), rows, cols, 0, 1).to_device(handle)
+    Bm = B.BlockSkylineMatrix(np.ones(B.BlockSkylineMatrix.numentries(rows, cols, 1, 0)), rows, cols, 1, 0).to_device(handle)
+    Cw = B.BlockSkylineMatrix(np.full(B.BlockSkylineMatrix.numentries(rows, cols, 1, 1), np.nan), rows, cols, 1, 1).to_device(handle)
+    B.mul_(Cw, A, Bm)
+    dense = A.to_dense() @ Bm.to_dense()
+    assert np.array_equal(Cw.to_dense(), dense)
+    Cn = B.BlockSkylineMatrix.zeros(np.float64, rows, cols, 0, 0).to_device(handle)
+    with pytest.raises(B.BandError):
+        B.mul_(Cn, A, Bm)
+    with pytest.raises(B.DimensionMismatch):
+        B.mul_(Cw, A, B.BlockSkylineMatrix.zeros(np.float64, [2, 2, 2], cols, 1, 1).to_device(handle))
+
+
+def test_sky_matmul_ragged_all_ones_exact(handle):
+    """test/test_blockskyline.jl:42-81: ragged M*M on all-ones data is exact, product bandwidths follow
+    add_bandwidths."""
+    rows = cols = [3] * 7
+    l, u = [2, 1, 2, 3, 1, 0, 0], [0, 1, 1, 2, 3, 1, 2]
+    n = B.BlockSkylineMatrix.numentries(rows, cols, l, u)
+    M = B.BlockSkylineMatrix(np.ones(n), rows, cols, l, u)
+    Md = M.to_device(handle)
+    MM = B.mul(Md, Md)
+    dense = M.to_dense() @ M.to_dense()
+    assert np.array_equal(MM.to_dense(), dense)
+
+
+TRI_CASES = [
+    # rows, l, u
+    (list(range(1, 11)), 1, 1),        # test/test_linalg.jl:59-76
+    ([64] * 8, 0, 3),                  # cfg5-like
+    ([64] * 8, 3, 0),
+    ([40, 7, 100, 33, 1, 65], 2, 2),
+    ([512, 300], 1, 1),                # diagonal blocks spanning many 32-row sub-blocks
+    ([5, 0, 6, 3], 1, 2),
+    ([3] * 7, [2, 1, 2, 3, 1, 0, 0], [0, 1, 1, 2, 3, 1, 2]),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
+@pytest.mark.parametrize("case", TRI_CASES, ids=lambda c: f"N{len(c[0])}")
+def test_sky_trsm_matches_oracle(handle, case, uplo, unit, dtype):
+    rows, l, u = case
+    rng = np.random.default_rng(8)
+    A = B.BlockSkylineMatrix.zeros(dtype, rows, rows, l, u)
+    m = A.shape[0]
+    # well conditioned: N(0,1)/sqrt(m) off the diagonal, +10 on the global diagonal
+    data = (rng.standard_normal(A.data.shape) / np.sqrt(max(m, 1))).astype(dtype)
+    A = B.BlockSkylineMatrix(data, rows, rows, l, u)
+    for K in range(len(rows)):
+        s, ld = A.block_start(K, K), int(A.block_strides[K])
+        for i in range(rows[K]):
+            data[s + i + i * ld] += 10
+    Ad = A.to_device(handle)
+    T = {"U": (B.UnitUpperTriangular if unit else B.UpperTriangular),
+         "L": (B.UnitLowerTriangular if unit else B.LowerTriangular)}[uplo](Ad)
+    for nrhs in (None, 5, 64):
+        shape = (m,) if nrhs is None else (m, nrhs)
+        B0 = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+        dB = handle.to_device(B0)
+        out = B.ldiv_(T, dB)
+        assert out is dB
+        got = dB.to_host()
+        ref = B0.copy(order="F")
+        O.sky_trsm(rows, l, u, uplo, unit, data, ref)
+        assert not np.isnan(got).any()
+        assert relerr(got, ref) <= tol(dtype, max(m, 1))
+    # residual check against the dense triangle (independent of the oracle)
+    if m:
+        D = A.to_dense().astype(np.float64)
+        Tm = np.triu(D) if uplo == "U" else np.tril(D)
+        if unit:
+            np.fill_diagonal(Tm, 1.0)
+        X = B.ldiv(T, handle.to_device(B0)).to_host().astype(np.float64)
+        assert relerr(Tm @ X, B0.astype(np.float64)) <= tol(dtype, m) * 4
+
+
+def test_sky_trsm_errors(handle):
+    A = B.BlockSkylineMatrix.zeros(np.float64, [3, 4], [4, 3], 1, 1).to_device(handle)
+    with pytest.raises(B.BBMError):   # no matching square diagonal blocks: not taken by the device path
+        B.ldiv_(B.UpperTriangular(A), handle.empty(7, np.float64))
+    A2 = B.BlockSkylineMatrix.zeros(np.float64, [3, 3, 3], [3, 3, 3], -1, 2).to_device(handle)
+    with pytest.raises(B.BandError):  # diagonal blocks not stored
+        B.ldiv_(B.UpperTriangular(A2), handle.empty(9, np.float64))
+    A3 = B.BlockSkylineMatrix.zeros(np.float64, [3, 3], [3, 3], 1, 1).to_device(handle)
+    with pytest.raises(B.DimensionMismatch):
+        B.ldiv_(B.UpperTriangular(A3), handle.empty(5, np.float64))
+
+
+def test_sky_layout_matches_host_container(handle):
+    """Device descriptor's panel table == the host container's block_starts / block_strides."""
+    import ctypes as C
+    rows, cols = [1, 2, 3, 4], [1, 2, 3, 4]
+    A = B.BlockBandedMatrix(np.arange(1, 71, dtype=np.float64), rows, cols, (1, 1)).to_device(handle)
+    d = A.descriptor(handle)
+    off = np.zeros(5, dtype=np.int64); S = np.zeros(4, dtype=np.int64)
+    klo = np.zeros(4, dtype=np.int64); khi = np.zeros(4, dtype=np.int64)
+    assert handle._lib.bbm_sky_desc_layout(d, off.ctypes.data_as(C.c_void_p), S.ctypes.data_as(C.c_void_p),
+                                           klo.ctypes.data_as(C.c_void_p), khi.ctypes.data_as(C.c_void_p)) == 0
+    assert list(S) == list(A.block_strides) == [3, 6, 9, 7]      # strides (1,7) of Block(4,4): test/test_linalg.jl:42-47
+    assert list(off) == list(A.panel_offsets)
+    assert off[3] + (A.R[3] - A.R[klo[3]]) == 45                 # first element of Block(4,4) is data[46] (1-based)
