@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Secondary measurements: every BASELINE.json config at FULL size on one B200, each with a parity
+check (against the CPU oracle where the oracle finishes in seconds, through size-independent
+properties otherwise) and a roofline line.  bench.py stays the headline (cfg2); this script feeds
+DESIGN.md's per-kernel table.
+
+  python benchmarks/configs.py [--configs 1,2,3,4,5] [--reps 10] [--no-oracle]
+
+One JSON line per config on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+EPS = {8: 2.220446049250313e-16, 4: 1.1920929e-07}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def relerr(a, b):
+    den = float(np.linalg.norm(np.asarray(b, dtype=np.float64).ravel()))
+    return float(np.linalg.norm((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).ravel())) / max(den, 1e-300)
+
+
+def time_gpu(torch, stream, fn, reps, warm=3):
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record(stream)
+        for i in range(reps):
+            fn()
+            ev[i + 1].record(stream)
+        torch.cuda.synchronize()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+    return float(np.mean(per)), float(np.min(per))
+
+
+def dgemm_peak(torch, n=8192, reps=5):
+    """cuBLAS FP64 GEMM throughput on this GPU = the tensor roofline's denominator for cfg4/cfg5."""
+    a = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    b = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def wrap(B, h, t):
+    """DeviceArray view of a torch tensor's memory (column-major interpretation by the caller)."""
+    d = B.DeviceArray(h, tuple(reversed(t.shape)) if t.dim() == 2 else tuple(t.shape), np.dtype(str(t.dtype).replace("torch.", "")), ptr=t.data_ptr())
+    d._keep = t
+    return d
+
+
+def run_bbb(torch, B, h, stream, name, rows, cols, lu, lm, dtype, reps, oracle, laplacian=None):
+    dt = np.dtype(dtype)
+    P = max(0, lu[0] + lu[1] + 1) * max(0, lm[0] + lm[1] + 1)
+    n, m = int(np.sum(cols)), int(np.sum(rows))
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    gen = torch.Generator(device="cuda").manual_seed(1003)
+    if laplacian is not None:
+        col = torch.tensor([0, 1, 0, 1, -4, 1, 0, 1, 0], dtype=tdt, device="cuda") * float(laplacian) ** 2
+        data_t = col.repeat(n, 1).contiguous()            # n x P row-major == P x n column-major
+    else:
+        data_t = torch.randn(n, P, generator=gen, device="cuda", dtype=tdt)
+    x_t = torch.randn(n, generator=gen, device="cuda", dtype=tdt)
+    y_t = torch.full((m,), float("nan"), device="cuda", dtype=tdt)
+    A = B.BandedBlockBandedMatrix(wrap(B, h, data_t), rows, cols, lu, lm)
+    dx, dy = wrap(B, h, x_t), wrap(B, h, y_t)
+    avg, best = time_gpu(torch, stream, lambda: B.mul_(dy, A, dx), reps)
+    nbytes = dt.itemsize * (P * n + n + m)
+    nnz = (lu[0] + lu[1] + 1) * (lm[0] + lm[1] + 1)
+    out = {"config": name, "dtype": str(dt), "unknowns": m, "ms_avg": avg, "ms_min": best,
+           "algorithmic_bytes": nbytes, "GBps": nbytes / (avg * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "peak_GBps": peaks(), "frac": nbytes / (avg * 1e-3) / 1e9 / peaks()},
+           "tolerance": 64 * EPS[dt.itemsize] * nnz}
+    y = y_t.cpu().numpy()
+    if oracle:
+        from oracle import cpu as O
+        O.use_openblas(threads=1)
+        data = np.asfortranarray(data_t.cpu().numpy().T)
+        ref = np.zeros(m, dtype=dt)
+        t0 = time.perf_counter()
+        O.bbb_mul(rows, cols, lu[0], lu[1], lm[0], lm[1], 1.0, data, x_t.cpu().numpy(), 0.0, ref)
+        out["cpu_seconds_full_size"] = time.perf_counter() - t0
+        out["cpu_GBps"] = nbytes / out["cpu_seconds_full_size"] / 1e9
+        out["rel_err_vs_oracle_full_size"] = relerr(y, ref)
+        out["parity_ok"] = bool(out["rel_err_vs_oracle_full_size"] <= out["tolerance"])
+    else:  # linearity
+        x2 = torch.randn(n, generator=gen, device="cuda", dtype=tdt)
+        y2 = torch.empty_like(y_t); y12 = torch.empty_like(y_t)
+        B.mul_(wrap(B, h, y2), A, wrap(B, h, x2))
+        B.mul_(wrap(B, h, y12), A, wrap(B, h, (2.0 * x_t - 3.0 * x2).contiguous()))
+        h.synchronize()
+        out["linearity_rel_err"] = relerr(y12.cpu().numpy(), (2.0 * y_t - 3.0 * y2).cpu().numpy())
+        out["parity_ok"] = bool(out["linearity_rel_err"] <= 4 * out["tolerance"])
+    return out
+
+
+def run_cfg4(torch, B, h, stream, reps, oracle, nblk=2048, bs=256, peak_tf=None):
+    rows = [bs] * nblk
+    gen = torch.Generator(device="cuda").manual_seed(1004)
+    nA = B.BlockSkylineMatrix.numentries(rows, rows, 2, 2)
+    nC = B.BlockSkylineMatrix.numentries(rows, rows, 4, 4)
+    a_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / 16
+    b_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / 16
+    c_t = torch.full((nC,), float("nan"), device="cuda", dtype=torch.float64)
+    A = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, 2, 2)
+    Bm = B.BlockSkylineMatrix(wrap(B, h, b_t), rows, rows, 2, 2)
+    Cm = B.BlockSkylineMatrix(wrap(B, h, c_t), rows, rows, 4, 4)
+    assert B.add_bandwidths(A, Bm) == (4, 4)
+    avg, best = time_gpu(torch, stream, lambda: B.mul_(Cm, A, Bm), reps, warm=2)
+    # flops: sum over (J, N in colsupport(B,J), K in colsupport(A,N)) of 2*bs^3
+    triples = 0
+    for J in range(nblk):
+        for N in range(max(0, J - 2), min(nblk - 1, J + 2) + 1):
+            triples += min(nblk - 1, N + 2) - max(0, N - 2) + 1
+    flops = 2.0 * bs ** 3 * triples
+    nbytes = 8 * (2 * nA + nC)
+    out = {"config": f"cfg4: BlockBandedMatrix {nblk} blocks of {bs}, (2,2) x (2,2) -> (4,4), Float64", "ms_avg": avg, "ms_min": best,
+           "block_triples": triples, "flops": flops, "TFLOPs": flops / (avg * 1e-3) / 1e12, "algorithmic_bytes": nbytes,
+           "GBps": nbytes / (avg * 1e-3) / 1e9, "tolerance": 64 * EPS[8] * 5 * bs}
+    if peak_tf:
+        out["roofline"] = {"bound": "tensor(fp64)", "peak_TFLOPs": peak_tf, "peak_source": "torch.matmul float64 8192^3 (cuBLAS DGEMM) measured in this run",
+                           "frac": out["TFLOPs"] / peak_tf}
+    # parity: a sample of C blocks against float64 block products computed by numpy on the host
+    rng = np.random.default_rng(7)
+    h.synchronize()
+    worst = 0.0
+    for _ in range(6):
+        J = int(rng.integers(0, nblk))
+        K = int(rng.integers(max(0, J - 4), min(nblk - 1, J + 4) + 1))
+        ref = np.zeros((bs, bs))
+        for N in range(max(0, J - 2), min(nblk - 1, J + 2) + 1):
+            if abs(K - N) <= 2:
+                sa, la = A.block_start(K, N), int(A.block_strides[N])
+                sb, lb = Bm.block_start(N, J), int(Bm.block_strides[J])
+                Ab = a_t[sa:sa + la * bs].cpu().numpy().reshape((la, bs), order="F")[:bs]
+                Bb = b_t[sb:sb + lb * bs].cpu().numpy().reshape((lb, bs), order="F")[:bs]
+                ref += Ab @ Bb
+        sc, lc = Cm.block_start(K, J), int(Cm.block_strides[J])
+        got = c_t[sc:sc + lc * bs].cpu().numpy().reshape((lc, bs), order="F")[:bs]
+        worst = max(worst, relerr(got, ref) if np.linalg.norm(ref) else float(np.abs(got).max()))
+    out["rel_err_sampled_blocks_vs_numpy"] = worst
+    out["nan_in_C"] = bool(torch.isnan(c_t).any().item())
+    out["parity_ok"] = bool(worst <= out["tolerance"] and not out["nan_in_C"])
+    return out
+
+
+def run_cfg5(torch, B, h, stream, reps, oracle, nblk=1024, bs=512, nrhs=64, peak_tf=None):
+    rows = [bs] * nblk
+    m = bs * nblk
+    gen = torch.Generator(device="cuda").manual_seed(1005)
+    nA = B.BlockSkylineMatrix.numentries(rows, rows, 0, 3)
+    a_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / np.sqrt(bs)
+    A = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, 0, 3)
+    # +10 on the global diagonal (well conditioned)
+    idx = torch.arange(bs, device="cuda", dtype=torch.int64)
+    for K in range(nblk):
+        s, ld = A.block_start(K, K), int(A.block_strides[K])
+        a_t[s + idx + idx * ld] += 10.0
+    b0 = torch.randn(nrhs, m, generator=gen, device="cuda", dtype=torch.float64)   # row-major (nrhs, m) == m x nrhs col-major
+    b_t = b0.clone()
+    dB = wrap(B, h, b_t)
+    T = B.UpperTriangular(A)
+
+    def step():
+        b_t.copy_(b0)
+        B.ldiv_(T, dB)
+
+    # time the copy alone and subtract (the solve is in place)
+    with torch.cuda.stream(stream):
+        cavg, _ = time_gpu(torch, stream, lambda: b_t.copy_(b0), 5, warm=1)
+    avg, best = time_gpu(torch, stream, step, reps, warm=1)
+    avg -= cavg; best -= cavg
+    trsm_flops = nblk * bs * bs * nrhs
+    upd_blocks = sum(min(3, K) for K in range(nblk))
+    flops = trsm_flops + 2.0 * upd_blocks * bs * bs * nrhs
+    nbytes = 8 * (nA + 2 * m * nrhs)
+    out = {"config": f"cfg5: UpperTriangular BlockBandedMatrix {nblk} blocks of {bs}, (0,3), {nrhs} RHS, Float64 ldiv!",
+           "ms_avg": avg, "ms_min": best, "us_per_block_step": avg * 1e3 / nblk, "flops": flops, "TFLOPs": flops / (avg * 1e-3) / 1e12,
+           "algorithmic_bytes": nbytes, "GBps": nbytes / (avg * 1e-3) / 1e9, "tolerance": 64 * EPS[8] * 4 * bs,
+           "roofline": {"bound": "latency chain (1024 sequential block steps); stream 1x matrix + tensor flops as lower bounds",
+                        "hbm_frac": nbytes / (avg * 1e-3) / 1e9 / peaks(), "fp64_frac": (flops / (avg * 1e-3) / 1e12 / peak_tf) if peak_tf else None}}
+    h.synchronize()
+    X = b_t.cpu().numpy()          # (nrhs, m): row q = solution of column q
+    if oracle:
+        from oracle import cpu as O
+        O.use_openblas(threads=os.cpu_count() or 1)
+        data = a_t.cpu().numpy()
+        ncheck = 2
+        ref = np.asfortranarray(b0[:ncheck].cpu().numpy().T.copy())
+        t0 = time.perf_counter()
+        O.sky_trsm(rows, 0, 3, "U", False, data, ref)
+        dtc = time.perf_counter() - t0
+        out["cpu_seconds_per_rhs_column"] = dtc / ncheck
+        out["cpu_seconds_64_columns_extrapolated"] = dtc / ncheck * nrhs
+        out["rel_err_vs_oracle_full_size_2cols"] = relerr(X[:ncheck].T, ref)
+        out["parity_ok"] = bool(out["rel_err_vs_oracle_full_size_2cols"] <= out["tolerance"])
+    else:
+        out["parity_ok"] = bool(np.isfinite(X).all())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,3,4,5")
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--no-oracle", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import bbm_b200 as B
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    h = B.Handle(0, stream=stream.cuda_stream)
+    want = set(args.configs.split(","))
+    oracle = not args.no_oracle
+    peak_tf = dgemm_peak(torch) if want & {"4", "5"} else None
+    if peak_tf:
+        print(json.dumps({"measured": "cuBLAS DGEMM 8192^3 via torch.matmul", "TFLOPs": peak_tf}), flush=True)
+    if "1" in want:
+        r = [100] * 100
+        print(json.dumps(run_bbb(torch, B, h, stream, "cfg1: Laplacian BBB 100x100 blocks of 100, F64 (L2-resident: latency, not a roofline)", r, r, (1, 1), (1, 1), np.float64, 200, oracle, laplacian=100)), flush=True)
+    if "2" in want:
+        r = [4096] * 4096
+        print(json.dumps(run_bbb(torch, B, h, stream, "cfg2: Laplacian BBB 4096 blocks of 4096, F64", r, r, (1, 1), (1, 1), np.float64, args.reps, oracle, laplacian=4096)), flush=True)
+    if "3" in want:
+        r = list(range(1, 4001))
+        for dt in (np.float64, np.float32):
+            print(json.dumps(run_bbb(torch, B, h, stream, "cfg3: BBB rows=cols=1:4000, (2,2),(2,2)", r, r, (2, 2), (2, 2), dt, args.reps, oracle)), flush=True)
+    if "4" in want:
+        print(json.dumps(run_cfg4(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
+    if "5" in want:
+        print(json.dumps(run_cfg5(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

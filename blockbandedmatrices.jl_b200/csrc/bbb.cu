@@ -292,45 +292,74 @@ void walk_stage_bytes(int tile, int w, i64 P, int* dbytes, int* xbytes) {
     *xbytes = (int)((x + 15) & ~size_t(15));
 }
 
-// Split the (tile, block-row) work into items of about equal weight.  A tile t covers in-block
-// rows [t*T, (t+1)*T); only block rows with r[K] > t*T take part, in maximal runs.
-int32_t build_partition(bbm_bbb_desc_t d, int tile, int target_items, int maxseg_cap, Partition* out) {
+// Split the (tile, block-row) work into at most `slots` items of about equal weight, `slots` being a
+// whole number of waves of resident CTAs (measured on B200: 1 wave beats 1.5 or 3.03 waves by
+// 20-30%, a partial last wave cannot saturate HBM).  A tile t covers in-block rows [t*T, (t+1)*T);
+// only block rows with r[K] > t*T take part, in maximal runs; every run gets a share of the slots
+// proportional to its weight and is cut into that many segments of equal weight.
+int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, Partition* out) {
     bbm_handle_t h = d->h;
     const i64 Nr = d->Nr;
-    const int NS = (int)(d->l + d->u + 1);
-    const i64 ovh = 16;
-    struct Run { int t; i64 Ka, Kb; double wt; };
+    const i64 ovh = 16;  // per-step cost that does not shrink with the tile's height
+    struct Run { int t; i64 Ka, Kb; double wt; int nseg; };
     std::vector<Run> runs;
     const i64 ntiles = (d->maxr + tile - 1) / tile;
     double total = 0;
+    auto weight = [&](i64 K, i64 k0) { return (double)(std::min<i64>(tile, d->r[K] - k0) + ovh); };
     for (i64 t = 0; t < ntiles; ++t) {
         const i64 k0 = t * tile;
         i64 K = 0;
         while (K < Nr) {
             if (d->r[K] <= k0) { ++K; continue; }
-            Run run{(int)t, K, K, 0.0};
-            while (K < Nr && d->r[K] > k0) { run.wt += (double)(std::min<i64>(tile, d->r[K] - k0) + ovh); ++K; }
+            Run run{(int)t, K, K, 0.0, 1};
+            while (K < Nr && d->r[K] > k0) { run.wt += weight(K, k0); ++K; }
             run.Kb = K;
             total += run.wt;
             runs.push_back(run);
         }
     }
+    // segments per run: proportional share of the slots, at least what the table size demands, at
+    // most one per block row; leftovers go to the runs whose segments are heaviest
+    i64 used = 0;
+    for (Run& run : runs) {
+        const i64 len = run.Kb - run.Ka;
+        i64 n = (i64)((double)slots * run.wt / std::max(total, 1.0));
+        n = std::max<i64>(n, (len + maxseg_cap - 1) / maxseg_cap);
+        n = std::min<i64>(std::max<i64>(n, 1), len);
+        run.nseg = (int)n;
+        used += n;
+    }
+    while (used < slots) {
+        Run* best = nullptr;
+        for (Run& run : runs)
+            if (run.nseg < run.Kb - run.Ka && (!best || run.wt / run.nseg > best->wt / best->nseg)) best = &run;
+        if (!best) break;
+        ++best->nseg;
+        ++used;
+    }
     std::vector<BbbItem> items;
-    const double target = std::max(total / std::max(1, target_items), 1.0);
-    const i64 minlen = std::max<i64>(1, 8 * (NS - 1));  // keep the (NS-1)-step ramp under ~12%
     int maxseg = 1;
     for (const Run& run : runs) {
+        const i64 k0 = (i64)run.t * tile;
         i64 Ka = run.Ka;
-        while (Ka < run.Kb) {
-            double acc = 0;
+        double done = 0;
+        for (int sidx = 0; sidx < run.nseg && Ka < run.Kb; ++sidx) {
+            const double goal = run.wt * (sidx + 1) / run.nseg;
             i64 Kb = Ka;
-            const i64 k0 = (i64)run.t * tile;
-            while (Kb < run.Kb && (Kb - Ka) < maxseg_cap && (acc < target || (Kb - Ka) < minlen)) {
-                acc += (double)(std::min<i64>(tile, d->r[Kb] - k0) + ovh);
+            const i64 must_leave = run.nseg - 1 - sidx;  // one block row at least for every later segment
+            while (Kb < run.Kb - must_leave && (Kb == Ka || done + 0.5 * weight(Kb, k0) <= goal) && (Kb - Ka) < maxseg_cap) {
+                done += weight(Kb, k0);
                 ++Kb;
             }
-            // do not leave a sliver behind
-            if (run.Kb - Kb < minlen / 2 && (run.Kb - Ka) <= maxseg_cap) Kb = run.Kb;
+            if (sidx == run.nseg - 1) {
+                // last segment takes the rest (split further only if the table size forces it)
+                while (run.Kb - Ka > maxseg_cap) {
+                    items.push_back(BbbItem{(int32_t)Ka, (int32_t)(Ka + maxseg_cap), (int32_t)k0, 0});
+                    maxseg = std::max(maxseg, maxseg_cap);
+                    Ka += maxseg_cap;
+                }
+                Kb = run.Kb;
+            }
             items.push_back(BbbItem{(int32_t)Ka, (int32_t)Kb, (int32_t)k0, 0});
             maxseg = std::max<int>(maxseg, (int)(Kb - Ka));
             Ka = Kb;
@@ -352,11 +381,13 @@ int32_t build_partition(bbm_bbb_desc_t d, int tile, int target_items, int maxseg
     return BBM_OK;
 }
 
+// grid.x == 0: do not launch, report the resident CTAs per SM for (tile, smem) in *occ instead
 template <typename T, int NS>
-cudaError_t launch_walk_w(const BbbParams<T>& p, int w, dim3 grid, int tile, size_t smem, cudaStream_t st) {
+cudaError_t launch_walk_w(const BbbParams<T>& p, int w, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ) {
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        if (grid.x == 0) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, tile, smem);
         kern<<<grid, tile, smem, st>>>(p);
         return cudaGetLastError();
     };
@@ -366,16 +397,16 @@ cudaError_t launch_walk_w(const BbbParams<T>& p, int w, dim3 grid, int tile, siz
 }
 
 template <typename T>
-cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, dim3 grid, int tile, size_t smem, cudaStream_t st) {
+cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ = nullptr) {
     switch (NS) {
-        case 1: return launch_walk_w<T, 1>(p, w, grid, tile, smem, st);
-        case 2: return launch_walk_w<T, 2>(p, w, grid, tile, smem, st);
-        case 3: return launch_walk_w<T, 3>(p, w, grid, tile, smem, st);
-        case 4: return launch_walk_w<T, 4>(p, w, grid, tile, smem, st);
-        case 5: return launch_walk_w<T, 5>(p, w, grid, tile, smem, st);
-        case 6: return launch_walk_w<T, 6>(p, w, grid, tile, smem, st);
-        case 7: return launch_walk_w<T, 7>(p, w, grid, tile, smem, st);
-        case 8: return launch_walk_w<T, 8>(p, w, grid, tile, smem, st);
+        case 1: return launch_walk_w<T, 1>(p, w, grid, tile, smem, st, occ);
+        case 2: return launch_walk_w<T, 2>(p, w, grid, tile, smem, st, occ);
+        case 3: return launch_walk_w<T, 3>(p, w, grid, tile, smem, st, occ);
+        case 4: return launch_walk_w<T, 4>(p, w, grid, tile, smem, st, occ);
+        case 5: return launch_walk_w<T, 5>(p, w, grid, tile, smem, st, occ);
+        case 6: return launch_walk_w<T, 6>(p, w, grid, tile, smem, st, occ);
+        case 7: return launch_walk_w<T, 7>(p, w, grid, tile, smem, st, occ);
+        case 8: return launch_walk_w<T, 8>(p, w, grid, tile, smem, st, occ);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -440,8 +471,19 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     }
 
     if (walk) {
-        const int target_items = h->num_sms * (int)std::max<i64>(1, bbm_opt(h, "bbb.items_per_sm", 6));
+        walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
         const int maxseg_cap = (int)std::min<i64>(512, std::max<i64>(1, bbm_opt(h, "bbb.maxseg", 512)));
+        // slots = whole waves of resident CTAs (table size taken at its cap: a few KB either way)
+        int occ = 1;
+        {
+            const size_t smem_cap = walk_tab_bytes(maxseg_cap, (int)NS) + (size_t)stages * ((size_t)dbytes + xbytes);
+            cudaError_t e = launch_walk<T>(p, (int)NS, w, dim3(0, 1, 1), tile, smem_cap, h->stream, &occ);
+            if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
+            occ = std::max(1, occ);
+        }
+        const i64 ips = bbm_opt(h, "bbb.items_per_sm", 0);
+        const i64 waves = std::max<i64>(1, bbm_opt(h, "bbb.waves", 1));
+        const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves);
         auto key = std::make_pair(tile, target_items * 1024 + maxseg_cap);
         auto it = d->parts.find(key);
         if (it == d->parts.end()) {

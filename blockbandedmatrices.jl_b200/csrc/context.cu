@@ -4,7 +4,7 @@
 #include "bbm_internal.h"
 
 static const char* const kOptionKeys[] = {
-    "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint",
+    "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves",
     "sky.kernel", "sky.mm_kernel", "trsm.kernel", "dist.graph", nullptr};
 
 extern "C" {

@@ -61,7 +61,7 @@ int32_t bbm_destroy(bbm_handle_t h);
 int32_t bbm_set_stream(bbm_handle_t h, void* cuda_stream /* cudaStream_t, NULL = default */);
 int32_t bbm_synchronize(bbm_handle_t h);
 const char* bbm_last_error(bbm_handle_t h);
-/* tuning / diagnostics knobs ("bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.maxseg",
+/* tuning / diagnostics knobs ("bbb.tile", "bbb.stages", "bbb.waves", "bbb.items_per_sm", "bbb.maxseg",
  * "bbb.l2hint", "bbb.kernel": 0 auto, 1 band-walk, 2 generic; "dist.graph": 1 (default) replays a
  * CUDA graph of the whole multi-GPU step, 0 enqueues eagerly); unknown keys -> BBM_ERR_ARG.    */
 int32_t bbm_set_option(bbm_handle_t h, const char* key, int64_t value);

@@ -1,0 +1,188 @@
+# BlockBandedMatricesB200Ext — package extension that routes the reference's MulAdd / Ldiv lazy ops
+# to libbbm_b200.so when the matrix `data` lives in B200 memory.
+#
+# NOT EXECUTED IN THE BUILD IMAGE (no julia binary there): this file is the reference-side binding a
+# maintainer would add; every ccall below names an entry point declared in include/bbm_b200.h and
+# exercised through the same C ABI by the Python/ctypes harness of this repository.
+#
+# Activation, same mechanism as ext/BlockBandedMatricesSparseArraysExt.jl (Project.toml:13-17):
+#
+#   [weakdeps]
+#   BBMB200 = "<uuid of a 20-line stub package that only defines `const libbbm = \"/path/libbbm_b200.so\"`>"
+#   [extensions]
+#   BlockBandedMatricesB200Ext = "BBMB200"
+#
+# What stays host-side Julia (unchanged): the BlockBandedMatrix / BandedBlockBandedMatrix
+# constructors, block axes, blockbandwidths / subblockbandwidths, the MemoryLayout traits
+# (src/AbstractBlockBandedMatrix.jl:8-30, src/BandedBlockBandedMatrix.jl:263-269,
+# src/BlockSkylineMatrix.jl:369) and the MulAdd / Ldiv / materialize! dispatch of ArrayLayouts.
+# What moves: `data` (shape unchanged) and the arithmetic.
+module BlockBandedMatricesB200Ext
+
+using BlockBandedMatrices
+using BlockBandedMatrices: BandedBlockBandedMatrix, BlockSkylineMatrix, BandedBlockBandedColumns,
+                           BlockBandedColumns, blockbandwidths, subblockbandwidths, colblockbandwidths
+using BlockBandedMatrices.ArrayLayouts: MulAdd, Ldiv, TriangularLayout, MemoryLayout, DenseColumnMajor
+import BlockBandedMatrices.ArrayLayouts: materialize!, triangulardata
+using BlockBandedMatrices.BlockArrays: BlockedMatrix, blocklengths, blocksize
+using BlockBandedMatrices.BandedMatrices: BandError
+using LinearAlgebra
+import BBMB200: libbbm
+
+# ---- status codes (bbm_status, include/bbm_b200.h) -------------------------------------------
+const BBM_OK, BBM_ERR_DIM, BBM_ERR_BAND = Int32(0), Int32(2), Int32(3)
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:bbm_create, libbbm), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r)
+        rc == 0 || error("bbm_create failed: ", unsafe_string(ccall((:bbm_status_string, libbbm), Cstring, (Int32,), rc)),
+                         " (no CPU fallback: a B200 is required)")
+        h = new(r[])
+        finalizer(x -> ccall((:bbm_destroy, libbbm), Int32, (Ptr{Cvoid},), x.ptr), h)
+    end
+end
+const default_handle = Ref{Handle}()
+handle() = isassigned(default_handle) ? default_handle[] : (default_handle[] = Handle(0))
+
+function check(rc::Int32, h::Handle=handle())
+    rc == BBM_OK && return nothing
+    msg = unsafe_string(ccall((:bbm_last_error, libbbm), Cstring, (Ptr{Cvoid},), h.ptr))
+    rc == BBM_ERR_DIM  && throw(DimensionMismatch(msg))          # where [upstream] BlockArrays / src/linalg.jl:42,61 throw
+    rc == BBM_ERR_BAND && throw(BandError(nothing, 0))           # src/BlockSkylineMatrix.jl:491
+    error("libbbm_b200 [status $rc]: $msg")
+end
+
+# ---- device buffers: the storage type the extension's methods are keyed on ------------------
+"Dense column-major array in B200 memory (owned through bbm_malloc / bbm_free)."
+mutable struct B200Array{T,N} <: DenseArray{T,N}
+    ptr::Ptr{T}
+    dims::NTuple{N,Int}
+    function B200Array{T,N}(::UndefInitializer, dims::NTuple{N,Int}) where {T,N}
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bbm_malloc, libbbm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Csize_t), handle().ptr, r, sizeof(T) * prod(dims)))
+        a = new{T,N}(Ptr{T}(r[]), dims)
+        finalizer(x -> ccall((:bbm_free, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), handle().ptr, x.ptr), a)
+    end
+end
+const B200Vector{T} = B200Array{T,1}
+const B200Matrix{T} = B200Array{T,2}
+Base.size(a::B200Array) = a.dims
+Base.similar(a::B200Array{T}, ::Type{S}, dims::Dims{N}) where {T,S,N} = B200Array{S,N}(undef, dims)
+Base.unsafe_convert(::Type{Ptr{T}}, a::B200Array{T}) where T = a.ptr
+Base.strides(a::B200Array) = Base.size_to_strides(1, a.dims...)
+MemoryLayout(::Type{<:B200Array}) = DenseColumnMajor()
+Base.getindex(a::B200Array, i...) = error("scalar indexing of device memory; copy to the host with Array(a)")
+
+"One memcpy of the parent array, shape unchanged."
+function B200Array(a::Array{T,N}) where {T,N}
+    d = B200Array{T,N}(undef, size(a))
+    check(ccall((:bbm_memcpy_h2d, libbbm), Int32, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Csize_t), handle().ptr, d.ptr, a, sizeof(a)))
+    check(ccall((:bbm_synchronize, libbbm), Int32, (Ptr{Cvoid},), handle().ptr))
+    d
+end
+function Base.Array(d::B200Array{T,N}) where {T,N}
+    a = Array{T,N}(undef, size(d))
+    check(ccall((:bbm_memcpy_d2h, libbbm), Int32, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Csize_t), handle().ptr, a, d.ptr, sizeof(a)))
+    check(ccall((:bbm_synchronize, libbbm), Int32, (Ptr{Cvoid},), handle().ptr))
+    a
+end
+
+"Device-resident copy of a BandedBlockBandedMatrix: same axes and bandwidths, `data` parent in HBM."
+function b200(A::BandedBlockBandedMatrix{T}) where T<:Union{Float32,Float64}
+    l, u = blockbandwidths(A); λ, μ = subblockbandwidths(A)
+    data = BlockedMatrix(B200Array(Matrix(parent(A.data))), axes(A.data))
+    BlockBandedMatrices._BandedBlockBandedMatrix(data, A.raxis, (l, u), (λ, μ))
+end
+"Device-resident copy of a BlockSkylineMatrix / BlockBandedMatrix: same BlockSkylineSizes, `data` vector in HBM."
+b200(A::BlockSkylineMatrix{T}) where T<:Union{Float32,Float64} =
+    BlockBandedMatrices._BlockSkylineMatrix(B200Array(Vector(A.data)), A.block_sizes)
+
+const B200BBB{T} = BandedBlockBandedMatrix{T,<:BlockedMatrix{T,<:B200Matrix{T}}}
+const B200Sky{T} = BlockSkylineMatrix{T,<:B200Vector{T}}
+
+# ---- descriptors (cached per matrix structure) -----------------------------------------------
+const desc_cache = IdDict{Any,Ptr{Cvoid}}()
+function descriptor(A::B200BBB)
+    get!(desc_cache, A) do
+        r = Int64.(blocklengths(axes(A, 1))); c = Int64.(blocklengths(axes(A, 2)))
+        l, u = blockbandwidths(A); λ, μ = subblockbandwidths(A)
+        d = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bbm_bbb_desc_create, libbbm), Int32,
+                    (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Int64, Int64, Ref{Ptr{Cvoid}}),
+                    handle().ptr, length(r), length(c), r, c, l, u, λ, μ, d))
+        d[]
+    end
+end
+function descriptor(A::B200Sky)
+    get!(desc_cache, A) do
+        r = Int64.(blocklengths(axes(A, 1))); c = Int64.(blocklengths(axes(A, 2)))
+        l, u = colblockbandwidths(A)
+        d = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bbm_sky_desc_create, libbbm), Int32,
+                    (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                    handle().ptr, length(r), length(c), r, c, Vector{Int64}(l), Vector{Int64}(u), d))
+        d[]
+    end
+end
+
+suffix(::Type{Float64}) = :f64
+suffix(::Type{Float32}) = :f32
+ld(x::AbstractVecOrMat) = max(1, size(x, 1))
+
+# ---- mul!(y, A, x, α, β)  ==  materialize!(MulAdd(α, A, x, β, y)) ----------------------------
+# Replaces [upstream BlockArrays] materialize!(::MatMulVecAdd / ::MatMulMatAdd{<:AbstractBlockLayout,...})
+# and its one-BLAS-gbmv-per-block loop (SURVEY.md 3.1).  Field names M.α, M.A, M.B, M.β, M.C as in
+# src/linalg.jl:33,51.
+for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
+    @eval function materialize!(M::MulAdd{<:BandedBlockBandedColumns,<:Any,<:Any,$T,<:B200BBB{$T},<:B200Array{$T},<:B200Array{$T}})
+        A, x, y = M.A, M.B, M.C
+        size(A, 2) == size(x, 1) && size(A, 1) == size(y, 1) && size(x, 2) == size(y, 2) ||
+            throw(DimensionMismatch("A has size $(size(A)), x has size $(size(x)), y has size $(size(y))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_mul_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
+                    handle().ptr, descriptor(A), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
+        y
+    end
+    # host vectors with a device-resident matrix: one call that uploads x, multiplies and downloads y
+    @eval function materialize!(M::MulAdd{<:BandedBlockBandedColumns,<:Any,<:Any,$T,<:B200BBB{$T},<:StridedVecOrMat{$T},<:StridedVecOrMat{$T}})
+        A, x, y = M.A, M.B, M.C
+        size(A, 2) == size(x, 1) && size(A, 1) == size(y, 1) && size(x, 2) == size(y, 2) ||
+            throw(DimensionMismatch("A has size $(size(A)), x has size $(size(x)), y has size $(size(y))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_mul_host_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
+                    handle().ptr, descriptor(A), M.α, parent(A.data).ptr, x, stride(x, 2), size(x, 2), M.β, y, stride(y, 2)))
+        y
+    end
+    @eval function materialize!(M::MulAdd{<:BlockBandedColumns,<:Any,<:Any,$T,<:B200Sky{$T},<:B200Array{$T},<:B200Array{$T}})
+        A, x, y = M.A, M.B, M.C
+        size(A, 2) == size(x, 1) && size(A, 1) == size(y, 1) && size(x, 2) == size(y, 2) ||
+            throw(DimensionMismatch("A has size $(size(A)), x has size $(size(x)), y has size $(size(y))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_sky_mul_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
+                    handle().ptr, descriptor(A), M.α, A.data.ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
+        y
+    end
+    # C <- α A B + β C, all block-skyline (result structure from similar(::MulAdd), src/linalg.jl:32-48,
+    # which returns a B200-backed BlockSkylineMatrix because `similar(::B200Vector)` is a B200Vector)
+    @eval function materialize!(M::MulAdd{<:BlockBandedColumns,<:BlockBandedColumns,<:BlockBandedColumns,$T,<:B200Sky{$T},<:B200Sky{$T},<:B200Sky{$T}})
+        check(ccall(($(QuoteNode(Symbol("bbm_sky_matmul_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, $T, Ptr{$T}),
+                    handle().ptr, descriptor(M.A), descriptor(M.B), descriptor(M.C), M.α, M.A.data.ptr, M.B.data.ptr, M.β, M.C.data.ptr))
+        M.C
+    end
+    # ldiv!(UpperTriangular(A), B) etc.  ==  materialize!(Ldiv(U, B)); callers: src/blockskylineqr.jl:136-155
+    @eval function materialize!(L::Ldiv{<:TriangularLayout{UPLO,UNIT,<:BlockBandedColumns},<:Any,<:AbstractTriangular{$T,<:B200Sky{$T}},<:B200Array{$T}}) where {UPLO,UNIT}
+        A, B = triangulardata(L.A), L.B
+        size(A, 1) == size(B, 1) || throw(DimensionMismatch("T has size $(size(A)), B has size $(size(B))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_sky_trsm_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{$T}, Ptr{$T}, Int64, Int64),
+                    handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), A.data.ptr, B.ptr, ld(B), size(B, 2)))
+        B
+    end
+end
+
+synchronize() = check(ccall((:bbm_synchronize, libbbm), Int32, (Ptr{Cvoid},), handle().ptr))
+
+end # module
