@@ -234,12 +234,16 @@ def main():
     ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     args = ap.parse_args()
     import torch
     import bbm_b200 as B
     torch.cuda.set_device(0)
     stream = torch.cuda.Stream()
     h = B.Handle(0, stream=stream.cuda_stream)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        h.set_option(k, int(v))
     want = set(args.configs.split(","))
     oracle = not args.no_oracle
     peak_tf = dgemm_peak(torch) if want & {"4", "5"} else None

@@ -200,19 +200,37 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             const T* Ds = reinterpret_cast<const T*>(sd + (d0 & 15));
             const T* Xs = reinterpret_cast<const T*>(sx + (x0 & 15));
             const int cJ = g.cJ, jlo = g.jlo;
+            if (W > 0) {
+                // the w x-values of this row are shared by all NS slabs: fetch them once
+                constexpr int WW = W > 0 ? W : 1;
+                T xr[WW];
+                int off[WW];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int K = J + s - p.u;
-                if (K >= Ka && K < Kb) {  // block-uniform
-                    const int rK = static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]);
-                    if (k < rK) {
-                        if (W > 0) {
+                for (int ii = 0; ii < WW; ++ii) {
+                    const int j = k + p.mu - ii;
+                    const bool ok = j >= 0 && j < cJ;
+                    off[ii] = ok ? (j - jlo) * P + ii : -1;
+                    xr[ii] = ok ? Xs[j - jlo] : T(0);
+                }
 #pragma unroll
-                            for (int ii = (W > 0 ? W : 1) - 1; ii >= 0; --ii) {  // ascending column j
-                                const int j = k + p.mu - ii;
-                                if (j >= 0 && j < cJ) acc[s] = fma(Ds[(j - jlo) * P + s * w + ii], Xs[j - jlo], acc[s]);
-                            }
-                        } else {
+                for (int s = 0; s < NS; ++s) {
+                    const int K = J + s - p.u;
+                    if (K >= Ka && K < Kb) {  // block-uniform
+                        const int rK = static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]);
+                        if (k < rK) {
+#pragma unroll
+                            for (int ii = WW - 1; ii >= 0; --ii)  // ascending column j
+                                if (off[ii] >= 0) acc[s] = fma(Ds[off[ii] + s * WW], xr[ii], acc[s]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int K = J + s - p.u;
+                    if (K >= Ka && K < Kb) {  // block-uniform
+                        const int rK = static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]);
+                        if (k < rK) {
                             for (int ii = w - 1; ii >= 0; --ii) {
                                 const int j = k + p.mu - ii;
                                 if (j >= 0 && j < cJ) acc[s] = fma(Ds[(j - jlo) * P + s * w + ii], Xs[j - jlo], acc[s]);

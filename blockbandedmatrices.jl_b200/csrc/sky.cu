@@ -100,14 +100,18 @@ struct GemvParams {
     int nrhs;
 };
 
-template <typename T, int NR>
+// KSPLIT (gridDim.z > 1): CTA z takes the z-th slice of every entry's columns and accumulates its
+// partial product with atomic adds -- only used with beta == 1 (the triangular-solve update), where
+// it turns a latency-bound 1536-row panel product into several hundred independent CTAs.
+template <typename T, int NR, int BATCH>
 __global__ void __launch_bounds__(kGemvRows) sky_gemv_kernel(const GemvParams<T> p) {
-    __shared__ T xs[NR][kGemvChunk];
+    __shared__ T xs[kGemvChunk][NR];
     const SkyItem it = p.items[blockIdx.x];
     const int q0 = blockIdx.y * NR;
     const int nq = min(NR, p.nrhs - q0);
     const int tid = threadIdx.x;
     const bool active = tid < it.nrows;
+    const int nz = gridDim.z, z = blockIdx.z;
     T acc[NR];
 #pragma unroll
     for (int q = 0; q < NR; ++q) acc[q] = T(0);
@@ -115,30 +119,37 @@ __global__ void __launch_bounds__(kGemvRows) sky_gemv_kernel(const GemvParams<T>
     for (int e = it.ent_begin; e < it.ent_end; ++e) {
         const SkyEnt en = p.ents[e];
         const T* __restrict__ a = p.data + en.start + it.koff + tid;
-        for (i64 j0 = 0; j0 < en.ncols; j0 += kGemvChunk) {
-            const int nj = (int)min((i64)kGemvChunk, en.ncols - j0);
+        // column slice of this CTA (multiples of the chunk so that slices stay aligned)
+        i64 jbeg = 0, jend = en.ncols;
+        if (nz > 1) {
+            const i64 per = ((en.ncols + nz - 1) / nz + kGemvChunk - 1) / kGemvChunk * kGemvChunk;
+            jbeg = min(en.ncols, per * z);
+            jend = min(en.ncols, jbeg + per);
+        }
+        for (i64 j0 = jbeg; j0 < jend; j0 += kGemvChunk) {
+            const int nj = (int)min((i64)kGemvChunk, jend - j0);
             __syncthreads();
             for (int idx = tid; idx < NR * kGemvChunk; idx += kGemvRows) {
                 const int q = idx / kGemvChunk, jj = idx % kGemvChunk;
-                xs[q][jj] = (q < nq && jj < nj) ? p.X[(i64)(q0 + q) * p.ldx + en.xoff + j0 + jj] : T(0);
+                xs[jj][q] = (q < nq && jj < nj) ? p.X[(i64)(q0 + q) * p.ldx + en.xoff + j0 + jj] : T(0);
             }
             __syncthreads();
             if (active) {
                 const T* __restrict__ aj = a + j0 * en.ld;
                 int jj = 0;
-                for (; jj + 8 <= nj; jj += 8) {
-                    T v[8];
+                for (; jj + BATCH <= nj; jj += BATCH) {
+                    T v[BATCH];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) v[t] = __ldg(aj + (i64)(jj + t) * en.ld);
+                    for (int t = 0; t < BATCH; ++t) v[t] = __ldg(aj + (i64)(jj + t) * en.ld);
 #pragma unroll
-                    for (int t = 0; t < 8; ++t)
+                    for (int t = 0; t < BATCH; ++t)
 #pragma unroll
-                        for (int q = 0; q < NR; ++q) acc[q] = fma(v[t], xs[q][jj + t], acc[q]);
+                        for (int q = 0; q < NR; ++q) acc[q] = fma(v[t], xs[jj + t][q], acc[q]);
                 }
                 for (; jj < nj; ++jj) {
                     const T v = __ldg(aj + (i64)jj * en.ld);
 #pragma unroll
-                    for (int q = 0; q < NR; ++q) acc[q] = fma(v, xs[q][jj], acc[q]);
+                    for (int q = 0; q < NR; ++q) acc[q] = fma(v, xs[jj][q], acc[q]);
                 }
             }
         }
@@ -148,24 +159,32 @@ __global__ void __launch_bounds__(kGemvRows) sky_gemv_kernel(const GemvParams<T>
         for (int q = 0; q < NR; ++q) {
             if (q < nq) {
                 T* yp = p.Y + (i64)(q0 + q) * p.ldy + it.yrow0 + tid;
-                T y = p.alpha * acc[q];
-                if (p.beta != T(0)) y = fma(p.beta, *yp, y);
-                *yp = y;
+                if (nz > 1) {
+                    atomicAdd(yp, p.alpha * acc[q]);
+                } else {
+                    T y = p.alpha * acc[q];
+                    if (p.beta != T(0)) y = fma(p.beta, *yp, y);
+                    *yp = y;
+                }
             }
         }
     }
 }
 
 template <typename T>
-int32_t launch_gemv(bbm_handle_t h, const GemvParams<T>& p, int nitems, int nrhs) {
+int32_t launch_gemv(bbm_handle_t h, const GemvParams<T>& p, int nitems, int nrhs, int ksplit = 1) {
     if (nitems <= 0 || nrhs <= 0) return BBM_OK;
+    if (ksplit > 1 && p.beta != T(1)) return bbm_fail(h, BBM_ERR_ARG, "internal: split products need beta == 1");
     cudaError_t e;
+    const unsigned z = (unsigned)std::max(1, ksplit);
     if (nrhs == 1) {
-        sky_gemv_kernel<T, 1><<<dim3(nitems, 1), kGemvRows, 0, h->stream>>>(p);
+        sky_gemv_kernel<T, 1, 8><<<dim3(nitems, 1, z), kGemvRows, 0, h->stream>>>(p);
     } else if (nrhs <= 4) {
-        sky_gemv_kernel<T, 4><<<dim3(nitems, 1), kGemvRows, 0, h->stream>>>(p);
+        sky_gemv_kernel<T, 4, 8><<<dim3(nitems, 1, z), kGemvRows, 0, h->stream>>>(p);
+    } else if (nrhs <= 8 || ksplit <= 1) {
+        sky_gemv_kernel<T, 8, 8><<<dim3(nitems, (nrhs + 7) / 8, z), kGemvRows, 0, h->stream>>>(p);
     } else {
-        sky_gemv_kernel<T, 8><<<dim3(nitems, (nrhs + 7) / 8), kGemvRows, 0, h->stream>>>(p);
+        sky_gemv_kernel<T, 16, 16><<<dim3(nitems, (nrhs + 15) / 16, z), kGemvRows, 0, h->stream>>>(p);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_gemv_kernel launch: %s", cudaGetErrorString(e));
@@ -616,38 +635,55 @@ __global__ void __launch_bounds__(256) sky_tri_diag_kernel(const T* __restrict__
         const int q = idx / rK, i = idx % rK;
         bs[idx] = q < nq ? Bk[(i64)(q0 + q) * ldb + i] : T(0);
     }
-    __syncthreads();
     const int nsb = (rK + 31) / 32;
     const T* __restrict__ A = data + dstart;
+    const int i = tid & 31, q = tid >> 5;
+    // row i of the pre-inverted sub-block, kept in registers and prefetched one sub-step ahead
+    T wreg[32];
+    {
+        const T* __restrict__ w = W + (i64)(upper ? nsb - 1 : 0) * 1024;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) wreg[j] = (q < RC) ? w[i + 32 * j] : T(0);
+    }
+    __syncthreads();
     for (int s = 0; s < nsb; ++s) {
         const int ib = upper ? nsb - 1 - s : s;
         const int i0 = ib * 32, nb = min(32, rK - i0);
-        const T* __restrict__ w = W + (i64)ib * 1024;
-        // x_ib = inv(T_ib,ib) * b_ib
+        // x_ib = inv(T_ib,ib) * b_ib   (entries of the inverse beyond nb are zero)
         T xv = T(0);
-        const int i = tid & 31, q = tid >> 5;
         if (q < RC) {
-#pragma unroll 8
-            for (int j = 0; j < nb; ++j) xv = fma(w[i + 32 * j], bs[q * rK + i0 + j], xv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nb) xv = fma(wreg[j], bs[q * rK + i0 + j], xv);
         }
         __syncthreads();
         if (q < RC && i < nb) {
             bs[q * rK + i0 + i] = xv;
             if (q < nq) Bk[(i64)(q0 + q) * ldb + i0 + i] = xv;
         }
+        if (s + 1 < nsb) {
+            const T* __restrict__ w = W + (i64)(upper ? ib - 1 : ib + 1) * 1024;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) wreg[j] = (q < RC) ? w[i + 32 * j] : T(0);
+        }
         __syncthreads();
-        // remaining rows of the diagonal block: b -= T[rows, ib] * x_ib
+        // remaining rows of the diagonal block: b -= T[rows, ib] * x_ib; all 32 loads of a row are
+        // issued before the first use so that one memory latency covers the whole sub-step
         const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
         for (int row = rlo + tid; row < rhi; row += 256) {
+            const T* __restrict__ a = A + row + (i64)i0 * ld;
+            T v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (j < nb) ? a[(i64)j * ld] : T(0);
             T acc[RC];
 #pragma unroll
             for (int qq = 0; qq < RC; ++qq) acc[qq] = T(0);
-            const T* __restrict__ a = A + row + (i64)i0 * ld;
-            for (int j = 0; j < nb; ++j) {
-                const T v = a[(i64)j * ld];
 #pragma unroll
-                for (int qq = 0; qq < RC; ++qq) acc[qq] = fma(v, bs[qq * rK + i0 + j], acc[qq]);
-            }
+            for (int j = 0; j < 32; ++j)
+                if (j < nb) {
+#pragma unroll
+                    for (int qq = 0; qq < RC; ++qq) acc[qq] = fma(v[j], bs[qq * rK + i0 + j], acc[qq]);
+                }
 #pragma unroll
             for (int qq = 0; qq < RC; ++qq) bs[qq * rK + row] -= acc[qq];
         }
@@ -725,10 +761,10 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     i64 maxr = 0;
     for (i64 K = 0; K < d->Nr; ++K) maxr = std::max(maxr, d->r[K]);
     const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
-    int RC = 8;
+    int RC = nrhs > 128 ? 8 : 4;  // more CTAs along the right-hand sides shorten the sequential chain
     while (RC > 1 && (size_t)RC * maxr * sizeof(T) > budget) RC /= 2;
     if ((size_t)RC * maxr * sizeof(T) > budget) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "diagonal block of %lld rows does not fit the shared-memory solve", (long long)maxr);
-    if (nrhs < RC) RC = nrhs >= 4 ? 4 : (nrhs >= 2 ? 2 : 1);
+    while (RC > 1 && nrhs < RC) RC /= 2;
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)RC * maxr * sizeof(T))); };
     if (RC == 8) e = set_attr(sky_tri_diag_kernel<T, 8>);
     else if (RC == 4) e = set_attr(sky_tri_diag_kernel<T, 4>);
@@ -754,7 +790,12 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
         const int ni = t.item_ptr[K + 1] - t.item_ptr[K];
         if (ni > 0) {
             GemvParams<T> p{d_data, d_B, d_B, ldb, ldb, t.d_items + t.item_ptr[K], t.d_ents, T(-1), T(1), (int)nrhs};
-            rc = launch_gemv<T>(h, p, ni, (int)nrhs);
+            // split the block's columns over CTAs until a few hundred are in flight
+            const int groups = ni * (int)((nrhs + 15) / 16);
+            int ksplit = 1;
+            while (ksplit < 16 && groups * ksplit < 2 * h->num_sms && rK / (ksplit * 2) >= kGemvChunk) ksplit *= 2;
+            if (nrhs <= 8) ksplit = 1;
+            rc = launch_gemv<T>(h, p, ni, (int)nrhs, ksplit);
             if (rc != BBM_OK) return rc;
         }
     }
