@@ -25,6 +25,9 @@ struct bbm_context {
     // workspace for the *_host_* calls (device copies of X and Y)
     void* ws_x = nullptr; size_t ws_x_bytes = 0;
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
+    // low-priority side stream (L2 prefetch ahead of the triangular solve's sequential chain)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ev[2] = {nullptr, nullptr};
 };
 
 inline bool bbm_valid(bbm_handle_t h) { return h != nullptr && h->magic == 0xBB200C0Du; }

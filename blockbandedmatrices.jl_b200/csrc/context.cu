@@ -5,7 +5,7 @@
 
 static const char* const kOptionKeys[] = {
     "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves",
-    "sky.kernel", "sky.mm_kernel", "trsm.kernel", "dist.graph", nullptr};
+    "sky.kernel", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "dist.graph", nullptr};
 
 extern "C" {
 
@@ -50,6 +50,8 @@ int32_t bbm_destroy(bbm_handle_t h) {
     cudaSetDevice(h->device);
     if (h->ws_x) cudaFree(h->ws_x);
     if (h->ws_y) cudaFree(h->ws_y);
+    if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
+    for (int i = 0; i < 2; ++i) if (h->side_ev[i]) cudaEventDestroy(h->side_ev[i]);
     h->magic = 0;
     delete h;
     return BBM_OK;

@@ -255,15 +255,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int kMmBK = 16;
 constexpr int kMmStages = 3;
 
-template <int BM, int BN>
+template <int BM, int BN, int kMmBK>
 constexpr size_t mm_smem_bytes() {
     return (size_t)kMmStages * ((size_t)kMmBK * (BM + 4) + (size_t)BN * (kMmBK + 4)) * sizeof(double);
 }
 
-template <int BM, int BN, int WM, int WN, bool ALIGNED>
+template <int BM, int BN, int WM, int WN, int kMmBK, bool ALIGNED>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_kernel(const MmParams<double> p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int LDA = BM + 4;     // As[k][m]: 4 k-rows of a fragment land in distinct bank groups
@@ -546,13 +545,15 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
     if (sizeof(T) == 8 && force != 2) {
         const bool al = pl->aligned && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % 16 == 0);
         MmParams<double> pd{(const double*)dA, (const double*)dB, (double*)dC, pl->d_cblks, pl->d_segs, pl->d_tiles[0], (double)alpha, (double)beta};
-        constexpr size_t smem = mm_smem_bytes<128, 128>();
-        auto go = [&](auto kern) {
+        auto go = [&](auto kern, size_t smem) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) { kern<<<pl->ntiles[0], 256, smem, h->stream>>>(pd); e = cudaGetLastError(); }
         };
-        if (al) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, true>);
-        else go(sky_dgemm_dmma_kernel<128, 128, 64, 32, false>);
+        // k-chunk depth 32 halves the per-chunk barrier/issue bubble of the DMMA pipe (207 KB of smem)
+        const bool bk32 = bbm_opt(h, "sky.mm_bk", 32) >= 32 && h->smem_optin >= mm_smem_bytes<128, 128, 32>();
+        if (al && bk32) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 32, true>, mm_smem_bytes<128, 128, 32>());
+        else if (al) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, true>, mm_smem_bytes<128, 128, 16>());
+        else go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, false>, mm_smem_bytes<128, 128, 16>());
     } else {
         p.tiles = pl->d_tiles[1];
         sky_gemm_simt_kernel<T><<<pl->ntiles[1], 256, 0, h->stream>>>(p);
@@ -691,6 +692,109 @@ __global__ void __launch_bounds__(256) sky_tri_diag_kernel(const T* __restrict__
     }
 }
 
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* dst, const T* src) {
+    if (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// Same blocked substitution, but the diagonal block streams through shared memory: none of its
+// loads depends on the solution, so the off-diagonal pieces T[rows, HC columns] (and the inverted
+// 32x32 sub-blocks) are fetched with cp.async one piece ahead of the dependency chain
+// x_ib -> update -> x_ib-1 ..., which then only touches shared memory.
+template <typename T, int RC>
+__global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __restrict__ data, i64 dstart, i64 ld, int rK, int upper,
+                                                                  const T* __restrict__ W, T* __restrict__ Bk, i64 ldb, int nrhs, int HC) {
+    extern __shared__ __align__(16) unsigned char tri_smem[];
+    const int PRS = (rK + 1) & ~1;
+    T* bs = reinterpret_cast<T*>(tri_smem);  // bs[q * rK + i]
+    T* ws = bs + (size_t)RC * PRS;           // two inverted sub-blocks
+    T* us = ws + 2 * 1024;                   // two pieces of HC columns x PRS rows
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * RC;
+    const int nq = min(RC, nrhs - q0);
+    const int nsb = (rK + 31) / 32;
+    const int npp = 32 / HC;
+    const int npieces = nsb * npp;
+    const T* __restrict__ A = data + dstart;
+
+    auto load_piece = [&](int pc) {
+        if (pc >= npieces) return;
+        const int s = pc / npp, hp = pc % npp;
+        const int ib = upper ? nsb - 1 - s : s;
+        const int i0 = ib * 32, nb = min(32, rK - i0);
+        const int c0 = i0 + hp * HC, nc = max(0, min(HC, i0 + nb - c0));
+        const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
+        T* u = us + (size_t)(pc & 1) * HC * PRS;
+        for (int c = 0; c < nc; ++c) {
+            const T* __restrict__ src = A + (i64)(c0 + c) * ld;
+            for (int r = rlo + tid; r < rhi; r += 256) cp_async_elem(u + c * PRS + (r - rlo), src + r);
+        }
+        if (hp == 0) {  // first piece of a sub-step brings its inverted diagonal sub-block along
+            T* w = ws + (s & 1) * 1024;
+            const T* __restrict__ wg = W + (i64)ib * 1024;
+            for (int idx = tid; idx < 1024; idx += 256) cp_async_elem(w + idx, wg + idx);
+        }
+    };
+
+    load_piece(0);
+    cp_async_commit();
+    for (int idx = tid; idx < RC * rK; idx += 256) {
+        const int q = idx / rK, i = idx % rK;
+        bs[q * PRS + i] = q < nq ? Bk[(i64)(q0 + q) * ldb + i] : T(0);
+    }
+    const int li = tid & 31, lq = tid >> 5;
+    for (int pc = 0; pc < npieces; ++pc) {
+        load_piece(pc + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int s = pc / npp, hp = pc % npp;
+        const int ib = upper ? nsb - 1 - s : s;
+        const int i0 = ib * 32, nb = min(32, rK - i0);
+        if (hp == 0) {
+            // x_ib = inv(T_ib,ib) * b_ib   (entries of the inverse beyond nb are zero)
+            const T* w = ws + (s & 1) * 1024;
+            T xv = T(0);
+            if (lq < RC) {
+#pragma unroll 8
+                for (int j = 0; j < nb; ++j) xv = fma(w[li + 32 * j], bs[lq * PRS + i0 + j], xv);
+            }
+            __syncthreads();
+            if (lq < RC && li < nb) {
+                bs[lq * PRS + i0 + li] = xv;
+                if (lq < nq) Bk[(i64)(q0 + lq) * ldb + i0 + li] = xv;
+            }
+            __syncthreads();
+        }
+        const int c0 = i0 + hp * HC, nc = max(0, min(HC, i0 + nb - c0));
+        const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
+        const T* u = us + (size_t)(pc & 1) * HC * PRS;
+        for (int row = rlo + tid; row < rhi; row += 256) {
+            T acc[RC];
+#pragma unroll
+            for (int qq = 0; qq < RC; ++qq) acc[qq] = T(0);
+            for (int c = 0; c < nc; ++c) {
+                const T v = u[c * PRS + (row - rlo)];
+#pragma unroll
+                for (int qq = 0; qq < RC; ++qq) acc[qq] = fma(v, bs[qq * PRS + c0 + c], acc[qq]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < RC; ++qq) bs[qq * PRS + row] -= acc[qq];
+        }
+        __syncthreads();
+    }
+}
+
+// pulls a byte range into L2 ahead of the sequential chain (the next block column's panel)
+__global__ void __launch_bounds__(256) sky_l2_prefetch_kernel(const char* __restrict__ p, size_t bytes) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 128;
+    for (size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128; off < bytes; off += stride)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+
 int32_t build_tri(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
     bbm_sky_desc::Tri& t = d->tri[upper];
     if (t.built) return BBM_OK;
@@ -765,25 +869,69 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     while (RC > 1 && (size_t)RC * maxr * sizeof(T) > budget) RC /= 2;
     if ((size_t)RC * maxr * sizeof(T) > budget) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "diagonal block of %lld rows does not fit the shared-memory solve", (long long)maxr);
     while (RC > 1 && nrhs < RC) RC /= 2;
-    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)RC * maxr * sizeof(T))); };
-    if (RC == 8) e = set_attr(sky_tri_diag_kernel<T, 8>);
-    else if (RC == 4) e = set_attr(sky_tri_diag_kernel<T, 4>);
-    else if (RC == 2) e = set_attr(sky_tri_diag_kernel<T, 2>);
-    else e = set_attr(sky_tri_diag_kernel<T, 1>);
+    // streaming variant: b_K + two inverted sub-blocks + two pieces of HC columns in shared memory
+    const size_t prs = (size_t)((maxr + 1) & ~i64(1));
+    int HC = 0;
+    if (bbm_opt(h, "trsm.kernel", 0) != 2)
+        for (int hc = 16; hc >= 2 && !HC; hc /= 2)
+            if (((size_t)RC * prs + 2048 + 2 * (size_t)hc * prs) * sizeof(T) <= budget) HC = hc;
+    const size_t smem_max = HC ? ((size_t)RC * prs + 2048 + 2 * (size_t)HC * prs) * sizeof(T) : (size_t)RC * maxr * sizeof(T);
+    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max); };
+    if (HC) {
+        if (RC == 8) e = set_attr(sky_tri_diag_stream_kernel<T, 8>);
+        else if (RC == 4) e = set_attr(sky_tri_diag_stream_kernel<T, 4>);
+        else if (RC == 2) e = set_attr(sky_tri_diag_stream_kernel<T, 2>);
+        else e = set_attr(sky_tri_diag_stream_kernel<T, 1>);
+    } else {
+        if (RC == 8) e = set_attr(sky_tri_diag_kernel<T, 8>);
+        else if (RC == 4) e = set_attr(sky_tri_diag_kernel<T, 4>);
+        else if (RC == 2) e = set_attr(sky_tri_diag_kernel<T, 2>);
+        else e = set_attr(sky_tri_diag_kernel<T, 1>);
+    }
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const unsigned gq = (unsigned)((nrhs + RC - 1) / RC);
+    // L2 prefetch of the next block column's panel on a side stream, throttled to one step ahead
+    const bool prefetch = bbm_opt(h, "trsm.prefetch", 1) != 0 && d->Nr > 2;
+    if (prefetch && !h->side_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        BBM_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 2; ++i) BBM_CUDA(h, cudaEventCreateWithFlags(&h->side_ev[i], cudaEventDisableTiming));
+    }
+    if (prefetch) {  // the side stream starts after everything queued so far (d_data may still be being written)
+        BBM_CUDA(h, cudaEventRecord(h->side_ev[0], h->stream));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->side_ev[0], 0));
+    }
     for (i64 s = 0; s < d->Nr; ++s) {
         const i64 K = upper ? d->Nr - 1 - s : s;
         const int rK = (int)d->r[K];
         if (rK == 0) continue;
+        if (prefetch && s + 1 < d->Nr) {
+            const i64 Kn = upper ? K - 1 : K + 1;
+            const size_t bytes = (size_t)(d->off[Kn + 1] - d->off[Kn]) * sizeof(T);
+            if (bytes > 0) {
+                const unsigned blocks = (unsigned)std::min<size_t>(512, (bytes / 128 + 255) / 256 + 1);
+                sky_l2_prefetch_kernel<<<blocks, 256, 0, h->side_stream>>>(reinterpret_cast<const char*>(d_data + d->off[Kn]), bytes);
+                h->launches += 1;
+            }
+        }
         const i64 dstart = sky_start(d, K, K);
-        const size_t smem = (size_t)RC * rK * sizeof(T);
         const T* Wk = W + t.sub_ptr[K] * 1024;
         T* Bk = d_B + d->R[K];
-        if (RC == 8) sky_tri_diag_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
-        else if (RC == 4) sky_tri_diag_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
-        else if (RC == 2) sky_tri_diag_kernel<T, 2><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
-        else sky_tri_diag_kernel<T, 1><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+        if (HC) {
+            const size_t p2 = (size_t)((rK + 1) & ~1);
+            const size_t smem = ((size_t)RC * p2 + 2048 + 2 * (size_t)HC * p2) * sizeof(T);
+            if (RC == 8) sky_tri_diag_stream_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
+            else if (RC == 4) sky_tri_diag_stream_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
+            else if (RC == 2) sky_tri_diag_stream_kernel<T, 2><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
+            else sky_tri_diag_stream_kernel<T, 1><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
+        } else {
+            const size_t smem = (size_t)RC * rK * sizeof(T);
+            if (RC == 8) sky_tri_diag_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+            else if (RC == 4) sky_tri_diag_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+            else if (RC == 2) sky_tri_diag_kernel<T, 2><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+            else sky_tri_diag_kernel<T, 1><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_tri_diag_kernel launch: %s", cudaGetErrorString(e));
         h->launches += 1;
@@ -798,6 +946,14 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
             rc = launch_gemv<T>(h, p, ni, (int)nrhs, ksplit);
             if (rc != BBM_OK) return rc;
         }
+        if (prefetch) {  // the prefetch of step s+2 may start once step s is done
+            BBM_CUDA(h, cudaEventRecord(h->side_ev[s & 1], h->stream));
+            BBM_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->side_ev[s & 1], 0));
+        }
+    }
+    if (prefetch) {  // join: nothing of this call is still in flight once the handle's stream is drained
+        BBM_CUDA(h, cudaEventRecord(h->side_ev[0], h->side_stream));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->side_ev[0], 0));
     }
     return BBM_OK;
 }
