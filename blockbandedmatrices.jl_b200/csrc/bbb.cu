@@ -212,16 +212,25 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
                     off[ii] = ok ? (j - jlo) * P + ii : -1;
                     xr[ii] = ok ? Xs[j - jlo] : T(0);
                 }
+                // which of the NS block rows this step feeds are live for this thread
+                bool act[NS];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     const int K = J + s - p.u;
-                    if (K >= Ka && K < Kb) {  // block-uniform
-                        const int rK = static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]);
-                        if (k < rK) {
+                    const bool in = K >= Ka && K < Kb;
+                    const int rK = in ? static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]) : 0;
+                    act[s] = k < rK;
+                }
+                // column-major over the sub-band (ascending j per accumulator, as the reference), the NS
+                // accumulators interleaved: branch-free straight-line code with NS independent FMA chains
 #pragma unroll
-                            for (int ii = WW - 1; ii >= 0; --ii)  // ascending column j
-                                if (off[ii] >= 0) acc[s] = fma(Ds[off[ii] + s * WW], xr[ii], acc[s]);
-                        }
+                for (int ii = WW - 1; ii >= 0; --ii) {
+                    const int o = off[ii] >= 0 ? off[ii] : 0;   // any in-chunk address; its value is discarded
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const T dv = Ds[o + s * WW];
+                        const T r = fma(dv, xr[ii], acc[s]);
+                        acc[s] = (act[s] && off[ii] >= 0) ? r : acc[s];   // never lets an unused slot (NaN) in
                     }
                 }
             } else {

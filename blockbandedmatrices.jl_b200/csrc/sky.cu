@@ -692,6 +692,8 @@ __global__ void __launch_bounds__(256) sky_tri_diag_kernel(const T* __restrict__
     }
 }
 
+constexpr int kTriBufs = 4;  // pieces in flight ahead of the chain: (kTriBufs-1) x HC columns
+
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T* dst, const T* src) {
     if (sizeof(T) == 8)
@@ -711,7 +713,7 @@ __global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __res
     const int PRS = (rK + 1) & ~1;
     T* bs = reinterpret_cast<T*>(tri_smem);  // bs[q * rK + i]
     T* ws = bs + (size_t)RC * PRS;           // two inverted sub-blocks
-    T* us = ws + 2 * 1024;                   // two pieces of HC columns x PRS rows
+    T* us = ws + 2 * 1024;                   // kTriBufs pieces of HC columns x PRS rows
     const int tid = threadIdx.x;
     const int q0 = blockIdx.x * RC;
     const int nq = min(RC, nrhs - q0);
@@ -727,7 +729,7 @@ __global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __res
         const int i0 = ib * 32, nb = min(32, rK - i0);
         const int c0 = i0 + hp * HC, nc = max(0, min(HC, i0 + nb - c0));
         const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
-        T* u = us + (size_t)(pc & 1) * HC * PRS;
+        T* u = us + (size_t)(pc % kTriBufs) * HC * PRS;
         for (int c = 0; c < nc; ++c) {
             const T* __restrict__ src = A + (i64)(c0 + c) * ld;
             for (int r = rlo + tid; r < rhi; r += 256) cp_async_elem(u + c * PRS + (r - rlo), src + r);
@@ -739,17 +741,19 @@ __global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __res
         }
     };
 
-    load_piece(0);
-    cp_async_commit();
+    for (int pc = 0; pc < kTriBufs - 1; ++pc) {
+        load_piece(pc);
+        cp_async_commit();
+    }
     for (int idx = tid; idx < RC * rK; idx += 256) {
         const int q = idx / rK, i = idx % rK;
         bs[q * PRS + i] = q < nq ? Bk[(i64)(q0 + q) * ldb + i] : T(0);
     }
     const int li = tid & 31, lq = tid >> 5;
     for (int pc = 0; pc < npieces; ++pc) {
-        load_piece(pc + 1);
+        load_piece(pc + kTriBufs - 1);
         cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<kTriBufs - 1>();
         __syncthreads();
         const int s = pc / npp, hp = pc % npp;
         const int ib = upper ? nsb - 1 - s : s;
@@ -771,7 +775,7 @@ __global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __res
         }
         const int c0 = i0 + hp * HC, nc = max(0, min(HC, i0 + nb - c0));
         const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
-        const T* u = us + (size_t)(pc & 1) * HC * PRS;
+        const T* u = us + (size_t)(pc % kTriBufs) * HC * PRS;
         for (int row = rlo + tid; row < rhi; row += 256) {
             T acc[RC];
 #pragma unroll
@@ -788,11 +792,17 @@ __global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __res
     }
 }
 
-// pulls a byte range into L2 ahead of the sequential chain (the next block column's panel)
-__global__ void __launch_bounds__(256) sky_l2_prefetch_kernel(const char* __restrict__ p, size_t bytes) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x * 128;
-    for (size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128; off < bytes; off += stride)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+// pulls a byte range into L2 ahead of the sequential chain (the next block column's panel): one
+// 4-byte ld.global.cg per 32-byte sector (prefetch.global.L2 hints were measured to be ineffective)
+__global__ void __launch_bounds__(256) sky_l2_prefetch_kernel(const char* __restrict__ p, size_t bytes, unsigned* sink) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 32;
+    unsigned acc = 0;
+    for (size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 32; off + 4 <= bytes; off += stride) {
+        unsigned v;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p + off));
+        acc ^= v;
+    }
+    if (acc == 0x9E3779B9u && sink) *sink = acc;  // keeps the loads alive; practically never true
 }
 
 int32_t build_tri(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
@@ -872,10 +882,11 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     // streaming variant: b_K + two inverted sub-blocks + two pieces of HC columns in shared memory
     const size_t prs = (size_t)((maxr + 1) & ~i64(1));
     int HC = 0;
-    if (bbm_opt(h, "trsm.kernel", 0) != 2)
-        for (int hc = 16; hc >= 2 && !HC; hc /= 2)
-            if (((size_t)RC * prs + 2048 + 2 * (size_t)hc * prs) * sizeof(T) <= budget) HC = hc;
-    const size_t smem_max = HC ? ((size_t)RC * prs + 2048 + 2 * (size_t)HC * prs) * sizeof(T) : (size_t)RC * maxr * sizeof(T);
+    // "trsm.kernel" = 1 selects the streaming variant (measured slower on cfg5: 148 vs 91 us per block step)
+    if (bbm_opt(h, "trsm.kernel", 0) == 1)
+        for (int hc = 8; hc >= 2 && !HC; hc /= 2)  // 32/HC >= kTriBufs-1 keeps at most one later sub-block in flight
+            if (((size_t)RC * prs + 2048 + kTriBufs * (size_t)hc * prs) * sizeof(T) <= budget) HC = hc;
+    const size_t smem_max = HC ? ((size_t)RC * prs + 2048 + kTriBufs * (size_t)HC * prs) * sizeof(T) : (size_t)RC * maxr * sizeof(T);
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max); };
     if (HC) {
         if (RC == 8) e = set_attr(sky_tri_diag_stream_kernel<T, 8>);
@@ -910,8 +921,8 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
             const i64 Kn = upper ? K - 1 : K + 1;
             const size_t bytes = (size_t)(d->off[Kn + 1] - d->off[Kn]) * sizeof(T);
             if (bytes > 0) {
-                const unsigned blocks = (unsigned)std::min<size_t>(512, (bytes / 128 + 255) / 256 + 1);
-                sky_l2_prefetch_kernel<<<blocks, 256, 0, h->side_stream>>>(reinterpret_cast<const char*>(d_data + d->off[Kn]), bytes);
+                const unsigned blocks = (unsigned)std::min<size_t>(592, (bytes / 32 + 255) / 256 + 1);
+                sky_l2_prefetch_kernel<<<blocks, 256, 0, h->side_stream>>>(reinterpret_cast<const char*>(d_data + d->off[Kn]), bytes, nullptr);
                 h->launches += 1;
             }
         }
@@ -920,7 +931,7 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
         T* Bk = d_B + d->R[K];
         if (HC) {
             const size_t p2 = (size_t)((rK + 1) & ~1);
-            const size_t smem = ((size_t)RC * p2 + 2048 + 2 * (size_t)HC * p2) * sizeof(T);
+            const size_t smem = ((size_t)RC * p2 + 2048 + kTriBufs * (size_t)HC * p2) * sizeof(T);
             if (RC == 8) sky_tri_diag_stream_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
             else if (RC == 4) sky_tri_diag_stream_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
             else if (RC == 2) sky_tri_diag_stream_kernel<T, 2><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);

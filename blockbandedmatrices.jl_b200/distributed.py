@@ -155,3 +155,162 @@ class DistBandedBlockBandedMatrix:
             self.close()
         except Exception:
             pass
+
+
+# ==================================================================================================
+# Row-block-partitioned BlockBandedMatrix (constant block bandwidths): matvec and A*B
+# ==================================================================================================
+# A contiguous block-row range [S0,S1) of a block-banded matrix is itself a BlockSkylineMatrix with
+# per-column bandwidths (cf. the sub-view bandwidths of src/linalg.jl:78-87): block column J keeps the
+# block rows colsupport(J) & [S0,S1).  Unlike the banded-block-banded format its storage is NOT a
+# slice of the parent (every panel is cut by rows), so each rank builds / receives its own panels.
+# Structure planning below is pure numpy (exercised on CPU by tests/test_dist_cpu.py); the products
+# are the single-GPU kernels on the local structures; halos travel as packed blocks over
+# torch.distributed point-to-point (NCCL on GPUs).
+
+def sky_rowrange_structure(rows, cols, l, u, S0, S1):
+    """Local structure of rows [S0,S1) of a BlockBandedMatrix(rows, cols, (l,u)).
+
+    Returns (Jlo, Jhi, lloc, uloc): stored block columns [Jlo,Jhi) and the per-column local block
+    bandwidths such that local block (K-S0, J-Jlo) is stored iff global block (K,J) is, K in [S0,S1)."""
+    Nr, Nc = len(rows), len(cols)
+    if S1 <= S0 or l + u + 1 <= 0:
+        J0 = min(max(S0, 0), Nc)
+        return J0, J0, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    Jlo = min(max(S0 - l, 0), Nc)
+    Jhi = min(max(S1 - 1 + u + 1, Jlo), Nc)
+    lloc = np.zeros(Jhi - Jlo, dtype=np.int64)
+    uloc = np.zeros(Jhi - Jlo, dtype=np.int64)
+    for J in range(Jlo, Jhi):
+        lo = max(J - u, 0, S0) - S0
+        hi = min(J + l, Nr - 1, S1 - 1) - S0
+        Jp = J - Jlo
+        if hi < lo:
+            lloc[Jp], uloc[Jp] = -1 - Jp, Jp   # empty column: max(Jp-u,0)=0 > min(Jp+l,..)=-1
+        else:
+            lloc[Jp], uloc[Jp] = hi - Jp, Jp - lo
+    return Jlo, Jhi, lloc, uloc
+
+
+def sky_cut_rows(parent, S0, S1):
+    """Host helper: the local BlockSkylineMatrix holding rows [S0,S1) of a host BlockBandedMatrix."""
+    from .matrices import BlockSkylineMatrix
+    l, u = int(parent.l[0]) if len(parent.l) else 0, int(parent.u[0]) if len(parent.u) else 0
+    Jlo, Jhi, ll, uu = sky_rowrange_structure(parent.rows, parent.cols, l, u, S0, S1)
+    loc = BlockSkylineMatrix.zeros(parent.dtype, parent.rows[S0:S1], parent.cols[Jlo:Jhi], ll, uu)
+    for Jp in range(Jhi - Jlo):
+        for Kp in loc.blockcolsupport(Jp):
+            blk = parent.block(S0 + Kp, Jlo + Jp)
+            s, ld = loc.block_start(Kp, Jp), int(loc.block_strides[Jp])
+            for j in range(blk.shape[1]):
+                loc.data[s + j * ld:s + j * ld + blk.shape[0]] = blk[:, j]
+    return loc, Jlo, Jhi
+
+
+def owned_cols(Kbounds, Nc, p):
+    """Block columns of x (= block rows of a right factor B) owned by rank p (same rule as bbm_bbb_dist_layout)."""
+    nranks = len(Kbounds) - 1
+    J0 = min(int(Kbounds[p]), Nc)
+    J1 = Nc if p == nranks - 1 else min(int(Kbounds[p + 1]), Nc)
+    return J0, max(J0, J1)
+
+
+def matmul_plan(rowsA, colsA, lA, uA, colsB, lB, uB, Kbounds, rank):
+    """Plan of rank `rank` for C[K0:K1,:] = A[K0:K1,:] * B with A, C partitioned by block rows and B's
+    block rows owned like x.  Returns a dict with the stored ranges and the halo transfer lists:
+    sends / recvs = {peer: [(N, J), ...]} blocks of B in a fixed (N, J) order both sides agree on."""
+    nranks = len(Kbounds) - 1
+    NrA, NcA, NcB = len(rowsA), len(colsA), len(colsB)
+
+    def stored_B_rows(p):   # B block rows rank p multiplies with = column hull of its A rows
+        K0, K1 = int(Kbounds[p]), int(Kbounds[p + 1])
+        Jlo, Jhi, _, _ = sky_rowrange_structure(rowsA, colsA, lA, uA, K0, K1)
+        return Jlo, Jhi
+
+    def rowsupport_B(N):
+        return range(max(N - lB, 0), min(N + uB, NcB - 1) + 1)
+
+    K0, K1 = int(Kbounds[rank]), int(Kbounds[rank + 1])
+    S0, S1 = stored_B_rows(rank)
+    O0, O1 = owned_cols(Kbounds, NcA, rank)
+    sends, recvs = {}, {}
+    for q in range(nranks):
+        if q == rank:
+            continue
+        q0, q1 = owned_cols(Kbounds, NcA, q)
+        t0, t1 = stored_B_rows(q)
+        need = [(N, J) for N in range(max(S0, q0), min(S1, q1)) for J in rowsupport_B(N) if colsA[N] and colsB[J]]
+        give = [(N, J) for N in range(max(t0, O0), min(t1, O1)) for J in rowsupport_B(N) if colsA[N] and colsB[J]]
+        if need:
+            recvs[q] = need
+        if give:
+            sends[q] = give
+    return {"K0": K0, "K1": K1, "S0": S0, "S1": S1, "O0": O0, "O1": O1, "sends": sends, "recvs": recvs}
+
+
+class DistBlockBandedProduct:
+    """C[K0:K1,:] <- alpha*A[K0:K1,:]*B + beta*C[K0:K1,:] on one rank of a row-block partition.
+
+    A_loc, C_loc hold the rank's own block rows, B_loc holds the block rows [S0,S1) the rank multiplies
+    with; rows of B_loc outside the owned range [O0,O1) are halo and are refreshed by `exchange()`
+    (packed blocks over torch.distributed isend/irecv -- NCCL between GPUs).  Storage is torch tensors
+    so that packing is ordinary strided copies; the product is the single-GPU DMMA kernel."""
+
+    def __init__(self, handle, dist, torch, rows, cols, lA, uA, colsB, lB, uB, Kbounds, rank, dtype=np.float64):
+        from .matrices import BlockSkylineMatrix
+        from .linalg import add_bandwidths
+        self.h, self.dist, self.torch, self.rank = handle, dist, torch, rank
+        self.rows, self.cols, self.colsB = _sizes(rows), _sizes(cols), _sizes(colsB)
+        self.plan = matmul_plan(self.rows, self.cols, lA, uA, self.colsB, lB, uB, Kbounds, rank)
+        P = self.plan
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        dev = torch.device("cuda", handle.device) if handle is not None else torch.device("cpu")
+        self.dev = dev
+
+        def make(rws, cls, l, u, S0, S1):
+            Jlo, Jhi, ll, uu = sky_rowrange_structure(rws, cls, l, u, S0, S1)
+            n = BlockSkylineMatrix.numentries(rws[S0:S1], cls[Jlo:Jhi], ll, uu)
+            t = torch.zeros(max(n, 1), dtype=tdt, device=dev)
+            if handle is not None:
+                from .device import DeviceArray
+                d = DeviceArray(handle, (n,), np.dtype(dtype), ptr=t.data_ptr())
+            else:
+                d = t.numpy()[:n]
+            return BlockSkylineMatrix(d, rws[S0:S1], cls[Jlo:Jhi], ll, uu), t, Jlo
+
+        self.A, self.tA, self.JloA = make(self.rows, self.cols, lA, uA, P["K0"], P["K1"])
+        self.B, self.tB, self.JloB = make(self.cols, self.colsB, lB, uB, P["S0"], P["S1"])
+        self.C, self.tC, self.JloC = make(self.rows, self.colsB, lA + lB, uA + uB, P["K0"], P["K1"])
+
+    # ---- block views of the local B storage -------------------------------------------------
+    def _b_block(self, N, J):
+        Kp, Jp = N - self.plan["S0"], J - self.JloB
+        s, ld = self.B.block_start(Kp, Jp), int(self.B.block_strides[Jp])
+        rN, cJ = int(self.cols[N]), int(self.colsB[J])
+        return self.tB.as_strided((cJ, rN), (ld, 1), s)     # [j][i] view of the column-major block
+
+    def exchange(self):
+        """Refresh the halo block rows of B_loc from their owners."""
+        torch, dist = self.torch, self.dist
+        ops, unpack = [], []
+        for q, blocks in sorted(self.plan["recvs"].items()):
+            n = sum(int(self.cols[N]) * int(self.colsB[J]) for N, J in blocks)
+            buf = torch.empty(n, dtype=self.tB.dtype, device=self.dev)
+            ops.append(dist.P2POp(dist.irecv, buf, q))
+            unpack.append((buf, blocks))
+        for q, blocks in sorted(self.plan["sends"].items()):
+            buf = torch.cat([self._b_block(N, J).reshape(-1) for N, J in blocks])
+            ops.append(dist.P2POp(dist.isend, buf, q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for buf, blocks in unpack:
+            o = 0
+            for N, J in blocks:
+                v = self._b_block(N, J)
+                v.copy_(buf[o:o + v.numel()].view(v.shape))
+                o += v.numel()
+
+    def mul_(self, alpha=1.0, beta=0.0):
+        from .linalg import mul_
+        return mul_(self.C, self.A, self.B, alpha, beta)

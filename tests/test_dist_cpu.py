@@ -159,3 +159,90 @@ def test_layout_cfg2_halo_sizes():
         assert all(cnt == 4096 for _, _, cnt in sends + recvs)
         assert lay["n_local"] == (512 + nb) * 4096
         assert lay["Ka"] == lay["K0"] + (rank > 0) and lay["Kb"] == lay["K1"] - (rank < 7)
+
+
+# --------------------------------------------------------------------------------------------------
+# row-block-partitioned BlockBandedMatrix product C = A*B (cfg4's sharding) on gloo
+# --------------------------------------------------------------------------------------------------
+MM_CASES = [
+    # rows(=cols of A = rows of B), colsB, (lA,uA), (lB,uB)
+    ([4] * 10, [4] * 10, (2, 2), (2, 2)),
+    ([3, 5, 2, 4, 6, 1, 3, 4], [3, 5, 2, 4, 6, 1, 3, 4], (1, 2), (2, 1)),
+    ([4] * 9, [4] * 9, (0, 3), (3, 0)),
+    ([2] * 5, [2] * 5, (2, 2), (1, 1)),      # halos reach past the neighbour with 3 ranks
+]
+
+
+def _mm_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bbm_b200 as B
+        from bbm_b200 import distributed as D
+        from oracle import cpu as O
+        from oracle import formats as F
+        from tests.helpers import random_sky, relerr, tol
+        failures = []
+        for ci, (rows, colsB, (lA, uA), (lB, uB)) in enumerate(MM_CASES):
+            rng = np.random.default_rng(300 + ci)
+            adata = random_sky(rng, rows, rows, lA, uA)
+            bdata = random_sky(rng, rows, colsB, lB, uB)
+            A = B.BlockSkylineMatrix(adata, rows, rows, lA, uA)
+            Bm = B.BlockSkylineMatrix(bdata, rows, colsB, lB, uB)
+            kb = D.partition_rows(rows, world)
+            prod = D.DistBlockBandedProduct(None, dist, torch, rows, rows, lA, uA, colsB, lB, uB, kb, rank)
+            P = prod.plan
+            locA, _, _ = D.sky_cut_rows(A, P["K0"], P["K1"])
+            locB, _, _ = D.sky_cut_rows(Bm, P["S0"], P["S1"])
+            prod.A.data[:] = locA.data
+            prod.B.data[:] = locB.data
+            # poison the halo rows of B: only the exchange may fill them
+            for N in range(P["S0"], P["S1"]):
+                if not (P["O0"] <= N < P["O1"]):
+                    for J in range(max(N - lB, 0), min(N + uB, len(colsB) - 1) + 1):
+                        if rows[N] and colsB[J]:
+                            prod._b_block(N, J).fill_(float("nan"))
+            prod.exchange()
+            if np.isnan(prod.B.data).any():
+                failures.append((ci, "halo rows of B not filled by the exchange"))
+                continue
+            if not np.array_equal(prod.B.data, locB.data):
+                failures.append((ci, "exchange delivered wrong blocks"))
+            # local product on the local (ragged) structures with the oracle
+            c0 = rng.standard_normal(prod.C.data.shape)
+            prod.C.data[:] = c0
+            O.sky_matmul((prod.A.rows, prod.A.cols, prod.A.l, prod.A.u), (prod.B.rows, prod.B.cols, prod.B.l, prod.B.u),
+                         (prod.C.rows, prod.C.cols, prod.C.l, prod.C.u), 1.5, prod.A.data, prod.B.data, 0.0, prod.C.data)
+            # compare the owned rows of C with the global oracle product
+            ol, ou = lA + lB, uA + uB
+            cref = np.zeros(B.BlockSkylineMatrix.numentries(rows, colsB, ol, ou))
+            O.sky_matmul((rows, rows, lA, uA), (rows, colsB, lB, uB), (rows, colsB, ol, ou), 1.5, adata, bdata, 0.0, cref)
+            Cref = B.BlockSkylineMatrix(cref, rows, colsB, ol, ou)
+            want, _, _ = D.sky_cut_rows(Cref, P["K0"], P["K1"])
+            if want.data.shape != prod.C.data.shape:
+                failures.append((ci, "local C structure mismatch"))
+            elif relerr(prod.C.data, want.data) > tol(np.float64, 64):
+                failures.append((ci, f"C rows mismatch {relerr(prod.C.data, want.data)}"))
+        q.put((rank, failures))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, [("exception", traceback.format_exc() + repr(e))]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_block_banded_product_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, failures in results:
+        assert not failures, f"rank {rank}: {failures}"
