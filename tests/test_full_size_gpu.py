@@ -1,0 +1,115 @@
+"""BASELINE.json's configs at (or near) full size on the GPU.
+
+cfg2 / cfg3 are checked against the CPU oracle at FULL size (the oracle needs < 1 s for them);
+cfg4 / cfg5 run at full block size with fewer blocks against the oracle, plus size-independent
+properties (linearity, solve-then-multiply round trip) on the GPU results themselves."""
+import numpy as np
+import pytest
+
+import bbm_b200 as B
+from oracle import cpu as O
+from tests.helpers import relerr, tol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    h = B.Handle(0)
+    yield h
+    h.close()
+
+
+def test_cfg2_full_size_laplacian_vs_oracle(handle):
+    """2D Laplacian BandedBlockBandedMatrix, 4096 blocks of size 4096 (16.7M unknowns), Float64."""
+    n = 4096
+    A = B.BandedBlockBandedMatrix.finitedifference_2d(n)
+    rng = np.random.default_rng(2)
+    # the true reference leaves out-of-block slots undefined: poison them so that masking is exercised
+    A.data[0:3, :n] = np.nan          # super-diagonal slab of the first block column (block row -1)
+    A.data[6:9, -n:] = np.nan         # sub-diagonal slab of the last block column (block row Nr)
+    x = rng.standard_normal(n * n)
+    Ad = A.to_device(handle)
+    dx, dy = handle.to_device(x), handle.empty(n * n, np.float64).fill_bytes(0xFF)
+    B.mul_(dy, Ad, dx)
+    y = dy.to_host()
+    ref = np.zeros(n * n)
+    O.use_openblas(threads=1)
+    O.bbb_mul([n] * n, [n] * n, 1, 1, 1, 1, 1.0, A.data, x, 0.0, ref)
+    O.use_builtin()
+    assert not np.isnan(y).any()
+    assert relerr(y, ref) <= tol(np.float64, 9)
+    # linearity on the GPU result alone
+    x2 = rng.standard_normal(n * n)
+    y2 = (Ad @ handle.to_device(x2)).to_host()
+    y12 = (Ad @ handle.to_device(2.0 * x - 3.0 * x2)).to_host()
+    assert relerr(y12, 2.0 * y - 3.0 * y2) <= 4 * tol(np.float64, 9)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cfg3_full_size_triangular_blocks_vs_oracle(handle, dtype):
+    """BandedBlockBandedMatrix rows=cols=1:4000, (2,2),(2,2): 8.0M unknowns, P=25."""
+    rows = list(range(1, 4001))
+    rng = np.random.default_rng(3)
+    n = sum(rows)
+    data = rng.standard_normal((n, 25), dtype=np.float32).astype(dtype).T   # F-contiguous 25 x n, no copy
+    x = rng.standard_normal(n).astype(dtype)
+    Ad = B.BandedBlockBandedMatrix(data, rows, rows, (2, 2), (2, 2)).to_device(handle)
+    y = (Ad @ handle.to_device(x)).to_host()
+    ref = np.zeros(n, dtype=dtype)
+    O.bbb_mul(rows, rows, 2, 2, 2, 2, 1.0, data, x, 0.0, ref)
+    assert relerr(y, ref) <= tol(dtype, 25)
+
+
+def test_cfg4_block_size_256_vs_oracle(handle):
+    """BlockBandedMatrix fill(256, N), (2,2) x (2,2) -> (4,4) on the FP64 tensor cores (N=24 of 2048)."""
+    rows = [256] * 24
+    rng = np.random.default_rng(4)
+    na = B.BlockSkylineMatrix.numentries(rows, rows, 2, 2)
+    adata, bdata = rng.standard_normal(na) / 16, rng.standard_normal(na) / 16
+    Ad = B.BlockSkylineMatrix(adata, rows, rows, 2, 2).to_device(handle)
+    Bd = B.BlockSkylineMatrix(bdata, rows, rows, 2, 2).to_device(handle)
+    Cd = B.mul(Ad, Bd)
+    assert Cd.blockbandwidths == (4, 4)
+    got = Cd.data.to_host()
+    ref = np.zeros_like(got)
+    O.use_openblas(threads=8)
+    O.sky_matmul((rows, rows, 2, 2), (rows, rows, 2, 2), (rows, rows, 4, 4), 1.0, adata, bdata, 0.0, ref)
+    O.use_builtin()
+    assert relerr(got, ref) <= tol(np.float64, 1280)
+    # (A*B)*x == A*(B*x) on the GPU
+    x = handle.to_device(rng.standard_normal(sum(rows)))
+    assert relerr((Cd @ x).to_host(), (Ad @ (Bd @ x)).to_host()) <= 8 * tol(np.float64, 1280)
+
+
+def test_cfg5_block_size_512_64rhs_vs_oracle(handle):
+    """UpperTriangular BlockBandedMatrix fill(512, N), (0,3), 64 right-hand sides (N=12 of 1024)."""
+    rows = [512] * 12
+    rng = np.random.default_rng(5)
+    m = sum(rows)
+    data = rng.standard_normal(B.BlockSkylineMatrix.numentries(rows, rows, 0, 3)) / np.sqrt(512)
+    A = B.BlockSkylineMatrix(data, rows, rows, 0, 3)
+    for K in range(len(rows)):
+        s, ld = A.block_start(K, K), int(A.block_strides[K])
+        idx = np.arange(512)
+        data[s + idx + idx * ld] += 10
+    Ad = A.to_device(handle)
+    B0 = np.asfortranarray(rng.standard_normal((m, 64)))
+    dB = handle.to_device(B0)
+    B.ldiv_(B.UpperTriangular(Ad), dB)
+    got = dB.to_host()
+    ref = B0.copy(order="F")
+    O.use_openblas(threads=8)
+    O.sky_trsm(rows, 0, 3, "U", False, data, ref)
+    O.use_builtin()
+    assert relerr(got, ref) <= tol(np.float64, 2048)
+    # round trip: U * (U \ B) == B with U = upper triangle (zero the strictly lower part of the diagonal blocks)
+    udata = data.copy()
+    for K in range(len(rows)):
+        s, ld = A.block_start(K, K), int(A.block_strides[K])
+        for j in range(512):
+            udata[s + j * ld + j + 1:s + j * ld + 512] = 0.0
+    Ud = B.BlockSkylineMatrix(udata, rows, rows, 0, 3).to_device(handle)
+    back = handle.empty((m, 64), np.float64)
+    B.mul_(back, Ud, dB)
+    assert relerr(back.to_host(), B0) <= 8 * tol(np.float64, 2048)
