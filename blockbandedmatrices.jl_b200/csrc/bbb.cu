@@ -41,6 +41,7 @@ struct Partition {
     int maxseg = 0;  // longest segment (block rows)
     int nitems = 0;
     BbbItem* d_items = nullptr;
+    std::vector<BbbItem> items;  // host copy (halo-consumer counts of the fused multi-GPU path)
 };
 
 }  // namespace
@@ -77,7 +78,25 @@ struct BbbParams {
     int stage_data_bytes;  // per-stage bytes reserved for the matrix chunk
     int stage_x_bytes;     // per-stage bytes reserved for the x chunk
     int l2hint;
+    BbmPeerParams peer;    // fused halo push over NVLink peer memory (enabled == 0: plain kernel)
 };
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded wait for a flag written by another GPU (about a second, then the call is marked failed)
+__device__ __forceinline__ void peer_wait(const unsigned* flag, unsigned epoch, unsigned* err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1u); break; }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // band-walk kernel
@@ -136,6 +155,36 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     }
     __syncthreads();
 
+    if (p.peer.enabled && blockIdx.x == 0 && blockIdx.y == 0) {
+        // wait until the neighbours have consumed what the previous epoch pushed, then push my boundary
+        // x blocks into their halo regions and publish the epoch
+        const BbmPeerParams& pe = p.peer;
+        if (tid == 0) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                if (pe.dst[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 1, &pe.local->err);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!pe.dst[sd]) continue;
+            T* dst = static_cast<T*>(pe.dst[sd]);
+            const T* src = p.X + pe.src_off[sd];
+            for (long long i = tid; i < pe.cnt[sd]; i += tile) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            // I am the RIGHT neighbour of my left neighbour, and vice versa
+            if (pe.dst[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
+            if (pe.dst[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
+            // a halo nobody reads (no work item touches it) is acknowledged at once
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                if (pe.has_halo[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
+        }
+    }
+
     uint64_t pol_stream = 0, pol_keep = 0;
     if (tid == 0 && p.l2hint) {
         pol_stream = ptx::policy_evict_first();
@@ -161,13 +210,18 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         const uint32_t dbytes = static_cast<uint32_t>(dg1 - dg0);
         const uint32_t xbytes = static_cast<uint32_t>(xg1 - xg0);
         ptx::mbar_arrive_expect_tx(&bars[st], dbytes + xbytes);
-        if (p.l2hint) {
-            ptx::bulk_g2s_hint(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st], pol_stream);
-            ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
-        } else {
-            ptx::bulk_g2s(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st]);
-            ptx::bulk_g2s(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st]);
+        if (p.l2hint) ptx::bulk_g2s_hint(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st], pol_stream);
+        else ptx::bulk_g2s(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st]);
+        if (p.peer.enabled) {
+            // a halo block column: its x block is stored by the neighbour's CTA 0 -- wait for its epoch flag,
+            // then order the (generic-proxy) acquire before the async-proxy bulk read
+            const int Jl = Jfirst + it;
+            if (Jl < p.peer.own_J0) peer_wait(&p.peer.local->data_flag[0], p.peer.epoch, &p.peer.local->err);
+            else if (Jl >= p.peer.own_J1) peer_wait(&p.peer.local->data_flag[1], p.peer.epoch, &p.peer.local->err);
+            asm volatile("fence.proxy.async;" ::: "memory");
         }
+        if (p.l2hint) ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
+        else ptx::bulk_g2s(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st]);
     };
 
     if (tid == 0) {
@@ -264,6 +318,25 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
 #pragma unroll
         for (int s = 0; s + 1 < NS; ++s) acc[s] = acc[s + 1];
         acc[NS - 1] = T(0);
+    }
+
+    if (p.peer.enabled && blockIdx.y == 0) {
+        // tell the neighbour whose data I read that its next push may overwrite my halo
+        const BbmPeerParams& pe = p.peer;
+        const bool used[2] = {Jfirst < pe.own_J0, Jfirst + nsteps - 1 >= pe.own_J1};
+        if (tid == 0) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                if (!used[sd] || !pe.has_halo[sd]) continue;
+                __threadfence();
+                const unsigned c = atomicAdd(&pe.local->count[sd], 1u);
+                if (c + 1 == (unsigned)pe.consumers[sd]) {
+                    pe.local->count[sd] = 0;
+                    __threadfence_system();
+                    st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
+                }
+            }
+        }
     }
 }
 
@@ -399,6 +472,7 @@ int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, P
     out->tile = tile;
     out->maxseg = maxseg;
     out->nitems = (int)items.size();
+    out->items = items;
     out->d_items = nullptr;
     if (!items.empty()) {
         cudaError_t e = cudaMalloc(&out->d_items, items.size() * sizeof(BbbItem));
@@ -465,7 +539,8 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     const i64 force = bbm_opt(h, "bbb.kernel", 0);
     bool walk = d->P > 0 && NS >= 1 && NS <= kMaxNS && force != 2;
     // tiny blocks leave the 32..256-row tiles mostly idle: use the per-row kernel
-    if (walk && force != 1 && d->m < 16 * d->Nr) walk = false;
+    if (walk && force != 1 && d->m < 16 * d->Nr && !h->peer) walk = false;
+    if (h->peer && (!walk || nrhs != 1)) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs the band-walk kernel and one right-hand side");
     const bool aligned = (reinterpret_cast<uintptr_t>(d_data) % sizeof(T) == 0) && (reinterpret_cast<uintptr_t>(d_X) % sizeof(T) == 0);
     if (!aligned) return bbm_fail(h, BBM_ERR_ARG, "device pointers must be aligned to the element size");
 
@@ -497,6 +572,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         }
         if (!tile) walk = false;  // P too large for shared memory staging
     }
+    if (h->peer && !walk) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs the band-walk kernel");
 
     if (walk) {
         walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
@@ -521,9 +597,18 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
             it = d->parts.emplace(key, part).first;
         }
         const Partition& part = it->second;
+        if (h->peer && part.nitems == 0) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push: empty work partition");
         if (part.nitems > 0) {
             walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
             p.items = part.d_items;
+            if (h->peer) {
+                p.peer = *h->peer;
+                p.peer.consumers[0] = p.peer.consumers[1] = 0;
+                for (const BbbItem& it : part.items) {
+                    if ((i64)it.Ka - d->l < p.peer.own_J0) ++p.peer.consumers[0];
+                    if ((i64)it.Kb - 1 + d->u >= p.peer.own_J1) ++p.peer.consumers[1];
+                }
+            }
             p.stages = stages;
             p.maxseg = part.maxseg;
             p.stage_data_bytes = dbytes;

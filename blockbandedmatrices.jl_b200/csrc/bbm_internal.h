@@ -13,6 +13,32 @@
 
 using i64 = int64_t;
 
+// Fused halo push of the multi-GPU band-walk matvec (csrc/dist.cu sets it up, csrc/bbb.cu consumes it).
+// CTA 0 of every rank's kernel stores its boundary x blocks straight into the neighbours' x_local halo
+// regions over NVLink peer memory and raises an epoch flag there; the CTAs whose steps read a halo
+// column wait for the flag (acquire.sys) before issuing that step's x copy.  The neighbour's "consumed"
+// acknowledgement keeps epoch e+1 from overwriting a halo that epoch e is still reading.
+struct BbmPeerSig {            // lives in each rank's device memory, mapped into both neighbours
+    unsigned data_flag[2];     // [0]: left neighbour filled my left halo for epoch e, [1]: right
+    unsigned ack_flag[2];      // [0]: left neighbour consumed what I pushed to it in epoch e, [1]: right
+    unsigned count[2];         // local: finished consumer CTAs of my left / right halo this epoch
+    unsigned err;              // set if a wait timed out (result of that call is invalid)
+    unsigned pad;
+};
+
+struct BbmPeerParams {
+    int enabled = 0;
+    unsigned epoch = 0;
+    void* dst[2] = {nullptr, nullptr};          // neighbour halo regions (left, right) in peer memory
+    long long src_off[2] = {0, 0};              // element offsets into my x_local
+    long long cnt[2] = {0, 0};                  // elements to push
+    BbmPeerSig* remote[2] = {nullptr, nullptr}; // neighbours' signal blocks
+    BbmPeerSig* local = nullptr;
+    int own_J0 = 0, own_J1 = 0;                 // local block-column range this rank owns
+    int has_halo[2] = {0, 0};                   // a neighbour fills my left / right halo
+    int consumers[2] = {0, 0};                  // CTAs reading each halo (filled by the launcher from the work partition)
+};
+
 struct bbm_context {
     uint32_t magic = 0xBB200C0Du;
     int device = 0;
@@ -26,6 +52,7 @@ struct bbm_context {
     void* ws_x = nullptr; size_t ws_x_bytes = 0;
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
     // low-priority side stream (L2 prefetch ahead of the triangular solve's sequential chain)
+    const BbmPeerParams* peer = nullptr;  // non-null only inside a fused multi-GPU product call
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_ev[2] = {nullptr, nullptr};
 };

@@ -37,6 +37,7 @@ struct Nccl {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -64,6 +65,7 @@ bool nccl_load() {
     BIND(CommDestroy, "ncclCommDestroy")
     BIND(Send, "ncclSend")
     BIND(Recv, "ncclRecv")
+    BIND(AllGather, "ncclAllGather")
     BIND(GroupStart, "ncclGroupStart")
     BIND(GroupEnd, "ncclGroupEnd")
     BIND(GetErrorString, "ncclGetErrorString")
@@ -120,6 +122,19 @@ struct GraphKey {
 
 struct bbm_dist_bbb_plan {
     uint32_t magic = 0xD157B200u;
+    // global structure (neighbour layouts are recomputed from it)
+    i64 Nr = 0, Nc = 0, l = 0, u = 0, lam = 0, mu = 0;
+    std::vector<i64> r, c, kb;
+    // fused halo push over NVLink peer memory (bbm_dist_bbb_register_x)
+    bool peer_ok = false;
+    void* reg_x = nullptr;
+    int reg_elem = 0;
+    unsigned epoch = 0;
+    BbmPeerParams peer_tpl;
+    BbmPeerSig* sig = nullptr;
+    void* ipc_x[2] = {nullptr, nullptr};
+    void* ipc_sig[2] = {nullptr, nullptr};
+    bbm_bbb_desc_t desc_all = nullptr;
     cudaGraphExec_t gexec = nullptr;  // cached CUDA graph of one whole step
     GraphKey gkey;
     i64 glaunches = 0;
@@ -259,7 +274,26 @@ int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* 
     if (nrhs == 0) return BBM_OK;
     BBM_CUDA(h, cudaSetDevice(h->device));
     const bool exchange = cm && cm->comm && cm->nranks > 1 && (!pl->sends.empty() || !pl->recvs.empty());
-    const bool want_graph = exchange && bbm_opt(h, "dist.graph", 1) != 0;
+    if (pl->peer_ok && nrhs == 1 && (void*)d_x_local == pl->reg_x && (int)sizeof(T) == pl->reg_elem &&
+        bbm_opt(h, "dist.peer", 1) != 0) {
+        // ONE kernel per step: CTA 0 pushes the boundary x blocks into the neighbours' halos over NVLink
+        // peer memory, halo-reading CTAs wait on the epoch flag, everything else streams as on one GPU
+        BbmPeerParams pp = pl->peer_tpl;
+        pp.enabled = 1;
+        pp.epoch = ++pl->epoch;
+        const bbm_dist_layout& L = pl->lay;
+        h->peer = &pp;
+        int32_t rc;
+        if (sizeof(T) == 8)
+            rc = bbm_bbb_mul_f64(h, pl->desc_all, (double)alpha, (const double*)d_data_local, (const double*)d_x_local,
+                                 std::max<i64>(1, L.n_local), 1, (double)beta, (double*)d_y_own, std::max<i64>(1, L.m_own));
+        else
+            rc = bbm_bbb_mul_f32(h, pl->desc_all, (float)alpha, (const float*)d_data_local, (const float*)d_x_local,
+                                 std::max<i64>(1, L.n_local), 1, (float)beta, (float*)d_y_own, std::max<i64>(1, L.m_own));
+        h->peer = nullptr;
+        return rc;
+    }
+    const bool want_graph = exchange && bbm_opt(h, "dist.graph", 0) != 0;
     if (!want_graph) return dist_enqueue<T>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
 
     // Repeated products with the same buffers (every iterative solver) replay one CUDA graph of the
@@ -408,6 +442,8 @@ int32_t bbm_dist_bbb_plan_create(bbm_comm_t cm, int64_t Nr, int64_t Nc, const in
     bbm_dist_bbb_plan* pl = new (std::nothrow) bbm_dist_bbb_plan();
     if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
     pl->comm = cm; pl->h = h;
+    pl->Nr = Nr; pl->Nc = Nc; pl->l = l; pl->u = u; pl->lam = lam; pl->mu = mu;
+    pl->r.assign(r, r + Nr); pl->c.assign(c, c + Nc); pl->kb = kb;
     int32_t rc = layout_impl(Nr, Nc, r, c, l, u, cm->nranks, cm->rank, kb.data(), &pl->lay, &pl->sends, &pl->recvs);
     if (rc != BBM_OK) { delete pl; return bbm_fail(h, rc, "bad partition"); }
     const i64 nb = std::max<i64>(0, l + u + 1), w = std::max<i64>(0, lam + mu + 1);
@@ -438,6 +474,12 @@ int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
     for (int i = 0; i < 3; ++i)
         if (pl->desc[i]) bbm_bbb_desc_destroy(pl->desc[i]);
     if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
+    if (pl->desc_all) bbm_bbb_desc_destroy(pl->desc_all);
+    for (int i = 0; i < 2; ++i) {
+        if (pl->ipc_x[i]) cudaIpcCloseMemHandle(pl->ipc_x[i]);
+        if (pl->ipc_sig[i]) cudaIpcCloseMemHandle(pl->ipc_sig[i]);
+    }
+    if (pl->sig) cudaFree(pl->sig);
     pl->magic = 0;
     delete pl;
     return BBM_OK;
@@ -446,6 +488,124 @@ int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
 int32_t bbm_dist_bbb_plan_layout(bbm_dist_bbb_plan_t pl, bbm_dist_layout* out) {
     if (!plan_valid(pl) || !out) return BBM_ERR_HANDLE;
     *out = pl->lay;
+    return BBM_OK;
+}
+
+
+int32_t bbm_dist_bbb_register_x(bbm_dist_bbb_plan_t pl, void* d_x_local, int32_t elem_size) {
+    if (!plan_valid(pl)) return BBM_ERR_HANDLE;
+    bbm_handle_t h = pl->h;
+    bbm_comm* cm = pl->comm;
+    if (!cm || !cm->comm || cm->nranks < 2) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs an NCCL communicator over >= 2 ranks");
+    if (!d_x_local || (elem_size != 4 && elem_size != 8)) return bbm_fail(h, BBM_ERR_ARG, "bad x_local registration");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const int rank = cm->rank, nranks = cm->nranks;
+    const bbm_dist_layout& L = pl->lay;
+    // local feasibility: halos only from / to the immediate neighbours, a non-empty band-walk problem
+    bool ok = pl->P > 0 && pl->l + pl->u + 1 <= 8 && L.m_own > 0;
+    BbmPeerParams tpl;
+    tpl.own_J0 = (int)(L.J0 - L.Jlo);
+    tpl.own_J1 = (int)(L.J1 - L.Jlo);
+    i64 dst_off[2] = {0, 0};
+    for (size_t i = 0; i + 2 < pl->recvs.size(); i += 3) {
+        const int q = (int)pl->recvs[i];
+        if (q == rank - 1 && !tpl.has_halo[0] && pl->recvs[i + 1] < L.own_offset) tpl.has_halo[0] = 1;
+        else if (q == rank + 1 && !tpl.has_halo[1] && pl->recvs[i + 1] >= L.own_offset + L.n_own) tpl.has_halo[1] = 1;
+        else ok = false;
+    }
+    for (size_t i = 0; i + 2 < pl->sends.size(); i += 3) {
+        const int q = (int)pl->sends[i];
+        const int sd = q == rank - 1 ? 0 : (q == rank + 1 ? 1 : -1);
+        if (sd < 0 || tpl.cnt[sd] != 0) { ok = false; continue; }
+        tpl.src_off[sd] = pl->sends[i + 1];
+        tpl.cnt[sd] = pl->sends[i + 2];
+        // where the neighbour expects it: its recv entry for me
+        bbm_dist_layout Lq;
+        std::vector<i64> sq, rq;
+        if (layout_impl(pl->Nr, pl->Nc, pl->r.data(), pl->c.data(), pl->l, pl->u, nranks, q, pl->kb.data(), &Lq, &sq, &rq) != BBM_OK) { ok = false; continue; }
+        bool found = false;
+        for (size_t k = 0; k + 2 < rq.size(); k += 3)
+            if ((int)rq[k] == rank && rq[k + 2] == tpl.cnt[sd]) { dst_off[sd] = rq[k + 1]; found = true; }
+        if (!found) ok = false;
+    }
+    // one descriptor for all owned rows over the local column slab
+    if (ok && !pl->desc_all) {
+        const i64 s = L.K0 - L.Jlo;
+        int32_t rc = bbm_bbb_desc_create(h, L.K1 - L.K0, L.Jhi - L.Jlo, pl->r.data() + L.K0, pl->c.data() + L.Jlo, pl->l - s,
+                                         pl->u + s, pl->lam, pl->mu, &pl->desc_all);
+        if (rc != BBM_OK) ok = false;
+    }
+    if (!pl->sig) {
+        BBM_CUDA(h, cudaMalloc(&pl->sig, sizeof(BbmPeerSig)));
+        BBM_CUDA(h, cudaMemset(pl->sig, 0, sizeof(BbmPeerSig)));
+    }
+    // all-gather (ok flag, IPC handle of x_local, IPC handle of the signal block) over NCCL
+    struct Rec { int ok; int pad[3]; cudaIpcMemHandle_t x, sig; };
+    Rec mine{};
+    mine.ok = ok ? 1 : 0;
+    if (cudaIpcGetMemHandle(&mine.x, d_x_local) != cudaSuccess || cudaIpcGetMemHandle(&mine.sig, pl->sig) != cudaSuccess) {
+        cudaGetLastError();
+        mine.ok = 0;
+    }
+    std::vector<Rec> all(nranks);
+    Rec* d_all = nullptr;
+    BBM_CUDA(h, cudaMalloc(&d_all, sizeof(Rec) * nranks));
+    BBM_CUDA(h, cudaMemcpy(d_all + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+    ncclResult_t nrc = nccl().AllGather(d_all + rank, d_all, sizeof(Rec), ncclChar, cm->comm, cm->stream);
+    if (nrc != ncclSuccess) { cudaFree(d_all); return bbm_fail(h, BBM_ERR_NCCL, "ncclAllGather: %s", nccl().GetErrorString(nrc)); }
+    BBM_CUDA(h, cudaStreamSynchronize(cm->stream));
+    BBM_CUDA(h, cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    bool all_ok = true;
+    for (int q = 0; q < nranks; ++q) all_ok = all_ok && all[q].ok == 1;
+    pl->peer_ok = false;
+    if (!all_ok) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push not applicable to this partition; the NCCL exchange stays in use");
+    for (int sd = 0; sd < 2; ++sd) {
+        const int q = sd == 0 ? rank - 1 : rank + 1;
+        if (q < 0 || q >= nranks || (tpl.cnt[sd] == 0 && !tpl.has_halo[sd])) continue;
+        if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
+        if (pl->ipc_x[sd]) { cudaIpcCloseMemHandle(pl->ipc_x[sd]); pl->ipc_x[sd] = nullptr; }
+        cudaError_t e = cudaIpcOpenMemHandle(&pl->ipc_sig[sd], all[q].sig, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess && tpl.cnt[sd] > 0) e = cudaIpcOpenMemHandle(&pl->ipc_x[sd], all[q].x, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); }
+        tpl.remote[sd] = static_cast<BbmPeerSig*>(pl->ipc_sig[sd]);
+        if (tpl.cnt[sd] > 0) tpl.dst[sd] = static_cast<char*>(pl->ipc_x[sd]) + dst_off[sd] * elem_size;
+    }
+    tpl.local = pl->sig;
+    pl->peer_tpl = tpl;
+    pl->reg_x = d_x_local;
+    pl->reg_elem = elem_size;
+    pl->epoch = 0;
+    BBM_CUDA(h, cudaMemset(pl->sig, 0, sizeof(BbmPeerSig)));
+    BBM_CUDA(h, cudaDeviceSynchronize());
+    // nobody may push before every rank has reset its flags and opened its mappings
+    {
+        int* d_tok = nullptr;
+        BBM_CUDA(h, cudaMalloc(&d_tok, sizeof(int) * nranks));
+        BBM_CUDA(h, cudaMemset(d_tok, 0, sizeof(int) * nranks));
+        nrc = nccl().AllGather(d_tok + rank, d_tok, sizeof(int), ncclChar, cm->comm, cm->stream);
+        cudaStreamSynchronize(cm->stream);
+        cudaFree(d_tok);
+        if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "registration barrier: %s", nccl().GetErrorString(nrc));
+    }
+    pl->peer_ok = true;
+    return BBM_OK;
+}
+
+int32_t bbm_dist_bbb_peer_status(bbm_dist_bbb_plan_t pl, int32_t* active, int32_t* timed_out) {
+    if (!plan_valid(pl)) return BBM_ERR_HANDLE;
+    bbm_handle_t h = pl->h;
+    if (active) *active = pl->peer_ok ? 1 : 0;
+    if (timed_out) {
+        *timed_out = 0;
+        if (pl->sig) {
+            BBM_CUDA(h, cudaSetDevice(h->device));
+            BBM_CUDA(h, cudaStreamSynchronize(h->stream));
+            BbmPeerSig sg;
+            BBM_CUDA(h, cudaMemcpy(&sg, pl->sig, sizeof sg, cudaMemcpyDeviceToHost));
+            *timed_out = (int32_t)sg.err;
+        }
+    }
     return BBM_OK;
 }
 

@@ -145,6 +145,24 @@ class DistBandedBlockBandedMatrix:
                    C.c_void_p(y_own.ptr)), h.h, "bbm_dist_bbb_mul")
         return y_own
 
+    def register_x(self, x_local) -> bool:
+        """Collective.  Switch products on this x_local buffer to the fused peer-memory halo push
+        (``bbm_dist_bbb_register_x``); returns False if the partition does not qualify and the NCCL
+        exchange stays in use."""
+        h = self.comm.handle
+        rc = h._lib.bbm_dist_bbb_register_x(self.plan, C.c_void_p(x_local.ptr), self.dtype.itemsize)
+        if rc == 8:  # BBM_ERR_UNSUPPORTED
+            return False
+        L.check(rc, h.h, "bbm_dist_bbb_register_x")
+        return True
+
+    def peer_status(self):
+        """(fused path active, a peer wait timed out) -- synchronises the stream."""
+        h = self.comm.handle
+        a, t = C.c_int32(0), C.c_int32(0)
+        L.check(h._lib.bbm_dist_bbb_peer_status(self.plan, C.byref(a), C.byref(t)), h.h)
+        return bool(a.value), bool(t.value)
+
     def close(self):
         if getattr(self, "plan", None):
             self.comm.handle._lib.bbm_dist_bbb_plan_destroy(self.plan)

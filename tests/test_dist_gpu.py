@@ -1,0 +1,28 @@
+"""Multi-GPU BandedBlockBandedMatrix matvec (NCCL halo exchange and the fused peer-memory halo push)
+against the oracle.  Needs >= 2 GPUs on the box; skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_dist_matvec_multi_gpu(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert "DIST_GPU_OK" in res.stdout, res.stdout[-4000:]
