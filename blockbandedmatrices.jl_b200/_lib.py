@@ -73,7 +73,7 @@ SIGNATURES = {
     "bbm_dist_bbb_plan_create": (i32, [vp, i64, i64, vp, vp, i64, i64, i64, i64, vp, pp]),
     "bbm_dist_bbb_plan_destroy": (i32, [vp]),
     "bbm_dist_bbb_plan_layout": (i32, [vp, vp]),
-    "bbm_dist_bbb_register_x": (i32, [vp, vp, i32]),
+    "bbm_dist_bbb_enable_peer": (i32, [vp, i32]),
     "bbm_dist_bbb_peer_status": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "bbm_dist_bbb_mul_f64": (i32, [vp, f64, vp, vp, i64, f64, vp]),
     "bbm_dist_bbb_mul_f32": (i32, [vp, f32, vp, vp, i64, f32, vp]),

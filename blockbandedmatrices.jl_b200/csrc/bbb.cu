@@ -126,7 +126,38 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     const int P = p.P;
     const int S = p.stages;
 
-    const BbbItem item = p.items[blockIdx.x];
+    if (p.peer.enabled && blockIdx.x == 0) {
+        // dedicated pusher CTA (always in the first wave): store my boundary x blocks into the neighbours'
+        // halo buffers of this epoch's parity and publish the epoch.  The buffer was last read two epochs ago.
+        const BbmPeerParams& pe = p.peer;
+        if (blockIdx.y != 0) return;
+        if (tid == 0 && pe.epoch >= 2) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                if (pe.dst[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, &pe.local->err);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!pe.dst[sd]) continue;
+            T* dst = static_cast<T*>(pe.dst[sd]);
+            const T* src = p.X + pe.src_off[sd];
+            for (long long i = tid; i < pe.cnt[sd]; i += tile) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            // I am the RIGHT neighbour of my left neighbour, and vice versa
+            if (pe.dst[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
+            if (pe.dst[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
+            // a halo nobody reads (no work item touches it) is acknowledged at once
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                if (pe.has_halo[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
+        }
+        return;
+    }
+    const BbbItem item = p.items[p.peer.enabled ? blockIdx.x - 1 : blockIdx.x];
     const int Ka = item.Ka, Kb = item.Kb, k0 = item.k0;
     const int Jfirst = Ka - p.l;
     const int nsteps = (Kb - Ka) + NS - 1;
@@ -155,41 +186,23 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     }
     __syncthreads();
 
-    if (p.peer.enabled && blockIdx.x == 0 && blockIdx.y == 0) {
-        // wait until the neighbours have consumed what the previous epoch pushed, then push my boundary
-        // x blocks into their halo regions and publish the epoch
-        const BbmPeerParams& pe = p.peer;
-        if (tid == 0) {
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                if (pe.dst[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 1, &pe.local->err);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            if (!pe.dst[sd]) continue;
-            T* dst = static_cast<T*>(pe.dst[sd]);
-            const T* src = p.X + pe.src_off[sd];
-            for (long long i = tid; i < pe.cnt[sd]; i += tile) dst[i] = src[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            // I am the RIGHT neighbour of my left neighbour, and vice versa
-            if (pe.dst[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
-            if (pe.dst[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
-            // a halo nobody reads (no work item touches it) is acknowledged at once
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                if (pe.has_halo[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
-        }
-    }
-
     uint64_t pol_stream = 0, pol_keep = 0;
     if (tid == 0 && p.l2hint) {
         pol_stream = ptx::policy_evict_first();
         pol_keep = ptx::policy_evict_last();
     }
+
+    // where step `it` takes its x block from: x itself, or (fused multi-GPU path) the halo buffer a
+    // neighbour filled; both indexed by local column
+    auto xsource = [&](int it, int* side) -> const T* {
+        *side = -1;
+        if (p.peer.enabled) {
+            const int Jl = Jfirst + it;
+            *side = Jl < p.peer.own_J0 ? 0 : (Jl >= p.peer.own_J1 ? 1 : -1);
+            if (*side >= 0) return static_cast<const T*>(p.peer.halo[*side]) - p.peer.halo_col0[*side];
+        }
+        return Xq;
+    };
 
     // producer: one thread issues the bulk copies of a step and arms its barrier
     auto issue = [&](int it) {
@@ -203,8 +216,10 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         unsigned char* sx = sd + p.stage_data_bytes;
         const uintptr_t d0 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jlo) * (i64)P);
         const uintptr_t d1 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jhi) * (i64)P);
-        const uintptr_t x0 = reinterpret_cast<uintptr_t>(Xq + g.cbeg + g.jlo);
-        const uintptr_t x1 = reinterpret_cast<uintptr_t>(Xq + g.cbeg + g.jhi);
+        int halo_side = -1;
+        const T* xsrc = xsource(it, &halo_side);
+        const uintptr_t x0 = reinterpret_cast<uintptr_t>(xsrc + g.cbeg + g.jlo);
+        const uintptr_t x1 = reinterpret_cast<uintptr_t>(xsrc + g.cbeg + g.jhi);
         const uintptr_t dg0 = d0 & ~uintptr_t(15), dg1 = (d1 + 15) & ~uintptr_t(15);
         const uintptr_t xg0 = x0 & ~uintptr_t(15), xg1 = (x1 + 15) & ~uintptr_t(15);
         const uint32_t dbytes = static_cast<uint32_t>(dg1 - dg0);
@@ -212,12 +227,10 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         ptx::mbar_arrive_expect_tx(&bars[st], dbytes + xbytes);
         if (p.l2hint) ptx::bulk_g2s_hint(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st], pol_stream);
         else ptx::bulk_g2s(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st]);
-        if (p.peer.enabled) {
-            // a halo block column: its x block is stored by the neighbour's CTA 0 -- wait for its epoch flag,
-            // then order the (generic-proxy) acquire before the async-proxy bulk read
-            const int Jl = Jfirst + it;
-            if (Jl < p.peer.own_J0) peer_wait(&p.peer.local->data_flag[0], p.peer.epoch, &p.peer.local->err);
-            else if (Jl >= p.peer.own_J1) peer_wait(&p.peer.local->data_flag[1], p.peer.epoch, &p.peer.local->err);
+        if (halo_side >= 0) {
+            // a halo block column: its x block is stored by the neighbour's pusher CTA -- wait for its epoch
+            // flag, then order the (generic-proxy) acquire before the async-proxy bulk read
+            peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, &p.peer.local->err);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
         if (p.l2hint) ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
@@ -249,7 +262,8 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             const unsigned char* sd = stage0 + (size_t)st * stage_bytes;
             const unsigned char* sx = sd + p.stage_data_bytes;
             const uintptr_t d0 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jlo) * (i64)P);
-            const uintptr_t x0 = reinterpret_cast<uintptr_t>(Xq + g.cbeg + g.jlo);
+            int side_unused;
+            const uintptr_t x0 = reinterpret_cast<uintptr_t>(xsource(it, &side_unused) + g.cbeg + g.jlo);
             // Ds[(j-jlo)*P + row] = data[row, cbeg+j];  Xs[j-jlo] = x[cbeg+j]
             const T* Ds = reinterpret_cast<const T*>(sd + (d0 & 15));
             const T* Xs = reinterpret_cast<const T*>(sx + (x0 & 15));
@@ -587,7 +601,8 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         }
         const i64 ips = bbm_opt(h, "bbb.items_per_sm", 0);
         const i64 waves = std::max<i64>(1, bbm_opt(h, "bbb.waves", 1));
-        const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves);
+        // the fused multi-GPU path adds one pusher CTA: leave it a slot of the wave
+        const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves) - (h->peer ? 1 : 0);
         auto key = std::make_pair(tile, target_items * 1024 + maxseg_cap);
         auto it = d->parts.find(key);
         if (it == d->parts.end()) {
@@ -614,7 +629,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
             p.stage_data_bytes = dbytes;
             p.stage_x_bytes = xbytes;
             const size_t smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + xbytes);
-            dim3 grid((unsigned)part.nitems, (unsigned)nrhs, 1);
+            dim3 grid((unsigned)part.nitems + (h->peer ? 1u : 0u), (unsigned)nrhs, 1);
             cudaError_t e = launch_walk<T>(p, (int)NS, w, grid, tile, smem, h->stream);
             if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_walk_kernel launch: %s", cudaGetErrorString(e));
             h->launches += 1;

@@ -14,11 +14,13 @@
 using i64 = int64_t;
 
 // Fused halo push of the multi-GPU band-walk matvec (csrc/dist.cu sets it up, csrc/bbb.cu consumes it).
-// CTA 0 of every rank's kernel stores its boundary x blocks straight into the neighbours' x_local halo
-// regions over NVLink peer memory and raises an epoch flag there; the CTAs whose steps read a halo
-// column wait for the flag (acquire.sys) before issuing that step's x copy.  The neighbour's "consumed"
-// acknowledgement keeps epoch e+1 from overwriting a halo that epoch e is still reading.
-struct BbmPeerSig {            // lives in each rank's device memory, mapped into both neighbours
+// Every rank owns a small device block [BbmPeerSig | left halo x2 | right halo x2] that is mapped into both
+// neighbours (CUDA IPC).  An extra CTA 0 of every rank's kernel stores the rank's boundary x blocks
+// straight into the neighbours' halo buffers of the epoch's parity over NVLink and raises the epoch flag
+// there; CTAs whose steps read a halo block column wait for the flag (acquire.sys) and take that step's x
+// from the halo buffer.  Buffers alternate by epoch parity, so a push only has to wait for the
+// acknowledgement of two epochs ago and never sits on the critical path.
+struct BbmPeerSig {
     unsigned data_flag[2];     // [0]: left neighbour filled my left halo for epoch e, [1]: right
     unsigned ack_flag[2];      // [0]: left neighbour consumed what I pushed to it in epoch e, [1]: right
     unsigned count[2];         // local: finished consumer CTAs of my left / right halo this epoch
@@ -29,14 +31,16 @@ struct BbmPeerSig {            // lives in each rank's device memory, mapped int
 struct BbmPeerParams {
     int enabled = 0;
     unsigned epoch = 0;
-    void* dst[2] = {nullptr, nullptr};          // neighbour halo regions (left, right) in peer memory
-    long long src_off[2] = {0, 0};              // element offsets into my x_local
-    long long cnt[2] = {0, 0};                  // elements to push
-    BbmPeerSig* remote[2] = {nullptr, nullptr}; // neighbours' signal blocks
+    void* dst[2] = {nullptr, nullptr};            // neighbour halo buffers of this parity (left, right neighbour)
+    long long src_off[2] = {0, 0};                // element offsets into my x_local of what I push
+    long long cnt[2] = {0, 0};                    // elements to push
+    BbmPeerSig* remote[2] = {nullptr, nullptr};   // neighbours' signal blocks
     BbmPeerSig* local = nullptr;
-    int own_J0 = 0, own_J1 = 0;                 // local block-column range this rank owns
-    int has_halo[2] = {0, 0};                   // a neighbour fills my left / right halo
-    int consumers[2] = {0, 0};                  // CTAs reading each halo (filled by the launcher from the work partition)
+    const void* halo[2] = {nullptr, nullptr};     // my halo buffers of this parity
+    long long halo_col0[2] = {0, 0};              // first local column each halo buffer stands for
+    int own_J0 = 0, own_J1 = 0;                   // local block-column range this rank owns
+    int has_halo[2] = {0, 0};                     // a neighbour fills my left / right halo
+    int consumers[2] = {0, 0};                    // CTAs reading each halo (filled by the launcher)
 };
 
 struct bbm_context {

@@ -127,13 +127,13 @@ struct bbm_dist_bbb_plan {
     std::vector<i64> r, c, kb;
     // fused halo push over NVLink peer memory (bbm_dist_bbb_register_x)
     bool peer_ok = false;
-    void* reg_x = nullptr;
     int reg_elem = 0;
     unsigned epoch = 0;
     BbmPeerParams peer_tpl;
     BbmPeerSig* sig = nullptr;
-    void* ipc_x[2] = {nullptr, nullptr};
-    void* ipc_sig[2] = {nullptr, nullptr};
+    void* ipc_sig[2] = {nullptr, nullptr};   // neighbours' blocks mapped here
+    size_t own_buf[2][2] = {{0, 0}, {0, 0}}; // [side][parity] byte offsets of my halo buffers in my block
+    size_t nb_buf[2][2] = {{0, 0}, {0, 0}};  // [side][parity] byte offsets of the buffers I fill in the neighbours' blocks
     bbm_bbb_desc_t desc_all = nullptr;
     cudaGraphExec_t gexec = nullptr;  // cached CUDA graph of one whole step
     GraphKey gkey;
@@ -274,13 +274,18 @@ int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* 
     if (nrhs == 0) return BBM_OK;
     BBM_CUDA(h, cudaSetDevice(h->device));
     const bool exchange = cm && cm->comm && cm->nranks > 1 && (!pl->sends.empty() || !pl->recvs.empty());
-    if (pl->peer_ok && nrhs == 1 && (void*)d_x_local == pl->reg_x && (int)sizeof(T) == pl->reg_elem &&
-        bbm_opt(h, "dist.peer", 1) != 0) {
-        // ONE kernel per step: CTA 0 pushes the boundary x blocks into the neighbours' halos over NVLink
-        // peer memory, halo-reading CTAs wait on the epoch flag, everything else streams as on one GPU
+    if (pl->peer_ok && nrhs == 1 && (int)sizeof(T) == pl->reg_elem && bbm_opt(h, "dist.peer", 1) != 0) {
+        // ONE kernel per step: a pusher CTA stores the boundary x blocks into the neighbours' halo buffers
+        // over NVLink peer memory, halo-reading CTAs wait on the epoch flag, everything else streams as on
+        // one GPU.  (The halo parts of x_local are neither read nor written on this path.)
         BbmPeerParams pp = pl->peer_tpl;
         pp.enabled = 1;
         pp.epoch = ++pl->epoch;
+        const int par = (int)(pp.epoch & 1u);
+        for (int sd = 0; sd < 2; ++sd) {
+            pp.halo[sd] = pp.has_halo[sd] ? reinterpret_cast<const char*>(pl->sig) + pl->own_buf[sd][par] : nullptr;
+            pp.dst[sd] = (pp.cnt[sd] > 0 && pl->ipc_sig[sd]) ? static_cast<char*>(pl->ipc_sig[sd]) + pl->nb_buf[sd][par] : nullptr;
+        }
         const bbm_dist_layout& L = pl->lay;
         h->peer = &pp;
         int32_t rc;
@@ -475,10 +480,8 @@ int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
         if (pl->desc[i]) bbm_bbb_desc_destroy(pl->desc[i]);
     if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
     if (pl->desc_all) bbm_bbb_desc_destroy(pl->desc_all);
-    for (int i = 0; i < 2; ++i) {
-        if (pl->ipc_x[i]) cudaIpcCloseMemHandle(pl->ipc_x[i]);
+    for (int i = 0; i < 2; ++i)
         if (pl->ipc_sig[i]) cudaIpcCloseMemHandle(pl->ipc_sig[i]);
-    }
     if (pl->sig) cudaFree(pl->sig);
     pl->magic = 0;
     delete pl;
@@ -492,41 +495,65 @@ int32_t bbm_dist_bbb_plan_layout(bbm_dist_bbb_plan_t pl, bbm_dist_layout* out) {
 }
 
 
-int32_t bbm_dist_bbb_register_x(bbm_dist_bbb_plan_t pl, void* d_x_local, int32_t elem_size) {
+int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t pl, int32_t elem_size) {
     if (!plan_valid(pl)) return BBM_ERR_HANDLE;
     bbm_handle_t h = pl->h;
     bbm_comm* cm = pl->comm;
     if (!cm || !cm->comm || cm->nranks < 2) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs an NCCL communicator over >= 2 ranks");
-    if (!d_x_local || (elem_size != 4 && elem_size != 8)) return bbm_fail(h, BBM_ERR_ARG, "bad x_local registration");
+    if (elem_size != 4 && elem_size != 8) return bbm_fail(h, BBM_ERR_ARG, "element size must be 4 or 8");
     BBM_CUDA(h, cudaSetDevice(h->device));
     const int rank = cm->rank, nranks = cm->nranks;
     const bbm_dist_layout& L = pl->lay;
-    // local feasibility: halos only from / to the immediate neighbours, a non-empty band-walk problem
+    // halo element counts (left, right) of any rank, from the deterministic layout
+    auto halo_counts = [&](int q, i64* cntL, i64* cntR, i64* colL, i64* colR) -> bool {
+        bbm_dist_layout Lq;
+        std::vector<i64> sq, rq;
+        if (layout_impl(pl->Nr, pl->Nc, pl->r.data(), pl->c.data(), pl->l, pl->u, nranks, q, pl->kb.data(), &Lq, &sq, &rq) != BBM_OK) return false;
+        *cntL = *cntR = 0; *colL = *colR = 0;
+        bool fine = true;
+        for (size_t k = 0; k + 2 < rq.size(); k += 3) {
+            const int from = (int)rq[k];
+            if (from == q - 1 && *cntL == 0 && rq[k + 1] < Lq.own_offset) { *cntL = rq[k + 2]; *colL = rq[k + 1]; }
+            else if (from == q + 1 && *cntR == 0 && rq[k + 1] >= Lq.own_offset + Lq.n_own) { *cntR = rq[k + 2]; *colR = rq[k + 1]; }
+            else fine = false;  // a halo that reaches past the immediate neighbour
+        }
+        return fine;
+    };
+    auto pad256 = [](size_t b) { return (b + 255) & ~size_t(255); };
+    // device block of rank q: [sig 256 B][pad 256][L0][L1][R0][R1], each buffer padded by 256 B on both sides
+    auto buf_off = [&](i64 cntL, i64 cntR, int side, int parity) -> size_t {
+        const size_t bl = pad256((size_t)cntL * elem_size) + 256, br = pad256((size_t)cntR * elem_size) + 256;
+        size_t off = 512;
+        if (side == 0) return off + (size_t)parity * bl;
+        off += 2 * bl;
+        return off + (size_t)parity * br;
+    };
+    i64 myL = 0, myR = 0, mycolL = 0, mycolR = 0;
     bool ok = pl->P > 0 && pl->l + pl->u + 1 <= 8 && L.m_own > 0;
+    ok = halo_counts(rank, &myL, &myR, &mycolL, &mycolR) && ok;
     BbmPeerParams tpl;
     tpl.own_J0 = (int)(L.J0 - L.Jlo);
     tpl.own_J1 = (int)(L.J1 - L.Jlo);
-    i64 dst_off[2] = {0, 0};
-    for (size_t i = 0; i + 2 < pl->recvs.size(); i += 3) {
-        const int q = (int)pl->recvs[i];
-        if (q == rank - 1 && !tpl.has_halo[0] && pl->recvs[i + 1] < L.own_offset) tpl.has_halo[0] = 1;
-        else if (q == rank + 1 && !tpl.has_halo[1] && pl->recvs[i + 1] >= L.own_offset + L.n_own) tpl.has_halo[1] = 1;
-        else ok = false;
-    }
+    tpl.has_halo[0] = myL > 0; tpl.has_halo[1] = myR > 0;
+    tpl.halo_col0[0] = mycolL; tpl.halo_col0[1] = mycolR;
+    i64 nbL[2] = {0, 0}, nbR[2] = {0, 0};  // halo counts of my left / right neighbour
     for (size_t i = 0; i + 2 < pl->sends.size(); i += 3) {
         const int q = (int)pl->sends[i];
         const int sd = q == rank - 1 ? 0 : (q == rank + 1 ? 1 : -1);
         if (sd < 0 || tpl.cnt[sd] != 0) { ok = false; continue; }
         tpl.src_off[sd] = pl->sends[i + 1];
         tpl.cnt[sd] = pl->sends[i + 2];
-        // where the neighbour expects it: its recv entry for me
-        bbm_dist_layout Lq;
-        std::vector<i64> sq, rq;
-        if (layout_impl(pl->Nr, pl->Nc, pl->r.data(), pl->c.data(), pl->l, pl->u, nranks, q, pl->kb.data(), &Lq, &sq, &rq) != BBM_OK) { ok = false; continue; }
-        bool found = false;
-        for (size_t k = 0; k + 2 < rq.size(); k += 3)
-            if ((int)rq[k] == rank && rq[k + 2] == tpl.cnt[sd]) { dst_off[sd] = rq[k + 1]; found = true; }
-        if (!found) ok = false;
+        i64 cl, cr;
+        if (!halo_counts(q, &nbL[sd], &nbR[sd], &cl, &cr)) ok = false;
+        // what I send to my left neighbour is its RIGHT halo and vice versa
+        if ((sd == 0 ? nbR[sd] : nbL[sd]) != tpl.cnt[sd]) ok = false;
+    }
+    for (int sd = 0; sd < 2; ++sd) {  // neighbours I only receive from still need their signal block
+        const int q = sd == 0 ? rank - 1 : rank + 1;
+        if (tpl.has_halo[sd] && tpl.cnt[sd] == 0 && q >= 0 && q < nranks) {
+            i64 cl, cr;
+            if (!halo_counts(q, &nbL[sd], &nbR[sd], &cl, &cr)) ok = false;
+        }
     }
     // one descriptor for all owned rows over the local column slab
     if (ok && !pl->desc_all) {
@@ -535,18 +562,16 @@ int32_t bbm_dist_bbb_register_x(bbm_dist_bbb_plan_t pl, void* d_x_local, int32_t
                                          pl->u + s, pl->lam, pl->mu, &pl->desc_all);
         if (rc != BBM_OK) ok = false;
     }
-    if (!pl->sig) {
-        BBM_CUDA(h, cudaMalloc(&pl->sig, sizeof(BbmPeerSig)));
-        BBM_CUDA(h, cudaMemset(pl->sig, 0, sizeof(BbmPeerSig)));
-    }
-    // all-gather (ok flag, IPC handle of x_local, IPC handle of the signal block) over NCCL
-    struct Rec { int ok; int pad[3]; cudaIpcMemHandle_t x, sig; };
+    if (pl->sig) { cudaFree(pl->sig); pl->sig = nullptr; }
+    const size_t block_bytes = buf_off(myL, myR, 1, 1) + pad256((size_t)myR * elem_size) + 512;
+    BBM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&pl->sig), block_bytes));
+    BBM_CUDA(h, cudaMemset(pl->sig, 0, block_bytes));
+    BBM_CUDA(h, cudaDeviceSynchronize());
+    // all-gather (ok flag, IPC handle of the block) over NCCL
+    struct Rec { int ok; int pad[3]; cudaIpcMemHandle_t blk; };
     Rec mine{};
     mine.ok = ok ? 1 : 0;
-    if (cudaIpcGetMemHandle(&mine.x, d_x_local) != cudaSuccess || cudaIpcGetMemHandle(&mine.sig, pl->sig) != cudaSuccess) {
-        cudaGetLastError();
-        mine.ok = 0;
-    }
+    if (cudaIpcGetMemHandle(&mine.blk, pl->sig) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
     std::vector<Rec> all(nranks);
     Rec* d_all = nullptr;
     BBM_CUDA(h, cudaMalloc(&d_all, sizeof(Rec) * nranks));
@@ -555,39 +580,34 @@ int32_t bbm_dist_bbb_register_x(bbm_dist_bbb_plan_t pl, void* d_x_local, int32_t
     if (nrc != ncclSuccess) { cudaFree(d_all); return bbm_fail(h, BBM_ERR_NCCL, "ncclAllGather: %s", nccl().GetErrorString(nrc)); }
     BBM_CUDA(h, cudaStreamSynchronize(cm->stream));
     BBM_CUDA(h, cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost));
-    cudaFree(d_all);
     bool all_ok = true;
     for (int q = 0; q < nranks; ++q) all_ok = all_ok && all[q].ok == 1;
     pl->peer_ok = false;
-    if (!all_ok) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push not applicable to this partition; the NCCL exchange stays in use");
+    if (!all_ok) { cudaFree(d_all); return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push not applicable to this partition; the NCCL exchange stays in use"); }
     for (int sd = 0; sd < 2; ++sd) {
         const int q = sd == 0 ? rank - 1 : rank + 1;
-        if (q < 0 || q >= nranks || (tpl.cnt[sd] == 0 && !tpl.has_halo[sd])) continue;
         if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
-        if (pl->ipc_x[sd]) { cudaIpcCloseMemHandle(pl->ipc_x[sd]); pl->ipc_x[sd] = nullptr; }
-        cudaError_t e = cudaIpcOpenMemHandle(&pl->ipc_sig[sd], all[q].sig, cudaIpcMemLazyEnablePeerAccess);
-        if (e == cudaSuccess && tpl.cnt[sd] > 0) e = cudaIpcOpenMemHandle(&pl->ipc_x[sd], all[q].x, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); }
+        if (q < 0 || q >= nranks || (tpl.cnt[sd] == 0 && !tpl.has_halo[sd])) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&pl->ipc_sig[sd], all[q].blk, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(d_all); return bbm_fail(h, BBM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); }
         tpl.remote[sd] = static_cast<BbmPeerSig*>(pl->ipc_sig[sd]);
-        if (tpl.cnt[sd] > 0) tpl.dst[sd] = static_cast<char*>(pl->ipc_x[sd]) + dst_off[sd] * elem_size;
     }
     tpl.local = pl->sig;
     pl->peer_tpl = tpl;
-    pl->reg_x = d_x_local;
     pl->reg_elem = elem_size;
     pl->epoch = 0;
-    BBM_CUDA(h, cudaMemset(pl->sig, 0, sizeof(BbmPeerSig)));
-    BBM_CUDA(h, cudaDeviceSynchronize());
-    // nobody may push before every rank has reset its flags and opened its mappings
-    {
-        int* d_tok = nullptr;
-        BBM_CUDA(h, cudaMalloc(&d_tok, sizeof(int) * nranks));
-        BBM_CUDA(h, cudaMemset(d_tok, 0, sizeof(int) * nranks));
-        nrc = nccl().AllGather(d_tok + rank, d_tok, sizeof(int), ncclChar, cm->comm, cm->stream);
-        cudaStreamSynchronize(cm->stream);
-        cudaFree(d_tok);
-        if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "registration barrier: %s", nccl().GetErrorString(nrc));
+    // byte offsets of the buffers this rank reads (its own) and writes (the neighbours')
+    for (int par = 0; par < 2; ++par) {
+        pl->own_buf[0][par] = buf_off(myL, myR, 0, par) + 256;
+        pl->own_buf[1][par] = buf_off(myL, myR, 1, par) + 256;
+        pl->nb_buf[0][par] = buf_off(nbL[0], nbR[0], 1, par) + 256;  // left neighbour's RIGHT halo
+        pl->nb_buf[1][par] = buf_off(nbL[1], nbR[1], 0, par) + 256;  // right neighbour's LEFT halo
     }
+    // nobody may push before every rank has reset its flags and opened its mappings
+    nrc = nccl().AllGather(d_all + rank, d_all, sizeof(Rec), ncclChar, cm->comm, cm->stream);
+    cudaStreamSynchronize(cm->stream);
+    cudaFree(d_all);
+    if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "enable_peer barrier: %s", nccl().GetErrorString(nrc));
     pl->peer_ok = true;
     return BBM_OK;
 }

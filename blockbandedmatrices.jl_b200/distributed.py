@@ -145,15 +145,15 @@ class DistBandedBlockBandedMatrix:
                    C.c_void_p(y_own.ptr)), h.h, "bbm_dist_bbb_mul")
         return y_own
 
-    def register_x(self, x_local) -> bool:
-        """Collective.  Switch products on this x_local buffer to the fused peer-memory halo push
-        (``bbm_dist_bbb_register_x``); returns False if the partition does not qualify and the NCCL
-        exchange stays in use."""
+    def enable_peer(self) -> bool:
+        """Collective.  Switch the halo exchange to the fused peer-memory push inside the band-walk
+        kernel (``bbm_dist_bbb_enable_peer``); returns False if the partition does not qualify and
+        the NCCL exchange stays in use."""
         h = self.comm.handle
-        rc = h._lib.bbm_dist_bbb_register_x(self.plan, C.c_void_p(x_local.ptr), self.dtype.itemsize)
+        rc = h._lib.bbm_dist_bbb_enable_peer(self.plan, self.dtype.itemsize)
         if rc == 8:  # BBM_ERR_UNSUPPORTED
             return False
-        L.check(rc, h.h, "bbm_dist_bbb_register_x")
+        L.check(rc, h.h, "bbm_dist_bbb_enable_peer")
         return True
 
     def peer_status(self):

@@ -64,7 +64,7 @@ const char* bbm_last_error(bbm_handle_t h);
 /* tuning / diagnostics knobs ("bbb.tile", "bbb.stages", "bbb.waves", "bbb.items_per_sm", "bbb.maxseg",
  * "bbb.l2hint", "bbb.kernel": 0 auto, 1 band-walk, 2 generic; "dist.graph": 1 replays a CUDA graph
  * of the whole NCCL-path multi-GPU step (default 0: measured slower); "dist.peer": 0 disables the
- * fused peer-memory halo push after bbm_dist_bbb_register_x); unknown keys -> BBM_ERR_ARG.       */
+ * fused peer-memory halo push after bbm_dist_bbb_enable_peer); unknown keys -> BBM_ERR_ARG.       */
 int32_t bbm_set_option(bbm_handle_t h, const char* key, int64_t value);
 int32_t bbm_get_option(bbm_handle_t h, const char* key, int64_t* value);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches)         */
@@ -210,14 +210,15 @@ int32_t bbm_dist_bbb_plan_layout(bbm_dist_bbb_plan_t p, bbm_dist_layout* out);
  * d_y_own:      m_own x nrhs (ld = max(1,m_own)).
  * The halo exchange (grouped ncclSend/ncclRecv on the communicator's stream) overlaps the
  * product of the interior block rows; boundary rows follow.  Collective over the ranks.        */
-/* Optional, collective: switch the halo exchange of products on this x_local buffer from NCCL
- * send/recv to a FUSED kernel: CTA 0 of every rank's band-walk kernel stores its boundary x blocks
- * straight into the neighbours' halo regions over NVLink peer memory (CUDA IPC mappings) and raises an
- * epoch flag; CTAs whose steps read a halo column wait for it.  One launch per step, no NCCL kernel.
- * d_x_local must be the base of a bbm_malloc / cudaMalloc allocation; halos must come from the
- * immediate neighbours only (else BBM_ERR_UNSUPPORTED on every rank and the NCCL path stays).
- * Contract: x_local's halo parts belong to the library between calls.                              */
-int32_t bbm_dist_bbb_register_x(bbm_dist_bbb_plan_t p, void* d_x_local, int32_t elem_size);
+/* Optional, collective, once per plan: switch the halo exchange from NCCL send/recv to a FUSED
+ * kernel.  Every rank gets a small device block (epoch flags + double-buffered halo buffers) that is
+ * mapped into both neighbours (CUDA IPC over NVLink).  A pusher CTA of every rank's band-walk kernel
+ * stores the rank's boundary x blocks straight into the neighbours' halo buffers and raises an epoch
+ * flag; CTAs whose steps read a halo block column wait for it and take that x block from the buffer.
+ * One launch per rank per step, no NCCL kernel, no host synchronisation.  Halos must come from the
+ * immediate neighbours only, else BBM_ERR_UNSUPPORTED on every rank and the NCCL path stays in use.
+ * On this path the halo parts of x_local are neither read nor written; nrhs must be 1.            */
+int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t p, int32_t elem_size);
 /* active: fused path in use; timed_out: a peer wait expired in some call (results invalid).  Synchronises. */
 int32_t bbm_dist_bbb_peer_status(bbm_dist_bbb_plan_t p, int32_t* active, int32_t* timed_out);
 

@@ -44,7 +44,7 @@ def main():
             o, c0 = lay["own_offset"], lay["col_offset"]
             dx = h.empty(max(1, lay["n_local"]), np.float64)
             dy = h.empty(max(1, lay["m_own"]), np.float64)
-            fused = A.register_x(dx) if use_peer else False
+            fused = A.enable_peer() if use_peer else False
             if use_peer and want_fused is True and not fused and world <= 4:
                 failures.append((ci, "fused path expected but registration declined"))
             y0 = rng.standard_normal(sum(rows))
