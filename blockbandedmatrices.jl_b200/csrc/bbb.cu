@@ -411,7 +411,10 @@ void walk_stage_bytes(int tile, int w, i64 P, int* dbytes, int* xbytes) {
 // 20-30%, a partial last wave cannot saturate HBM).  A tile t covers in-block rows [t*T, (t+1)*T);
 // only block rows with r[K] > t*T take part, in maximal runs; every run gets a share of the slots
 // proportional to its weight and is cut into that many segments of equal weight.
-int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, Partition* out) {
+// lead_steps > 0 (fused multi-GPU path): the items that start at block row 0 first wait for the left
+// neighbour's halo push (a few microseconds of NVLink latency and fences); they get that many steps less
+// work so that they still finish with the rest of the wave.
+int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, int lead_steps, Partition* out) {
     bbm_handle_t h = d->h;
     const i64 Nr = d->Nr;
     const i64 ovh = 16;  // per-step cost that does not shrink with the tile's height
@@ -419,7 +422,10 @@ int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, P
     std::vector<Run> runs;
     const i64 ntiles = (d->maxr + tile - 1) / tile;
     double total = 0;
-    auto weight = [&](i64 K, i64 k0) { return (double)(std::min<i64>(tile, d->r[K] - k0) + ovh); };
+    auto weight = [&](i64 K, i64 k0) {
+        const double wgt = (double)(std::min<i64>(tile, d->r[K] - k0) + ovh);
+        return K == 0 ? wgt * (1 + lead_steps) : wgt;
+    };
     for (i64 t = 0; t < ntiles; ++t) {
         const i64 k0 = t * tile;
         i64 K = 0;
@@ -603,11 +609,12 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         const i64 waves = std::max<i64>(1, bbm_opt(h, "bbb.waves", 1));
         // the fused multi-GPU path adds one pusher CTA: leave it a slot of the wave
         const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves) - (h->peer ? 1 : 0);
-        auto key = std::make_pair(tile, target_items * 1024 + maxseg_cap);
+        const int lead_steps = (h->peer && h->peer->has_halo[0]) ? (int)std::max<i64>(0, bbm_opt(h, "dist.lead_steps", 7)) : 0;
+        auto key = std::make_pair(tile * 64 + lead_steps, target_items * 1024 + maxseg_cap);
         auto it = d->parts.find(key);
         if (it == d->parts.end()) {
             Partition part;
-            int32_t rc = build_partition(d, tile, target_items, maxseg_cap, &part);
+            int32_t rc = build_partition(d, tile, target_items, maxseg_cap, lead_steps, &part);
             if (rc != BBM_OK) return rc;
             it = d->parts.emplace(key, part).first;
         }
