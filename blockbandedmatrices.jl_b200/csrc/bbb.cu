@@ -55,6 +55,10 @@ struct bbm_bbb_desc {
     i64* dR = nullptr;
     i64* dC = nullptr;
     std::map<std::pair<int, int>, Partition> parts;  // (tile, target items) -> partition
+    // block-row chunks of the pipelined host-vector product (sub-view descriptors, built on first use)
+    struct HostChunk { i64 Ka, Kb, Jl, Jh; bbm_bbb_desc_t sub; };
+    std::vector<HostChunk> chunks;
+    std::vector<cudaEvent_t> chunk_ev;
 };
 
 namespace {
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         if (tid == 0 && pe.epoch >= 2) {
 #pragma unroll
             for (int sd = 0; sd < 2; ++sd)
-                if (pe.dst[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, &pe.local->err);
+                if (pe.dst[sd] && pe.ack_wait[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, &pe.local->err);
         }
         __syncthreads();
 #pragma unroll
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             // a halo nobody reads (no work item touches it) is acknowledged at once
 #pragma unroll
             for (int sd = 0; sd < 2; ++sd)
-                if (pe.has_halo[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
+                if (pe.ack_send[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
         }
         return;
     }
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         if (tid == 0) {
 #pragma unroll
             for (int sd = 0; sd < 2; ++sd) {
-                if (!used[sd] || !pe.has_halo[sd]) continue;
+                if (!used[sd] || !pe.ack_send[sd]) continue;
                 __threadfence();
                 const unsigned c = atomicAdd(&pe.local->count[sd], 1u);
                 if (c + 1 == (unsigned)pe.consumers[sd]) {
@@ -674,6 +678,69 @@ int32_t bbb_mul_host_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_
     if (rc != BBM_OK) return rc;
     T* dX = static_cast<T*>(h->ws_x);
     T* dY = static_cast<T*>(h->ws_y);
+
+    // Large single-vector products are PCIe-bound (x up, y down): pipeline them over block-row chunks on
+    // three streams -- upload the x columns chunk i needs, multiply chunk i (a sub-view: block rows
+    // [Ka,Kb) are banded-block-banded with shifted bandwidths over a column range of the same storage,
+    // src/BandedBlockBandedMatrix.jl:416-420,450-456), download y of chunk i -- so that the two copy
+    // directions and the kernel overlap and the call costs about max(H2D, D2H) instead of their sum.
+    const i64 nchunk_opt = bbm_opt(h, "bbb.host_chunks", 16);
+    const bool pipelined = nrhs == 1 && nchunk_opt > 1 && d->P > 0 && d->Nr >= 2 * nchunk_opt &&
+                           (size_t)(d->m + d->n) * sizeof(T) >= (size_t)(8u << 20);
+    if (pipelined) {
+        if (d->chunks.empty()) {
+            const int nch = (int)std::min<i64>(nchunk_opt, 32);
+            std::vector<i64> kb(nch + 1);
+            if (bbm_bbb_partition_rows(d->Nr, d->r.data(), nch, kb.data()) != BBM_OK) return bbm_fail(h, BBM_ERR_ARG, "bad block sizes");
+            for (int i = 0; i < nch; ++i) {
+                if (kb[i + 1] <= kb[i]) continue;
+                bbm_bbb_desc::HostChunk ch{kb[i], kb[i + 1], 0, 0, nullptr};
+                ch.Jl = std::min<i64>(std::max<i64>(ch.Ka - d->l, 0), d->Nc);
+                ch.Jh = std::min<i64>(std::max<i64>(ch.Kb - 1 + d->u + 1, ch.Jl), d->Nc);
+                const i64 sft = ch.Ka - ch.Jl;
+                rc = bbm_bbb_desc_create(h, ch.Kb - ch.Ka, ch.Jh - ch.Jl, d->r.data() + ch.Ka, d->c.data() + ch.Jl, d->l - sft,
+                                         d->u + sft, d->lam, d->mu, &ch.sub);
+                if (rc != BBM_OK) return rc;
+                d->chunks.push_back(ch);
+            }
+            d->chunk_ev.resize(2 * d->chunks.size() + 1, nullptr);
+            for (auto& e : d->chunk_ev) BBM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        if (!h->copy_in) {
+            BBM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+            BBM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+        }
+        cudaEvent_t ev0 = d->chunk_ev.back();
+        BBM_CUDA(h, cudaEventRecord(ev0, h->stream));            // earlier work on the handle's stream
+        BBM_CUDA(h, cudaStreamWaitEvent(h->copy_in, ev0, 0));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->copy_out, ev0, 0));
+        i64 up = 0;  // x columns [0, up) are on the device
+        for (size_t i = 0; i < d->chunks.size(); ++i) {
+            const auto& ch = d->chunks[i];
+            const i64 need = d->C[ch.Jh];
+            if (need > up) {
+                BBM_CUDA(h, cudaMemcpyAsync(dX + up, h_X + up, (size_t)(need - up) * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+                up = need;
+            }
+            const i64 r0 = d->R[ch.Ka], nr = d->R[ch.Kb] - r0;
+            if (beta != T(0) && nr > 0)
+                BBM_CUDA(h, cudaMemcpyAsync(dY + r0, h_Y + r0, (size_t)nr * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+            BBM_CUDA(h, cudaEventRecord(d->chunk_ev[2 * i], h->copy_in));
+            BBM_CUDA(h, cudaStreamWaitEvent(h->stream, d->chunk_ev[2 * i], 0));
+            const i64 c0 = d->C[ch.Jl];
+            rc = bbb_mul_impl<T>(h, ch.sub, alpha, d_data + d->P * c0, dX + c0, n1, 1, beta, dY + r0, m1);
+            if (rc != BBM_OK) return rc;
+            BBM_CUDA(h, cudaEventRecord(d->chunk_ev[2 * i + 1], h->stream));
+            BBM_CUDA(h, cudaStreamWaitEvent(h->copy_out, d->chunk_ev[2 * i + 1], 0));
+            if (nr > 0)
+                BBM_CUDA(h, cudaMemcpyAsync(h_Y + r0, dY + r0, (size_t)nr * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
+        }
+        BBM_CUDA(h, cudaStreamSynchronize(h->copy_out));
+        BBM_CUDA(h, cudaStreamSynchronize(h->copy_in));
+        BBM_CUDA(h, cudaStreamSynchronize(h->stream));
+        return BBM_OK;
+    }
+
     if (d->n > 0)
         BBM_CUDA(h, cudaMemcpy2DAsync(dX, n1 * sizeof(T), h_X, ldx * sizeof(T), d->n * sizeof(T), nrhs, cudaMemcpyHostToDevice, h->stream));
     if (beta != T(0))
@@ -739,6 +806,10 @@ int32_t bbm_bbb_desc_destroy(bbm_bbb_desc_t d) {
     if (bbm_valid(d->h)) cudaSetDevice(d->h->device);
     for (auto& kv : d->parts)
         if (kv.second.d_items) cudaFree(kv.second.d_items);
+    for (auto& ch : d->chunks)
+        if (ch.sub) bbm_bbb_desc_destroy(ch.sub);
+    for (auto& e : d->chunk_ev)
+        if (e) cudaEventDestroy(e);
     if (d->dR) cudaFree(d->dR);
     if (d->dC) cudaFree(d->dC);
     d->magic = 0;

@@ -40,6 +40,12 @@ struct BbmPeerParams {
     long long halo_col0[2] = {0, 0};              // first local column each halo buffer stands for
     int own_J0 = 0, own_J1 = 0;                   // local block-column range this rank owns
     int has_halo[2] = {0, 0};                     // a neighbour fills my left / right halo
+    // Acknowledgements are only needed across ONE-SIDED neighbour pairs.  Where halos flow both ways, the
+    // neighbour's kernel e cannot start before its kernel e-1 completed, which needed my push of epoch e-1,
+    // whose kernel started after my kernel e-2 completed -- so the parity buffer epoch e overwrites was last
+    // read by a finished kernel, without any explicit signal (and without remote stores in the kernel tail).
+    int ack_wait[2] = {0, 0};                     // I push to that side but receive nothing from it
+    int ack_send[2] = {0, 0};                     // I receive from that side but push nothing to it
     int consumers[2] = {0, 0};                    // CTAs reading each halo (filled by the launcher)
 };
 
@@ -57,6 +63,7 @@ struct bbm_context {
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
     // low-priority side stream (L2 prefetch ahead of the triangular solve's sequential chain)
     const BbmPeerParams* peer = nullptr;  // non-null only inside a fused multi-GPU product call
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // pipelined host-vector product
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_ev[2] = {nullptr, nullptr};
 };

@@ -4,7 +4,7 @@
 #include "bbm_internal.h"
 
 static const char* const kOptionKeys[] = {
-    "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves",
+    "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves", "bbb.host_chunks",
     "sky.kernel", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "dist.graph", "dist.peer", "dist.lead_steps", nullptr};
 
 extern "C" {
@@ -50,6 +50,8 @@ int32_t bbm_destroy(bbm_handle_t h) {
     cudaSetDevice(h->device);
     if (h->ws_x) cudaFree(h->ws_x);
     if (h->ws_y) cudaFree(h->ws_y);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
     for (int i = 0; i < 2; ++i) if (h->side_ev[i]) cudaEventDestroy(h->side_ev[i]);
     h->magic = 0;

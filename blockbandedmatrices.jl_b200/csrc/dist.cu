@@ -592,6 +592,10 @@ int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t pl, int32_t elem_size) {
         if (e != cudaSuccess) { cudaGetLastError(); cudaFree(d_all); return bbm_fail(h, BBM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); }
         tpl.remote[sd] = static_cast<BbmPeerSig*>(pl->ipc_sig[sd]);
     }
+    for (int sd = 0; sd < 2; ++sd) {
+        tpl.ack_wait[sd] = tpl.cnt[sd] > 0 && !tpl.has_halo[sd];
+        tpl.ack_send[sd] = tpl.has_halo[sd] && tpl.cnt[sd] == 0;
+    }
     tpl.local = pl->sig;
     pl->peer_tpl = tpl;
     pl->reg_elem = elem_size;
