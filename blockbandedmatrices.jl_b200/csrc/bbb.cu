@@ -613,7 +613,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         const i64 waves = std::max<i64>(1, bbm_opt(h, "bbb.waves", 1));
         // the fused multi-GPU path adds one pusher CTA: leave it a slot of the wave
         const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves) - (h->peer ? 1 : 0);
-        const int lead_steps = (h->peer && h->peer->has_halo[0]) ? (int)std::max<i64>(0, bbm_opt(h, "dist.lead_steps", 7)) : 0;
+        const int lead_steps = (h->peer && h->peer->has_halo[0]) ? (int)std::max<i64>(0, bbm_opt(h, "dist.lead_steps", 0)) : 0;
         auto key = std::make_pair(tile * 64 + lead_steps, target_items * 1024 + maxseg_cap);
         auto it = d->parts.find(key);
         if (it == d->parts.end()) {
@@ -684,7 +684,7 @@ int32_t bbb_mul_host_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_
     // [Ka,Kb) are banded-block-banded with shifted bandwidths over a column range of the same storage,
     // src/BandedBlockBandedMatrix.jl:416-420,450-456), download y of chunk i -- so that the two copy
     // directions and the kernel overlap and the call costs about max(H2D, D2H) instead of their sum.
-    const i64 nchunk_opt = bbm_opt(h, "bbb.host_chunks", 16);
+    const i64 nchunk_opt = bbm_opt(h, "bbb.host_chunks", 8);
     const bool pipelined = nrhs == 1 && nchunk_opt > 1 && d->P > 0 && d->Nr >= 2 * nchunk_opt &&
                            (size_t)(d->m + d->n) * sizeof(T) >= (size_t)(8u << 20);
     if (pipelined) {

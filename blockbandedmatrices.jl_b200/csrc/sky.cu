@@ -341,13 +341,18 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_ker
     for (int c = 0; c < total; ++c) {
         cp_async_wait<kMmStages - 2>();
         __syncthreads();
-        if (issued < total) load_chunk(issued % kMmStages);
-        cp_async_commit();
-        ++issued;
         const double* as = As + (size_t)(c % kMmStages) * kMmBK * LDA;
         const double* bs = Bs + (size_t)(c % kMmStages) * BN * LDB;
 #pragma unroll
         for (int k4 = 0; k4 < kMmBK; k4 += 4) {
+            // the next chunk's cp.async issue (address arithmetic, ~100 instructions) is staggered: the
+            // first half of the warps issues after the 1st k-step, the second half mid-chunk, so that on
+            // every scheduler one warp keeps the DMMA pipe fed while the other issues loads
+            if ((k4 == 4 && warp < NT / 64) || (k4 == 4 * (kMmBK / 8) + 4 && warp >= NT / 64)) {
+                if (issued < total) load_chunk(issued % kMmStages);
+                cp_async_commit();
+                ++issued;
+            }
             double af[MF], bf[NF];
 #pragma unroll
             for (int i = 0; i < MF; ++i) af[i] = as[(k4 + ac) * LDA + wm0 + i * 8 + ar];
