@@ -61,6 +61,8 @@ struct bbm_context {
     // workspace for the *_host_* calls (device copies of X and Y)
     void* ws_x = nullptr; size_t ws_x_bytes = 0;
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
+    void* ws_z = nullptr; size_t ws_z_bytes = 0;   // triangular solve: inverses of the diagonal blocks
+    void* ws_w = nullptr; size_t ws_w_bytes = 0;   // triangular solve: level temporaries
     // low-priority side stream (L2 prefetch ahead of the triangular solve's sequential chain)
     const BbmPeerParams* peer = nullptr;  // non-null only inside a fused multi-GPU product call
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // pipelined host-vector product

@@ -50,6 +50,8 @@ int32_t bbm_destroy(bbm_handle_t h) {
     cudaSetDevice(h->device);
     if (h->ws_x) cudaFree(h->ws_x);
     if (h->ws_y) cudaFree(h->ws_y);
+    if (h->ws_z) cudaFree(h->ws_z);
+    if (h->ws_w) cudaFree(h->ws_w);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }

@@ -58,7 +58,17 @@ struct bbm_sky_desc {
         std::vector<int> item_ptr;     // Nr+1
         std::vector<i64> sub_ptr;      // prefix of 32-row sub-blocks per diagonal block
         i64* d_sub = nullptr;          // per sub-block: (data offset of its top-left, ld, size)
+        i64* d_place = nullptr;        // per sub-block: (offset in the dense inverse block storage, ld, size)
         i64 nsub = 0;
+        // GEMM-based solve (Float64, many right-hand sides): explicit inverses of the diagonal blocks
+        struct Batch { void* cblks = nullptr; void* segs = nullptr; void* tiles = nullptr; int ntiles = 0; bool aligned = false; };
+        bool inv_built = false;
+        std::vector<i64> woff, wld;    // inverse of diagonal block K: W + woff[K], leading dimension wld[K]
+        i64 wtotal = 0;
+        std::vector<Batch> inv_levels; // two batches per level (T = off-diagonal * X22, X12 = -X11 * T)
+        i64 step_ldb = -1, step_nrhs = -1, step_ldx = -1;
+        Batch stepA, stepB;            // all block steps; tiles of step K are [ptr[K], ptr[K+1])
+        std::vector<int> ptrA, ptrB;
     } tri[2];
     // product plans keyed by the serials of (A, B), owned by the C descriptor
     struct MmPlan;
@@ -262,7 +272,7 @@ constexpr size_t mm_smem_bytes() {
     return (size_t)kMmStages * ((size_t)kMmBK * (BM + 4) + (size_t)BN * (kMmBK + 4)) * sizeof(double);
 }
 
-template <int BM, int BN, int WM, int WN, int kMmBK, bool ALIGNED>
+template <int BM, int BN, int WM, int WN, int kMmBK, bool ALIGNED, bool ATOMIC = false>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_kernel(const MmParams<double> p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int LDA = BM + 4;     // As[k][m]: 4 k-rows of a fragment land in distinct bank groups
@@ -380,8 +390,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_ker
                 if (col < cb.cJ) {
                     double* cp = p.C + cb.cstart + row + (i64)col * cb.ldc;
                     double v = alpha * acc[i][j][t];
-                    if (beta != 0.0) v = fma(beta, *cp, v);
-                    *cp = v;
+                    if (ATOMIC) {
+                        atomicAdd(cp, v);  // split-k partial product (beta == 1 by construction)
+                    } else {
+                        if (beta != 0.0) v = fma(beta, *cp, v);
+                        *cp = v;
+                    }
                 }
             }
         }
@@ -848,6 +862,227 @@ int32_t build_tri(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
     return BBM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// GEMM-based block triangular solve (Float64, >= 16 right-hand sides).
+// The blocked substitution above is bound by its dependency chain (16 sub-steps per 512-row block, each a
+// latency-exposed shared-memory product).  Here every diagonal block is inverted explicitly up front --
+// 32x32 sub-blocks by substitution, then doubling: for T = [T11 T12; 0 T22], inv(T)12 = -inv(T11) T12 inv(T22),
+// two batched DMMA products per level over ALL diagonal blocks at once -- and each block step becomes two
+// tensor-core products with split-k (atomic) accumulation:
+//     X_K  = inv(T_KK) * B_K                 (only the non-zero triangle of the inverse is multiplied)
+//     B_KR = B_KR - A[KR,K] * X_K            (the off-diagonal panel of src/linalg.jl:93-115)
+// Rounding differs from substitution by O(cond(T_KK) eps); the tolerance tests run on the reference's
+// well-conditioned inputs.  "trsm.kernel" = 2 keeps the substitution path.
+// ------------------------------------------------------------------------------------------------
+struct MmBatchHost {
+    std::vector<MmCBlk> cblks;
+    std::vector<MmSeg> segs;
+    std::vector<MmTile> tiles;
+    bool aligned = true;
+    // one C block of rows x cols at (cstart, ldc) with a single product segment, cut into 64x64 tiles
+    void add(i64 cstart, i64 ldc, i64 rows, i64 cols, const MmSeg& sg) {
+        if (rows <= 0 || cols <= 0 || sg.kc <= 0) return;
+        MmCBlk cb{cstart, ldc, (int32_t)rows, (int32_t)cols, (int32_t)segs.size(), (int32_t)segs.size() + 1};
+        aligned = aligned && !(sg.astart & 1) && !(sg.lda & 1) && !(sg.bstart & 1) && !(sg.ldb & 1);
+        segs.push_back(sg);
+        const int32_t ci = (int32_t)cblks.size();
+        cblks.push_back(cb);
+        for (int tj = 0; tj * 64 < cols; ++tj)
+            for (int ti = 0; ti * 64 < rows; ++ti) tiles.push_back(MmTile{ci, ti, tj, 0});
+    }
+};
+
+void free_batch(bbm_sky_desc::Tri::Batch& b) {
+    if (b.cblks) cudaFree(b.cblks);
+    if (b.segs) cudaFree(b.segs);
+    if (b.tiles) cudaFree(b.tiles);
+    b = bbm_sky_desc::Tri::Batch();
+}
+
+int32_t upload_batch(bbm_handle_t h, const MmBatchHost& hb, bbm_sky_desc::Tri::Batch* out) {
+    free_batch(*out);
+    MmCBlk* c = nullptr; MmSeg* sgs = nullptr; MmTile* t = nullptr;
+    int32_t rc = upload(h, hb.cblks, &c);
+    if (rc == BBM_OK) rc = upload(h, hb.segs, &sgs);
+    if (rc == BBM_OK) rc = upload(h, hb.tiles, &t);
+    out->cblks = c; out->segs = sgs; out->tiles = t;
+    out->ntiles = (int)hb.tiles.size();
+    out->aligned = hb.aligned;
+    return rc;
+}
+
+// C (+)= alpha * A * B over the tiles [t0, t0+nt) of a batch; 64x64 DMMA tiles, 4 warps
+int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, int nt, const double* A, const double* Bm,
+                    double* Cm, double alpha, double beta, bool atomic) {
+    if (nt <= 0) return BBM_OK;
+    MmParams<double> p{A, Bm, Cm, (const MmCBlk*)b.cblks, (const MmSeg*)b.segs, (const MmTile*)b.tiles + t0, alpha, beta};
+    const bool al = b.aligned && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(Bm) % 16 == 0);
+    constexpr size_t smem = mm_smem_bytes<64, 64, 16>();
+    cudaError_t e = cudaSuccess;
+    auto go = [&](auto kern) {
+        static bool attr_done = false;  // per instantiation
+        if (!attr_done) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = (e == cudaSuccess); }
+        if (e == cudaSuccess) { kern<<<nt, 128, smem, h->stream>>>(p); e = cudaGetLastError(); }
+    };
+    if (al && atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, true>);
+    else if (al) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, false>);
+    else if (atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, true>);
+    else go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, false>);
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "triangular-solve product launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return BBM_OK;
+}
+
+int32_t build_tri_inverse_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    if (t.inv_built) return BBM_OK;
+    const i64 N = d->Nr;
+    t.woff.assign(N + 1, 0); t.wld.assign(N, 2);
+    i64 maxr = 0;
+    for (i64 K = 0; K < N; ++K) {
+        t.wld[K] = std::max<i64>(2, (d->r[K] + 1) & ~i64(1));
+        t.woff[K + 1] = t.woff[K] + t.wld[K] * ((d->r[K] + 1) & ~i64(1));
+        maxr = std::max(maxr, d->r[K]);
+    }
+    t.wtotal = t.woff[N];
+    {
+        std::vector<i64> place;
+        for (i64 K = 0; K < N; ++K)
+            for (i64 i0 = 0; i0 < d->r[K]; i0 += 32) {
+                place.push_back(t.woff[K] + i0 + i0 * t.wld[K]);
+                place.push_back(t.wld[K]);
+                place.push_back(std::min<i64>(32, d->r[K] - i0));
+            }
+        if (t.d_place) { cudaFree(t.d_place); t.d_place = nullptr; }
+        int32_t rcp = upload(h, place, &t.d_place);
+        if (rcp != BBM_OK) return rcp;
+    }
+    for (auto& b : t.inv_levels) free_batch(b);
+    t.inv_levels.clear();
+    for (i64 sz = 32; sz < maxr; sz *= 2) {
+        MmBatchHost g1, g2;  // g1: T = offdiag * X22 (upper) / offdiag * X11 (lower);  g2: X12 = -X11 * T / X21 = -X22 * T
+        for (i64 K = 0; K < N; ++K) {
+            const i64 rK = d->r[K];
+            if (rK <= sz) continue;
+            const i64 ds = sky_start(d, K, K), ld = d->S[K], wo = t.woff[K], wl = t.wld[K];
+            for (i64 base = 0; base + sz < rK; base += 2 * sz) {
+                const i64 s1 = sz, s2 = std::min<i64>(sz, rK - base - sz), mid = base + s1;
+                if (upper) {
+                    // T12 (s1 x s2) = U12 * X22 ;  X12 = -X11 * T12
+                    g1.add(wo + base + mid * wl, wl, s1, s2, MmSeg{ds + base + mid * ld, ld, wo + mid + mid * wl, wl, s2});
+                    g2.add(wo + base + mid * wl, wl, s1, s2, MmSeg{wo + base + base * wl, wl, wo + base + mid * wl, wl, s1});
+                } else {
+                    // T21 (s2 x s1) = L21 * X11 ;  X21 = -X22 * T21
+                    g1.add(wo + mid + base * wl, wl, s2, s1, MmSeg{ds + mid + base * ld, ld, wo + base + base * wl, wl, s1});
+                    g2.add(wo + mid + base * wl, wl, s2, s1, MmSeg{wo + mid + mid * wl, wl, wo + mid + base * wl, wl, s2});
+                }
+            }
+        }
+        t.inv_levels.emplace_back(); t.inv_levels.emplace_back();
+        int32_t rc = upload_batch(h, g1, &t.inv_levels[t.inv_levels.size() - 2]);
+        if (rc == BBM_OK) rc = upload_batch(h, g2, &t.inv_levels[t.inv_levels.size() - 1]);
+        if (rc != BBM_OK) return rc;
+    }
+    t.inv_built = true;
+    return BBM_OK;
+}
+
+// scatter the inverted 32x32 diagonal sub-blocks (1024 entries each) into the dense inverse blocks
+__global__ void __launch_bounds__(256) sky_tri_scatter_kernel(const double* __restrict__ W32, const i64* __restrict__ place, i64 nsub,
+                                                              double* __restrict__ W) {
+    const i64 sb = blockIdx.x;
+    if (sb >= nsub) return;
+    const i64 dst = place[3 * sb], ld = place[3 * sb + 1];
+    const int nb = (int)place[3 * sb + 2];
+    for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+        const int i = idx & 31, j = idx >> 5;
+        if (i < nb && j < nb) W[dst + i + (i64)j * ld] = W32[sb * 1024 + idx];
+    }
+}
+
+int32_t build_tri_step_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb, i64 ldx, i64 nrhs) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    if (t.step_ldb == ldb && t.step_nrhs == nrhs && t.step_ldx == ldx && t.stepA.tiles) return BBM_OK;
+    const i64 N = d->Nr;
+    MmBatchHost a, b;
+    t.ptrA.assign(N + 1, 0); t.ptrB.assign(N + 1, 0);
+    const i64 ksplit = 128;
+    for (i64 K = 0; K < N; ++K) {
+        t.ptrA[K] = (int)a.tiles.size();
+        t.ptrB[K] = (int)b.tiles.size();
+        const i64 rK = d->r[K];
+        if (rK == 0) continue;
+        const i64 wo = t.woff[K], wl = t.wld[K];
+        // X[R_K + rows of tile ti] += inv(T)[rows, k-part] * B[R_K + k-part]   (skip the zero triangle)
+        for (i64 i0 = 0; i0 < rK; i0 += 64) {
+            const i64 nr = std::min<i64>(64, rK - i0);
+            const i64 klo = upper ? i0 : 0, khi = upper ? rK : std::min<i64>(rK, i0 + 64);
+            for (i64 k0 = klo; k0 < khi; k0 += ksplit) {
+                const i64 kc = std::min<i64>(ksplit, khi - k0);
+                a.add(d->R[K] + i0, ldx, nr, nrhs, MmSeg{wo + i0 + k0 * wl, wl, d->R[K] + k0, ldb, kc});
+            }
+        }
+        // B[panel rows] -= A[panel, K] * X[R_K ...]
+        i64 prow0, prows, yrow0;
+        if (upper) { prow0 = 0; prows = d->R[K] - d->R[d->klo[K]]; yrow0 = d->R[d->klo[K]]; }
+        else { prow0 = d->R[K + 1] - d->R[d->klo[K]]; prows = d->R[d->khi[K] + 1] - d->R[K + 1]; yrow0 = d->R[K + 1]; }
+        for (i64 k0 = 0; k0 < rK && prows > 0; k0 += ksplit) {
+            const i64 kc = std::min<i64>(ksplit, rK - k0);
+            b.add(yrow0, ldb, prows, nrhs, MmSeg{d->off[K] + prow0 + k0 * d->S[K], d->S[K], d->R[K] + k0, ldx, kc});
+        }
+    }
+    t.ptrA[N] = (int)a.tiles.size();
+    t.ptrB[N] = (int)b.tiles.size();
+    int32_t rc = upload_batch(h, a, &t.stepA);
+    if (rc == BBM_OK) rc = upload_batch(h, b, &t.stepB);
+    if (rc != BBM_OK) return rc;
+    t.step_ldb = ldb; t.step_nrhs = nrhs; t.step_ldx = ldx;
+    return BBM_OK;
+}
+
+int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, const double* d_data, double* d_B, i64 ldb, i64 nrhs) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    int32_t rc = build_tri_inverse_plan(h, d, upper);
+    if (rc != BBM_OK) return rc;
+    const i64 ldx = std::max<i64>(2, (d->m + 1) & ~i64(1));
+    rc = build_tri_step_plan(h, d, upper, ldb, ldx, nrhs);
+    if (rc != BBM_OK) return rc;
+    // workspaces: W (inverses), Tw (level temporaries, same layout), X (solutions), W32 (32x32 inverses)
+    rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, (size_t)t.nsub * 1024 * sizeof(double));
+    if (rc == BBM_OK) rc = bbm_ws_reserve(h, &h->ws_y, &h->ws_y_bytes, (size_t)ldx * nrhs * sizeof(double));
+    if (rc == BBM_OK) rc = bbm_ws_reserve(h, &h->ws_z, &h->ws_z_bytes, (size_t)t.wtotal * sizeof(double));
+    if (rc == BBM_OK) rc = bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, (size_t)t.wtotal * sizeof(double));
+    if (rc != BBM_OK) return rc;
+    double* W32 = static_cast<double*>(h->ws_x);
+    double* X = static_cast<double*>(h->ws_y);
+    double* W = static_cast<double*>(h->ws_z);
+    double* Tw = static_cast<double*>(h->ws_w);
+    BBM_CUDA(h, cudaMemsetAsync(W, 0, (size_t)t.wtotal * sizeof(double), h->stream));
+    BBM_CUDA(h, cudaMemsetAsync(X, 0, (size_t)ldx * nrhs * sizeof(double), h->stream));
+    // level 0: 32x32 inverses by substitution, scattered onto the diagonals of the dense inverse blocks
+    sky_tri_invdiag_kernel<double><<<(unsigned)((t.nsub + 3) / 4), 128, 0, h->stream>>>(d_data, t.d_sub, t.nsub, upper, unit ? 1 : 0, W32);
+    sky_tri_scatter_kernel<<<(unsigned)t.nsub, 256, 0, h->stream>>>(W32, t.d_place, t.nsub, W);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_tri_invdiag launch: %s", cudaGetErrorString(e));
+    h->launches += 2;
+    // doubling levels, all diagonal blocks at once
+    for (size_t lv = 0; lv + 1 < t.inv_levels.size(); lv += 2) {
+        rc = launch_mm64(h, t.inv_levels[lv], 0, t.inv_levels[lv].ntiles, d_data, W, Tw, 1.0, 0.0, false);
+        if (rc == BBM_OK) rc = launch_mm64(h, t.inv_levels[lv + 1], 0, t.inv_levels[lv + 1].ntiles, W, Tw, W, -1.0, 0.0, false);
+        if (rc != BBM_OK) return rc;
+    }
+    // the sequential chain: two split-k tensor-core products per block
+    for (i64 s = 0; s < d->Nr; ++s) {
+        const i64 K = upper ? d->Nr - 1 - s : s;
+        rc = launch_mm64(h, t.stepA, t.ptrA[K], t.ptrA[K + 1] - t.ptrA[K], W, d_B, X, 1.0, 1.0, true);
+        if (rc == BBM_OK) rc = launch_mm64(h, t.stepB, t.ptrB[K], t.ptrB[K + 1] - t.ptrB[K], d_data, X, d_B, -1.0, 1.0, true);
+        if (rc != BBM_OK) return rc;
+    }
+    BBM_CUDA(h, cudaMemcpy2DAsync(d_B, (size_t)ldb * sizeof(double), X, (size_t)ldx * sizeof(double), (size_t)d->m * sizeof(double),
+                                  (size_t)nrhs, cudaMemcpyDeviceToDevice, h->stream));
+    return BBM_OK;
+}
+
 template <typename T>
 int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs) {
     BBM_REQUIRE_HANDLE(h);
@@ -868,6 +1103,8 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     int32_t rc = build_tri(h, d, upper);
     if (rc != BBM_OK) return rc;
     bbm_sky_desc::Tri& t = d->tri[upper];
+    if (sizeof(T) == 8 && nrhs >= 16 && bbm_opt(h, "trsm.kernel", 0) == 0)
+        return sky_trsm_gemm(h, d, upper, unit ? 1 : 0, reinterpret_cast<const double*>(d_data), reinterpret_cast<double*>(d_B), ldb, nrhs);
     // pass 0: inverses of the 32x32 diagonal sub-blocks (workspace: 1024 entries per sub-block)
     rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, (size_t)t.nsub * 1024 * sizeof(T));
     if (rc != BBM_OK) return rc;
@@ -1046,6 +1283,10 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         if (d->tri[t].d_ents) cudaFree(d->tri[t].d_ents);
         if (d->tri[t].d_items) cudaFree(d->tri[t].d_items);
         if (d->tri[t].d_sub) cudaFree(d->tri[t].d_sub);
+        if (d->tri[t].d_place) cudaFree(d->tri[t].d_place);
+        for (auto& b : d->tri[t].inv_levels) free_batch(b);
+        free_batch(d->tri[t].stepA);
+        free_batch(d->tri[t].stepB);
     }
     for (auto& kv : d->plans) free_plan(kv.second);
     d->magic = 0;
