@@ -43,6 +43,16 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json; null if there is none for this kernel)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(P, n, m, itemsize=8, nrhs=1):
     return itemsize * (P * n + n * nrhs + m * nrhs)
 
@@ -61,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -308,7 +318,8 @@ def bench_single(args, torch, B, h, stream, nb, n, rank):
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n, "call": "bbm_bbb_mul_host_f64"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "bbb_walk_kernel<double,3,3>", "achieved": nbytes / (kernel_ms * 1e-3) / 1e9,
-                     "peak": None, "unit": UNIT, "frac": None, "traffic": None,
+                     "peak": None, "unit": UNIT, "frac": None,
+                     "traffic": ncu_traffic("bbb_walk_kernel<double,3,3>") if nb == BLOCK else None,
                      "kernel_ms_avg": kernel_ms, "kernel_ms_min": float(min(per)), "algorithmic_bytes_per_launch": nbytes},
         "cpu_baseline": cpu,
     }
@@ -451,8 +462,8 @@ def bench_distributed(args, torch, dist, B, h, stream, nb, block, rank, world, l
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=BLOCK, help="number of blocks (default 4096 = cfg2; smaller only for debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")

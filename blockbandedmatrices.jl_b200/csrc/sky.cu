@@ -913,22 +913,27 @@ int32_t upload_batch(bbm_handle_t h, const MmBatchHost& hb, bbm_sky_desc::Tri::B
 
 // C (+)= alpha * A * B over the tiles [t0, t0+nt) of a batch; 64x64 DMMA tiles, 4 warps
 int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, int nt, const double* A, const double* Bm,
-                    double* Cm, double alpha, double beta, bool atomic) {
+                    double* Cm, double alpha, double beta, bool atomic, bool set_attr = true) {
     if (nt <= 0) return BBM_OK;
     MmParams<double> p{A, Bm, Cm, (const MmCBlk*)b.cblks, (const MmSeg*)b.segs, (const MmTile*)b.tiles + t0, alpha, beta};
     const bool al = b.aligned && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(Bm) % 16 == 0);
     constexpr size_t smem = mm_smem_bytes<64, 64, 16>();
     cudaError_t e = cudaSuccess;
+    const char* where = "";
     auto go = [&](auto kern) {
-        static bool attr_done = false;  // per instantiation
-        if (!attr_done) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = (e == cudaSuccess); }
-        if (e == cudaSuccess) { kern<<<nt, 128, smem, h->stream>>>(p); e = cudaGetLastError(); }
+        if (set_attr) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            where = "cudaFuncSetAttribute";
+        }
+        if (e == cudaSuccess) { kern<<<nt, 128, smem, h->stream>>>(p); e = cudaGetLastError(); where = "launch"; }
     };
     if (al && atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, true>);
     else if (al) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, false>);
     else if (atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, true>);
     else go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, false>);
-    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "triangular-solve product launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess)
+        return bbm_fail(h, BBM_ERR_CUDA, "triangular-solve product %s (tiles %d..+%d of %d, aligned %d, atomic %d): %s", where, t0, nt,
+                        b.ntiles, (int)al, (int)atomic, cudaGetErrorString(e));
     h->launches += 1;
     return BBM_OK;
 }
@@ -1074,8 +1079,9 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
     // the sequential chain: two split-k tensor-core products per block
     for (i64 s = 0; s < d->Nr; ++s) {
         const i64 K = upper ? d->Nr - 1 - s : s;
-        rc = launch_mm64(h, t.stepA, t.ptrA[K], t.ptrA[K + 1] - t.ptrA[K], W, d_B, X, 1.0, 1.0, true);
-        if (rc == BBM_OK) rc = launch_mm64(h, t.stepB, t.ptrB[K], t.ptrB[K + 1] - t.ptrB[K], d_data, X, d_B, -1.0, 1.0, true);
+        // (the opt-in shared-memory size of the kernel variant only has to be set once per call)
+        rc = launch_mm64(h, t.stepA, t.ptrA[K], t.ptrA[K + 1] - t.ptrA[K], W, d_B, X, 1.0, 1.0, true, s < 2);
+        if (rc == BBM_OK) rc = launch_mm64(h, t.stepB, t.ptrB[K], t.ptrB[K + 1] - t.ptrB[K], d_data, X, d_B, -1.0, 1.0, true, s < 2);
         if (rc != BBM_OK) return rc;
     }
     BBM_CUDA(h, cudaMemcpy2DAsync(d_B, (size_t)ldb * sizeof(double), X, (size_t)ldx * sizeof(double), (size_t)d->m * sizeof(double),

@@ -332,3 +332,59 @@ class DistBlockBandedProduct:
     def mul_(self, alpha=1.0, beta=0.0):
         from .linalg import mul_
         return mul_(self.C, self.A, self.B, alpha, beta)
+
+
+class DistBlockBandedMatvec:
+    """y[K0:K1) <- alpha*A[K0:K1,:]*x + beta*y[K0:K1) for a row-block-partitioned BlockBandedMatrix.
+
+    A_loc holds the rank's own block rows (a ragged BlockSkylineMatrix, see sky_rowrange_structure);
+    x_local = [halo | owned | halo] covers the block columns A_loc touches, the halo parts are refreshed
+    by `exchange()` (torch.distributed isend/irecv -- NCCL between GPUs) with the same send/recv lists as
+    the banded-block-banded plan (they depend on the block structure and (l,u) only)."""
+
+    def __init__(self, handle, dist, torch, rows, cols, l, u, Kbounds, rank, dtype=np.float64):
+        from .matrices import BlockSkylineMatrix
+        self.h, self.dist, self.torch, self.rank = handle, dist, torch, rank
+        self.rows, self.cols = _sizes(rows), _sizes(cols)
+        world = len(Kbounds) - 1
+        self.layout, self.sends, self.recvs = layout(self.rows, self.cols, l, u, world, rank, Kbounds)
+        lay = self.layout
+        K0, K1 = lay["K0"], lay["K1"]
+        Jlo, Jhi, ll, uu = sky_rowrange_structure(self.rows, self.cols, l, u, K0, K1)
+        # the skyline sub-structure only spans the touched columns; x_local spans the layout's hull
+        self.Jlo, self.Jhi = Jlo, Jhi
+        C = _cum(self.cols)
+        self.x_off = int(C[Jlo] - lay["col_offset"]) if Jhi > Jlo else 0   # where A_loc's columns start in x_local
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.dev = torch.device("cuda", handle.device) if handle is not None else torch.device("cpu")
+        n = BlockSkylineMatrix.numentries(self.rows[K0:K1], self.cols[Jlo:Jhi], ll, uu)
+        self.tA = torch.zeros(max(n, 1), dtype=tdt, device=self.dev)
+        self.x_local = torch.zeros(max(lay["n_local"], 1), dtype=tdt, device=self.dev)
+        self.y_own = torch.zeros(max(lay["m_own"], 1), dtype=tdt, device=self.dev)
+        if handle is not None:
+            from .device import DeviceArray
+            data = DeviceArray(handle, (n,), np.dtype(dtype), ptr=self.tA.data_ptr())
+        else:
+            data = self.tA.numpy()[:n]
+        self.A = BlockSkylineMatrix(data, self.rows[K0:K1], self.cols[Jlo:Jhi], ll, uu)
+
+    def exchange(self):
+        dist, ops = self.dist, []
+        for peer, off, cnt in self.recvs:
+            ops.append(dist.P2POp(dist.irecv, self.x_local[off:off + cnt], peer))
+        for peer, off, cnt in self.sends:
+            ops.append(dist.P2POp(dist.isend, self.x_local[off:off + cnt], peer))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def mul_(self, alpha=1.0, beta=0.0):
+        """Device path: y_own <- alpha*A_loc*x_local[cols of A_loc] + beta*y_own (after exchange())."""
+        from .device import DeviceArray
+        from .linalg import mul_
+        n_loc, m = self.A.shape[1], self.A.shape[0]
+        es = self.tA.element_size()
+        dx = DeviceArray(self.h, (n_loc,), self.A.dtype, ptr=self.x_local.data_ptr() + self.x_off * es)
+        dy = DeviceArray(self.h, (m,), self.A.dtype, ptr=self.y_own.data_ptr())
+        mul_(dy, self.A, dx, alpha, beta)
+        return self.y_own

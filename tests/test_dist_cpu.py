@@ -246,3 +246,65 @@ def test_partitioned_block_banded_product_gloo(world):
         p.join(timeout=60)
     for rank, failures in results:
         assert not failures, f"rank {rank}: {failures}"
+
+
+def _mv_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bbm_b200 as B
+        from bbm_b200 import distributed as D
+        from oracle import cpu as O
+        from tests.helpers import random_sky, relerr, tol
+        failures = []
+        for ci, (rows, cols, l, u) in enumerate([([4] * 10, [4] * 10, 2, 2), ([3, 5, 2, 4, 6, 1, 3, 4], [3, 5, 2, 4, 6, 1, 3, 4], 1, 2),
+                                                 ([5, 3, 7, 2, 6], [4, 6, 2, 5, 3, 7], 1, 2), ([4] * 9, [4] * 9, 0, 3)]):
+            rng = np.random.default_rng(700 + ci)
+            adata = random_sky(rng, rows, cols, l, u)
+            x = rng.standard_normal(sum(cols))
+            A = B.BlockSkylineMatrix(adata, rows, cols, l, u)
+            kb = D.partition_rows(rows, world)
+            mv = D.DistBlockBandedMatvec(None, dist, torch, rows, cols, l, u, kb, rank)
+            lay = mv.layout
+            loc, _, _ = D.sky_cut_rows(A, lay["K0"], lay["K1"])
+            mv.A.data[:] = loc.data
+            xl = mv.x_local.numpy()
+            xl[:] = np.nan
+            o, c0 = lay["own_offset"], lay["col_offset"]
+            xl[o:o + lay["n_own"]] = x[c0 + o:c0 + o + lay["n_own"]]
+            mv.exchange()
+            n_loc = mv.A.shape[1]
+            xs = np.ascontiguousarray(xl[mv.x_off:mv.x_off + n_loc])
+            if np.isnan(xs).any():
+                failures.append((ci, "x halo not filled"))
+                continue
+            y = np.zeros(mv.A.shape[0])
+            O.sky_mul(mv.A.rows, mv.A.cols, mv.A.l, mv.A.u, 1.0, mv.A.data, xs, 0.0, y)
+            ref = np.zeros(sum(rows))
+            O.sky_mul(rows, cols, l, u, 1.0, adata, x, 0.0, ref)
+            want = ref[lay["row_offset"]:lay["row_offset"] + lay["m_own"]]
+            if relerr(y, want) > tol(np.float64, 64):
+                failures.append((ci, f"mismatch {relerr(y, want)}"))
+        q.put((rank, failures))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, [("exception", traceback.format_exc() + repr(e))]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_block_banded_matvec_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mv_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, failures in results:
+        assert not failures, f"rank {rank}: {failures}"
