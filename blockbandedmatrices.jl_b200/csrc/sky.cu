@@ -265,14 +265,12 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int kMmStages = 3;
-
-template <int BM, int BN, int kMmBK>
+template <int BM, int BN, int kMmBK, int kMmStages = 3>
 constexpr size_t mm_smem_bytes() {
     return (size_t)kMmStages * ((size_t)kMmBK * (BM + 4) + (size_t)BN * (kMmBK + 4)) * sizeof(double);
 }
 
-template <int BM, int BN, int WM, int WN, int kMmBK, bool ALIGNED, bool ATOMIC = false>
+template <int BM, int BN, int WM, int WN, int kMmBK, bool ALIGNED, bool ATOMIC = false, int kMmStages = 3>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_kernel(const MmParams<double> p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int LDA = BM + 4;     // As[k][m]: 4 k-rows of a fragment land in distinct bank groups
@@ -917,7 +915,7 @@ int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, i
     if (nt <= 0) return BBM_OK;
     MmParams<double> p{A, Bm, Cm, (const MmCBlk*)b.cblks, (const MmSeg*)b.segs, (const MmTile*)b.tiles + t0, alpha, beta};
     const bool al = b.aligned && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(Bm) % 16 == 0);
-    constexpr size_t smem = mm_smem_bytes<64, 64, 16>();
+    constexpr size_t smem = mm_smem_bytes<64, 64, 16, 4>();  // 4 stages: a 64-deep k-slice is requested at once
     cudaError_t e = cudaSuccess;
     const char* where = "";
     auto go = [&](auto kern) {
@@ -927,10 +925,10 @@ int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, i
         }
         if (e == cudaSuccess) { kern<<<nt, 128, smem, h->stream>>>(p); e = cudaGetLastError(); where = "launch"; }
     };
-    if (al && atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, true>);
-    else if (al) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, false>);
-    else if (atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, true>);
-    else go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, false>);
+    if (al && atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, true, 4>);
+    else if (al) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, false, 4>);
+    else if (atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, true, 4>);
+    else go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, false, false, 4>);
     if (e != cudaSuccess)
         return bbm_fail(h, BBM_ERR_CUDA, "triangular-solve product %s (tiles %d..+%d of %d, aligned %d, atomic %d): %s", where, t0, nt,
                         b.ntiles, (int)al, (int)atomic, cudaGetErrorString(e));
@@ -1011,7 +1009,7 @@ int32_t build_tri_step_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
     const i64 N = d->Nr;
     MmBatchHost a, b;
     t.ptrA.assign(N + 1, 0); t.ptrB.assign(N + 1, 0);
-    const i64 ksplit = 128;
+    const i64 ksplit = 64;  // k-slice per CTA: latency-bound products, so many short CTAs beat few long ones
     for (i64 K = 0; K < N; ++K) {
         t.ptrA[K] = (int)a.tiles.size();
         t.ptrB[K] = (int)b.tiles.size();
@@ -1076,13 +1074,48 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
         if (rc == BBM_OK) rc = launch_mm64(h, t.inv_levels[lv + 1], 0, t.inv_levels[lv + 1].ntiles, W, Tw, W, -1.0, 0.0, false);
         if (rc != BBM_OK) return rc;
     }
-    // the sequential chain: two split-k tensor-core products per block
+    // the sequential chain: two split-k tensor-core products per block; the next block column's panel and
+    // inverse are pulled into L2 on a low-priority side stream one step ahead
+    const bool prefetch = bbm_opt(h, "trsm.prefetch", 1) != 0 && d->Nr > 2;
+    if (prefetch && !h->side_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        BBM_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 2; ++i) BBM_CUDA(h, cudaEventCreateWithFlags(&h->side_ev[i], cudaEventDisableTiming));
+    }
+    if (prefetch) {
+        BBM_CUDA(h, cudaEventRecord(h->side_ev[0], h->stream));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->side_ev[0], 0));
+    }
     for (i64 s = 0; s < d->Nr; ++s) {
         const i64 K = upper ? d->Nr - 1 - s : s;
+        if (prefetch && s + 1 < d->Nr) {
+            const i64 Kn = upper ? K - 1 : K + 1;
+            const size_t pb = (size_t)(d->off[Kn + 1] - d->off[Kn]) * sizeof(double);
+            const size_t wb = (size_t)(t.woff[Kn + 1] - t.woff[Kn]) * sizeof(double);
+            if (pb > 0) {
+                sky_l2_prefetch_kernel<<<(unsigned)std::min<size_t>(592, (pb / 32 + 255) / 256 + 1), 256, 0, h->side_stream>>>(
+                    reinterpret_cast<const char*>(d_data + d->off[Kn]), pb, nullptr);
+                h->launches += 1;
+            }
+            if (wb > 0) {
+                sky_l2_prefetch_kernel<<<(unsigned)std::min<size_t>(592, (wb / 32 + 255) / 256 + 1), 256, 0, h->side_stream>>>(
+                    reinterpret_cast<const char*>(W + t.woff[Kn]), wb, nullptr);
+                h->launches += 1;
+            }
+        }
         // (the opt-in shared-memory size of the kernel variant only has to be set once per call)
         rc = launch_mm64(h, t.stepA, t.ptrA[K], t.ptrA[K + 1] - t.ptrA[K], W, d_B, X, 1.0, 1.0, true, s < 2);
         if (rc == BBM_OK) rc = launch_mm64(h, t.stepB, t.ptrB[K], t.ptrB[K + 1] - t.ptrB[K], d_data, X, d_B, -1.0, 1.0, true, s < 2);
         if (rc != BBM_OK) return rc;
+        if (prefetch) {
+            BBM_CUDA(h, cudaEventRecord(h->side_ev[s & 1], h->stream));
+            BBM_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->side_ev[s & 1], 0));
+        }
+    }
+    if (prefetch) {
+        BBM_CUDA(h, cudaEventRecord(h->side_ev[0], h->side_stream));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->side_ev[0], 0));
     }
     BBM_CUDA(h, cudaMemcpy2DAsync(d_B, (size_t)ldb * sizeof(double), X, (size_t)ldx * sizeof(double), (size_t)d->m * sizeof(double),
                                   (size_t)nrhs, cudaMemcpyDeviceToDevice, h->stream));
