@@ -1076,7 +1076,8 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
     }
     // the sequential chain: two split-k tensor-core products per block; the next block column's panel and
     // inverse are pulled into L2 on a low-priority side stream one step ahead
-    const bool prefetch = bbm_opt(h, "trsm.prefetch", 1) != 0 && d->Nr > 2;
+    // (measured on cfg5: 27.1 us per block step without, 27.8 us with the prefetch -- off by default here)
+    const bool prefetch = bbm_opt(h, "trsm.prefetch", 0) != 0 && d->Nr > 2;
     if (prefetch && !h->side_stream) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
