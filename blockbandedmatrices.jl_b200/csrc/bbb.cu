@@ -82,6 +82,7 @@ struct BbbParams {
     int stage_data_bytes;  // per-stage bytes reserved for the matrix chunk
     int stage_x_bytes;     // per-stage bytes reserved for the x chunk
     int l2hint;
+    int tri, unit;         // 0: whole matrix; 1 / 2: Upper- / LowerTriangular(A) (unit: ones on the diagonal)
     BbmPeerParams peer;    // fused halo push over NVLink peer memory (enabled == 0: plain kernel)
 };
 
@@ -300,9 +301,17 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
                     const int o = off[ii] >= 0 ? off[ii] : 0;   // any in-chunk address; its value is discarded
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        const T dv = Ds[o + s * WW];
+                        T dv = Ds[o + s * WW];
+                        bool keep = act[s] && off[ii] >= 0;
+                        if (p.tri) {
+                            // slab s is block (J+s-u, J): above the diagonal iff s < u; inside the diagonal block
+                            // entry (k,j) has j - k = mu - ii
+                            const bool up = p.tri == 1;
+                            keep = keep && (s == p.u ? (up ? ii <= p.mu : ii >= p.mu) : (up ? s < p.u : s > p.u));
+                            if (p.unit && s == p.u && ii == p.mu) dv = T(1);
+                        }
                         const T r = fma(dv, xr[ii], acc[s]);
-                        acc[s] = (act[s] && off[ii] >= 0) ? r : acc[s];   // never lets an unused slot (NaN) in
+                        acc[s] = keep ? r : acc[s];   // never lets an unused slot (NaN) in
                     }
                 }
             } else {
@@ -314,7 +323,14 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
                         if (k < rK) {
                             for (int ii = w - 1; ii >= 0; --ii) {
                                 const int j = k + p.mu - ii;
-                                if (j >= 0 && j < cJ) acc[s] = fma(Ds[(j - jlo) * P + s * w + ii], Xs[j - jlo], acc[s]);
+                                if (j < 0 || j >= cJ) continue;
+                                T dv = Ds[(j - jlo) * P + s * w + ii];
+                                if (p.tri) {
+                                    const bool up = p.tri == 1;
+                                    if (!(s == p.u ? (up ? ii <= p.mu : ii >= p.mu) : (up ? s < p.u : s > p.u))) continue;
+                                    if (p.unit && s == p.u && ii == p.mu) dv = T(1);
+                                }
+                                acc[s] = fma(dv, Xs[j - jlo], acc[s]);
                             }
                         }
                     }
@@ -384,7 +400,14 @@ __global__ void __launch_bounds__(256) bbb_generic_kernel(const BbbParams<T> p) 
                 const T* slab = p.data + (i64)(p.u + K - J) * p.w;
                 for (int ii = p.w - 1; ii >= 0; --ii) {
                     const i64 j = k + p.mu - ii;
-                    if (j >= 0 && j < cJ) acc = fma(slab[ii + (i64)p.P * (cbeg + j)], Xq[cbeg + j], acc);
+                    if (j < 0 || j >= cJ) continue;
+                    if (p.tri) {
+                        const bool up = p.tri == 1;
+                        if (!(J == K ? (up ? ii <= p.mu : ii >= p.mu) : (up ? J > K : J < K))) continue;
+                    }
+                    T dv = slab[ii + (i64)p.P * (cbeg + j)];
+                    if (p.tri && p.unit && J == K && ii == p.mu) dv = T(1);
+                    acc = fma(dv, Xq[cbeg + j], acc);
                 }
             }
         }
@@ -421,7 +444,10 @@ void walk_stage_bytes(int tile, int w, i64 P, int* dbytes, int* xbytes) {
 int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, int lead_steps, Partition* out) {
     bbm_handle_t h = d->h;
     const i64 Nr = d->Nr;
-    const i64 ovh = 16;  // per-step cost that does not shrink with the tile's height
+    // per-step cost that does not shrink with the tile's height.  Measured on cfg3 (block sizes 1..4000): a step
+    // costs nearly the same whether its tile is full or almost empty (it is latency-, not byte-bound), so
+    // the items are balanced by step count with the row count as a tie-breaker: 0.61 -> 0.96 of HBM peak (F32)
+    const i64 ovh = std::max<i64>(0, bbm_opt(h, "bbb.ovh", 4096));
     struct Run { int t; i64 Ka, Kb; double wt; int nseg; };
     std::vector<Run> runs;
     const i64 ntiles = (d->maxr + tile - 1) / tile;
@@ -538,7 +564,7 @@ cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, dim3 grid, int til
 
 template <typename T>
 int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs,
-                     T beta, T* d_Y, i64 ldy) {
+                     T beta, T* d_Y, i64 ldy, int tri = 0, int unit = 0) {
     BBM_REQUIRE_HANDLE(h);
     if (!desc_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BandedBlockBandedMatrix descriptor");
     if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
@@ -557,6 +583,9 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     p.l = (int)d->l; p.u = (int)d->u; p.lam = (int)d->lam; p.mu = (int)d->mu;
     p.w = (int)(d->lam + d->mu + 1); p.P = (int)d->P;
     p.l2hint = (int)bbm_opt(h, "bbb.l2hint", 1);
+    p.tri = tri; p.unit = unit;
+    if (tri && (d->Nr != d->Nc || d->r != d->c))  // hasmatchingblocks, src/triblockbanded.jl:12,20
+        return bbm_fail(h, BBM_ERR_UNSUPPORTED, "triangular product needs matching square diagonal blocks");
 
     const i64 NS = d->l + d->u + 1;
     const int w = p.w;
@@ -614,7 +643,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         // the fused multi-GPU path adds one pusher CTA: leave it a slot of the wave
         const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves) - (h->peer ? 1 : 0);
         const int lead_steps = (h->peer && h->peer->has_halo[0]) ? (int)std::max<i64>(0, bbm_opt(h, "dist.lead_steps", 0)) : 0;
-        auto key = std::make_pair(tile * 64 + lead_steps, target_items * 1024 + maxseg_cap);
+        auto key = std::make_pair(tile * 64 + lead_steps + 65536 * (int)bbm_opt(h, "bbb.ovh", 4096), target_items * 1024 + maxseg_cap);
         auto it = d->parts.find(key);
         if (it == d->parts.end()) {
             Partition part;
@@ -836,6 +865,16 @@ int32_t bbm_bbb_mul_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const do
 int32_t bbm_bbb_mul_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data, const float* d_X,
                         int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
     return bbb_mul_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_bbb_trimul_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, double alpha, const double* d_data,
+                           const double* d_X, int64_t ldx, int64_t nrhs, double beta, double* d_Y, int64_t ldy) {
+    if (uplo != 'U' && uplo != 'L' && uplo != 'u' && uplo != 'l') return bbm_valid(h) ? bbm_fail(h, BBM_ERR_ARG, "uplo must be 'U' or 'L'") : BBM_ERR_HANDLE;
+    return bbb_mul_impl<double>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy, (uplo == 'U' || uplo == 'u') ? 1 : 2, unit ? 1 : 0);
+}
+int32_t bbm_bbb_trimul_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, float alpha, const float* d_data,
+                           const float* d_X, int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
+    if (uplo != 'U' && uplo != 'L' && uplo != 'u' && uplo != 'l') return bbm_valid(h) ? bbm_fail(h, BBM_ERR_ARG, "uplo must be 'U' or 'L'") : BBM_ERR_HANDLE;
+    return bbb_mul_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy, (uplo == 'U' || uplo == 'u') ? 1 : 2, unit ? 1 : 0);
 }
 int32_t bbm_bbb_mul_host_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data, const double* h_X,
                              int64_t ldx, int64_t nrhs, double beta, double* h_Y, int64_t ldy) {

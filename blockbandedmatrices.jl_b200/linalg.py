@@ -53,6 +53,8 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
     (host vectors: copied through the C ABI's *_host_* call, synchronous)."""
     if isinstance(A, BlockSkylineMatrix) and isinstance(x, BlockSkylineMatrix):
         return _sky_matmul_(y, A, x, alpha, beta)
+    if isinstance(A, _Triangular):
+        return _bbb_trimul_(y, A, x, alpha, beta)
     if not isinstance(A, (BandedBlockBandedMatrix, BlockSkylineMatrix)):
         raise TypeError(f"unsupported matrix type {type(A).__name__}")
     kind = "bbb" if isinstance(A, BandedBlockBandedMatrix) else "sky"
@@ -87,6 +89,31 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
         fn = getattr(h._lib, f"bbm_bbb_mul_host_{suf}")
         rc = fn(h.h, desc, ct(alpha), C.c_void_p(A.data.ptr), x.ctypes.data_as(C.c_void_p), _ld(x), xc, ct(beta),
                 y.ctypes.data_as(C.c_void_p), _ld(y))
+    L.check(rc, h.h, "mul!")
+    return y
+
+
+def _bbb_trimul_(y, T, x, alpha=1.0, beta=0.0):
+    """``mul!(y, UpperTriangular(A), x, alpha, beta)`` etc. for a device-resident BandedBlockBandedMatrix
+    (the ``U*b`` / ``lmul(U,b)`` of test/test_triblockbanded.jl:17-53)."""
+    A = T.parent
+    if not isinstance(A, BandedBlockBandedMatrix):
+        raise TypeError("triangular products are taken for BandedBlockBandedMatrix parents only")
+    h = _require_device(A)
+    m, n = A.shape
+    xr, xc = _vec_dims(x, "x")
+    yr, yc = _vec_dims(y, "y")
+    if xr != n or yr != m or xc != yc:
+        raise L.DimensionMismatch(f"A is {m}x{n}, x is {x.shape}, y is {y.shape}")
+    if not (isinstance(x, DeviceArray) and isinstance(y, DeviceArray)):
+        raise TypeError("triangular products take device vectors")
+    dt = A.dtype
+    if dt not in _SUF or np.dtype(x.dtype) != dt or np.dtype(y.dtype) != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, ct = _SUF[dt]
+    fn = getattr(h._lib, f"bbm_bbb_trimul_{suf}")
+    rc = fn(h.h, A.descriptor(h), ord(T.uplo), 1 if T.unit else 0, ct(alpha), C.c_void_p(A.data.ptr), C.c_void_p(x.ptr), _ld(x), xc,
+            ct(beta), C.c_void_p(y.ptr), _ld(y))
     L.check(rc, h.h, "mul!")
     return y
 
@@ -165,6 +192,11 @@ def ldiv(T, B):
 def mul(A, x):
     """``A*x``: allocates the result where x lives (``similar`` + ``mul!``).  For two
     BlockSkylineMatrix operands the result structure is ``similar(::MulAdd)`` of src/linalg.jl:32-48."""
+    if isinstance(A, _Triangular):
+        h = _require_device(A.parent)
+        m = A.parent.shape[0]
+        shape = (m,) if len(x.shape) == 1 else (m, x.shape[1])
+        return mul_(h.empty(shape, A.parent.dtype), A, x, 1.0, 0.0)
     h = _require_device(A)
     if isinstance(A, BlockSkylineMatrix) and isinstance(x, BlockSkylineMatrix):
         if len(A.cols) != len(x.rows) or (A.cols != x.rows).any():

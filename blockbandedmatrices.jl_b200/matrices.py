@@ -417,6 +417,10 @@ class _Triangular:
     def __init__(self, parent, uplo: str, unit: bool):
         self.parent, self.uplo, self.unit = parent, uplo, bool(unit)
 
+    def __matmul__(self, x):
+        from .linalg import mul
+        return mul(self, x)
+
     @property
     def blockbandwidths(self):
         """src/triblockbanded.jl:10-25: clip to (min(0,l),u) / (l,min(0,u)) when the blocks match."""

@@ -102,6 +102,18 @@ int32_t bbm_bbb_mul_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const do
 int32_t bbm_bbb_mul_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data,
                         const float* d_X, int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
 
+/* Y <- alpha*T*X + beta*Y with T = UpperTriangular(A) ('U') / LowerTriangular(A) ('L'), unit != 0 for the
+ * Unit variants: the triangular BandedBlockBandedMatrix product of test/test_triblockbanded.jl:17-53
+ * (layout TriangularLayout{UPLO,UNIT,BandedBlockBandedColumnMajor}; block bandwidths clipped as in
+ * src/triblockbanded.jl:10-25).  Same kernels with a triangular mask: the other triangle of `data` is
+ * never read into the arithmetic.  Needs matching square diagonal blocks, else BBM_ERR_UNSUPPORTED.  */
+int32_t bbm_bbb_trimul_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, double alpha,
+                           const double* d_data, const double* d_X, int64_t ldx, int64_t nrhs, double beta,
+                           double* d_Y, int64_t ldy);
+int32_t bbm_bbb_trimul_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, float alpha,
+                           const float* d_data, const float* d_X, int64_t ldx, int64_t nrhs, float beta,
+                           float* d_Y, int64_t ldy);
+
 /* Same product with HOST vectors (the reference-facing call when x, y live in Julia Arrays and
  * the matrix is device-resident): copies X host->device, runs the kernel, copies Y back and
  * synchronises.  h_X / h_Y should be pinned (bbm_host_alloc) for full PCIe speed.             */

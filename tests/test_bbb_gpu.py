@@ -168,3 +168,50 @@ def test_dist_plan_virtual_ranks(handle, world):
             A.close()
             comm.close()
         assert relerr(y, ref) <= tol(np.float64, F.bbb_nnz_per_row_max(l, u, lam, mu) + 1)
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["walk", "generic"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
+def test_bbb_triangular_mul(handle, uplo, unit, dtype, kernel):
+    """test/test_triblockbanded.jl:17-53: U*b == Matrix(U)*b for Upper/UnitUpper/Lower/UnitLower
+    triangular BandedBlockBandedMatrix; the other triangle of `data` is poisoned with NaN."""
+    handle.set_option("bbb.kernel", kernel)
+    try:
+        for rows, lu, lm in [(list(range(1, 11)), (1, 1), (1, 1)), ([40] * 9, (2, 1), (2, 3)), ([300, 17, 64], (1, 1), (1, 1))]:
+            rng = np.random.default_rng(21)
+            data = random_bbb(rng, rows, rows, *lu, *lm, dtype)
+            A = B.BandedBlockBandedMatrix(data, rows, rows, lu, lm)
+            D = A.to_dense().astype(np.float64)
+            Tm = np.triu(D) if uplo == "U" else np.tril(D)
+            if unit:
+                np.fill_diagonal(Tm, 1.0)
+            # poison the triangle that must not be read (and the diagonal for the unit variants)
+            pois = data.copy(order="F")
+            mask_other = (np.tril(np.ones_like(D), -1) if uplo == "U" else np.triu(np.ones_like(D), 1)).astype(bool)
+            if unit:
+                mask_other |= np.eye(D.shape[0], dtype=bool)
+            for rho, gi, gj in A._slot_map():
+                sel = mask_other[gi, gj]
+                pois[rho, gj[sel]] = np.nan
+            Ad = B.BandedBlockBandedMatrix(pois, rows, rows, lu, lm).to_device(handle)
+            T = {"U": (B.UnitUpperTriangular if unit else B.UpperTriangular),
+                 "L": (B.UnitLowerTriangular if unit else B.LowerTriangular)}[uplo](Ad)
+            x = rng.standard_normal(sum(rows)).astype(dtype)
+            y0 = rng.standard_normal(sum(rows)).astype(dtype)
+            got = (T @ handle.to_device(x)).to_host()
+            ref = Tm.astype(np.longdouble) @ x.astype(np.longdouble)
+            assert not np.isnan(got).any()
+            assert relerr(got, ref) <= tol(dtype, F.bbb_nnz_per_row_max(*lu, *lm) + 1)
+            dy = handle.to_device(y0)
+            B.mul_(dy, T, handle.to_device(x), 2.0, -1.0)
+            assert relerr(dy.to_host(), 2.0 * ref - y0.astype(np.longdouble)) <= 2 * tol(dtype, F.bbb_nnz_per_row_max(*lu, *lm) + 1)
+        assert T.blockbandwidths == ((0, lu[1]) if uplo == "U" else (lu[0], 0))   # src/triblockbanded.jl:10-25
+    finally:
+        handle.set_option("bbb.kernel", 0)
+
+
+def test_bbb_triangular_mul_needs_matching_blocks(handle):
+    A = B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4], [4, 3], (1, 1), (1, 1)).to_device(handle)
+    with pytest.raises(B.BBMError):
+        B.mul(B.UpperTriangular(A), handle.empty(7, np.float64))
