@@ -48,6 +48,10 @@ SIGNATURES = {
     "bbm_memcpy_d2h": (i32, [vp, vp, vp, sz]),
     "bbm_memcpy_d2d": (i32, [vp, vp, vp, sz]),
     "bbm_memset": (i32, [vp, vp, i32, sz]),
+    "bbm_axpy_f64": (i32, [vp, i64, f64, vp, vp]),
+    "bbm_axpy_f32": (i32, [vp, i64, f32, vp, vp]),
+    "bbm_scal_f64": (i32, [vp, i64, f64, vp]),
+    "bbm_scal_f32": (i32, [vp, i64, f32, vp]),
     "bbm_bbb_desc_create": (i32, [vp, i64, i64, vp, vp, i64, i64, i64, i64, pp]),
     "bbm_bbb_desc_destroy": (i32, [vp]),
     "bbm_bbb_desc_info": (i32, [vp, pi64, pi64, pi64, pi64]),

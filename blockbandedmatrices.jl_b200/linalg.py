@@ -118,6 +118,51 @@ def _bbb_trimul_(y, T, x, alpha=1.0, beta=0.0):
     return y
 
 
+def _same_structure(A, B):
+    if type(A) is not type(B) or A.shape != B.shape or len(A.rows) != len(B.rows) or len(A.cols) != len(B.cols):
+        return False
+    if (A.rows != B.rows).any() or (A.cols != B.cols).any():
+        return False
+    if isinstance(A, BandedBlockBandedMatrix):
+        return (A.l, A.u, A.lam, A.mu) == (B.l, B.u, B.lam, B.mu)
+    return (A.l == B.l).all() and (A.u == B.u).all()
+
+
+def axpy_(a, X, Y):
+    """``axpy!(a, X, Y)``: Y <- a*X + Y for device vectors or two device matrices of identical structure
+    (src/BandedBlockBandedMatrix.jl:605-606, src/broadcast.jl:307-314); returns Y."""
+    if isinstance(X, DeviceArray) and isinstance(Y, DeviceArray):
+        dx, dy, h = X, Y, X.handle
+        if X.shape != Y.shape:
+            raise L.DimensionMismatch(f"{X.shape} vs {Y.shape}")
+    else:
+        if not _same_structure(X, Y):
+            raise TypeError("device axpy! takes operands of identical structure (others keep the host path)")
+        h = _require_device(X)
+        _require_device(Y)
+        dx, dy = X.data, Y.data
+    dt = np.dtype(dx.dtype)
+    if dt not in _SUF or np.dtype(dy.dtype) != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, ct = _SUF[dt]
+    n = int(np.prod(dx.shape, dtype=np.int64))
+    L.check(getattr(h._lib, f"bbm_axpy_{suf}")(h.h, n, ct(a), C.c_void_p(dx.ptr), C.c_void_p(dy.ptr)), h.h, "axpy!")
+    return Y
+
+
+def lmul_(a, A):
+    """``lmul!(a, A)`` / ``rmul!(A, a)``: scale a device vector or the storage of a device matrix in place."""
+    d = A if isinstance(A, DeviceArray) else A.data
+    h = d.handle
+    dt = np.dtype(d.dtype)
+    if dt not in _SUF:
+        raise TypeError("device path takes Float32/Float64 only")
+    suf, ct = _SUF[dt]
+    n = int(np.prod(d.shape, dtype=np.int64))
+    L.check(getattr(h._lib, f"bbm_scal_{suf}")(h.h, n, ct(a), C.c_void_p(d.ptr)), h.h, "lmul!")
+    return A
+
+
 def muladd_(alpha, A, B, beta, Cdest):
     """``ArrayLayouts.muladd!(alpha, A, B, beta, C)`` = ``materialize!(MulAdd(alpha,A,B,beta,C))``."""
     return mul_(Cdest, A, B, alpha, beta)

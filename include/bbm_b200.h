@@ -80,6 +80,16 @@ int32_t bbm_memcpy_d2h(bbm_handle_t h, void* h_dst, const void* d_src, size_t by
 int32_t bbm_memcpy_d2d(bbm_handle_t h, void* d_dst, const void* d_src, size_t bytes);
 int32_t bbm_memset(bbm_handle_t h, void* d_ptr, int32_t byte_value, size_t bytes);
 
+/* ---- level-1 operations on storage arrays -------------------------------------------------
+ * axpy!(a, A, B) for two matrices of IDENTICAL structure is y <- a*x + y on their `data`
+ * (src/BandedBlockBandedMatrix.jl:605-606, src/broadcast.jl:307-314); lmul!(a, A) / rmul!(A, a) scale
+ * `data` (src/BandedBlockBandedMatrix.jl:609-612).  n = number of stored entries (P*n resp. bb_numentries).
+ * Operands of different bandwidths keep the reference's host path.                               */
+int32_t bbm_axpy_f64(bbm_handle_t h, int64_t n, double alpha, const double* d_x, double* d_y);
+int32_t bbm_axpy_f32(bbm_handle_t h, int64_t n, float alpha, const float* d_x, float* d_y);
+int32_t bbm_scal_f64(bbm_handle_t h, int64_t n, double alpha, double* d_x);
+int32_t bbm_scal_f32(bbm_handle_t h, int64_t n, float alpha, float* d_x);
+
 /* ---- BandedBlockBandedMatrix -------------------------------------------------------------
  * Descriptor = the host-side fields of the reference struct (raxis, column axis, l, u, lam, mu;
  * src/BandedBlockBandedMatrix.jl:25-40) plus cached device index tables and the work

@@ -215,3 +215,28 @@ def test_bbb_triangular_mul_needs_matching_blocks(handle):
     A = B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4], [4, 3], (1, 1), (1, 1)).to_device(handle)
     with pytest.raises(B.BBMError):
         B.mul(B.UpperTriangular(A), handle.empty(7, np.float64))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_axpy_and_scalar_mul_on_storage(handle, dtype):
+    """axpy!(a, A, B) for identical structure and lmul!(a, A) act on `data`
+    (src/BandedBlockBandedMatrix.jl:605-612); checked densely like test/test_broadcasting.jl."""
+    rows, cols, lu, lm = list(range(1, 12)), list(range(1, 12)), (1, 2), (2, 1)
+    rng = np.random.default_rng(31)
+    a_data = random_bbb(rng, rows, cols, *lu, *lm, dtype, poison=False)
+    b_data = random_bbb(rng, rows, cols, *lu, *lm, dtype, poison=False)
+    A = B.BandedBlockBandedMatrix(a_data, rows, cols, lu, lm)
+    Bm = B.BandedBlockBandedMatrix(b_data, rows, cols, lu, lm)
+    Ad, Bd = A.to_device(handle), Bm.to_device(handle)
+    B.axpy_(2.5, Ad, Bd)
+    assert relerr(Bd.to_dense(), 2.5 * A.to_dense().astype(np.float64) + Bm.to_dense()) <= tol(dtype, 2)
+    B.lmul_(-3.0, Ad)
+    assert relerr(Ad.to_dense(), -3.0 * A.to_dense().astype(np.float64)) <= tol(dtype, 1)
+    # odd length / unaligned tail, vectors
+    x = rng.standard_normal(1001).astype(dtype)
+    y = rng.standard_normal(1001).astype(dtype)
+    dx, dy = handle.to_device(x), handle.to_device(y)
+    B.axpy_(0.5, dx, dy)
+    assert relerr(dy.to_host(), 0.5 * x.astype(np.float64) + y) <= tol(dtype, 2)
+    with pytest.raises(TypeError):
+        B.axpy_(1.0, Ad, B.BandedBlockBandedMatrix.zeros(dtype, rows, cols, (1, 1), lm).to_device(handle))
