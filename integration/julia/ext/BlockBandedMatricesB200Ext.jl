@@ -172,6 +172,30 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
                     handle().ptr, descriptor(M.A), descriptor(M.B), descriptor(M.C), M.α, M.A.data.ptr, M.B.data.ptr, M.β, M.C.data.ptr))
         M.C
     end
+    # mul!(y, UpperTriangular(A), x) etc. for a triangular BandedBlockBandedMatrix (test/test_triblockbanded.jl:17-53)
+    @eval function materialize!(M::MulAdd{<:TriangularLayout{UPLO,UNIT,<:BandedBlockBandedColumns},<:Any,<:Any,$T,<:AbstractTriangular{$T,<:B200BBB{$T}},<:B200Array{$T},<:B200Array{$T}}) where {UPLO,UNIT}
+        A, x, y = triangulardata(M.A), M.B, M.C
+        size(A, 2) == size(x, 1) && size(A, 1) == size(y, 1) && size(x, 2) == size(y, 2) ||
+            throw(DimensionMismatch("A has size $(size(A)), x has size $(size(x)), y has size $(size(y))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_trimul_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
+                    handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
+        y
+    end
+    # axpy!(a, X, Y) on identical structures and lmul!(a, A): level-1 kernels on `data`
+    # (src/BandedBlockBandedMatrix.jl:605-612)
+    @eval function LinearAlgebra.axpy!(a::$T, X::B200BBB{$T}, Y::B200BBB{$T})
+        (axes(X) == axes(Y) && blockbandwidths(X) == blockbandwidths(Y) && subblockbandwidths(X) == subblockbandwidths(Y)) ||
+            return invoke(LinearAlgebra.axpy!, Tuple{$T,BandedBlockBandedMatrix{$T},BandedBlockBandedMatrix{$T}}, a, X, Y)
+        check(ccall(($(QuoteNode(Symbol("bbm_axpy_", suf))), libbbm), Int32, (Ptr{Cvoid}, Int64, $T, Ptr{$T}, Ptr{$T}),
+                    handle().ptr, length(parent(X.data)), a, parent(X.data).ptr, parent(Y.data).ptr))
+        Y
+    end
+    @eval function LinearAlgebra.lmul!(a::$T, A::B200BBB{$T})
+        check(ccall(($(QuoteNode(Symbol("bbm_scal_", suf))), libbbm), Int32, (Ptr{Cvoid}, Int64, $T, Ptr{$T}),
+                    handle().ptr, length(parent(A.data)), a, parent(A.data).ptr))
+        A
+    end
     # ldiv!(UpperTriangular(A), B) etc.  ==  materialize!(Ldiv(U, B)); callers: src/blockskylineqr.jl:136-155
     @eval function materialize!(L::Ldiv{<:TriangularLayout{UPLO,UNIT,<:BlockBandedColumns},<:Any,<:AbstractTriangular{$T,<:B200Sky{$T}},<:B200Array{$T}}) where {UPLO,UNIT}
         A, B = triangulardata(L.A), L.B
