@@ -174,6 +174,42 @@ def run_cfg4(torch, B, h, stream, reps, oracle, nblk=2048, bs=256, peak_tf=None)
     return out
 
 
+def run_sky_mv(torch, B, h, stream, reps, oracle, nblk=2048, bs=256, nrhs=1):
+    """Skyline matvec / multi-vector product on cfg4's operand (BlockBandedMatrix fill(256,2048), (2,2))."""
+    rows = [bs] * nblk
+    gen = torch.Generator(device="cuda").manual_seed(1006)
+    nA = B.BlockSkylineMatrix.numentries(rows, rows, 2, 2)
+    m = bs * nblk
+    a_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / 16
+    x_t = torch.randn(nrhs, m, generator=gen, device="cuda", dtype=torch.float64)
+    y_t = torch.full((nrhs, m), float("nan"), device="cuda", dtype=torch.float64)
+    A = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, 2, 2)
+    dx = wrap(B, h, x_t if nrhs > 1 else x_t[0])
+    dy = wrap(B, h, y_t if nrhs > 1 else y_t[0])
+    avg, best = time_gpu(torch, stream, lambda: B.mul_(dy, A, dx), reps)
+    nbytes = 8 * (nA + 2 * m * nrhs)
+    out = {"config": f"skyline matvec: BlockBandedMatrix {nblk} blocks of {bs}, (2,2), Float64, nrhs={nrhs}", "ms_avg": avg, "ms_min": best,
+           "algorithmic_bytes": nbytes, "GBps": nbytes / (avg * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "peak_GBps": peaks(), "frac": nbytes / (avg * 1e-3) / 1e9 / peaks()}, "tolerance": 64 * EPS[8] * 5 * bs}
+    # parity on a sample of block rows against numpy
+    h.synchronize()
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    xh = x_t.cpu().numpy()
+    for _ in range(4):
+        K = int(rng.integers(0, nblk))
+        ref = np.zeros((bs, nrhs))
+        for J in range(max(0, K - 2), min(nblk - 1, K + 2) + 1):
+            s, ld = A.block_start(K, J), int(A.block_strides[J])
+            blk = a_t[s:s + ld * bs].cpu().numpy().reshape((ld, bs), order="F")[:bs]
+            ref += blk @ xh[:, J * bs:(J + 1) * bs].T
+        got = y_t[:, K * bs:(K + 1) * bs].cpu().numpy().T
+        worst = max(worst, relerr(got, ref))
+    out["rel_err_sampled_rows_vs_numpy"] = worst
+    out["parity_ok"] = bool(worst <= out["tolerance"])
+    return out
+
+
 def run_cfg5(torch, B, h, stream, reps, oracle, nblk=1024, bs=512, nrhs=64, peak_tf=None):
     rows = [bs] * nblk
     m = bs * nblk
@@ -261,6 +297,9 @@ def main():
             print(json.dumps(run_bbb(torch, B, h, stream, "cfg3: BBB rows=cols=1:4000, (2,2),(2,2)", r, r, (2, 2), (2, 2), dt, args.reps, oracle)), flush=True)
     if "4" in want:
         print(json.dumps(run_cfg4(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
+    if "4mv" in want:
+        for q in (1, 8):
+            print(json.dumps(run_sky_mv(torch, B, h, stream, args.reps, oracle, nrhs=q)), flush=True)
     if "5" in want:
         print(json.dumps(run_cfg5(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
 
