@@ -82,6 +82,7 @@ struct BbbParams {
     int stage_data_bytes;  // per-stage bytes reserved for the matrix chunk
     int stage_x_bytes;     // per-stage bytes reserved for the x chunk
     int l2hint;
+    int nrhs;
     int tri, unit;         // 0: whole matrix; 1 / 2: Upper- / LowerTriangular(A) (unit: ones on the diagonal)
     BbmPeerParams peer;    // fused halo push over NVLink peer memory (enabled == 0: plain kernel)
 };
@@ -122,7 +123,9 @@ __device__ __forceinline__ StepGeom<T> step_geom(const i64* Ctab, int it, int k0
     return g;
 }
 
-template <typename T, int NS, int W>
+// NR right-hand sides per CTA (1, or 4 for multi-vector products A*X): the matrix chunk of a step is staged
+// once and multiplied with NR x chunks, so A is streamed once per group of NR columns instead of once per column.
+template <typename T, int NS, int W, int NR>
 __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -176,8 +179,11 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     unsigned char* stage0 = smem + tab_bytes;
     const int stage_bytes = p.stage_data_bytes + p.stage_x_bytes;
 
-    const T* __restrict__ Xq = p.X + (i64)blockIdx.y * p.ldx;
-    T* __restrict__ Yq = p.Y + (i64)blockIdx.y * p.ldy;
+    const int q0 = blockIdx.y * NR;
+    const int nq = NR == 1 ? 1 : min(NR, p.nrhs - q0);   // live right-hand sides of this CTA
+    const T* __restrict__ Xq = p.X + (i64)q0 * p.ldx;
+    T* __restrict__ Yq = p.Y + (i64)q0 * p.ldy;
+    const int xone = p.stage_x_bytes / NR;                // bytes reserved per x chunk
 
     for (int i = tid; i <= Kb - Ka; i += tile) Rtab[i] = p.R[Ka + i];
     for (int i = tid; i <= nsteps; i += tile) {
@@ -229,7 +235,17 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         const uintptr_t xg0 = x0 & ~uintptr_t(15), xg1 = (x1 + 15) & ~uintptr_t(15);
         const uint32_t dbytes = static_cast<uint32_t>(dg1 - dg0);
         const uint32_t xbytes = static_cast<uint32_t>(xg1 - xg0);
-        ptx::mbar_arrive_expect_tx(&bars[st], dbytes + xbytes);
+        uint32_t xtotal = xbytes;
+        if (NR > 1) {
+            xtotal = 0;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                if (q >= nq) break;
+                const uintptr_t sh = (uintptr_t)q * (uintptr_t)p.ldx * sizeof(T);
+                xtotal += static_cast<uint32_t>((((x1 + sh) + 15) & ~uintptr_t(15)) - ((x0 + sh) & ~uintptr_t(15)));
+            }
+        }
+        ptx::mbar_arrive_expect_tx(&bars[st], dbytes + xtotal);
         if (p.l2hint) ptx::bulk_g2s_hint(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st], pol_stream);
         else ptx::bulk_g2s(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st]);
         if (halo_side >= 0) {
@@ -238,17 +254,27 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, &p.peer.local->err);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
-        if (p.l2hint) ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
-        else ptx::bulk_g2s(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st]);
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            if (q >= nq) break;
+            // columns of X may start at different 16-byte phases: every column gets its own aligned window
+            const uintptr_t sh = (uintptr_t)q * (uintptr_t)p.ldx * sizeof(T);
+            const uintptr_t g0 = (x0 + sh) & ~uintptr_t(15), g1 = ((x1 + sh) + 15) & ~uintptr_t(15);
+            const uint32_t nb = static_cast<uint32_t>(g1 - g0);
+            if (p.l2hint) ptx::bulk_g2s_hint(sx + q * xone, reinterpret_cast<const void*>(g0), nb, &bars[st], pol_keep);
+            else ptx::bulk_g2s(sx + q * xone, reinterpret_cast<const void*>(g0), nb, &bars[st]);
+        }
     };
 
     if (tid == 0) {
         for (int it = 0; it < S - 1 && it < nsteps; ++it) issue(it);
     }
 
-    T acc[NS];
+    T acc[NS][NR];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc[s] = T(0);
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[s][q] = T(0);
 
     const int k = k0 + tid;
     const T alpha = p.alpha, beta = p.beta;
@@ -271,19 +297,22 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             const uintptr_t x0 = reinterpret_cast<uintptr_t>(xsource(it, &side_unused) + g.cbeg + g.jlo);
             // Ds[(j-jlo)*P + row] = data[row, cbeg+j];  Xs[j-jlo] = x[cbeg+j]
             const T* Ds = reinterpret_cast<const T*>(sd + (d0 & 15));
-            const T* Xs = reinterpret_cast<const T*>(sx + (x0 & 15));
+            const T* Xs[NR];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) Xs[q] = reinterpret_cast<const T*>(sx + q * xone + ((x0 + (uintptr_t)q * (uintptr_t)p.ldx * sizeof(T)) & 15));
             const int cJ = g.cJ, jlo = g.jlo;
             if (W > 0) {
                 // the w x-values of this row are shared by all NS slabs: fetch them once
                 constexpr int WW = W > 0 ? W : 1;
-                T xr[WW];
+                T xr[WW][NR];
                 int off[WW];
 #pragma unroll
                 for (int ii = 0; ii < WW; ++ii) {
                     const int j = k + p.mu - ii;
                     const bool ok = j >= 0 && j < cJ;
                     off[ii] = ok ? (j - jlo) * P + ii : -1;
-                    xr[ii] = ok ? Xs[j - jlo] : T(0);
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) xr[ii][q] = (ok && q < nq) ? Xs[q][j - jlo] : T(0);
                 }
                 // which of the NS block rows this step feeds are live for this thread
                 bool act[NS];
@@ -310,8 +339,11 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
                             keep = keep && (s == p.u ? (up ? ii <= p.mu : ii >= p.mu) : (up ? s < p.u : s > p.u));
                             if (p.unit && s == p.u && ii == p.mu) dv = T(1);
                         }
-                        const T r = fma(dv, xr[ii], acc[s]);
-                        acc[s] = keep ? r : acc[s];   // never lets an unused slot (NaN) in
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) {
+                            const T r = fma(dv, xr[ii][q], acc[s][q]);
+                            acc[s][q] = keep ? r : acc[s][q];   // never lets an unused slot (NaN) in
+                        }
                     }
                 }
             } else {
@@ -330,7 +362,9 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
                                     if (!(s == p.u ? (up ? ii <= p.mu : ii >= p.mu) : (up ? s < p.u : s > p.u))) continue;
                                     if (p.unit && s == p.u && ii == p.mu) dv = T(1);
                                 }
-                                acc[s] = fma(dv, Xs[j - jlo], acc[s]);
+#pragma unroll
+                                for (int q = 0; q < NR; ++q)
+                                    if (q < nq) acc[s][q] = fma(dv, Xs[q][j - jlo], acc[s][q]);
                             }
                         }
                     }
@@ -344,14 +378,22 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             const i64 r0 = Rtab[Kdone - Ka];
             const int rK = static_cast<int>(Rtab[Kdone - Ka + 1] - r0);
             if (k < rK) {
-                T y = alpha * acc[0];
-                if (beta != T(0)) y = fma(beta, Yq[r0 + k], y);
-                Yq[r0 + k] = y;
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    if (q >= nq) break;
+                    T* yp = Yq + (i64)q * p.ldy + r0 + k;
+                    T y = alpha * acc[0][q];
+                    if (beta != T(0)) y = fma(beta, *yp, y);
+                    *yp = y;
+                }
             }
         }
 #pragma unroll
-        for (int s = 0; s + 1 < NS; ++s) acc[s] = acc[s + 1];
-        acc[NS - 1] = T(0);
+        for (int s = 0; s + 1 < NS; ++s)
+#pragma unroll
+            for (int q = 0; q < NR; ++q) acc[s][q] = acc[s + 1][q];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[NS - 1][q] = T(0);
     }
 
     if (p.peer.enabled && blockIdx.y == 0) {
@@ -534,7 +576,7 @@ int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, i
 
 // grid.x == 0: do not launch, report the resident CTAs per SM for (tile, smem) in *occ instead
 template <typename T, int NS>
-cudaError_t launch_walk_w(const BbbParams<T>& p, int w, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ) {
+cudaError_t launch_walk_w(const BbbParams<T>& p, int w, int nr, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ) {
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -542,22 +584,27 @@ cudaError_t launch_walk_w(const BbbParams<T>& p, int w, dim3 grid, int tile, siz
         kern<<<grid, tile, smem, st>>>(p);
         return cudaGetLastError();
     };
-    if (w == 3) return go(bbb_walk_kernel<T, NS, 3>);
-    if (w == 5) return go(bbb_walk_kernel<T, NS, 5>);
-    return go(bbb_walk_kernel<T, NS, 0>);
+    if (nr == 4) {
+        if (w == 3) return go(bbb_walk_kernel<T, NS, 3, 4>);
+        if (w == 5) return go(bbb_walk_kernel<T, NS, 5, 4>);
+        return go(bbb_walk_kernel<T, NS, 0, 4>);
+    }
+    if (w == 3) return go(bbb_walk_kernel<T, NS, 3, 1>);
+    if (w == 5) return go(bbb_walk_kernel<T, NS, 5, 1>);
+    return go(bbb_walk_kernel<T, NS, 0, 1>);
 }
 
 template <typename T>
-cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ = nullptr) {
+cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, int nr, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ = nullptr) {
     switch (NS) {
-        case 1: return launch_walk_w<T, 1>(p, w, grid, tile, smem, st, occ);
-        case 2: return launch_walk_w<T, 2>(p, w, grid, tile, smem, st, occ);
-        case 3: return launch_walk_w<T, 3>(p, w, grid, tile, smem, st, occ);
-        case 4: return launch_walk_w<T, 4>(p, w, grid, tile, smem, st, occ);
-        case 5: return launch_walk_w<T, 5>(p, w, grid, tile, smem, st, occ);
-        case 6: return launch_walk_w<T, 6>(p, w, grid, tile, smem, st, occ);
-        case 7: return launch_walk_w<T, 7>(p, w, grid, tile, smem, st, occ);
-        case 8: return launch_walk_w<T, 8>(p, w, grid, tile, smem, st, occ);
+        case 1: return launch_walk_w<T, 1>(p, w, nr, grid, tile, smem, st, occ);
+        case 2: return launch_walk_w<T, 2>(p, w, nr, grid, tile, smem, st, occ);
+        case 3: return launch_walk_w<T, 3>(p, w, nr, grid, tile, smem, st, occ);
+        case 4: return launch_walk_w<T, 4>(p, w, nr, grid, tile, smem, st, occ);
+        case 5: return launch_walk_w<T, 5>(p, w, nr, grid, tile, smem, st, occ);
+        case 6: return launch_walk_w<T, 6>(p, w, nr, grid, tile, smem, st, occ);
+        case 7: return launch_walk_w<T, 7>(p, w, nr, grid, tile, smem, st, occ);
+        case 8: return launch_walk_w<T, 8>(p, w, nr, grid, tile, smem, st, occ);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -583,7 +630,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     p.l = (int)d->l; p.u = (int)d->u; p.lam = (int)d->lam; p.mu = (int)d->mu;
     p.w = (int)(d->lam + d->mu + 1); p.P = (int)d->P;
     p.l2hint = (int)bbm_opt(h, "bbb.l2hint", 1);
-    p.tri = tri; p.unit = unit;
+    p.tri = tri; p.unit = unit; p.nrhs = (int)nrhs;
     if (tri && (d->Nr != d->Nc || d->r != d->c))  // hasmatchingblocks, src/triblockbanded.jl:12,20
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "triangular product needs matching square diagonal blocks");
 
@@ -598,6 +645,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     if (!aligned) return bbm_fail(h, BBM_ERR_ARG, "device pointers must be aligned to the element size");
 
     int tile = 0, stages = 0, dbytes = 0, xbytes = 0;
+    const int nr = (nrhs >= 2 && !h->peer) ? 4 : 1;  // right-hand sides per CTA of the band-walk kernel
     if (walk) {
         // measured on B200: 4 stages saturate HBM; 5-6 stages (more smem, same occupancy) are 5% slower on cfg2
         const int want_stages = (int)std::min<i64>(8, std::max<i64>(2, bbm_opt(h, "bbb.stages", 4)));
@@ -617,7 +665,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
                 const int t = cands[ci];
                 if (!forced_tile && t > 32 && t / 2 >= d->maxr) continue;  // tile twice the largest block: mostly idle
                 walk_stage_bytes<T>(t, w, d->P, &dbytes, &xbytes);
-                const size_t per = (size_t)dbytes + xbytes;
+                const size_t per = (size_t)dbytes + (size_t)nr * xbytes;
                 if (limit <= tabs) continue;
                 const int s = (int)std::min<size_t>(want_stages, (limit - tabs) / per);
                 if (s >= min_stages) { tile = t; stages = s; }
@@ -633,8 +681,8 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         // slots = whole waves of resident CTAs (table size taken at its cap: a few KB either way)
         int occ = 1;
         {
-            const size_t smem_cap = walk_tab_bytes(maxseg_cap, (int)NS) + (size_t)stages * ((size_t)dbytes + xbytes);
-            cudaError_t e = launch_walk<T>(p, (int)NS, w, dim3(0, 1, 1), tile, smem_cap, h->stream, &occ);
+            const size_t smem_cap = walk_tab_bytes(maxseg_cap, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
+            cudaError_t e = launch_walk<T>(p, (int)NS, w, nr, dim3(0, 1, 1), tile, smem_cap, h->stream, &occ);
             if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
             occ = std::max(1, occ);
         }
@@ -667,10 +715,10 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
             p.stages = stages;
             p.maxseg = part.maxseg;
             p.stage_data_bytes = dbytes;
-            p.stage_x_bytes = xbytes;
-            const size_t smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + xbytes);
-            dim3 grid((unsigned)part.nitems + (h->peer ? 1u : 0u), (unsigned)nrhs, 1);
-            cudaError_t e = launch_walk<T>(p, (int)NS, w, grid, tile, smem, h->stream);
+            p.stage_x_bytes = nr * xbytes;
+            const size_t smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
+            dim3 grid((unsigned)part.nitems + (h->peer ? 1u : 0u), (unsigned)((nrhs + nr - 1) / nr), 1);
+            cudaError_t e = launch_walk<T>(p, (int)NS, w, nr, grid, tile, smem, h->stream);
             if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_walk_kernel launch: %s", cudaGetErrorString(e));
             h->launches += 1;
             return BBM_OK;
