@@ -123,10 +123,264 @@ __device__ __forceinline__ StepGeom<T> step_geom(const i64* Ctab, int it, int k0
     return g;
 }
 
-// NR right-hand sides per CTA (1, or 4 for multi-vector products A*X): the matrix chunk of a step is staged
-// once and multiplied with NR x chunks, so A is streamed once per group of NR columns instead of once per column.
-template <typename T, int NS, int W, int NR>
+template <typename T, int NS, int W>
 __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int tile = blockDim.x;
+    const int w = (W > 0) ? W : p.w;
+    const int P = p.P;
+    const int S = p.stages;
+
+    if (p.peer.enabled && blockIdx.x == 0) {
+        // dedicated pusher CTA (always in the first wave): store my boundary x blocks into the neighbours'
+        // halo buffers of this epoch's parity and publish the epoch.  The buffer was last read two epochs ago.
+        const BbmPeerParams& pe = p.peer;
+        if (blockIdx.y != 0) return;
+        if (tid == 0 && pe.epoch >= 2) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                if (pe.dst[sd] && pe.ack_wait[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, &pe.local->err);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!pe.dst[sd]) continue;
+            T* dst = static_cast<T*>(pe.dst[sd]);
+            const T* src = p.X + pe.src_off[sd];
+            for (long long i = tid; i < pe.cnt[sd]; i += tile) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            // I am the RIGHT neighbour of my left neighbour, and vice versa
+            if (pe.dst[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
+            if (pe.dst[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
+            // a halo nobody reads (no work item touches it) is acknowledged at once
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                if (pe.ack_send[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
+        }
+        return;
+    }
+    const BbbItem item = p.items[p.peer.enabled ? blockIdx.x - 1 : blockIdx.x];
+    const int Ka = item.Ka, Kb = item.Kb, k0 = item.k0;
+    const int Jfirst = Ka - p.l;
+    const int nsteps = (Kb - Ka) + NS - 1;
+
+    // shared memory carve-up
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                       // S barriers (<= 16)
+    i64* Rtab = reinterpret_cast<i64*>(smem + 128);                           // maxseg+1
+    i64* Ctab = Rtab + (p.maxseg + 1);                                        // maxseg+NS+1
+    size_t tab_bytes = 128 + sizeof(i64) * (size_t)(2 * p.maxseg + NS + 2);
+    tab_bytes = (tab_bytes + 127) & ~size_t(127);
+    unsigned char* stage0 = smem + tab_bytes;
+    const int stage_bytes = p.stage_data_bytes + p.stage_x_bytes;
+
+    const T* __restrict__ Xq = p.X + (i64)blockIdx.y * p.ldx;
+    T* __restrict__ Yq = p.Y + (i64)blockIdx.y * p.ldy;
+
+    for (int i = tid; i <= Kb - Ka; i += tile) Rtab[i] = p.R[Ka + i];
+    for (int i = tid; i <= nsteps; i += tile) {
+        i64 J = (i64)Jfirst + i;
+        J = J < 0 ? 0 : (J > p.Nc ? p.Nc : J);
+        Ctab[i] = p.C[J];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) ptx::mbar_init(&bars[s], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint64_t pol_stream = 0, pol_keep = 0;
+    if (tid == 0 && p.l2hint) {
+        pol_stream = ptx::policy_evict_first();
+        pol_keep = ptx::policy_evict_last();
+    }
+
+    // where step `it` takes its x block from: x itself, or (fused multi-GPU path) the halo buffer a
+    // neighbour filled; both indexed by local column
+    auto xsource = [&](int it, int* side) -> const T* {
+        *side = -1;
+        if (p.peer.enabled) {
+            const int Jl = Jfirst + it;
+            *side = Jl < p.peer.own_J0 ? 0 : (Jl >= p.peer.own_J1 ? 1 : -1);
+            if (*side >= 0) return static_cast<const T*>(p.peer.halo[*side]) - p.peer.halo_col0[*side];
+        }
+        return Xq;
+    };
+
+    // producer: one thread issues the bulk copies of a step and arms its barrier
+    auto issue = [&](int it) {
+        const int st = it % S;
+        const StepGeom<T> g = step_geom<T>(Ctab, it, k0, tile, p.lam, p.mu);
+        if (g.jlo >= g.jhi) {
+            ptx::mbar_arrive(&bars[st]);  // nothing to load for this step
+            return;
+        }
+        unsigned char* sd = stage0 + (size_t)st * stage_bytes;
+        unsigned char* sx = sd + p.stage_data_bytes;
+        const uintptr_t d0 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jlo) * (i64)P);
+        const uintptr_t d1 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jhi) * (i64)P);
+        int halo_side = -1;
+        const T* xsrc = xsource(it, &halo_side);
+        const uintptr_t x0 = reinterpret_cast<uintptr_t>(xsrc + g.cbeg + g.jlo);
+        const uintptr_t x1 = reinterpret_cast<uintptr_t>(xsrc + g.cbeg + g.jhi);
+        const uintptr_t dg0 = d0 & ~uintptr_t(15), dg1 = (d1 + 15) & ~uintptr_t(15);
+        const uintptr_t xg0 = x0 & ~uintptr_t(15), xg1 = (x1 + 15) & ~uintptr_t(15);
+        const uint32_t dbytes = static_cast<uint32_t>(dg1 - dg0);
+        const uint32_t xbytes = static_cast<uint32_t>(xg1 - xg0);
+        ptx::mbar_arrive_expect_tx(&bars[st], dbytes + xbytes);
+        if (p.l2hint) ptx::bulk_g2s_hint(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st], pol_stream);
+        else ptx::bulk_g2s(sd, reinterpret_cast<const void*>(dg0), dbytes, &bars[st]);
+        if (halo_side >= 0) {
+            // a halo block column: its x block is stored by the neighbour's pusher CTA -- wait for its epoch
+            // flag, then order the (generic-proxy) acquire before the async-proxy bulk read
+            peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, &p.peer.local->err);
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        if (p.l2hint) ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
+        else ptx::bulk_g2s(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st]);
+    };
+
+    if (tid == 0) {
+        for (int it = 0; it < S - 1 && it < nsteps; ++it) issue(it);
+    }
+
+    T acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = T(0);
+
+    const int k = k0 + tid;
+    const T alpha = p.alpha, beta = p.beta;
+
+    for (int it = 0; it < nsteps; ++it) {
+        // every thread has finished reading the stage that step it+S-1 will overwrite
+        __syncthreads();
+        if (tid == 0 && it + S - 1 < nsteps) issue(it + S - 1);
+
+        const int st = it % S;
+        const int J = Jfirst + it;
+        const StepGeom<T> g = step_geom<T>(Ctab, it, k0, tile, p.lam, p.mu);
+        ptx::mbar_wait(&bars[st], (uint32_t)((it / S) & 1));
+
+        if (g.jlo < g.jhi) {
+            const unsigned char* sd = stage0 + (size_t)st * stage_bytes;
+            const unsigned char* sx = sd + p.stage_data_bytes;
+            const uintptr_t d0 = reinterpret_cast<uintptr_t>(p.data + (g.cbeg + g.jlo) * (i64)P);
+            int side_unused;
+            const uintptr_t x0 = reinterpret_cast<uintptr_t>(xsource(it, &side_unused) + g.cbeg + g.jlo);
+            // Ds[(j-jlo)*P + row] = data[row, cbeg+j];  Xs[j-jlo] = x[cbeg+j]
+            const T* Ds = reinterpret_cast<const T*>(sd + (d0 & 15));
+            const T* Xs = reinterpret_cast<const T*>(sx + (x0 & 15));
+            const int cJ = g.cJ, jlo = g.jlo;
+            if (W > 0) {
+                // the w x-values of this row are shared by all NS slabs: fetch them once
+                constexpr int WW = W > 0 ? W : 1;
+                T xr[WW];
+                int off[WW];
+#pragma unroll
+                for (int ii = 0; ii < WW; ++ii) {
+                    const int j = k + p.mu - ii;
+                    const bool ok = j >= 0 && j < cJ;
+                    off[ii] = ok ? (j - jlo) * P + ii : -1;
+                    xr[ii] = ok ? Xs[j - jlo] : T(0);
+                }
+                // which of the NS block rows this step feeds are live for this thread
+                bool act[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int K = J + s - p.u;
+                    const bool in = K >= Ka && K < Kb;
+                    const int rK = in ? static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]) : 0;
+                    act[s] = k < rK;
+                }
+                // column-major over the sub-band (ascending j per accumulator, as the reference), the NS
+                // accumulators interleaved: branch-free straight-line code with NS independent FMA chains
+#pragma unroll
+                for (int ii = WW - 1; ii >= 0; --ii) {
+                    const int o = off[ii] >= 0 ? off[ii] : 0;   // any in-chunk address; its value is discarded
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        T dv = Ds[o + s * WW];
+                        bool keep = act[s] && off[ii] >= 0;
+                        if (p.tri) {
+                            // slab s is block (J+s-u, J): above the diagonal iff s < u; inside the diagonal block
+                            // entry (k,j) has j - k = mu - ii
+                            const bool up = p.tri == 1;
+                            keep = keep && (s == p.u ? (up ? ii <= p.mu : ii >= p.mu) : (up ? s < p.u : s > p.u));
+                            if (p.unit && s == p.u && ii == p.mu) dv = T(1);
+                        }
+                        const T r = fma(dv, xr[ii], acc[s]);
+                        acc[s] = keep ? r : acc[s];   // never lets an unused slot (NaN) in
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int K = J + s - p.u;
+                    if (K >= Ka && K < Kb) {  // block-uniform
+                        const int rK = static_cast<int>(Rtab[K - Ka + 1] - Rtab[K - Ka]);
+                        if (k < rK) {
+                            for (int ii = w - 1; ii >= 0; --ii) {
+                                const int j = k + p.mu - ii;
+                                if (j < 0 || j >= cJ) continue;
+                                T dv = Ds[(j - jlo) * P + s * w + ii];
+                                if (p.tri) {
+                                    const bool up = p.tri == 1;
+                                    if (!(s == p.u ? (up ? ii <= p.mu : ii >= p.mu) : (up ? s < p.u : s > p.u))) continue;
+                                    if (p.unit && s == p.u && ii == p.mu) dv = T(1);
+                                }
+                                acc[s] = fma(dv, Xs[j - jlo], acc[s]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // block row J-u has now received every block column it overlaps: write it out once
+        const int Kdone = J - p.u;
+        if (Kdone >= Ka && Kdone < Kb) {
+            const i64 r0 = Rtab[Kdone - Ka];
+            const int rK = static_cast<int>(Rtab[Kdone - Ka + 1] - r0);
+            if (k < rK) {
+                T y = alpha * acc[0];
+                if (beta != T(0)) y = fma(beta, Yq[r0 + k], y);
+                Yq[r0 + k] = y;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s + 1 < NS; ++s) acc[s] = acc[s + 1];
+        acc[NS - 1] = T(0);
+    }
+
+    if (p.peer.enabled && blockIdx.y == 0) {
+        // tell the neighbour whose data I read that its next push may overwrite my halo
+        const BbmPeerParams& pe = p.peer;
+        const bool used[2] = {Jfirst < pe.own_J0, Jfirst + nsteps - 1 >= pe.own_J1};
+        if (tid == 0) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                if (!used[sd] || !pe.ack_send[sd]) continue;
+                __threadfence();
+                const unsigned c = atomicAdd(&pe.local->count[sd], 1u);
+                if (c + 1 == (unsigned)pe.consumers[sd]) {
+                    pe.local->count[sd] = 0;
+                    __threadfence_system();
+                    st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
+                }
+            }
+        }
+    }
+}
+
+// Multi-vector variant (A*X): NR right-hand sides per CTA -- the matrix chunk of a step is staged once and
+// multiplied with NR x chunks, so A is streamed once per group of NR columns instead of once per column.
+// Kept apart from the single-vector kernel above: folding NR into it cost the headline path 5-10 %
+// (different unrolling / register allocation), measured on cfg2 and cfg3.
+template <typename T, int NS, int W, int NR>
+__global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int tile = blockDim.x;
@@ -585,13 +839,13 @@ cudaError_t launch_walk_w(const BbbParams<T>& p, int w, int nr, dim3 grid, int t
         return cudaGetLastError();
     };
     if (nr == 4) {
-        if (w == 3) return go(bbb_walk_kernel<T, NS, 3, 4>);
-        if (w == 5) return go(bbb_walk_kernel<T, NS, 5, 4>);
-        return go(bbb_walk_kernel<T, NS, 0, 4>);
+        if (w == 3) return go(bbb_walk_mr_kernel<T, NS, 3, 4>);
+        if (w == 5) return go(bbb_walk_mr_kernel<T, NS, 5, 4>);
+        return go(bbb_walk_mr_kernel<T, NS, 0, 4>);
     }
-    if (w == 3) return go(bbb_walk_kernel<T, NS, 3, 1>);
-    if (w == 5) return go(bbb_walk_kernel<T, NS, 5, 1>);
-    return go(bbb_walk_kernel<T, NS, 0, 1>);
+    if (w == 3) return go(bbb_walk_kernel<T, NS, 3>);
+    if (w == 5) return go(bbb_walk_kernel<T, NS, 5>);
+    return go(bbb_walk_kernel<T, NS, 0>);
 }
 
 template <typename T>
@@ -829,6 +1083,91 @@ int32_t bbb_mul_host_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_
     return BBM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BandedBlockBandedMatrix x BandedBlockBandedMatrix -> BandedBlockBandedMatrix
+// ([upstream] _block_muladd! with one banded x banded gbmm per block triple; result structure
+// src/linalg.jl:50-71).  One thread per stored entry of C: it gathers the (<= (lA+uA+1) blocks) x
+// (<= min(wA,wB) inner indices) products of its row of A and column of B in ascending (N, i) order.
+// Every entry of C's storage is written exactly once (unused slots get beta*old, or 0 for beta == 0, like
+// the reference's _fill_lmul!), so there are no atomics; HBM-bound on C with A and B served by L1/L2.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct BbbMmParams {
+    const T* A; const T* B; T* C;
+    const i64 *RA, *CA, *CB;   // prefix sums: rows of A (= rows of C), cols of A (= rows of B), cols of B (= cols of C)
+    i64 NrA, NcA, NcB, nC;
+    int lA, uA, lamA, muA, wA, PA;
+    int lB, uB, lamB, muB, wB, PB;
+    int lC, uC, lamC, muC, wC, PC;
+    T alpha, beta;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) bbb_matmul_kernel(const BbbMmParams<T> p) {
+    const i64 total = (i64)p.PC * p.nC;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const i64 col = e / p.PC;
+        const int rho = (int)(e - col * p.PC);
+        const int sC = rho / p.wC, ii = rho - sC * p.wC;
+        // J = block column of `col` (last block with CB[J] <= col; empty blocks share a start)
+        i64 lo = 0, hi = p.NcB;
+        while (hi - lo > 1) {
+            const i64 mid = (lo + hi) >> 1;
+            if (p.CB[mid] <= col) lo = mid; else hi = mid;
+        }
+        const i64 J = lo, j = col - p.CB[J];
+        const i64 K = J + sC - p.uC;
+        const i64 k = j - p.muC + ii;
+        T acc = T(0);
+        const bool live = K >= 0 && K < p.NrA && k >= 0 && k < p.RA[K + 1] - p.RA[K];
+        if (live && p.PA > 0 && p.PB > 0) {
+            const i64 Nlo = max(max(K - p.lA, J - p.uB), (i64)0), Nhi = min(min(K + p.uA, J + p.lB), p.NcA - 1);
+            for (i64 N = Nlo; N <= Nhi; ++N) {
+                const i64 cN = p.CA[N + 1] - p.CA[N];
+                const i64 ilo = max(max(k - p.lamA, j - p.muB), (i64)0), ihi = min(min(k + p.muA, j + p.lamB), cN - 1);
+                const T* __restrict__ a = p.A + (i64)(p.uA + K - N) * p.wA + p.muA + k;        // + (-i) + PA*(CA[N]+i)
+                const T* __restrict__ b = p.B + (i64)(p.uB + N - J) * p.wB + p.muB - j + (i64)p.PB * col;  // + i
+                for (i64 i = ilo; i <= ihi; ++i) acc = fma(a[-i + (i64)p.PA * (p.CA[N] + i)], b[i], acc);
+            }
+        }
+        T v = p.alpha * acc;
+        if (p.beta != T(0)) v = fma(p.beta, p.C[e], v);
+        p.C[e] = v;
+    }
+}
+
+template <typename T>
+int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t Cd, T alpha, const T* dA, const T* dB, T beta, T* dC) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!desc_valid(A) || !desc_valid(B) || !desc_valid(Cd)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BandedBlockBandedMatrix descriptor");
+    if (A->Nc != B->Nr || Cd->Nr != A->Nr || Cd->Nc != B->Nc || A->c != B->r || A->r != Cd->r || B->c != Cd->c)
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: block axes of A, B and C are incompatible");
+    if (A->P > 0 && B->P > 0 && (A->l + B->l > Cd->l || A->u + B->u > Cd->u || A->lam + B->lam > Cd->lam || A->mu + B->mu > Cd->mu))
+        return bbm_fail(h, BBM_ERR_BAND, "BandError: the bands of A*B ((%lld,%lld),(%lld,%lld)) do not fit C",
+                        (long long)(A->l + B->l), (long long)(A->u + B->u), (long long)(A->lam + B->lam), (long long)(A->mu + B->mu));
+    const i64 total = Cd->P * Cd->n;
+    if (total == 0) return BBM_OK;
+    if (!dC || (A->P * A->n > 0 && !dA) || (B->P * B->n > 0 && !dB)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (dC == dA || dC == dB) return bbm_fail(h, BBM_ERR_ARG, "mul!: destination must not alias an operand");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    BbbMmParams<T> p{};
+    p.A = dA; p.B = dB; p.C = dC;
+    p.RA = A->dR; p.CA = A->dC; p.CB = B->dC;
+    p.NrA = A->Nr; p.NcA = A->Nc; p.NcB = B->Nc; p.nC = Cd->n;
+    p.lA = (int)A->l; p.uA = (int)A->u; p.lamA = (int)A->lam; p.muA = (int)A->mu; p.wA = (int)std::max<i64>(0, A->lam + A->mu + 1); p.PA = (int)A->P;
+    p.lB = (int)B->l; p.uB = (int)B->u; p.lamB = (int)B->lam; p.muB = (int)B->mu; p.wB = (int)std::max<i64>(0, B->lam + B->mu + 1); p.PB = (int)B->P;
+    p.lC = (int)Cd->l; p.uC = (int)Cd->u; p.lamC = (int)Cd->lam; p.muC = (int)Cd->mu; p.wC = (int)std::max<i64>(1, Cd->lam + Cd->mu + 1); p.PC = (int)Cd->P;
+    p.alpha = alpha; p.beta = beta;
+    const i64 blocks = std::min<i64>((total + 255) / 256, (i64)h->num_sms * 32);
+    bbb_matmul_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_matmul_kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return BBM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -923,6 +1262,14 @@ int32_t bbm_bbb_trimul_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32
                            const float* d_X, int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
     if (uplo != 'U' && uplo != 'L' && uplo != 'u' && uplo != 'l') return bbm_valid(h) ? bbm_fail(h, BBM_ERR_ARG, "uplo must be 'U' or 'L'") : BBM_ERR_HANDLE;
     return bbb_mul_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy, (uplo == 'U' || uplo == 'u') ? 1 : 2, unit ? 1 : 0);
+}
+int32_t bbm_bbb_matmul_f64(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, double alpha, const double* d_A,
+                           const double* d_B, double beta, double* d_C) {
+    return bbb_matmul_impl<double>(h, A, B, C, alpha, d_A, d_B, beta, d_C);
+}
+int32_t bbm_bbb_matmul_f32(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, float alpha, const float* d_A,
+                           const float* d_B, float beta, float* d_C) {
+    return bbb_matmul_impl<float>(h, A, B, C, alpha, d_A, d_B, beta, d_C);
 }
 int32_t bbm_bbb_mul_host_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data, const double* h_X,
                              int64_t ldx, int64_t nrhs, double beta, double* h_Y, int64_t ldy) {

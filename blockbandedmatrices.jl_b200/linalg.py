@@ -55,6 +55,8 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
         return _sky_matmul_(y, A, x, alpha, beta)
     if isinstance(A, _Triangular):
         return _bbb_trimul_(y, A, x, alpha, beta)
+    if isinstance(A, BandedBlockBandedMatrix) and isinstance(x, BandedBlockBandedMatrix):
+        return _bbb_matmul_(y, A, x, alpha, beta)
     if not isinstance(A, (BandedBlockBandedMatrix, BlockSkylineMatrix)):
         raise TypeError(f"unsupported matrix type {type(A).__name__}")
     kind = "bbb" if isinstance(A, BandedBlockBandedMatrix) else "sky"
@@ -91,6 +93,26 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
                 y.ctypes.data_as(C.c_void_p), _ld(y))
     L.check(rc, h.h, "mul!")
     return y
+
+
+def _bbb_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
+    """``mul!(C, A, B, alpha, beta)`` for three device-resident BandedBlockBandedMatrix operands."""
+    if not isinstance(Cm, BandedBlockBandedMatrix):
+        raise TypeError("the destination of a banded-block-banded product must be a BandedBlockBandedMatrix")
+    h = _require_device(A)
+    _require_device(B)
+    _require_device(Cm)
+    if A.shape[1] != B.shape[0] or Cm.shape != (A.shape[0], B.shape[1]):
+        raise L.DimensionMismatch(f"A is {A.shape}, B is {B.shape}, C is {Cm.shape}")
+    dt = A.dtype
+    if dt not in _SUF or B.dtype != dt or Cm.dtype != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, ct = _SUF[dt]
+    fn = getattr(h._lib, f"bbm_bbb_matmul_{suf}")
+    rc = fn(h.h, A.descriptor(h), B.descriptor(h), Cm.descriptor(h), ct(alpha), C.c_void_p(A.data.ptr), C.c_void_p(B.data.ptr),
+            ct(beta), C.c_void_p(Cm.data.ptr))
+    L.check(rc, h.h, "mul!")
+    return Cm
 
 
 def _bbb_trimul_(y, T, x, alpha=1.0, beta=0.0):
@@ -243,6 +265,13 @@ def mul(A, x):
         shape = (m,) if len(x.shape) == 1 else (m, x.shape[1])
         return mul_(h.empty(shape, A.parent.dtype), A, x, 1.0, 0.0)
     h = _require_device(A)
+    if isinstance(A, BandedBlockBandedMatrix) and isinstance(x, BandedBlockBandedMatrix):
+        # similar(::MulAdd{BBB,BBB}) of src/linalg.jl:50-71: summed block and sub-block bandwidths
+        if len(A.cols) != len(x.rows) or (A.cols != x.rows).any():
+            raise L.DimensionMismatch("*")
+        lu, lm = (A.l + x.l, A.u + x.u), (A.lam + x.lam, A.mu + x.mu)
+        shape = BandedBlockBandedMatrix.data_shape(x.cols, lu, lm)
+        return _bbb_matmul_(BandedBlockBandedMatrix(h.empty(shape, A.dtype), A.rows, x.cols, lu, lm), A, x, 1.0, 0.0)
     if isinstance(A, BlockSkylineMatrix) and isinstance(x, BlockSkylineMatrix):
         if len(A.cols) != len(x.rows) or (A.cols != x.rows).any():
             raise L.DimensionMismatch("*")

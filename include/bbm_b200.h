@@ -124,6 +124,15 @@ int32_t bbm_bbb_trimul_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32
                            const float* d_data, const float* d_X, int64_t ldx, int64_t nrhs, float beta,
                            float* d_Y, int64_t ldy);
 
+/* C <- alpha*A*B + beta*C, all three BandedBlockBandedMatrix (replaces [upstream] _block_muladd! with one
+ * banded x banded gbmm per block triple; `similar(::MulAdd)` of src/linalg.jl:50-71 -- bandwidths
+ * (lA+lB, uA+uB), (lamA+lamB, muA+muB) -- stays on the host; test/test_linalg.jl:91-104, 160-171).
+ * BBM_ERR_DIM for incompatible block axes, BBM_ERR_BAND if the product's bands do not fit C.      */
+int32_t bbm_bbb_matmul_f64(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, double alpha,
+                           const double* d_A, const double* d_B, double beta, double* d_C);
+int32_t bbm_bbb_matmul_f32(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, float alpha,
+                           const float* d_A, const float* d_B, float beta, float* d_C);
+
 /* Same product with HOST vectors (the reference-facing call when x, y live in Julia Arrays and
  * the matrix is device-resident): copies X host->device, runs the kernel, copies Y back and
  * synchronises.  h_X / h_Y should be pinned (bbm_host_alloc) for full PCIe speed.             */

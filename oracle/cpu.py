@@ -156,6 +156,21 @@ def sky_matmul(A, B, Cs, alpha, Adata, Bdata, beta, Cdata):
     return Cdata
 
 
+def bbb_matmul(A, B, Cs, alpha, Adata, Bdata, beta, Cdata):
+    """A, B, Cs are (rows, cols, l, u, lam, mu) structure tuples; Cdata (band storage, F order) is updated in place."""
+    suf, ct = _suffix(Adata.dtype)
+    args, keep = [], []
+    for rows, cols, l, u, lam, mu in (A, B, Cs):
+        r, rp = _ia(rows)
+        c, cp = _ia(cols)
+        keep += [r, c]
+        args += [i64(len(r)), i64(len(c)), rp, cp, i64(l), i64(u), i64(lam), i64(mu)]
+    f = getattr(lib(), f"oracle_bbb_matmul_{suf}")
+    rc = f(*args, ct(alpha), Adata.ctypes.data_as(_p), Bdata.ctypes.data_as(_p), ct(beta), Cdata.ctypes.data_as(_p))
+    _check(rc, "bbb_matmul")
+    return Cdata
+
+
 def sky_trsm(rows, l, u, uplo, unit, data, B):
     """B <- T^-1 B in place, T = triangular part ('U'/'L', unit or not) of the skyline matrix."""
     suf, _ = _suffix(data.dtype)
