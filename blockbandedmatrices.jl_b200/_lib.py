@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbbm_b200.so")
+LIB_PATH = os.environ.get("BBM_B200_LIB") or os.path.join(_HERE, "lib", "libbbm_b200.so")  # override: A/B of builds
 CSRC = os.path.join(_HERE, "csrc")
 
 i32, i64, vp, f64, f32, sz = C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_float, C.c_size_t
@@ -117,6 +117,8 @@ def load():
             raise BBMError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("BBM_B200_LIB") and not hasattr(lib, name):
+                continue  # A/B runs against an older build: symbols added since are simply unavailable
             fn = getattr(lib, name)  # AttributeError if the header promises something the .so lacks
             fn.restype = res
             fn.argtypes = args

@@ -82,9 +82,10 @@ struct BbbParams {
     int stage_data_bytes;  // per-stage bytes reserved for the matrix chunk
     int stage_x_bytes;     // per-stage bytes reserved for the x chunk
     int l2hint;
-    int nrhs;
     int tri, unit;         // 0: whole matrix; 1 / 2: Upper- / LowerTriangular(A) (unit: ones on the diagonal)
     BbmPeerParams peer;    // fused halo push over NVLink peer memory (enabled == 0: plain kernel)
+    int nrhs;              // right-hand sides (multi-vector kernel); keep new fields at the END: ptxas' code for the
+                           // single-vector kernel proved sensitive to the parameter layout (5 % on cfg2)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {

@@ -148,3 +148,25 @@ def test_sky_trsm_vs_dense(dtype, uplo, unit, blas):
 def test_sky_trsm_needs_diagonal_blocks():
     with pytest.raises(IndexError):
         O.sky_trsm([2, 2, 2], -1, 2, "U", False, np.ones(F.sky_numentries([2, 2, 2], [2, 2, 2], -1, 2)), np.ones(6))
+
+
+@pytest.mark.parametrize("case", [
+    (list(range(1, 11)), (1, 1), (1, 1), (1, 1), (1, 1)),      # test/test_linalg.jl:91-104
+    (list(range(1, 6)), (-1, 1), (-1, 1), (1, -1), (1, -1)),   # test/test_linalg.jl:160-171
+    ([7, 3, 12, 5, 9], (2, 1), (1, 2), (0, 2), (2, 0)),
+])
+def test_oracle_bbb_matmul_vs_dense(case):
+    """Matrix(A*B) ~= Matrix(A)*Matrix(B) for the block-triple gbmm restatement."""
+    import numpy as np
+    from oracle import cpu as O
+    from oracle import formats as F
+    from tests.helpers import random_bbb, relerr, tol
+    rows, luA, lmA, luB, lmB = case
+    rng = np.random.default_rng(5)
+    adata = random_bbb(rng, rows, rows, *luA, *lmA, poison=False)
+    bdata = random_bbb(rng, rows, rows, *luB, *lmB, poison=False)
+    luC, lmC = (luA[0] + luB[0], luA[1] + luB[1]), (lmA[0] + lmB[0], lmA[1] + lmB[1])
+    c = np.zeros(F.bbb_data_shape(rows, *luC, *lmC), order="F")
+    O.bbb_matmul((rows, rows, *luA, *lmA), (rows, rows, *luB, *lmB), (rows, rows, *luC, *lmC), 1.0, adata, bdata, 0.0, c)
+    dense = F.bbb_to_dense(adata, rows, rows, *luA, *lmA).astype(np.longdouble) @ F.bbb_to_dense(bdata, rows, rows, *luB, *lmB).astype(np.longdouble)
+    assert relerr(F.bbb_to_dense(c, rows, rows, *luC, *lmC), dense) <= tol(np.float64, 16)
