@@ -174,6 +174,31 @@ def run_cfg4(torch, B, h, stream, reps, oracle, nblk=2048, bs=256, peak_tf=None)
     return out
 
 
+def run_bbb_mm(torch, B, h, stream, reps, oracle, n=2048):
+    """A*A for the 2-D Laplacian BandedBlockBandedMatrix (n blocks of size n): (1,1),(1,1)^2 -> (2,2),(2,2)."""
+    rows = [n] * n
+    col = torch.tensor([0, 1, 0, 1, -4, 1, 0, 1, 0], dtype=torch.float64, device="cuda")
+    a_t = col.repeat(n * n, 1).contiguous()
+    c_t = torch.full((n * n, 25), float("nan"), device="cuda", dtype=torch.float64)
+    A = B.BandedBlockBandedMatrix(wrap(B, h, a_t), rows, rows, (1, 1), (1, 1))
+    Cm = B.BandedBlockBandedMatrix(wrap(B, h, c_t), rows, rows, (2, 2), (2, 2))
+    avg, best = time_gpu(torch, stream, lambda: B.mul_(Cm, A, A), reps, warm=2)
+    nbytes = 8 * (2 * 9 + 25) * n * n
+    out = {"config": f"BBB x BBB: Laplacian^2, {n} blocks of {n}, (1,1),(1,1) x same -> (2,2),(2,2), Float64", "ms_avg": avg, "ms_min": best,
+           "algorithmic_bytes": nbytes, "GBps": nbytes / (avg * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "peak_GBps": peaks(), "frac": nbytes / (avg * 1e-3) / 1e9 / peaks()}}
+    # property: (A*A)*x == A*(A*x); interior stencil value check: centre of the 13-point biharmonic-like stencil = 20
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(n * n, generator=gen, device="cuda", dtype=torch.float64)
+    y1 = torch.empty_like(x); t = torch.empty_like(x); y2 = torch.empty_like(x)
+    B.mul_(wrap(B, h, y1), Cm, wrap(B, h, x))
+    B.mul_(wrap(B, h, t), A, wrap(B, h, x)); B.mul_(wrap(B, h, y2), A, wrap(B, h, t))
+    h.synchronize()
+    out["assoc_rel_err"] = relerr(y1.cpu().numpy(), y2.cpu().numpy())
+    out["parity_ok"] = bool(out["assoc_rel_err"] <= 64 * EPS[8] * 25 * 4)
+    return out
+
+
 def run_sky_mv(torch, B, h, stream, reps, oracle, nblk=2048, bs=256, nrhs=1):
     """Skyline matvec / multi-vector product on cfg4's operand (BlockBandedMatrix fill(256,2048), (2,2))."""
     rows = [bs] * nblk
@@ -297,6 +322,8 @@ def main():
             print(json.dumps(run_bbb(torch, B, h, stream, "cfg3: BBB rows=cols=1:4000, (2,2),(2,2)", r, r, (2, 2), (2, 2), dt, args.reps, oracle)), flush=True)
     if "4" in want:
         print(json.dumps(run_cfg4(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
+    if "bbbmm" in want:
+        print(json.dumps(run_bbb_mm(torch, B, h, stream, args.reps, oracle)), flush=True)
     if "4mv" in want:
         for q in (1, 8):
             print(json.dumps(run_sky_mv(torch, B, h, stream, args.reps, oracle, nrhs=q)), flush=True)

@@ -182,6 +182,13 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
                     handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
         y
     end
+    # C <- α A B + β C, all banded-block-banded (result structure from similar(::MulAdd), src/linalg.jl:50-71)
+    @eval function materialize!(M::MulAdd{<:BandedBlockBandedColumns,<:BandedBlockBandedColumns,<:BandedBlockBandedColumns,$T,<:B200BBB{$T},<:B200BBB{$T},<:B200BBB{$T}})
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_matmul_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, $T, Ptr{$T}),
+                    handle().ptr, descriptor(M.A), descriptor(M.B), descriptor(M.C), M.α, parent(M.A.data).ptr, parent(M.B.data).ptr, M.β, parent(M.C.data).ptr))
+        M.C
+    end
     # axpy!(a, X, Y) on identical structures and lmul!(a, A): level-1 kernels on `data`
     # (src/BandedBlockBandedMatrix.jl:605-612)
     @eval function LinearAlgebra.axpy!(a::$T, X::B200BBB{$T}, Y::B200BBB{$T})
