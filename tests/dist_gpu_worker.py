@@ -72,6 +72,52 @@ def main():
             if fused != active:
                 failures.append((ci, use_peer, "fused flag inconsistent"))
             A.close()
+    # ---- row-block-partitioned BlockBandedMatrix: matvec and A*B (halo rows over NCCL point-to-point) ----
+    from tests.helpers import random_sky
+    for ci, (rows, l, u) in enumerate([([16] * 12, 2, 2), ([5, 9, 4, 12, 7, 3, 8, 6], 1, 2), ([64] * 9, 0, 3)]):
+        rng = np.random.default_rng(900 + ci)
+        adata = random_sky(rng, rows, rows, l, u)
+        bdata = random_sky(rng, rows, rows, u, l)
+        Ah = B.BlockSkylineMatrix(adata, rows, rows, l, u)
+        Bh = B.BlockSkylineMatrix(bdata, rows, rows, u, l)
+        kb = D.partition_rows(rows, world)
+        x = rng.standard_normal(sum(rows))
+        mv = D.DistBlockBandedMatvec(h, dist, torch, rows, rows, l, u, kb, rank)
+        lay = mv.layout
+        loc, _, _ = D.sky_cut_rows(Ah, lay["K0"], lay["K1"])
+        mv.tA[:loc.data.size] = torch.from_numpy(loc.data).to(mv.dev)
+        xl = np.full(max(1, lay["n_local"]), np.nan)
+        o, c0 = lay["own_offset"], lay["col_offset"]
+        xl[o:o + lay["n_own"]] = x[c0 + o:c0 + o + lay["n_own"]]
+        mv.x_local[:] = torch.from_numpy(xl).to(mv.dev)
+        mv.exchange()
+        y = mv.mul_().cpu().numpy()[:lay["m_own"]]
+        ref = np.zeros(sum(rows))
+        O.sky_mul(rows, rows, l, u, 1.0, adata, x, 0.0, ref)
+        want = ref[lay["row_offset"]:lay["row_offset"] + lay["m_own"]]
+        if lay["m_own"] and (np.isnan(y).any() or relerr(y, want) > tol(np.float64, 64)):
+            failures.append(("sky matvec", ci, relerr(y, want)))
+        prod = D.DistBlockBandedProduct(h, dist, torch, rows, rows, l, u, rows, u, l, kb, rank)
+        P = prod.plan
+        locA, _, _ = D.sky_cut_rows(Ah, P["K0"], P["K1"])
+        locB, _, _ = D.sky_cut_rows(Bh, P["S0"], P["S1"])
+        prod.tA[:locA.data.size] = torch.from_numpy(locA.data).to(prod.dev)
+        prod.tB[:locB.data.size] = torch.from_numpy(locB.data).to(prod.dev)
+        for N in range(P["S0"], P["S1"]):          # only the exchange may fill the halo rows of B
+            if not (P["O0"] <= N < P["O1"]):
+                for J in range(max(N - u, 0), min(N + l, len(rows) - 1) + 1):
+                    prod._b_block(N, J).fill_(float("nan"))
+        prod.exchange()
+        prod.tC.fill_(float("nan"))
+        prod.mul_(1.0, 0.0)
+        h.synchronize()
+        cref = np.zeros(B.BlockSkylineMatrix.numentries(rows, rows, l + u, l + u))
+        O.sky_matmul((rows, rows, l, u), (rows, rows, u, l), (rows, rows, l + u, l + u), 1.0, adata, bdata, 0.0, cref)
+        wantC, _, _ = D.sky_cut_rows(B.BlockSkylineMatrix(cref, rows, rows, l + u, l + u), P["K0"], P["K1"])
+        gotC = prod.tC.cpu().numpy()[:wantC.data.size]
+        if wantC.data.size and (np.isnan(gotC).any() or relerr(gotC, wantC.data) > tol(np.float64, 256)):
+            failures.append(("sky product", ci, relerr(gotC, wantC.data)))
+
     flag = torch.tensor([len(failures)], device=f"cuda:{local_rank}")
     dist.all_reduce(flag)
     if failures:
