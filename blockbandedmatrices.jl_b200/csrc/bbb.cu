@@ -1139,6 +1139,66 @@ __global__ void __launch_bounds__(256) bbb_matmul_kernel(const BbbMmParams<T> p)
     }
 }
 
+// Column-per-thread variant: column (J,j) of C is A times column (J,j) of B.  The thread reads its P_B
+// contiguous entries of B once and, for each, the P_A contiguous entries of one column of A (neighbouring
+// threads read neighbouring columns of A: L1 hits); the P_C partial sums live in shared memory ([rho][thread],
+// padded, conflict-free both ways) and the CTA's 256 x P_C result slab -- contiguous in C's storage -- is written
+// back coalesced.  The storage row of C an (A entry, B entry) pair lands in depends only on the two storage rows,
+// not on the column, so no index search happens in the inner loops.  Ascending (N, i) order per entry.
+template <typename T>
+__global__ void __launch_bounds__(256) bbb_matmul_col_kernel(const BbbMmParams<T> p) {
+    extern __shared__ __align__(16) unsigned char mmc_smem[];
+    T* acc = reinterpret_cast<T*>(mmc_smem);  // acc[rho * 257 + t]
+    const int tid = threadIdx.x;
+    const int nsA = p.PA / max(p.wA, 1), nsB = p.PB / max(p.wB, 1);
+    for (i64 col0 = (i64)blockIdx.x * 256; col0 < p.nC; col0 += (i64)gridDim.x * 256) {
+        const i64 col = col0 + tid;
+        for (int rho = 0; rho < p.PC; ++rho) acc[rho * 257 + tid] = T(0);
+        if (col < p.nC && p.PA > 0 && p.PB > 0) {
+            i64 lo = 0, hi = p.NcB;
+            while (hi - lo > 1) {
+                const i64 mid = (lo + hi) >> 1;
+                if (p.CB[mid] <= col) lo = mid; else hi = mid;
+            }
+            const i64 J = lo, j = col - p.CB[J];
+            const T* __restrict__ bcol = p.B + (i64)p.PB * col;
+            for (int sB = 0; sB < nsB; ++sB) {
+                const i64 N = J + sB - p.uB;
+                if (N < 0 || N >= p.NcA) continue;
+                const i64 cN = p.CA[N + 1] - p.CA[N];
+                for (int iB = 0; iB < p.wB; ++iB) {
+                    const i64 i = j - p.muB + iB;
+                    if (i < 0 || i >= cN) continue;
+                    const T b = bcol[sB * p.wB + iB];
+                    const T* __restrict__ acol = p.A + (i64)p.PA * (p.CA[N] + i);
+                    for (int sA = 0; sA < nsA; ++sA) {
+                        const i64 K = N + sA - p.uA;
+                        if (K < 0 || K >= p.NrA) continue;
+                        const i64 rK = p.RA[K + 1] - p.RA[K];
+                        const int sC = p.uC - p.uA - p.uB + sA + sB;          // = uC + K - J
+                        for (int iA = 0; iA < p.wA; ++iA) {
+                            const i64 k = i - p.muA + iA;
+                            if (k < 0 || k >= rK) continue;
+                            const int rho = sC * p.wC + (p.muC - p.muA - p.muB + iA + iB);   // iiC = muC + k - j
+                            acc[rho * 257 + tid] = fma(acol[sA * p.wA + iA], b, acc[rho * 257 + tid]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const i64 ncol = min((i64)256, p.nC - col0);
+        T* __restrict__ cslab = p.C + (i64)p.PC * col0;
+        for (i64 idx = tid; idx < ncol * p.PC; idx += 256) {
+            const int t = (int)(idx / p.PC), rho = (int)(idx - (i64)t * p.PC);
+            T v = p.alpha * acc[rho * 257 + t];
+            if (p.beta != T(0)) v = fma(p.beta, cslab[idx], v);
+            cslab[idx] = v;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t Cd, T alpha, const T* dA, const T* dB, T beta, T* dC) {
     BBM_REQUIRE_HANDLE(h);
@@ -1161,9 +1221,17 @@ int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_
     p.lB = (int)B->l; p.uB = (int)B->u; p.lamB = (int)B->lam; p.muB = (int)B->mu; p.wB = (int)std::max<i64>(0, B->lam + B->mu + 1); p.PB = (int)B->P;
     p.lC = (int)Cd->l; p.uC = (int)Cd->u; p.lamC = (int)Cd->lam; p.muC = (int)Cd->mu; p.wC = (int)std::max<i64>(1, Cd->lam + Cd->mu + 1); p.PC = (int)Cd->P;
     p.alpha = alpha; p.beta = beta;
-    const i64 blocks = std::min<i64>((total + 255) / 256, (i64)h->num_sms * 32);
-    bbb_matmul_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    const size_t smem = (size_t)p.PC * 257 * sizeof(T);
+    if (smem <= std::min<size_t>(h->smem_optin, 200 * 1024) && bbm_opt(h, "bbb.mm_kernel", 0) != 2) {
+        e = cudaFuncSetAttribute(bbb_matmul_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const i64 blocks = std::min<i64>((Cd->n + 255) / 256, (i64)h->num_sms * 8);
+        if (e == cudaSuccess) bbb_matmul_col_kernel<T><<<(unsigned)blocks, 256, smem, h->stream>>>(p);
+    } else {
+        const i64 blocks = std::min<i64>((total + 255) / 256, (i64)h->num_sms * 32);
+        bbb_matmul_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_matmul_kernel launch: %s", cudaGetErrorString(e));
     h->launches += 1;
     return BBM_OK;

@@ -254,37 +254,42 @@ BBB_MM_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", [0, 2], ids=["column", "entry"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("case", BBB_MM_CASES, ids=lambda c: f"n{len(c[0])}_A{c[1]}{c[2]}_B{c[3]}{c[4]}".replace(" ", ""))
-def test_bbb_matmul_matches_oracle(handle, case, dtype):
+def test_bbb_matmul_matches_oracle(handle, case, dtype, kernel):
     rows, luA, lmA, luB, lmB = case
-    rng = np.random.default_rng(61)
-    adata = random_bbb(rng, rows, rows, *luA, *lmA, dtype)
-    bdata = random_bbb(rng, rows, rows, *luB, *lmB, dtype)
-    A = B.BandedBlockBandedMatrix(adata, rows, rows, luA, lmA)
-    Bm = B.BandedBlockBandedMatrix(bdata, rows, rows, luB, lmB)
-    Ad, Bd = A.to_device(handle), Bm.to_device(handle)
-    Cd = B.mul(Ad, Bd)                                              # similar(::MulAdd) + mul!
-    luC, lmC = (luA[0] + luB[0], luA[1] + luB[1]), (lmA[0] + lmB[0], lmA[1] + lmB[1])
-    assert Cd.blockbandwidths == luC and Cd.subblockbandwidths == lmC    # src/linalg.jl:50-71
-    nnz = max(1, (luA[0] + luA[1] + 1) * (lmA[0] + lmA[1] + 1)) + 1
-    dense = A.to_dense().astype(np.longdouble) @ Bm.to_dense().astype(np.longdouble)
-    got = Cd.to_dense()
-    assert not np.isnan(got).any()
-    assert relerr(got, dense) <= tol(dtype, nnz)
-    # against the oracle's block-triple loop, storage slot by storage slot (unused slots: beta*old)
-    shape = B.BandedBlockBandedMatrix.data_shape(rows, luC, lmC)
-    c0 = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
-    Cd2 = B.BandedBlockBandedMatrix(c0.copy(order="F"), rows, rows, luC, lmC).to_device(handle)
-    B.mul_(Cd2, Ad, Bd, 1.5, -0.5)
-    ref = c0.copy(order="F")
-    O.bbb_matmul((rows, rows, *luA, *lmA), (rows, rows, *luB, *lmB), (rows, rows, *luC, *lmC), 1.5,
-                 np.nan_to_num(adata), np.nan_to_num(bdata), -0.5, ref)
-    got2 = Cd2.data.to_host() if ref.size else ref
-    mask = F.bbb_valid_mask(rows, rows, *luC, *lmC) if ref.size else np.zeros(shape, dtype=bool)
-    if ref.size:
-        assert relerr(got2[mask], ref[mask]) <= tol(dtype, nnz)
-        assert relerr(got2[~mask], -0.5 * c0[~mask]) <= tol(dtype, 1)   # _fill_lmul! scales every stored slot
+    handle.set_option("bbb.mm_kernel", kernel)
+    try:
+        rng = np.random.default_rng(61)
+        adata = random_bbb(rng, rows, rows, *luA, *lmA, dtype)
+        bdata = random_bbb(rng, rows, rows, *luB, *lmB, dtype)
+        A = B.BandedBlockBandedMatrix(adata, rows, rows, luA, lmA)
+        Bm = B.BandedBlockBandedMatrix(bdata, rows, rows, luB, lmB)
+        Ad, Bd = A.to_device(handle), Bm.to_device(handle)
+        Cd = B.mul(Ad, Bd)                                              # similar(::MulAdd) + mul!
+        luC, lmC = (luA[0] + luB[0], luA[1] + luB[1]), (lmA[0] + lmB[0], lmA[1] + lmB[1])
+        assert Cd.blockbandwidths == luC and Cd.subblockbandwidths == lmC    # src/linalg.jl:50-71
+        nnz = max(1, (luA[0] + luA[1] + 1) * (lmA[0] + lmA[1] + 1)) + 1
+        dense = A.to_dense().astype(np.longdouble) @ Bm.to_dense().astype(np.longdouble)
+        got = Cd.to_dense()
+        assert not np.isnan(got).any()
+        assert relerr(got, dense) <= tol(dtype, nnz)
+        # against the oracle's block-triple loop, storage slot by storage slot (unused slots: beta*old)
+        shape = B.BandedBlockBandedMatrix.data_shape(rows, luC, lmC)
+        c0 = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+        Cd2 = B.BandedBlockBandedMatrix(c0.copy(order="F"), rows, rows, luC, lmC).to_device(handle)
+        B.mul_(Cd2, Ad, Bd, 1.5, -0.5)
+        ref = c0.copy(order="F")
+        O.bbb_matmul((rows, rows, *luA, *lmA), (rows, rows, *luB, *lmB), (rows, rows, *luC, *lmC), 1.5,
+                     np.nan_to_num(adata), np.nan_to_num(bdata), -0.5, ref)
+        got2 = Cd2.data.to_host() if ref.size else ref
+        mask = F.bbb_valid_mask(rows, rows, *luC, *lmC) if ref.size else np.zeros(shape, dtype=bool)
+        if ref.size:
+            assert relerr(got2[mask], ref[mask]) <= tol(dtype, nnz)
+            assert relerr(got2[~mask], -0.5 * c0[~mask]) <= tol(dtype, 1)   # _fill_lmul! scales every stored slot
+    finally:
+        handle.set_option("bbb.mm_kernel", 0)
 
 
 def test_bbb_matmul_errors(handle):
