@@ -25,6 +25,9 @@
  *     *_host_* convenience calls and bbm_synchronize.
  *   - a handle is not thread-safe; distinct handles are independent.  Every call does its own
  *     cudaSetDevice, so calls may come from any host thread / Julia task.
+ *   - the band-walk matvec moves `data` and `x` with 16-byte-granular bulk copies: the 16-byte-aligned
+ *     windows around the addressed ranges must be readable (true for cudaMalloc / bbm_malloc memory, whose
+ *     allocations are padded to at least 256 bytes; bytes outside the addressed range are never used).
  *   - there is NO CPU fallback: without a usable CUDA device bbm_create fails with BBM_ERR_CUDA.
  */
 #ifndef BBM_B200_H
