@@ -991,6 +991,70 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     return BBM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// transposed product  Y <- alpha*A^T*X + beta*Y  (`mul!(y, A', x)`; layouts of src/adjtransblockbanded.jl:2-7)
+// In band storage column c of `data` holds exactly the entries of column c of A, i.e. of row c of A^T: output
+// entry c is the dot product of that contiguous column (P values) with gathered x -- no accumulation across
+// columns, no atomics.  One thread per column; for a fixed storage row the threads of a warp read x at
+// consecutive rows (coalesced) and `data` at stride P (every byte of the touched lines is used by the warp's
+// next storage rows: L1 absorbs the stride).  Summation order: ascending storage row = ascending (K, k).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bbb_mul_t_kernel(const BbbParams<T> p, i64 n) {
+    const T* __restrict__ Xq = p.X + (i64)blockIdx.y * p.ldx;
+    T* __restrict__ Yq = p.Y + (i64)blockIdx.y * p.ldy;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const int NS = p.w > 0 ? p.P / p.w : 0;
+    for (i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x; col < n; col += stride) {
+        i64 lo = 0, hi = p.Nc;  // J = last block column with C[J] <= col
+        while (hi - lo > 1) {
+            const i64 mid = (lo + hi) >> 1;
+            if (p.C[mid] <= col) lo = mid; else hi = mid;
+        }
+        const i64 J = lo, j = col - p.C[J];
+        const T* __restrict__ dcol = p.data + (i64)p.P * col;
+        T acc = T(0);
+        for (int s = 0; s < NS; ++s) {
+            const i64 K = J + s - p.u;
+            if (K < 0 || K >= p.Nr) continue;
+            const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
+            for (int ii = 0; ii < p.w; ++ii) {
+                const i64 k = j - p.mu + ii;
+                if (k >= 0 && k < rK) acc = fma(dcol[s * p.w + ii], Xq[r0 + k], acc);
+            }
+        }
+        T y = p.alpha * acc;
+        if (p.beta != T(0)) y = fma(p.beta, Yq[col], y);
+        Yq[col] = y;
+    }
+}
+
+template <typename T>
+int32_t bbb_mul_t_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs, T beta,
+                       T* d_Y, i64 ldy) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!desc_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BandedBlockBandedMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && (ldx < std::max<i64>(1, d->m) || ldy < std::max<i64>(1, d->n)))
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: A' is %lld x %lld, ldx=%lld, ldy=%lld", (long long)d->n,
+                        (long long)d->m, (long long)ldx, (long long)ldy);
+    if (d->n == 0 || nrhs == 0) return BBM_OK;
+    if (!d_Y || (d->m > 0 && !d_X) || (d->P > 0 && !d_data)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (nrhs > 65535) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "nrhs > 65535");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    BbbParams<T> p{};
+    p.data = d_data; p.X = d_X; p.Y = d_Y; p.ldx = ldx; p.ldy = ldy; p.alpha = alpha; p.beta = beta;
+    p.R = d->dR; p.C = d->dC; p.Nr = d->Nr; p.Nc = d->Nc; p.m = d->m;
+    p.l = (int)d->l; p.u = (int)d->u; p.lam = (int)d->lam; p.mu = (int)d->mu;
+    p.w = (int)std::max<i64>(0, d->lam + d->mu + 1); p.P = (int)d->P;
+    const i64 blocks = std::min<i64>((d->n + 255) / 256, (i64)h->num_sms * 32);
+    bbb_mul_t_kernel<T><<<dim3((unsigned)std::max<i64>(1, blocks), (unsigned)nrhs), 256, 0, h->stream>>>(p, d->n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_mul_t_kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return BBM_OK;
+}
+
 template <typename T>
 int32_t bbb_mul_host_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data, const T* h_X, i64 ldx, i64 nrhs,
                           T beta, T* h_Y, i64 ldy) {
@@ -1331,6 +1395,14 @@ int32_t bbm_bbb_trimul_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32
                            const float* d_X, int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
     if (uplo != 'U' && uplo != 'L' && uplo != 'u' && uplo != 'l') return bbm_valid(h) ? bbm_fail(h, BBM_ERR_ARG, "uplo must be 'U' or 'L'") : BBM_ERR_HANDLE;
     return bbb_mul_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy, (uplo == 'U' || uplo == 'u') ? 1 : 2, unit ? 1 : 0);
+}
+int32_t bbm_bbb_mul_t_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data, const double* d_X, int64_t ldx,
+                          int64_t nrhs, double beta, double* d_Y, int64_t ldy) {
+    return bbb_mul_t_impl<double>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_bbb_mul_t_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data, const float* d_X, int64_t ldx,
+                          int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
+    return bbb_mul_t_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
 }
 int32_t bbm_bbb_matmul_f64(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, double alpha, const double* d_A,
                            const double* d_B, double beta, double* d_C) {

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from .device import DeviceArray
-from .matrices import BandedBlockBandedMatrix, BlockSkylineMatrix, _Triangular
+from .matrices import Adjoint, BandedBlockBandedMatrix, BlockSkylineMatrix, _Triangular
 
 _SUF = {np.dtype(np.float64): ("f64", C.c_double), np.dtype(np.float32): ("f32", C.c_float)}
 
@@ -55,6 +55,8 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
         return _sky_matmul_(y, A, x, alpha, beta)
     if isinstance(A, _Triangular):
         return _bbb_trimul_(y, A, x, alpha, beta)
+    if isinstance(A, Adjoint):
+        return _bbb_mul_t_(y, A, x, alpha, beta)
     if isinstance(A, BandedBlockBandedMatrix) and isinstance(x, BandedBlockBandedMatrix):
         return _bbb_matmul_(y, A, x, alpha, beta)
     if not isinstance(A, (BandedBlockBandedMatrix, BlockSkylineMatrix)):
@@ -113,6 +115,30 @@ def _bbb_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
             ct(beta), C.c_void_p(Cm.data.ptr))
     L.check(rc, h.h, "mul!")
     return Cm
+
+
+def _bbb_mul_t_(y, At, x, alpha=1.0, beta=0.0):
+    """``mul!(y, A', x, alpha, beta)`` for a device-resident real BandedBlockBandedMatrix."""
+    A = At.parent
+    if not isinstance(A, BandedBlockBandedMatrix):
+        raise TypeError("adjoint products are taken for BandedBlockBandedMatrix parents only")
+    h = _require_device(A)
+    m, n = A.shape
+    xr, xc = _vec_dims(x, "x")
+    yr, yc = _vec_dims(y, "y")
+    if xr != m or yr != n or xc != yc:
+        raise L.DimensionMismatch(f"A' is {n}x{m}, x is {x.shape}, y is {y.shape}")
+    if not (isinstance(x, DeviceArray) and isinstance(y, DeviceArray)):
+        raise TypeError("adjoint products take device vectors")
+    dt = A.dtype
+    if dt not in _SUF or np.dtype(x.dtype) != dt or np.dtype(y.dtype) != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, ct = _SUF[dt]
+    fn = getattr(h._lib, f"bbm_bbb_mul_t_{suf}")
+    rc = fn(h.h, A.descriptor(h), ct(alpha), C.c_void_p(A.data.ptr), C.c_void_p(x.ptr), _ld(x), xc, ct(beta),
+            C.c_void_p(y.ptr), _ld(y))
+    L.check(rc, h.h, "mul!")
+    return y
 
 
 def _bbb_trimul_(y, T, x, alpha=1.0, beta=0.0):
@@ -259,6 +285,11 @@ def ldiv(T, B):
 def mul(A, x):
     """``A*x``: allocates the result where x lives (``similar`` + ``mul!``).  For two
     BlockSkylineMatrix operands the result structure is ``similar(::MulAdd)`` of src/linalg.jl:32-48."""
+    if isinstance(A, Adjoint):
+        h = _require_device(A.parent)
+        n = A.parent.shape[1]
+        shape = (n,) if len(x.shape) == 1 else (n, x.shape[1])
+        return mul_(h.empty(shape, A.parent.dtype), A, x, 1.0, 0.0)
     if isinstance(A, _Triangular):
         h = _require_device(A.parent)
         m = A.parent.shape[0]

@@ -431,6 +431,32 @@ class _Triangular:
         return (l, u)
 
 
+class Adjoint:
+    """``A'`` / ``transpose(A)`` of a real BandedBlockBandedMatrix: reversed bandwidths
+    (src/adjtransblockbanded.jl:2-3), products through the transposed kernel."""
+
+    def __init__(self, parent):
+        self.parent = parent
+
+    @property
+    def shape(self):
+        return (self.parent.shape[1], self.parent.shape[0])
+
+    @property
+    def blockbandwidths(self):
+        l, u = self.parent.blockbandwidths
+        return (u, l)
+
+    @property
+    def subblockbandwidths(self):
+        lam, mu = self.parent.subblockbandwidths
+        return (mu, lam)
+
+    def __matmul__(self, x):
+        from .linalg import mul
+        return mul(self, x)
+
+
 def UpperTriangular(A):
     return _Triangular(A, "U", False)
 

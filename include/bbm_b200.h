@@ -127,6 +127,14 @@ int32_t bbm_bbb_trimul_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32
                            const float* d_data, const float* d_X, int64_t ldx, int64_t nrhs, float beta,
                            float* d_Y, int64_t ldy);
 
+/* Y <- alpha*A^T*X + beta*Y: `mul!(y, A', x)` / `transpose(A)*x` for real element types (the adjoint's
+ * Rows layouts and reversed bandwidths: src/adjtransblockbanded.jl:2-7, src/AbstractBlockBandedMatrix.jl:32-40;
+ * [upstream] block loop + gbmv 'T' per block on the same band arrays).  d_X: m x nrhs, d_Y: n x nrhs.      */
+int32_t bbm_bbb_mul_t_f64(bbm_handle_t h, bbm_bbb_desc_t d, double alpha, const double* d_data, const double* d_X,
+                          int64_t ldx, int64_t nrhs, double beta, double* d_Y, int64_t ldy);
+int32_t bbm_bbb_mul_t_f32(bbm_handle_t h, bbm_bbb_desc_t d, float alpha, const float* d_data, const float* d_X,
+                          int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
+
 /* C <- alpha*A*B + beta*C, all three BandedBlockBandedMatrix (replaces [upstream] _block_muladd! with one
  * banded x banded gbmm per block triple; `similar(::MulAdd)` of src/linalg.jl:50-71 -- bandwidths
  * (lA+lB, uA+uB), (lamA+lamB, muA+muB) -- stays on the host; test/test_linalg.jl:91-104, 160-171).

@@ -302,3 +302,39 @@ def test_bbb_matmul_errors(handle):
     B.mul_(Cw, A, A)
     with pytest.raises(B.DimensionMismatch):
         B.mul_(Cw, A, B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4, 5, 1], rows, (1, 1), (1, 1)).to_device(handle))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", BBB_CASES, ids=lambda c: f"r{len(c[0])}c{len(c[1])}_l{c[2]}u{c[3]}_lam{c[4]}mu{c[5]}")
+def test_bbb_adjoint_mul_matches_oracle(handle, case, dtype):
+    """mul!(y, A', x): reversed bandwidths (src/adjtransblockbanded.jl:2-3, test/test_adjtransblockbanded.jl)
+    and the transposed product against the oracle's gbmv-'T' block loop and a dense check."""
+    rows, cols, l, u, lam, mu = case
+    rng = np.random.default_rng(71)
+    data = random_bbb(rng, rows, cols, l, u, lam, mu, dtype)
+    A = B.BandedBlockBandedMatrix(data, rows, cols, (l, u), (lam, mu))
+    Ad = A.to_device(handle)
+    At = B.Adjoint(Ad)
+    assert At.blockbandwidths == (u, l) and At.subblockbandwidths == (mu, lam)
+    m, n = A.shape
+    for nrhs, alpha, beta in [(None, 1.0, 0.0), (3, 2.0, -0.5)]:
+        xs = (m,) if nrhs is None else (m, nrhs)
+        ys = (n,) if nrhs is None else (n, nrhs)
+        X = np.asfortranarray(rng.standard_normal(xs).astype(dtype))
+        Y0 = np.asfortranarray(rng.standard_normal(ys).astype(dtype))
+        Yin = Y0.copy(order="F")
+        if beta == 0:
+            Yin[...] = np.nan
+        dY = handle.to_device(Yin)
+        B.mul_(dY, At, handle.to_device(X), alpha, beta)
+        got = dY.to_host()
+        ref = Y0.copy(order="F")
+        O.bbb_mul_t(rows, cols, l, u, lam, mu, alpha, np.nan_to_num(data), X, beta, ref)
+        nnz = F.bbb_nnz_per_row_max(l, u, lam, mu) + 1
+        assert not np.isnan(got).any()
+        assert relerr(got, ref) <= tol(dtype, nnz)
+        if m and n:
+            dense = alpha * (A.to_dense().astype(np.longdouble).T @ X.astype(np.longdouble)) + beta * Y0.astype(np.longdouble)
+            assert relerr(got, dense) <= tol(dtype, nnz)
+    with pytest.raises(B.DimensionMismatch):
+        B.mul_(handle.empty(n + 1, dtype), At, handle.empty(m, dtype))
