@@ -182,6 +182,16 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
                     handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
         y
     end
+    # mul!(y, A', x) / transpose(A)*x for real T: the adjoint's Rows layout (src/adjtransblockbanded.jl:2-7)
+    @eval function materialize!(M::MulAdd{<:BlockBandedMatrices.BandedBlockBandedRows,<:Any,<:Any,$T,<:Union{Adjoint{$T,<:B200BBB{$T}},Transpose{$T,<:B200BBB{$T}}},<:B200Array{$T},<:B200Array{$T}})
+        A, x, y = parent(M.A), M.B, M.C
+        size(A, 1) == size(x, 1) && size(A, 2) == size(y, 1) && size(x, 2) == size(y, 2) ||
+            throw(DimensionMismatch("A' has size $(reverse(size(A))), x has size $(size(x)), y has size $(size(y))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_mul_t_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
+                    handle().ptr, descriptor(A), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
+        y
+    end
     # C <- α A B + β C, all banded-block-banded (result structure from similar(::MulAdd), src/linalg.jl:50-71)
     @eval function materialize!(M::MulAdd{<:BandedBlockBandedColumns,<:BandedBlockBandedColumns,<:BandedBlockBandedColumns,$T,<:B200BBB{$T},<:B200BBB{$T},<:B200BBB{$T}})
         check(ccall(($(QuoteNode(Symbol("bbm_bbb_matmul_", suf))), libbbm), Int32,
