@@ -352,7 +352,11 @@ def bench_distributed(args, torch, dist, B, h, stream, nb, block, rank, world, l
     nbytes = algorithmic_bytes(9, n, n)
     # fused halo push over NVLink peer memory (one kernel per step); falls back to the NCCL exchange
     no_peer = any(o.replace(" ", "") == "dist.peer=0" for o in args.opt)
-    fused = (not no_peer) and A.enable_peer()   # collective: every rank takes the same branch
+    try:
+        fused = (not no_peer) and A.enable_peer()   # collective: every rank takes the same branch
+    except Exception as exc:  # a rank-local setup failure is reported by the library as "unsupported" on all ranks
+        print(f"[rank {rank}] fused halo push unavailable: {exc}", file=sys.stderr)
+        fused = False
 
     with torch.cuda.stream(stream):
         for _ in range(W):

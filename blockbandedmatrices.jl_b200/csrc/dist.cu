@@ -584,12 +584,19 @@ int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t pl, int32_t elem_size) {
     for (int q = 0; q < nranks; ++q) all_ok = all_ok && all[q].ok == 1;
     pl->peer_ok = false;
     if (!all_ok) { cudaFree(d_all); return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push not applicable to this partition; the NCCL exchange stays in use"); }
+    bool opened = true;
     for (int sd = 0; sd < 2; ++sd) {
         const int q = sd == 0 ? rank - 1 : rank + 1;
         if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
         if (q < 0 || q >= nranks || (tpl.cnt[sd] == 0 && !tpl.has_halo[sd])) continue;
         cudaError_t e = cudaIpcOpenMemHandle(&pl->ipc_sig[sd], all[q].blk, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(d_all); return bbm_fail(h, BBM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); }
+        if (e != cudaSuccess) {  // no peer mapping on this system: every rank must learn it (second all-gather below)
+            cudaGetLastError();
+            bbm_fail(h, BBM_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+            pl->ipc_sig[sd] = nullptr;
+            opened = false;
+            continue;
+        }
         tpl.remote[sd] = static_cast<BbmPeerSig*>(pl->ipc_sig[sd]);
     }
     for (int sd = 0; sd < 2; ++sd) {
@@ -607,11 +614,21 @@ int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t pl, int32_t elem_size) {
         pl->nb_buf[0][par] = buf_off(nbL[0], nbR[0], 1, par) + 256;  // left neighbour's RIGHT halo
         pl->nb_buf[1][par] = buf_off(nbL[1], nbR[1], 0, par) + 256;  // right neighbour's LEFT halo
     }
-    // nobody may push before every rank has reset its flags and opened its mappings
+    // nobody may push before every rank has reset its flags and opened its mappings; the same all-gather
+    // tells every rank whether all mappings could be opened, so that the ranks switch paths together
+    mine.ok = opened ? 1 : 0;
+    BBM_CUDA(h, cudaMemcpy(d_all + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
     nrc = nccl().AllGather(d_all + rank, d_all, sizeof(Rec), ncclChar, cm->comm, cm->stream);
     cudaStreamSynchronize(cm->stream);
+    if (nrc == ncclSuccess) cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost);
     cudaFree(d_all);
     if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "enable_peer barrier: %s", nccl().GetErrorString(nrc));
+    for (int q = 0; q < nranks; ++q) opened = opened && all[q].ok == 1;
+    if (!opened) {
+        for (int sd = 0; sd < 2; ++sd)
+            if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
+        return bbm_fail(h, BBM_ERR_UNSUPPORTED, "peer memory mappings are not available on every rank; the NCCL exchange stays in use");
+    }
     pl->peer_ok = true;
     return BBM_OK;
 }
