@@ -280,8 +280,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_ker
     double* As = reinterpret_cast<double*>(mm_smem);
     double* Bs = As + (size_t)kMmStages * kMmBK * LDA;
 
+    // the tile tables are written once at plan time: they may be read before the predecessor kernel (a
+    // programmatic dependent launch of the triangular solve's chain) has finished; operands may not
     const MmTile tile = p.tiles[blockIdx.x];
     const MmCBlk cb = p.cblks[tile.cblk];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
     const int row0 = tile.ti * BM, col0 = tile.tj * BN;
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_ker
         }
     }
     cp_async_wait<0>();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the successor may start its prologue
 
     // epilogue: accumulator (row = lane/4, cols = 2*(lane%4)+{0,1}) -> C, written once
     const double alpha = p.alpha, beta = p.beta;
@@ -911,7 +915,7 @@ int32_t upload_batch(bbm_handle_t h, const MmBatchHost& hb, bbm_sky_desc::Tri::B
 
 // C (+)= alpha * A * B over the tiles [t0, t0+nt) of a batch; 64x64 DMMA tiles, 4 warps
 int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, int nt, const double* A, const double* Bm,
-                    double* Cm, double alpha, double beta, bool atomic, bool set_attr = true) {
+                    double* Cm, double alpha, double beta, bool atomic, bool set_attr = true, bool pdl = false) {
     if (nt <= 0) return BBM_OK;
     MmParams<double> p{A, Bm, Cm, (const MmCBlk*)b.cblks, (const MmSeg*)b.segs, (const MmTile*)b.tiles + t0, alpha, beta};
     const bool al = b.aligned && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(Bm) % 16 == 0);
@@ -923,7 +927,18 @@ int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, i
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             where = "cudaFuncSetAttribute";
         }
-        if (e == cudaSuccess) { kern<<<nt, 128, smem, h->stream>>>(p); e = cudaGetLastError(); where = "launch"; }
+        if (e == cudaSuccess) {
+            // programmatic dependent launch: the kernel's launch latency and prologue overlap the predecessor's
+            // tail; griddepcontrol.wait inside the kernel still orders all operand accesses after it
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)nt); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+            e = cudaLaunchKernelEx(&cfg, kern, p);
+            where = "launch";
+        }
     };
     if (al && atomic) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, true, 4>);
     else if (al) go(sky_dgemm_dmma_kernel<64, 64, 32, 32, 16, true, false, 4>);
@@ -1106,8 +1121,9 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
             }
         }
         // (the opt-in shared-memory size of the kernel variant only has to be set once per call)
-        rc = launch_mm64(h, t.stepA, t.ptrA[K], t.ptrA[K + 1] - t.ptrA[K], W, d_B, X, 1.0, 1.0, true, s < 2);
-        if (rc == BBM_OK) rc = launch_mm64(h, t.stepB, t.ptrB[K], t.ptrB[K + 1] - t.ptrB[K], d_data, X, d_B, -1.0, 1.0, true, s < 2);
+        const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
+        rc = launch_mm64(h, t.stepA, t.ptrA[K], t.ptrA[K + 1] - t.ptrA[K], W, d_B, X, 1.0, 1.0, true, s < 2, pdl);
+        if (rc == BBM_OK) rc = launch_mm64(h, t.stepB, t.ptrB[K], t.ptrB[K + 1] - t.ptrB[K], d_data, X, d_B, -1.0, 1.0, true, s < 2, pdl);
         if (rc != BBM_OK) return rc;
         if (prefetch) {
             BBM_CUDA(h, cudaEventRecord(h->side_ev[s & 1], h->stream));
