@@ -1159,8 +1159,18 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     int32_t rc = build_tri(h, d, upper);
     if (rc != BBM_OK) return rc;
     bbm_sky_desc::Tri& t = d->tri[upper];
-    if (sizeof(T) == 8 && nrhs >= 16 && bbm_opt(h, "trsm.kernel", 0) == 0)
-        return sky_trsm_gemm(h, d, upper, unit ? 1 : 0, reinterpret_cast<const double*>(d_data), reinterpret_cast<double*>(d_B), ldb, nrhs);
+    if (sizeof(T) == 8 && nrhs >= 16 && bbm_opt(h, "trsm.kernel", 0) == 0) {
+        // the GEMM path stores an explicit inverse (and a level temporary) per diagonal block: take it only if
+        // that workspace is a modest share of the free device memory, else solve by substitution
+        double wbytes = 0;
+        for (i64 K = 0; K < d->Nr; ++K) wbytes += 2.0 * 8.0 * (double)(d->r[K] + 1) * (double)(d->r[K] + 1);
+        wbytes += 8.0 * (double)(d->m + 2) * (double)nrhs;
+        size_t free_b = 0, total_b = 0;
+        const size_t have = h->ws_z_bytes + h->ws_w_bytes + h->ws_y_bytes;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        if (wbytes <= 0.5 * ((double)free_b + (double)have))
+            return sky_trsm_gemm(h, d, upper, unit ? 1 : 0, reinterpret_cast<const double*>(d_data), reinterpret_cast<double*>(d_B), ldb, nrhs);
+    }
     // pass 0: inverses of the 32x32 diagonal sub-blocks (workspace: 1024 entries per sub-block)
     rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, (size_t)t.nsub * 1024 * sizeof(T));
     if (rc != BBM_OK) return rc;
