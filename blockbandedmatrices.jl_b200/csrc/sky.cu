@@ -713,106 +713,6 @@ __global__ void __launch_bounds__(256) sky_tri_diag_kernel(const T* __restrict__
     }
 }
 
-constexpr int kTriBufs = 4;  // pieces in flight ahead of the chain: (kTriBufs-1) x HC columns
-
-template <typename T>
-__device__ __forceinline__ void cp_async_elem(T* dst, const T* src) {
-    if (sizeof(T) == 8)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-
-// Same blocked substitution, but the diagonal block streams through shared memory: none of its
-// loads depends on the solution, so the off-diagonal pieces T[rows, HC columns] (and the inverted
-// 32x32 sub-blocks) are fetched with cp.async one piece ahead of the dependency chain
-// x_ib -> update -> x_ib-1 ..., which then only touches shared memory.
-template <typename T, int RC>
-__global__ void __launch_bounds__(256) sky_tri_diag_stream_kernel(const T* __restrict__ data, i64 dstart, i64 ld, int rK, int upper,
-                                                                  const T* __restrict__ W, T* __restrict__ Bk, i64 ldb, int nrhs, int HC) {
-    extern __shared__ __align__(16) unsigned char tri_smem[];
-    const int PRS = (rK + 1) & ~1;
-    T* bs = reinterpret_cast<T*>(tri_smem);  // bs[q * rK + i]
-    T* ws = bs + (size_t)RC * PRS;           // two inverted sub-blocks
-    T* us = ws + 2 * 1024;                   // kTriBufs pieces of HC columns x PRS rows
-    const int tid = threadIdx.x;
-    const int q0 = blockIdx.x * RC;
-    const int nq = min(RC, nrhs - q0);
-    const int nsb = (rK + 31) / 32;
-    const int npp = 32 / HC;
-    const int npieces = nsb * npp;
-    const T* __restrict__ A = data + dstart;
-
-    auto load_piece = [&](int pc) {
-        if (pc >= npieces) return;
-        const int s = pc / npp, hp = pc % npp;
-        const int ib = upper ? nsb - 1 - s : s;
-        const int i0 = ib * 32, nb = min(32, rK - i0);
-        const int c0 = i0 + hp * HC, nc = max(0, min(HC, i0 + nb - c0));
-        const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
-        T* u = us + (size_t)(pc % kTriBufs) * HC * PRS;
-        for (int c = 0; c < nc; ++c) {
-            const T* __restrict__ src = A + (i64)(c0 + c) * ld;
-            for (int r = rlo + tid; r < rhi; r += 256) cp_async_elem(u + c * PRS + (r - rlo), src + r);
-        }
-        if (hp == 0) {  // first piece of a sub-step brings its inverted diagonal sub-block along
-            T* w = ws + (s & 1) * 1024;
-            const T* __restrict__ wg = W + (i64)ib * 1024;
-            for (int idx = tid; idx < 1024; idx += 256) cp_async_elem(w + idx, wg + idx);
-        }
-    };
-
-    for (int pc = 0; pc < kTriBufs - 1; ++pc) {
-        load_piece(pc);
-        cp_async_commit();
-    }
-    for (int idx = tid; idx < RC * rK; idx += 256) {
-        const int q = idx / rK, i = idx % rK;
-        bs[q * PRS + i] = q < nq ? Bk[(i64)(q0 + q) * ldb + i] : T(0);
-    }
-    const int li = tid & 31, lq = tid >> 5;
-    for (int pc = 0; pc < npieces; ++pc) {
-        load_piece(pc + kTriBufs - 1);
-        cp_async_commit();
-        cp_async_wait<kTriBufs - 1>();
-        __syncthreads();
-        const int s = pc / npp, hp = pc % npp;
-        const int ib = upper ? nsb - 1 - s : s;
-        const int i0 = ib * 32, nb = min(32, rK - i0);
-        if (hp == 0) {
-            // x_ib = inv(T_ib,ib) * b_ib   (entries of the inverse beyond nb are zero)
-            const T* w = ws + (s & 1) * 1024;
-            T xv = T(0);
-            if (lq < RC) {
-#pragma unroll 8
-                for (int j = 0; j < nb; ++j) xv = fma(w[li + 32 * j], bs[lq * PRS + i0 + j], xv);
-            }
-            __syncthreads();
-            if (lq < RC && li < nb) {
-                bs[lq * PRS + i0 + li] = xv;
-                if (lq < nq) Bk[(i64)(q0 + lq) * ldb + i0 + li] = xv;
-            }
-            __syncthreads();
-        }
-        const int c0 = i0 + hp * HC, nc = max(0, min(HC, i0 + nb - c0));
-        const int rlo = upper ? 0 : i0 + nb, rhi = upper ? i0 : rK;
-        const T* u = us + (size_t)(pc % kTriBufs) * HC * PRS;
-        for (int row = rlo + tid; row < rhi; row += 256) {
-            T acc[RC];
-#pragma unroll
-            for (int qq = 0; qq < RC; ++qq) acc[qq] = T(0);
-            for (int c = 0; c < nc; ++c) {
-                const T v = u[c * PRS + (row - rlo)];
-#pragma unroll
-                for (int qq = 0; qq < RC; ++qq) acc[qq] = fma(v, bs[qq * PRS + c0 + c], acc[qq]);
-            }
-#pragma unroll
-            for (int qq = 0; qq < RC; ++qq) bs[qq * PRS + row] -= acc[qq];
-        }
-        __syncthreads();
-    }
-}
-
 // pulls a byte range into L2 ahead of the sequential chain (the next block column's panel): one
 // 4-byte ld.global.cg per 32-byte sector (prefetch.global.L2 hints were measured to be ineffective)
 __global__ void __launch_bounds__(256) sky_l2_prefetch_kernel(const char* __restrict__ p, size_t bytes, unsigned* sink) {
@@ -1187,26 +1087,12 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     while (RC > 1 && (size_t)RC * maxr * sizeof(T) > budget) RC /= 2;
     if ((size_t)RC * maxr * sizeof(T) > budget) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "diagonal block of %lld rows does not fit the shared-memory solve", (long long)maxr);
     while (RC > 1 && nrhs < RC) RC /= 2;
-    // streaming variant: b_K + two inverted sub-blocks + two pieces of HC columns in shared memory
-    const size_t prs = (size_t)((maxr + 1) & ~i64(1));
-    int HC = 0;
-    // "trsm.kernel" = 1 selects the streaming variant (measured slower on cfg5: 148 vs 91 us per block step)
-    if (bbm_opt(h, "trsm.kernel", 0) == 1)
-        for (int hc = 8; hc >= 2 && !HC; hc /= 2)  // 32/HC >= kTriBufs-1 keeps at most one later sub-block in flight
-            if (((size_t)RC * prs + 2048 + kTriBufs * (size_t)hc * prs) * sizeof(T) <= budget) HC = hc;
-    const size_t smem_max = HC ? ((size_t)RC * prs + 2048 + kTriBufs * (size_t)HC * prs) * sizeof(T) : (size_t)RC * maxr * sizeof(T);
+    const size_t smem_max = (size_t)RC * maxr * sizeof(T);
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max); };
-    if (HC) {
-        if (RC == 8) e = set_attr(sky_tri_diag_stream_kernel<T, 8>);
-        else if (RC == 4) e = set_attr(sky_tri_diag_stream_kernel<T, 4>);
-        else if (RC == 2) e = set_attr(sky_tri_diag_stream_kernel<T, 2>);
-        else e = set_attr(sky_tri_diag_stream_kernel<T, 1>);
-    } else {
-        if (RC == 8) e = set_attr(sky_tri_diag_kernel<T, 8>);
-        else if (RC == 4) e = set_attr(sky_tri_diag_kernel<T, 4>);
-        else if (RC == 2) e = set_attr(sky_tri_diag_kernel<T, 2>);
-        else e = set_attr(sky_tri_diag_kernel<T, 1>);
-    }
+    if (RC == 8) e = set_attr(sky_tri_diag_kernel<T, 8>);
+    else if (RC == 4) e = set_attr(sky_tri_diag_kernel<T, 4>);
+    else if (RC == 2) e = set_attr(sky_tri_diag_kernel<T, 2>);
+    else e = set_attr(sky_tri_diag_kernel<T, 1>);
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const unsigned gq = (unsigned)((nrhs + RC - 1) / RC);
     // L2 prefetch of the next block column's panel on a side stream, throttled to one step ahead
@@ -1237,14 +1123,7 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
         const i64 dstart = sky_start(d, K, K);
         const T* Wk = W + t.sub_ptr[K] * 1024;
         T* Bk = d_B + d->R[K];
-        if (HC) {
-            const size_t p2 = (size_t)((rK + 1) & ~1);
-            const size_t smem = ((size_t)RC * p2 + 2048 + kTriBufs * (size_t)HC * p2) * sizeof(T);
-            if (RC == 8) sky_tri_diag_stream_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
-            else if (RC == 4) sky_tri_diag_stream_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
-            else if (RC == 2) sky_tri_diag_stream_kernel<T, 2><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
-            else sky_tri_diag_stream_kernel<T, 1><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs, HC);
-        } else {
+        {
             const size_t smem = (size_t)RC * rK * sizeof(T);
             if (RC == 8) sky_tri_diag_kernel<T, 8><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
             else if (RC == 4) sky_tri_diag_kernel<T, 4><<<gq, 256, smem, h->stream>>>(d_data, dstart, d->S[K], rK, upper, Wk, Bk, ldb, (int)nrhs);
