@@ -1324,6 +1324,13 @@ int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_
 
 }  // namespace
 
+bool bbm_bbb_desc_view(bbm_bbb_desc_t d, BbbDescView* out) {
+    if (!desc_valid(d) || !out) return false;
+    *out = BbbDescView{d->h, d->Nr, d->Nc, d->l, d->u, d->lam, d->mu, d->m, d->n, d->P, d->maxr,
+                       d->r.data(), d->c.data(), d->dR, d->dC};
+    return true;
+}
+
 extern "C" {
 
 int32_t bbm_bbb_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, int64_t l,

@@ -102,3 +102,12 @@ inline i64 bbm_opt(bbm_handle_t h, const char* key, i64 dflt) {
 
 // grow-only device workspace
 int32_t bbm_ws_reserve(bbm_handle_t h, void** ws, size_t* have, size_t need);
+
+// read-only view of a BandedBlockBandedMatrix descriptor for the other translation units
+struct BbbDescView {
+    bbm_handle_t h;
+    i64 Nr, Nc, l, u, lam, mu, m, n, P, maxr;
+    const i64 *r, *c;    // host block sizes
+    const i64 *dR, *dC;  // device prefix sums (Nr+1, Nc+1)
+};
+bool bbm_bbb_desc_view(bbm_bbb_desc_t d, BbbDescView* out);

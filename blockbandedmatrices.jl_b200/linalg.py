@@ -255,8 +255,8 @@ def _sky_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
 
 def ldiv_(T, B):
     """``ldiv!(UpperTriangular(A), B)`` etc.: B <- T^-1 B in place on the device, returns B."""
-    if not isinstance(T, _Triangular) or not isinstance(T.parent, BlockSkylineMatrix):
-        raise TypeError("ldiv! takes Upper/LowerTriangular wrappers of a BlockSkylineMatrix")
+    if not isinstance(T, _Triangular) or not isinstance(T.parent, (BlockSkylineMatrix, BandedBlockBandedMatrix)):
+        raise TypeError("ldiv! takes Upper/LowerTriangular wrappers of a BlockSkylineMatrix or BandedBlockBandedMatrix")
     A = T.parent
     h = _require_device(A)
     if not isinstance(B, DeviceArray):
@@ -268,7 +268,7 @@ def ldiv_(T, B):
     if dt not in _SUF or np.dtype(B.dtype) != dt:
         raise TypeError("device path takes matching Float32/Float64 operands only")
     suf, _ = _SUF[dt]
-    fn = getattr(h._lib, f"bbm_sky_trsm_{suf}")
+    fn = getattr(h._lib, f"bbm_sky_trsm_{suf}" if isinstance(A, BlockSkylineMatrix) else f"bbm_bbb_trsv_{suf}")
     rc = fn(h.h, A.descriptor(h), ord(T.uplo), 1 if T.unit else 0, C.c_void_p(A.data.ptr), C.c_void_p(B.ptr), _ld(B), bc)
     L.check(rc, h.h, "ldiv!")
     return B

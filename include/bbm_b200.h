@@ -144,6 +144,18 @@ int32_t bbm_bbb_matmul_f64(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, b
 int32_t bbm_bbb_matmul_f32(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, float alpha,
                            const float* d_A, const float* d_B, float beta, float* d_C);
 
+/* B <- T^-1 B in place, T = Upper ('U') / LowerTriangular ('L') of a BandedBlockBandedMatrix, unit != 0 for the
+ * Unit variants: `ldiv!(LowerTriangular(A), b)`, `Ldiv(U, b)` of test/test_triblockbanded.jl:80-99 and the
+ * Gauss-Seidel sweep of examples/finitedifference_2d.jl:17-47 (replaces [upstream] block substitution with a
+ * banded tbsv per diagonal block and a gbmv per off-diagonal block).  One thread-block cluster runs a systolic
+ * level schedule with the recent solution values in (distributed) shared memory.  Needs matching square
+ * diagonal blocks and non-negative bandwidths; BBM_ERR_UNSUPPORTED beyond about 24k block rows x small bands.
+ * d_B: m x nrhs, ldb >= m; right-hand sides are solved one after the other.                            */
+int32_t bbm_bbb_trsv_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const double* d_data,
+                         double* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_bbb_trsv_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const float* d_data,
+                         float* d_B, int64_t ldb, int64_t nrhs);
+
 /* Same product with HOST vectors (the reference-facing call when x, y live in Julia Arrays and
  * the matrix is device-resident): copies X host->device, runs the kernel, copies Y back and
  * synchronises.  h_X / h_Y should be pinned (bbm_host_alloc) for full PCIe speed.             */

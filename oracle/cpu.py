@@ -202,6 +202,20 @@ def sky_trsm(rows, l, u, uplo, unit, data, B):
     return B
 
 
+def bbb_trsm(rows, l, u, lam, mu, uplo, unit, data, B):
+    """B <- T^-1 B in place, T = triangular part ('U'/'L', unit or not) of the BandedBlockBandedMatrix."""
+    suf, _ = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    if B.shape[0] != int(r.sum()):
+        raise ValueError("DimensionMismatch")
+    bp, ldb, nrhs = _mat(B, 0)
+    f = getattr(lib(), f"oracle_bbb_trsm_{suf}")
+    rc = f(i64(len(r)), rp, i64(l), i64(u), i64(lam), i64(mu), C.c_int(1 if uplo.upper() == "U" else 0),
+           C.c_int(1 if unit else 0), data.ctypes.data_as(_p), bp, i64(ldb), i64(nrhs))
+    _check(rc, "bbb_trsm")
+    return B
+
+
 def sky_numentries(rows, cols, l, u) -> int:
     r, rp = _ia(rows)
     c, cp = _ia(cols)

@@ -211,6 +211,99 @@ def test_bbb_triangular_mul(handle, uplo, unit, dtype, kernel):
         handle.set_option("bbb.kernel", 0)
 
 
+def _well_conditioned_tri(rng, rows, lu, lm, dtype):
+    """random band storage whose triangles are comfortably invertible: small off-diagonal, diagonal ~ 2"""
+    data = random_bbb(rng, rows, rows, *lu, *lm, dtype)
+    lam, mu = lm
+    w = lam + mu + 1
+    data *= dtype(0.5 / (F.bbb_nnz_per_row_max(*lu, *lm) + 1))
+    data[lu[1] * w + mu, :] = (2.0 + rng.random(data.shape[1])).astype(dtype)
+    return data
+
+
+TRI_STRUCTURES = [
+    (list(range(1, 11)), (1, 1), (1, 1)),        # test/test_triblockbanded.jl:80-99
+    ([40] * 9, (2, 1), (2, 3)),
+    ([300, 17, 64], (1, 1), (1, 1)),
+    ([5, 0, 3, 7, 1, 1, 12], (3, 2), (0, 2)),    # empty block, lam = 0
+    ([6] * 700, (1, 2), (1, 1)),                 # more block rows than one CTA of the cluster owns
+    ([33] * 4, (0, 0), (3, 3)),                  # block diagonal
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
+def test_bbb_triangular_ldiv(handle, uplo, unit, dtype):
+    """test/test_triblockbanded.jl:80-99: U \\ b for Upper/UnitUpper/Lower/UnitLower triangular
+    BandedBlockBandedMatrix against the block-substitution restatement and a dense solve; the triangle
+    that must not be read (and the diagonal of the unit variants) is NaN."""
+    for rows, lu, lm in TRI_STRUCTURES:
+        rng = np.random.default_rng(41)
+        data = _well_conditioned_tri(rng, rows, lu, lm, dtype)
+        A = B.BandedBlockBandedMatrix(data, rows, rows, lu, lm)
+        m = sum(rows)
+        pois = data.copy(order="F")
+        for rho, gi, gj in A._slot_map():
+            sel = (gi > gj) if uplo == "U" else (gi < gj)
+            if unit:
+                sel = sel | (gi == gj)
+            pois[rho, gj[sel]] = np.nan
+        Ad = B.BandedBlockBandedMatrix(pois, rows, rows, lu, lm).to_device(handle)
+        T = {"U": (B.UnitUpperTriangular if unit else B.UpperTriangular),
+             "L": (B.UnitLowerTriangular if unit else B.LowerTriangular)}[uplo](Ad)
+        b = rng.standard_normal(m).astype(dtype)
+        db = handle.to_device(b)
+        B.ldiv_(T, db)
+        got = db.to_host()
+        ref = b.copy()
+        O.bbb_trsm(rows, *lu, *lm, uplo, unit, data, ref)
+        assert not np.isnan(got).any()
+        nnz = F.bbb_nnz_per_row_max(*lu, *lm) + 1
+        assert relerr(got, ref) <= tol(dtype, nnz)
+        if m <= 1200:
+            Dn = A.to_dense().astype(np.float64)
+            Tm = np.triu(Dn) if uplo == "U" else np.tril(Dn)
+            if unit:
+                np.fill_diagonal(Tm, 1.0)
+            assert relerr(got, np.linalg.solve(Tm, b.astype(np.float64))) <= tol(dtype, nnz)
+        # several right-hand sides with a padded leading dimension; T * (T \ B) == B on the GPU
+        Bm = np.asfortranarray(rng.standard_normal((m, 3)).astype(dtype))
+        dB = handle.to_device(Bm)
+        X = B.ldiv(T, dB)
+        Xh = X.to_host()
+        for q in range(3):
+            refq = Bm[:, q].copy()
+            O.bbb_trsm(rows, *lu, *lm, uplo, unit, data, refq)
+            assert relerr(Xh[:, q], refq) <= tol(dtype, nnz)
+            back = (T @ handle.to_device(np.ascontiguousarray(Xh[:, q]))).to_host()
+            assert relerr(back, Bm[:, q]) <= 4 * tol(dtype, nnz)
+        assert relerr(dB.to_host(), Bm) == 0.0      # ldiv (not ldiv!) leaves B alone
+
+
+def test_bbb_triangular_ldiv_gauss_seidel_sweep(handle):
+    """examples/finitedifference_2d.jl:17-47 flavour: (D+L) \\ b on the 2-D Laplacian, 200 x 200 blocks."""
+    n = 200
+    A = B.BandedBlockBandedMatrix.finitedifference_2d(n)
+    rng = np.random.default_rng(43)
+    b = rng.standard_normal(n * n)
+    Ad = A.to_device(handle)
+    for uplo, T in (("L", B.LowerTriangular(Ad)), ("U", B.UpperTriangular(Ad))):
+        db = handle.to_device(b)
+        B.ldiv_(T, db)
+        ref = b.copy()
+        O.bbb_trsm([n] * n, 1, 1, 1, 1, uplo, False, A.data, ref)
+        assert relerr(db.to_host(), ref) <= tol(np.float64, 9)
+
+
+def test_bbb_triangular_ldiv_errors(handle):
+    A = B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4], [4, 3], (1, 1), (1, 1)).to_device(handle)
+    with pytest.raises(B.BBMError):       # no matching diagonal blocks: the reference falls back to a generic solve
+        B.ldiv_(B.UpperTriangular(A), handle.empty(7, np.float64))
+    A2 = B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4], [3, 4], (1, 1), (1, 1)).to_device(handle)
+    with pytest.raises(B.BBMError):
+        B.ldiv_(B.LowerTriangular(A2), handle.empty(9, np.float64))
+
+
 def test_bbb_triangular_mul_needs_matching_blocks(handle):
     A = B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4], [4, 3], (1, 1), (1, 1)).to_device(handle)
     with pytest.raises(B.BBMError):

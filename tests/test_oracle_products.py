@@ -170,3 +170,23 @@ def test_oracle_bbb_matmul_vs_dense(case):
     O.bbb_matmul((rows, rows, *luA, *lmA), (rows, rows, *luB, *lmB), (rows, rows, *luC, *lmC), 1.0, adata, bdata, 0.0, c)
     dense = F.bbb_to_dense(adata, rows, rows, *luA, *lmA).astype(np.longdouble) @ F.bbb_to_dense(bdata, rows, rows, *luB, *lmB).astype(np.longdouble)
     assert relerr(F.bbb_to_dense(c, rows, rows, *luC, *lmC), dense) <= tol(np.float64, 16)
+
+
+@pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
+def test_oracle_bbb_trsm_vs_dense(uplo, unit):
+    """block substitution on the band storage == dense triangular solve (test/test_triblockbanded.jl:80-99)"""
+    for rows, lu, lm in [(list(range(1, 11)), (1, 1), (1, 1)), ([7, 0, 3, 12, 1], (2, 1), (2, 3)), ([20] * 6, (0, 0), (1, 2))]:
+        rng = np.random.default_rng(5)
+        shape = F.bbb_data_shape(rows, *lu, *lm)
+        data = np.asfortranarray(rng.standard_normal(shape) * 0.05)
+        w = lm[0] + lm[1] + 1
+        data[lu[1] * w + lm[1], :] = 2.0 + rng.random(shape[1])
+        Dn = F.bbb_to_dense(data, rows, rows, *lu, *lm)
+        Tm = np.triu(Dn) if uplo == "U" else np.tril(Dn)
+        if unit:
+            np.fill_diagonal(Tm, 1.0)
+        Bm = np.asfortranarray(rng.standard_normal((sum(rows), 3)))
+        ref = np.linalg.solve(Tm, Bm)
+        got = Bm.copy(order="F")
+        O.bbb_trsm(rows, *lu, *lm, uplo, unit, data, got)
+        assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
