@@ -290,6 +290,40 @@ def run_cfg5(torch, B, h, stream, reps, oracle, nblk=1024, bs=512, nrhs=64, peak
     return out
 
 
+def run_bbb_tri(torch, B, h, stream, reps, oracle, n=4096):
+    """Gauss-Seidel sweep of examples/finitedifference_2d.jl: (D+L) \\ b and (D+U) \\ b on the n^2 Laplacian."""
+    A = B.BandedBlockBandedMatrix.finitedifference_2d(n)
+    hdata = A.data
+    gen = torch.Generator(device="cuda").manual_seed(1007)
+    a_t = torch.from_numpy(np.ascontiguousarray(hdata.T)).cuda()     # (n*n, 9) row-major == 9 x n*n column-major
+    Ad = B.BandedBlockBandedMatrix(wrap(B, h, a_t), [n] * n, [n] * n, (1, 1), (1, 1))
+    b0 = torch.randn(n * n, generator=gen, device="cuda", dtype=torch.float64)
+    b_t = b0.clone()
+    db = wrap(B, h, b_t)
+    out = {"config": f"bbbtri: Lower/UpperTriangular of the 2-D Laplacian BBB, {n} blocks of {n}, Float64 ldiv!", "steps": 3 * n - 2,
+           "tolerance": 64 * EPS[8] * 9}
+    for uplo, T in (("L", B.LowerTriangular(Ad)), ("U", B.UpperTriangular(Ad))):
+        def step():
+            b_t.copy_(b0)
+            B.ldiv_(T, db)
+        with torch.cuda.stream(stream):
+            cavg, _ = time_gpu(torch, stream, lambda: b_t.copy_(b0), 5, warm=1)
+        avg, best = time_gpu(torch, stream, step, reps, warm=1)
+        out[f"ms_avg_{uplo}"] = avg - cavg
+        out[f"us_per_level_{uplo}"] = (avg - cavg) * 1e3 / (3 * n - 2)
+        h.synchronize()
+        if oracle:
+            from oracle import cpu as O
+            ref = b0.cpu().numpy().copy()
+            t0 = time.perf_counter()
+            O.bbb_trsm([n] * n, 1, 1, 1, 1, uplo, False, hdata, ref)
+            out[f"cpu_seconds_{uplo}"] = time.perf_counter() - t0
+            out[f"rel_err_{uplo}"] = relerr(b_t.cpu().numpy(), ref)
+    if oracle:
+        out["parity_ok"] = bool(max(out["rel_err_L"], out["rel_err_U"]) <= out["tolerance"])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,4,5")
@@ -324,6 +358,8 @@ def main():
         print(json.dumps(run_cfg4(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
     if "bbbmm" in want:
         print(json.dumps(run_bbb_mm(torch, B, h, stream, args.reps, oracle)), flush=True)
+    if "bbbtri" in want:
+        print(json.dumps(run_bbb_tri(torch, B, h, stream, max(2, args.reps // 3), oracle)), flush=True)
     if "4mv" in want:
         for q in (1, 8):
             print(json.dumps(run_sky_mv(torch, B, h, stream, args.reps, oracle, nrhs=q)), flush=True)

@@ -231,12 +231,23 @@ TRI_STRUCTURES = [
 ]
 
 
+@pytest.mark.parametrize("kernel,pf", [(0, 4), (0, 8), (1, 6), (1, 2), (2, 0)], ids=["wave4", "wave8", "staged6", "staged2", "direct"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
-def test_bbb_triangular_ldiv(handle, uplo, unit, dtype):
+def test_bbb_triangular_ldiv(handle, uplo, unit, dtype, kernel, pf):
     """test/test_triblockbanded.jl:80-99: U \\ b for Upper/UnitUpper/Lower/UnitLower triangular
     BandedBlockBandedMatrix against the block-substitution restatement and a dense solve; the triangle
     that must not be read (and the diagonal of the unit variants) is NaN."""
+    handle.set_option("tri.pf", pf)
+    handle.set_option("tri.kernel", kernel)
+    try:
+        _check_triangular_ldiv(handle, uplo, unit, dtype)
+    finally:
+        handle.set_option("tri.pf", 4)
+        handle.set_option("tri.kernel", 0)
+
+
+def _check_triangular_ldiv(handle, uplo, unit, dtype):
     for rows, lu, lm in TRI_STRUCTURES:
         rng = np.random.default_rng(41)
         data = _well_conditioned_tri(rng, rows, lu, lm, dtype)
@@ -300,7 +311,7 @@ def test_bbb_triangular_ldiv_errors(handle):
     with pytest.raises(B.BBMError):       # no matching diagonal blocks: the reference falls back to a generic solve
         B.ldiv_(B.UpperTriangular(A), handle.empty(7, np.float64))
     A2 = B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4], [3, 4], (1, 1), (1, 1)).to_device(handle)
-    with pytest.raises(B.BBMError):
+    with pytest.raises(B.DimensionMismatch):
         B.ldiv_(B.LowerTriangular(A2), handle.empty(9, np.float64))
 
 
