@@ -245,47 +245,49 @@ cudaError_t launch_staged(const TriSolveParams<T>& p, size_t smem, cudaStream_t 
 // In the staged kernel a warp's 32 threads own 32 different block rows, so each of its prefetch copies touches
 // 32 different cache lines: ~6 x 512 line requests per SM and step, which is what bounds it (2 us per step, the
 // L1 tag stage handles about one line per cycle).  Here a pre-pass running on all SMs gathers the right-hand
-// side and every matrix entry the substitution will use into WAVE ORDER -- plane c, position
-// base[s] + Kl - Klmin(s) for the unknown that block row Kl (in solve order) computes at step s -- so that the
-// solve kernel's warps read (and write the solution) with unit stride; a post-pass scatters the solution back.
-//   Klmin(s) = first block row still active at step s = max(0, floor((s - maxr)/delta) + 1)
+// side and every matrix entry the substitution will use into WAVE ORDER -- plane c, position s*Wd + Kl mod Wd
+// for the unknown that block row Kl (in solve order) computes at step s; the block rows active in one step are
+// fewer than Wd consecutive ones, so the positions are unique -- and the solve kernel's warps read their inputs
+// and write the solution with unit stride; a post-pass scatters the solution back.
 //   planes: 0 right-hand side / solution, 1 diagonal entry, 2+(d-1)w+ii off-diagonal block d band row ii,
 //           2+nd*w+t diagonal-block band row ii0+t; entries outside their block are stored as 0.
+// Only maxr/delta block rows are active at a time (a window sliding over the lanes), so consecutive groups of
+// 128 lanes are dealt round-robin to the 8 CTAs: all 8 SMs stay busy instead of the window's 4.
 template <typename T>
 struct TriWaveParams {
     const T* data;
     T* x;
     T* packed;         // [nc][total]
-    const i64* base;   // [iters+1] wave offsets
     const i64* R;
-    i64 N, maxr, iters, total;
+    i64 total, Wd;     // plane stride = iters*Wd
+    int N, maxr, iters;
     int l, u, lam, mu, w, P;
     int upper, unit, passes, D, nc, relaxed, what;
 };
 
-__device__ __forceinline__ i64 tri_klmin(i64 s, i64 maxr, int delta) { return s < maxr ? 0 : (s - maxr) / delta + 1; }
+constexpr int kTriGroup = 128;                      // lanes dealt to one CTA at a time
+constexpr int kTriGroups = kTriThreads / kTriGroup;
 
 // what: bit 0 = right-hand side plane, bit 1 = matrix planes
 template <typename T>
 __global__ void __launch_bounds__(256) bbb_tri_pack_kernel(const TriWaveParams<T> p) {
     const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= p.N * p.maxr) return;
-    const i64 Kl = idx / p.maxr, kk = idx % p.maxr;
-    const i64 K = p.upper ? p.N - 1 - Kl : Kl;
-    const i64 k = p.upper ? p.maxr - 1 - kk : kk;
+    if (idx >= (i64)p.N * p.maxr) return;
+    const int Kl = (int)(idx / p.maxr), kk = (int)(idx % p.maxr);
+    const int K = p.upper ? p.N - 1 - Kl : Kl;
+    const int k = p.upper ? p.maxr - 1 - kk : kk;
     const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
     if (k >= rK) return;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
     const int nd = p.upper ? p.u : p.l;
-    const i64 s = kk + (i64)delta * Kl;
-    T* out = p.packed + p.base[s] + Kl - tri_klmin(s, p.maxr, delta);
+    T* out = p.packed + (i64)(kk + delta * Kl) * p.Wd + Kl % p.Wd;
     if (p.what & 1) out[0] = p.x[r0 + k];
     if (!(p.what & 2)) return;
     const int w = p.w, mu = p.mu;
     const T* dcol = p.data + (i64)p.u * w;
     out[p.total] = p.unit ? T(1) : dcol[mu + (i64)p.P * (r0 + k)];
     for (int d = 1; d <= nd; ++d) {
-        const i64 J = p.upper ? K + d : K - d;
+        const int J = p.upper ? K + d : K - d;
         const bool have = J >= 0 && J < p.N;
         const i64 c0 = have ? p.R[J] : 0, rJ = have ? p.R[J + 1] - c0 : 0;
         const T* slab = p.data + (i64)(p.upper ? p.u - d : p.u + d) * w;
@@ -304,107 +306,117 @@ __global__ void __launch_bounds__(256) bbb_tri_pack_kernel(const TriWaveParams<T
 template <typename T>
 __global__ void __launch_bounds__(256) bbb_tri_unpack_kernel(const TriWaveParams<T> p) {
     const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= p.N * p.maxr) return;
-    const i64 Kl = idx / p.maxr, kk = idx % p.maxr;
-    const i64 K = p.upper ? p.N - 1 - Kl : Kl;
-    const i64 k = p.upper ? p.maxr - 1 - kk : kk;
+    if (idx >= (i64)p.N * p.maxr) return;
+    const int Kl = (int)(idx / p.maxr), kk = (int)(idx % p.maxr);
+    const int K = p.upper ? p.N - 1 - Kl : Kl;
+    const int k = p.upper ? p.maxr - 1 - kk : kk;
     const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
     if (k >= rK) return;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
-    const i64 s = kk + (i64)delta * Kl;
-    p.x[r0 + k] = p.packed[p.base[s] + Kl - tri_klmin(s, p.maxr, delta)];
+    p.x[r0 + k] = p.packed[(i64)(kk + delta * Kl) * p.Wd + Kl % p.Wd];
 }
 
-// shared memory: pos [passes][PF][kTriThreads] i64 | ring [passes][D][kTriThreads] | coef [passes][PF][NC][kTriThreads]
-//                | rn [passes][kTriThreads+nd] int (block sizes of block rows Kl-nd .. Kl)
+// shared memory: ring [passes][D][kTriThreads] | coef [passes][PF][NC][kTriThreads]
+//                | rn [passes][kTriGroups][kTriGroup+nd] int: block sizes of block rows Kl-nd..Kl of each lane group
+//                | klm [passes][kTriThreads] int: Kl mod Wd
 template <typename T, int PF>
 __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) bbb_trisolve_wave_kernel(const TriWaveParams<T> p) {
+    static_assert((PF & (PF - 1)) == 0, "PF must be a power of two");
     extern __shared__ __align__(16) unsigned char tri_ring_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const int rank = (int)cluster.block_rank();
-    const int g = rank * kTriThreads + tid;
-    const int D = p.D, w = p.w, NC = p.nc, mu = p.mu;
+    const int grp = tid / kTriGroup, lid = tid % kTriGroup;
+    const int g = (grp * kTriCtas + rank) * kTriGroup + lid;   // lane in solve order (block row g + kTriLanes*pass)
+    const int D = p.D, w = p.w, NC = p.nc, mu = p.mu, maxr = p.maxr, iters = p.iters;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
     const int nd = p.upper ? p.u : p.l;
     const int ndiag = p.upper ? p.mu : p.lam;
     const int ii0 = p.upper ? 0 : p.mu + 1;
-    const int mw = kTriThreads + nd;
-    i64* posr = reinterpret_cast<i64*>(tri_ring_smem);
-    T* ring = reinterpret_cast<T*>(posr + (size_t)p.passes * PF * kTriThreads);
+    const int gw = kTriGroup + nd;
+    T* ring = reinterpret_cast<T*>(tri_ring_smem);
     T* coef = ring + (size_t)p.passes * D * kTriThreads;
     int* rn = reinterpret_cast<int*>(coef + (size_t)p.passes * PF * NC * kTriThreads);
+    int* klm = rn + p.passes * kTriGroups * gw;
 
     for (int pass = 0; pass < p.passes; ++pass) {
-        for (int t = tid; t < mw; t += kTriThreads) {
-            const i64 Kl = (i64)rank * kTriThreads + (i64)kTriLanes * pass + t - nd;
-            i64 sz = 0;
+        for (int t = tid; t < kTriGroups * gw; t += kTriThreads) {
+            const int gq = t / gw, o = t % gw;
+            const i64 Kl = (i64)(gq * kTriCtas + rank) * kTriGroup + o - nd + (i64)kTriLanes * pass;
+            int sz = 0;
             if (Kl >= 0 && Kl < p.N) {
                 const i64 K = p.upper ? p.N - 1 - Kl : Kl;
-                sz = p.R[K + 1] - p.R[K];
+                sz = (int)(p.R[K + 1] - p.R[K]);
             }
-            rn[pass * mw + t] = (int)sz;
+            rn[pass * kTriGroups * gw + t] = sz;
         }
+        klm[pass * kTriThreads + tid] = (int)(((i64)g + (i64)kTriLanes * pass) % p.Wd);
         for (int t = tid; t < D * kTriThreads; t += kTriThreads) ring[(size_t)pass * D * kTriThreads + t] = T(0);
     }
     cluster.sync();  // every ring is zeroed before a neighbour CTA may read it
 
-    auto issue = [&](i64 st, i64 bs) {  // bs = base[st]
-        if (st < p.iters) {
-            const i64 kmin = tri_klmin(st, p.maxr, delta);
+    const int* rnme = rn + grp * gw + lid + nd;   // + pass*kTriGroups*gw; [-d] = block row Kl-d
+    // ring of the lane d block rows back (it may live in another CTA: distributed shared memory)
+    auto ring_of = [&](int pass, int d) -> const T* {
+        int gj = g - d, pj = pass;
+        if (gj < 0) { gj += kTriLanes; pj -= 1; }
+        if (pj < 0) return ring;  // no such block row (never dereferenced: its size is 0)
+        const int G = gj / kTriGroup;
+        return cluster.map_shared_rank(ring, G % kTriCtas) + (size_t)pj * D * kTriThreads + (G / kTriCtas) * kTriGroup + gj % kTriGroup;
+    };
+    const T* const rem1 = ring_of(0, 1);
+
+    auto issue = [&](int st) {
+        if (st < iters) {
             for (int pass = 0; pass < p.passes; ++pass) {
-                const i64 Kl = (i64)g + (i64)kTriLanes * pass;
-                const i64 kk = st - (i64)delta * Kl;
-                if (kk < 0 || kk >= p.maxr) continue;
-                const int rK = rn[pass * mw + tid + nd];
-                const i64 k = p.upper ? p.maxr - 1 - kk : kk;
-                if (k >= rK) continue;
-                const i64 pos = bs + Kl - kmin;
-                const int slot = pass * PF + (int)(st % PF);
-                posr[(size_t)slot * kTriThreads + tid] = pos;
-                T* cb = coef + (size_t)slot * NC * kTriThreads + tid;
-                const T* src = p.packed + pos;
-                for (int c = 0; c < NC; ++c) tri_cp_async(cb + (size_t)c * kTriThreads, src + (i64)c * p.total);
+                const int kk = st - delta * (g + kTriLanes * pass);
+                if ((unsigned)kk >= (unsigned)maxr) continue;
+                const int k = p.upper ? maxr - 1 - kk : kk;
+                if (k >= rnme[pass * kTriGroups * gw]) continue;
+                const T* src = p.packed + ((i64)st * p.Wd + klm[pass * kTriThreads + tid]);
+                T* cb = coef + (size_t)((pass * PF + (st & (PF - 1))) * NC) * kTriThreads + tid;
+                tri_cp_async(cb, src);
+                if (!p.unit) tri_cp_async(cb + kTriThreads, src + p.total);
+                for (int c = 2; c < NC; ++c) tri_cp_async(cb + (size_t)c * kTriThreads, src + (i64)c * p.total);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    for (int t = 0; t < PF - 1; ++t) issue(t, t < p.iters ? p.base[t] : 0);
-    i64 bnext = (PF - 1 < p.iters) ? p.base[PF - 1] : 0;  // offset of the step issued next, loaded one step early
-    for (i64 s = 0; s < p.iters; ++s) {
-        const i64 bcur = bnext;
-        if (s + PF < p.iters) bnext = p.base[s + PF];
-        issue(s + PF - 1, bcur);
+    for (int t = 0; t < PF - 1; ++t) issue(t);
+    for (int s = 0; s < iters; ++s) {
+        issue(s + PF - 1);
         asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
         for (int pass = 0; pass < p.passes; ++pass) {
-            const i64 Kl = (i64)g + (i64)kTriLanes * pass;
-            const i64 kk = s - (i64)delta * Kl;
-            if (kk < 0 || kk >= p.maxr) continue;
-            const int rK = rn[pass * mw + tid + nd];
-            const int k = (int)(p.upper ? p.maxr - 1 - kk : kk);
-            if (k >= rK) continue;
-            const int slot = pass * PF + (int)(s % PF);
-            const T* cb = coef + (size_t)slot * NC * kTriThreads + tid;
+            const int kk = s - delta * (g + kTriLanes * pass);
+            if ((unsigned)kk >= (unsigned)maxr) continue;
+            const int k = p.upper ? maxr - 1 - kk : kk;
+            const int* rnp = rnme + pass * kTriGroups * gw;
+            if (k >= rnp[0]) continue;
+            const T* cb = coef + (size_t)((pass * PF + (s & (PF - 1))) * NC) * kTriThreads + tid;
             T acc = cb[0];
+            const int km = k + mu;
             for (int d = 1; d <= nd; ++d) {
-                if (rn[pass * mw + tid + nd - d] == 0) continue;   // no such block row, or an empty one
-                int gj = g - d, pj = pass;                          // owner of block row Kl-d
-                if (gj < 0) { gj += kTriLanes; pj -= 1; }
-                const T* rem = cluster.map_shared_rank(ring, gj / kTriThreads) + (size_t)pj * D * kTriThreads + (gj % kTriThreads);
+                if (rnp[-d] == 0) continue;   // no such block row, or an empty one
+                const T* rem = (d == 1 && pass == 0) ? rem1 : ring_of(pass, d);
                 const T* cd = cb + (size_t)(2 + (d - 1) * w) * kTriThreads;
                 for (int ii = 0; ii < w; ++ii)   // entries outside the block were packed as zeros
-                    acc = fma(-cd[(size_t)ii * kTriThreads], rem[(size_t)((k + mu - ii) & (D - 1)) * kTriThreads], acc);
+                    acc = fma(-cd[ii * kTriThreads], rem[((km - ii) & (D - 1)) * kTriThreads], acc);
             }
             T* mine = ring + (size_t)pass * D * kTriThreads + tid;
             const T* cd = cb + (size_t)(2 + nd * w) * kTriThreads;
             for (int t = 0; t < ndiag; ++t)
-                acc = fma(-cd[(size_t)t * kTriThreads], mine[(size_t)((k + mu - ii0 - t) & (D - 1)) * kTriThreads], acc);
+                acc = fma(-cd[t * kTriThreads], mine[((km - ii0 - t) & (D - 1)) * kTriThreads], acc);
             const T xk = p.unit ? acc : acc / cb[kTriThreads];
-            mine[(size_t)(k & (D - 1)) * kTriThreads] = xk;
-            p.packed[posr[(size_t)slot * kTriThreads + tid]] = xk;
+            mine[(k & (D - 1)) * kTriThreads] = xk;
+            p.packed[(i64)s * p.Wd + klm[pass * kTriThreads + tid]] = xk;
         }
         if (p.relaxed) {
+            // Step boundary without the cluster-scope release: that fence (MEMBAR.ALL.GPU + ERRBAR in SASS) also
+            // waits for the global store of x and for every prefetch copy still in flight.  Only the shared-memory
+            // ring has to be ordered: a CTA-scope fence completes this thread's ring store in its own SM's shared
+            // memory -- the single copy that local and DSMEM readers both access -- before the arrive; readers
+            // pass the wait (acquire) only after every thread of the cluster arrived.
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -412,7 +424,115 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
             cluster.sync();
         }
     }
-    cluster.sync();
+    cluster.sync();  // nothing may leave while a neighbour could still read its ring
+}
+
+// Lean instantiation of the wave kernel for at most kTriLanes block rows with compile-time block bandwidth ND
+// (towards the already solved side) and sub-block band width W: everything a step needs besides the neighbours'
+// newest values -- prefetch issue, coefficient loads into registers, the reciprocal of the diagonal entry -- is
+// done between the barrier's arrive and wait, so the dependent chain of a step is: barrier release -> ring loads
+// (shared / distributed shared memory) -> ND*W + W-1 FMAs -> quotient correction -> ring store -> arrive.
+template <typename T, int PF, int ND, int W>
+__global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) bbb_trisolve_lean_kernel(const TriWaveParams<T> p) {
+    static_assert((PF & (PF - 1)) == 0, "PF must be a power of two");
+    extern __shared__ __align__(16) unsigned char tri_ring_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster.block_rank();
+    const int g = ((tid / kTriGroup) * kTriCtas + rank) * kTriGroup + tid % kTriGroup;   // block row in solve order
+    const int D = p.D, mu = p.mu, iters = p.iters;
+    const int delta = p.upper ? p.lam + 1 : p.mu + 1;
+    const int ndiag = p.upper ? p.mu : p.lam;
+    const int ii0 = p.upper ? 0 : p.mu + 1;
+    const int NC = 2 + ND * W + ndiag;
+    T* ring = reinterpret_cast<T*>(tri_ring_smem);            // [D][kTriThreads]
+    T* coef = ring + (size_t)D * kTriThreads;                 // [PF][NC][kTriThreads]
+
+    int rK = 0;
+    if (g < p.N) {
+        const i64 K = p.upper ? p.N - 1 - g : g;
+        rK = (int)(p.R[K + 1] - p.R[K]);
+    }
+    for (int t = tid; t < D * kTriThreads; t += kTriThreads) ring[t] = T(0);
+    cluster.sync();  // every ring is zeroed before a neighbour CTA may read it
+
+    // rings of the lanes 1..ND block rows back; a lane without such a neighbour reads its own ring (times zero)
+    const T* rem[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 1; d <= ND; ++d) {
+        const int gj = g - d;
+        const int G = (gj < 0 ? 0 : gj) / kTriGroup;
+        rem[d - 1] = gj < 0 ? ring + tid : cluster.map_shared_rank(ring, G % kTriCtas) + (G / kTriCtas) * kTriGroup + gj % kTriGroup;
+    }
+    T* const mine = ring + tid;
+    // step s works on in-block row k = kbase + ksgn*kr, kr = s - delta*g - kk0, if 0 <= kr < rK
+    const int kk0 = p.upper ? p.maxr - rK : 0;
+    const int kbase = p.upper ? rK - 1 : 0, ksgn = p.upper ? -1 : 1;
+    int kr = -delta * g - kk0;
+    const T* src = p.packed + (g % p.Wd);   // + s*Wd
+
+    auto issue = [&](int st, int krs, const T* sp) {
+        if ((unsigned)krs < (unsigned)rK) {
+            T* cb = coef + (size_t)((st & (PF - 1)) * NC) * kTriThreads + tid;
+            tri_cp_async(cb, sp);
+            if (!p.unit) tri_cp_async(cb + kTriThreads, sp + p.total);
+            for (int c = 2; c < NC; ++c) tri_cp_async(cb + (size_t)c * kTriThreads, sp + (i64)c * p.total);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int t = 0; t < PF - 1; ++t) issue(t, kr + t, src + (i64)t * p.Wd);
+
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    for (int s = 0; s < iters; ++s) {
+        issue(s + PF - 1, kr + PF - 1, src + (i64)(PF - 1) * p.Wd);
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+        const bool active = (unsigned)kr < (unsigned)rK;
+        const int k = kbase + ksgn * kr;
+        T acc = T(0), rinv = T(1), dg = T(1), co[ND > 0 ? ND : 1][W], cg_[W > 1 ? W - 1 : 1];
+        if (active) {
+            const T* cb = coef + (size_t)((s & (PF - 1)) * NC) * kTriThreads + tid;
+            acc = cb[0];
+            if (!p.unit) { dg = cb[kTriThreads]; rinv = T(1) / dg; }
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+#pragma unroll
+                for (int ii = 0; ii < W; ++ii) co[d][ii] = cb[(size_t)(2 + d * W + ii) * kTriThreads];
+#pragma unroll
+            for (int t = 0; t < W - 1; ++t) cg_[t] = t < ndiag ? cb[(size_t)(2 + ND * W + t) * kTriThreads] : T(0);
+        }
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // step s-1 is complete cluster-wide
+        if (active) {
+            const int km = k + mu;
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+#pragma unroll
+                for (int ii = 0; ii < W; ++ii) acc = fma(-co[d][ii], rem[d][((km - ii) & (D - 1)) * kTriThreads], acc);
+#pragma unroll
+            for (int t = 0; t < W - 1; ++t) acc = fma(-cg_[t], mine[((km - ii0 - t) & (D - 1)) * kTriThreads], acc);
+            T xk = acc;
+            if (!p.unit) {   // acc / dg from the reciprocal prepared above (quotient, exact residual, correction)
+                const T q = acc * rinv;
+                xk = fma(fma(-dg, q, acc), rinv, q);
+            }
+            mine[(k & (D - 1)) * kTriThreads] = xk;
+            const_cast<T*>(src)[0] = xk;
+        }
+        // only the shared-memory ring has to be ordered across the step boundary (see the generic kernel)
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        ++kr;
+        src += p.Wd;
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    cluster.sync();  // nothing may leave while a neighbour could still read its ring
+}
+
+template <typename T, int PF, int ND, int W>
+cudaError_t launch_lean(const TriWaveParams<T>& p, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(bbb_trisolve_lean_kernel<T, PF, ND, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bbb_trisolve_lean_kernel<T, PF, ND, W><<<kTriCtas, kTriThreads, smem, stream>>>(p);
+    return cudaGetLastError();
 }
 
 template <typename T, int PF>
@@ -429,52 +549,45 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     const int upper = sp.upper;
     const i64 delta = upper ? v.lam + 1 : v.mu + 1;
     const i64 nd = upper ? v.u : v.l;
+    if (sp.iters + 8 >= (i64)1 << 31 || delta * (sp.N + (i64)kTriLanes) >= (i64)1 << 31) return 1;   // 32-bit step counters
     TriWaveParams<T> p{};
-    p.data = sp.data; p.R = sp.R; p.N = sp.N; p.maxr = sp.maxr; p.iters = sp.iters;
+    p.data = sp.data; p.R = sp.R; p.N = (int)sp.N; p.maxr = (int)sp.maxr; p.iters = (int)sp.iters;
     p.l = sp.l; p.u = sp.u; p.lam = sp.lam; p.mu = sp.mu; p.w = sp.w; p.P = sp.P;
     p.upper = upper; p.unit = sp.unit; p.passes = sp.passes; p.D = sp.D; p.nc = sp.nc; p.relaxed = sp.relaxed;
     const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
-    const size_t fixed = (size_t)p.passes * (kTriThreads * p.D * sizeof(T) + (kTriThreads + nd) * sizeof(int)) + 16;
+    const size_t fixed = (size_t)p.passes * (kTriThreads * p.D * sizeof(T) + (kTriGroups * (kTriGroup + nd) + kTriThreads) * sizeof(int)) + 16;
     int pf = 0;
     const int want_pf = (int)bbm_opt(h, "tri.pf", 4);
-    for (int cand : {8, 6, 4, 2})
-        if (cand <= want_pf && pf == 0 && fixed + (size_t)p.passes * cand * kTriThreads * (p.nc * sizeof(T) + sizeof(i64)) <= budget) pf = cand;
+    for (int cand : {8, 4, 2})
+        if (cand <= want_pf && pf == 0 && fixed + (size_t)p.passes * cand * kTriThreads * p.nc * sizeof(T) <= budget) pf = cand;
     if (pf == 0) return 1;
-    // wave offsets (host, cached in the handle)
-    const size_t tbytes = (size_t)(p.iters + 1) * sizeof(i64);
-    i64 total = 0;
-    {
-        std::vector<i64> base((size_t)p.iters + 1);
-        for (i64 s = 0; s < p.iters; ++s) {
-            base[(size_t)s] = total;
-            const i64 kmax = std::min<i64>(p.N - 1, s / delta);
-            const i64 kmin = s < p.maxr ? 0 : (s - p.maxr) / delta + 1;
-            total += kmax >= kmin ? kmax - kmin + 1 : 0;
-        }
-        base[(size_t)p.iters] = total;
-        const size_t need = (size_t)total * p.nc * sizeof(T);
-        if (need > (size_t)bbm_opt(h, "tri.ws_max_mb", 16384) * 1048576) return 1;
-        if (h->tri_base_key[0] != p.N || h->tri_base_key[1] != p.maxr || h->tri_base_key[2] != delta) {
-            h->tri_base_key[0] = -1;
-            if (bbm_ws_reserve(h, &h->tri_base, &h->tri_base_bytes, tbytes) != BBM_OK) return 1;
-            BBM_CUDA(h, cudaMemcpyAsync(h->tri_base, base.data(), tbytes, cudaMemcpyHostToDevice, h->stream));
-            BBM_CUDA(h, cudaStreamSynchronize(h->stream));  // `base` is pageable and dies with this scope
-            h->tri_base_key[0] = p.N; h->tri_base_key[1] = p.maxr; h->tri_base_key[2] = delta;
-        }
-        if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, need) != BBM_OK) return 1;
-    }
-    p.base = static_cast<const i64*>(h->tri_base);
+    // the block rows active in one step are fewer than Wd consecutive ones
+    i64 Wd = std::min<i64>(sp.N, sp.maxr / delta + 1);
+    Wd = (Wd + 15) / 16 * 16;
+    p.Wd = Wd;
+    p.total = (i64)p.iters * Wd;
+    const size_t need = (size_t)p.total * p.nc * sizeof(T);
+    if (need > (size_t)bbm_opt(h, "tri.ws_max_mb", 16384) * 1048576) return 1;
+    if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, need) != BBM_OK) return 1;
     p.packed = static_cast<T*>(h->ws_w);
-    p.total = total;
-    const size_t smem = fixed + (size_t)p.passes * pf * kTriThreads * (p.nc * sizeof(T) + sizeof(i64));
-    const i64 cells = p.N * p.maxr;
+    const size_t smem = fixed + (size_t)p.passes * pf * kTriThreads * p.nc * sizeof(T);
+    // lean instantiations: one pass, the two common shapes (l or u = 1 with 3 sub-block bands, 2 with 5)
+    int lean = 0;
+    if (p.passes == 1 && bbm_opt(h, "tri.lean", 1) != 0 && (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T) <= budget) {
+        if (nd == 1 && p.w == 3) lean = 13;
+        if (nd == 2 && p.w == 5) lean = 25;
+    }
+    const i64 cells = (i64)p.N * p.maxr;
     const unsigned grid = (unsigned)((cells + 255) / 256);
     for (i64 q = 0; q < nrhs; ++q) {
         p.x = d_B + q * ldb;
         p.what = q == 0 ? 3 : 1;
         bbb_tri_pack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
-        cudaError_t e = pf == 8 ? launch_wave<T, 8>(p, smem, h->stream) : pf == 6 ? launch_wave<T, 6>(p, smem, h->stream)
-                      : pf == 4 ? launch_wave<T, 4>(p, smem, h->stream) : launch_wave<T, 2>(p, smem, h->stream);
+        cudaError_t e;
+        const size_t lsmem = (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T);
+        if (lean == 13) e = launch_lean<T, 4, 1, 3>(p, lsmem, h->stream);
+        else if (lean == 25) e = launch_lean<T, 4, 2, 5>(p, lsmem, h->stream);
+        else e = pf == 8 ? launch_wave<T, 8>(p, smem, h->stream) : pf == 4 ? launch_wave<T, 4>(p, smem, h->stream) : launch_wave<T, 2>(p, smem, h->stream);
         if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_trisolve_wave_kernel launch: %s", cudaGetErrorString(e));
         bbb_tri_unpack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
         e = cudaGetLastError();
