@@ -20,8 +20,10 @@
 #include <vector>
 
 #include "bbm_internal.h"
+#include "ptx.cuh"
 
 namespace cg = cooperative_groups;
+using namespace ptx;
 
 namespace {
 
@@ -262,7 +264,8 @@ struct TriWaveParams {
     i64 total, Wd;     // plane stride = iters*Wd
     int N, maxr, iters;
     int l, u, lam, mu, w, P;
-    int upper, unit, passes, D, nc, relaxed, what;
+    int upper, unit, passes, D, nc, relaxed, what, dbg, push;
+    int* status;       // set to 1 if a halo value never arrived (lean kernel; the result is then invalid)
 };
 
 constexpr int kTriGroup = 128;                      // lanes dealt to one CTA at a time
@@ -313,7 +316,9 @@ __global__ void __launch_bounds__(256) bbb_tri_unpack_kernel(const TriWaveParams
     const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
     if (k >= rK) return;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
-    p.x[r0 + k] = p.packed[(i64)(kk + delta * Kl) * p.Wd + Kl % p.Wd];
+    T v = p.packed[(i64)(kk + delta * Kl) * p.Wd + Kl % p.Wd];
+    if (*p.status) v = T(NAN);   // a halo value never arrived inside the solve kernel: poison instead of a wrong answer
+    p.x[r0 + k] = v;
 }
 
 // shared memory: ring [passes][D][kTriThreads] | coef [passes][PF][NC][kTriThreads]
@@ -428,110 +433,213 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
 }
 
 // Lean instantiation of the wave kernel for at most kTriLanes block rows with compile-time block bandwidth ND
-// (towards the already solved side) and sub-block band width W: everything a step needs besides the neighbours'
-// newest values -- prefetch issue, coefficient loads into registers, the reciprocal of the diagonal entry -- is
-// done between the barrier's arrive and wait, so the dependent chain of a step is: barrier release -> ring loads
-// (shared / distributed shared memory) -> ND*W + W-1 FMAs -> quotient correction -> ring store -> arrive.
-template <typename T, int PF, int ND, int W>
+// (towards the already solved side), sub-block band width W and NDIAG diagonal-block entries beside the diagonal.
+// A step is latency-bound (every warp runs the same short dependent instruction stream, then the cluster
+// barrier), so everything that does not need the neighbours' newest values -- prefetch issue, coefficient loads
+// into registers, the reciprocal of the diagonal entry, the ring addresses -- sits between the barrier's arrive
+// and its wait, where it overlaps the barrier's own latency; the dependent chain of a step is then: barrier
+// release -> ND*W + NDIAG ring loads -> as many FMAs -> quotient correction -> ring store -> arrive.  The
+// solution's global store is issued after the arrive.
+//
+// Lane groups of neighbouring CTAs meet at every 128th block row.  Reading the neighbour's ring there through
+// distributed shared memory costs ~600 cycles inside the dependent chain of EVERY step (the slowest warp sets
+// the pace: measured 0.87 -> 0.55 us per step with those reads made local).  So the producer pushes instead:
+// the last ND lanes of a group send each new value with st.async into a halo ring in the consumer's CTA, which
+// completes a transaction on an mbarrier there; the first warp of the consumer group arms the mbarrier with
+// expect_tx before the cluster barrier and checks it after -- by then the value has normally landed -- and every
+// ring load of every lane is a local shared-memory load.
+__device__ __forceinline__ uint32_t tri_mapa(uint32_t smem_addr, int cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void tri_st_async(uint32_t remote_addr, double v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void tri_st_async(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_mbar)
+                 : "memory");
+}
+
+template <typename T, int PF, int ND, int W, int NDIAG>
 __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) bbb_trisolve_lean_kernel(const TriWaveParams<T> p) {
     static_assert((PF & (PF - 1)) == 0, "PF must be a power of two");
+    static_assert(ND >= 1 && ND <= 32, "halo bookkeeping is done by the first warp of a lane group");
+    constexpr int NC = 2 + ND * W + NDIAG;
     extern __shared__ __align__(16) unsigned char tri_ring_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const int rank = (int)cluster.block_rank();
-    const int g = ((tid / kTriGroup) * kTriCtas + rank) * kTriGroup + tid % kTriGroup;   // block row in solve order
-    const int D = p.D, mu = p.mu, iters = p.iters;
+    const int grp = tid / kTriGroup, lid = tid % kTriGroup;
+    const int G = grp * kTriCtas + rank;          // lane group in solve order
+    const int g = G * kTriGroup + lid;            // block row in solve order
+    const int Dm = p.D - 1, mu = p.mu, iters = p.iters;
+    const bool unit = p.unit != 0, push = p.push != 0;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
-    const int ndiag = p.upper ? p.mu : p.lam;
     const int ii0 = p.upper ? 0 : p.mu + 1;
-    const int NC = 2 + ND * W + ndiag;
+    const i64 tot = p.total, Wd = p.Wd;
     T* ring = reinterpret_cast<T*>(tri_ring_smem);            // [D][kTriThreads]
-    T* coef = ring + (size_t)D * kTriThreads;                 // [PF][NC][kTriThreads]
+    T* coef = ring + (size_t)p.D * kTriThreads;               // [PF][NC][kTriThreads]
+    T* halo = coef + (size_t)PF * NC * kTriThreads;           // [kTriGroups][ND][D]: rings of the previous group's last ND lanes
+    uint64_t* hbar = reinterpret_cast<uint64_t*>(halo + kTriGroups * ND * p.D);   // [kTriGroups][ND][2]: steps alternate
 
-    int rK = 0;
-    if (g < p.N) {
-        const i64 K = p.upper ? p.N - 1 - g : g;
-        rK = (int)(p.R[K + 1] - p.R[K]);
-    }
-    for (int t = tid; t < D * kTriThreads; t += kTriThreads) ring[t] = T(0);
-    cluster.sync();  // every ring is zeroed before a neighbour CTA may read it
+    auto block_size = [&](int lane) -> int {
+        if (lane < 0 || lane >= p.N) return 0;
+        const i64 K = p.upper ? p.N - 1 - lane : lane;
+        return (int)(p.R[K + 1] - p.R[K]);
+    };
+    const int rK = block_size(g);
+    for (int t = tid; t < p.D * kTriThreads; t += kTriThreads) ring[t] = T(0);
+    for (int t = tid; t < kTriGroups * ND * p.D; t += kTriThreads) halo[t] = T(0);
+    if (tid < kTriGroups * ND * 2) mbar_init(&hbar[tid], 1);
+    fence_mbar_init();
+    cluster.sync();  // rings zeroed and mbarriers initialised before a neighbour CTA may touch them
 
-    // rings of the lanes 1..ND block rows back; a lane without such a neighbour reads its own ring (times zero)
-    const T* rem[ND > 0 ? ND : 1];
+    // ring of the lane d block rows back and its slot stride; a lane without such a neighbour reads its own ring
+    // (times a zero coefficient)
+    const T* rem[ND];
+    int rstride[ND];
 #pragma unroll
     for (int d = 1; d <= ND; ++d) {
         const int gj = g - d;
-        const int G = (gj < 0 ? 0 : gj) / kTriGroup;
-        rem[d - 1] = gj < 0 ? ring + tid : cluster.map_shared_rank(ring, G % kTriCtas) + (G / kTriCtas) * kTriGroup + gj % kTriGroup;
+        rstride[d - 1] = kTriThreads;
+        if (gj < 0) {
+            rem[d - 1] = ring + tid;
+        } else if (lid >= d) {
+            rem[d - 1] = ring + tid - d;
+        } else if (push) {
+            rem[d - 1] = halo + (grp * ND + (d - lid - 1)) * p.D;
+            rstride[d - 1] = 1;
+        } else {
+            const int Gj = gj / kTriGroup;
+            rem[d - 1] = cluster.map_shared_rank(ring, Gj % kTriCtas) + (Gj / kTriCtas) * kTriGroup + gj % kTriGroup;
+        }
     }
     T* const mine = ring + tid;
+    T* const cmine = coef + tid;
     // step s works on in-block row k = kbase + ksgn*kr, kr = s - delta*g - kk0, if 0 <= kr < rK
     const int kk0 = p.upper ? p.maxr - rK : 0;
     const int kbase = p.upper ? rK - 1 : 0, ksgn = p.upper ? -1 : 1;
     int kr = -delta * g - kk0;
-    const T* src = p.packed + (g % p.Wd);   // + s*Wd
+    T* src = p.packed + (g % Wd);   // + s*Wd
+
+    // producer side of the halo: my values go to halo ring q of the next lane group
+    const int q_out = kTriGroup - 1 - lid;
+    const bool pushes = push && q_out < ND && G + 1 < kTriGroups * kTriCtas;
+    uint32_t out_ring = 0, out_bar = 0;
+    if (pushes) {
+        const int Gn = G + 1;
+        out_ring = tri_mapa(smem_u32(halo + ((Gn / kTriCtas) * ND + q_out) * p.D), Gn % kTriCtas);
+        out_bar = tri_mapa(smem_u32(&hbar[((Gn / kTriCtas) * ND + q_out) * 2]), Gn % kTriCtas);
+    }
+    // consumer side (first warp of the group): halo ring q receives a value in step t iff its producer is active
+    // then.  That value completes a transaction on mbarrier [q][t&1], which the consumer armed in step t-1 (right
+    // after it was done with the value of step t-2 on the same mbarrier, and before its own arrive, hence before
+    // the producer can get to step t) and waits for in step t+1.
+    const bool halo_warp = push && lid < 32 && G > 0;
+    int krP[ND], rKP[ND];
+    uint32_t par = 0, failed = 0;   // bit 2q+b of par = phase parity of mbarrier [q][b]
+#pragma unroll
+    for (int q = 0; q < ND; ++q) {
+        const int gP = G * kTriGroup - 1 - q;
+        rKP[q] = halo_warp ? block_size(gP) : 0;
+        krP[q] = -1 - delta * gP - (p.upper ? p.maxr - rKP[q] : 0);   // the producer's kr at step s-1
+        if (halo_warp && lid == 0 && (unsigned)(krP[q] + 1) < (unsigned)rKP[q]) mbar_arrive_expect_tx(&hbar[(grp * ND + q) * 2], (uint32_t)sizeof(T));
+    }
 
     auto issue = [&](int st, int krs, const T* sp) {
         if ((unsigned)krs < (unsigned)rK) {
-            T* cb = coef + (size_t)((st & (PF - 1)) * NC) * kTriThreads + tid;
+            T* cb = cmine + (size_t)((st & (PF - 1)) * NC) * kTriThreads;
             tri_cp_async(cb, sp);
-            if (!p.unit) tri_cp_async(cb + kTriThreads, sp + p.total);
-            for (int c = 2; c < NC; ++c) tri_cp_async(cb + (size_t)c * kTriThreads, sp + (i64)c * p.total);
+            if (!unit) tri_cp_async(cb + kTriThreads, sp + tot);
+#pragma unroll
+            for (int c = 2; c < NC; ++c) tri_cp_async(cb + c * kTriThreads, sp + c * tot);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    for (int t = 0; t < PF - 1; ++t) issue(t, kr + t, src + (i64)t * p.Wd);
+    for (int t = 0; t < PF - 1; ++t) issue(t, kr + t, src + (i64)t * Wd);
 
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     for (int s = 0; s < iters; ++s) {
-        issue(s + PF - 1, kr + PF - 1, src + (i64)(PF - 1) * p.Wd);
+        issue(s + PF - 1, kr + PF - 1, src + (PF - 1) * Wd);
         asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
         const bool active = (unsigned)kr < (unsigned)rK;
         const int k = kbase + ksgn * kr;
-        T acc = T(0), rinv = T(1), dg = T(1), co[ND > 0 ? ND : 1][W], cg_[W > 1 ? W - 1 : 1];
+        T acc = T(0), rinv = T(1), dg = T(1), co[ND][W], cl[NDIAG > 0 ? NDIAG : 1];
+        const T* pr[ND][W];
+        const T* pl[NDIAG > 0 ? NDIAG : 1];
+        T* const pme = mine + (k & Dm) * kTriThreads;
         if (active) {
-            const T* cb = coef + (size_t)((s & (PF - 1)) * NC) * kTriThreads + tid;
+            const T* cb = cmine + (size_t)((s & (PF - 1)) * NC) * kTriThreads;
             acc = cb[0];
-            if (!p.unit) { dg = cb[kTriThreads]; rinv = T(1) / dg; }
-#pragma unroll
-            for (int d = 0; d < ND; ++d)
-#pragma unroll
-                for (int ii = 0; ii < W; ++ii) co[d][ii] = cb[(size_t)(2 + d * W + ii) * kTriThreads];
-#pragma unroll
-            for (int t = 0; t < W - 1; ++t) cg_[t] = t < ndiag ? cb[(size_t)(2 + ND * W + t) * kTriThreads] : T(0);
-        }
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // step s-1 is complete cluster-wide
-        if (active) {
+            if (!unit) { dg = cb[kTriThreads]; rinv = T(1) / dg; }
             const int km = k + mu;
 #pragma unroll
             for (int d = 0; d < ND; ++d)
 #pragma unroll
-                for (int ii = 0; ii < W; ++ii) acc = fma(-co[d][ii], rem[d][((km - ii) & (D - 1)) * kTriThreads], acc);
+                for (int ii = 0; ii < W; ++ii) {
+                    co[d][ii] = cb[(2 + d * W + ii) * kTriThreads];
+                    pr[d][ii] = rem[d] + ((km - ii) & Dm) * rstride[d];
+                }
 #pragma unroll
-            for (int t = 0; t < W - 1; ++t) acc = fma(-cg_[t], mine[((km - ii0 - t) & (D - 1)) * kTriThreads], acc);
-            T xk = acc;
-            if (!p.unit) {   // acc / dg from the reciprocal prepared above (quotient, exact residual, correction)
+            for (int t = 0; t < NDIAG; ++t) {
+                cl[t] = cb[(2 + ND * W + t) * kTriThreads];
+                pl[t] = mine + ((km - ii0 - t) & Dm) * kTriThreads;
+            }
+        }
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // step s-1 is complete cluster-wide
+        if (halo_warp) {
+#pragma unroll
+            for (int q = 0; q < ND; ++q) {
+                uint64_t* bar = &hbar[(grp * ND + q) * 2 + ((s + 1) & 1)];   // the mbarrier of steps s-1 and s+1
+                const int bit = 2 * q + ((s + 1) & 1);
+                if ((unsigned)krP[q] < (unsigned)rKP[q] && !failed) {          // a value was pushed in step s-1
+                    int spin = 0;
+                    while (!mbar_try_wait(bar, (par >> bit) & 1u))
+                        if (++spin > (1 << 14)) { failed = 1; break; }   // never hang: a lost value poisons the result
+                    par ^= 1u << bit;
+                }
+                if (lid == 0 && (unsigned)(krP[q] + 2) < (unsigned)rKP[q]) mbar_arrive_expect_tx(bar, (uint32_t)sizeof(T));
+            }
+        }
+        T xk = T(0);
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+#pragma unroll
+                for (int ii = 0; ii < W; ++ii) acc = fma(-co[d][ii], *pr[d][ii], acc);
+#pragma unroll
+            for (int t = 0; t < NDIAG; ++t) acc = fma(-cl[t], *pl[t], acc);
+            xk = acc;
+            if (!unit) {   // acc / dg from the reciprocal prepared above (quotient, exact residual, correction)
                 const T q = acc * rinv;
                 xk = fma(fma(-dg, q, acc), rinv, q);
             }
-            mine[(k & (D - 1)) * kTriThreads] = xk;
-            const_cast<T*>(src)[0] = xk;
+            *pme = xk;
+            if (pushes) tri_st_async(out_ring + (uint32_t)((k & Dm) * sizeof(T)), xk, out_bar + 8u * (s & 1));
         }
         // only the shared-memory ring has to be ordered across the step boundary (see the generic kernel)
         asm volatile("fence.acq_rel.cta;" ::: "memory");
         asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        if (active) *src = xk;
         ++kr;
-        src += p.Wd;
+#pragma unroll
+        for (int q = 0; q < ND; ++q) ++krP[q];
+        src += Wd;
     }
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (failed) *p.status = 1;
     cluster.sync();  // nothing may leave while a neighbour could still read its ring
 }
 
-template <typename T, int PF, int ND, int W>
+template <typename T, int PF, int ND, int W, int NDIAG>
 cudaError_t launch_lean(const TriWaveParams<T>& p, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(bbb_trisolve_lean_kernel<T, PF, ND, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bbb_trisolve_lean_kernel<T, PF, ND, W, NDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bbb_trisolve_lean_kernel<T, PF, ND, W><<<kTriCtas, kTriThreads, smem, stream>>>(p);
+    bbb_trisolve_lean_kernel<T, PF, ND, W, NDIAG><<<kTriCtas, kTriThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -553,7 +661,7 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     TriWaveParams<T> p{};
     p.data = sp.data; p.R = sp.R; p.N = (int)sp.N; p.maxr = (int)sp.maxr; p.iters = (int)sp.iters;
     p.l = sp.l; p.u = sp.u; p.lam = sp.lam; p.mu = sp.mu; p.w = sp.w; p.P = sp.P;
-    p.upper = upper; p.unit = sp.unit; p.passes = sp.passes; p.D = sp.D; p.nc = sp.nc; p.relaxed = sp.relaxed;
+    p.upper = upper; p.unit = sp.unit; p.passes = sp.passes; p.D = sp.D; p.nc = sp.nc; p.relaxed = sp.relaxed; p.dbg = sp.dbg;
     const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
     const size_t fixed = (size_t)p.passes * (kTriThreads * p.D * sizeof(T) + (kTriGroups * (kTriGroup + nd) + kTriThreads) * sizeof(int)) + 16;
     int pf = 0;
@@ -566,16 +674,21 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     Wd = (Wd + 15) / 16 * 16;
     p.Wd = Wd;
     p.total = (i64)p.iters * Wd;
-    const size_t need = (size_t)p.total * p.nc * sizeof(T);
+    const size_t need = ((size_t)p.total * p.nc * sizeof(T) + 255) / 256 * 256;
     if (need > (size_t)bbm_opt(h, "tri.ws_max_mb", 16384) * 1048576) return 1;
-    if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, need) != BBM_OK) return 1;
+    if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, need + 256) != BBM_OK) return 1;
     p.packed = static_cast<T*>(h->ws_w);
+    p.status = reinterpret_cast<int*>(static_cast<char*>(h->ws_w) + need);
+    p.push = bbm_opt(h, "tri.push", 1) != 0 ? 1 : 0;
+    BBM_CUDA(h, cudaMemsetAsync(p.status, 0, sizeof(int), h->stream));
     const size_t smem = fixed + (size_t)p.passes * pf * kTriThreads * p.nc * sizeof(T);
     // lean instantiations: one pass, the two common shapes (l or u = 1 with 3 sub-block bands, 2 with 5)
     int lean = 0;
-    if (p.passes == 1 && bbm_opt(h, "tri.lean", 1) != 0 && (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T) <= budget) {
-        if (nd == 1 && p.w == 3) lean = 13;
-        if (nd == 2 && p.w == 5) lean = 25;
+    if (p.passes == 1 && bbm_opt(h, "tri.lean", 1) != 0 &&
+        (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T) + (size_t)kTriGroups * nd * (p.D * sizeof(T) + 2 * sizeof(uint64_t)) <= budget) {
+        const int ndiag = upper ? p.mu : p.lam;
+        if (nd == 1 && p.w == 3 && ndiag == 1) lean = 13;
+        if (nd == 2 && p.w == 5 && ndiag == 2) lean = 25;
     }
     const i64 cells = (i64)p.N * p.maxr;
     const unsigned grid = (unsigned)((cells + 255) / 256);
@@ -584,9 +697,9 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
         p.what = q == 0 ? 3 : 1;
         bbb_tri_pack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
         cudaError_t e;
-        const size_t lsmem = (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T);
-        if (lean == 13) e = launch_lean<T, 4, 1, 3>(p, lsmem, h->stream);
-        else if (lean == 25) e = launch_lean<T, 4, 2, 5>(p, lsmem, h->stream);
+        const size_t lsmem = (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T) + (size_t)kTriGroups * nd * (p.D * sizeof(T) + 2 * sizeof(uint64_t));
+        if (lean == 13) e = launch_lean<T, 4, 1, 3, 1>(p, lsmem, h->stream);
+        else if (lean == 25) e = launch_lean<T, 4, 2, 5, 2>(p, lsmem, h->stream);
         else e = pf == 8 ? launch_wave<T, 8>(p, smem, h->stream) : pf == 4 ? launch_wave<T, 4>(p, smem, h->stream) : launch_wave<T, 2>(p, smem, h->stream);
         if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_trisolve_wave_kernel launch: %s", cudaGetErrorString(e));
         bbb_tri_unpack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
@@ -631,7 +744,7 @@ int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t un
     // staged variant: deepest prefetch ring (6, 4 or 2 steps) that fits next to the solution rings
     p.nc = 2 + (int)(nd * (v.lam + v.mu + 1)) + (int)(upper ? v.mu : v.lam);
     const size_t meta = (size_t)p.passes * (kTriThreads + nd) * (sizeof(i64) + sizeof(int)) + 16;
-    p.relaxed = bbm_opt(h, "tri.sync", 1) != 0 ? 1 : 0;
+    p.relaxed = (int)bbm_opt(h, "tri.sync", 1);  // 0 = cluster.sync(), 1 = CTA fence + relaxed arrive, 2/3 = experiments (lean kernel)
     p.dbg = (int)bbm_opt(h, "tri.dbg", 0);  // timing experiments only (bit 0: no substitution, bit 1: no prefetch)
     const int which = (int)bbm_opt(h, "tri.kernel", 0);  // 0 = wave-ordered, 1 = staged, 2 = direct
     if (which == 0) {

@@ -229,26 +229,29 @@ TRI_STRUCTURES = [
     ([6] * 700, (1, 2), (1, 1)),                 # more block rows than one CTA of the cluster owns
     ([33] * 4, (0, 0), (3, 3)),                  # block diagonal
     ([9, 4, 11] * 10, (2, 2), (2, 2)),           # cfg3's bandwidths
+    ([5, 3] * 200, (2, 2), (2, 2)),              # ... across several lane groups / CTAs of the cluster
 ]
 
 
-@pytest.mark.parametrize("kernel,pf,lean", [(0, 4, 1), (0, 4, 0), (0, 2, 0), (1, 6, 0), (1, 2, 0), (2, 0, 0)],
-                         ids=["lean", "wave4", "wave2", "staged6", "staged2", "direct"])
+@pytest.mark.parametrize("kernel,pf,lean,push", [(0, 4, 1, 1), (0, 4, 1, 0), (0, 4, 0, 0), (0, 2, 0, 0), (1, 6, 0, 0), (1, 2, 0, 0), (2, 0, 0, 0)],
+                         ids=["lean-push", "lean-dsmem", "wave4", "wave2", "staged6", "staged2", "direct"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("uplo,unit", [("U", False), ("U", True), ("L", False), ("L", True)])
-def test_bbb_triangular_ldiv(handle, uplo, unit, dtype, kernel, pf, lean):
+def test_bbb_triangular_ldiv(handle, uplo, unit, dtype, kernel, pf, lean, push):
     """test/test_triblockbanded.jl:80-99: U \\ b for Upper/UnitUpper/Lower/UnitLower triangular
     BandedBlockBandedMatrix against the block-substitution restatement and a dense solve; the triangle
     that must not be read (and the diagonal of the unit variants) is NaN."""
     handle.set_option("tri.pf", pf)
     handle.set_option("tri.kernel", kernel)
     handle.set_option("tri.lean", lean)
+    handle.set_option("tri.push", push)
     try:
         _check_triangular_ldiv(handle, uplo, unit, dtype)
     finally:
         handle.set_option("tri.pf", 4)
         handle.set_option("tri.kernel", 0)
         handle.set_option("tri.lean", 1)
+        handle.set_option("tri.push", 1)
 
 
 def _check_triangular_ldiv(handle, uplo, unit, dtype):
