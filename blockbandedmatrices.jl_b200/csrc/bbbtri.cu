@@ -13,11 +13,17 @@
 // l block rows -- through distributed shared memory when those sit in another CTA of the 8-CTA thread-block
 // cluster -- and the steps are separated by the hardware cluster barrier: no global-memory round trip, no
 // spin-waits, 4096 block rows in flight on 8 SMs.  Upper solves run the mirror image (block rows and rows
-// descending, delta = lam+1).  n + delta*N steps in total (12 285 for the 16.7M-unknown cfg2 Laplacian).
+// descending, delta = lam+1).  n + delta*N steps in total (12 286 for the 16.7M-unknown cfg2 Laplacian).
+//
+// Four kernels, fastest first; the entry point takes the first one that applies:
+//   lean   wave-ordered inputs, one block row per thread, compile-time bandwidths ((1,1),(1,1) and (2,2),(2,2)),
+//          group-boundary values pushed with st.async                      0.40 us/step   7.2 ms on cfg2 (CPU 154 ms)
+//   wave   wave-ordered inputs, any bandwidths / up to 6 block rows per thread          1.3 us/step
+//   staged band storage read in place, prefetched with cp.async (no workspace)          3.0 us/step
+//   direct band storage read in place inside the step                                   4.4 us/step
 #include <cooperative_groups.h>
 
 #include <algorithm>
-#include <vector>
 
 #include "bbm_internal.h"
 #include "ptx.cuh"
@@ -38,7 +44,7 @@ struct TriSolveParams {
     const i64* R;      // prefix sums of the (square) block sizes
     i64 N, maxr, iters;
     int l, u, lam, mu, w, P;
-    int upper, unit, passes, D, nc, relaxed, dbg;
+    int upper, unit, passes, D, nc, relaxed;
 };
 
 template <typename T>
@@ -185,9 +191,9 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
 
     for (int t = 0; t < PF - 1; ++t) issue(t);
     for (i64 s = 0; s < p.iters; ++s) {
-        if (!(p.dbg & 2)) issue(s + PF - 1);
+        issue(s + PF - 1);
         asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
-        for (int pass = 0; pass < ((p.dbg & 1) ? 0 : p.passes); ++pass) {
+        for (int pass = 0; pass < p.passes; ++pass) {
             const i64 Kl = (i64)g + (i64)kTriLanes * pass;
             const i64 kk = s - (i64)delta * Kl;
             if (kk < 0 || kk >= p.maxr) continue;
@@ -264,7 +270,7 @@ struct TriWaveParams {
     i64 total, Wd;     // plane stride = iters*Wd
     int N, maxr, iters;
     int l, u, lam, mu, w, P;
-    int upper, unit, passes, D, nc, relaxed, what, dbg, push;
+    int upper, unit, passes, D, nc, relaxed, what, push;
     int* status;       // set to 1 if a halo value never arrived (lean kernel; the result is then invalid)
 };
 
@@ -661,7 +667,7 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     TriWaveParams<T> p{};
     p.data = sp.data; p.R = sp.R; p.N = (int)sp.N; p.maxr = (int)sp.maxr; p.iters = (int)sp.iters;
     p.l = sp.l; p.u = sp.u; p.lam = sp.lam; p.mu = sp.mu; p.w = sp.w; p.P = sp.P;
-    p.upper = upper; p.unit = sp.unit; p.passes = sp.passes; p.D = sp.D; p.nc = sp.nc; p.relaxed = sp.relaxed; p.dbg = sp.dbg;
+    p.upper = upper; p.unit = sp.unit; p.passes = sp.passes; p.D = sp.D; p.nc = sp.nc; p.relaxed = sp.relaxed;
     const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
     const size_t fixed = (size_t)p.passes * (kTriThreads * p.D * sizeof(T) + (kTriGroups * (kTriGroup + nd) + kTriThreads) * sizeof(int)) + 16;
     int pf = 0;
@@ -744,8 +750,7 @@ int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t un
     // staged variant: deepest prefetch ring (6, 4 or 2 steps) that fits next to the solution rings
     p.nc = 2 + (int)(nd * (v.lam + v.mu + 1)) + (int)(upper ? v.mu : v.lam);
     const size_t meta = (size_t)p.passes * (kTriThreads + nd) * (sizeof(i64) + sizeof(int)) + 16;
-    p.relaxed = (int)bbm_opt(h, "tri.sync", 1);  // 0 = cluster.sync(), 1 = CTA fence + relaxed arrive, 2/3 = experiments (lean kernel)
-    p.dbg = (int)bbm_opt(h, "tri.dbg", 0);  // timing experiments only (bit 0: no substitution, bit 1: no prefetch)
+    p.relaxed = bbm_opt(h, "tri.sync", 1) != 0 ? 1 : 0;  // 0 = cluster.sync(), 1 = CTA fence + relaxed arrive (staged / generic wave kernels)
     const int which = (int)bbm_opt(h, "tri.kernel", 0);  // 0 = wave-ordered, 1 = staged, 2 = direct
     if (which == 0) {
         const int32_t rc = bbb_trsv_wave<T>(h, v, p, d_B, ldb, nrhs);

@@ -63,8 +63,6 @@ struct bbm_context {
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
     void* ws_z = nullptr; size_t ws_z_bytes = 0;   // triangular solve: inverses of the diagonal blocks
     void* ws_w = nullptr; size_t ws_w_bytes = 0;   // triangular solve: level temporaries / wave-ordered coefficients
-    void* tri_base = nullptr; size_t tri_base_bytes = 0;  // banded-block-banded triangular solve: wave offsets
-    i64 tri_base_key[3] = {-1, -1, -1};                   // (block rows, largest block, skew) the table was built for
     // low-priority side stream (L2 prefetch ahead of the triangular solve's sequential chain)
     const BbmPeerParams* peer = nullptr;  // non-null only inside a fused multi-GPU product call
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // pipelined host-vector product

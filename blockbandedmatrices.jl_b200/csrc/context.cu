@@ -5,7 +5,7 @@
 
 static const char* const kOptionKeys[] = {
     "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves", "bbb.host_chunks", "bbb.ovh", "bbb.mm_kernel", "bbb.pdl",
-    "sky.kernel", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "tri.pf", "tri.sync", "tri.dbg", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "dist.graph", "dist.peer", "dist.lead_steps", nullptr};
+    "sky.kernel", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "dist.graph", "dist.peer", "dist.lead_steps", nullptr};
 
 extern "C" {
 
@@ -52,7 +52,6 @@ int32_t bbm_destroy(bbm_handle_t h) {
     if (h->ws_y) cudaFree(h->ws_y);
     if (h->ws_z) cudaFree(h->ws_z);
     if (h->ws_w) cudaFree(h->ws_w);
-    if (h->tri_base) cudaFree(h->tri_base);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }

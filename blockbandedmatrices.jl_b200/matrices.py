@@ -203,6 +203,29 @@ class BandedBlockBandedMatrix(_BlockAxes):
                 out[k, jj] = band[self.mu + k - jj, jj]
         return out
 
+    def view(self, block_rows, block_cols) -> "BandedBlockBandedMatrix":
+        """``view(A, Block.(K0:K1-1), Block.(J0:J1-1))`` for contiguous block ranges (0-based ``range``s or ints):
+        again a BandedBlockBandedMatrix over the SAME storage -- the column slab ``C[J0]:C[J1]`` of ``data`` --
+        with the block bandwidths shifted to ``(l-K0+J0, u+K0-J0)`` (test/test_triblockbanded.jl:55-78,
+        layout BandedBlockBandedColumnMajor of block-range sub-views).  No copy, host or device."""
+        def rng(b, n):
+            if isinstance(b, (int, np.integer)):
+                b = range(int(b), int(b) + 1)
+            if not isinstance(b, range) or b.step != 1 or b.start < 0 or b.stop > n or b.stop < b.start:
+                raise IndexError(f"block range {b!r} is not a contiguous range inside 0:{n}")
+            return b
+        br, bc = rng(block_rows, len(self.rows)), rng(block_cols, len(self.cols))
+        K0, J0 = br.start, bc.start
+        c0, c1 = int(self.C[bc.start]), int(self.C[bc.stop])
+        P = self.data.shape[0]
+        if isinstance(self.data, np.ndarray):
+            d = self.data[:, c0:c1]
+        else:
+            d = DeviceArray(self.data.handle, (P, c1 - c0), self.dtype, ptr=self.data.ptr + P * c0 * self.dtype.itemsize)
+            d._keep = self.data
+        return BandedBlockBandedMatrix(d, self.rows[br.start:br.stop], self.cols[bc.start:bc.stop],
+                                       (self.l - K0 + J0, self.u + K0 - J0), (self.lam, self.mu))
+
     # ---- device residency ----------------------------------------------------------------------
     def to_device(self, handle: Handle) -> "BandedBlockBandedMatrix":
         """Device-resident copy: one memcpy of the parent array, shape unchanged."""

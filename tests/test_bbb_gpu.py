@@ -211,6 +211,28 @@ def test_bbb_triangular_mul(handle, uplo, unit, dtype, kernel):
         handle.set_option("bbb.kernel", 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_bbb_block_range_view_mul(handle, dtype):
+    """test/test_triblockbanded.jl:55-78: c .= MulAdd(V, b) for block-range sub-views V of a device matrix."""
+    rows = list(range(1, 11))
+    rng = np.random.default_rng(51)
+    data = random_bbb(rng, rows, rows, 1, 1, 1, 1, dtype)
+    A = B.BandedBlockBandedMatrix(data, rows, rows, (1, 1), (1, 1))
+    Dn = A.to_dense().astype(np.float64)
+    Ad = A.to_device(handle)
+    R = np.concatenate([[0], np.cumsum(rows)])
+    for br, bc in [(2, range(2, 5)), (range(1, 4), 2), (range(3, 9), range(2, 10)), (range(0, 2), range(6, 9)), (range(0, 10), range(0, 10))]:
+        V = Ad.view(br, bc)
+        br = range(br, br + 1) if isinstance(br, int) else br
+        bc = range(bc, bc + 1) if isinstance(bc, int) else bc
+        sub = Dn[R[br.start]:R[br.stop], R[bc.start]:R[bc.stop]]
+        assert V.shape == sub.shape
+        b = rng.standard_normal(sub.shape[1]).astype(dtype)
+        c = handle.empty(sub.shape[0], dtype).fill_bytes(0xFF)
+        B.mul_(c, V, handle.to_device(b))
+        assert relerr(c.to_host(), sub @ b.astype(np.float64)) <= tol(dtype, 10)
+
+
 def _well_conditioned_tri(rng, rows, lu, lm, dtype):
     """random band storage whose triangles are comfortably invertible: small off-diagonal, diagonal ~ 2"""
     data = random_bbb(rng, rows, rows, *lu, *lm, dtype)
@@ -311,6 +333,18 @@ def test_bbb_triangular_ldiv_gauss_seidel_sweep(handle):
         ref = b.copy()
         O.bbb_trsm([n] * n, 1, 1, 1, 1, uplo, False, A.data, ref)
         assert relerr(db.to_host(), ref) <= tol(np.float64, 9)
+
+
+def test_gauss_seidel_example_on_device(handle):
+    """examples/finitedifference_2d.jl:17-47: x <- L \\ (b - U x) sweeps for A = I - dt*Laplacian."""
+    from benchmarks.gauss_seidel import gauss_seidel_device, gauss_seidel_host, heat_step_matrix
+    n = 48
+    A = heat_step_matrix(B, n)
+    b = np.random.default_rng(61).standard_normal(n * n)
+    x = gauss_seidel_device(B, handle, A.to_device(handle), handle.to_device(b), 5).to_host()
+    ref = gauss_seidel_host(A, b, 5)
+    assert relerr(x, ref) <= 5 * tol(np.float64, 9)
+    assert np.linalg.norm(A.to_dense() @ x - b) < 1e-3 * np.linalg.norm(b)     # and it converges
 
 
 def test_bbb_triangular_ldiv_errors(handle):

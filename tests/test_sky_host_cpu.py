@@ -64,3 +64,24 @@ def test_triangular_bandwidths():
     assert B.LowerTriangular(A).blockbandwidths == (1, 0)
     A = B.BlockSkylineMatrix.zeros(np.float64, [2, 3], [3, 2], 1, 1)
     assert B.UpperTriangular(A).blockbandwidths == (1, 1)     # blocks do not match: unchanged
+
+
+def test_bbb_block_range_views():
+    """test/test_triblockbanded.jl:55-78: view(A, Block(3), Block.(3:5)) / view(A, Block.(2:4), Block(3)) stay
+    banded-block-banded over the same storage with shifted block bandwidths."""
+    rows = list(range(1, 11))
+    rng = np.random.default_rng(3)
+    A = B.BandedBlockBandedMatrix(rng.standard_normal(B.BandedBlockBandedMatrix.data_shape(rows, (1, 1), (1, 1))), rows, rows, (1, 1), (1, 1))
+    D = A.to_dense()
+    V = A.view(2, range(2, 5))
+    assert V.blockbandwidths == (1, 1) and V.shape == (3, 3 + 4 + 5)
+    assert np.array_equal(V.to_dense(), D[3:6, 3:15])
+    V = A.view(range(1, 4), 2)
+    assert V.blockbandwidths == (2, 0) and V.blockshape == (3, 1)      # reference: blockbandwidths(V) == (2,0)
+    assert list(V.rows) == [2, 3, 4] and list(V.cols) == [3]
+    assert np.array_equal(V.to_dense(), D[1:10, 3:6])
+    assert np.shares_memory(V.data, A.data)
+    V = A.view(range(0, 2), range(6, 9))                                 # entirely outside the block band
+    assert not V.to_dense().any()
+    with pytest.raises(IndexError):
+        A.view(range(0, 11), 0)
