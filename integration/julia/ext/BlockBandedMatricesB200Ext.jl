@@ -30,7 +30,7 @@ using LinearAlgebra
 import BBMB200: libbbm
 
 # ---- status codes (bbm_status, include/bbm_b200.h) -------------------------------------------
-const BBM_OK, BBM_ERR_DIM, BBM_ERR_BAND = Int32(0), Int32(2), Int32(3)
+const BBM_OK, BBM_ERR_DIM, BBM_ERR_BAND, BBM_ERR_UNSUPPORTED = Int32(0), Int32(2), Int32(3), Int32(8)
 
 mutable struct Handle
     ptr::Ptr{Cvoid}
@@ -220,6 +220,19 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
         check(ccall(($(QuoteNode(Symbol("bbm_sky_trsm_", suf))), libbbm), Int32,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{$T}, Ptr{$T}, Int64, Int64),
                     handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), A.data.ptr, B.ptr, ld(B), size(B, 2)))
+        B
+    end
+    # ldiv!(LowerTriangular(A), b) etc. for a triangular BandedBlockBandedMatrix (test/test_triblockbanded.jl:80-99,
+    # the x .= Ldiv(L, x) of examples/finitedifference_2d.jl:21); BBM_ERR_UNSUPPORTED (blocks that do not match)
+    # falls through to the reference's generic solve
+    @eval function materialize!(L::Ldiv{<:TriangularLayout{UPLO,UNIT,<:BandedBlockBandedColumns},<:Any,<:AbstractTriangular{$T,<:B200BBB{$T}},<:B200Array{$T}}) where {UPLO,UNIT}
+        A, B = triangulardata(L.A), L.B
+        size(A, 1) == size(B, 1) || throw(DimensionMismatch("T has size $(size(A)), B has size $(size(B))"))
+        rc = ccall(($(QuoteNode(Symbol("bbm_bbb_trsv_", suf))), libbbm), Int32,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{$T}, Ptr{$T}, Int64, Int64),
+                   handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), parent(A.data).ptr, B.ptr, ld(B), size(B, 2))
+        rc == BBM_ERR_UNSUPPORTED && return invoke(materialize!, Tuple{Ldiv}, L)
+        check(rc)
         B
     end
 end
