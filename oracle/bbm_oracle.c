@@ -19,13 +19,14 @@
  * arithmetic pinned to "structured ~= dense", which is all the reference's own tests pin.
  */
 #include <dlfcn.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
 typedef int64_t i64;
 
-enum { ORACLE_OK = 0, ORACLE_ERR_DIM = 2, ORACLE_ERR_BAND = 3, ORACLE_ERR_BLAS = 7 };
+enum { ORACLE_OK = 0, ORACLE_ERR_ARG = 1, ORACLE_ERR_DIM = 2, ORACLE_ERR_BAND = 3, ORACLE_ERR_BLAS = 7 };
 
 /* ---- optional OpenBLAS binding (cblas, LP64) ------------------------------------------- */
 enum { CblasColMajor = 102, CblasNoTrans = 111, CblasUpper = 121, CblasLower = 122,

@@ -202,6 +202,50 @@ def sky_trsm(rows, l, u, uplo, unit, data, B):
     return B
 
 
+def sky_qr(rows, cols, l, u, data):
+    """qr!(A) in place on the skyline storage of the FACTORS structure (block bandwidths (l, u) with u = l_A+u_A
+    already, src/blockskylineqr.jl:29-43,75); returns tau (blocked like the shorter axis)."""
+    suf, _ = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    c, cp = _ia(cols)
+    lv, uv = _vecbw(l, len(c)), _vecbw(u, len(c))
+    tau = np.zeros(int(c.sum()) if len(r) >= len(c) else int(r.sum()), dtype=data.dtype)
+    f = getattr(lib(), f"oracle_sky_qr_{suf}")
+    rc = f(i64(len(r)), i64(len(c)), rp, cp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p), data.ctypes.data_as(_p), tau.ctypes.data_as(_p))
+    _check(rc, "sky_qr")
+    return tau
+
+
+def sky_qr_lmul_adj(rows, cols, l, u, data, tau, B):
+    """B <- Q' B in place for the packed Q of sky_qr (lmul!(F.Q', B), src/blockskylineqr.jl:77-127)."""
+    suf, _ = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    c, cp = _ia(cols)
+    lv, uv = _vecbw(l, len(c)), _vecbw(u, len(c))
+    if B.shape[0] != int(r.sum()):
+        raise ValueError("DimensionMismatch")
+    bp, ldb, nrhs = _mat(B, 0)
+    f = getattr(lib(), f"oracle_sky_qr_lmul_adj_{suf}")
+    rc = f(i64(len(r)), i64(len(c)), rp, cp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p), data.ctypes.data_as(_p),
+           tau.ctypes.data_as(_p), bp, i64(ldb), i64(nrhs))
+    _check(rc, "sky_qr_lmul_adj")
+    return B
+
+
+def sky_qr_ldiv(rows, l, u, data, tau, B):
+    """B <- F \\ B in place for a square block-banded QR (ldiv!(F, B), src/blockskylineqr.jl:131-145)."""
+    suf, _ = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    lv, uv = _vecbw(l, len(r)), _vecbw(u, len(r))
+    if B.shape[0] != int(r.sum()):
+        raise ValueError("DimensionMismatch")
+    bp, ldb, nrhs = _mat(B, 0)
+    f = getattr(lib(), f"oracle_sky_qr_ldiv_{suf}")
+    rc = f(i64(len(r)), rp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p), data.ctypes.data_as(_p), tau.ctypes.data_as(_p), bp, i64(ldb), i64(nrhs))
+    _check(rc, "sky_qr_ldiv")
+    return B
+
+
 def bbb_trsm(rows, l, u, lam, mu, uplo, unit, data, B):
     """B <- T^-1 B in place, T = triangular part ('U'/'L', unit or not) of the BandedBlockBandedMatrix."""
     suf, _ = _suffix(data.dtype)

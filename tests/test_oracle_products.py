@@ -190,3 +190,37 @@ def test_oracle_bbb_trsm_vs_dense(uplo, unit):
         got = Bm.copy(order="F")
         O.bbb_trsm(rows, *lu, *lm, uplo, unit, data, got)
         assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+QR_CASES = [
+    (list(range(1, 6)), list(range(1, 6)), 2, 1),     # test/test_blockskylineqr.jl:13-35 "Square QR"
+    (list(range(1, 7)), list(range(1, 6)), 2, 1),     # :37-58 "Thin QR"
+    ([4] * 6, [4] * 6, 1, 1),
+    ([3, 5, 2, 4], [3, 5, 2, 4], 1, 2),
+    ([7], [7], 0, 0),
+]
+
+
+@pytest.mark.parametrize("rows,cols,l,u", QR_CASES)
+def test_oracle_block_banded_qr_matches_lapack(rows, cols, l, u):
+    """test/test_blockskylineqr.jl:19-20,43-44: F.factors == qr(Matrix(A)).factors and F.tau == the dense
+    unblocked Householder taus; lmul!(Q', b) and F \\ b against dense LAPACK (:29-34)."""
+    rng = np.random.default_rng(17)
+    m, n = sum(rows), sum(cols)
+    Ad = F.sky_to_dense(F.sky_from_dense(rng.standard_normal((m, n)), rows, cols, l, u), rows, cols, l, u)
+    data = F.sky_from_dense(Ad, rows, cols, l, l + u)            # `_qr` widens to (l, l+u), src/blockskylineqr.jl:75
+    tau = O.sky_qr(rows, cols, l, l + u, data)
+    h, t = np.linalg.qr(Ad, mode="raw")                          # LAPACK geqrf: same reflector convention
+    fac = F.sky_to_dense(data, rows, cols, l, l + u)
+    assert np.abs(fac - h.T).max() <= 1e-13 * np.abs(h).max()    # R and the Householder vectors, nothing outside the band
+    assert np.abs(tau - t[:len(tau)]).max() <= 1e-13
+    B0 = rng.standard_normal((m, 3))
+    QtB = np.asfortranarray(B0.copy())
+    O.sky_qr_lmul_adj(rows, cols, l, l + u, data, tau, QtB)
+    Q, _ = np.linalg.qr(Ad, mode="complete")
+    assert np.abs(QtB - Q.T @ B0).max() <= 1e-13 * np.abs(B0).max()
+    if rows == cols:
+        X = np.asfortranarray(B0.copy())
+        O.sky_qr_ldiv(rows, l, l + u, data, tau, X)
+        ref = np.linalg.solve(Ad, B0)
+        assert np.linalg.norm(X - ref) <= 1e-10 * np.linalg.norm(ref)
