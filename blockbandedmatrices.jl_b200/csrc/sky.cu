@@ -70,6 +70,22 @@ struct bbm_sky_desc {
         Batch stepA, stepB;            // all block steps; tiles of step K are [ptr[K], ptr[K+1])
         std::vector<int> ptrA, ptrB;
     } tri[2];
+    // QR-solve plan (Float64): compact-WY form of every panel's reflectors, built on first use
+    struct Qr {
+        bool built = false;
+        i64 ncols = 0;                       // panels = min(Nr, Nc)
+        std::vector<i64> srows, vc, vt, g, tt, yt, xx;   // per panel: rows of V; workspace offsets (doubles)
+        i64 total = 0, tt_lo = 0, tt_hi = 0; // workspace size; the range holding the T' blocks (zeroed per call)
+        i64 maxel = 0;
+        i64* d_pan = nullptr;                // per panel: V start in the factors, ld, rows, cols, vc, vt
+        i64* d_blk = nullptr;                // per 32-reflector block: G diag offset, ld, T' diag offset, tau offset, size
+        i64 nblk = 0;
+        Tri::Batch gram, ytb;
+        std::vector<Tri::Batch> levels;      // two batches per doubling level of the T factors
+        i64 step_ldb = -1, step_nrhs = -1, step_ldw = -1;
+        Tri::Batch stepW, stepB;             // the sweep; tiles of panel K are [ptr[K], ptr[K+1])
+        std::vector<int> ptrW, ptrB;
+    } qr;
     // product plans keyed by the serials of (A, B), owned by the C descriptor
     struct MmPlan;
     std::map<std::pair<uint64_t, uint64_t>, MmPlan*> plans;
@@ -1039,6 +1055,199 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
     return BBM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// QR solve: lmul!(F.Q', B) and ldiv!(F, B) for F = qr(A) of a block-banded matrix
+// (src/blockskylineqr.jl:77-145).  F.factors is block-skyline with bandwidths (l, l+u): block column K
+// holds R in and above its diagonal block and, in block rows K..K+l, the Householder vectors of panel K
+// (LAPACK packing, unit diagonal implied); F.tau their scalar factors.
+//
+// The reference applies panel after panel with ormqr (one reflector after the other inside).  Here each
+// panel's product of reflectors is put into compact-WY form once, for all panels in parallel,
+//      Q_K = I - V T V',      Q_K' B = B - V (T' V') B = B - V (YT B),      YT = T' V'
+// with T from the Gram matrix G = V'V: 32x32 diagonal blocks by the larft recurrence
+// T[0:j,j] = -tau_j T[0:j,0:j] G[0:j,j], then doubling merges T12 = -T11 G12 T22 as batched tensor-core
+// products (stored transposed: T'21 = -T'22 (G21 T'11)).  What stays sequential is two split-k DMMA
+// products per panel, chained with programmatic dependent launches like the triangular solve:
+//      W_K = YT_K B[KR,:]   (c_K x nrhs),       B[KR,:] -= V_K W_K.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sky_qr_extract_kernel(const double* __restrict__ fac, const i64* __restrict__ pan, double* __restrict__ ws) {
+    const i64* q = pan + (i64)blockIdx.y * 6;
+    const i64 fstart = q[0], ld = q[1], S = q[2], c = q[3], vc = q[4], vt = q[5];
+    for (i64 idx = (i64)blockIdx.x * 256 + threadIdx.x; idx < S * c; idx += (i64)gridDim.x * 256) {
+        const i64 i = idx % S, j = idx / S;
+        const double v = i < j ? 0.0 : (i == j ? 1.0 : fac[fstart + i + j * ld]);
+        ws[vc + i + j * S] = v;   // V, unit lower trapezoidal, zeros above
+        ws[vt + j + i * c] = v;   // V'
+    }
+}
+
+// one warp per block of up to 32 reflectors: T by the larft recurrence, written transposed
+__global__ void __launch_bounds__(64) sky_qr_t32_kernel(const double* __restrict__ tau, const i64* __restrict__ blk, i64 nblk, double* __restrict__ ws) {
+    __shared__ double Ts[2][32][33], Gs[2][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 b = (i64)blockIdx.x * 2 + warp;
+    if (b >= nblk) return;
+    const i64 g0 = blk[b * 5], ld = blk[b * 5 + 1], t0 = blk[b * 5 + 2], tau0 = blk[b * 5 + 3];
+    const int sz = (int)blk[b * 5 + 4];
+    for (int j = 0; j < sz; ++j) {
+        Gs[warp][lane][j] = lane < sz ? ws[g0 + lane + (i64)j * ld] : 0.0;
+        Ts[warp][lane][j] = 0.0;
+    }
+    __syncwarp();
+    for (int j = 0; j < sz; ++j) {
+        const double tj = tau[tau0 + j];
+        double sum = 0.0;
+        if (lane < j)
+            for (int k = lane; k < j; ++k) sum = fma(Ts[warp][lane][k], Gs[warp][k][j], sum);
+        __syncwarp();
+        if (lane < j) Ts[warp][lane][j] = -tj * sum;
+        if (lane == j) Ts[warp][j][j] = tj;
+        __syncwarp();
+    }
+    for (int i = 0; i < sz; ++i)   // T'[j,i] = T[i,j]; lane = j
+        if (lane < sz && lane >= i) ws[t0 + lane + (i64)i * ld] = Ts[warp][i][lane];
+}
+
+int32_t build_qr_plan(bbm_handle_t h, bbm_sky_desc_t d) {
+    bbm_sky_desc::Qr& q = d->qr;
+    if (q.built) return BBM_OK;
+    const i64 L = d->Nc > 0 ? d->l[0] : 0;
+    for (i64 J = 0; J < d->Nc; ++J)
+        if (d->l[J] != L) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "QR solve needs a uniform lower block bandwidth (BlockBandedMatrix factors)");
+    if (d->Nr < d->Nc) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "wide QR (fewer block rows than block columns) is not taken by the device path");
+    q.ncols = d->Nc;
+    const i64 P = q.ncols;
+    q.srows.assign(P, 0); q.vc.assign(P, 0); q.vt.assign(P, 0); q.g.assign(P, 0); q.tt.assign(P, 0); q.yt.assign(P, 0); q.xx.assign(P, 0);
+    auto even = [](i64 v) { return (v + 1) & ~i64(1); };
+    i64 off = 0;
+    std::vector<i64> pan((size_t)P * 6), blk;
+    // layout: [V | V' | YT] per panel, then [G], then [T'] (one contiguous range, zeroed per call), then [X]
+    for (i64 K = 0; K < P; ++K) {
+        if (d->c[K] > 0 && !sky_has(d, K, K)) return bbm_fail(h, BBM_ERR_BAND, "BandError: the factors have no diagonal block (%lld,%lld)", (long long)K, (long long)K);
+        const i64 K1 = std::min(K + L, d->Nr - 1);
+        const i64 S = d->R[K1 + 1] - d->R[K], c = d->c[K];
+        q.srows[K] = S;
+        q.vc[K] = off; off = even(off + S * c);
+        q.vt[K] = off; off = even(off + S * c);
+        q.yt[K] = off; off = even(off + S * c);
+        q.maxel = std::max(q.maxel, S * c);
+        pan[K * 6 + 0] = c > 0 ? sky_start(d, K, K) : 0; pan[K * 6 + 1] = d->S[K]; pan[K * 6 + 2] = S; pan[K * 6 + 3] = c;
+        pan[K * 6 + 4] = q.vc[K]; pan[K * 6 + 5] = q.vt[K];
+    }
+    for (i64 K = 0; K < P; ++K) { q.g[K] = off; off = even(off + d->c[K] * d->c[K]); }
+    q.tt_lo = off;
+    for (i64 K = 0; K < P; ++K) { q.tt[K] = off; off = even(off + d->c[K] * d->c[K]); }
+    q.tt_hi = off;
+    for (i64 K = 0; K < P; ++K) { q.xx[K] = off; off = even(off + d->c[K] * d->c[K]); }
+    q.total = off;
+    MmBatchHost gram, ytb;
+    std::vector<MmBatchHost> lev;
+    for (i64 K = 0; K < P; ++K) {
+        const i64 c = d->c[K], S = q.srows[K];
+        if (c == 0 || S == 0) continue;
+        gram.add(q.g[K], c, c, c, MmSeg{q.vt[K], c, q.vc[K], S, S});                 // G = V' V
+        ytb.add(q.yt[K], c, c, S, MmSeg{q.tt[K], c, q.vt[K], c, c});                 // YT = T' V'
+        for (i64 i0 = 0; i0 < c; i0 += 32) {
+            blk.push_back(q.g[K] + i0 + i0 * c); blk.push_back(c); blk.push_back(q.tt[K] + i0 + i0 * c);
+            blk.push_back(d->C[K] + i0); blk.push_back(std::min<i64>(32, c - i0));
+        }
+        int lv = 0;
+        for (i64 hh = 32; hh < c; hh *= 2, ++lv) {
+            if ((size_t)(2 * lv + 2) > lev.size()) lev.resize(2 * lv + 2);
+            for (i64 i0 = 0; i0 + hh < c; i0 += 2 * hh) {
+                const i64 h1 = hh, h2 = std::min(hh, c - i0 - hh);
+                const i64 lo = (i0 + hh) + i0 * c, dg = (i0 + hh) + (i0 + hh) * c;
+                lev[2 * lv].add(q.xx[K] + lo, c, h2, h1, MmSeg{q.g[K] + lo, c, q.tt[K] + i0 + i0 * c, c, h1});     // X = G21 T'11
+                lev[2 * lv + 1].add(q.tt[K] + lo, c, h2, h1, MmSeg{q.tt[K] + dg, c, q.xx[K] + lo, c, h2});        // T'21 = -T'22 X
+            }
+        }
+    }
+    q.nblk = (i64)blk.size() / 5;
+    int32_t rc = upload(h, pan, &q.d_pan);
+    if (rc == BBM_OK) rc = upload(h, blk, &q.d_blk);
+    if (rc == BBM_OK) rc = upload_batch(h, gram, &q.gram);
+    if (rc == BBM_OK) rc = upload_batch(h, ytb, &q.ytb);
+    q.levels.resize(lev.size());
+    for (size_t i = 0; i < lev.size() && rc == BBM_OK; ++i) rc = upload_batch(h, lev[i], &q.levels[i]);
+    if (rc != BBM_OK) return rc;
+    q.built = true;
+    return BBM_OK;
+}
+
+int32_t build_qr_step_plan(bbm_handle_t h, bbm_sky_desc_t d, i64 ldb, i64 ldw, i64 nrhs) {
+    bbm_sky_desc::Qr& q = d->qr;
+    if (q.step_ldb == ldb && q.step_nrhs == nrhs && q.step_ldw == ldw && q.stepW.tiles) return BBM_OK;
+    MmBatchHost w, b;
+    const i64 P = q.ncols, ksplit = 64;
+    q.ptrW.assign(P + 1, 0); q.ptrB.assign(P + 1, 0);
+    for (i64 K = 0; K < P; ++K) {
+        q.ptrW[K] = (int)w.tiles.size();
+        q.ptrB[K] = (int)b.tiles.size();
+        const i64 c = d->c[K], S = q.srows[K];
+        if (c == 0 || S == 0) continue;
+        for (i64 k0 = 0; k0 < S; k0 += ksplit)   // W_K += YT_K[:, k-slice] B[R_K + k-slice, :]
+            w.add(d->C[K], ldw, c, nrhs, MmSeg{q.yt[K] + k0 * c, c, d->R[K] + k0, ldb, std::min(ksplit, S - k0)});
+        for (i64 k0 = 0; k0 < c; k0 += ksplit)   // B[KR, :] -= V_K[:, k-slice] W_K[k-slice, :]
+            b.add(d->R[K], ldb, S, nrhs, MmSeg{q.vc[K] + k0 * S, S, d->C[K] + k0, ldw, std::min(ksplit, c - k0)});
+    }
+    q.ptrW[P] = (int)w.tiles.size();
+    q.ptrB[P] = (int)b.tiles.size();
+    int32_t rc = upload_batch(h, w, &q.stepW);
+    if (rc == BBM_OK) rc = upload_batch(h, b, &q.stepB);
+    if (rc != BBM_OK) return rc;
+    q.step_ldb = ldb; q.step_nrhs = nrhs; q.step_ldw = ldw;
+    return BBM_OK;
+}
+
+int32_t sky_qr_lmul_adj_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_fac, const double* d_tau, double* d_B, i64 ldb, i64 nrhs) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && ldb < std::max<i64>(1, d->m)) return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: Q is %lld x %lld, ldb=%lld", (long long)d->m, (long long)d->m, (long long)ldb);
+    if (d->m == 0 || d->n == 0 || nrhs == 0) return BBM_OK;
+    if (!d_fac || !d_tau || !d_B) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    int32_t rc = build_qr_plan(h, d);
+    if (rc != BBM_OK) return rc;
+    bbm_sky_desc::Qr& q = d->qr;
+    const i64 ldw = std::max<i64>(2, (d->n + 1) & ~i64(1));
+    rc = build_qr_step_plan(h, d, ldb, ldw, nrhs);
+    if (rc == BBM_OK) rc = bbm_ws_reserve(h, &h->ws_z, &h->ws_z_bytes, (size_t)q.total * sizeof(double));
+    if (rc == BBM_OK) rc = bbm_ws_reserve(h, &h->ws_y, &h->ws_y_bytes, (size_t)ldw * nrhs * sizeof(double));
+    if (rc != BBM_OK) return rc;
+    double* WS = static_cast<double*>(h->ws_z);
+    double* W = static_cast<double*>(h->ws_y);
+    BBM_CUDA(h, cudaMemsetAsync(WS + q.tt_lo, 0, (size_t)(q.tt_hi - q.tt_lo) * sizeof(double), h->stream));
+    BBM_CUDA(h, cudaMemsetAsync(W, 0, (size_t)ldw * nrhs * sizeof(double), h->stream));
+    // compact-WY form of all panels, in parallel
+    const unsigned gx = (unsigned)std::min<i64>(64, (q.maxel + 255) / 256);
+    sky_qr_extract_kernel<<<dim3(std::max(1u, gx), (unsigned)q.ncols), 256, 0, h->stream>>>(d_fac, q.d_pan, WS);
+    h->launches += 1;
+    rc = launch_mm64(h, q.gram, 0, q.gram.ntiles, WS, WS, WS, 1.0, 0.0, false);
+    if (rc != BBM_OK) return rc;
+    if (q.nblk > 0) {
+        sky_qr_t32_kernel<<<(unsigned)((q.nblk + 1) / 2), 64, 0, h->stream>>>(d_tau, q.d_blk, q.nblk, WS);
+        h->launches += 1;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "QR compact-WY kernels: %s", cudaGetErrorString(e));
+    for (size_t lv = 0; lv + 1 < q.levels.size(); lv += 2) {
+        rc = launch_mm64(h, q.levels[lv], 0, q.levels[lv].ntiles, WS, WS, WS, 1.0, 0.0, false);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.levels[lv + 1], 0, q.levels[lv + 1].ntiles, WS, WS, WS, -1.0, 0.0, false);
+        if (rc != BBM_OK) return rc;
+    }
+    rc = launch_mm64(h, q.ytb, 0, q.ytb.ntiles, WS, WS, WS, 1.0, 0.0, false);
+    if (rc != BBM_OK) return rc;
+    // the sequential sweep over the panels
+    const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
+    for (i64 K = 0; K < q.ncols; ++K) {
+        rc = launch_mm64(h, q.stepW, q.ptrW[K], q.ptrW[K + 1] - q.ptrW[K], WS, d_B, W, 1.0, 1.0, true, K < 2, pdl);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.stepB, q.ptrB[K], q.ptrB[K + 1] - q.ptrB[K], WS, W, d_B, -1.0, 1.0, true, K < 2, pdl);
+        if (rc != BBM_OK) return rc;
+    }
+    return BBM_OK;
+}
+
 template <typename T>
 int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs) {
     BBM_REQUIRE_HANDLE(h);
@@ -1233,6 +1442,10 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         free_batch(d->tri[t].stepA);
         free_batch(d->tri[t].stepB);
     }
+    if (d->qr.d_pan) cudaFree(d->qr.d_pan);
+    if (d->qr.d_blk) cudaFree(d->qr.d_blk);
+    free_batch(d->qr.gram); free_batch(d->qr.ytb); free_batch(d->qr.stepW); free_batch(d->qr.stepB);
+    for (auto& b : d->qr.levels) free_batch(b);
     for (auto& kv : d->plans) free_plan(kv.second);
     d->magic = 0;
     delete d;
@@ -1272,6 +1485,21 @@ int32_t bbm_sky_matmul_f64(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, b
 int32_t bbm_sky_matmul_f32(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, float alpha, const float* dA,
                            const float* dB, float beta, float* dC) {
     return sky_matmul_impl<float>(h, A, B, C, alpha, dA, dB, beta, dC);
+}
+int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,
+                                int64_t nrhs) {
+    return sky_qr_lmul_adj_impl(h, d, d_factors, d_tau, d_B, ldb, nrhs);
+}
+int32_t bbm_sky_qr_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,
+                            int64_t nrhs) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    bool match = d->Nr == d->Nc;
+    for (i64 K = 0; match && K < d->Nr; ++K) match = d->r[K] == d->c[K];
+    if (!match) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "QR solve on the device needs a square matrix with matching diagonal blocks");
+    int32_t rc = sky_qr_lmul_adj_impl(h, d, d_factors, d_tau, d_B, ldb, nrhs);
+    if (rc != BBM_OK) return rc;
+    return sky_trsm_impl<double>(h, d, 'U', 0, d_factors, d_B, ldb, nrhs);
 }
 int32_t bbm_sky_trsm_f64(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const double* d_data, double* d_B,
                          int64_t ldb, int64_t nrhs) {

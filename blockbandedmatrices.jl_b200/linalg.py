@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from .device import DeviceArray
-from .matrices import Adjoint, BandedBlockBandedMatrix, BlockSkylineMatrix, _Triangular
+from .matrices import Adjoint, BandedBlockBandedMatrix, BlockBandedQR, BlockSkylineMatrix, _Triangular
 
 _SUF = {np.dtype(np.float64): ("f64", C.c_double), np.dtype(np.float32): ("f32", C.c_float)}
 
@@ -253,8 +253,35 @@ def _sky_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
     return Cm
 
 
+def _qr_call(name, F, B):
+    A = F.factors
+    h = _require_device(A)
+    if not isinstance(B, DeviceArray) or not isinstance(F.tau, DeviceArray):
+        raise TypeError("the right-hand side and tau must be device arrays")
+    br, _bc = _vec_dims(B, "B")
+    if br != A.shape[0]:
+        raise L.DimensionMismatch(f"Q is {A.shape[0]} x {A.shape[0]}, B is {B.shape}")
+    if A.dtype != np.float64 or np.dtype(B.dtype) != np.float64 or np.dtype(F.tau.dtype) != np.float64:
+        raise TypeError("the device QR solve takes Float64 operands only")
+    rc = getattr(h._lib, name)(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(F.tau.ptr), C.c_void_p(B.ptr), _ld(B), _bc)
+    L.check(rc, h.h, name)
+    return B
+
+
+def lmul_adj_(F, B):
+    """``lmul!(F.Q', B)`` for a block-banded QR: B <- Q' B in place (src/blockskylineqr.jl:77-127)."""
+    if not isinstance(F, BlockBandedQR):
+        raise TypeError("lmul_adj_ takes a BlockBandedQR")
+    return _qr_call("bbm_sky_qr_lmul_adj_f64", F, B)
+
+
 def ldiv_(T, B):
-    """``ldiv!(UpperTriangular(A), B)`` etc.: B <- T^-1 B in place on the device, returns B."""
+    """``ldiv!(UpperTriangular(A), B)`` etc.: B <- T^-1 B in place on the device, returns B.
+    ``ldiv!(F, B)`` for a square ``BlockBandedQR`` (src/blockskylineqr.jl:131-145): Q' B, then the triangular solve."""
+    if isinstance(T, BlockBandedQR):
+        if T.shape[0] != T.shape[1]:
+            raise L.DimensionMismatch(f"F is {T.shape}: the device path solves square systems")
+        return _qr_call("bbm_sky_qr_ldiv_f64", T, B)
     if not isinstance(T, _Triangular) or not isinstance(T.parent, (BlockSkylineMatrix, BandedBlockBandedMatrix)):
         raise TypeError("ldiv! takes Upper/LowerTriangular wrappers of a BlockSkylineMatrix or BandedBlockBandedMatrix")
     A = T.parent
@@ -276,7 +303,7 @@ def ldiv_(T, B):
 
 def ldiv(T, B):
     """``T \\ B``: solves into a copy of B."""
-    h = _require_device(T.parent)
+    h = _require_device(T.factors if isinstance(T, BlockBandedQR) else T.parent)
     X = h.empty(B.shape, B.dtype)
     L.check(h._lib.bbm_memcpy_d2d(h.h, C.c_void_p(X.ptr), C.c_void_p(B.ptr), B.nbytes), h.h)
     return ldiv_(T, X)

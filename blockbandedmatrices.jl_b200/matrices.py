@@ -454,6 +454,28 @@ class _Triangular:
         return (l, u)
 
 
+class BlockBandedQR:
+    """``F = qr(A)`` of a BlockBandedMatrix as the reference stores it (``MatrixFactorizations.QR{T,<:BlockSkylineMatrix}``,
+    src/blockskylineqr.jl:45-49): ``factors`` is block-skyline with block bandwidths ``(l, l+u)`` -- R in and above
+    the diagonal blocks, the Householder vectors of panel K below them -- and ``tau`` the reflector scalars.
+    The factorisation is the reference's host-side ``qr!``; this wrapper only carries a device-resident copy of
+    its result to ``lmul_adj_`` (``lmul!(F.Q', B)``) and ``ldiv_`` (``ldiv!(F, B)`` / ``F \\ B``)."""
+
+    def __init__(self, factors: "BlockSkylineMatrix", tau):
+        n_tau = int(factors.C[-1]) if len(factors.rows) >= len(factors.cols) else int(factors.R[-1])
+        if int(np.prod(tau.shape)) != n_tau:
+            raise L.DimensionMismatch(f"tau has {tau.shape} entries, the factors need {n_tau}")
+        self.factors, self.tau = factors, tau
+
+    @property
+    def shape(self):
+        return self.factors.shape
+
+    def to_device(self, handle: Handle) -> "BlockBandedQR":
+        t = self.tau if isinstance(self.tau, DeviceArray) else handle.to_device(np.ascontiguousarray(self.tau))
+        return BlockBandedQR(self.factors.to_device(handle), t)
+
+
 class Adjoint:
     """``A'`` / ``transpose(A)`` of a real BandedBlockBandedMatrix: reversed bandwidths
     (src/adjtransblockbanded.jl:2-3), products through the transposed kernel."""

@@ -210,6 +210,19 @@ int32_t bbm_sky_trsm_f64(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t
 int32_t bbm_sky_trsm_f32(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const float* d_data,
                          float* d_B, int64_t ldb, int64_t nrhs);
 
+/* lmul!(F.Q', B) and ldiv!(F, B) for F = qr(A) of a BlockBandedMatrix (src/blockskylineqr.jl:77-127 and :131-145;
+ * test/test_blockskylineqr.jl:29-34).  `d` describes F.factors -- block-skyline with bandwidths (l, l+u), R in and
+ * above the diagonal blocks, the Householder vectors of panel K below them in block rows K..K+l (LAPACK packing) --
+ * d_tau is F.tau (length n).  The factorisation itself stays where the reference computes it (qr! on the host, one
+ * LAPACK panel after the other); these calls replace the per-panel ormqr + the triangular solve: every panel is
+ * brought into compact-WY form in parallel, then two tensor-core products per panel run in sequence.
+ * Float64; at least as many block rows as block columns; bbm_sky_qr_ldiv needs a square matrix with matching
+ * diagonal blocks (BBM_ERR_UNSUPPORTED otherwise: the call falls through to the reference).  In place on B.  */
+int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
+                                double* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_sky_qr_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
+                            double* d_B, int64_t ldb, int64_t nrhs);
+
 /* ---- several GPUs: row-block partition + halo exchange ------------------------------------
  * One process per GPU.  Block rows are split into contiguous ranges (the reference's one
  * data-parallel strategy, examples/shared_array_backend.jl:92-122, partition :106-107); rank p owns
