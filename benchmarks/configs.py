@@ -290,6 +290,115 @@ def run_cfg5(torch, B, h, stream, reps, oracle, nblk=1024, bs=512, nrhs=64, peak
     return out
 
 
+def host_block_banded_qr(F, rows, cols, l, u, data):
+    """qr! of a block-banded matrix on the host with LAPACK (scipy dgeqrf per panel, dormqr on the trailing blocks):
+    the loop of src/blockskylineqr.jl:29-43 on the skyline storage `data` of the (l, l+u) factors, in place."""
+    from scipy.linalg import lapack
+    as_strided = np.lib.stride_tricks.as_strided
+    off, S, klo, khi = F.sky_layout(rows, cols, l, l + u)
+    R = np.concatenate([[0], np.cumsum(rows)]); N = len(cols)
+    tau = np.zeros(int(np.sum(cols)))
+    C0 = np.concatenate([[0], np.cumsum(cols)])
+    it = data.itemsize
+    for K in range(N):
+        K1 = min(K + l, len(rows) - 1)
+        Sr, c = int(R[K1 + 1] - R[K]), int(cols[K])
+        V = as_strided(data[int(off[K] + R[K] - R[klo[K]]):], shape=(Sr, c), strides=(it, it * int(S[K])))
+        qr_, t_, _, info = lapack.dgeqrf(np.asfortranarray(V))
+        assert info == 0
+        V[:, :] = qr_
+        tau[C0[K]:C0[K] + len(t_)] = t_
+        for J in range(K + 1, min(K + l + u, N - 1) + 1):
+            Bv = as_strided(data[int(off[J] + R[K] - R[klo[J]]):], shape=(Sr, int(cols[J])), strides=(it, it * int(S[J])))
+            cq, _, info = lapack.dormqr("L", "T", qr_, t_, np.asfortranarray(Bv), max(64, 64 * int(cols[J])))
+            assert info == 0
+            Bv[:, :] = cq
+    return tau
+
+
+def host_qr_solve(F, rows, l, u, data, tau, Bm, O):
+    """ldiv!(F, B) on the host: dormqr per panel (src/blockskylineqr.jl:77-127), then the block triangular solve"""
+    from scipy.linalg import lapack
+    as_strided = np.lib.stride_tricks.as_strided
+    off, S, klo, khi = F.sky_layout(rows, rows, l, l + u)
+    R = np.concatenate([[0], np.cumsum(rows)]); N = len(rows)
+    it = data.itemsize
+    for K in range(N):
+        K1 = min(K + l, N - 1)
+        Sr, c = int(R[K1 + 1] - R[K]), int(rows[K])
+        V = np.asfortranarray(as_strided(data[int(off[K] + R[K] - R[klo[K]]):], shape=(Sr, c), strides=(it, it * int(S[K]))))
+        cq, _, info = lapack.dormqr("L", "T", V, tau[R[K]:R[K] + min(Sr, c)], np.asfortranarray(Bm[R[K]:R[K1 + 1], :]), max(64, 64 * Bm.shape[1]))
+        assert info == 0
+        Bm[R[K]:R[K1 + 1], :] = cq
+    O.sky_trsm(rows, l, l + u, "U", False, data, Bm)
+    return Bm
+
+
+def run_qr(torch, B, h, stream, reps, oracle, nblk=512, bs=256, nrhs=64, peak_tf=None):
+    """F = qr(A) on the host (as the reference does), F \\ B on the device: BlockBandedMatrix nblk blocks of bs, (1,1)."""
+    from oracle import formats as F
+    from oracle import cpu as O
+    rows = [bs] * nblk
+    l, u = 1, 1
+    rng = np.random.default_rng(1011)
+    nA = F.sky_numentries(rows, rows, l, l + u)
+    data = np.zeros(nA)
+    off, S, klo, khi = F.sky_layout(rows, rows, l, l + u)
+    Rr = np.concatenate([[0], np.cumsum(rows)])
+    # A with bandwidths (1,1) inside the (1,2) factor structure: fill blocks K-1..K+1 of every block column
+    for J in range(nblk):
+        ld = int(S[J])
+        pan = data[int(off[J]):int(off[J]) + ld * bs].reshape((ld, bs), order="F")
+        lo = int(Rr[max(J - u, 0)] - Rr[klo[J]])
+        pan[lo:, :] = rng.standard_normal((ld - lo, bs)) / np.sqrt(3 * bs)
+        dg = int(Rr[J] - Rr[klo[J]])
+        pan[dg + np.arange(bs), np.arange(bs)] += 2.0
+    Adata = data.copy()
+    t0 = time.perf_counter()
+    tau = host_block_banded_qr(F, rows, rows, l, u, data)
+    t_fact = time.perf_counter() - t0
+    m = bs * nblk
+    B0 = np.asfortranarray(rng.standard_normal((m, nrhs)))
+    Fd = B.BlockBandedQR(B.BlockSkylineMatrix(data, rows, rows, l, l + u), tau).to_device(h)
+    b0_t = torch.from_numpy(np.ascontiguousarray(B0.T)).cuda()        # (nrhs, m) row-major == m x nrhs column-major
+    b_t = b0_t.clone()
+    dB = wrap(B, h, b_t)
+
+    def step():
+        b_t.copy_(b0_t)
+        B.ldiv_(Fd, dB)
+
+    def step_q():
+        b_t.copy_(b0_t)
+        B.lmul_adj_(Fd, dB)
+
+    with torch.cuda.stream(stream):
+        cavg, _ = time_gpu(torch, stream, lambda: b_t.copy_(b0_t), 5, warm=1)
+    qavg, _ = time_gpu(torch, stream, step_q, reps, warm=1)
+    avg, best = time_gpu(torch, stream, step, reps, warm=1)
+    h.synchronize()
+    X = b_t.cpu().numpy().T
+    out = {"config": f"qr: F \\ B for F = qr(BlockBandedMatrix {nblk} blocks of {bs}, (1,1)) computed on the host, {nrhs} RHS, Float64",
+           "host_qr_seconds_lapack": t_fact, "ms_ldiv": avg - cavg, "ms_lmul_adj": qavg - cavg, "us_per_panel_lmul_adj": (qavg - cavg) * 1e3 / nblk,
+           "tolerance": 64 * EPS[8] * 4 * bs}
+    # residual against the original matrix: A X = B
+    Ad = B.BlockSkylineMatrix(Adata, rows, rows, l, l + u).to_device(h)
+    back = h.empty((m, nrhs), np.float64)
+    B.mul_(back, Ad, wrap(B, h, b_t))
+    h.synchronize()
+    out["residual_rel_AX_minus_B"] = relerr(back.to_host(), B0)
+    if oracle:
+        O.use_openblas(threads=os.cpu_count() or 1)
+        ref = B0.copy(order="F")
+        t0 = time.perf_counter()
+        host_qr_solve(F, rows, l, u, data, tau, ref, O)
+        out["cpu_seconds_ldiv_lapack"] = time.perf_counter() - t0
+        O.use_builtin()
+        out["rel_err_vs_host_lapack"] = relerr(X, ref)
+        out["parity_ok"] = bool(out["rel_err_vs_host_lapack"] <= out["tolerance"])
+    return out
+
+
 def run_bbb_tri(torch, B, h, stream, reps, oracle, n=4096):
     """Gauss-Seidel sweep of examples/finitedifference_2d.jl: (D+L) \\ b and (D+U) \\ b on the n^2 Laplacian."""
     A = B.BandedBlockBandedMatrix.finitedifference_2d(n)
@@ -358,6 +467,8 @@ def main():
         print(json.dumps(run_cfg4(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
     if "bbbmm" in want:
         print(json.dumps(run_bbb_mm(torch, B, h, stream, args.reps, oracle)), flush=True)
+    if "qr" in want:
+        print(json.dumps(run_qr(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
     if "bbbtri" in want:
         print(json.dumps(run_bbb_tri(torch, B, h, stream, max(2, args.reps // 3), oracle)), flush=True)
     if "4mv" in want:

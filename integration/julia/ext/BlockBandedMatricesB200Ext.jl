@@ -237,6 +237,25 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
     end
 end
 
+# ldiv!(F, B) / lmul!(F.Q', B) for F = qr(A) computed by the reference on the host and moved with b200(F):
+# src/blockskylineqr.jl:77-127 (Q'B panel by panel) and :131-145 (then the triangular solve).  Float64.
+b200(F::MatrixFactorizations.QR{Float64,<:BlockSkylineMatrix}) = MatrixFactorizations.QR(b200(F.factors), B200Array(F.τ))
+function LinearAlgebra.ldiv!(F::MatrixFactorizations.QR{Float64,<:B200Sky{Float64}}, B::B200Array{Float64})
+    A = F.factors
+    size(A, 1) == size(B, 1) || throw(DimensionMismatch("F has size $(size(A)), B has size $(size(B))"))
+    rc = ccall((:bbm_sky_qr_ldiv_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+               handle().ptr, descriptor(A), A.data.ptr, F.τ.ptr, B.ptr, ld(B), size(B, 2))
+    rc == BBM_ERR_UNSUPPORTED && error("thin/wide block-banded QR solves stay on the host: use Array(B)")
+    check(rc)
+    B
+end
+function LinearAlgebra.lmul!(adjQ::Adjoint{Float64,<:MatrixFactorizations.QRPackedQ{Float64,<:B200Sky{Float64}}}, B::B200Array{Float64})
+    Q = parent(adjQ)
+    check(ccall((:bbm_sky_qr_lmul_adj_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+                handle().ptr, descriptor(Q.factors), Q.factors.data.ptr, Q.τ.ptr, B.ptr, ld(B), size(B, 2)))
+    B
+end
+
 synchronize() = check(ccall((:bbm_synchronize, libbbm), Int32, (Ptr{Cvoid},), handle().ptr))
 
 end # module
