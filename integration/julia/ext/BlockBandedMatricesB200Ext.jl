@@ -26,6 +26,7 @@ using BlockBandedMatrices.ArrayLayouts: MulAdd, Ldiv, TriangularLayout, MemoryLa
 import BlockBandedMatrices.ArrayLayouts: materialize!, triangulardata
 using BlockBandedMatrices.BlockArrays: BlockedMatrix, blocklengths, blocksize
 using BlockBandedMatrices.BandedMatrices: BandError
+import BlockBandedMatrices.MatrixFactorizations
 using LinearAlgebra
 import BBMB200: libbbm
 
