@@ -86,6 +86,16 @@ struct bbm_sky_desc {
         Tri::Batch stepW, stepB;             // the sweep; tiles of panel K are [ptr[K], ptr[K+1])
         std::vector<int> ptrW, ptrB;
     } qr;
+    // qr! plan (Float64): sub-panels of nb reflectors; tiles of step t are [ptr[t], ptr[t+1])
+    struct QrFact {
+        bool built = false;
+        int nb = 32;
+        i64 nsteps = 0, maxrows = 0, ws_total = 0;
+        i64 slotV[2] = {0, 0}, slotY[2] = {0, 0}, slotW[2] = {0, 0};
+        i64* d_steps = nullptr;              // per step: slab start, ld, rows, width, tau offset, parity
+        Tri::Batch bW, bC;
+        std::vector<int> ptrW, ptrC;
+    } qrf;
     // product plans keyed by the serials of (A, B), owned by the C descriptor
     struct MmPlan;
     std::map<std::pair<uint64_t, uint64_t>, MmPlan*> plans;
@@ -1248,6 +1258,246 @@ int32_t sky_qr_lmul_adj_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_f
     return BBM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// qr!(A) for a BlockBandedMatrix already widened to the factors' bandwidths (l, l+u)
+// (_blockbanded_qr!, src/blockskylineqr.jl:29-43): for every block column K, Householder QR of the panel
+// V = A[K..K+l, K] and Q_K' applied to the blocks to its right.  The reference does the panel with the
+// unblocked algorithm and the rest with ormqr; here a panel is processed in sub-panels of nb <= 32 columns:
+//   sky_qr_panel_kernel  one CTA holds the (rows x nb) slab in shared memory, runs the nb reflector steps there
+//                        (same reflector convention as LinearAlgebra.reflector!: nu = copysign(|x|, x0), ...),
+//                        writes R / v / tau back in place and leaves the slab's compact-WY pieces V and
+//                        YT = T' V' in a workspace slot;
+//   two batched DMMA launches apply it to everything to the right (rest of the panel + trailing blocks):
+//                        W = YT C,   C -= V W.
+// The tile tables of all steps are built once per descriptor.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) sky_qr_panel_kernel(double* __restrict__ data, double* __restrict__ tau, const i64* __restrict__ steps,
+                                                          i64 step, double* __restrict__ ws, i64 slotV0, i64 slotV1, i64 slotY0, i64 slotY1) {
+    extern __shared__ __align__(16) unsigned char qr_smem[];
+    const i64* st = steps + step * 6;
+    const i64 a0 = st[0], ld = st[1];
+    const int rows = (int)st[2], w = (int)st[3];
+    const i64 tau0 = st[4];
+    const int par = (int)st[5];
+    const int lds = rows | 1;                       // odd leading dimension: rows of one column hit all banks
+    double* As = reinterpret_cast<double*>(qr_smem);            // [w][lds]
+    double* Ts = As + (size_t)w * lds;                           // [32][33]  T (upper)
+    double* Gs = Ts + 32 * 33;                                   // [32][33]  V'V
+    double* red = Gs + 32 * 33;                                  // [8] + scalars
+    double* sc = red + 8;                                        // [0] xi1, [1] tau
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < rows * w; idx += 256) {
+        const int r = idx % rows, c = idx / rows;
+        As[r + c * lds] = data[a0 + r + (i64)c * ld];
+    }
+    __syncthreads();
+    for (int jj = 0; jj < w; ++jj) {
+        double* x = As + jj + jj * lds;
+        const int n = rows - jj;
+        if (n <= 1) {                                // real element type: nothing to annihilate in the last row
+            if (tid == 0 && n == 1) tau[tau0 + jj] = 0.0;
+            continue;
+        }
+        double ss = 0.0;
+        for (int r = tid; r < n; r += 256) ss = fma(x[r], x[r], ss);
+        ss = block_sum_256(ss, red);
+        if (tid == 0) {
+            const double normu = sqrt(ss);
+            double tj = 0.0, xi1 = 1.0;
+            if (normu != 0.0) {
+                xi1 = x[0];
+                const double nu = copysign(normu, xi1);
+                xi1 += nu;
+                x[0] = -nu;
+                tj = xi1 / nu;
+            }
+            sc[0] = xi1; sc[1] = tj;
+            tau[tau0 + jj] = tj;
+        }
+        __syncthreads();
+        const double xi1 = sc[0], tj = sc[1];
+        if (tj != 0.0)
+            for (int r = 1 + tid; r < n; r += 256) x[r] /= xi1;
+        __syncthreads();
+        if (tj != 0.0) {
+            for (int t = jj + 1 + warp; t < w; t += 8) {     // reflectorApply!: one warp per remaining column
+                double* a = As + jj + t * lds;
+                double v = 0.0;
+                for (int r = 1 + lane; r < n; r += 32) v = fma(x[r], a[r], v);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                v = tj * (v + a[0]);
+                __syncwarp();
+                if (lane == 0) a[0] -= v;
+                for (int r = 1 + lane; r < n; r += 32) a[r] = fma(-x[r], v, a[r]);
+            }
+        }
+        __syncthreads();
+    }
+    // R and the Householder vectors go back in place
+    for (int idx = tid; idx < rows * w; idx += 256) {
+        const int r = idx % rows, c = idx / rows;
+        data[a0 + r + (i64)c * ld] = As[r + c * lds];
+    }
+    __syncthreads();
+    // clean V in shared memory (zeros above, ones on the diagonal), Gram matrix, T, then V and YT = T'V' out
+    for (int idx = tid; idx < rows * w; idx += 256) {
+        const int r = idx % rows, c = idx / rows;
+        if (r < c) As[r + c * lds] = 0.0;
+        else if (r == c) As[r + c * lds] = 1.0;
+    }
+    __syncthreads();
+    for (int pq = warp; pq < w * w; pq += 8) {
+        const int i = pq / w, j = pq % w;
+        if (i > j) continue;
+        double v = 0.0;
+        for (int r = j + lane; r < rows; r += 32) v = fma(As[r + i * lds], As[r + j * lds], v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) Gs[i * 33 + j] = v;
+    }
+    for (int idx = tid; idx < 32 * 33; idx += 256) Ts[idx] = 0.0;
+    __syncthreads();
+    if (warp == 0) {
+        for (int j = 0; j < w; ++j) {
+            const double tj = (rows - j <= 1) ? 0.0 : tau[tau0 + j];   // written above by thread 0 of this CTA
+            double sum = 0.0;
+            if (lane < j)
+                for (int k = lane; k < j; ++k) sum = fma(Ts[lane * 33 + k], Gs[k * 33 + j], sum);
+            __syncwarp();
+            if (lane < j) Ts[lane * 33 + j] = -tj * sum;
+            if (lane == j) Ts[j * 33 + j] = tj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* Vout = ws + (par ? slotV1 : slotV0);   // rows x w, ld = rows
+    double* Yout = ws + (par ? slotY1 : slotY0);   // w x rows, ld = w
+    for (int idx = tid; idx < rows * w; idx += 256) {
+        const int r = idx % rows, c = idx / rows;
+        Vout[idx] = As[r + c * lds];
+    }
+    for (int r = tid; r < rows; r += 256) {
+        for (int i = 0; i < w; ++i) {              // YT[i, r] = sum_{k <= i} T[k, i] V[r, k]
+            double v = 0.0;
+            for (int k = 0; k <= i; ++k) v = fma(Ts[k * 33 + i], As[r + k * lds], v);
+            Yout[i + (i64)r * w] = v;
+        }
+    }
+}
+
+int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
+    bbm_sky_desc::QrFact& q = d->qrf;
+    if (q.built) return BBM_OK;
+    const i64 L = d->Nc > 0 ? d->l[0] : 0, U = d->Nc > 0 ? d->u[0] : 0;
+    for (i64 J = 0; J < d->Nc; ++J)
+        if (d->l[J] != L || d->u[J] != U) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "qr! needs uniform block bandwidths (BlockBandedMatrix)");
+    const i64 P = std::min(d->Nr, d->Nc);
+    i64 maxS = 0, maxcols = 0;
+    for (i64 K = 0; K < P; ++K) {
+        if (d->c[K] > 0 && d->r[K] > 0 && !sky_has(d, K, K)) return bbm_fail(h, BBM_ERR_BAND, "BandError: no diagonal block (%lld,%lld)", (long long)K, (long long)K);
+        const i64 K1 = std::min(K + L, d->Nr - 1);
+        maxS = std::max(maxS, d->R[K1 + 1] - d->R[K]);
+        i64 cols = 0;
+        for (i64 J = K; J <= std::min(K + U, d->Nc - 1); ++J) cols += d->c[J];
+        maxcols = std::max(maxcols, cols);
+    }
+    q.nb = maxS <= 704 ? 32 : maxS <= 1472 ? 16 : 8;
+    if ((size_t)q.nb * (maxS | 1) * 8 + 2 * 32 * 33 * 8 + 128 > std::min<size_t>(h->smem_optin, 220 * 1024))
+        return bbm_fail(h, BBM_ERR_UNSUPPORTED, "qr!: panels of %lld rows exceed the shared-memory slab", (long long)maxS);
+    q.maxrows = maxS;
+    auto even = [](i64 v) { return (v + 1) & ~i64(1); };
+    i64 off = 0;
+    for (int p = 0; p < 2; ++p) {
+        q.slotV[p] = off; off = even(off + maxS * q.nb);
+        q.slotY[p] = off; off = even(off + maxS * q.nb);
+        q.slotW[p] = off; off = even(off + (i64)q.nb * maxcols);
+    }
+    q.ws_total = off;
+    std::vector<i64> steps;
+    MmBatchHost bw, bc;
+    q.ptrW.clear(); q.ptrC.clear();
+    i64 nsteps = 0;
+    for (i64 K = 0; K < P; ++K) {
+        const i64 K1 = std::min(K + L, d->Nr - 1);
+        const i64 S = d->R[K1 + 1] - d->R[K], c = d->c[K];
+        if (S == 0 || c == 0) continue;
+        const i64 vstart = sky_start(d, K, K), ld = d->S[K];
+        for (i64 j0 = 0; j0 < std::min(S, c); j0 += q.nb) {
+            const i64 w = std::min<i64>(q.nb, std::min(S, c) - j0), rows = S - j0;
+            const int par = (int)(nsteps & 1);
+            steps.insert(steps.end(), {vstart + j0 + j0 * ld, ld, rows, w, d->C[K] + j0, (i64)par});
+            q.ptrW.push_back((int)bw.tiles.size());
+            q.ptrC.push_back((int)bc.tiles.size());
+            i64 woff = q.slotW[par];
+            auto piece = [&](i64 cstart, i64 ldc, i64 cols) {   // rows x cols target with top-left at data[cstart]
+                if (cols <= 0) return;
+                bw.add(woff, w, w, cols, MmSeg{q.slotY[par], w, cstart, ldc, rows});          // W = YT C
+                bc.add(cstart, ldc, rows, cols, MmSeg{q.slotV[par], rows, woff, w, w});       // C -= V W
+                woff += w * cols;
+            };
+            piece(vstart + j0 + (j0 + w) * ld, ld, c - j0 - w);                              // rest of the panel
+            for (i64 J = K + 1; J <= std::min(K + U, d->Nc - 1); ++J) {
+                if (d->c[J] == 0) continue;
+                if (!sky_has(d, K, J) || !sky_has(d, K1, J)) return bbm_fail(h, BBM_ERR_BAND, "BandError: the factors structure must have upper block bandwidth l+u");
+                piece(sky_start(d, K, J) + j0, d->S[J], d->c[J]);
+            }
+            ++nsteps;
+        }
+    }
+    q.ptrW.push_back((int)bw.tiles.size());
+    q.ptrC.push_back((int)bc.tiles.size());
+    q.nsteps = nsteps;
+    int32_t rc = upload(h, steps, &q.d_steps);
+    if (rc == BBM_OK) rc = upload_batch(h, bw, &q.bW);
+    if (rc == BBM_OK) rc = upload_batch(h, bc, &q.bC);
+    if (rc != BBM_OK) return rc;
+    q.built = true;
+    return BBM_OK;
+}
+
+int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    const i64 ntau = d->Nr < d->Nc ? d->m : d->n;
+    if (ntau == 0) return BBM_OK;
+    if (!d_data || !d_tau) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    int32_t rc = build_qr_fact_plan(h, d);
+    if (rc != BBM_OK) return rc;
+    bbm_sky_desc::QrFact& q = d->qrf;
+    rc = bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, (size_t)q.ws_total * sizeof(double));
+    if (rc != BBM_OK) return rc;
+    double* WS = static_cast<double*>(h->ws_w);
+    BBM_CUDA(h, cudaMemsetAsync(d_tau, 0, (size_t)ntau * sizeof(double), h->stream));
+    const size_t smem = ((size_t)q.nb * (q.maxrows | 1) + 2 * 32 * 33 + 16) * sizeof(double);
+    BBM_CUDA(h, cudaFuncSetAttribute(sky_qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
+    for (i64 t = 0; t < q.nsteps; ++t) {
+        sky_qr_panel_kernel<<<1, 256, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1]);
+        h->launches += 1;
+        rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 0.0, false, t < 2, pdl);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
+        if (rc != BBM_OK) return rc;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_qr_panel_kernel: %s", cudaGetErrorString(e));
+    return BBM_OK;
+}
+
 template <typename T>
 int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs) {
     BBM_REQUIRE_HANDLE(h);
@@ -1442,6 +1692,8 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         free_batch(d->tri[t].stepA);
         free_batch(d->tri[t].stepB);
     }
+    if (d->qrf.d_steps) cudaFree(d->qrf.d_steps);
+    free_batch(d->qrf.bW); free_batch(d->qrf.bC);
     if (d->qr.d_pan) cudaFree(d->qr.d_pan);
     if (d->qr.d_blk) cudaFree(d->qr.d_blk);
     free_batch(d->qr.gram); free_batch(d->qr.ytb); free_batch(d->qr.stepW); free_batch(d->qr.stepB);
@@ -1486,6 +1738,7 @@ int32_t bbm_sky_matmul_f32(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, b
                            const float* dB, float beta, float* dC) {
     return sky_matmul_impl<float>(h, A, B, C, alpha, dA, dB, beta, dC);
 }
+int32_t bbm_sky_qr_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau) { return sky_qr_fact_impl(h, d, d_data, d_tau); }
 int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,
                                 int64_t nrhs) {
     return sky_qr_lmul_adj_impl(h, d, d_factors, d_tau, d_B, ldb, nrhs);

@@ -268,6 +268,26 @@ def _qr_call(name, F, B):
     return B
 
 
+def qr_(A):
+    """``qr!(A)`` on the device (src/blockskylineqr.jl:29-49): A must be a Float64 BlockBandedMatrix already in the
+    factors' block bandwidths ``(l, l+u)`` (``A.with_bandwidths(l, l+u)`` on the host, then ``to_device``);
+    its storage becomes ``F.factors``.  Returns the BlockBandedQR."""
+    if not isinstance(A, BlockSkylineMatrix):
+        raise TypeError("qr! takes a BlockBandedMatrix")
+    h = _require_device(A)
+    if A.dtype != np.float64:
+        raise TypeError("the device qr! takes Float64 only")
+    n_tau = A.shape[1] if len(A.rows) >= len(A.cols) else A.shape[0]
+    tau = h.empty(max(n_tau, 1), np.float64)
+    rc = h._lib.bbm_sky_qr_f64(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(tau.ptr))
+    L.check(rc, h.h, "qr!")
+    if n_tau == 0:
+        tau = DeviceArray(h, (0,), np.float64, ptr=tau.ptr)
+    elif tau.shape[0] != n_tau:
+        tau = DeviceArray(h, (n_tau,), np.float64, ptr=tau.ptr)
+    return BlockBandedQR(A, tau)
+
+
 def lmul_adj_(F, B):
     """``lmul!(F.Q', B)`` for a block-banded QR: B <- Q' B in place (src/blockskylineqr.jl:77-127)."""
     if not isinstance(F, BlockBandedQR):

@@ -336,6 +336,24 @@ class BlockSkylineMatrix(_BlockAxes):
                 A[r0:r0 + S, out.C[J]:out.C[J + 1]].reshape(-1, order="F")
         return out
 
+    def with_bandwidths(self, l, u) -> "BlockSkylineMatrix":
+        """``BlockBandedMatrix(A, (l, u))``: a host copy in wider (or equal) block bandwidths, new blocks zero --
+        what the reference's ``_qr`` does before factorising (src/blockskylineqr.jl:75: ``(l, l+u)``)."""
+        if self.on_device:
+            raise TypeError("with_bandwidths re-lays the storage out on the host: call it before to_device")
+        out = BlockSkylineMatrix(np.zeros(self._numentries(self.rows, self.cols, l, u), dtype=self.dtype), self.rows, self.cols, l, u)
+        for J in range(len(self.cols)):
+            S0, S1, c = int(self.block_strides[J]), int(out.block_strides[J]), int(self.cols[J])
+            if S0 == 0 or c == 0:
+                continue
+            if out.klo[J] > self.klo[J] or out.khi[J] < self.khi[J]:
+                raise L.BandError("the new block bandwidths do not contain the old ones")
+            src = self.data[int(self.panel_offsets[J]):int(self.panel_offsets[J]) + S0 * c].reshape((S0, c), order="F")
+            dst = out.data[int(out.panel_offsets[J]):int(out.panel_offsets[J]) + S1 * c].reshape((S1, c), order="F")
+            r0 = int(self.R[self.klo[J]] - out.R[out.klo[J]])
+            dst[r0:r0 + S0, :] = src
+        return out
+
     # ---- queries -----------------------------------------------------------------------------
     @property
     def dtype(self):

@@ -220,6 +220,12 @@ int32_t bbm_sky_trsm_f32(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t
  * diagonal blocks (BBM_ERR_UNSUPPORTED otherwise: the call falls through to the reference).  In place on B.  */
 int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
                                 double* d_B, int64_t ldb, int64_t nrhs);
+/* qr!(A) in place (_blockbanded_qr!, src/blockskylineqr.jl:29-49): d_data holds A in the skyline storage of the
+ * FACTORS structure -- block bandwidths (l, l+u), the extra upper blocks zero, exactly what the reference's `_qr`
+ * (:75) allocates -- and becomes F.factors; d_tau (length n for at least as many block rows as columns, else m)
+ * becomes F.tau.  Same Householder convention as LinearAlgebra.reflector! / LAPACK geqrf, so factors and tau
+ * agree with the reference's to rounding.  Uniform block bandwidths, Float64.                              */
+int32_t bbm_sky_qr_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau);
 int32_t bbm_sky_qr_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
                             double* d_B, int64_t ldb, int64_t nrhs);
 

@@ -278,3 +278,29 @@ def test_block_banded_qr_errors(handle):
     Fd = B.BlockBandedQR(B.BlockSkylineMatrix(data, [4] * 3, [4] * 3, 1, 2), tau).to_device(handle)
     with pytest.raises(B.DimensionMismatch):
         B.ldiv_(Fd, handle.empty(11, np.float64))
+
+
+@pytest.mark.parametrize("rows,cols,l,u", QR_GPU_CASES + [([300, 20, 150], [300, 20, 150], 1, 1), ([50] * 4, [50] * 4, 3, 0)])
+def test_block_banded_qr_factorisation_on_device(handle, rows, cols, l, u):
+    """qr!(A) (test/test_blockskylineqr.jl:19-20,43-44): F.factors and F.tau against the restated
+    _blockbanded_qr! and against LAPACK's dense geqrf; then F \\ b with the device factors."""
+    rng = np.random.default_rng(73)
+    m, n = sum(rows), sum(cols)
+    A = B.BlockSkylineMatrix(F.sky_from_dense(rng.standard_normal((m, n)) + 3.0 * np.eye(m, n), rows, cols, l, u), rows, cols, l, u)
+    Aw = A.with_bandwidths(l, l + u)                          # `_qr`, src/blockskylineqr.jl:75
+    Ad = A.to_dense()
+    assert np.array_equal(Aw.to_dense(), Ad)
+    ref = Aw.data.copy()
+    tau_ref = O.sky_qr(rows, cols, l, l + u, ref)
+    Fd = B.qr_(Aw.to_device(handle))
+    got, tau = Fd.factors.data.to_host(), Fd.tau.to_host()
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 64 * 2.3e-16 * (max(rows) * (l + 1)) * scale
+    assert np.abs(tau - tau_ref).max() <= 64 * 2.3e-16 * (max(rows) * (l + 1))
+    h, t = np.linalg.qr(Ad, mode="raw")
+    fac = F.sky_to_dense(got, rows, cols, l, l + u)
+    assert np.abs(fac - h.T).max() <= 1e-12 * np.abs(h).max()
+    if rows == cols:
+        b = rng.standard_normal(m)
+        x = B.ldiv(Fd, handle.to_device(b)).to_host()
+        assert relerr(Ad @ x, b) <= tol(np.float64, max(rows) * (2 * l + u + 1)) * max(1.0, np.linalg.cond(Ad))

@@ -85,3 +85,14 @@ def test_bbb_block_range_views():
     assert not V.to_dense().any()
     with pytest.raises(IndexError):
         A.view(range(0, 11), 0)
+
+
+def test_with_bandwidths_keeps_the_entries():
+    """BlockBandedMatrix(A, (l, l+u)) of src/blockskylineqr.jl:75"""
+    rows, cols = [3, 1, 4, 2], [2, 5, 1, 3]
+    rng = np.random.default_rng(4)
+    A = B.BlockSkylineMatrix(random_sky(rng, rows, cols, 1, 1), rows, cols, 1, 1)
+    W = A.with_bandwidths(1, 2)
+    assert W.blockbandwidths == (1, 2) and np.array_equal(W.to_dense(), A.to_dense())
+    with pytest.raises(IndexError):
+        A.with_bandwidths(0, 2)
