@@ -381,6 +381,33 @@ def run_qr(torch, B, h, stream, reps, oracle, nblk=512, bs=256, nrhs=64, peak_tf
     out = {"config": f"qr: F \\ B for F = qr(BlockBandedMatrix {nblk} blocks of {bs}, (1,1)) computed on the host, {nrhs} RHS, Float64",
            "host_qr_seconds_lapack": t_fact, "ms_ldiv": avg - cavg, "ms_lmul_adj": qavg - cavg, "us_per_panel_lmul_adj": (qavg - cavg) * 1e3 / nblk,
            "tolerance": 64 * EPS[8] * 4 * bs}
+    # qr! itself on the device, from the same matrix (the solve above used the host factors)
+    a0_t = torch.from_numpy(Adata).cuda()
+    a_t = a0_t.clone()
+    Aq = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, l, l + u)
+
+    def fact():
+        a_t.copy_(a0_t)
+        B.qr_(Aq)
+
+    with torch.cuda.stream(stream):
+        c2, _ = time_gpu(torch, stream, lambda: a_t.copy_(a0_t), 3, warm=1)
+    favg, _ = time_gpu(torch, stream, fact, max(2, reps // 2), warm=1)
+    out["ms_qr_device"] = favg - c2
+    with torch.cuda.stream(stream):
+        a_t.copy_(a0_t)
+    Fq = B.qr_(Aq)
+    h.synchronize()
+    out["factors_rel_diff_device_vs_lapack"] = relerr(a_t.cpu().numpy(), data)
+    out["tau_max_diff_device_vs_lapack"] = float(np.abs(Fq.tau.to_host() - tau).max())
+    with torch.cuda.stream(stream):
+        b_t.copy_(b0_t)
+    B.ldiv_(Fq, dB)
+    h.synchronize()
+    out["rel_diff_solution_device_factors_vs_host_factors"] = relerr(b_t.cpu().numpy().T, X)
+    with torch.cuda.stream(stream):
+        b_t.copy_(torch.from_numpy(np.ascontiguousarray(X.T)).cuda())
+    h.synchronize()
     # residual against the original matrix: A X = B
     Ad = B.BlockSkylineMatrix(Adata, rows, rows, l, l + u).to_device(h)
     back = h.empty((m, nrhs), np.float64)

@@ -90,7 +90,7 @@ struct bbm_sky_desc {
     struct QrFact {
         bool built = false;
         int nb = 32;
-        i64 nsteps = 0, maxrows = 0, ws_total = 0;
+        i64 nsteps = 0, maxrows = 0, ws_total = 0, wlen = 0;
         i64 slotV[2] = {0, 0}, slotY[2] = {0, 0}, slotW[2] = {0, 0};
         i64* d_steps = nullptr;              // per step: slab start, ld, rows, width, tau offset, parity
         Tri::Batch bW, bC;
@@ -1271,21 +1271,24 @@ int32_t sky_qr_lmul_adj_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_f
 //                        W = YT C,   C -= V W.
 // The tile tables of all steps are built once per descriptor.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum_256(double v, double* red) {
+constexpr int kQrThreads = 1024;   // one warp per slab column during a reflector step
+
+__device__ __forceinline__ double qr_block_sum(double v, double* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    double t = 0.0;
+    double t = red[lane];   // kQrThreads / 32 == 32 partial sums
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
 }
 
-__global__ void __launch_bounds__(256) sky_qr_panel_kernel(double* __restrict__ data, double* __restrict__ tau, const i64* __restrict__ steps,
-                                                          i64 step, double* __restrict__ ws, i64 slotV0, i64 slotV1, i64 slotY0, i64 slotY1) {
+__global__ void __launch_bounds__(kQrThreads) sky_qr_panel_kernel(double* __restrict__ data, double* __restrict__ tau, const i64* __restrict__ steps,
+                                                                 i64 step, double* __restrict__ ws, i64 slotV0, i64 slotV1, i64 slotY0, i64 slotY1,
+                                                                 i64 slotW0, i64 slotW1, i64 wlen) {
     extern __shared__ __align__(16) unsigned char qr_smem[];
     const i64* st = steps + step * 6;
     const i64 a0 = st[0], ld = st[1];
@@ -1295,13 +1298,18 @@ __global__ void __launch_bounds__(256) sky_qr_panel_kernel(double* __restrict__ 
     const int lds = rows | 1;                       // odd leading dimension: rows of one column hit all banks
     double* As = reinterpret_cast<double*>(qr_smem);            // [w][lds]
     double* Ts = As + (size_t)w * lds;                           // [32][33]  T (upper)
-    double* Gs = Ts + 32 * 33;                                   // [32][33]  V'V
-    double* red = Gs + 32 * 33;                                  // [8] + scalars
-    double* sc = red + 8;                                        // [0] xi1, [1] tau
+    double* Gs = Ts + 32 * 33;                                   // [32][33]  V'V (upper)
+    double* red = Gs + 32 * 33;                                  // [32]
+    double* sc = red + 32;                                       // [0] xi1, [1] tau
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < rows * w; idx += 256) {
+    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
         const int r = idx % rows, c = idx / rows;
         As[r + c * lds] = data[a0 + r + (i64)c * ld];
+    }
+    for (int idx = tid; idx < 32 * 33; idx += kQrThreads) { Ts[idx] = 0.0; Gs[idx] = 0.0; }
+    {   // the split-k products of this step accumulate into a zeroed W
+        double* W = ws + (par ? slotW1 : slotW0);
+        for (i64 idx = tid; idx < wlen; idx += kQrThreads) W[idx] = 0.0;
     }
     __syncthreads();
     for (int jj = 0; jj < w; ++jj) {
@@ -1309,11 +1317,12 @@ __global__ void __launch_bounds__(256) sky_qr_panel_kernel(double* __restrict__ 
         const int n = rows - jj;
         if (n <= 1) {                                // real element type: nothing to annihilate in the last row
             if (tid == 0 && n == 1) tau[tau0 + jj] = 0.0;
+            if (tid == 0) sc[2 + jj] = 0.0;
             continue;
         }
         double ss = 0.0;
-        for (int r = tid; r < n; r += 256) ss = fma(x[r], x[r], ss);
-        ss = block_sum_256(ss, red);
+        for (int r = tid; r < n; r += kQrThreads) ss = fma(x[r], x[r], ss);
+        ss = qr_block_sum(ss, red);
         if (tid == 0) {
             const double normu = sqrt(ss);
             double tj = 0.0, xi1 = 1.0;
@@ -1324,56 +1333,53 @@ __global__ void __launch_bounds__(256) sky_qr_panel_kernel(double* __restrict__ 
                 x[0] = -nu;
                 tj = xi1 / nu;
             }
-            sc[0] = xi1; sc[1] = tj;
+            sc[0] = xi1; sc[1] = tj; sc[2 + jj] = tj;
             tau[tau0 + jj] = tj;
         }
         __syncthreads();
         const double xi1 = sc[0], tj = sc[1];
         if (tj != 0.0)
-            for (int r = 1 + tid; r < n; r += 256) x[r] /= xi1;
+            for (int r = 1 + tid; r < n; r += kQrThreads) x[r] /= xi1;
         __syncthreads();
-        if (tj != 0.0) {
-            for (int t = jj + 1 + warp; t < w; t += 8) {     // reflectorApply!: one warp per remaining column
-                double* a = As + jj + t * lds;
-                double v = 0.0;
-                for (int r = 1 + lane; r < n; r += 32) v = fma(x[r], a[r], v);
+        // one warp per other column: to the right the reflector is applied (reflectorApply!), to the left the
+        // dot product v_t'v_jj is kept for the T factor
+        if (warp < w && warp != jj && tj != 0.0) {
+            double* a = As + jj + warp * lds;
+            double v0 = 0.0, v1 = 0.0;
+            for (int r = 1 + lane; r < n; r += 64) {
+                v0 = fma(x[r], a[r], v0);
+                if (r + 32 < n) v1 = fma(x[r + 32], a[r + 32], v1);
+            }
+            double v = v0 + v1;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                v = tj * (v + a[0]);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            v += a[0];
+            if (warp > jj) {
+                v *= tj;
                 __syncwarp();
                 if (lane == 0) a[0] -= v;
                 for (int r = 1 + lane; r < n; r += 32) a[r] = fma(-x[r], v, a[r]);
+            } else if (lane == 0) {
+                Gs[warp * 33 + jj] = v;
             }
         }
         __syncthreads();
     }
     // R and the Householder vectors go back in place
-    for (int idx = tid; idx < rows * w; idx += 256) {
+    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
         const int r = idx % rows, c = idx / rows;
         data[a0 + r + (i64)c * ld] = As[r + c * lds];
     }
     __syncthreads();
-    // clean V in shared memory (zeros above, ones on the diagonal), Gram matrix, T, then V and YT = T'V' out
-    for (int idx = tid; idx < rows * w; idx += 256) {
+    // clean V in shared memory (zeros above, ones on the diagonal); T by the larft recurrence; V and YT = T'V' out
+    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
         const int r = idx % rows, c = idx / rows;
         if (r < c) As[r + c * lds] = 0.0;
         else if (r == c) As[r + c * lds] = 1.0;
     }
-    __syncthreads();
-    for (int pq = warp; pq < w * w; pq += 8) {
-        const int i = pq / w, j = pq % w;
-        if (i > j) continue;
-        double v = 0.0;
-        for (int r = j + lane; r < rows; r += 32) v = fma(As[r + i * lds], As[r + j * lds], v);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) Gs[i * 33 + j] = v;
-    }
-    for (int idx = tid; idx < 32 * 33; idx += 256) Ts[idx] = 0.0;
-    __syncthreads();
     if (warp == 0) {
         for (int j = 0; j < w; ++j) {
-            const double tj = (rows - j <= 1) ? 0.0 : tau[tau0 + j];   // written above by thread 0 of this CTA
+            const double tj = sc[2 + j];
             double sum = 0.0;
             if (lane < j)
                 for (int k = lane; k < j; ++k) sum = fma(Ts[lane * 33 + k], Gs[k * 33 + j], sum);
@@ -1386,16 +1392,15 @@ __global__ void __launch_bounds__(256) sky_qr_panel_kernel(double* __restrict__ 
     __syncthreads();
     double* Vout = ws + (par ? slotV1 : slotV0);   // rows x w, ld = rows
     double* Yout = ws + (par ? slotY1 : slotY0);   // w x rows, ld = w
-    for (int idx = tid; idx < rows * w; idx += 256) {
+    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
         const int r = idx % rows, c = idx / rows;
         Vout[idx] = As[r + c * lds];
     }
-    for (int r = tid; r < rows; r += 256) {
-        for (int i = 0; i < w; ++i) {              // YT[i, r] = sum_{k <= i} T[k, i] V[r, k]
-            double v = 0.0;
-            for (int k = 0; k <= i; ++k) v = fma(Ts[k * 33 + i], As[r + k * lds], v);
-            Yout[i + (i64)r * w] = v;
-        }
+    for (int idx = tid; idx < rows * w; idx += kQrThreads) {   // YT[i, r] = sum_{k <= i} T[k, i] V[r, k]; a warp writes one contiguous column
+        const int i = idx % w, r = idx / w;
+        double v = 0.0;
+        for (int k = 0; k <= i; ++k) v = fma(Ts[k * 33 + i], As[r + k * lds], v);
+        Yout[i + (i64)r * w] = v;
     }
 }
 
@@ -1416,7 +1421,7 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
         maxcols = std::max(maxcols, cols);
     }
     q.nb = maxS <= 704 ? 32 : maxS <= 1472 ? 16 : 8;
-    if ((size_t)q.nb * (maxS | 1) * 8 + 2 * 32 * 33 * 8 + 128 > std::min<size_t>(h->smem_optin, 220 * 1024))
+    if ((size_t)q.nb * (maxS | 1) * 8 + 2 * 32 * 33 * 8 + 1024 > std::min<size_t>(h->smem_optin, 220 * 1024))
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "qr!: panels of %lld rows exceed the shared-memory slab", (long long)maxS);
     q.maxrows = maxS;
     auto even = [](i64 v) { return (v + 1) & ~i64(1); };
@@ -1426,6 +1431,7 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
         q.slotY[p] = off; off = even(off + maxS * q.nb);
         q.slotW[p] = off; off = even(off + (i64)q.nb * maxcols);
     }
+    q.wlen = (i64)q.nb * maxcols;
     q.ws_total = off;
     std::vector<i64> steps;
     MmBatchHost bw, bc;
@@ -1445,7 +1451,8 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
             i64 woff = q.slotW[par];
             auto piece = [&](i64 cstart, i64 ldc, i64 cols) {   // rows x cols target with top-left at data[cstart]
                 if (cols <= 0) return;
-                bw.add(woff, w, w, cols, MmSeg{q.slotY[par], w, cstart, ldc, rows});          // W = YT C
+                for (i64 k0 = 0; k0 < rows; k0 += 64)                                           // W += YT[:, k-slice] C[k-slice, :]
+                    bw.add(woff, w, w, cols, MmSeg{q.slotY[par] + k0 * w, w, cstart + k0, ldc, std::min<i64>(64, rows - k0)});
                 bc.add(cstart, ldc, rows, cols, MmSeg{q.slotV[par], rows, woff, w, w});       // C -= V W
                 woff += w * cols;
             };
@@ -1483,13 +1490,14 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
     if (rc != BBM_OK) return rc;
     double* WS = static_cast<double*>(h->ws_w);
     BBM_CUDA(h, cudaMemsetAsync(d_tau, 0, (size_t)ntau * sizeof(double), h->stream));
-    const size_t smem = ((size_t)q.nb * (q.maxrows | 1) + 2 * 32 * 33 + 16) * sizeof(double);
+    const size_t smem = ((size_t)q.nb * (q.maxrows | 1) + 2 * 32 * 33 + 32 + 2 + 32 + 2) * sizeof(double);
     BBM_CUDA(h, cudaFuncSetAttribute(sky_qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
     for (i64 t = 0; t < q.nsteps; ++t) {
-        sky_qr_panel_kernel<<<1, 256, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1]);
+        sky_qr_panel_kernel<<<1, kQrThreads, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1],
+                                                               q.slotW[0], q.slotW[1], q.wlen);
         h->launches += 1;
-        rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 0.0, false, t < 2, pdl);
+        rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
         if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
         if (rc != BBM_OK) return rc;
     }

@@ -241,6 +241,14 @@ end
 # ldiv!(F, B) / lmul!(F.Q', B) for F = qr(A) computed by the reference on the host and moved with b200(F):
 # src/blockskylineqr.jl:77-127 (Q'B panel by panel) and :131-145 (then the triangular solve).  Float64.
 b200(F::MatrixFactorizations.QR{Float64,<:BlockSkylineMatrix}) = MatrixFactorizations.QR(b200(F.factors), B200Array(F.τ))
+# qr!(A) on the device (src/blockskylineqr.jl:45-49); `_qr` (:75) has already widened A to (l, l+u) with similar/copyto!
+function BlockBandedMatrices.qr!(A::B200Sky{Float64})
+    M, N = blocksize(A)
+    τ = B200Array{Float64}(undef, M < N ? size(A, 1) : size(A, 2))
+    check(ccall((:bbm_sky_qr_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                handle().ptr, descriptor(A), A.data.ptr, τ.ptr))
+    MatrixFactorizations.QR(A, τ)
+end
 function LinearAlgebra.ldiv!(F::MatrixFactorizations.QR{Float64,<:B200Sky{Float64}}, B::B200Array{Float64})
     A = F.factors
     size(A, 1) == size(B, 1) || throw(DimensionMismatch("F has size $(size(A)), B has size $(size(B))"))
