@@ -1,4 +1,4 @@
-"""BASELINE.json's configs at (or near) full size on the GPU.
+"""BASELINE.json's configs at (or near) full size on the GPU, and the widened rows at the same scale.
 
 cfg2 / cfg3 are checked against the CPU oracle at FULL size (the oracle needs < 1 s for them);
 cfg4 / cfg5 run at full block size with fewer blocks against the oracle, plus size-independent
@@ -8,6 +8,7 @@ import pytest
 
 import bbm_b200 as B
 from oracle import cpu as O
+from oracle import formats as F
 from tests.helpers import relerr, tol
 
 pytestmark = pytest.mark.gpu
@@ -113,3 +114,53 @@ def test_cfg5_block_size_512_64rhs_vs_oracle(handle):
     back = handle.empty((m, 64), np.float64)
     B.mul_(back, Ud, dB)
     assert relerr(back.to_host(), B0) <= 8 * tol(np.float64, 2048)
+
+
+@pytest.mark.parametrize("uplo", ["L", "U"])
+def test_gauss_seidel_half_step_full_size(handle, uplo):
+    """ldiv!(LowerTriangular(A), b) / UpperTriangular on cfg2's 16.7M-unknown Laplacian (examples/finitedifference_2d.jl:21)
+    against the oracle's block substitution, plus the round trip T * (T \\ b) == b on the GPU alone."""
+    n = 4096
+    A = B.BandedBlockBandedMatrix.finitedifference_2d(n)
+    rng = np.random.default_rng(6)
+    b = rng.standard_normal(n * n)
+    Ad = A.to_device(handle)
+    T = (B.LowerTriangular if uplo == "L" else B.UpperTriangular)(Ad)
+    dx = B.ldiv(T, handle.to_device(b))
+    x = dx.to_host()
+    ref = b.copy()
+    O.bbb_trsm([n] * n, 1, 1, 1, 1, uplo, False, A.data, ref)
+    assert relerr(x, ref) <= tol(np.float64, 9)
+    assert relerr((T @ dx).to_host(), b) <= 4 * tol(np.float64, 9)
+
+
+def test_block_banded_qr_solve_moderate_size(handle):
+    """F = qr(A); F \\ B on the device for a BlockBandedMatrix of 96 blocks of 128, (1,1), 16 right-hand sides:
+    A * (F \\ B) == B, R'R == A'A on sampled columns (size-independent properties), factors vs the restated qr!."""
+    rows, l, u = [128] * 96, 1, 1
+    rng = np.random.default_rng(7)
+    m = sum(rows)
+    A = B.BlockSkylineMatrix(rng.standard_normal(B.BlockSkylineMatrix.numentries(rows, rows, l, u)) / np.sqrt(3 * 128), rows, rows, l, u)
+    for K in range(len(rows)):
+        s, ld = A.block_start(K, K), int(A.block_strides[K])
+        i = np.arange(128)
+        A.data[s + i + i * ld] += 2.0
+    Aw = A.with_bandwidths(l, l + u)
+    Fd = B.qr_(Aw.to_device(handle))
+    B0 = np.asfortranarray(rng.standard_normal((m, 16)))
+    dX = B.ldiv(Fd, handle.to_device(B0))
+    back = handle.empty((m, 16), np.float64)
+    B.mul_(back, A.to_device(handle), dX)
+    assert relerr(back.to_host(), B0) <= tol(np.float64, 3 * 128)
+    ref = Aw.data.copy()
+    tau_ref = O.sky_qr(rows, rows, l, l + u, ref)
+    got = Fd.factors.data.to_host()
+    assert np.abs(got - ref).max() <= tol(np.float64, 2 * 128) * np.abs(ref).max()
+    assert np.abs(Fd.tau.to_host() - tau_ref).max() <= tol(np.float64, 2 * 128)
+    # Q' applied to the columns of A reproduces R: lmul!(Q', A e_j) == R e_j for sampled j
+    Ad = A.to_dense()
+    cols = rng.integers(0, m, 8)
+    dC = handle.to_device(np.asfortranarray(Ad[:, cols]))
+    B.lmul_adj_(Fd, dC)
+    Rd = np.triu(F.sky_to_dense(got, rows, rows, l, l + u))
+    assert relerr(dC.to_host(), Rd[:, cols]) <= tol(np.float64, 3 * 128)
