@@ -86,6 +86,9 @@ struct bbm_sky_desc {
         Tri::Batch stepW, stepB;             // the sweep; tiles of panel K are [ptr[K], ptr[K+1])
         std::vector<int> ptrW, ptrB;
     } qr;
+    // transposed matvec: one item per group of up to 8 columns of a panel (start, ld = rows, x row start, y row start, columns)
+    i64* d_titems = nullptr;
+    i64 ntitems = 0;
     // qr! plan (Float64): sub-panels of nb reflectors; tiles of step t are [ptr[t], ptr[t+1])
     struct QrFact {
         bool built = false;
@@ -1066,6 +1069,78 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Transposed matvec  Y <- alpha * A' * X + beta * Y  (mul!(y, A', x), src/adjtransblockbanded.jl:2-7).
+// A column of a panel is one contiguous run of S_J entries and its x operand the contiguous rows the panel
+// spans, so y[c] is a plain dot product of two unit-stride streams: one warp per column, 8 columns per CTA,
+// the matrix read exactly once, no atomics.  Summation order: lanes stride the rows, then a shuffle tree.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NR>
+__global__ void __launch_bounds__(256) sky_gemv_t_kernel(const T* __restrict__ data, const i64* __restrict__ items, T alpha, const T* __restrict__ X,
+                                                        i64 ldx, int q0, T beta, T* __restrict__ Y, i64 ldy) {
+    const i64* it = items + (i64)blockIdx.x * 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= (int)it[4]) return;
+    const i64 S = it[1];
+    const T* col = data + it[0] + (i64)warp * S;
+    const T* x = X + it[2] + (i64)q0 * ldx;
+    T acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = T(0);
+    for (i64 i = lane; i < S; i += 32) {
+        const T a = col[i];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[q] = fma(a, x[i + (i64)q * ldx], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+        T v = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            T* y = Y + it[3] + warp + (i64)(q0 + q) * ldy;
+            *y = beta == T(0) ? alpha * v : fma(beta, *y, alpha * v);
+        }
+    }
+}
+
+template <typename T>
+int32_t sky_mul_t_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs, T beta, T* d_Y, i64 ldy) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && (ldx < std::max<i64>(1, d->m) || ldy < std::max<i64>(1, d->n)))
+        return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: A' is %lld x %lld, ldx=%lld, ldy=%lld", (long long)d->n, (long long)d->m, (long long)ldx, (long long)ldy);
+    if (d->n == 0 || nrhs == 0) return BBM_OK;
+    if (!d_X && d->m > 0) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if (!d_Y || (!d_data && d->numel > 0)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    if (!d->d_titems) {
+        std::vector<i64> items;
+        for (i64 J = 0; J < d->Nc; ++J) {
+            // empty panels (no stored block, or only empty block rows) still own their y entries: S = 0 gives beta*y
+            const i64 S = d->S[J];
+            const i64 xrow = S > 0 ? d->R[d->klo[J]] : 0;
+            for (i64 j0 = 0; j0 < d->c[J]; j0 += 8)
+                items.insert(items.end(), {d->off[J] + j0 * S, S, xrow, d->C[J] + j0, std::min<i64>(8, d->c[J] - j0)});
+        }
+        d->ntitems = (i64)items.size() / 5;
+        int32_t rc = upload(h, items, &d->d_titems);
+        if (rc != BBM_OK) return rc;
+    }
+    if (d->ntitems == 0) return BBM_OK;
+    for (i64 q0 = 0; q0 < nrhs;) {
+        const int nr = nrhs - q0 >= 4 ? 4 : 1;
+        if (nr == 4) sky_gemv_t_kernel<T, 4><<<(unsigned)d->ntitems, 256, 0, h->stream>>>(d_data, d->d_titems, alpha, d_X, ldx, (int)q0, beta, d_Y, ldy);
+        else sky_gemv_t_kernel<T, 1><<<(unsigned)d->ntitems, 256, 0, h->stream>>>(d_data, d->d_titems, alpha, d_X, ldx, (int)q0, beta, d_Y, ldy);
+        h->launches += 1;
+        q0 += nr;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_gemv_t_kernel launch: %s", cudaGetErrorString(e));
+    return BBM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // QR solve: lmul!(F.Q', B) and ldiv!(F, B) for F = qr(A) of a block-banded matrix
 // (src/blockskylineqr.jl:77-145).  F.factors is block-skyline with bandwidths (l, l+u): block column K
 // holds R in and above its diagonal block and, in block rows K..K+l, the Householder vectors of panel K
@@ -1700,6 +1775,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         free_batch(d->tri[t].stepA);
         free_batch(d->tri[t].stepB);
     }
+    if (d->d_titems) cudaFree(d->d_titems);
     if (d->qrf.d_steps) cudaFree(d->qrf.d_steps);
     free_batch(d->qrf.bW); free_batch(d->qrf.bC);
     if (d->qr.d_pan) cudaFree(d->qr.d_pan);
@@ -1745,6 +1821,14 @@ int32_t bbm_sky_matmul_f64(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, b
 int32_t bbm_sky_matmul_f32(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, float alpha, const float* dA,
                            const float* dB, float beta, float* dC) {
     return sky_matmul_impl<float>(h, A, B, C, alpha, dA, dB, beta, dC);
+}
+int32_t bbm_sky_mul_t_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_data, const double* d_X, int64_t ldx,
+                          int64_t nrhs, double beta, double* d_Y, int64_t ldy) {
+    return sky_mul_t_impl<double>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_sky_mul_t_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X, int64_t ldx,
+                          int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
+    return sky_mul_t_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
 }
 int32_t bbm_sky_qr_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau) { return sky_qr_fact_impl(h, d, d_data, d_tau); }
 int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,

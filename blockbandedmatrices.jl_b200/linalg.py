@@ -120,8 +120,8 @@ def _bbb_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
 def _bbb_mul_t_(y, At, x, alpha=1.0, beta=0.0):
     """``mul!(y, A', x, alpha, beta)`` for a device-resident real BandedBlockBandedMatrix."""
     A = At.parent
-    if not isinstance(A, BandedBlockBandedMatrix):
-        raise TypeError("adjoint products are taken for BandedBlockBandedMatrix parents only")
+    if not isinstance(A, (BandedBlockBandedMatrix, BlockSkylineMatrix)):
+        raise TypeError("adjoint products are taken for BandedBlockBandedMatrix / BlockSkylineMatrix parents only")
     h = _require_device(A)
     m, n = A.shape
     xr, xc = _vec_dims(x, "x")
@@ -134,7 +134,7 @@ def _bbb_mul_t_(y, At, x, alpha=1.0, beta=0.0):
     if dt not in _SUF or np.dtype(x.dtype) != dt or np.dtype(y.dtype) != dt:
         raise TypeError("device path takes matching Float32/Float64 operands only")
     suf, ct = _SUF[dt]
-    fn = getattr(h._lib, f"bbm_bbb_mul_t_{suf}")
+    fn = getattr(h._lib, f"bbm_bbb_mul_t_{suf}" if isinstance(A, BandedBlockBandedMatrix) else f"bbm_sky_mul_t_{suf}")
     rc = fn(h.h, A.descriptor(h), ct(alpha), C.c_void_p(A.data.ptr), C.c_void_p(x.ptr), _ld(x), xc, ct(beta),
             C.c_void_p(y.ptr), _ld(y))
     L.check(rc, h.h, "mul!")

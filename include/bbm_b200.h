@@ -188,6 +188,14 @@ int32_t bbm_sky_mul_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const do
 int32_t bbm_sky_mul_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X,
                         int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
 
+/* Y <- alpha * A' * X + beta * Y: mul!(y, A', x) / transpose(A)*x for a real BlockSkylineMatrix
+ * (src/adjtransblockbanded.jl:2-7: the adjoint keeps a block-banded layout with reversed bandwidths).
+ * d_X: m x nrhs (ldx >= m), d_Y: n x nrhs (ldy >= n); beta == 0 never reads Y.                         */
+int32_t bbm_sky_mul_t_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_data, const double* d_X,
+                          int64_t ldx, int64_t nrhs, double beta, double* d_Y, int64_t ldy);
+int32_t bbm_sky_mul_t_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X,
+                          int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
+
 /* C <- alpha*A*B + beta*C, all three block-skyline (replaces [upstream] _block_muladd! + one BLAS
  * gemm per block triple; C's structure is the caller's: src/linalg.jl:27-48 for A*B, a wider C is
  * allowed, test/test_blockbanded.jl:213-221).  BBM_ERR_DIM if the block axes are incompatible,

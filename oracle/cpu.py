@@ -139,6 +139,23 @@ def bbb_mul_t(rows, cols, l, u, lam, mu, alpha, data, X, beta, Y):
     return Y
 
 
+def sky_mul_t(rows, cols, l, u, alpha, data, X, beta, Y):
+    """Y <- alpha*A^T*X + beta*Y in place for a block-skyline A (X has sum(rows) rows, Y has sum(cols) rows)."""
+    suf, ct = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    c, cp = _ia(cols)
+    lv, uv = _vecbw(l, len(c)), _vecbw(u, len(c))
+    if X.shape[0] != int(r.sum()) or Y.shape[0] != int(c.sum()):
+        raise ValueError("DimensionMismatch")
+    xp, ldx, nrhs = _mat(X, 0)
+    yp, ldy, _ = _mat(Y, 0)
+    f = getattr(lib(), f"oracle_sky_mul_t_{suf}")
+    rc = f(i64(len(r)), i64(len(c)), rp, cp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p), ct(alpha),
+           data.ctypes.data_as(_p), xp, i64(ldx), i64(nrhs), ct(beta), yp, i64(ldy))
+    _check(rc, "sky_mul_t")
+    return Y
+
+
 def sky_mul(rows, cols, l, u, alpha, data, X, beta, Y):
     suf, ct = _suffix(data.dtype)
     r, rp = _ia(rows)

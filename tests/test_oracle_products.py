@@ -224,3 +224,15 @@ def test_oracle_block_banded_qr_matches_lapack(rows, cols, l, u):
         O.sky_qr_ldiv(rows, l, l + u, data, tau, X)
         ref = np.linalg.solve(Ad, B0)
         assert np.linalg.norm(X - ref) <= 1e-10 * np.linalg.norm(ref)
+
+
+def test_oracle_sky_mul_t_vs_dense():
+    rng = np.random.default_rng(23)
+    for rows, cols, l, u in [([5, 3, 7, 2, 6], [4, 6, 2, 5, 3, 7], 1, 2), ([3] * 7, [3] * 7, [2, 1, 2, 3, 1, 0, 0], [0, 1, 1, 2, 3, 1, 2])]:
+        data = random_sky(rng, rows, cols, l, u)
+        Dn = F.sky_to_dense(data, rows, cols, l, u)
+        X = np.asfortranarray(rng.standard_normal((sum(rows), 3)))
+        Y = np.asfortranarray(rng.standard_normal((sum(cols), 3)))
+        ref = 2.0 * Dn.T @ X - 0.5 * Y
+        O.sky_mul_t(rows, cols, l, u, 2.0, data, X, -0.5, Y)
+        assert relerr(Y, ref) <= 1e-14

@@ -66,6 +66,37 @@ def test_sky_mul_matches_oracle(handle, case, dtype):
         assert relerr(got, ref) <= tol(dtype, nnz)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", SKY_CASES, ids=ids)
+def test_sky_transposed_mul_matches_oracle(handle, case, dtype):
+    """mul!(y, A', x) / transpose(A)*x for a BlockSkylineMatrix (src/adjtransblockbanded.jl:2-7)."""
+    rows, cols, l, u = case
+    rng = np.random.default_rng(5)
+    data = random_sky(rng, rows, cols, l, u, dtype)
+    A = B.BlockSkylineMatrix(data, rows, cols, l, u)
+    Ad = A.to_device(handle)
+    m, n = A.shape
+    nnz = int(max(A.block_strides.max() if len(A.cols) else 0, 1))
+    Dn = A.to_dense().astype(np.float64)
+    for nrhs, alpha, beta in [(None, 1.0, 0.0), (None, 2.5, -0.5), (3, 1.0, 1.0), (9, -1.0, 0.0)]:
+        xs = (m,) if nrhs is None else (m, nrhs)
+        ys = (n,) if nrhs is None else (n, nrhs)
+        X = np.asfortranarray(rng.standard_normal(xs).astype(dtype))
+        Y0 = np.asfortranarray(rng.standard_normal(ys).astype(dtype))
+        Yin = Y0.copy(order="F")
+        if beta == 0:
+            Yin[...] = np.nan
+        dX, dY = handle.to_device(X), handle.to_device(Yin)
+        B.mul_(dY, B.Adjoint(Ad), dX, alpha, beta)
+        got = dY.to_host()
+        ref = Y0.copy(order="F")
+        O.sky_mul_t(rows, cols, l, u, alpha, data, X, beta, ref)
+        assert not np.isnan(got).any()
+        assert relerr(got, ref) <= tol(dtype, nnz)
+        dense = alpha * (Dn.T @ X.astype(np.float64)) + beta * Y0.astype(np.float64)
+        assert relerr(got, dense) <= tol(dtype, nnz)
+
+
 def product_structure(A, Bm):
     l, u = B.add_bandwidths(A, Bm)
     return l, u
