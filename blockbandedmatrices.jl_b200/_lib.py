@@ -68,6 +68,9 @@ SIGNATURES = {
     "bbm_sky_qr_ldiv_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
     "bbm_bbb_trsv_f64": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_bbb_trsv_f32": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
+    "bbm_bbb_sparse_colptr": (i32, [vp, vp, i32, vp, C.POINTER(i64)]),
+    "bbm_bbb_sparse_fill_f64": (i32, [vp, vp, vp, vp, i32, vp, vp]),
+    "bbm_bbb_sparse_fill_f32": (i32, [vp, vp, vp, vp, i32, vp, vp]),
     "bbm_bbb_matmul_f64": (i32, [vp, vp, vp, vp, f64, vp, vp, f64, vp]),
     "bbm_bbb_matmul_f32": (i32, [vp, vp, vp, vp, f32, vp, vp, f32, vp]),
     "bbm_bbb_mul_host_f64": (i32, [vp, vp, f64, vp, vp, i64, i64, f64, vp, i64]),

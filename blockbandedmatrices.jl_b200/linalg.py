@@ -268,6 +268,29 @@ def _qr_call(name, F, B):
     return B
 
 
+def sparse(A, index_base: int = 0):
+    """``sparse(A)`` for a device-resident BandedBlockBandedMatrix (ext/BlockBandedMatricesSparseArraysExt.jl:10-27):
+    returns the CSC arrays ``(colptr, rowval, nzval)`` as device arrays (``index_base=1`` for Julia's
+    ``SparseMatrixCSC``); explicit zeros inside the bands are kept like the reference's."""
+    if not isinstance(A, BandedBlockBandedMatrix):
+        raise TypeError("sparse takes a BandedBlockBandedMatrix")
+    h = _require_device(A)
+    dt = A.dtype
+    if dt not in _SUF:
+        raise TypeError(f"device path takes Float32/Float64 only, got {dt}")
+    n = A.shape[1]
+    colptr = h.empty(n + 1, np.int64)
+    nnz = C.c_int64(0)
+    L.check(h._lib.bbm_bbb_sparse_colptr(h.h, A.descriptor(h), index_base, C.c_void_p(colptr.ptr), C.byref(nnz)), h.h, "sparse")
+    rowval, nzval = h.empty(max(nnz.value, 1), np.int64), h.empty(max(nnz.value, 1), dt)
+    fn = getattr(h._lib, f"bbm_bbb_sparse_fill_{_SUF[dt][0]}")
+    L.check(fn(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(colptr.ptr), index_base, C.c_void_p(rowval.ptr),
+               C.c_void_p(nzval.ptr)), h.h, "sparse")
+    if nnz.value == 0:
+        rowval, nzval = DeviceArray(h, (0,), np.int64, ptr=rowval.ptr), DeviceArray(h, (0,), dt, ptr=nzval.ptr)
+    return colptr, rowval, nzval
+
+
 def qr_(A):
     """``qr!(A)`` on the device (src/blockskylineqr.jl:29-49): A must be a Float64 BlockBandedMatrix already in the
     factors' block bandwidths ``(l, l+u)`` (``A.with_bandwidths(l, l+u)`` on the host, then ``to_device``);

@@ -156,6 +156,18 @@ int32_t bbm_bbb_trsv_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t
 int32_t bbm_bbb_trsv_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const float* d_data,
                          float* d_B, int64_t ldb, int64_t nrhs);
 
+/* sparse(A) (ext/BlockBandedMatricesSparseArraysExt.jl:10-27) as CSC arrays built on the device: every in-band entry
+ * of every in-band block, explicit zeros included, rows ascending within a column.  Two calls, like any CSC build:
+ *   bbm_bbb_sparse_colptr  fills d_colptr (n+1 entries) and returns nnz (synchronises for that number; pass
+ *                          nnz = NULL to stay asynchronous);
+ *   bbm_bbb_sparse_fill_*  writes d_rowval / d_nzval (nnz entries each).
+ * index_base = 1 gives Julia's SparseMatrixCSC(m, n, colptr, rowval, nzval) directly, 0 the C / cuSPARSE form.  */
+int32_t bbm_bbb_sparse_colptr(bbm_handle_t h, bbm_bbb_desc_t d, int32_t index_base, int64_t* d_colptr, int64_t* nnz);
+int32_t bbm_bbb_sparse_fill_f64(bbm_handle_t h, bbm_bbb_desc_t d, const double* d_data, const int64_t* d_colptr,
+                                int32_t index_base, int64_t* d_rowval, double* d_nzval);
+int32_t bbm_bbb_sparse_fill_f32(bbm_handle_t h, bbm_bbb_desc_t d, const float* d_data, const int64_t* d_colptr,
+                                int32_t index_base, int64_t* d_rowval, float* d_nzval);
+
 /* Same product with HOST vectors (the reference-facing call when x, y live in Julia Arrays and
  * the matrix is device-resident): copies X host->device, runs the kernel, copies Y back and
  * synchronises.  h_X / h_Y should be pinned (bbm_host_alloc) for full PCIe speed.             */

@@ -238,6 +238,19 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
     end
 end
 
+# sparse(A) built on the device (ext/BlockBandedMatricesSparseArraysExt.jl:10-27); needs SparseArrays loaded by the caller
+function b200_sparse_arrays(A::B200BBB{T}) where {T<:Union{Float32,Float64}}
+    colptr = B200Array{Int64}(undef, size(A, 2) + 1)
+    nnz = Ref{Int64}(0)
+    check(ccall((:bbm_bbb_sparse_colptr, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int64}, Ref{Int64}),
+                handle().ptr, descriptor(A), Int32(1), colptr.ptr, nnz))
+    rowval, nzval = B200Array{Int64}(undef, nnz[]), B200Array{T}(undef, nnz[])
+    fill = T === Float64 ? :bbm_bbb_sparse_fill_f64 : :bbm_bbb_sparse_fill_f32
+    check(ccall((fill, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{T}, Ptr{Int64}, Int32, Ptr{Int64}, Ptr{T}),
+                handle().ptr, descriptor(A), parent(A.data).ptr, colptr.ptr, Int32(1), rowval.ptr, nzval.ptr))
+    Array(colptr), Array(rowval), Array(nzval)      # SparseMatrixCSC(size(A)..., colptr, rowval, nzval)
+end
+
 # ldiv!(F, B) / lmul!(F.Q', B) for F = qr(A) computed by the reference on the host and moved with b200(F):
 # src/blockskylineqr.jl:77-127 (Q'B panel by panel) and :131-145 (then the triangular solve).  Float64.
 b200(F::MatrixFactorizations.QR{Float64,<:BlockSkylineMatrix}) = MatrixFactorizations.QR(b200(F.factors), B200Array(F.τ))

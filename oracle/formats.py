@@ -173,6 +173,31 @@ def bbb_valid_mask(rows, cols, l, u, lam, mu) -> np.ndarray:
     return mask
 
 
+def bbb_sparse(data, rows, cols, l, u, lam, mu):
+    """``sparse(A)`` of ext/BlockBandedMatricesSparseArraysExt.jl:10-27 as CSC arrays (0-based colptr, rowval, nzval):
+    every in-band entry of every in-band block is stored, explicit zeros included; within a column the rows
+    ascend (what ``sparse(i, j, z, m, n)`` produces from the per-block triplets)."""
+    R, C = prefix(rows), prefix(cols)
+    n = int(C[-1])
+    w = lam + mu + 1
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    rowval, nzval = [], []
+    Nr, Nc = len(R) - 1, len(C) - 1
+    for J in range(Nc):
+        for j in range(int(C[J + 1] - C[J])):
+            c = int(C[J]) + j
+            cnt = 0
+            if data.shape[0] > 0:
+                for K in blockcolsupport(Nr, J, l, u):
+                    rK = int(R[K + 1] - R[K])
+                    for k in range(max(0, j - mu), min(rK - 1, j + lam) + 1):
+                        rowval.append(int(R[K]) + k)
+                        nzval.append(data[(u + K - J) * w + (mu + k - j), c])
+                        cnt += 1
+            colptr[c + 1] = colptr[c] + cnt
+    return colptr, np.asarray(rowval, dtype=np.int64), np.asarray(nzval, dtype=data.dtype)
+
+
 def bbb_nnz_per_row_max(l, u, lam, mu) -> int:
     return max(0, l + u + 1) * max(0, lam + mu + 1)
 

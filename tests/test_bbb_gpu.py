@@ -233,6 +233,26 @@ def test_bbb_block_range_view_mul(handle, dtype):
         assert relerr(c.to_host(), sub @ b.astype(np.float64)) <= tol(dtype, 10)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("base", [0, 1])
+def test_bbb_sparse_export(handle, dtype, base):
+    """sparse(A) (ext/BlockBandedMatricesSparseArraysExt.jl:10-27; test/test_bandedblockbanded.jl "sparse"):
+    the device CSC arrays equal the restated per-block triplet construction and reproduce Matrix(A)."""
+    import scipy.sparse as sp
+    for rows, cols, lu, lm in [(list(range(1, 11)), list(range(1, 11)), (1, 1), (1, 1)), ([5, 0, 3, 7], [4, 2, 0, 6, 3], (1, 2), (2, 1)),
+                               ([300, 17, 64], [300, 17, 64], (1, 1), (0, 2)), ([4] * 5, [4] * 5, (-1, 2), (1, 1)), ([3, 3], [2, 2], (0, 0), (-1, 0))]:
+        rng = np.random.default_rng(81)
+        data = random_bbb(rng, rows, cols, *lu, *lm, dtype)
+        A = B.BandedBlockBandedMatrix(data, rows, cols, lu, lm)
+        colptr, rowval, nzval = B.sparse(A.to_device(handle), index_base=base)
+        cp, rv, nz = colptr.to_host(), rowval.to_host(), nzval.to_host()
+        rcp, rrv, rnz = F.bbb_sparse(data, rows, cols, *lu, *lm)
+        assert np.array_equal(cp - base, rcp) and np.array_equal(rv - base, rrv)
+        assert np.array_equal(nz, rnz) and not np.isnan(nz).any()
+        S = sp.csc_matrix((nz, rv - base, cp - base), shape=A.shape)
+        assert np.array_equal(S.toarray(), A.to_dense())
+
+
 def _well_conditioned_tri(rng, rows, lu, lm, dtype):
     """random band storage whose triangles are comfortably invertible: small off-diagonal, diagonal ~ 2"""
     data = random_bbb(rng, rows, rows, *lu, *lm, dtype)

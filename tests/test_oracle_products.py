@@ -236,3 +236,15 @@ def test_oracle_sky_mul_t_vs_dense():
         ref = 2.0 * Dn.T @ X - 0.5 * Y
         O.sky_mul_t(rows, cols, l, u, 2.0, data, X, -0.5, Y)
         assert relerr(Y, ref) <= 1e-14
+
+
+def test_oracle_bbb_sparse_matches_dense():
+    import scipy.sparse as sp
+    rng = np.random.default_rng(29)
+    for rows, cols, lu, lm in [(list(range(1, 8)), list(range(1, 8)), (1, 1), (1, 1)), ([5, 0, 3, 7], [4, 2, 0, 6, 3], (1, 2), (2, 1))]:
+        data = random_bbb(rng, rows, cols, *lu, *lm, poison=False)
+        cp, rv, nz = F.bbb_sparse(data, rows, cols, *lu, *lm)
+        S = sp.csc_matrix((nz, rv, cp), shape=(sum(rows), sum(cols)))
+        assert S.has_sorted_indices or np.all(np.diff(rv[cp[0]:cp[1]]) > 0)
+        assert np.array_equal(S.toarray(), F.bbb_to_dense(data, rows, cols, *lu, *lm))
+        assert cp[-1] == F.bbb_valid_mask(rows, cols, *lu, *lm).sum()
