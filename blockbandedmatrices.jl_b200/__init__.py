@@ -8,10 +8,10 @@ equivalent Julia package extension).
 """
 from ._lib import BandError, BBMError, DimensionMismatch, build_library, LIB_PATH, SIGNATURES  # noqa: F401
 from .device import DeviceArray, Handle, PinnedArray  # noqa: F401
-from .linalg import add_bandwidths, axpy_, ldiv, ldiv_, lmul_, lmul_adj_, mul, qr_, mul_, muladd_, sparse  # noqa: F401
-from .matrices import (Adjoint, BandedBlockBandedMatrix, BlockBandedMatrix, BlockBandedQR, BlockSkylineMatrix, LowerTriangular,  # noqa: F401
+from .linalg import add_bandwidths, axpy_, ldiv, ldiv_, lmul_, lmul_adj_, mul, ql_, qr_, mul_, muladd_, sparse  # noqa: F401
+from .matrices import (Adjoint, BandedBlockBandedMatrix, BlockBandedMatrix, BlockBandedQL, BlockBandedQR, BlockSkylineMatrix, LowerTriangular,  # noqa: F401
                        UnitLowerTriangular, UnitUpperTriangular, UpperTriangular)
 
 __all__ = ["BandedBlockBandedMatrix", "BlockSkylineMatrix", "BlockBandedMatrix", "UpperTriangular", "LowerTriangular",
-           "UnitUpperTriangular", "UnitLowerTriangular", "Adjoint", "BlockBandedQR", "lmul_adj_", "qr_", "sparse", "ldiv", "ldiv_", "add_bandwidths", "axpy_", "lmul_", "Handle", "DeviceArray", "PinnedArray", "mul", "mul_", "muladd_",
+           "UnitUpperTriangular", "UnitLowerTriangular", "Adjoint", "BlockBandedQR", "BlockBandedQL", "lmul_adj_", "qr_", "ql_", "sparse", "ldiv", "ldiv_", "add_bandwidths", "axpy_", "lmul_", "Handle", "DeviceArray", "PinnedArray", "mul", "mul_", "muladd_",
            "DimensionMismatch", "BandError", "BBMError", "build_library"]

@@ -63,6 +63,9 @@ SIGNATURES = {
     "bbm_bbb_mul_t_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
     "bbm_sky_mul_t_f64": (i32, [vp, vp, f64, vp, vp, i64, i64, f64, vp, i64]),
     "bbm_sky_mul_t_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
+    "bbm_sky_ql_f64": (i32, [vp, vp, vp, vp]),
+    "bbm_sky_ql_lmul_adj_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
+    "bbm_sky_ql_ldiv_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
     "bbm_sky_qr_f64": (i32, [vp, vp, vp, vp]),
     "bbm_sky_qr_lmul_adj_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
     "bbm_sky_qr_ldiv_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),

@@ -86,6 +86,8 @@ struct bbm_sky_desc {
         Tri::Batch stepW, stepB;             // the sweep; tiles of panel K are [ptr[K], ptr[K+1])
         std::vector<int> ptrW, ptrB;
     } qr;
+    // descriptor of the row-and-column reversed matrix (its storage is the reversed `data`), for the QL calls
+    bbm_sky_desc* rev = nullptr;
     // transposed matvec: one item per group of up to 8 columns of a panel (start, ld = rows, x row start, y row start, columns)
     i64* d_titems = nullptr;
     i64 ntitems = 0;
@@ -1582,6 +1584,99 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
 }
 
 template <typename T>
+int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs);
+
+// ------------------------------------------------------------------------------------------------
+// QL (ql!, lmul!(F.Q', B), ldiv!(F::QL, B); src/blockskylineqr.jl:51-72, 96-111, 149-157) by reversal.
+// LAPACK's geqlf/ormql are geqrf/ormqr on the matrix with rows and columns reversed, and for block-skyline
+// storage that reversed matrix is simply the flat `data` vector read backwards (panels in reverse order, every
+// panel reversed, block sizes reversed, l and u swapped).  So the QL calls flip the operands, run the QR
+// kernels above on the reversed descriptor, and flip back; factors and tau come out in geqlf's packing.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sky_flip_kernel(double* __restrict__ a, i64 n) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n / 2) { const double t = a[i]; a[i] = a[n - 1 - i]; a[n - 1 - i] = t; }
+}
+__global__ void __launch_bounds__(256) sky_flip_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, i64 n) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = src[n - 1 - i];
+}
+__global__ void __launch_bounds__(256) sky_flip_rows_kernel(double* __restrict__ B, i64 m, i64 ldb) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    double* b = B + (i64)blockIdx.y * ldb;
+    if (i < m / 2) { const double t = b[i]; b[i] = b[m - 1 - i]; b[m - 1 - i] = t; }
+}
+
+int32_t sky_reversed_desc(bbm_handle_t h, bbm_sky_desc_t d, bbm_sky_desc_t* out) {
+    if (d->Nr != d->Nc) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "block-banded QL on the device takes square block structures");
+    if (!d->rev) {
+        std::vector<i64> r(d->r.rbegin(), d->r.rend()), c(d->c.rbegin(), d->c.rend());
+        std::vector<i64> l(d->u.rbegin(), d->u.rend()), u(d->l.rbegin(), d->l.rend());
+        bbm_sky_desc_t rv = nullptr;
+        int32_t rc = bbm_sky_desc_create(h, d->Nr, d->Nc, r.data(), c.data(), l.data(), u.data(), &rv);
+        if (rc != BBM_OK) return rc;
+        if (rv->numel != d->numel) { bbm_sky_desc_destroy(rv); return bbm_fail(h, BBM_ERR_UNSUPPORTED, "reversed structure has a different storage size"); }
+        d->rev = rv;
+    }
+    *out = d->rev;
+    return BBM_OK;
+}
+
+inline void sky_flip(bbm_handle_t h, double* a, i64 n) {
+    if (n > 1) { sky_flip_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, h->stream>>>(a, n); h->launches += 1; }
+}
+inline void sky_flip_rows(bbm_handle_t h, double* B, i64 m, i64 ldb, i64 nrhs) {
+    if (m > 1 && nrhs > 0) { sky_flip_rows_kernel<<<dim3((unsigned)((m / 2 + 255) / 256), (unsigned)nrhs), 256, 0, h->stream>>>(B, m, ldb); h->launches += 1; }
+}
+
+int32_t sky_ql_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (d->n == 0) return BBM_OK;
+    if (!d_data || !d_tau) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    bbm_sky_desc_t rv = nullptr;
+    int32_t rc = sky_reversed_desc(h, d, &rv);
+    if (rc != BBM_OK) return rc;
+    sky_flip(h, d_data, d->numel);
+    rc = sky_qr_fact_impl(h, rv, d_data, d_tau);
+    sky_flip(h, d_data, d->numel);
+    sky_flip(h, d_tau, d->n);
+    return rc;
+}
+
+// Q' B for the packed Q of a QL; with solve != 0 the LowerTriangular solve follows (ldiv!(F::QL, B))
+int32_t sky_ql_apply_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_fac, const double* d_tau, double* d_B, i64 ldb, i64 nrhs, int solve) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && ldb < std::max<i64>(1, d->m)) return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: Q is %lld x %lld, ldb=%lld", (long long)d->m, (long long)d->m, (long long)ldb);
+    if (d->m == 0 || d->n == 0 || nrhs == 0) return BBM_OK;
+    if (!d_fac || !d_tau || !d_B) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    bbm_sky_desc_t rv = nullptr;
+    int32_t rc = sky_reversed_desc(h, d, &rv);
+    if (rc != BBM_OK) return rc;
+    bool match = true;
+    for (i64 K = 0; match && K < d->Nr; ++K) match = d->r[K] == d->c[K];
+    if (!match) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "QL solve on the device needs matching diagonal blocks");
+    // reversed copies of the factors and tau (the caller's stay untouched)
+    const size_t fb = ((size_t)d->numel * sizeof(double) + 255) / 256 * 256;
+    rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, fb + (size_t)d->n * sizeof(double) + 256);
+    if (rc != BBM_OK) return rc;
+    double* frev = static_cast<double*>(h->ws_x);
+    double* trev = reinterpret_cast<double*>(static_cast<char*>(h->ws_x) + fb);
+    sky_flip_copy_kernel<<<(unsigned)((d->numel + 255) / 256), 256, 0, h->stream>>>(d_fac, frev, d->numel);
+    sky_flip_copy_kernel<<<(unsigned)((d->n + 255) / 256), 256, 0, h->stream>>>(d_tau, trev, d->n);
+    h->launches += 2;
+    sky_flip_rows(h, d_B, d->m, ldb, nrhs);
+    rc = sky_qr_lmul_adj_impl(h, rv, frev, trev, d_B, ldb, nrhs);
+    sky_flip_rows(h, d_B, d->m, ldb, nrhs);
+    if (rc != BBM_OK || !solve) return rc;
+    return sky_trsm_impl<double>(h, d, 'L', 0, d_fac, d_B, ldb, nrhs);
+}
+
+template <typename T>
 int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs) {
     BBM_REQUIRE_HANDLE(h);
     if (!sky_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
@@ -1775,6 +1870,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         free_batch(d->tri[t].stepA);
         free_batch(d->tri[t].stepB);
     }
+    if (d->rev) { bbm_sky_desc_destroy(d->rev); d->rev = nullptr; }
     if (d->d_titems) cudaFree(d->d_titems);
     if (d->qrf.d_steps) cudaFree(d->qrf.d_steps);
     free_batch(d->qrf.bW); free_batch(d->qrf.bC);
@@ -1821,6 +1917,15 @@ int32_t bbm_sky_matmul_f64(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, b
 int32_t bbm_sky_matmul_f32(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, float alpha, const float* dA,
                            const float* dB, float beta, float* dC) {
     return sky_matmul_impl<float>(h, A, B, C, alpha, dA, dB, beta, dC);
+}
+int32_t bbm_sky_ql_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau) { return sky_ql_fact_impl(h, d, d_data, d_tau); }
+int32_t bbm_sky_ql_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,
+                                int64_t nrhs) {
+    return sky_ql_apply_impl(h, d, d_factors, d_tau, d_B, ldb, nrhs, 0);
+}
+int32_t bbm_sky_ql_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,
+                            int64_t nrhs) {
+    return sky_ql_apply_impl(h, d, d_factors, d_tau, d_B, ldb, nrhs, 1);
 }
 int32_t bbm_sky_mul_t_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_data, const double* d_X, int64_t ldx,
                           int64_t nrhs, double beta, double* d_Y, int64_t ldy) {

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from .device import DeviceArray
-from .matrices import Adjoint, BandedBlockBandedMatrix, BlockBandedQR, BlockSkylineMatrix, _Triangular
+from .matrices import Adjoint, BandedBlockBandedMatrix, BlockBandedQL, BlockBandedQR, BlockSkylineMatrix, _Triangular
 
 _SUF = {np.dtype(np.float64): ("f64", C.c_double), np.dtype(np.float32): ("f32", C.c_float)}
 
@@ -311,11 +311,30 @@ def qr_(A):
     return BlockBandedQR(A, tau)
 
 
+def ql_(A):
+    """``ql!(A)`` on the device (src/blockskylineqr.jl:51-72): A must be a square Float64 BlockBandedMatrix already in
+    the factors' block bandwidths ``(l+u, u)`` (``A.with_bandwidths(l+u, u)``); returns the BlockBandedQL."""
+    if not isinstance(A, BlockSkylineMatrix):
+        raise TypeError("ql! takes a BlockBandedMatrix")
+    h = _require_device(A)
+    if A.dtype != np.float64:
+        raise TypeError("the device ql! takes Float64 only")
+    if len(A.rows) < len(A.cols):
+        raise ValueError("Wide block-QL not implemented")      # ArgumentError, src/blockskylineqr.jl:56
+    n_tau = A.shape[1]
+    tau = h.empty(max(n_tau, 1), np.float64)
+    rc = h._lib.bbm_sky_ql_f64(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(tau.ptr))
+    L.check(rc, h.h, "ql!")
+    if tau.shape[0] != n_tau:
+        tau = DeviceArray(h, (n_tau,), np.float64, ptr=tau.ptr)
+    return BlockBandedQL(A, tau)
+
+
 def lmul_adj_(F, B):
     """``lmul!(F.Q', B)`` for a block-banded QR: B <- Q' B in place (src/blockskylineqr.jl:77-127)."""
     if not isinstance(F, BlockBandedQR):
-        raise TypeError("lmul_adj_ takes a BlockBandedQR")
-    return _qr_call("bbm_sky_qr_lmul_adj_f64", F, B)
+        raise TypeError("lmul_adj_ takes a BlockBandedQR / BlockBandedQL")
+    return _qr_call("bbm_sky_ql_lmul_adj_f64" if isinstance(F, BlockBandedQL) else "bbm_sky_qr_lmul_adj_f64", F, B)
 
 
 def ldiv_(T, B):
@@ -324,7 +343,7 @@ def ldiv_(T, B):
     if isinstance(T, BlockBandedQR):
         if T.shape[0] != T.shape[1]:
             raise L.DimensionMismatch(f"F is {T.shape}: the device path solves square systems")
-        return _qr_call("bbm_sky_qr_ldiv_f64", T, B)
+        return _qr_call("bbm_sky_ql_ldiv_f64" if isinstance(T, BlockBandedQL) else "bbm_sky_qr_ldiv_f64", T, B)
     if not isinstance(T, _Triangular) or not isinstance(T.parent, (BlockSkylineMatrix, BandedBlockBandedMatrix)):
         raise TypeError("ldiv! takes Upper/LowerTriangular wrappers of a BlockSkylineMatrix or BandedBlockBandedMatrix")
     A = T.parent

@@ -494,6 +494,15 @@ class BlockBandedQR:
         return BlockBandedQR(self.factors.to_device(handle), t)
 
 
+class BlockBandedQL(BlockBandedQR):
+    """``F = ql(A)`` (``MatrixFactorizations.QL{T,<:BlockSkylineMatrix}``, src/blockskylineqr.jl:51-72): ``factors`` has
+    block bandwidths ``(l+u, u)`` -- L in and below the diagonal blocks, Householder vectors above (geqlf packing)."""
+
+    def to_device(self, handle: Handle) -> "BlockBandedQL":
+        t = self.tau if isinstance(self.tau, DeviceArray) else handle.to_device(np.ascontiguousarray(self.tau))
+        return BlockBandedQL(self.factors.to_device(handle), t)
+
+
 class Adjoint:
     """``A'`` / ``transpose(A)`` of a real BandedBlockBandedMatrix: reversed bandwidths
     (src/adjtransblockbanded.jl:2-3), products through the transposed kernel."""

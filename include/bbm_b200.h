@@ -246,6 +246,16 @@ int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* 
  * becomes F.tau.  Same Householder convention as LinearAlgebra.reflector! / LAPACK geqrf, so factors and tau
  * agree with the reference's to rounding.  Uniform block bandwidths, Float64.                              */
 int32_t bbm_sky_qr_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau);
+
+/* The QL counterparts (ql!, lmul!(F.Q', B), ldiv!(F::QL, B); src/blockskylineqr.jl:51-72, 96-111, 149-157): `d`
+ * describes the factors structure (l+u, u); factors and tau come out in LAPACK geqlf's packing (L in and below the
+ * diagonal blocks, the Householder vectors above).  Implemented by reversal -- the row-and-column reversed matrix
+ * is the flat skyline vector read backwards -- on top of the QR kernels.  Square block structures, Float64.   */
+int32_t bbm_sky_ql_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau);
+int32_t bbm_sky_ql_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
+                                double* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_sky_ql_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
+                            double* d_B, int64_t ldb, int64_t nrhs);
 int32_t bbm_sky_qr_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
                             double* d_B, int64_t ldb, int64_t nrhs);
 

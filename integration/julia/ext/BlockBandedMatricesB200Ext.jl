@@ -271,6 +271,28 @@ function LinearAlgebra.ldiv!(F::MatrixFactorizations.QR{Float64,<:B200Sky{Float6
     check(rc)
     B
 end
+# the QL counterparts (src/blockskylineqr.jl:51-72, 96-111, 149-157); `_ql` (:76) has widened A to (l+u, u)
+function BlockBandedMatrices.ql!(A::B200Sky{Float64})
+    M, N = blocksize(A)
+    M < N && throw(ArgumentError("Wide block-QL not implented"))
+    τ = B200Array{Float64}(undef, size(A, 2))
+    check(ccall((:bbm_sky_ql_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                handle().ptr, descriptor(A), A.data.ptr, τ.ptr))
+    MatrixFactorizations.QL(A, τ)
+end
+function LinearAlgebra.ldiv!(F::MatrixFactorizations.QL{Float64,<:B200Sky{Float64}}, B::B200Array{Float64})
+    A = F.factors
+    size(A, 1) == size(B, 1) || throw(DimensionMismatch("F has size $(size(A)), B has size $(size(B))"))
+    check(ccall((:bbm_sky_ql_ldiv_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+                handle().ptr, descriptor(A), A.data.ptr, F.τ.ptr, B.ptr, ld(B), size(B, 2)))
+    B
+end
+function LinearAlgebra.lmul!(adjQ::Adjoint{Float64,<:MatrixFactorizations.QLPackedQ{Float64,<:B200Sky{Float64}}}, B::B200Array{Float64})
+    Q = parent(adjQ)
+    check(ccall((:bbm_sky_ql_lmul_adj_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+                handle().ptr, descriptor(Q.factors), Q.factors.data.ptr, Q.τ.ptr, B.ptr, ld(B), size(B, 2)))
+    B
+end
 function LinearAlgebra.lmul!(adjQ::Adjoint{Float64,<:MatrixFactorizations.QRPackedQ{Float64,<:B200Sky{Float64}}}, B::B200Array{Float64})
     Q = parent(adjQ)
     check(ccall((:bbm_sky_qr_lmul_adj_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),

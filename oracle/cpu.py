@@ -263,6 +263,45 @@ def sky_qr_ldiv(rows, l, u, data, tau, B):
     return B
 
 
+def sky_ql(rows, cols, l, u, data):
+    """ql!(A) in place on the skyline storage of the FACTORS structure (block bandwidths (l, u) with l = l_A+u_A
+    already, src/blockskylineqr.jl:51-72,76); returns tau."""
+    suf, _ = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    c, cp = _ia(cols)
+    lv, uv = _vecbw(l, len(c)), _vecbw(u, len(c))
+    tau = np.zeros(int(c.sum()), dtype=data.dtype)
+    f = getattr(lib(), f"oracle_sky_ql_{suf}")
+    rc = f(i64(len(r)), i64(len(c)), rp, cp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p), data.ctypes.data_as(_p), tau.ctypes.data_as(_p))
+    if rc == 1:
+        raise ValueError("sky_ql: ArgumentError (wide block-QL / non-uniform bandwidths)")
+    _check(rc, "sky_ql")
+    return tau
+
+
+def _sky_ql_call(name, rows, l, u, data, tau, B):
+    suf, _ = _suffix(data.dtype)
+    r, rp = _ia(rows)
+    lv, uv = _vecbw(l, len(r)), _vecbw(u, len(r))
+    if B.shape[0] != int(r.sum()):
+        raise ValueError("DimensionMismatch")
+    bp, ldb, nrhs = _mat(B, 0)
+    f = getattr(lib(), f"{name}_{suf}")
+    rc = f(i64(len(r)), rp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p), data.ctypes.data_as(_p), tau.ctypes.data_as(_p), bp, i64(ldb), i64(nrhs))
+    _check(rc, name)
+    return B
+
+
+def sky_ql_lmul_adj(rows, l, u, data, tau, B):
+    """B <- Q' B in place for the packed Q of a square block-banded QL (src/blockskylineqr.jl:96-111)."""
+    return _sky_ql_call("oracle_sky_ql_lmul_adj", rows, l, u, data, tau, B)
+
+
+def sky_ql_ldiv(rows, l, u, data, tau, B):
+    """B <- F \\ B in place for a square block-banded QL (src/blockskylineqr.jl:149-157)."""
+    return _sky_ql_call("oracle_sky_ql_ldiv", rows, l, u, data, tau, B)
+
+
 def bbb_trsm(rows, l, u, lam, mu, uplo, unit, data, B):
     """B <- T^-1 B in place, T = triangular part ('U'/'L', unit or not) of the BandedBlockBandedMatrix."""
     suf, _ = _suffix(data.dtype)

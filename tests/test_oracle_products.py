@@ -248,3 +248,27 @@ def test_oracle_bbb_sparse_matches_dense():
         assert S.has_sorted_indices or np.all(np.diff(rv[cp[0]:cp[1]]) > 0)
         assert np.array_equal(S.toarray(), F.bbb_to_dense(data, rows, cols, *lu, *lm))
         assert cp[-1] == F.bbb_valid_mask(rows, cols, *lu, *lm).sum()
+
+
+@pytest.mark.parametrize("rows,l,u", [(list(range(1, 6)), 2, 1), ([3, 2, 1, 3], 1, 1), ([4] * 6, 1, 1), ([3, 5, 2, 4], 1, 2)])
+def test_oracle_block_banded_ql_matches_lapack(rows, l, u):
+    """test/test_blockskylineqr.jl:86-88: F.factors == ql(Matrix(A)).factors, F.tau == the dense taus.  scipy has no
+    geqlf binding, so LAPACK enters through the identity geqlf(A) = reverse(geqrf(reverse(A)))."""
+    rng = np.random.default_rng(19)
+    m = sum(rows)
+    Ad = F.sky_to_dense(F.sky_from_dense(rng.standard_normal((m, m)) + 3.0 * np.eye(m), rows, rows, l, u), rows, rows, l, u)
+    data = F.sky_from_dense(Ad, rows, rows, l + u, u)
+    tau = O.sky_ql(rows, rows, l + u, u, data)
+    h, t = np.linalg.qr(Ad[::-1, ::-1], mode="raw")
+    fac = F.sky_to_dense(data, rows, rows, l + u, u)
+    assert np.abs(fac - h.T[::-1, ::-1]).max() <= 1e-13 * np.abs(h).max()
+    assert np.abs(tau - t[::-1]).max() <= 1e-13
+    Lm = np.tril(fac)
+    assert np.abs(Lm.T @ Lm - Ad.T @ Ad).max() <= 1e-12 * np.abs(Ad.T @ Ad).max()
+    B0 = rng.standard_normal((m, 3))
+    X = np.asfortranarray(B0.copy())
+    O.sky_ql_ldiv(rows, l + u, u, data, tau, X)
+    ref = np.linalg.solve(Ad, B0)
+    assert np.linalg.norm(X - ref) <= 1e-10 * np.linalg.norm(ref)
+    with pytest.raises(ValueError):
+        O.sky_ql([3, 3], [3, 3, 3], 2, 1, np.zeros(F.sky_numentries([3, 3], [3, 3, 3], 2, 1)))

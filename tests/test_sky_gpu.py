@@ -335,3 +335,57 @@ def test_block_banded_qr_factorisation_on_device(handle, rows, cols, l, u):
         b = rng.standard_normal(m)
         x = B.ldiv(Fd, handle.to_device(b)).to_host()
         assert relerr(Ad @ x, b) <= tol(np.float64, max(rows) * (2 * l + u + 1)) * max(1.0, np.linalg.cond(Ad))
+
+
+QL_GPU_CASES = [
+    (list(range(1, 6)), 2, 1),                  # test/test_blockskylineqr.jl:81-100 "Square QL"
+    ([3, 2, 1, 3], 1, 1),                       # :125-140 "Off-diagonals"
+    ([4] * 6, 1, 1),
+    ([100, 70, 129, 33], 2, 1),
+    ([64] * 10, 1, 2),
+    ([7], 0, 0),
+]
+
+
+@pytest.mark.parametrize("rows,l,u", QL_GPU_CASES)
+def test_block_banded_ql_on_device(handle, rows, l, u):
+    """ql!(A), lmul!(F.Q', B) and F \\ B for the QL factorisation (test/test_blockskylineqr.jl:81-100): factors and
+    tau against the restated geql2 loop and against LAPACK through the reversal identity; solves against dense."""
+    rng = np.random.default_rng(91)
+    m = sum(rows)
+    A = B.BlockSkylineMatrix(F.sky_from_dense(rng.standard_normal((m, m)) + 3.0 * np.eye(m), rows, rows, l, u), rows, rows, l, u)
+    Aw = A.with_bandwidths(l + u, u)                          # `_ql`, src/blockskylineqr.jl:76
+    Ad = A.to_dense()
+    ref = Aw.data.copy()
+    tau_ref = O.sky_ql(rows, rows, l + u, u, ref)
+    Fd = B.ql_(Aw.to_device(handle))
+    got, tau = Fd.factors.data.to_host(), Fd.tau.to_host()
+    bound = 64 * 2.3e-16 * (max(rows) * (u + 1))
+    assert np.abs(got - ref).max() <= bound * np.abs(ref).max()
+    assert np.abs(tau - tau_ref).max() <= bound
+    h, t = np.linalg.qr(Ad[::-1, ::-1], mode="raw")            # geqlf(A) is geqrf of the reversed matrix, reversed
+    fac = F.sky_to_dense(got, rows, rows, l + u, u)
+    assert np.abs(fac - h.T[::-1, ::-1]).max() <= 1e-12 * np.abs(h).max()
+    for nrhs in (1, 7):
+        B0 = np.asfortranarray(rng.standard_normal((m, nrhs))) if nrhs > 1 else rng.standard_normal(m)
+        # host-computed factors through the device solve, and Q'B alone
+        Fh = B.BlockBandedQL(B.BlockSkylineMatrix(ref, rows, rows, l + u, u), tau_ref).to_device(handle)
+        dQ = handle.to_device(B0)
+        B.lmul_adj_(Fh, dQ)
+        rq = np.asfortranarray(B0.copy())
+        O.sky_ql_lmul_adj(rows, l + u, u, ref, tau_ref, rq)
+        nnz = max(rows) * (l + u + 1)
+        assert relerr(dQ.to_host(), rq) <= tol(np.float64, nnz)
+        cond = max(1.0, np.linalg.cond(Ad))
+        for Fx in (Fh, Fd):
+            x = B.ldiv(Fx, handle.to_device(B0)).to_host()
+            assert relerr(Ad @ x, B0) <= tol(np.float64, nnz) * cond
+        rs = np.asfortranarray(B0.copy())
+        O.sky_ql_ldiv(rows, l + u, u, ref, tau_ref, rs)
+        assert relerr(x, rs) <= tol(np.float64, nnz) * cond
+
+
+def test_block_banded_ql_wide_is_an_argument_error(handle):
+    A = B.BlockSkylineMatrix(np.zeros(F.sky_numentries([3, 3], [3, 3, 3], 2, 1)), [3, 3], [3, 3, 3], 2, 1).to_device(handle)
+    with pytest.raises(ValueError):            # test/test_blockskylineqr.jl:121-123 "Wide QL"
+        B.ql_(A)
