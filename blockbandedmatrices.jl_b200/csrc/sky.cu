@@ -1379,10 +1379,8 @@ __global__ void __launch_bounds__(kQrThreads) sky_qr_panel_kernel(double* __rest
     double* red = Gs + 32 * 33;                                  // [32]
     double* sc = red + 32;                                       // [0] xi1, [1] tau
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
-        const int r = idx % rows, c = idx / rows;
-        As[r + c * lds] = data[a0 + r + (i64)c * ld];
-    }
+    for (int c = warp; c < w; c += kQrThreads / 32)        // one warp per slab column: no index division
+        for (int r = lane; r < rows; r += 32) As[r + c * lds] = data[a0 + r + (i64)c * ld];
     for (int idx = tid; idx < 32 * 33; idx += kQrThreads) { Ts[idx] = 0.0; Gs[idx] = 0.0; }
     {   // the split-k products of this step accumulate into a zeroed W
         double* W = ws + (par ? slotW1 : slotW0);
@@ -1443,17 +1441,12 @@ __global__ void __launch_bounds__(kQrThreads) sky_qr_panel_kernel(double* __rest
         __syncthreads();
     }
     // R and the Householder vectors go back in place
-    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
-        const int r = idx % rows, c = idx / rows;
-        data[a0 + r + (i64)c * ld] = As[r + c * lds];
-    }
+    for (int c = warp; c < w; c += kQrThreads / 32)
+        for (int r = lane; r < rows; r += 32) data[a0 + r + (i64)c * ld] = As[r + c * lds];
     __syncthreads();
     // clean V in shared memory (zeros above, ones on the diagonal); T by the larft recurrence; V and YT = T'V' out
-    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
-        const int r = idx % rows, c = idx / rows;
-        if (r < c) As[r + c * lds] = 0.0;
-        else if (r == c) As[r + c * lds] = 1.0;
-    }
+    for (int c = warp; c < w; c += kQrThreads / 32)
+        for (int r = lane; r <= c; r += 32) As[r + c * lds] = r == c ? 1.0 : 0.0;
     if (warp == 0) {
         for (int j = 0; j < w; ++j) {
             const double tj = sc[2 + j];
@@ -1469,15 +1462,14 @@ __global__ void __launch_bounds__(kQrThreads) sky_qr_panel_kernel(double* __rest
     __syncthreads();
     double* Vout = ws + (par ? slotV1 : slotV0);   // rows x w, ld = rows
     double* Yout = ws + (par ? slotY1 : slotY0);   // w x rows, ld = w
-    for (int idx = tid; idx < rows * w; idx += kQrThreads) {
-        const int r = idx % rows, c = idx / rows;
-        Vout[idx] = As[r + c * lds];
-    }
-    for (int idx = tid; idx < rows * w; idx += kQrThreads) {   // YT[i, r] = sum_{k <= i} T[k, i] V[r, k]; a warp writes one contiguous column
-        const int i = idx % w, r = idx / w;
-        double v = 0.0;
-        for (int k = 0; k <= i; ++k) v = fma(Ts[k * 33 + i], As[r + k * lds], v);
-        Yout[i + (i64)r * w] = v;
+    for (int c = warp; c < w; c += kQrThreads / 32)
+        for (int r = lane; r < rows; r += 32) Vout[r + (i64)c * rows] = As[r + c * lds];
+    for (int r = warp; r < rows; r += kQrThreads / 32) {       // YT[i, r] = sum_{k <= i} T[k, i] V[r, k]; lane = i, a warp writes one contiguous column
+        if (lane < w) {
+            double v = 0.0;
+            for (int k = 0; k <= lane; ++k) v = fma(Ts[k * 33 + lane], As[r + k * lds], v);
+            Yout[lane + (i64)r * w] = v;
+        }
     }
 }
 
