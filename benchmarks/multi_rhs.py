@@ -1,5 +1,5 @@
 import sys, json, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, bbm_b200 as B
 from benchmarks.configs import wrap, time_gpu
 torch.cuda.set_device(0); stream = torch.cuda.Stream(); h = B.Handle(0, stream=stream.cuda_stream)

@@ -1,5 +1,7 @@
+"""Micro-benchmark of the device qr! (bbm_sky_qr_f64): 64 blocks of 256, (1,1) -> 512 sub-panel steps; prints the
+mean time per step (panel kernel + two trailing-update launches).  Used with ncu to look at the panel kernel."""
 import sys, json, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, bbm_b200 as B
 from oracle import formats as F
 torch.cuda.set_device(0); stream = torch.cuda.Stream(); h = B.Handle(0, stream=stream.cuda_stream)
