@@ -340,6 +340,26 @@ def _check_triangular_ldiv(handle, uplo, unit, dtype):
         assert relerr(dB.to_host(), Bm) == 0.0      # ldiv (not ldiv!) leaves B alone
 
 
+@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["wave", "staged", "direct"])
+@pytest.mark.parametrize("uplo", ["U", "L"])
+def test_bbb_triangular_ldiv_more_block_rows_than_lanes(handle, uplo, kernel):
+    """more than 4096 block rows: every thread of the cluster owns two block rows (round-robin passes)"""
+    rows, lu, lm = [3, 2] * 2300, (1, 1), (1, 1)
+    rng = np.random.default_rng(45)
+    data = _well_conditioned_tri(rng, rows, lu, lm, np.float64)
+    Ad = B.BandedBlockBandedMatrix(data, rows, rows, lu, lm).to_device(handle)
+    T = (B.UpperTriangular if uplo == "U" else B.LowerTriangular)(Ad)
+    b = rng.standard_normal(sum(rows))
+    handle.set_option("tri.kernel", kernel)
+    try:
+        got = B.ldiv(T, handle.to_device(b)).to_host()
+    finally:
+        handle.set_option("tri.kernel", 0)
+    ref = b.copy()
+    O.bbb_trsm(rows, *lu, *lm, uplo, False, np.nan_to_num(data), ref)
+    assert relerr(got, ref) <= tol(np.float64, 10)
+
+
 def test_bbb_triangular_ldiv_gauss_seidel_sweep(handle):
     """examples/finitedifference_2d.jl:17-47 flavour: (D+L) \\ b on the 2-D Laplacian, 200 x 200 blocks."""
     n = 200
