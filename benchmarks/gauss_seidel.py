@@ -77,10 +77,12 @@ def main():
     Ad, db = A.to_device(h), h.to_device(b)
     gauss_seidel_device(B, h, Ad, db, 2)      # warm-up (workspace allocation)
     h.synchronize()
-    t0 = time.perf_counter()
-    x = gauss_seidel_device(B, h, Ad, db, args.sweeps)
-    h.synchronize()
-    dt = time.perf_counter() - t0
+    dt = float("inf")
+    for _ in range(3):                         # best of 3: the loop is short enough for host jitter to show
+        t0 = time.perf_counter()
+        x = gauss_seidel_device(B, h, Ad, db, args.sweeps)
+        h.synchronize()
+        dt = min(dt, time.perf_counter() - t0)
     xh = x.to_host()
     res = A.to_device(h) @ x
     out = {"example": "examples/finitedifference_2d.jl Gauss-Seidel", "n": n, "unknowns": n * n, "sweeps": args.sweeps,

@@ -17,7 +17,7 @@
 //
 // Four kernels, fastest first; the entry point takes the first one that applies:
 //   lean   wave-ordered inputs, one block row per thread, compile-time bandwidths ((1,1),(1,1) and (2,2),(2,2)),
-//          group-boundary values pushed with st.async                      0.40 us/step   7.2 ms on cfg2 (CPU 154 ms)
+//          group-boundary values pushed with st.async                      0.40 us/step   6.75 ms on cfg2 (CPU 154 ms)
 //   wave   wave-ordered inputs, any bandwidths / up to 6 block rows per thread          1.3 us/step
 //   staged band storage read in place, prefetched with cp.async (no workspace)          3.0 us/step
 //   direct band storage read in place inside the step                                   4.4 us/step
@@ -277,54 +277,111 @@ struct TriWaveParams {
 constexpr int kTriGroup = 128;                      // lanes dealt to one CTA at a time
 constexpr int kTriGroups = kTriThreads / kTriGroup;
 
-// what: bit 0 = right-hand side plane, bit 1 = matrix planes
+// Pack / unpack run on all SMs as tiled transposes between the two orders: a tile is 32 block rows (Kl) x 32
+// steps (s).  On the band-storage side a warp handles one block row and its lanes 32 consecutive steps =
+// 32 consecutive columns of `data` / entries of x (unit stride); on the wave-ordered side a warp handles one step
+// and its lanes 32 consecutive block rows (unit stride again); the tile turns in shared memory.
+// what: bit 0 = right-hand side plane, bit 1 = matrix planes.  Planes are staged kTriPackPlanes at a time.
+constexpr int kTriPackPlanes = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) bbb_tri_pack_kernel(const TriWaveParams<T> p) {
-    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (i64)p.N * p.maxr) return;
-    const int Kl = (int)(idx / p.maxr), kk = (int)(idx % p.maxr);
-    const int K = p.upper ? p.N - 1 - Kl : Kl;
-    const int k = p.upper ? p.maxr - 1 - kk : kk;
-    const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
-    if (k >= rK) return;
+    __shared__ T stage[kTriPackPlanes][32][33];
+    __shared__ unsigned char ok[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
     const int nd = p.upper ? p.u : p.l;
-    T* out = p.packed + (i64)(kk + delta * Kl) * p.Wd + Kl % p.Wd;
-    if (p.what & 1) out[0] = p.x[r0 + k];
-    if (!(p.what & 2)) return;
     const int w = p.w, mu = p.mu;
-    const T* dcol = p.data + (i64)p.u * w;
-    out[p.total] = p.unit ? T(1) : dcol[mu + (i64)p.P * (r0 + k)];
-    for (int d = 1; d <= nd; ++d) {
-        const int J = p.upper ? K + d : K - d;
-        const bool have = J >= 0 && J < p.N;
-        const i64 c0 = have ? p.R[J] : 0, rJ = have ? p.R[J + 1] - c0 : 0;
-        const T* slab = p.data + (i64)(p.upper ? p.u - d : p.u + d) * w;
-        for (int ii = 0; ii < w; ++ii) {
-            const i64 j = k + mu - ii;
-            out[(i64)(2 + (d - 1) * w + ii) * p.total] = (j >= 0 && j < rJ) ? slab[ii + (i64)p.P * (c0 + j)] : T(0);
-        }
-    }
     const int ndiag = p.upper ? p.mu : p.lam, ii0 = p.upper ? 0 : p.mu + 1;
-    for (int t = 0; t < ndiag; ++t) {
-        const i64 j = k + mu - (ii0 + t);
-        out[(i64)(2 + nd * w + t) * p.total] = (j >= 0 && j < rK) ? dcol[ii0 + t + (i64)p.P * (r0 + j)] : T(0);
+    const int Kl0 = blockIdx.y * 32;
+    const i64 s0 = (i64)delta * Kl0 + (i64)blockIdx.x * 32;
+    const int c_lo = (p.what & 1) ? 0 : 1, c_hi = (p.what & 2) ? p.nc : 1;
+    for (int cg0 = c_lo; cg0 < c_hi; cg0 += kTriPackPlanes) {
+        const int ncg = min(kTriPackPlanes, c_hi - cg0);
+        // gather: warp = block row, lanes = consecutive steps
+        for (int a = warp; a < 32; a += 8) {
+            const int Kl = Kl0 + a;
+            const i64 s = s0 + lane;
+            const i64 kk64 = s - (i64)delta * Kl;
+            bool valid = Kl < p.N && kk64 >= 0 && kk64 < p.maxr;
+            int K = 0, k = 0;
+            i64 r0 = 0, rK = 0;
+            if (valid) {
+                K = p.upper ? p.N - 1 - Kl : Kl;
+                k = p.upper ? p.maxr - 1 - (int)kk64 : (int)kk64;
+                r0 = p.R[K]; rK = p.R[K + 1] - r0;
+                valid = k < rK;
+            }
+            if (cg0 == c_lo) ok[a][lane] = valid ? 1 : 0;
+            if (!valid) continue;
+            const T* dcol = p.data + (i64)p.u * w;
+            for (int cc = 0; cc < ncg; ++cc) {
+                const int c = cg0 + cc;
+                T v;
+                if (c == 0) {
+                    v = p.x[r0 + k];
+                } else if (c == 1) {
+                    v = p.unit ? T(1) : dcol[mu + (i64)p.P * (r0 + k)];
+                } else if (c < 2 + nd * w) {
+                    const int d = 1 + (c - 2) / w, ii = (c - 2) % w;
+                    const int J = p.upper ? K + d : K - d;
+                    v = T(0);
+                    if (J >= 0 && J < p.N) {
+                        const i64 c0 = p.R[J], rJ = p.R[J + 1] - c0;
+                        const i64 j = (i64)k + mu - ii;
+                        if (j >= 0 && j < rJ) v = p.data[(i64)(p.upper ? p.u - d : p.u + d) * w + ii + (i64)p.P * (c0 + j)];
+                    }
+                } else {
+                    const int t = c - 2 - nd * w;
+                    const i64 j = (i64)k + mu - (ii0 + t);
+                    v = (t < ndiag && j >= 0 && j < rK) ? dcol[ii0 + t + (i64)p.P * (r0 + j)] : T(0);
+                }
+                stage[cc][a][lane] = v;
+            }
+        }
+        __syncthreads();
+        // scatter: warp = step, lanes = consecutive block rows
+        for (int b = warp; b < 32; b += 8) {
+            const int Kl = Kl0 + lane;
+            if (ok[lane][b]) {
+                T* out = p.packed + (s0 + b) * p.Wd + Kl % p.Wd;
+                for (int cc = 0; cc < ncg; ++cc) out[(i64)(cg0 + cc) * p.total] = stage[cc][lane][b];
+            }
+        }
+        __syncthreads();
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) bbb_tri_unpack_kernel(const TriWaveParams<T> p) {
-    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (i64)p.N * p.maxr) return;
-    const int Kl = (int)(idx / p.maxr), kk = (int)(idx % p.maxr);
-    const int K = p.upper ? p.N - 1 - Kl : Kl;
-    const int k = p.upper ? p.maxr - 1 - kk : kk;
-    const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
-    if (k >= rK) return;
+    __shared__ T stage[32][33];
+    __shared__ unsigned char ok[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
-    T v = p.packed[(i64)(kk + delta * Kl) * p.Wd + Kl % p.Wd];
-    if (*p.status) v = T(NAN);   // a halo value never arrived inside the solve kernel: poison instead of a wrong answer
-    p.x[r0 + k] = v;
+    const int Kl0 = blockIdx.y * 32;
+    const i64 s0 = (i64)delta * Kl0 + (i64)blockIdx.x * 32;
+    const bool poison = *p.status != 0;   // a halo value never arrived inside the solve kernel: NaN instead of a wrong answer
+    // wave-ordered side: warp = step, lanes = consecutive block rows
+    for (int b = warp; b < 32; b += 8) {
+        const int Kl = Kl0 + lane;
+        const i64 s = s0 + b;
+        const i64 kk = s - (i64)delta * Kl;
+        const bool in = Kl < p.N && kk >= 0 && kk < p.maxr && s < p.iters;
+        ok[lane][b] = in ? 1 : 0;
+        if (in) stage[lane][b] = p.packed[s * p.Wd + Kl % p.Wd];
+    }
+    __syncthreads();
+    // x side: warp = block row, lanes = consecutive steps = consecutive entries of x
+    for (int a = warp; a < 32; a += 8) {
+        if (!ok[a][lane]) continue;
+        const int Kl = Kl0 + a;
+        const i64 kk = s0 + lane - (i64)delta * Kl;
+        const int K = p.upper ? p.N - 1 - Kl : Kl;
+        const int k = p.upper ? p.maxr - 1 - (int)kk : (int)kk;
+        const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
+        if (k >= rK) continue;
+        p.x[r0 + k] = poison ? T(NAN) : stage[a][lane];
+    }
 }
 
 // shared memory: ring [passes][D][kTriThreads] | coef [passes][PF][NC][kTriThreads]
@@ -696,8 +753,8 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
         if (nd == 1 && p.w == 3 && ndiag == 1) lean = 13;
         if (nd == 2 && p.w == 5 && ndiag == 2) lean = 25;
     }
-    const i64 cells = (i64)p.N * p.maxr;
-    const unsigned grid = (unsigned)((cells + 255) / 256);
+    // transposing tiles of 32 block rows x 32 steps; a block-row tile is active for maxr + 31*delta steps
+    const dim3 grid((unsigned)((p.maxr + 31 * delta + 31) / 32), (unsigned)((p.N + 31) / 32));
     for (i64 q = 0; q < nrhs; ++q) {
         p.x = d_B + q * ldb;
         p.what = q == 0 ? 3 : 1;
