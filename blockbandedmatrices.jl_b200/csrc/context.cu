@@ -5,7 +5,7 @@
 
 static const char* const kOptionKeys[] = {
     "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves", "bbb.host_chunks", "bbb.ovh", "bbb.mm_kernel", "bbb.pdl",
-    "sky.kernel", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "dist.graph", "dist.peer", "dist.lead_steps", nullptr};
+    "sky.kernel", "sky.mv_split", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "dist.graph", "dist.peer", "dist.lead_steps", nullptr};
 
 extern "C" {
 

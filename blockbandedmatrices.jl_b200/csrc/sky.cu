@@ -234,6 +234,15 @@ int32_t launch_gemv(bbm_handle_t h, const GemvParams<T>& p, int nitems, int nrhs
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256) sky_prescale_kernel(T* __restrict__ Y, i64 ldy, i64 m, i64 nrhs, T beta) {
+    for (i64 q = blockIdx.y; q < nrhs; q += gridDim.y)
+        for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < m; i += (i64)gridDim.x * 256) {
+            T* y = Y + i + q * ldy;
+            *y = beta == T(0) ? T(0) : beta * *y;   // beta == 0 never reads the destination
+        }
+}
+
+template <typename T>
 int32_t sky_mul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs, T beta,
                      T* d_Y, i64 ldy) {
     BBM_REQUIRE_HANDLE(h);
@@ -247,6 +256,22 @@ int32_t sky_mul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data,
     if (nrhs > 8 * 65535) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "too many right-hand sides");
     BBM_CUDA(h, cudaSetDevice(h->device));
     GemvParams<T> p{d_data, d_X, d_Y, ldx, ldy, d->d_items, d->d_ents, alpha, beta, (int)nrhs};
+    // Few row tiles (a small matrix, or one rank's share of a large one) leave most of an SM's warp slots empty and
+    // the stream latency-bound: split every panel's columns over gridDim.z CTAs that accumulate with atomics into a
+    // pre-scaled y (the same split the triangular solve's update uses).
+    const i64 ycols = nrhs == 1 ? 1 : (nrhs <= 4 ? 1 : (nrhs + 7) / 8);
+    // measured (256-row blocks, (2,2), one vector): a CTA's column loop alone takes ~190 us whatever the matrix size,
+    // so up to ~1000 row tiles a 4-way split is 1.2x - 3x faster (164 MB: 191 -> 60 us, 668 MB: 206 -> 110 us,
+    // 1.3 GB: 239 -> 203 us); at 4096 tiles (cfg4's operand, 7.07 TB/s) the unsplit kernel already saturates HBM
+    i64 z = bbm_opt(h, "sky.mv_split", 0);
+    if (z <= 0) z = (i64)d->nitems * ycols <= 14 * (i64)h->num_sms ? 4 : ((i64)d->nitems * ycols <= 21 * (i64)h->num_sms ? 2 : 1);
+    if (z >= 2 && d->nitems > 0) {
+        const unsigned gx = (unsigned)std::min<i64>(65535, (d->m + 255) / 256);
+        sky_prescale_kernel<T><<<dim3(gx, (unsigned)std::min<i64>(nrhs, 65535)), 256, 0, h->stream>>>(d_Y, ldy, d->m, nrhs, beta);
+        h->launches += 1;
+        p.beta = T(1);
+        return launch_gemv<T>(h, p, d->nitems, (int)nrhs, (int)z);
+    }
     return launch_gemv<T>(h, p, d->nitems, (int)nrhs);
 }
 

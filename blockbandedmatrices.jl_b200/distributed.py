@@ -367,6 +367,7 @@ class DistBlockBandedMatvec:
         else:
             data = self.tA.numpy()[:n]
         self.A = BlockSkylineMatrix(data, self.rows[K0:K1], self.cols[Jlo:Jhi], ll, uu)
+        self._call = None
 
     def exchange(self):
         dist, ops = self.dist, []
@@ -379,12 +380,20 @@ class DistBlockBandedMatvec:
                 w.wait()
 
     def mul_(self, alpha=1.0, beta=0.0):
-        """Device path: y_own <- alpha*A_loc*x_local[cols of A_loc] + beta*y_own (after exchange())."""
-        from .device import DeviceArray
-        from .linalg import mul_
-        n_loc, m = self.A.shape[1], self.A.shape[0]
-        es = self.tA.element_size()
-        dx = DeviceArray(self.h, (n_loc,), self.A.dtype, ptr=self.x_local.data_ptr() + self.x_off * es)
-        dy = DeviceArray(self.h, (m,), self.A.dtype, ptr=self.y_own.data_ptr())
-        mul_(dy, self.A, dx, alpha, beta)
+        """Device path: y_own <- alpha*A_loc*x_local[cols of A_loc] + beta*y_own (after exchange()).
+        One C-ABI call with cached arguments: at 8 GPUs the per-rank kernel is ~0.1 ms, shorter than the generic
+        `mul_` wrapper's host-side checks."""
+        import ctypes as C
+        from . import _lib as L
+        if self._call is None:
+            n_loc, m = self.A.shape[1], self.A.shape[0]
+            es = self.tA.element_size()
+            f64 = np.dtype(self.A.dtype) == np.float64
+            ct = C.c_double if f64 else C.c_float
+            fn = getattr(self.h._lib, "bbm_sky_mul_f64" if f64 else "bbm_sky_mul_f32")
+            args = (self.h.h, self.A.descriptor(self.h), C.c_void_p(self.A.data.ptr),
+                    C.c_void_p(self.x_local.data_ptr() + self.x_off * es), max(1, n_loc), 1, C.c_void_p(self.y_own.data_ptr()), max(1, m))
+            self._call = (fn, ct, args)
+        fn, ct, a = self._call
+        L.check(fn(a[0], a[1], ct(alpha), a[2], a[3], a[4], a[5], ct(beta), a[6], a[7]), self.h.h, "mul!")
         return self.y_own
