@@ -1,7 +1,10 @@
 /*
  * bbm_b200.h -- C ABI of libbbm_b200.so: hand-written sm_100a CUDA kernels for the data-parallel
  * hot path of BlockBandedMatrices.jl (mul!/muladd! for BandedBlockBandedMatrix and
- * BlockBandedMatrix/BlockSkylineMatrix, block-banded triangular ldiv!).
+ * BlockBandedMatrix/BlockSkylineMatrix, block-banded triangular ldiv!) and the callers either side of
+ * it: triangular banded-block-banded products and solves, transposed products, A*B in band storage,
+ * axpy!/lmul! on storage, sparse(A), qr!/ql! with lmul!(Q', B) and F \ B, and the row-block-partitioned
+ * multi-GPU matvec.
  *
  * This is what a Julia package extension `ccall`s (INTEGRATION.md shows the binding): plain
  * pointers and sizes, no CUDA.jl / torch types.  All matrices keep the reference's storage
