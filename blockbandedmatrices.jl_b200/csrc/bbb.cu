@@ -1284,6 +1284,79 @@ __global__ void __launch_bounds__(256) bbb_matmul_col_kernel(const BbbMmParams<T
     }
 }
 
+// Compile-time bandwidths for the column kernel (NSA/NSB block bands, WA/WB sub-block bands of A and B): the
+// four product loops unroll completely, the NS x NW = (NSA+NSB-1) x (WA+WB-1) partial sums of a column of C
+// live in registers instead of being read-modified-written in shared memory, and block sizes are looked up once
+// per column.  Shared memory only turns the 256 x P_C slab for the coalesced write-back.  Same ascending (N, i)
+// summation order as the generic kernel.
+template <typename T, int NSA, int WA, int NSB, int WB>
+__global__ void __launch_bounds__(256) bbb_matmul_col_fixed_kernel(const BbbMmParams<T> p) {
+    extern __shared__ __align__(16) unsigned char mmc_smem[];
+    T* acc = reinterpret_cast<T*>(mmc_smem);  // acc[rho * 257 + t]
+    constexpr int NS = NSA + NSB - 1, NW = WA + WB - 1;
+    const int tid = threadIdx.x;
+    const int s0 = p.uC - p.uA - p.uB, i0 = p.muC - p.muA - p.muB;   // >= 0 (BandError otherwise)
+    for (i64 col0 = (i64)blockIdx.x * 256; col0 < p.nC; col0 += (i64)gridDim.x * 256) {
+        const i64 col = col0 + tid;
+        T r[NS][NW];
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int b = 0; b < NW; ++b) r[a][b] = T(0);
+        if (col < p.nC) {
+            i64 lo = 0, hi = p.NcB;
+            while (hi - lo > 1) {
+                const i64 mid = (lo + hi) >> 1;
+                if (p.CB[mid] <= col) lo = mid; else hi = mid;
+            }
+            const i64 J = lo, j = col - p.CB[J];
+            i64 rK[NS];   // sizes of the block rows K = J - uA - uB + a of A (0 outside the matrix)
+#pragma unroll
+            for (int a = 0; a < NS; ++a) {
+                const i64 K = J - p.uA - p.uB + a;
+                rK[a] = (K >= 0 && K < p.NrA) ? p.RA[K + 1] - p.RA[K] : 0;
+            }
+            const T* __restrict__ bcol = p.B + (i64)p.PB * col;
+#pragma unroll
+            for (int sB = 0; sB < NSB; ++sB) {
+                const i64 N = J + sB - p.uB;
+                if (N < 0 || N >= p.NcA) continue;
+                const i64 cN0 = p.CA[N], cN = p.CA[N + 1] - cN0;
+#pragma unroll
+                for (int iB = 0; iB < WB; ++iB) {
+                    const i64 i = j - p.muB + iB;
+                    if (i < 0 || i >= cN) continue;
+                    const T b = bcol[sB * WB + iB];
+                    const T* __restrict__ acol = p.A + (i64)(NSA * WA) * (cN0 + i);
+#pragma unroll
+                    for (int sA = 0; sA < NSA; ++sA) {
+#pragma unroll
+                        for (int iA = 0; iA < WA; ++iA) {
+                            const i64 k = i - p.muA + iA;
+                            if (k >= 0 && k < rK[sA + sB]) r[sA + sB][iA + iB] = fma(acol[sA * WA + iA], b, r[sA + sB][iA + iB]);
+                        }
+                    }
+                }
+            }
+        }
+        for (int rho = 0; rho < p.PC; ++rho) acc[rho * 257 + tid] = T(0);
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int b = 0; b < NW; ++b) acc[((s0 + a) * p.wC + i0 + b) * 257 + tid] = r[a][b];
+        __syncthreads();
+        const i64 ncol = min((i64)256, p.nC - col0);
+        T* __restrict__ cslab = p.C + (i64)p.PC * col0;
+        for (i64 idx = tid; idx < ncol * p.PC; idx += 256) {
+            const int t = (int)(idx / p.PC), rho = (int)(idx - (i64)t * p.PC);
+            T v = p.alpha * acc[rho * 257 + t];
+            if (p.beta != T(0)) v = fma(p.beta, cslab[idx], v);
+            cslab[idx] = v;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t Cd, T alpha, const T* dA, const T* dB, T beta, T* dC) {
     BBM_REQUIRE_HANDLE(h);
@@ -1309,9 +1382,15 @@ int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_
     cudaError_t e = cudaSuccess;
     const size_t smem = (size_t)p.PC * 257 * sizeof(T);
     if (smem <= std::min<size_t>(h->smem_optin, 200 * 1024) && bbm_opt(h, "bbb.mm_kernel", 0) != 2) {
-        e = cudaFuncSetAttribute(bbb_matmul_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const i64 blocks = std::min<i64>((Cd->n + 255) / 256, (i64)h->num_sms * 8);
-        if (e == cudaSuccess) bbb_matmul_col_kernel<T><<<(unsigned)blocks, 256, smem, h->stream>>>(p);
+        const bool fixed33 = bbm_opt(h, "bbb.mm_kernel", 0) == 0 && A->P == 9 && B->P == 9 && p.wA == 3 && p.wB == 3;   // (1,1),(1,1) x (1,1),(1,1) and kin
+        if (fixed33) {
+            e = cudaFuncSetAttribute(bbb_matmul_col_fixed_kernel<T, 3, 3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) bbb_matmul_col_fixed_kernel<T, 3, 3, 3, 3><<<(unsigned)blocks, 256, smem, h->stream>>>(p);
+        } else {
+            e = cudaFuncSetAttribute(bbb_matmul_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) bbb_matmul_col_kernel<T><<<(unsigned)blocks, 256, smem, h->stream>>>(p);
+        }
     } else {
         const i64 blocks = std::min<i64>((total + 255) / 256, (i64)h->num_sms * 32);
         bbb_matmul_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(p);

@@ -439,7 +439,7 @@ BBB_MM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", [0, 2], ids=["column", "entry"])
+@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["auto", "column", "entry"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("case", BBB_MM_CASES, ids=lambda c: f"n{len(c[0])}_A{c[1]}{c[2]}_B{c[3]}{c[4]}".replace(" ", ""))
 def test_bbb_matmul_matches_oracle(handle, case, dtype, kernel):
@@ -485,6 +485,13 @@ def test_bbb_matmul_errors(handle):
         B.mul_(Cn, A, A)
     Cw = B.BandedBlockBandedMatrix.zeros(np.float64, rows, rows, (2, 2), (3, 3)).to_device(handle)   # wider C is fine
     B.mul_(Cw, A, A)
+    rng = np.random.default_rng(63)
+    Ah = B.BandedBlockBandedMatrix(random_bbb(rng, rows, rows, 1, 1, 1, 1), rows, rows, (1, 1), (1, 1))
+    for luC, lmC in (((2, 2), (3, 3)), ((3, 2), (2, 4))):               # products landing inside a wider C
+        Cw = B.BandedBlockBandedMatrix.zeros(np.float64, rows, rows, luC, lmC).to_device(handle).data.fill_bytes(0xFF)
+        Cw = B.BandedBlockBandedMatrix(Cw, rows, rows, luC, lmC)
+        B.mul_(Cw, Ah.to_device(handle), Ah.to_device(handle))
+        assert relerr(Cw.to_dense(), Ah.to_dense() @ Ah.to_dense()) <= tol(np.float64, 10)
     with pytest.raises(B.DimensionMismatch):
         B.mul_(Cw, A, B.BandedBlockBandedMatrix.zeros(np.float64, [3, 4, 5, 1], rows, (1, 1), (1, 1)).to_device(handle))
 
