@@ -6,6 +6,9 @@
  *   mul!(y, A::BlockSkylineMatrix, x) / A*X     
  *   mul!(C, A::BlockSkylineMatrix, B::...)      
  *   ldiv!(Upper/LowerTriangular(A), B)          
+ * and of the callers either side of it: A'x for both formats, A*B in band storage,
+ * the triangular BandedBlockBandedMatrix substitution, qr!/ql! with lmul!(Q',B) and F \ B
+ * (src/blockskylineqr.jl),
  * i.e. the [upstream BlockArrays/ArrayLayouts/BandedMatrices] block loops, whose bounds and
  * operands come from the reference files cited at each function, calling one BLAS routine per
  * block (gbmv / gemv / gemm / trsv).  The BLAS routines are either the small reference-order
@@ -16,7 +19,8 @@
  * load this library.  The product never links or calls it.
  *
  * Parity status: layout pinned by the reference's integer goldens (tests/test_oracle_golden.py);
- * arithmetic pinned to "structured ~= dense", which is all the reference's own tests pin.
+ * arithmetic pinned to "structured ~= dense", which is all the reference's own tests pin; the QR/QL
+ * factors and taus are pinned to LAPACK's dense geqrf, as test/test_blockskylineqr.jl pins them.
  */
 #include <dlfcn.h>
 #include <math.h>
