@@ -260,6 +260,8 @@ QR_GPU_CASES = [
     ([100, 70, 129, 33], [100, 70, 129, 33], 2, 1),    # ragged, three doubling levels, odd leading dimensions
     ([64] * 12, [64] * 12, 1, 2),
     ([7], [7], 0, 0),
+    ([4, 0, 3, 5], [4, 0, 3, 5], 1, 1),                # zero-size block
+    ([0, 3, 2], [0, 3, 2], 1, 1),
 ]
 
 
@@ -344,6 +346,7 @@ QL_GPU_CASES = [
     ([100, 70, 129, 33], 2, 1),
     ([64] * 10, 1, 2),
     ([7], 0, 0),
+    ([3, 2, 0, 4], 2, 1),                       # zero-size block
 ]
 
 
