@@ -240,7 +240,8 @@ def test_bbb_sparse_export(handle, dtype, base):
     the device CSC arrays equal the restated per-block triplet construction and reproduce Matrix(A)."""
     import scipy.sparse as sp
     for rows, cols, lu, lm in [(list(range(1, 11)), list(range(1, 11)), (1, 1), (1, 1)), ([5, 0, 3, 7], [4, 2, 0, 6, 3], (1, 2), (2, 1)),
-                               ([300, 17, 64], [300, 17, 64], (1, 1), (0, 2)), ([4] * 5, [4] * 5, (-1, 2), (1, 1)), ([3, 3], [2, 2], (0, 0), (-1, 0))]:
+                               ([300, 17, 64], [300, 17, 64], (1, 1), (0, 2)), ([4] * 5, [4] * 5, (-1, 2), (1, 1)), ([3, 3], [2, 2], (0, 0), (-1, 0)),
+                               ([], [], (1, 1), (1, 1)), ([0, 0], [0], (1, 1), (1, 1))]:
         rng = np.random.default_rng(81)
         data = random_bbb(rng, rows, cols, *lu, *lm, dtype)
         A = B.BandedBlockBandedMatrix(data, rows, cols, lu, lm)
