@@ -55,6 +55,21 @@ struct bbm_bbb_desc {
     i64* dR = nullptr;
     i64* dC = nullptr;
     std::map<std::pair<int, int>, Partition> parts;  // (tile, target items) -> partition
+    // Launch plans of the band-walk kernel: everything bbb_mul_impl derives from (descriptor, element type,
+    // right-hand-side class, options, fused-halo geometry) -- tile, stages, partition, shared-memory size, the
+    // kernel's address with its attribute already set -- so that a repeated product costs one cudaLaunchKernelExC
+    // on the host (the 8-GPU step is ~30 us: a few tens of microseconds of host work per call would bound it).
+    struct WalkPlan {
+        i64 gen = -1;
+        int elem = 0, nr = 0, peer = 0, own_J0 = 0, own_J1 = 0, force = 0;
+        bool walk = false;
+        int tile = 0, stages = 0, dbytes = 0, xbytes = 0, maxseg = 0, nitems = 0, pdl = 0, l2hint = 1;
+        const BbbItem* d_items = nullptr;
+        size_t smem = 0;
+        int consumers[2] = {0, 0};
+        const void* func = nullptr;
+    };
+    std::vector<WalkPlan> plans;
     // block-row chunks of the pipelined host-vector product (sub-view descriptors, built on first use)
     struct HostChunk { i64 Ka, Kb, Jl, Jh; bbm_bbb_desc_t sub; };
     std::vector<HostChunk> chunks;
@@ -86,7 +101,12 @@ struct BbbParams {
     BbmPeerParams peer;    // fused halo push over NVLink peer memory (enabled == 0: plain kernel)
     int nrhs;              // right-hand sides (multi-vector kernel); keep new fields at the END: ptxas' code for the
                            // single-vector kernel proved sensitive to the parameter layout (5 % on cfg2)
+    int pdl_early;         // != 0: release the dependent launch at the first step instead of the last one
 };
+
+template <typename T> __device__ __forceinline__ T bbm_nan();
+template <> __device__ __forceinline__ double bbm_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <> __device__ __forceinline__ float bbm_nan<float>() { return __int_as_float(0x7fc00000); }
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
@@ -96,12 +116,56 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// bounded wait for a flag written by another GPU (about a second, then the call is marked failed)
-__device__ __forceinline__ void peer_wait(const unsigned* flag, unsigned epoch, unsigned* err) {
+// Wait for a flag written by another GPU.  timeout_clk == 0 waits for ever (what an NCCL receive would do);
+// otherwise the wait gives up after that many SM clocks, latches the plan's error words (device block and the
+// host-mapped word the next call checks) and returns false: the caller then poisons what it would have computed.
+__device__ __forceinline__ bool peer_wait(const unsigned* flag, unsigned epoch, const BbmPeerParams& pe) {
+    if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return true;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
         __nanosleep(64);
-        if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1u); break; }
+        if (pe.timeout_clk > 0 && clock64() - t0 > pe.timeout_clk) {
+            atomicExch(&pe.local->err, 1u);
+            if (pe.err_host) { *reinterpret_cast<volatile unsigned*>(pe.err_host) = 1u; __threadfence_system(); }
+            return false;
+        }
+    }
+    return true;
+}
+
+// The pusher CTA of the fused multi-GPU step (blockIdx.x == 0, always in the first wave): store my boundary x
+// blocks into the neighbours' halo buffers of this epoch's parity and publish the epoch.  The buffer was last
+// read two epochs ago.  If the acknowledgement of that read never arrives, nothing is pushed and nothing is
+// published (the neighbour's own wait then expires and it poisons its rows) -- never overwrite a buffer in use.
+template <typename T>
+__device__ __forceinline__ void peer_push(const BbmPeerParams& pe, const T* X, int tid, int nthreads) {
+    __shared__ int push_ok[2];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // x may come from the previous kernel in the stream
+    if (tid == 0) {
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            push_ok[sd] = 1;
+            if (pe.epoch >= 2 && pe.dst[sd] && pe.ack_wait[sd]) push_ok[sd] = peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, pe) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!pe.dst[sd] || !push_ok[sd]) continue;
+        T* dst = static_cast<T*>(pe.dst[sd]);
+        const T* src = X + pe.src_off[sd];
+        for (long long i = tid; i < pe.cnt[sd]; i += nthreads) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        // I am the RIGHT neighbour of my left neighbour, and vice versa
+        if (pe.dst[0] && push_ok[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
+        if (pe.dst[1] && push_ok[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
+        // a halo nobody reads (no work item touches it) is acknowledged at once
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd)
+            if (pe.ack_send[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
     }
 }
 
@@ -134,35 +198,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     const int S = p.stages;
 
     if (p.peer.enabled && blockIdx.x == 0) {
-        // dedicated pusher CTA (always in the first wave): store my boundary x blocks into the neighbours'
-        // halo buffers of this epoch's parity and publish the epoch.  The buffer was last read two epochs ago.
-        const BbmPeerParams& pe = p.peer;
-        if (blockIdx.y != 0) return;
-        asm volatile("griddepcontrol.wait;" ::: "memory");   // x may come from the previous kernel in the stream
-        if (tid == 0 && pe.epoch >= 2) {
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                if (pe.dst[sd] && pe.ack_wait[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, &pe.local->err);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            if (!pe.dst[sd]) continue;
-            T* dst = static_cast<T*>(pe.dst[sd]);
-            const T* src = p.X + pe.src_off[sd];
-            for (long long i = tid; i < pe.cnt[sd]; i += tile) dst[i] = src[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            // I am the RIGHT neighbour of my left neighbour, and vice versa
-            if (pe.dst[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
-            if (pe.dst[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
-            // a halo nobody reads (no work item touches it) is acknowledged at once
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                if (pe.ack_send[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
-        }
+        if (blockIdx.y == 0) peer_push<T>(p.peer, p.X, tid, tile);
         return;
     }
     const BbbItem item = p.items[p.peer.enabled ? blockIdx.x - 1 : blockIdx.x];
@@ -171,7 +207,8 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     const int nsteps = (Kb - Ka) + NS - 1;
 
     // shared memory carve-up
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                       // S barriers (<= 16)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                       // S barriers (<= 8)
+    volatile int* poison = reinterpret_cast<volatile int*>(smem + 120);       // a halo never arrived: rows become NaN
     i64* Rtab = reinterpret_cast<i64*>(smem + 128);                           // maxseg+1
     i64* Ctab = Rtab + (p.maxseg + 1);                                        // maxseg+NS+1
     size_t tab_bytes = 128 + sizeof(i64) * (size_t)(2 * p.maxseg + NS + 2);
@@ -191,6 +228,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     if (tid == 0) {
         for (int s = 0; s < S; ++s) ptx::mbar_init(&bars[s], 1);
         ptx::fence_mbar_init();
+        *poison = 0;
     }
     __syncthreads();
     // Programmatic dependent launch: everything above only touched the descriptor's tables (written at plan
@@ -242,7 +280,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
         if (halo_side >= 0) {
             // a halo block column: its x block is stored by the neighbour's pusher CTA -- wait for its epoch
             // flag, then order the (generic-proxy) acquire before the async-proxy bulk read
-            peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, &p.peer.local->err);
+            if (!peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, p.peer)) *poison = 1;
             asm volatile("fence.proxy.async;" ::: "memory");
         }
         if (p.l2hint) ptx::bulk_g2s_hint(sx, reinterpret_cast<const void*>(xg0), xbytes, &bars[st], pol_keep);
@@ -263,7 +301,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
     for (int it = 0; it < nsteps; ++it) {
         // every thread has finished reading the stage that step it+S-1 will overwrite
         __syncthreads();
-        if (it == nsteps - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // successor may set up
+        if (it == (p.pdl_early ? 0 : nsteps - 1)) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // successor may set up
         if (tid == 0 && it + S - 1 < nsteps) issue(it + S - 1);
 
         const int st = it % S;
@@ -354,6 +392,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
             if (k < rK) {
                 T y = alpha * acc[0];
                 if (beta != T(0)) y = fma(beta, Yq[r0 + k], y);
+                if (p.peer.enabled && *poison) y = bbm_nan<T>();
                 Yq[r0 + k] = y;
             }
         }
@@ -396,35 +435,7 @@ __global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) 
     const int S = p.stages;
 
     if (p.peer.enabled && blockIdx.x == 0) {
-        // dedicated pusher CTA (always in the first wave): store my boundary x blocks into the neighbours'
-        // halo buffers of this epoch's parity and publish the epoch.  The buffer was last read two epochs ago.
-        const BbmPeerParams& pe = p.peer;
-        if (blockIdx.y != 0) return;
-        asm volatile("griddepcontrol.wait;" ::: "memory");   // x may come from the previous kernel in the stream
-        if (tid == 0 && pe.epoch >= 2) {
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                if (pe.dst[sd] && pe.ack_wait[sd]) peer_wait(&pe.local->ack_flag[sd], pe.epoch - 2, &pe.local->err);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            if (!pe.dst[sd]) continue;
-            T* dst = static_cast<T*>(pe.dst[sd]);
-            const T* src = p.X + pe.src_off[sd];
-            for (long long i = tid; i < pe.cnt[sd]; i += tile) dst[i] = src[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            // I am the RIGHT neighbour of my left neighbour, and vice versa
-            if (pe.dst[0]) st_release_sys(&pe.remote[0]->data_flag[1], pe.epoch);
-            if (pe.dst[1]) st_release_sys(&pe.remote[1]->data_flag[0], pe.epoch);
-            // a halo nobody reads (no work item touches it) is acknowledged at once
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                if (pe.ack_send[sd] && pe.consumers[sd] == 0) st_release_sys(&pe.remote[sd]->ack_flag[1 - sd], pe.epoch);
-        }
+        if (blockIdx.y == 0) peer_push<T>(p.peer, p.X, tid, tile);
         return;
     }
     const BbbItem item = p.items[p.peer.enabled ? blockIdx.x - 1 : blockIdx.x];
@@ -433,7 +444,8 @@ __global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) 
     const int nsteps = (Kb - Ka) + NS - 1;
 
     // shared memory carve-up
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                       // S barriers (<= 16)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                       // S barriers (<= 8)
+    volatile int* poison = reinterpret_cast<volatile int*>(smem + 120);       // a halo never arrived: rows become NaN
     i64* Rtab = reinterpret_cast<i64*>(smem + 128);                           // maxseg+1
     i64* Ctab = Rtab + (p.maxseg + 1);                                        // maxseg+NS+1
     size_t tab_bytes = 128 + sizeof(i64) * (size_t)(2 * p.maxseg + NS + 2);
@@ -456,6 +468,7 @@ __global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) ptx::mbar_init(&bars[s], 1);
         ptx::fence_mbar_init();
+        *poison = 0;
     }
     __syncthreads();
     // Programmatic dependent launch: everything above only touched the descriptor's tables (written at plan
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) 
         if (halo_side >= 0) {
             // a halo block column: its x block is stored by the neighbour's pusher CTA -- wait for its epoch
             // flag, then order the (generic-proxy) acquire before the async-proxy bulk read
-            peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, &p.peer.local->err);
+            if (!peer_wait(&p.peer.local->data_flag[halo_side], p.peer.epoch, p.peer)) *poison = 1;
             asm volatile("fence.proxy.async;" ::: "memory");
         }
 #pragma unroll
@@ -548,7 +561,7 @@ __global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) 
     for (int it = 0; it < nsteps; ++it) {
         // every thread has finished reading the stage that step it+S-1 will overwrite
         __syncthreads();
-        if (it == nsteps - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // successor may set up
+        if (it == (p.pdl_early ? 0 : nsteps - 1)) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // successor may set up
         if (tid == 0 && it + S - 1 < nsteps) issue(it + S - 1);
 
         const int st = it % S;
@@ -651,6 +664,7 @@ __global__ void __launch_bounds__(256) bbb_walk_mr_kernel(const BbbParams<T> p) 
                     T* yp = Yq + (i64)q * p.ldy + r0 + k;
                     T y = alpha * acc[0][q];
                     if (beta != T(0)) y = fma(beta, *yp, y);
+                    if (p.peer.enabled && *poison) y = bbm_nan<T>();
                     *yp = y;
                 }
             }
@@ -841,45 +855,125 @@ int32_t build_partition(bbm_bbb_desc_t d, int tile, int slots, int maxseg_cap, i
     return BBM_OK;
 }
 
-// grid.x == 0: do not launch, report the resident CTAs per SM for (tile, smem) in *occ instead
+// address of the band-walk kernel instantiation for (NS block bands, w sub-bands, nr right-hand sides per CTA)
 template <typename T, int NS>
-cudaError_t launch_walk_w(const BbbParams<T>& p, int w, int nr, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ, bool pdl) {
-    auto go = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (grid.x == 0) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, tile, smem);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)tile); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-        return cudaLaunchKernelEx(&cfg, kern, p);
-    };
+const void* walk_kernel_w(int w, int nr) {
     if (nr == 4) {
-        if (w == 3) return go(bbb_walk_mr_kernel<T, NS, 3, 4>);
-        if (w == 5) return go(bbb_walk_mr_kernel<T, NS, 5, 4>);
-        return go(bbb_walk_mr_kernel<T, NS, 0, 4>);
+        if (w == 3) return reinterpret_cast<const void*>(&bbb_walk_mr_kernel<T, NS, 3, 4>);
+        if (w == 5) return reinterpret_cast<const void*>(&bbb_walk_mr_kernel<T, NS, 5, 4>);
+        return reinterpret_cast<const void*>(&bbb_walk_mr_kernel<T, NS, 0, 4>);
     }
-    if (w == 3) return go(bbb_walk_kernel<T, NS, 3>);
-    if (w == 5) return go(bbb_walk_kernel<T, NS, 5>);
-    return go(bbb_walk_kernel<T, NS, 0>);
+    if (w == 3) return reinterpret_cast<const void*>(&bbb_walk_kernel<T, NS, 3>);
+    if (w == 5) return reinterpret_cast<const void*>(&bbb_walk_kernel<T, NS, 5>);
+    return reinterpret_cast<const void*>(&bbb_walk_kernel<T, NS, 0>);
 }
 
 template <typename T>
-cudaError_t launch_walk(const BbbParams<T>& p, int NS, int w, int nr, dim3 grid, int tile, size_t smem, cudaStream_t st, int* occ = nullptr,
-                        bool pdl = false) {
+const void* walk_kernel(int NS, int w, int nr) {
     switch (NS) {
-        case 1: return launch_walk_w<T, 1>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 2: return launch_walk_w<T, 2>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 3: return launch_walk_w<T, 3>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 4: return launch_walk_w<T, 4>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 5: return launch_walk_w<T, 5>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 6: return launch_walk_w<T, 6>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 7: return launch_walk_w<T, 7>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        case 8: return launch_walk_w<T, 8>(p, w, nr, grid, tile, smem, st, occ, pdl);
-        default: return cudaErrorInvalidValue;
+        case 1: return walk_kernel_w<T, 1>(w, nr);
+        case 2: return walk_kernel_w<T, 2>(w, nr);
+        case 3: return walk_kernel_w<T, 3>(w, nr);
+        case 4: return walk_kernel_w<T, 4>(w, nr);
+        case 5: return walk_kernel_w<T, 5>(w, nr);
+        case 6: return walk_kernel_w<T, 6>(w, nr);
+        case 7: return walk_kernel_w<T, 7>(w, nr);
+        case 8: return walk_kernel_w<T, 8>(w, nr);
+        default: return nullptr;
     }
+}
+
+// Builds the launch plan of the band-walk kernel for (descriptor, T, nr, options, fused-halo geometry); plan->walk
+// stays false when the generic kernel has to take the product.
+template <typename T>
+int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::WalkPlan* plan) {
+    const i64 NS = d->l + d->u + 1;
+    const int w = (int)(d->lam + d->mu + 1);
+    const i64 force = bbm_opt(h, "bbb.kernel", 0);
+    plan->walk = false;
+    plan->l2hint = (int)bbm_opt(h, "bbb.l2hint", 1);
+    bool walk = d->P > 0 && NS >= 1 && NS <= kMaxNS && force != 2;
+    // tiny blocks leave the 32..256-row tiles mostly idle: use the per-row kernel
+    if (walk && force != 1 && d->m < 16 * d->Nr && !h->peer) walk = false;
+    if (!walk) return BBM_OK;
+    const void* func = walk_kernel<T>((int)NS, w, nr);
+    if (!func) return BBM_OK;
+
+    int tile = 0, stages = 0, dbytes = 0, xbytes = 0;
+    // measured on B200: 4 stages saturate HBM; 5-6 stages (more smem, same occupancy) are 5% slower on cfg2
+    const int want_stages = (int)std::min<i64>(8, std::max<i64>(2, bbm_opt(h, "bbb.stages", 4)));
+    const i64 forced_tile = bbm_opt(h, "bbb.tile", 0);
+    if (forced_tile && (forced_tile < 32 || forced_tile > 256 || forced_tile % 32))
+        return bbm_fail(h, BBM_ERR_ARG, "bbb.tile must be a multiple of 32 in [32,256]");
+    const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
+    const size_t soft = (228 * 1024 - 2 * 1024) / 2 - 256;  // two CTAs per SM (1 KB reserved per CTA)
+    const int cands[4] = {forced_tile ? (int)forced_tile : 256, 128, 64, 32};
+    const int ncand = forced_tile ? 1 : 4;
+    const size_t tabs = walk_tab_bytes(512, (int)NS);
+    // pass 0: >= 3 stages within the two-CTA budget; pass 1: >= 2 stages within the opt-in limit
+    for (int pass = 0; pass < 2 && !tile; ++pass) {
+        const size_t limit = pass == 0 ? soft : budget;
+        const int min_stages = pass == 0 ? 3 : 2;
+        for (int ci = 0; ci < ncand && !tile; ++ci) {
+            const int t = cands[ci];
+            if (!forced_tile && t > 32 && t / 2 >= d->maxr) continue;  // tile twice the largest block: mostly idle
+            walk_stage_bytes<T>(t, w, d->P, &dbytes, &xbytes);
+            const size_t per = (size_t)dbytes + (size_t)nr * xbytes;
+            if (limit <= tabs) continue;
+            const int s = (int)std::min<size_t>(want_stages, (limit - tabs) / per);
+            if (s >= min_stages) { tile = t; stages = s; }
+        }
+    }
+    if (!tile) return BBM_OK;  // P too large for shared memory staging
+
+    walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
+    const int maxseg_cap = (int)std::min<i64>(512, std::max<i64>(1, bbm_opt(h, "bbb.maxseg", 512)));
+    // slots = whole waves of resident CTAs (table size taken at its cap: a few KB either way).  "bbb.ctas_per_sm"
+    // overrides the occupancy (programmatic dependent launch wants a free slot per SM for the successor's CTAs).
+    int occ = 1;
+    {
+        const size_t smem_cap = walk_tab_bytes(maxseg_cap, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
+        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, tile, smem_cap);
+        if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
+        occ = std::max(1, occ);
+        const i64 cps = bbm_opt(h, "bbb.ctas_per_sm", 0);
+        if (cps > 0) occ = (int)std::min<i64>(occ, cps);
+    }
+    const i64 ips = bbm_opt(h, "bbb.items_per_sm", 0);
+    const i64 waves = std::max<i64>(1, bbm_opt(h, "bbb.waves", 1));
+    // the fused multi-GPU path adds one pusher CTA: leave it a slot of the wave
+    const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves) - (h->peer ? 1 : 0);
+    const int lead_steps = (h->peer && h->peer->has_halo[0]) ? (int)std::max<i64>(0, bbm_opt(h, "dist.lead_steps", 0)) : 0;
+    auto key = std::make_pair(tile * 64 + lead_steps + 65536 * (int)bbm_opt(h, "bbb.ovh", 4096), target_items * 1024 + maxseg_cap);
+    auto it = d->parts.find(key);
+    if (it == d->parts.end()) {
+        Partition part;
+        int32_t rc = build_partition(d, tile, target_items, maxseg_cap, lead_steps, &part);
+        if (rc != BBM_OK) return rc;
+        it = d->parts.emplace(key, part).first;
+    }
+    const Partition& part = it->second;
+    if (part.nitems == 0) return BBM_OK;
+    plan->consumers[0] = plan->consumers[1] = 0;
+    if (h->peer) {
+        for (const BbbItem& bi : part.items) {
+            if ((i64)bi.Ka - d->l < h->peer->own_J0) ++plan->consumers[0];
+            if ((i64)bi.Kb - 1 + d->u >= h->peer->own_J1) ++plan->consumers[1];
+        }
+    }
+    plan->tile = tile; plan->stages = stages; plan->dbytes = dbytes; plan->xbytes = xbytes;
+    plan->maxseg = part.maxseg; plan->nitems = part.nitems; plan->d_items = part.d_items;
+    plan->smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
+    plan->func = func;
+    // "bbb.pdl": 0 plain launch; 1 programmatic dependent launch released at the last step; 2 released at the FIRST
+    // step -- with a CTA slot per SM left free ("bbb.stages" = 3 makes three CTAs fit, the partition fills two) the
+    // successor's CTAs are placed, read their tables and arm their barriers while this kernel still streams
+    plan->pdl = (int)bbm_opt(h, "bbb.pdl", 0);
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem);
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "cudaFuncSetAttribute(bbb_walk_kernel): %s", cudaGetErrorString(e));
+    plan->walk = true;
+    return BBM_OK;
 }
 
 template <typename T>
@@ -902,103 +996,57 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
     p.R = d->dR; p.C = d->dC; p.Nr = d->Nr; p.Nc = d->Nc; p.m = d->m;
     p.l = (int)d->l; p.u = (int)d->u; p.lam = (int)d->lam; p.mu = (int)d->mu;
     p.w = (int)(d->lam + d->mu + 1); p.P = (int)d->P;
-    p.l2hint = (int)bbm_opt(h, "bbb.l2hint", 1);
     p.tri = tri; p.unit = unit; p.nrhs = (int)nrhs;
     if (tri && (d->Nr != d->Nc || d->r != d->c))  // hasmatchingblocks, src/triblockbanded.jl:12,20
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "triangular product needs matching square diagonal blocks");
-
-    const i64 NS = d->l + d->u + 1;
-    const int w = p.w;
-    const i64 force = bbm_opt(h, "bbb.kernel", 0);
-    bool walk = d->P > 0 && NS >= 1 && NS <= kMaxNS && force != 2;
-    // tiny blocks leave the 32..256-row tiles mostly idle: use the per-row kernel
-    if (walk && force != 1 && d->m < 16 * d->Nr && !h->peer) walk = false;
-    if (h->peer && (!walk || nrhs != 1)) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs the band-walk kernel and one right-hand side");
     const bool aligned = (reinterpret_cast<uintptr_t>(d_data) % sizeof(T) == 0) && (reinterpret_cast<uintptr_t>(d_X) % sizeof(T) == 0);
     if (!aligned) return bbm_fail(h, BBM_ERR_ARG, "device pointers must be aligned to the element size");
+    if (h->peer && nrhs != 1) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs the band-walk kernel and one right-hand side");
 
-    int tile = 0, stages = 0, dbytes = 0, xbytes = 0;
     const int nr = (nrhs >= 2 && !h->peer) ? 4 : 1;  // right-hand sides per CTA of the band-walk kernel
-    if (walk) {
-        // measured on B200: 4 stages saturate HBM; 5-6 stages (more smem, same occupancy) are 5% slower on cfg2
-        const int want_stages = (int)std::min<i64>(8, std::max<i64>(2, bbm_opt(h, "bbb.stages", 4)));
-        const i64 forced_tile = bbm_opt(h, "bbb.tile", 0);
-        if (forced_tile && (forced_tile < 32 || forced_tile > 256 || forced_tile % 32))
-            return bbm_fail(h, BBM_ERR_ARG, "bbb.tile must be a multiple of 32 in [32,256]");
-        const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
-        const size_t soft = (228 * 1024 - 2 * 1024) / 2 - 256;  // two CTAs per SM (1 KB reserved per CTA)
-        const int cands[4] = {forced_tile ? (int)forced_tile : 256, 128, 64, 32};
-        const int ncand = forced_tile ? 1 : 4;
-        const size_t tabs = walk_tab_bytes(512, (int)NS);
-        // pass 0: >= 3 stages within the two-CTA budget; pass 1: >= 2 stages within the opt-in limit
-        for (int pass = 0; pass < 2 && !tile; ++pass) {
-            const size_t limit = pass == 0 ? soft : budget;
-            const int min_stages = pass == 0 ? 3 : 2;
-            for (int ci = 0; ci < ncand && !tile; ++ci) {
-                const int t = cands[ci];
-                if (!forced_tile && t > 32 && t / 2 >= d->maxr) continue;  // tile twice the largest block: mostly idle
-                walk_stage_bytes<T>(t, w, d->P, &dbytes, &xbytes);
-                const size_t per = (size_t)dbytes + (size_t)nr * xbytes;
-                if (limit <= tabs) continue;
-                const int s = (int)std::min<size_t>(want_stages, (limit - tabs) / per);
-                if (s >= min_stages) { tile = t; stages = s; }
-            }
-        }
-        if (!tile) walk = false;  // P too large for shared memory staging
+    bbm_bbb_desc::WalkPlan* plan = nullptr;
+    for (auto& pl : d->plans)
+        if (pl.gen == h->opt_gen && pl.elem == (int)sizeof(T) && pl.nr == nr && pl.peer == (h->peer ? 1 : 0) &&
+            (!h->peer || (pl.own_J0 == h->peer->own_J0 && pl.own_J1 == h->peer->own_J1))) { plan = &pl; break; }
+    if (!plan) {
+        bbm_bbb_desc::WalkPlan np;
+        np.gen = h->opt_gen; np.elem = (int)sizeof(T); np.nr = nr; np.peer = h->peer ? 1 : 0;
+        if (h->peer) { np.own_J0 = h->peer->own_J0; np.own_J1 = h->peer->own_J1; }
+        int32_t rc = build_walk_plan<T>(h, d, nr, &np);
+        if (rc != BBM_OK) return rc;
+        if (d->plans.size() >= 16) d->plans.erase(d->plans.begin());   // stale option generations
+        d->plans.push_back(np);
+        plan = &d->plans.back();
     }
-    if (h->peer && !walk) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs the band-walk kernel");
+    p.l2hint = plan->l2hint;
+    if (h->peer && !plan->walk) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push needs the band-walk kernel");
 
-    if (walk) {
-        walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
-        const int maxseg_cap = (int)std::min<i64>(512, std::max<i64>(1, bbm_opt(h, "bbb.maxseg", 512)));
-        // slots = whole waves of resident CTAs (table size taken at its cap: a few KB either way)
-        int occ = 1;
-        {
-            const size_t smem_cap = walk_tab_bytes(maxseg_cap, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
-            cudaError_t e = launch_walk<T>(p, (int)NS, w, nr, dim3(0, 1, 1), tile, smem_cap, h->stream, &occ);
-            if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
-            occ = std::max(1, occ);
+    if (plan->walk) {
+        p.items = plan->d_items;
+        if (h->peer) {
+            p.peer = *h->peer;
+            p.peer.consumers[0] = plan->consumers[0];
+            p.peer.consumers[1] = plan->consumers[1];
         }
-        const i64 ips = bbm_opt(h, "bbb.items_per_sm", 0);
-        const i64 waves = std::max<i64>(1, bbm_opt(h, "bbb.waves", 1));
-        // the fused multi-GPU path adds one pusher CTA: leave it a slot of the wave
-        const int target_items = (int)(ips > 0 ? h->num_sms * ips : h->num_sms * occ * waves) - (h->peer ? 1 : 0);
-        const int lead_steps = (h->peer && h->peer->has_halo[0]) ? (int)std::max<i64>(0, bbm_opt(h, "dist.lead_steps", 0)) : 0;
-        auto key = std::make_pair(tile * 64 + lead_steps + 65536 * (int)bbm_opt(h, "bbb.ovh", 4096), target_items * 1024 + maxseg_cap);
-        auto it = d->parts.find(key);
-        if (it == d->parts.end()) {
-            Partition part;
-            int32_t rc = build_partition(d, tile, target_items, maxseg_cap, lead_steps, &part);
-            if (rc != BBM_OK) return rc;
-            it = d->parts.emplace(key, part).first;
-        }
-        const Partition& part = it->second;
-        if (h->peer && part.nitems == 0) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push: empty work partition");
-        if (part.nitems > 0) {
-            walk_stage_bytes<T>(tile, w, d->P, &dbytes, &xbytes);
-            p.items = part.d_items;
-            if (h->peer) {
-                p.peer = *h->peer;
-                p.peer.consumers[0] = p.peer.consumers[1] = 0;
-                for (const BbbItem& it : part.items) {
-                    if ((i64)it.Ka - d->l < p.peer.own_J0) ++p.peer.consumers[0];
-                    if ((i64)it.Kb - 1 + d->u >= p.peer.own_J1) ++p.peer.consumers[1];
-                }
-            }
-            p.stages = stages;
-            p.maxseg = part.maxseg;
-            p.stage_data_bytes = dbytes;
-            p.stage_x_bytes = nr * xbytes;
-            const size_t smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
-            dim3 grid((unsigned)part.nitems + (h->peer ? 1u : 0u), (unsigned)((nrhs + nr - 1) / nr), 1);
-            // programmatic dependent launch is wired in ("bbb.pdl" = 1) but off: with one full wave resident the
-            // successor's CTAs cannot be placed before the predecessor's exit, and it measured no gain (35.5 us
-            // per step either way at the 8-GPU per-rank size)
-            cudaError_t e = launch_walk<T>(p, (int)NS, w, nr, grid, tile, smem, h->stream, nullptr, bbm_opt(h, "bbb.pdl", 0) != 0);
-            if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_walk_kernel launch: %s", cudaGetErrorString(e));
-            h->launches += 1;
-            return BBM_OK;
-        }
+        p.stages = plan->stages;
+        p.maxseg = plan->maxseg;
+        p.stage_data_bytes = plan->dbytes;
+        p.stage_x_bytes = nr * plan->xbytes;
+        p.pdl_early = plan->pdl == 2 ? 1 : 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)plan->nitems + (h->peer ? 1u : 0u), (unsigned)((nrhs + nr - 1) / nr), 1);
+        cfg.blockDim = dim3((unsigned)plan->tile);
+        cfg.dynamicSmemBytes = plan->smem;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = plan->pdl ? 1 : 0;
+        void* args[1] = {&p};
+        cudaError_t e = cudaLaunchKernelExC(&cfg, plan->func, args);
+        if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_walk_kernel launch: %s", cudaGetErrorString(e));
+        h->launches += 1;
+        return BBM_OK;
     }
     {
         const int threads = 256;

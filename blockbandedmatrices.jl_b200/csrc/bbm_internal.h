@@ -47,6 +47,8 @@ struct BbmPeerParams {
     int ack_wait[2] = {0, 0};                     // I push to that side but receive nothing from it
     int ack_send[2] = {0, 0};                     // I receive from that side but push nothing to it
     int consumers[2] = {0, 0};                    // CTAs reading each halo (filled by the launcher)
+    long long timeout_clk = 0;                    // SM clocks a peer wait may take; 0 = wait for ever
+    unsigned* err_host = nullptr;                 // host-mapped word latched by a timed-out wait (checked by the next call)
 };
 
 struct bbm_context {
@@ -57,6 +59,7 @@ struct bbm_context {
     size_t smem_optin = 0;
     std::string err;
     std::map<std::string, i64> opts;
+    i64 opt_gen = 0;   // bumped by bbm_set_option: cached launch plans are keyed on it
     i64 launches = 0;
     // workspace for the *_host_* calls (device copies of X and Y)
     void* ws_x = nullptr; size_t ws_x_bytes = 0;

@@ -4,8 +4,8 @@
 #include "bbm_internal.h"
 
 static const char* const kOptionKeys[] = {
-    "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves", "bbb.host_chunks", "bbb.ovh", "bbb.mm_kernel", "bbb.pdl",
-    "sky.kernel", "sky.mv_split", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "dist.graph", "dist.peer", "dist.lead_steps", nullptr};
+    "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.waves", "bbb.host_chunks", "bbb.ovh", "bbb.mm_kernel", "bbb.pdl", "bbb.ctas_per_sm",
+    "sky.kernel", "sky.mv_split", "sky.mm_kernel", "sky.mm_bk", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "dist.graph", "dist.peer", "dist.lead_steps", "dist.peer_timeout_ms", nullptr};
 
 extern "C" {
 
@@ -80,7 +80,7 @@ int32_t bbm_set_option(bbm_handle_t h, const char* key, int64_t value) {
     BBM_REQUIRE_HANDLE(h);
     if (!key) return bbm_fail(h, BBM_ERR_ARG, "null option key");
     for (int i = 0; kOptionKeys[i]; ++i)
-        if (strcmp(kOptionKeys[i], key) == 0) { h->opts[key] = value; return BBM_OK; }
+        if (strcmp(kOptionKeys[i], key) == 0) { h->opts[key] = value; ++h->opt_gen; return BBM_OK; }
     return bbm_fail(h, BBM_ERR_ARG, "unknown option '%s'", key);
 }
 

@@ -135,6 +135,9 @@ struct bbm_dist_bbb_plan {
     size_t own_buf[2][2] = {{0, 0}, {0, 0}}; // [side][parity] byte offsets of my halo buffers in my block
     size_t nb_buf[2][2] = {{0, 0}, {0, 0}};  // [side][parity] byte offsets of the buffers I fill in the neighbours' blocks
     bbm_bbb_desc_t desc_all = nullptr;
+    unsigned* err_host = nullptr;     // host-mapped word a timed-out peer wait latches (checked before every product)
+    unsigned* err_host_dev = nullptr; // its device address
+    int clock_khz = 0;                // SM clock (peer-wait time-out in clocks)
     cudaGraphExec_t gexec = nullptr;  // cached CUDA graph of one whole step
     GraphKey gkey;
     i64 glaunches = 0;
@@ -278,9 +281,20 @@ int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* 
         // ONE kernel per step: a pusher CTA stores the boundary x blocks into the neighbours' halo buffers
         // over NVLink peer memory, halo-reading CTAs wait on the epoch flag, everything else streams as on
         // one GPU.  (The halo parts of x_local are neither read nor written on this path.)
+        // a peer wait of an earlier product expired: that product's rows were poisoned with NaN, the epochs of the
+        // ranks no longer agree -- refuse (every rank sees its own or its neighbour's time-out) instead of computing
+        // on stale halos.  bbm_dist_bbb_enable_peer re-arms the path.
+        if (pl->err_host && *reinterpret_cast<volatile unsigned*>(pl->err_host) != 0)
+            return bbm_fail(h, BBM_ERR_NCCL, "fused halo push: a peer wait timed out in an earlier product (results since are invalid); "
+                                             "call bbm_dist_bbb_enable_peer again or set dist.peer=0");
         BbmPeerParams pp = pl->peer_tpl;
         pp.enabled = 1;
         pp.epoch = ++pl->epoch;
+        {   // "dist.peer_timeout_ms": how long a wait for a neighbour may take (default 30 s; 0 = for ever, like NCCL)
+            const i64 ms = bbm_opt(h, "dist.peer_timeout_ms", 30000);
+            pp.timeout_clk = ms <= 0 ? 0 : (long long)ms * (long long)std::max(1, pl->clock_khz);
+            pp.err_host = pl->err_host_dev;
+        }
         const int par = (int)(pp.epoch & 1u);
         for (int sd = 0; sd < 2; ++sd) {
             pp.halo[sd] = pp.has_halo[sd] ? reinterpret_cast<const char*>(pl->sig) + pl->own_buf[sd][par] : nullptr;
@@ -483,6 +497,7 @@ int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
     for (int i = 0; i < 2; ++i)
         if (pl->ipc_sig[i]) cudaIpcCloseMemHandle(pl->ipc_sig[i]);
     if (pl->sig) cudaFree(pl->sig);
+    if (pl->err_host) cudaFreeHost(pl->err_host);
     pl->magic = 0;
     delete pl;
     return BBM_OK;
@@ -562,33 +577,50 @@ int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t pl, int32_t elem_size) {
                                          pl->u + s, pl->lam, pl->mu, &pl->desc_all);
         if (rc != BBM_OK) ok = false;
     }
-    if (pl->sig) { cudaFree(pl->sig); pl->sig = nullptr; }
+    // From here to the end every rank takes part in two all-gathers: a local failure must not return early (the
+    // peers would hang in the collective) -- it is folded into the ok flag that is gathered.
+    const char* local_fail = nullptr;
+    auto soft = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess) { cudaGetLastError(); ok = false; if (!local_fail) local_fail = what; }
+    };
+    pl->peer_ok = false;
+    // the old block may still be mapped by the neighbours: they close their mappings below before anybody pushes
+    // again, and nobody pushes while peer_ok is false; the block itself is released only after the first all-gather
+    BbmPeerSig* old_sig = pl->sig;
+    pl->sig = nullptr;
     const size_t block_bytes = buf_off(myL, myR, 1, 1) + pad256((size_t)myR * elem_size) + 512;
-    BBM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&pl->sig), block_bytes));
-    BBM_CUDA(h, cudaMemset(pl->sig, 0, block_bytes));
-    BBM_CUDA(h, cudaDeviceSynchronize());
+    soft(cudaMalloc(reinterpret_cast<void**>(&pl->sig), block_bytes), "cudaMalloc(halo block)");
+    if (pl->sig) soft(cudaMemset(pl->sig, 0, block_bytes), "cudaMemset(halo block)");
+    if (!pl->err_host) {
+        soft(cudaHostAlloc(reinterpret_cast<void**>(&pl->err_host), 64, cudaHostAllocMapped), "cudaHostAlloc(error word)");
+        if (pl->err_host) soft(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pl->err_host_dev), pl->err_host, 0), "cudaHostGetDevicePointer");
+    }
+    if (pl->err_host) *pl->err_host = 0;
+    soft(cudaDeviceGetAttribute(&pl->clock_khz, cudaDevAttrClockRate, h->device), "cudaDeviceGetAttribute(clock rate)");
+    soft(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     // all-gather (ok flag, IPC handle of the block) over NCCL
     struct Rec { int ok; int pad[3]; cudaIpcMemHandle_t blk; };
     Rec mine{};
-    mine.ok = ok ? 1 : 0;
-    if (cudaIpcGetMemHandle(&mine.blk, pl->sig) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    if (!pl->sig || cudaIpcGetMemHandle(&mine.blk, pl->sig) != cudaSuccess) { cudaGetLastError(); ok = false; }
     std::vector<Rec> all(nranks);
     Rec* d_all = nullptr;
-    BBM_CUDA(h, cudaMalloc(&d_all, sizeof(Rec) * nranks));
-    BBM_CUDA(h, cudaMemcpy(d_all + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+    // the gather buffer itself: without it this rank cannot take part at all (the one unavoidable early return)
+    if (cudaMalloc(&d_all, sizeof(Rec) * nranks) != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(all-gather buffer)"); }
+    mine.ok = ok ? 1 : 0;
+    soft(cudaMemcpy(d_all + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice), "cudaMemcpy(record)");
     ncclResult_t nrc = nccl().AllGather(d_all + rank, d_all, sizeof(Rec), ncclChar, cm->comm, cm->stream);
-    if (nrc != ncclSuccess) { cudaFree(d_all); return bbm_fail(h, BBM_ERR_NCCL, "ncclAllGather: %s", nccl().GetErrorString(nrc)); }
-    BBM_CUDA(h, cudaStreamSynchronize(cm->stream));
-    BBM_CUDA(h, cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost));
-    bool all_ok = true;
+    if (nrc != ncclSuccess) { cudaFree(d_all); if (old_sig) cudaFree(old_sig); return bbm_fail(h, BBM_ERR_NCCL, "ncclAllGather: %s", nccl().GetErrorString(nrc)); }
+    soft(cudaStreamSynchronize(cm->stream), "cudaStreamSynchronize");
+    soft(cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost), "cudaMemcpy(records)");
+    // every rank has passed the gather: nobody reads the previous blocks any more
+    for (int sd = 0; sd < 2; ++sd)
+        if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
+    bool all_ok = ok;
     for (int q = 0; q < nranks; ++q) all_ok = all_ok && all[q].ok == 1;
-    pl->peer_ok = false;
-    if (!all_ok) { cudaFree(d_all); return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push not applicable to this partition; the NCCL exchange stays in use"); }
-    bool opened = true;
+    bool opened = all_ok;
     for (int sd = 0; sd < 2; ++sd) {
         const int q = sd == 0 ? rank - 1 : rank + 1;
-        if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
-        if (q < 0 || q >= nranks || (tpl.cnt[sd] == 0 && !tpl.has_halo[sd])) continue;
+        if (!all_ok || q < 0 || q >= nranks || (tpl.cnt[sd] == 0 && !tpl.has_halo[sd])) continue;
         cudaError_t e = cudaIpcOpenMemHandle(&pl->ipc_sig[sd], all[q].blk, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {  // no peer mapping on this system: every rank must learn it (second all-gather below)
             cudaGetLastError();
@@ -617,16 +649,19 @@ int32_t bbm_dist_bbb_enable_peer(bbm_dist_bbb_plan_t pl, int32_t elem_size) {
     // nobody may push before every rank has reset its flags and opened its mappings; the same all-gather
     // tells every rank whether all mappings could be opened, so that the ranks switch paths together
     mine.ok = opened ? 1 : 0;
-    BBM_CUDA(h, cudaMemcpy(d_all + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+    if (cudaMemcpy(d_all + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaMemset(d_all + rank, 0, sizeof(Rec)); opened = false; }
     nrc = nccl().AllGather(d_all + rank, d_all, sizeof(Rec), ncclChar, cm->comm, cm->stream);
     cudaStreamSynchronize(cm->stream);
-    if (nrc == ncclSuccess) cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost);
+    if (nrc == ncclSuccess && cudaMemcpy(all.data(), d_all, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); opened = false; }
     cudaFree(d_all);
+    if (old_sig) cudaFree(old_sig);   // every neighbour closed its mapping of it before this second gather
     if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "enable_peer barrier: %s", nccl().GetErrorString(nrc));
     for (int q = 0; q < nranks; ++q) opened = opened && all[q].ok == 1;
     if (!opened) {
         for (int sd = 0; sd < 2; ++sd)
             if (pl->ipc_sig[sd]) { cudaIpcCloseMemHandle(pl->ipc_sig[sd]); pl->ipc_sig[sd] = nullptr; }
+        if (local_fail) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push unavailable (%s failed on this rank); the NCCL exchange stays in use", local_fail);
+        if (!all_ok) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "fused halo push not applicable to this partition; the NCCL exchange stays in use");
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "peer memory mappings are not available on every rank; the NCCL exchange stays in use");
     }
     pl->peer_ok = true;
@@ -644,7 +679,7 @@ int32_t bbm_dist_bbb_peer_status(bbm_dist_bbb_plan_t pl, int32_t* active, int32_
             BBM_CUDA(h, cudaStreamSynchronize(h->stream));
             BbmPeerSig sg;
             BBM_CUDA(h, cudaMemcpy(&sg, pl->sig, sizeof sg, cudaMemcpyDeviceToHost));
-            *timed_out = (int32_t)sg.err;
+            *timed_out = (int32_t)(sg.err != 0 || (pl->err_host && *reinterpret_cast<volatile unsigned*>(pl->err_host) != 0));
         }
     }
     return BBM_OK;

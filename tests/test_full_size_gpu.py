@@ -1,8 +1,9 @@
 """BASELINE.json's configs at (or near) full size on the GPU, and the widened rows at the same scale.
 
-cfg2 / cfg3 are checked against the CPU oracle at FULL size (the oracle needs < 1 s for them);
-cfg4 / cfg5 run at full block size with fewer blocks against the oracle, plus size-independent
-properties (linearity, solve-then-multiply round trip) on the GPU results themselves."""
+Every config is checked against the CPU oracle at FULL size: cfg2 / cfg3 in one oracle call (< 1 s), cfg4
+(2048 blocks of 256, all of C, block-column chunk by chunk) and cfg5 (1024 blocks of 512, all 64 right-hand
+sides) against the oracle bound to threaded OpenBLAS (10-30 s each).  Reduced-size cfg4 / cfg5 cases add the
+size-independent properties (associativity, solve-then-multiply round trip) on the GPU results themselves."""
 import numpy as np
 import pytest
 
@@ -60,6 +61,67 @@ def test_cfg3_full_size_triangular_blocks_vs_oracle(handle, dtype):
     ref = np.zeros(n, dtype=dtype)
     O.bbb_mul(rows, rows, 2, 2, 2, 2, 1.0, data, x, 0.0, ref)
     assert relerr(y, ref) <= tol(dtype, 25)
+
+
+def _torch_handle():
+    import torch
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    return torch, stream, B.Handle(0, stream=stream.cuda_stream)
+
+
+def test_cfg4_full_size_vs_oracle():
+    """cfg4 at FULL size: BlockBandedMatrix fill(256, 2048), (2,2) x (2,2) -> (4,4), Float64, 1.72 TFLOP on the FP64
+    tensor cores; ALL of C (9.65 GB) against the oracle's per-block dgemm loop (test/test_linalg.jl:91-104 at scale)."""
+    from benchmarks.configs import cfg4_oracle_check, wrap
+    torch, stream, h = _torch_handle()
+    rows = [256] * 2048
+    gen = torch.Generator(device="cuda").manual_seed(1004)
+    nA = B.BlockSkylineMatrix.numentries(rows, rows, 2, 2)
+    nC = B.BlockSkylineMatrix.numentries(rows, rows, 4, 4)
+    assert (nA, nC) == (670695424, 1206648832)          # SURVEY.md 8(a2)
+    with torch.cuda.stream(stream):
+        a_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / 16
+        b_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / 16
+        c_t = torch.full((nC,), float("nan"), device="cuda", dtype=torch.float64)     # beta = 0 must never read C
+        A = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, 2, 2)
+        Bm = B.BlockSkylineMatrix(wrap(B, h, b_t), rows, rows, 2, 2)
+        Cm = B.BlockSkylineMatrix(wrap(B, h, c_t), rows, rows, 4, 4)
+        B.mul_(Cm, A, Bm)
+        h.synchronize()
+        assert not bool(torch.isnan(c_t).any().item())
+        err, worst, secs, nchk = cfg4_oracle_check(torch, a_t, b_t, c_t, rows)
+    assert nchk == 8
+    assert err <= tol(np.float64, 1280) and worst <= tol(np.float64, 1280), (err, worst)
+    h.close()
+
+
+def test_cfg5_full_size_vs_oracle():
+    """cfg5 at FULL size: UpperTriangular BlockBandedMatrix fill(512, 1024), (0,3), ldiv! with 64 right-hand sides;
+    every column against the oracle's block back-substitution (test/test_triblockbanded.jl:80-99 at scale)."""
+    from benchmarks.configs import cfg5_oracle_check, wrap
+    torch, stream, h = _torch_handle()
+    bs, nblk, nrhs = 512, 1024, 64
+    rows = [bs] * nblk
+    m = bs * nblk
+    gen = torch.Generator(device="cuda").manual_seed(1005)
+    nA = B.BlockSkylineMatrix.numentries(rows, rows, 0, 3)
+    assert nA * 8 == 8577351680                          # SURVEY.md 8(d)
+    with torch.cuda.stream(stream):
+        a_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float64) / np.sqrt(bs)
+        A = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, 0, 3)
+        idx = torch.arange(bs, device="cuda", dtype=torch.int64)
+        starts = torch.tensor([A.block_start(K, K) for K in range(nblk)], device="cuda", dtype=torch.int64)
+        lds = torch.tensor([int(A.block_strides[K]) for K in range(nblk)], device="cuda", dtype=torch.int64)
+        a_t[(starts[:, None] + idx[None, :] * (lds[:, None] + 1)).reshape(-1)] += 10.0      # +10 on the global diagonal
+        b0 = torch.randn(nrhs, m, generator=gen, device="cuda", dtype=torch.float64)
+        x_t = b0.clone()
+        torch.cuda.synchronize()
+        B.ldiv_(B.UpperTriangular(A), wrap(B, h, x_t))
+        h.synchronize()
+        err, secs = cfg5_oracle_check(torch, a_t, b0, x_t, rows)
+    assert err <= tol(np.float64, 2048), err
+    h.close()
 
 
 def test_cfg4_block_size_256_vs_oracle(handle):
