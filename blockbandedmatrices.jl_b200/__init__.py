@@ -7,6 +7,8 @@ the tests and the benchmark (Julia is not available in the build image; INTEGRAT
 equivalent Julia package extension).
 """
 from ._lib import BandError, BBMError, DimensionMismatch, build_library, LIB_PATH, SIGNATURES  # noqa: F401
+from .broadcast import (Bidiagonal, Diagonal, SymTridiagonal, Tridiagonal, UniformScaling, accommodating_bandwidths, add, add_diags_,  # noqa: F401
+                        axpby_, scaled_add, similar_sum, sub)
 from .device import DeviceArray, Handle, PinnedArray  # noqa: F401
 from .linalg import add_bandwidths, axpy_, ldiv, ldiv_, lmul_, lmul_adj_, mul, ql_, qr_, mul_, muladd_, sparse  # noqa: F401
 from .matrices import (Adjoint, BandedBlockBandedMatrix, BlockBandedMatrix, BlockBandedQL, BlockBandedQR, BlockSkylineMatrix, LowerTriangular,  # noqa: F401

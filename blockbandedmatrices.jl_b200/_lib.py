@@ -52,6 +52,14 @@ SIGNATURES = {
     "bbm_axpy_f32": (i32, [vp, i64, f32, vp, vp]),
     "bbm_scal_f64": (i32, [vp, i64, f64, vp]),
     "bbm_scal_f32": (i32, [vp, i64, f32, vp]),
+    "bbm_bbb_add_f64": (i32, [vp, vp, vp, vp, f64, vp, f64, vp, vp]),
+    "bbm_bbb_add_f32": (i32, [vp, vp, vp, vp, f32, vp, f32, vp, vp]),
+    "bbm_sky_add_f64": (i32, [vp, vp, vp, vp, vp, vp, f64, vp, f64, vp, vp]),
+    "bbm_sky_add_f32": (i32, [vp, vp, vp, vp, vp, vp, f32, vp, f32, vp, vp]),
+    "bbm_bbb_add_diags_f64": (i32, [vp, vp, vp, f64, f64, vp, vp, vp]),
+    "bbm_bbb_add_diags_f32": (i32, [vp, vp, vp, f32, f32, vp, vp, vp]),
+    "bbm_sky_add_diags_f64": (i32, [vp, vp, vp, f64, f64, vp, vp, vp]),
+    "bbm_sky_add_diags_f32": (i32, [vp, vp, vp, f32, f32, vp, vp, vp]),
     "bbm_bbb_desc_create": (i32, [vp, i64, i64, vp, vp, i64, i64, i64, i64, pp]),
     "bbm_bbb_desc_destroy": (i32, [vp]),
     "bbm_bbb_desc_info": (i32, [vp, pi64, pi64, pi64, pi64]),

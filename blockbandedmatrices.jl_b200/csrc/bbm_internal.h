@@ -114,3 +114,12 @@ struct BbbDescView {
     const i64 *dR, *dC;  // device prefix sums (Nr+1, Nc+1)
 };
 bool bbm_bbb_desc_view(bbm_bbb_desc_t d, BbbDescView* out);
+
+// read-only view of a BlockSkylineMatrix descriptor (host tables + device copies) for the other translation units
+struct SkyDescView {
+    bbm_handle_t h;
+    i64 Nr, Nc, m, n, numel;
+    const i64 *r, *c, *R, *C, *klo, *khi, *off, *S;           // host
+    const i64 *d_off, *d_S, *d_klo, *d_khi, *d_R, *d_C;       // device
+};
+bool bbm_sky_desc_view(bbm_sky_desc_t d, SkyDescView* out);

@@ -101,6 +101,9 @@ struct bbm_sky_desc {
         Tri::Batch bW, bC;
         std::vector<int> ptrW, ptrC;
     } qrf;
+    // device copy of the structure tables [off(Nc+1) | S(Nc) | klo(Nc) | khi(Nc) | R(Nr+1) | C(Nc+1)] for the
+    // element-wise kernels of csrc/structadd.cu, uploaded on first use
+    i64* d_struct = nullptr;
     // product plans keyed by the serials of (A, B), owned by the C descriptor
     struct MmPlan;
     std::map<std::pair<uint64_t, uint64_t>, MmPlan*> plans;
@@ -1812,6 +1815,30 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
 
 }  // namespace
 
+bool bbm_sky_desc_view(bbm_sky_desc_t d, SkyDescView* out) {
+    if (!sky_valid(d) || !out) return false;
+    if (!d->d_struct) {
+        std::vector<i64> t;
+        t.insert(t.end(), d->off.begin(), d->off.end());
+        t.insert(t.end(), d->S.begin(), d->S.end());
+        t.insert(t.end(), d->klo.begin(), d->klo.end());
+        t.insert(t.end(), d->khi.begin(), d->khi.end());
+        t.insert(t.end(), d->R.begin(), d->R.end());
+        t.insert(t.end(), d->C.begin(), d->C.end());
+        if (cudaSetDevice(d->h->device) != cudaSuccess) return false;
+        if (upload(d->h, t, &d->d_struct) != BBM_OK) return false;
+    }
+    const i64 Nc = d->Nc, Nr = d->Nr;
+    SkyDescView v{};
+    v.h = d->h; v.Nr = Nr; v.Nc = Nc; v.m = d->m; v.n = d->n; v.numel = d->numel;
+    v.r = d->r.data(); v.c = d->c.data(); v.R = d->R.data(); v.C = d->C.data();
+    v.klo = d->klo.data(); v.khi = d->khi.data(); v.off = d->off.data(); v.S = d->S.data();
+    v.d_off = d->d_struct; v.d_S = v.d_off + (Nc + 1); v.d_klo = v.d_S + Nc; v.d_khi = v.d_klo + Nc;
+    v.d_R = v.d_khi + Nc; v.d_C = v.d_R + (Nr + 1);
+    *out = v;
+    return true;
+}
+
 extern "C" {
 
 int32_t bbm_sky_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* c, const int64_t* lvec,
@@ -1889,6 +1916,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
     }
     if (d->rev) { bbm_sky_desc_destroy(d->rev); d->rev = nullptr; }
     if (d->d_titems) cudaFree(d->d_titems);
+    if (d->d_struct) cudaFree(d->d_struct);
     if (d->qrf.d_steps) cudaFree(d->qrf.d_steps);
     free_batch(d->qrf.bW); free_batch(d->qrf.bC);
     if (d->qr.d_pan) cudaFree(d->qr.d_pan);

@@ -96,6 +96,40 @@ int32_t bbm_axpy_f32(bbm_handle_t h, int64_t n, float alpha, const float* d_x, f
 int32_t bbm_scal_f64(bbm_handle_t h, int64_t n, double alpha, double* d_x);
 int32_t bbm_scal_f32(bbm_handle_t h, int64_t n, float alpha, float* d_x);
 
+/* ---- structured element-wise operations ------------------------------------------------------
+ * C <- alpha*A + beta*B for operands with the SAME block axes but different bandwidths / storage formats: the
+ * block-wise `A + B`, `A - B` (alpha, beta = 1, +-1; src/broadcast.jl:317-372: joint block range op(A,B), ranges only
+ * one operand covers that operand, the rest of C's band zero), `C .= alpha .* A .+ B` (src/broadcast.jl:379-388 on
+ * top of blockbanded_copyto! / blockbanded_axpy!, :307-314) and the copy of a matrix into a wider structure
+ * (B = NULL; `BlockSkylineMatrix{T}(A, sizes)` of copy_accommodating_diagonals, src/BlockSkylineMatrix.jl:530).
+ * The result structure (`similar`: the maximum of the bandwidths, src/broadcast.jl:391-411) stays on the host.
+ * A or B may be absent (NULL descriptor).  BBM_ERR_DIM if block axes differ, BBM_ERR_BAND if an operand's bands do
+ * not fit C.  d_C may alias an operand only if that operand has C's exact structure.  alpha*a and beta*b are rounded
+ * separately and then added -- exactly a+b / a-b for unit coefficients, the un-fused `a .* x .+ y` otherwise.
+ * bbm_bbb_add_*: all three in band storage.  bbm_sky_add_*: C block-skyline, each operand EITHER block-skyline
+ * (X_sky) or banded-block-banded (X_bbb) -- the mixed sums of test/test_broadcasting.jl:205-215.               */
+int32_t bbm_bbb_add_f64(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, double alpha, const double* d_A,
+                        double beta, const double* d_B, double* d_C);
+int32_t bbm_bbb_add_f32(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t C, float alpha, const float* d_A,
+                        float beta, const float* d_B, float* d_C);
+int32_t bbm_sky_add_f64(bbm_handle_t h, bbm_sky_desc_t A_sky, bbm_bbb_desc_t A_bbb, bbm_sky_desc_t B_sky, bbm_bbb_desc_t B_bbb,
+                        bbm_sky_desc_t C, double alpha, const double* d_A, double beta, const double* d_B, double* d_C);
+int32_t bbm_sky_add_f32(bbm_handle_t h, bbm_sky_desc_t A_sky, bbm_bbb_desc_t A_bbb, bbm_sky_desc_t B_sky, bbm_bbb_desc_t B_bbb,
+                        bbm_sky_desc_t C, float alpha, const float* d_A, float beta, const float* d_B, float* d_C);
+/* In place on the storage: A[i,i] += alpha*(lambda + d[i]), A[i,i+1] += alpha*du[i], A[i+1,i] += alpha*dl[i]; d_d, d_du,
+ * d_dl may each be NULL (absent).  The second half of `A +- I`, `A +- Diagonal / Bidiagonal / Tridiagonal /
+ * SymTridiagonal` (src/BlockSkylineMatrix.jl:535-638) and of `I - dt*Delta` for a BandedBlockBandedMatrix
+ * (examples/finitedifference_2d.jl:50-51).  Needs square diagonal blocks (checksquareblocks, BBM_ERR_DIM) and
+ * every touched entry stored (BBM_ERR_BAND otherwise, where the reference's setindex! throws).                */
+int32_t bbm_bbb_add_diags_f64(bbm_handle_t h, bbm_bbb_desc_t d, double* d_data, double alpha, double lambda, const double* d_dl,
+                              const double* d_d, const double* d_du);
+int32_t bbm_bbb_add_diags_f32(bbm_handle_t h, bbm_bbb_desc_t d, float* d_data, float alpha, float lambda, const float* d_dl,
+                              const float* d_d, const float* d_du);
+int32_t bbm_sky_add_diags_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double alpha, double lambda, const double* d_dl,
+                              const double* d_d, const double* d_du);
+int32_t bbm_sky_add_diags_f32(bbm_handle_t h, bbm_sky_desc_t d, float* d_data, float alpha, float lambda, const float* d_dl,
+                              const float* d_d, const float* d_du);
+
 /* ---- BandedBlockBandedMatrix -------------------------------------------------------------
  * Descriptor = the host-side fields of the reference struct (raxis, column axis, l, u, lam, mu;
  * src/BandedBlockBandedMatrix.jl:25-40) plus cached device index tables and the work
