@@ -900,8 +900,6 @@ int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::
     if (!func) return BBM_OK;
 
     int tile = 0, stages = 0, dbytes = 0, xbytes = 0;
-    // measured on B200: 4 stages saturate HBM; 5-6 stages (more smem, same occupancy) are 5% slower on cfg2
-    const int want_stages = (int)std::min<i64>(8, std::max<i64>(2, bbm_opt(h, "bbb.stages", 4)));
     const i64 forced_tile = bbm_opt(h, "bbb.tile", 0);
     if (forced_tile && (forced_tile < 32 || forced_tile > 256 || forced_tile % 32))
         return bbm_fail(h, BBM_ERR_ARG, "bbb.tile must be a multiple of 32 in [32,256]");
@@ -910,19 +908,34 @@ int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::
     const int cands[4] = {forced_tile ? (int)forced_tile : 256, 128, 64, 32};
     const int ncand = forced_tile ? 1 : 4;
     const size_t tabs = walk_tab_bytes(512, (int)NS);
-    // pass 0: >= 3 stages within the two-CTA budget; pass 1: >= 2 stages within the opt-in limit
-    for (int pass = 0; pass < 2 && !tile; ++pass) {
-        const size_t limit = pass == 0 ? soft : budget;
-        const int min_stages = pass == 0 ? 3 : 2;
-        for (int ci = 0; ci < ncand && !tile; ++ci) {
-            const int t = cands[ci];
-            if (!forced_tile && t > 32 && t / 2 >= d->maxr) continue;  // tile twice the largest block: mostly idle
-            walk_stage_bytes<T>(t, w, d->P, &dbytes, &xbytes);
-            const size_t per = (size_t)dbytes + (size_t)nr * xbytes;
-            if (limit <= tabs) continue;
-            const int s = (int)std::min<size_t>(want_stages, (limit - tabs) / per);
-            if (s >= min_stages) { tile = t; stages = s; }
+    auto choose = [&](int want_stages) {
+        tile = 0; stages = 0;
+        // pass 0: >= 3 stages within the two-CTA budget; pass 1: >= 2 stages within the opt-in limit
+        for (int pass = 0; pass < 2 && !tile; ++pass) {
+            const size_t limit = pass == 0 ? soft : budget;
+            const int min_stages = pass == 0 ? 3 : 2;
+            for (int ci = 0; ci < ncand && !tile; ++ci) {
+                const int t = cands[ci];
+                if (!forced_tile && t > 32 && t / 2 >= d->maxr) continue;  // tile twice the largest block: mostly idle
+                walk_stage_bytes<T>(t, w, d->P, &dbytes, &xbytes);
+                const size_t per = (size_t)dbytes + (size_t)nr * xbytes;
+                if (limit <= tabs) continue;
+                const int s = (int)std::min<size_t>(want_stages, (limit - tabs) / per);
+                if (s >= min_stages) { tile = t; stages = s; }
+            }
         }
+    };
+    // Stage count.  Measured on B200 (2-D Laplacian, 4096-row blocks): with long items (221 steps each at 4096 block
+    // rows) 4 stages x 2 CTAs per SM saturate HBM (231 us; 3 stages: 245 us; 5-6 stages 5 % slower); with short items
+    // (28 steps each at 512 block rows, one rank's share of the 8-GPU run) 3 stages let a THIRD CTA fit per SM and the
+    // step drops from 34.4 to 30.8 us (27.2 us with the dependent launch on top): the kernel is then bound by per-CTA
+    // latencies (prologue, barrier, tail), which a third resident CTA hides.  "bbb.stages" overrides.
+    const i64 opt_stages = bbm_opt(h, "bbb.stages", 0);
+    choose((int)std::min<i64>(8, std::max<i64>(2, opt_stages > 0 ? opt_stages : 4)));
+    if (tile && opt_stages <= 0 && stages > 3) {
+        i64 units = 0;
+        for (i64 K = 0; K < d->Nr; ++K) units += (d->r[K] + tile - 1) / tile;
+        if (units < (i64)64 * 2 * h->num_sms) choose(3);
     }
     if (!tile) return BBM_OK;  // P too large for shared memory staging
 
@@ -966,10 +979,12 @@ int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::
     plan->maxseg = part.maxseg; plan->nitems = part.nitems; plan->d_items = part.d_items;
     plan->smem = walk_tab_bytes(part.maxseg, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
     plan->func = func;
-    // "bbb.pdl": 0 plain launch; 1 programmatic dependent launch released at the last step; 2 released at the FIRST
-    // step -- with a CTA slot per SM left free ("bbb.stages" = 3 makes three CTAs fit, the partition fills two) the
-    // successor's CTAs are placed, read their tables and arm their barriers while this kernel still streams
-    plan->pdl = (int)bbm_opt(h, "bbb.pdl", 0);
+    // "bbb.pdl": 0 plain launch; 1 programmatic dependent launch released at the last step; 2 (default) released at
+    // the first step: the successor's CTAs are placed as soon as slots free up, read their tables and arm their
+    // barriers while this kernel still streams, and block in griddepcontrol.wait before touching x, y or data.
+    // Measured (back-to-back products, one event at either end): 34.4 -> 31.2 us at 512 block rows, 27.2 us together
+    // with the third CTA per SM; 231.1 -> 228.2 us at 4096 block rows.
+    plan->pdl = (int)bbm_opt(h, "bbb.pdl", 2);
     cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem);
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "cudaFuncSetAttribute(bbb_walk_kernel): %s", cudaGetErrorString(e));
     plan->walk = true;

@@ -123,3 +123,12 @@ struct SkyDescView {
     const i64 *d_off, *d_S, *d_klo, *d_khi, *d_R, *d_C;       // device
 };
 bool bbm_sky_desc_view(bbm_sky_desc_t d, SkyDescView* out);
+
+// Pieces of the skyline products for the sharded paths (csrc/distsky.cu).  elem = sizeof(T).
+//  bbm_sky_mul_rows:     only block rows [Klo,Khi); phase 0 self-contained, 1 first piece (pre-scales all of y when the
+//                        split kernel is in use), 2 later piece
+//  bbm_sky_matmul_phase: phase 0 whole product, 1 tiles that only multiply B's owned block rows [own_lo,own_hi), 2 the rest
+int32_t bbm_sky_mul_rows(bbm_handle_t h, bbm_sky_desc_t d, int elem, double alpha, const void* data, const void* X, i64 ldx, i64 nrhs, double beta,
+                         void* Y, i64 ldy, i64 Klo, i64 Khi, int phase);
+int32_t bbm_sky_matmul_phase(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, int elem, double alpha, const void* dA,
+                             const void* dB, double beta, void* dC, int phase, i64 own_lo, i64 own_hi);

@@ -20,38 +20,15 @@
 #include <new>
 
 #include "bbm_internal.h"
+#include "dist_internal.h"
 
-namespace {
-
-// ---- NCCL, bound at run time (libnccl.so.2 is only needed once a communicator is created) -------
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-typedef int ncclResult_t;
-enum { ncclSuccess = 0 };
-enum { ncclChar = 0 };
-
-struct Nccl {
-    void* lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    ncclResult_t (*GetVersion)(int*) = nullptr;
-    std::string err;
-};
-
-Nccl& nccl() {
-    static Nccl n;
+BbmNccl& bbm_nccl() {
+    static BbmNccl n;
     return n;
 }
 
-bool nccl_load() {
-    Nccl& n = nccl();
+bool bbm_nccl_load() {
+    BbmNccl& n = bbm_nccl();
     if (n.lib) return true;
     const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
     void* lib = nullptr;
@@ -74,6 +51,12 @@ bool nccl_load() {
     n.lib = lib;
     return true;
 }
+
+namespace {
+
+inline BbmNccl& nccl() { return bbm_nccl(); }
+inline bool nccl_load() { return bbm_nccl_load(); }
+typedef BbmNccl Nccl;
 
 inline i64 clampi(i64 v, i64 lo, i64 hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -100,16 +83,6 @@ RankRanges rank_ranges(i64 Nr, i64 Nc, i64 l, i64 u, int nranks, int p, const i6
 }
 
 }  // namespace
-
-struct bbm_comm {
-    uint32_t magic = 0xC0221234u;
-    bbm_handle_t h = nullptr;
-    int nranks = 1, rank = 0;
-    ncclComm_t comm = nullptr;
-    cudaStream_t stream = nullptr;   // exchange stream
-    cudaEvent_t ev_ready = nullptr;  // x ready on the compute stream
-    cudaEvent_t ev_halo = nullptr;   // halo landed on the exchange stream
-};
 
 struct GraphKey {
     const void* data = nullptr; void* x = nullptr; void* y = nullptr;
@@ -153,7 +126,7 @@ struct bbm_dist_bbb_plan {
 };
 
 namespace {
-inline bool comm_valid(bbm_comm* c) { return c && c->magic == 0xC0221234u && bbm_valid(c->h); }
+inline bool comm_valid(bbm_comm* c) { return bbm_comm_valid(c); }
 inline bool plan_valid(bbm_dist_bbb_plan* p) { return p && p->magic == 0xD157B200u && bbm_valid(p->h); }
 
 int32_t layout_impl(i64 Nr, i64 Nc, const i64* r, const i64* c, i64 l, i64 u, int nranks, int rank, const i64* Kb,
@@ -360,6 +333,11 @@ int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* 
 }
 
 }  // namespace
+
+int32_t bbm_dist_layout_impl(i64 Nr, i64 Nc, const i64* r, const i64* c, i64 l, i64 u, int nranks, int rank, const i64* Kb,
+                             bbm_dist_layout* out, std::vector<i64>* sends, std::vector<i64>* recvs) {
+    return layout_impl(Nr, Nc, r, c, l, u, nranks, rank, Kb, out, sends, recvs);
+}
 
 extern "C" {
 

@@ -50,6 +50,7 @@ struct bbm_sky_desc {
     SkyEnt* d_ents = nullptr;
     SkyItem* d_items = nullptr;
     int nitems = 0;
+    std::vector<int> row_item_ptr;  // Nr+1: the items of block row K are [row_item_ptr[K], row_item_ptr[K+1])
     // triangular-solve tables, built on first use, per uplo (0 lower, 1 upper)
     struct Tri {
         bool built = false;
@@ -245,9 +246,12 @@ __global__ void __launch_bounds__(256) sky_prescale_kernel(T* __restrict__ Y, i6
         }
 }
 
+// Klo/Khi: only the block rows [Klo,Khi) are multiplied (Khi < 0: all).  phase: 0 = one self-contained product;
+// 1 = first part of a product issued in pieces (does the beta pre-scale of ALL rows if the split kernel is used);
+// 2 = a later piece (no pre-scale; split decision taken from the whole matrix so that the pieces agree).
 template <typename T>
 int32_t sky_mul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data, const T* d_X, i64 ldx, i64 nrhs, T beta,
-                     T* d_Y, i64 ldy) {
+                     T* d_Y, i64 ldy, i64 Klo = 0, i64 Khi = -1, int phase = 0) {
     BBM_REQUIRE_HANDLE(h);
     if (!sky_valid(d)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
     if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
@@ -258,7 +262,10 @@ int32_t sky_mul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data,
     if (!d_Y || (d->n > 0 && !d_X) || (d->numel > 0 && !d_data)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
     if (nrhs > 8 * 65535) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "too many right-hand sides");
     BBM_CUDA(h, cudaSetDevice(h->device));
-    GemvParams<T> p{d_data, d_X, d_Y, ldx, ldy, d->d_items, d->d_ents, alpha, beta, (int)nrhs};
+    if (Khi < 0) Khi = d->Nr;
+    if (Klo < 0 || Khi > d->Nr || Klo > Khi) return bbm_fail(h, BBM_ERR_ARG, "bad block-row range");
+    const int it0 = d->row_item_ptr[Klo], it1 = d->row_item_ptr[Khi];
+    GemvParams<T> p{d_data, d_X, d_Y, ldx, ldy, d->d_items + it0, d->d_ents, alpha, beta, (int)nrhs};
     // Few row tiles (a small matrix, or one rank's share of a large one) leave most of an SM's warp slots empty and
     // the stream latency-bound: split every panel's columns over gridDim.z CTAs that accumulate with atomics into a
     // pre-scaled y (the same split the triangular solve's update uses).
@@ -269,13 +276,15 @@ int32_t sky_mul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_data,
     i64 z = bbm_opt(h, "sky.mv_split", 0);
     if (z <= 0) z = (i64)d->nitems * ycols <= 14 * (i64)h->num_sms ? 4 : ((i64)d->nitems * ycols <= 21 * (i64)h->num_sms ? 2 : 1);
     if (z >= 2 && d->nitems > 0) {
-        const unsigned gx = (unsigned)std::min<i64>(65535, (d->m + 255) / 256);
-        sky_prescale_kernel<T><<<dim3(gx, (unsigned)std::min<i64>(nrhs, 65535)), 256, 0, h->stream>>>(d_Y, ldy, d->m, nrhs, beta);
-        h->launches += 1;
+        if (phase != 2) {
+            const unsigned gx = (unsigned)std::min<i64>(65535, (d->m + 255) / 256);
+            sky_prescale_kernel<T><<<dim3(gx, (unsigned)std::min<i64>(nrhs, 65535)), 256, 0, h->stream>>>(d_Y, ldy, d->m, nrhs, beta);
+            h->launches += 1;
+        }
         p.beta = T(1);
-        return launch_gemv<T>(h, p, d->nitems, (int)nrhs, (int)z);
+        return launch_gemv<T>(h, p, it1 - it0, (int)nrhs, (int)z);
     }
-    return launch_gemv<T>(h, p, d->nitems, (int)nrhs);
+    return launch_gemv<T>(h, p, it1 - it0, (int)nrhs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -532,6 +541,7 @@ struct bbm_sky_desc::MmPlan {
     MmSeg* d_segs = nullptr;
     MmTile* d_tiles[2] = {nullptr, nullptr};  // [0] 128x128 DMMA tiles, [1] 64x64 tiles
     int ntiles[2] = {0, 0};
+    int ninterior[2] = {0, 0};                // leading tiles whose product segments only use owned block rows of B
     bool aligned = false;
     double flops = 0;
 };
@@ -548,7 +558,11 @@ void free_plan(bbm_sky_desc::MmPlan* pl) {
 }
 
 // structure checks + plan construction for C <- A*B
-int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t Cd, bbm_sky_desc::MmPlan** out) {
+// own_lo/own_hi: the block rows [own_lo, own_hi) of B this rank owns (sharded product: the others are halo rows that
+// arrive over NVLink); tiles that only multiply owned rows are ordered first so that they can run while the halo is
+// still in flight.  Default: everything is owned.
+int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t Cd, bbm_sky_desc::MmPlan** out,
+                      i64 own_lo = 0, i64 own_hi = INT64_MAX) {
     // block axes must be compatible ([upstream] DimensionMismatch)
     if (A->Nc != B->Nr || Cd->Nr != A->Nr || Cd->Nc != B->Nc || A->c != B->r || A->r != Cd->r || B->c != Cd->c)
         return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: block axes of A (%lldx%lld blocks), B (%lldx%lld) and C (%lldx%lld) are incompatible",
@@ -561,7 +575,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
                     return bbm_fail(h, BBM_ERR_BAND, "BandError: product block (%lld,%lld) lies outside the block band of C", (long long)K, (long long)J);
     std::vector<MmCBlk> cblks;
     std::vector<MmSeg> segs;
-    std::vector<MmTile> tiles[2];
+    std::vector<MmTile> tiles[2], btiles[2];
     const int tsz[2] = {128, 64};
     bool aligned = true;
     double flops = 0;
@@ -573,8 +587,10 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
             cb.cstart = sky_start(Cd, K, J); cb.ldc = Cd->S[J];
             cb.rK = (int32_t)Cd->r[K]; cb.cJ = (int32_t)Cd->c[J];
             cb.seg_begin = (int32_t)segs.size();
+            bool interior = true;
             for (i64 N = B->klo[J]; N <= B->khi[J]; ++N) {
                 if (A->c[N] == 0 || !sky_has(A, K, N)) continue;
+                interior = interior && N >= own_lo && N < own_hi;
                 MmSeg sg{sky_start(A, K, N), A->S[N], sky_start(B, N, J), B->S[J], A->c[N]};
                 aligned = aligned && !(sg.astart & 1) && !(sg.lda & 1) && !(sg.bstart & 1) && !(sg.ldb & 1);
                 flops += 2.0 * (double)cb.rK * (double)cb.cJ * (double)sg.kc;
@@ -585,14 +601,20 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
             cblks.push_back(cb);
             for (int t = 0; t < 2; ++t)
                 for (int tj = 0; tj * tsz[t] < cb.cJ; ++tj)
-                    for (int ti = 0; ti * tsz[t] < cb.rK; ++ti) tiles[t].push_back(MmTile{ci, ti, tj, 0});
+                    for (int ti = 0; ti * tsz[t] < cb.rK; ++ti) (interior ? tiles[t] : btiles[t]).push_back(MmTile{ci, ti, tj, 0});
         }
+    }
+    int ninterior[2];
+    for (int t = 0; t < 2; ++t) {
+        ninterior[t] = (int)tiles[t].size();
+        tiles[t].insert(tiles[t].end(), btiles[t].begin(), btiles[t].end());
     }
     if (segs.size() > (size_t)INT32_MAX / 2 || tiles[1].size() > (size_t)INT32_MAX / 2)
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "product plan too large");
     auto* pl = new (std::nothrow) bbm_sky_desc::MmPlan();
     if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
     pl->aligned = aligned; pl->flops = flops;
+    pl->ninterior[0] = ninterior[0]; pl->ninterior[1] = ninterior[1];
     int32_t rc = upload(h, cblks, &pl->d_cblks);
     if (rc == BBM_OK) rc = upload(h, segs, &pl->d_segs);
     for (int t = 0; t < 2 && rc == BBM_OK; ++t) { rc = upload(h, tiles[t], &pl->d_tiles[t]); pl->ntiles[t] = (int)tiles[t].size(); }
@@ -601,9 +623,11 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
     return BBM_OK;
 }
 
+// phase 0: the whole product; 1: only the tiles that multiply owned block rows [own_lo,own_hi) of B; 2: the others
+// (sharded product: phase 1 runs while the halo rows of B are in flight, phase 2 behind their arrival)
 template <typename T>
 int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t Cd, T alpha, const T* dA,
-                        const T* dB, T beta, T* dC) {
+                        const T* dB, T beta, T* dC, int phase = 0, i64 own_lo = 0, i64 own_hi = INT64_MAX) {
     BBM_REQUIRE_HANDLE(h);
     if (!sky_valid(A) || !sky_valid(B) || !sky_valid(Cd)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
     BBM_CUDA(h, cudaSetDevice(h->device));
@@ -611,12 +635,18 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
     auto it = Cd->plans.find(key);
     if (it == Cd->plans.end()) {
         bbm_sky_desc::MmPlan* pl = nullptr;
-        int32_t rc = build_mm_plan(h, A, B, Cd, &pl);
+        int32_t rc = build_mm_plan(h, A, B, Cd, &pl, own_lo, own_hi);
         if (rc != BBM_OK) return rc;
         it = Cd->plans.emplace(key, pl).first;
     }
     const bbm_sky_desc::MmPlan* pl = it->second;
     if (pl->ntiles[1] == 0) return BBM_OK;
+    int t0[2], nt[2];
+    for (int t = 0; t < 2; ++t) {
+        t0[t] = phase == 2 ? pl->ninterior[t] : 0;
+        nt[t] = phase == 0 ? pl->ntiles[t] : (phase == 1 ? pl->ninterior[t] : pl->ntiles[t] - pl->ninterior[t]);
+    }
+    if (nt[1] == 0) return BBM_OK;
     if (!dC || (A->numel > 0 && !dA) || (B->numel > 0 && !dB)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
     if (dC == dA || dC == dB) return bbm_fail(h, BBM_ERR_ARG, "mul!: destination must not alias an operand");
     MmParams<T> p{dA, dB, dC, pl->d_cblks, pl->d_segs, nullptr, alpha, beta};
@@ -624,10 +654,10 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
     cudaError_t e = cudaSuccess;
     if (sizeof(T) == 8 && force != 2) {
         const bool al = pl->aligned && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % 16 == 0);
-        MmParams<double> pd{(const double*)dA, (const double*)dB, (double*)dC, pl->d_cblks, pl->d_segs, pl->d_tiles[0], (double)alpha, (double)beta};
+        MmParams<double> pd{(const double*)dA, (const double*)dB, (double*)dC, pl->d_cblks, pl->d_segs, pl->d_tiles[0] + t0[0], (double)alpha, (double)beta};
         auto go = [&](auto kern, size_t smem) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) { kern<<<pl->ntiles[0], 256, smem, h->stream>>>(pd); e = cudaGetLastError(); }
+            if (e == cudaSuccess) { kern<<<nt[0], 256, smem, h->stream>>>(pd); e = cudaGetLastError(); }
         };
         // k-chunk depth 32 halves the per-chunk barrier/issue bubble of the DMMA pipe (207 KB of smem)
         const bool bk32 = bbm_opt(h, "sky.mm_bk", 32) >= 32 && h->smem_optin >= mm_smem_bytes<128, 128, 32>();
@@ -635,8 +665,8 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
         else if (al) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, true>, mm_smem_bytes<128, 128, 16>());
         else go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, false>, mm_smem_bytes<128, 128, 16>());
     } else {
-        p.tiles = pl->d_tiles[1];
-        sky_gemm_simt_kernel<T><<<pl->ntiles[1], 256, 0, h->stream>>>(p);
+        p.tiles = pl->d_tiles[1] + t0[1];
+        sky_gemm_simt_kernel<T><<<nt[1], 256, 0, h->stream>>>(p);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "block-banded product launch: %s", cudaGetErrorString(e));
@@ -1815,6 +1845,18 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
 
 }  // namespace
 
+int32_t bbm_sky_mul_rows(bbm_handle_t h, bbm_sky_desc_t d, int elem, double alpha, const void* data, const void* X, i64 ldx, i64 nrhs, double beta,
+                         void* Y, i64 ldy, i64 Klo, i64 Khi, int phase) {
+    if (elem == 8) return sky_mul_impl<double>(h, d, alpha, (const double*)data, (const double*)X, ldx, nrhs, beta, (double*)Y, ldy, Klo, Khi, phase);
+    return sky_mul_impl<float>(h, d, (float)alpha, (const float*)data, (const float*)X, ldx, nrhs, (float)beta, (float*)Y, ldy, Klo, Khi, phase);
+}
+
+int32_t bbm_sky_matmul_phase(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sky_desc_t C, int elem, double alpha, const void* dA,
+                             const void* dB, double beta, void* dC, int phase, i64 own_lo, i64 own_hi) {
+    if (elem == 8) return sky_matmul_impl<double>(h, A, B, C, alpha, (const double*)dA, (const double*)dB, beta, (double*)dC, phase, own_lo, own_hi);
+    return sky_matmul_impl<float>(h, A, B, C, (float)alpha, (const float*)dA, (const float*)dB, (float)beta, (float*)dC, phase, own_lo, own_hi);
+}
+
 bool bbm_sky_desc_view(bbm_sky_desc_t d, SkyDescView* out) {
     if (!sky_valid(d) || !out) return false;
     if (!d->d_struct) {
@@ -1882,7 +1924,9 @@ int32_t bbm_sky_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_
             if (c[J] > 0) rowJ[K].push_back(J);
     std::vector<SkyEnt> ents;
     std::vector<SkyItem> items;
+    d->row_item_ptr.assign(Nr + 1, 0);
     for (i64 K = 0; K < Nr; ++K) {
+        d->row_item_ptr[K] = (int)items.size();
         if (r[K] == 0) continue;
         const int32_t e0 = (int32_t)ents.size();
         for (i64 J : rowJ[K]) ents.push_back(SkyEnt{sky_start(d, K, J), d->S[J], d->C[J], c[J]});
@@ -1891,6 +1935,7 @@ int32_t bbm_sky_desc_create(bbm_handle_t h, int64_t Nr, int64_t Nc, const int64_
             items.push_back(SkyItem{d->R[K] + k0, k0, (int32_t)std::min<i64>(kGemvRows, r[K] - k0), e0, e1, 0});
     }
     d->nitems = (int)items.size();
+    d->row_item_ptr[Nr] = d->nitems;
     cudaError_t e = cudaSetDevice(h->device);
     int32_t rc = e == cudaSuccess ? BBM_OK : bbm_fail(h, BBM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     if (rc == BBM_OK) rc = upload(h, ents, &d->d_ents);

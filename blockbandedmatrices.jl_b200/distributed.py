@@ -397,3 +397,145 @@ class DistBlockBandedMatvec:
         fn, ct, a = self._call
         L.check(fn(a[0], a[1], ct(alpha), a[2], a[3], a[4], a[5], ct(beta), a[6], a[7]), self.h.h, "mul!")
         return self.y_own
+
+
+# ==================================================================================================
+# The same two sharded BlockBandedMatrix operations through the C ABI (bbm_dist_sky_*): planning, halo
+# pack / exchange (ncclSend/ncclRecv inside the library) and the overlapped local kernels all live in
+# csrc/distsky.cu.  The classes above stay as the torch/gloo mirror the CPU tests drive.
+# ==================================================================================================
+def rowrange_structure_c(Nr, Nc, l, u, S0, S1):
+    """``bbm_sky_rowrange_structure``: (Jlo, Jhi, lvec, uvec) of block rows [S0,S1) -- host-only, no GPU."""
+    lib = L.load()
+    jlo, jhi = C.c_int64(), C.c_int64()
+    L.check(lib.bbm_sky_rowrange_structure(Nr, Nc, l, u, S0, S1, C.byref(jlo), C.byref(jhi), None, None), None, "bbm_sky_rowrange_structure")
+    n = jhi.value - jlo.value
+    lv, uv = np.zeros(max(n, 1), dtype=np.int64), np.zeros(max(n, 1), dtype=np.int64)
+    L.check(lib.bbm_sky_rowrange_structure(Nr, Nc, l, u, S0, S1, C.byref(jlo), C.byref(jhi), lv.ctypes.data_as(C.c_void_p),
+                                           uv.ctypes.data_as(C.c_void_p)), None, "bbm_sky_rowrange_structure")
+    return jlo.value, jhi.value, lv[:n], uv[:n]
+
+
+def mm_layout_c(colsA, colsB, NrA, lA, uA, lB, uB, Kbounds, rank):
+    """``bbm_dist_sky_mm_layout``: ({K0,K1,S0,S1,O0,O1}, blocks sent to each rank, blocks received from each rank)."""
+    cA, cB = _sizes(colsA), _sizes(colsB)
+    kb = np.ascontiguousarray(Kbounds, dtype=np.int64)
+    nranks = len(kb) - 1
+    rng6 = np.zeros(6, dtype=np.int64)
+    sb, rb = np.zeros(nranks, dtype=np.int64), np.zeros(nranks, dtype=np.int64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.check(L.load().bbm_dist_sky_mm_layout(NrA, len(cA), len(cB), p(cA), p(cB), lA, uA, lB, uB, nranks, rank, p(kb), p(rng6), p(sb), p(rb)),
+            None, "bbm_dist_sky_mm_layout")
+    return dict(zip(("K0", "K1", "S0", "S1", "O0", "O1"), (int(v) for v in rng6))), sb, rb
+
+
+class DistBlockBandedMatrix:
+    """Rank-local part of a row-block-partitioned BlockBandedMatrix(rows, cols, (l,u)) for ``mul!`` (``bbm_dist_sky_plan_*``).
+
+    ``local`` is the BlockSkylineMatrix structure of the rank's block rows (its ``data`` a device vector of
+    ``numentries`` entries, filled with ``set_local_data``); ``x_local`` / ``y_own`` are device buffers of the layout's
+    sizes like in the banded-block-banded case."""
+
+    def __init__(self, comm: Communicator, rows, cols, l, u, dtype=np.float64, Kbounds=None):
+        from .matrices import BlockSkylineMatrix
+        self.comm = comm
+        self.rows, self.cols = _sizes(rows), _sizes(cols)
+        self.dtype = np.dtype(dtype)
+        h = comm.handle
+        kb = None if Kbounds is None else np.ascontiguousarray(Kbounds, dtype=np.int64)
+        p = C.c_void_p()
+        L.check(h._lib.bbm_dist_sky_plan_create(comm.c, len(self.rows), len(self.cols), self.rows.ctypes.data_as(C.c_void_p),
+                                                self.cols.ctypes.data_as(C.c_void_p), int(l), int(u),
+                                                None if kb is None else kb.ctypes.data_as(C.c_void_p), C.byref(p)), h.h, "bbm_dist_sky_plan_create")
+        self.plan = p
+        lay = L.DistLayout()
+        jlo, jhi, ne, xo = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        L.check(h._lib.bbm_dist_sky_plan_layout(p, C.byref(lay), C.byref(jlo), C.byref(jhi), C.byref(ne), C.byref(xo)), h.h)
+        self.layout = lay.asdict()
+        self.Jlo, self.Jhi, self.numentries, self.x_off = jlo.value, jhi.value, ne.value, xo.value
+        n = self.Jhi - self.Jlo
+        lv, uv = np.zeros(max(n, 1), dtype=np.int64), np.zeros(max(n, 1), dtype=np.int64)
+        L.check(h._lib.bbm_dist_sky_plan_bandwidths(p, lv.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p)), h.h)
+        K0, K1 = self.layout["K0"], self.layout["K1"]
+        self.local = BlockSkylineMatrix(h.empty(self.numentries, self.dtype), self.rows[K0:K1], self.cols[self.Jlo:self.Jhi], lv[:n], uv[:n])
+
+    def set_local_data(self, vec: np.ndarray):
+        if vec.shape != (self.numentries,):
+            raise L.DimensionMismatch(f"local panels hold {self.numentries} entries, got {vec.shape}")
+        if vec.size:
+            self.local.data.copy_from_host(np.ascontiguousarray(vec, dtype=self.dtype))
+        return self
+
+    def mul_(self, y_own, x_local, alpha=1.0, beta=0.0, nrhs=1):
+        """y_own <- alpha*A[K0:K1,:]*x + beta*y_own (collective; asynchronous on the handle's stream)."""
+        h = self.comm.handle
+        suf, ct = ("f64", C.c_double) if self.dtype == np.float64 else ("f32", C.c_float)
+        fn = getattr(h._lib, f"bbm_dist_sky_mul_{suf}")
+        L.check(fn(self.plan, ct(alpha), C.c_void_p(self.local.data.ptr), C.c_void_p(x_local.ptr), nrhs, ct(beta), C.c_void_p(y_own.ptr)),
+                h.h, "bbm_dist_sky_mul")
+        return y_own
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self.comm.handle._lib.bbm_dist_sky_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DistBlockBandedMatmul:
+    """C[K0:K1,:] <- alpha*A[K0:K1,:]*B + beta*C[K0:K1,:] on one rank of a row-block partition (``bbm_dist_sky_mm_plan_*``).
+
+    ``A``, ``B``, ``C`` are the rank-local BlockSkylineMatrix structures with device storage: the rank's own block rows of
+    A and C, and the block rows ``[S0,S1)`` of B it multiplies with (rows outside ``[O0,O1)`` are halo, refreshed by every
+    ``mul_``)."""
+
+    def __init__(self, comm: Communicator, rowsA, colsA, colsB, luA, luB, dtype=np.float64, Kbounds=None):
+        from .matrices import BlockSkylineMatrix
+        self.comm = comm
+        self.rowsA, self.colsA, self.colsB = _sizes(rowsA), _sizes(colsA), _sizes(colsB)
+        self.dtype = np.dtype(dtype)
+        h = comm.handle
+        kb = None if Kbounds is None else np.ascontiguousarray(Kbounds, dtype=np.int64)
+        p = C.c_void_p()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        L.check(h._lib.bbm_dist_sky_mm_plan_create(comm.c, len(self.rowsA), len(self.colsA), len(self.colsB), ptr(self.rowsA), ptr(self.colsA),
+                                                   ptr(self.colsB), int(luA[0]), int(luA[1]), int(luB[0]), int(luB[1]),
+                                                   None if kb is None else ptr(kb), C.byref(p)), h.h, "bbm_dist_sky_mm_plan_create")
+        self.plan = p
+        rng6, jlo, jhi, ne = (np.zeros(k, dtype=np.int64) for k in (6, 3, 3, 3))
+        L.check(h._lib.bbm_dist_sky_mm_plan_info(p, ptr(rng6), ptr(jlo), ptr(jhi), ptr(ne)), h.h)
+        self.ranges = dict(zip(("K0", "K1", "S0", "S1", "O0", "O1"), (int(v) for v in rng6)))
+        R = self.ranges
+        axes = ((self.rowsA[R["K0"]:R["K1"]], self.colsA), (self.colsA[R["S0"]:R["S1"]], self.colsB), (self.rowsA[R["K0"]:R["K1"]], self.colsB))
+        mats = []
+        for t in range(3):
+            n = int(jhi[t] - jlo[t])
+            lv, uv = np.zeros(max(n, 1), dtype=np.int64), np.zeros(max(n, 1), dtype=np.int64)
+            L.check(h._lib.bbm_dist_sky_mm_plan_bandwidths(p, t, ptr(lv), ptr(uv)), h.h)
+            mats.append(BlockSkylineMatrix(h.empty(int(ne[t]), self.dtype), axes[t][0], axes[t][1][int(jlo[t]):int(jhi[t])], lv[:n], uv[:n]))
+        self.A, self.B, self.C = mats
+        self.Jlo, self.Jhi = [int(v) for v in jlo], [int(v) for v in jhi]
+
+    def mul_(self, alpha=1.0, beta=0.0):
+        h = self.comm.handle
+        suf, ct = ("f64", C.c_double) if self.dtype == np.float64 else ("f32", C.c_float)
+        fn = getattr(h._lib, f"bbm_dist_sky_matmul_{suf}")
+        L.check(fn(self.plan, ct(alpha), C.c_void_p(self.A.data.ptr), C.c_void_p(self.B.data.ptr), ct(beta), C.c_void_p(self.C.data.ptr)),
+                h.h, "bbm_dist_sky_matmul")
+        return self.C
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self.comm.handle._lib.bbm_dist_sky_mm_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -367,6 +367,56 @@ int32_t bbm_dist_bbb_mul_f64(bbm_dist_bbb_plan_t p, double alpha, const double* 
 int32_t bbm_dist_bbb_mul_f32(bbm_dist_bbb_plan_t p, float alpha, const float* d_data_local, float* d_x_local,
                              int64_t nrhs, float beta, float* d_y_own);
 
+/* ---- several GPUs: row-block-partitioned BlockBandedMatrix (matvec and A*B, cfg4) -----------------------------
+ * Block rows are split exactly like the banded-block-banded case (bbm_bbb_partition_rows; x / the block rows of a
+ * right factor B are owned like y).  A block-row range [S0,S1) of a BlockBandedMatrix(rows, cols, (l,u)) is a
+ * BlockSkylineMatrix over the block columns [Jlo,Jhi) it touches, with per-column bandwidths (cf. the sub-view
+ * bandwidths of src/linalg.jl:78-87); its storage is NOT a slice of the parent's, so each rank holds its own panels
+ * in exactly the layout bbm_sky_desc_create gives for (rows[S0:S1], cols[Jlo:Jhi], lvec, uvec).                      */
+typedef struct bbm_dist_sky_plan* bbm_dist_sky_plan_t;
+typedef struct bbm_dist_sky_mm_plan* bbm_dist_sky_mm_plan_t;
+
+/* Host-only planning (no GPU, no handle).  lvec / uvec receive Jhi-Jlo entries (NULL to query the range only).      */
+int32_t bbm_sky_rowrange_structure(int64_t Nr, int64_t Nc, int64_t l, int64_t u, int64_t S0, int64_t S1, int64_t* Jlo, int64_t* Jhi,
+                                   int64_t* lvec, int64_t* uvec);
+/* Host-only: ranges6 = {K0,K1 (owned block rows of A and C), S0,S1 (block rows of B stored locally), O0,O1 (block rows
+ * of B owned)}; send_blocks[q] / recv_blocks[q] = number of halo blocks of B exchanged with rank q (length nranks).  */
+int32_t bbm_dist_sky_mm_layout(int64_t NrA, int64_t NcA, int64_t NcB, const int64_t* cA, const int64_t* cB, int64_t lA, int64_t uA,
+                               int64_t lB, int64_t uB, int32_t nranks, int32_t rank, const int64_t* Kbounds, int64_t* ranges6,
+                               int64_t* send_blocks, int64_t* recv_blocks);
+
+/* y_own <- alpha * A[K0:K1,:] * x + beta * y_own.  d_data_local: the rank's panels (numentries_local entries);
+ * d_x_local: n_local x nrhs like bbm_dist_bbb_mul_* (owned part at own_offset, halo parts overwritten by the NCCL
+ * exchange, which overlaps the product of the interior block rows); the local structure's columns start at x_offset
+ * inside x_local.  Collective over the ranks.                                                                    */
+int32_t bbm_dist_sky_plan_create(bbm_comm_t c, int64_t Nr, int64_t Nc, const int64_t* r, const int64_t* cols, int64_t l, int64_t u,
+                                 const int64_t* Kbounds, bbm_dist_sky_plan_t* out);
+int32_t bbm_dist_sky_plan_destroy(bbm_dist_sky_plan_t p);
+int32_t bbm_dist_sky_plan_layout(bbm_dist_sky_plan_t p, bbm_dist_layout* out, int64_t* Jlo, int64_t* Jhi, int64_t* numentries_local,
+                                 int64_t* x_offset);
+int32_t bbm_dist_sky_plan_bandwidths(bbm_dist_sky_plan_t p, int64_t* lvec, int64_t* uvec);
+int32_t bbm_dist_sky_mul_f64(bbm_dist_sky_plan_t p, double alpha, const double* d_data_local, double* d_x_local, int64_t nrhs, double beta,
+                             double* d_y_own);
+int32_t bbm_dist_sky_mul_f32(bbm_dist_sky_plan_t p, float alpha, const float* d_data_local, float* d_x_local, int64_t nrhs, float beta,
+                             float* d_y_own);
+
+/* C[K0:K1,:] <- alpha * A[K0:K1,:] * B + beta * C[K0:K1,:]  (cfg4: "row blocks sharded over 8 GPUs").  A_loc / C_loc hold the
+ * rank's own block rows of A and of C (block bandwidths (lA+lB, uA+uB), `similar(::MulAdd)` of src/linalg.jl:27-48), B_loc
+ * the block rows [S0,S1) of B the rank multiplies with; rows of B_loc outside the owned range [O0,O1) are halo: every call
+ * packs the blocks the neighbours need (gather kernel), exchanges them with ncclSend/ncclRecv on the communicator's stream
+ * and scatters them into d_B_local, while the tiles of C that only multiply owned rows already run on the FP64 tensor
+ * cores; the remaining tiles follow the arrival.  which = 0 / 1 / 2 selects A_loc / B_loc / C_loc in the queries.   */
+int32_t bbm_dist_sky_mm_plan_create(bbm_comm_t c, int64_t NrA, int64_t NcA, int64_t NcB, const int64_t* rA, const int64_t* cA,
+                                    const int64_t* cB, int64_t lA, int64_t uA, int64_t lB, int64_t uB, const int64_t* Kbounds,
+                                    bbm_dist_sky_mm_plan_t* out);
+int32_t bbm_dist_sky_mm_plan_destroy(bbm_dist_sky_mm_plan_t p);
+int32_t bbm_dist_sky_mm_plan_info(bbm_dist_sky_mm_plan_t p, int64_t* ranges6, int64_t* Jlo3, int64_t* Jhi3, int64_t* numentries3);
+int32_t bbm_dist_sky_mm_plan_bandwidths(bbm_dist_sky_mm_plan_t p, int32_t which, int64_t* lvec, int64_t* uvec);
+int32_t bbm_dist_sky_matmul_f64(bbm_dist_sky_mm_plan_t p, double alpha, const double* d_A_local, double* d_B_local, double beta,
+                                double* d_C_local);
+int32_t bbm_dist_sky_matmul_f32(bbm_dist_sky_mm_plan_t p, float alpha, const float* d_A_local, float* d_B_local, float beta,
+                                float* d_C_local);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,51 +72,125 @@ def main():
             if fused != active:
                 failures.append((ci, use_peer, "fused flag inconsistent"))
             A.close()
-    # ---- row-block-partitioned BlockBandedMatrix: matvec and A*B (halo rows over NCCL point-to-point) ----
+    # ---- row-block-partitioned BlockBandedMatrix through the C ABI: matvec (bbm_dist_sky_mul_*) and A*B
+    # (bbm_dist_sky_matmul_*: halo rows of B packed, exchanged with ncclSend/Recv and scattered inside the library) ----
     from tests.helpers import random_sky
-    for ci, (rows, l, u) in enumerate([([16] * 12, 2, 2), ([5, 9, 4, 12, 7, 3, 8, 6], 1, 2), ([64] * 9, 0, 3)]):
+    for ci, (rows, l, u) in enumerate([([16] * 12, 2, 2), ([5, 9, 4, 12, 7, 3, 8, 6], 1, 2), ([64] * 9, 0, 3), ([130] * 11, 2, 1)]):
         rng = np.random.default_rng(900 + ci)
         adata = random_sky(rng, rows, rows, l, u)
         bdata = random_sky(rng, rows, rows, u, l)
         Ah = B.BlockSkylineMatrix(adata, rows, rows, l, u)
         Bh = B.BlockSkylineMatrix(bdata, rows, rows, u, l)
         kb = D.partition_rows(rows, world)
-        x = rng.standard_normal(sum(rows))
-        mv = D.DistBlockBandedMatvec(h, dist, torch, rows, rows, l, u, kb, rank)
-        lay = mv.layout
-        loc, _, _ = D.sky_cut_rows(Ah, lay["K0"], lay["K1"])
-        mv.tA[:loc.data.size] = torch.from_numpy(loc.data).to(mv.dev)
-        xl = np.full(max(1, lay["n_local"]), np.nan)
-        o, c0 = lay["own_offset"], lay["col_offset"]
-        xl[o:o + lay["n_own"]] = x[c0 + o:c0 + o + lay["n_own"]]
-        mv.x_local[:] = torch.from_numpy(xl).to(mv.dev)
-        mv.exchange()
-        y = mv.mul_().cpu().numpy()[:lay["m_own"]]
-        ref = np.zeros(sum(rows))
-        O.sky_mul(rows, rows, l, u, 1.0, adata, x, 0.0, ref)
-        want = ref[lay["row_offset"]:lay["row_offset"] + lay["m_own"]]
-        if lay["m_own"] and (np.isnan(y).any() or relerr(y, want) > tol(np.float64, 64)):
-            failures.append(("sky matvec", ci, relerr(y, want)))
-        prod = D.DistBlockBandedProduct(h, dist, torch, rows, rows, l, u, rows, u, l, kb, rank)
-        P = prod.plan
+        for nrhs in (1, 3):
+            X = rng.standard_normal((sum(rows), nrhs))
+            mv = D.DistBlockBandedMatrix(comm, rows, rows, l, u, Kbounds=kb)
+            lay = mv.layout
+            loc, Jlo, Jhi = D.sky_cut_rows(Ah, lay["K0"], lay["K1"])
+            if (Jlo, Jhi) != (mv.Jlo, mv.Jhi) or loc.data.shape != (mv.numentries,) or list(loc.l) != list(mv.local.l) or list(loc.u) != list(mv.local.u):
+                failures.append(("sky matvec structure", ci))
+                continue
+            mv.set_local_data(loc.data)
+            nl, mo = max(1, lay["n_local"]), max(1, lay["m_own"])
+            xl = np.full((nl, nrhs), np.nan, order="F")
+            o, c0 = lay["own_offset"], lay["col_offset"]
+            xl[o:o + lay["n_own"], :] = X[c0 + o:c0 + o + lay["n_own"], :]
+            dxs = h.to_device(xl)
+            y0 = rng.standard_normal((mo, nrhs))
+            dys = h.to_device(np.asfortranarray(y0))
+            for epoch in range(2):
+                dist.barrier()
+                mv.mul_(dys, dxs, 1.5, 0.5 if epoch == 0 else 0.0, nrhs=nrhs)
+                got = dys.to_host()[:lay["m_own"], :]
+                ref = np.zeros((sum(rows), nrhs), order="F")
+                O.sky_mul(rows, rows, l, u, 1.5, adata, np.asfortranarray(X), 0.0, ref)
+                want = ref[lay["row_offset"]:lay["row_offset"] + lay["m_own"], :] + (0.5 * y0[:lay["m_own"], :] if epoch == 0 else 0.0)
+                if lay["m_own"] and (np.isnan(got).any() or relerr(got, want) > tol(np.float64, 64)):
+                    failures.append(("sky matvec", ci, nrhs, epoch, relerr(got, want)))
+            mv.close()
+        prod = D.DistBlockBandedMatmul(comm, rows, rows, rows, (l, u), (u, l), Kbounds=kb)
+        P = prod.ranges
         locA, _, _ = D.sky_cut_rows(Ah, P["K0"], P["K1"])
-        locB, _, _ = D.sky_cut_rows(Bh, P["S0"], P["S1"])
-        prod.tA[:locA.data.size] = torch.from_numpy(locA.data).to(prod.dev)
-        prod.tB[:locB.data.size] = torch.from_numpy(locB.data).to(prod.dev)
+        locB, JloB, _ = D.sky_cut_rows(Bh, P["S0"], P["S1"])
+        if locA.data.shape != prod.A.data.shape or locB.data.shape != prod.B.data.shape:
+            failures.append(("sky product structure", ci))
+            continue
+        bloc = locB.data.copy()
         for N in range(P["S0"], P["S1"]):          # only the exchange may fill the halo rows of B
             if not (P["O0"] <= N < P["O1"]):
-                for J in range(max(N - u, 0), min(N + l, len(rows) - 1) + 1):
-                    prod._b_block(N, J).fill_(float("nan"))
-        prod.exchange()
-        prod.tC.fill_(float("nan"))
-        prod.mul_(1.0, 0.0)
+                for J in [J for J in range(len(locB.cols)) if locB.has_block(N - P["S0"], J)]:
+                    s, ld = locB.block_start(N - P["S0"], J), int(locB.block_strides[J])
+                    for j in range(int(locB.cols[J])):
+                        bloc[s + j * ld:s + j * ld + int(locB.rows[N - P["S0"]])] = np.nan
+        if locA.data.size:
+            prod.A.data.copy_from_host(locA.data)
+        if bloc.size:
+            prod.B.data.copy_from_host(bloc)
+        prod.C.data.fill_bytes(0xFF)
+        dist.barrier()
+        for rep in range(2):                          # the second product re-sends the same halos
+            prod.mul_(1.0, 0.0)
         h.synchronize()
+        if bloc.size and not np.array_equal(prod.B.data.to_host(), locB.data):
+            failures.append(("sky product halo rows of B", ci))
         cref = np.zeros(B.BlockSkylineMatrix.numentries(rows, rows, l + u, l + u))
         O.sky_matmul((rows, rows, l, u), (rows, rows, u, l), (rows, rows, l + u, l + u), 1.0, adata, bdata, 0.0, cref)
         wantC, _, _ = D.sky_cut_rows(B.BlockSkylineMatrix(cref, rows, rows, l + u, l + u), P["K0"], P["K1"])
-        gotC = prod.tC.cpu().numpy()[:wantC.data.size]
-        if wantC.data.size and (np.isnan(gotC).any() or relerr(gotC, wantC.data) > tol(np.float64, 256)):
+        gotC = prod.C.data.to_host()
+        if gotC.shape != wantC.data.shape:
+            failures.append(("sky product C structure", ci))
+        elif wantC.data.size and (np.isnan(gotC).any() or relerr(gotC, wantC.data) > tol(np.float64, 256)):
             failures.append(("sky product", ci, relerr(gotC, wantC.data)))
+        prod.close()
+
+    # ---- a rank that is late by more than the configured wait: the fused path must not return wrong numbers silently ----
+    rows = [64] * (4 * world)
+    rng = np.random.default_rng(77)
+    data = random_bbb(rng, rows, rows, 1, 1, 1, 1)
+    for timeout_ms, delay_s, expect_ok in ((30000, 1.5, True), (200, 1.0, False)):
+        A = D.DistBandedBlockBandedMatrix(comm, rows, rows, (1, 1), (1, 1))
+        lay = A.layout
+        A.set_local_data(A.local_data(data))
+        h.set_option("dist.peer_timeout_ms", timeout_ms)
+        if not A.enable_peer():
+            A.close()
+            continue
+        x = rng.standard_normal(sum(rows))
+        o, c0 = lay["own_offset"], lay["col_offset"]
+        xl = np.full(lay["n_local"], np.nan)
+        xl[o:o + lay["n_own"]] = x[c0 + o:c0 + o + lay["n_own"]]
+        dx, dy = h.to_device(xl), h.empty(lay["m_own"], np.float64)
+        dist.barrier()
+        if rank == world - 1:
+            import time
+            time.sleep(delay_s)                    # GC pause, I/O, a first-call plan build ...
+        A.mul_(dy, dx)
+        got = dy.to_host()
+        ref = np.zeros(sum(rows))
+        O.bbb_mul(rows, rows, 1, 1, 1, 1, 1.0, data, x, 0.0, ref)
+        want = ref[lay["row_offset"]:lay["row_offset"] + lay["m_own"]]
+        _active, timed_out = A.peer_status()
+        if expect_ok:
+            if timed_out or np.isnan(got).any() or relerr(got, want) > tol(np.float64, 9):
+                failures.append(("late rank within the time-out", timed_out, relerr(got, want)))
+        else:
+            # ranks whose neighbour was late see a time-out: their halo rows are NaN (never stale numbers) and the next
+            # product is refused; everything that is not NaN is still right
+            ok = ~np.isnan(got)
+            if ok.any() and relerr(got[ok], want[ok]) > tol(np.float64, 9):
+                failures.append(("late rank: wrong finite values", relerr(got[ok], want[ok])))
+            if rank == world - 2 and not (timed_out and np.isnan(got).any()):
+                failures.append(("late rank: the waiting neighbour saw no time-out", timed_out, int(np.isnan(got).sum())))
+            if timed_out:
+                try:
+                    A.mul_(dy, dx)
+                    failures.append(("late rank: product after a time-out was not refused",))
+                except B.BBMError:
+                    pass
+        dist.barrier()
+        h.synchronize()
+        A.close()
+    h.set_option("dist.peer_timeout_ms", 30000)
 
     flag = torch.tensor([len(failures)], device=f"cuda:{local_rank}")
     dist.all_reduce(flag)

@@ -308,3 +308,39 @@ def test_partitioned_block_banded_matvec_gloo(world):
         p.join(timeout=60)
     for rank, failures in results:
         assert not failures, f"rank {rank}: {failures}"
+
+
+# --------------------------------------------------------------------------------------------------
+# host-only planning of the C ABI's sharded BlockBandedMatrix paths against the Python planners above
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(10, 10, 2, 2), (8, 8, 1, 2), (9, 9, 0, 3), (5, 6, 1, 2), (7, 5, 3, 0), (6, 6, -1, 2), (4, 4, 5, 5)])
+def test_c_rowrange_structure_matches_python(case):
+    sys.path.insert(0, ROOT)
+    from bbm_b200 import distributed as D
+    Nr, Nc, l, u = case
+    rows, cols = [3] * Nr, [2] * Nc
+    for S0 in range(Nr + 1):
+        for S1 in range(S0, Nr + 1):
+            Jlo, Jhi, ll, uu = D.sky_rowrange_structure(rows, cols, l, u, S0, S1)
+            cJlo, cJhi, cl, cu = D.rowrange_structure_c(Nr, Nc, l, u, S0, S1)
+            assert (Jlo, Jhi) == (cJlo, cJhi)
+            assert list(ll) == list(cl) and list(uu) == list(cu)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_c_mm_layout_matches_python(world):
+    sys.path.insert(0, ROOT)
+    from bbm_b200 import distributed as D
+    for rows, colsB, (lA, uA), (lB, uB) in MM_CASES + [([4, 0, 3, 5, 0, 2, 6, 1], [4, 0, 3, 5, 0, 2, 6, 1], (1, 1), (1, 2))]:
+        kb = D.partition_rows(rows, world)
+        for rank in range(world):
+            P = D.matmul_plan(rows, rows, lA, uA, colsB, lB, uB, kb, rank)
+            rng, sb, rb = D.mm_layout_c(rows, colsB, len(rows), lA, uA, lB, uB, kb, rank)
+            assert rng == {k: P[k] for k in ("K0", "K1", "S0", "S1", "O0", "O1")}
+            for q in range(world):
+                assert sb[q] == len(P["sends"].get(q, [])) and rb[q] == len(P["recvs"].get(q, []))
+        # what p sends to q is what q receives from p
+        lay = [D.mm_layout_c(rows, colsB, len(rows), lA, uA, lB, uB, kb, r) for r in range(world)]
+        for p in range(world):
+            for q in range(world):
+                assert lay[p][1][q] == lay[q][2][p]
