@@ -503,7 +503,7 @@ def bench_distributed(args, torch, dist, B, h, stream, nb, block, rank, world, l
 
     def e2e_step():
         if host_call:
-            A.mul_host_(hy.array, hx.array, dx)
+            A.mul_host_(hy.array, hx.array)
             return
         L.check(lib.bbm_memcpy_h2d(h.h, C_.c_void_p(xown_ptr), C_.c_void_p(hx.ptr), 8 * lay["n_own"]), h.h)
         A.mul_(dy, dx)

@@ -108,6 +108,8 @@ SIGNATURES = {
     "bbm_dist_bbb_peer_status": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "bbm_dist_bbb_mul_f64": (i32, [vp, f64, vp, vp, i64, f64, vp]),
     "bbm_dist_bbb_mul_f32": (i32, [vp, f32, vp, vp, i64, f32, vp]),
+    "bbm_dist_bbb_mul_host_f64": (i32, [vp, f64, vp, vp, f64, vp]),
+    "bbm_dist_bbb_mul_host_f32": (i32, [vp, f32, vp, vp, f32, vp]),
     "bbm_sky_rowrange_structure": (i32, [i64, i64, i64, i64, i64, i64, pi64, pi64, vp, vp]),
     "bbm_dist_sky_mm_layout": (i32, [i64, i64, i64, vp, vp, i64, i64, i64, i64, i32, i32, vp, vp, vp, vp]),
     "bbm_dist_sky_plan_create": (i32, [vp, i64, i64, vp, vp, i64, i64, vp, pp]),

@@ -61,6 +61,7 @@ struct bbm_context {
     std::map<std::string, i64> opts;
     i64 opt_gen = 0;   // bumped by bbm_set_option: cached launch plans are keyed on it
     i64 launches = 0;
+    double last_cond = 0.0;   // largest ||T_KK|| ||inv(T_KK)|| seen by the last block triangular solve's condition guard
     // workspace for the *_host_* calls (device copies of X and Y)
     void* ws_x = nullptr; size_t ws_x_bytes = 0;
     void* ws_y = nullptr; size_t ws_y_bytes = 0;

@@ -123,6 +123,14 @@ struct bbm_dist_bbb_plan {
     // sub-problems: 0 interior, 1 left boundary, 2 right boundary; each (desc, data col offset, y row offset)
     bbm_bbb_desc_t desc[3] = {nullptr, nullptr, nullptr};
     i64 coloff[3] = {0, 0, 0}, rowoff[3] = {0, 0, 0};
+    // pipelined host-vector product (bbm_dist_bbb_mul_host_*): block-row chunks of the owned rows as sub-views of the
+    // local slab, device workspaces for x_local / y_own / the staged send blocks, events
+    struct HostChunk { i64 Ka, Kb, Jl, Jh; bool halo; bbm_bbb_desc_t sub; };
+    std::vector<HostChunk> hchunks;
+    std::vector<cudaEvent_t> hev;
+    std::vector<i64> C_local, R_own;   // prefix sums of the local block columns / owned block rows (elements)
+    void* ws_x = nullptr; void* ws_y = nullptr; void* ws_s = nullptr;
+    int ws_elem = 0;
 };
 
 namespace {
@@ -332,6 +340,142 @@ int32_t dist_mul_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, T* 
     return BBM_OK;
 }
 
+
+// y_own (host) <- alpha * A[K0:K1,:] * x + beta * y_own with the rank's x_own in (pinned) host memory.
+// Everything a rank does for one product is pipelined over block-row chunks on four streams:
+//   copy_in : [blocks the neighbours need -> staging] [x_own chunk 0] [x_own chunk 1] ...
+//   comm    :        NCCL send (staging) / recv (halo parts of x_local)
+//   compute :                         [chunk 0: waits x chunk 0 (+ halo)] [chunk 1] ...   (sub-views of the local slab)
+//   copy_out:                                              [y chunk 0] [y chunk 1] ...
+// so the call costs about max(upload, download) instead of upload + product + download.
+template <typename T>
+int32_t dist_mul_host_impl(bbm_dist_bbb_plan* pl, T alpha, const T* d_data_local, const T* h_x_own, T beta, T* h_y_own) {
+    if (!plan_valid(pl)) return BBM_ERR_HANDLE;
+    bbm_handle_t h = pl->h;
+    bbm_comm* cm = pl->comm;
+    const bbm_dist_layout& L = pl->lay;
+    if ((L.n_own > 0 && !h_x_own) || (L.m_own > 0 && !h_y_own)) return bbm_fail(h, BBM_ERR_ARG, "null host pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const bool exchange = cm && cm->comm && cm->nranks > 1 && (!pl->sends.empty() || !pl->recvs.empty());
+    if (pl->ws_elem != (int)sizeof(T)) {
+        for (void** w : {&pl->ws_x, &pl->ws_y, &pl->ws_s})
+            if (*w) { cudaFree(*w); *w = nullptr; }
+        i64 nsend = 0;
+        for (size_t i = 0; i + 2 < pl->sends.size(); i += 3) nsend += pl->sends[i + 2];
+        cudaError_t e = cudaMalloc(&pl->ws_x, (size_t)std::max<i64>(1, L.n_local) * sizeof(T) + 64);
+        if (e == cudaSuccess) e = cudaMalloc(&pl->ws_y, (size_t)std::max<i64>(1, L.m_own) * sizeof(T) + 64);
+        if (e == cudaSuccess) e = cudaMalloc(&pl->ws_s, (size_t)std::max<i64>(1, nsend) * sizeof(T) + 64);
+        if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "host-vector workspaces: %s", cudaGetErrorString(e)); }
+        pl->ws_elem = (int)sizeof(T);
+    }
+    if (pl->hchunks.empty() && L.K1 > L.K0) {
+        const i64 nown = L.K1 - L.K0;
+        const int nch = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(bbm_opt(h, "bbb.host_chunks", 8), 32), nown));
+        std::vector<i64> kb(nch + 1);
+        if (bbm_bbb_partition_rows(nown, pl->r.data() + L.K0, nch, kb.data()) != BBM_OK) return bbm_fail(h, BBM_ERR_ARG, "bad block sizes");
+        pl->C_local.assign(L.Jhi - L.Jlo + 1, 0);
+        for (i64 J = L.Jlo; J < L.Jhi; ++J) pl->C_local[J - L.Jlo + 1] = pl->C_local[J - L.Jlo] + pl->c[J];
+        pl->R_own.assign(nown + 1, 0);
+        for (i64 K = L.K0; K < L.K1; ++K) pl->R_own[K - L.K0 + 1] = pl->R_own[K - L.K0] + pl->r[K];
+        for (int i = 0; i < nch; ++i) {
+            if (kb[i + 1] <= kb[i]) continue;
+            bbm_dist_bbb_plan::HostChunk ch{L.K0 + kb[i], L.K0 + kb[i + 1], 0, 0, false, nullptr};
+            ch.Jl = clampi(ch.Ka - pl->l, L.Jlo, L.Jhi);
+            ch.Jh = clampi(ch.Kb - 1 + pl->u + 1, ch.Jl, L.Jhi);
+            if (pl->P == 0) ch.Jh = ch.Jl;
+            ch.halo = ch.Jl < L.J0 || ch.Jh > L.J1;
+            const i64 sft = ch.Ka - ch.Jl;
+            int32_t rc = bbm_bbb_desc_create(h, ch.Kb - ch.Ka, ch.Jh - ch.Jl, pl->r.data() + ch.Ka, pl->c.data() + ch.Jl, pl->l - sft, pl->u + sft,
+                                             pl->lam, pl->mu, &ch.sub);
+            if (rc != BBM_OK) return rc;
+            pl->hchunks.push_back(ch);
+        }
+        pl->hev.resize(2 * pl->hchunks.size() + 3, nullptr);
+        for (auto& e : pl->hev) BBM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!h->copy_in) {
+        BBM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+        BBM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    }
+    T* dX = static_cast<T*>(pl->ws_x);
+    T* dY = static_cast<T*>(pl->ws_y);
+    T* dS = static_cast<T*>(pl->ws_s);
+    const size_t nch = pl->hchunks.size();
+    cudaEvent_t ev0 = nch ? pl->hev[2 * nch] : nullptr, ev_stage = nch ? pl->hev[2 * nch + 1] : nullptr, ev_halo = nch ? pl->hev[2 * nch + 2] : nullptr;
+    if (nch) {
+        BBM_CUDA(h, cudaEventRecord(ev0, h->stream));            // earlier work on the handle's stream
+        BBM_CUDA(h, cudaStreamWaitEvent(h->copy_in, ev0, 0));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->copy_out, ev0, 0));
+    }
+    const i64 own0 = L.own_offset;
+    if (exchange) {
+        Nccl& n = nccl();
+        // the blocks the neighbours need go up first, into a staging buffer of their own (the owned part of x_local is
+        // filled chunk by chunk below; the halo parts only by the receives)
+        i64 so = 0;
+        for (size_t i = 0; i + 2 < pl->sends.size(); i += 3) {
+            const i64 off = pl->sends[i + 1], cnt = pl->sends[i + 2];
+            BBM_CUDA(h, cudaMemcpyAsync(dS + so, h_x_own + (off - own0), (size_t)cnt * sizeof(T), cudaMemcpyHostToDevice, h->copy_in ? h->copy_in : h->stream));
+            so += cnt;
+        }
+        cudaStream_t cin = h->copy_in ? h->copy_in : h->stream;
+        cudaEvent_t evs = ev_stage ? ev_stage : cm->ev_ready;
+        BBM_CUDA(h, cudaEventRecord(evs, cin));
+        BBM_CUDA(h, cudaStreamWaitEvent(cm->stream, evs, 0));
+        if (ev0) BBM_CUDA(h, cudaStreamWaitEvent(cm->stream, ev0, 0));
+        ncclResult_t nrc = n.GroupStart();
+        for (size_t i = 0; i + 2 < pl->recvs.size() && nrc == ncclSuccess; i += 3)
+            nrc = n.Recv(dX + pl->recvs[i + 1], (size_t)pl->recvs[i + 2] * sizeof(T), ncclChar, (int)pl->recvs[i], cm->comm, cm->stream);
+        so = 0;
+        for (size_t i = 0; i + 2 < pl->sends.size() && nrc == ncclSuccess; i += 3) {
+            nrc = n.Send(dS + so, (size_t)pl->sends[i + 2] * sizeof(T), ncclChar, (int)pl->sends[i], cm->comm, cm->stream);
+            so += pl->sends[i + 2];
+        }
+        ncclResult_t nrc2 = n.GroupEnd();
+        if (nrc == ncclSuccess) nrc = nrc2;
+        if (nrc != ncclSuccess) return bbm_fail(h, BBM_ERR_NCCL, "halo exchange: %s", n.GetErrorString(nrc));
+        if (ev_halo) BBM_CUDA(h, cudaEventRecord(ev_halo, cm->stream));
+    }
+    const i64 ldx = std::max<i64>(1, L.n_local), ldy = std::max<i64>(1, L.m_own);
+    i64 up = own0;  // x_local[own0, up) is on the device
+    const i64 own1 = own0 + L.n_own;
+    int32_t rc = BBM_OK;
+    for (size_t i = 0; i < nch; ++i) {
+        const auto& ch = pl->hchunks[i];
+        const i64 need = std::min<i64>(own1, std::max<i64>(own0, pl->C_local[ch.Jh - L.Jlo]));
+        if (need > up) {
+            BBM_CUDA(h, cudaMemcpyAsync(dX + up, h_x_own + (up - own0), (size_t)(need - up) * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+            up = need;
+        }
+        const i64 r0 = pl->R_own[ch.Ka - L.K0], nr = pl->R_own[ch.Kb - L.K0] - r0;
+        if (beta != T(0) && nr > 0)
+            BBM_CUDA(h, cudaMemcpyAsync(dY + r0, h_y_own + r0, (size_t)nr * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+        BBM_CUDA(h, cudaEventRecord(pl->hev[2 * i], h->copy_in));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->stream, pl->hev[2 * i], 0));
+        if (ch.halo && exchange) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, ev_halo, 0));
+        const i64 c0 = pl->C_local[ch.Jl - L.Jlo];
+        if (sizeof(T) == 8)
+            rc = bbm_bbb_mul_f64(h, ch.sub, (double)alpha, (const double*)d_data_local + pl->P * c0, (const double*)dX + c0, ldx, 1, (double)beta,
+                                 (double*)dY + r0, ldy);
+        else
+            rc = bbm_bbb_mul_f32(h, ch.sub, (float)alpha, (const float*)d_data_local + pl->P * c0, (const float*)dX + c0, ldx, 1, (float)beta,
+                                 (float*)dY + r0, ldy);
+        if (rc != BBM_OK) return rc;
+        BBM_CUDA(h, cudaEventRecord(pl->hev[2 * i + 1], h->stream));
+        BBM_CUDA(h, cudaStreamWaitEvent(h->copy_out, pl->hev[2 * i + 1], 0));
+        if (nr > 0) BBM_CUDA(h, cudaMemcpyAsync(h_y_own + r0, dY + r0, (size_t)nr * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    if (nch) {
+        if (up < own1)   // owned columns no owned row touches (they still had to reach the neighbours above)
+            up = own1;
+        BBM_CUDA(h, cudaStreamSynchronize(h->copy_out));
+        BBM_CUDA(h, cudaStreamSynchronize(h->copy_in));
+    }
+    if (exchange) BBM_CUDA(h, cudaStreamSynchronize(cm->stream));
+    BBM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BBM_OK;
+}
+
 }  // namespace
 
 int32_t bbm_dist_layout_impl(i64 Nr, i64 Nc, const i64* r, const i64* c, i64 l, i64 u, int nranks, int rank, const i64* Kb,
@@ -476,6 +620,13 @@ int32_t bbm_dist_bbb_plan_destroy(bbm_dist_bbb_plan_t pl) {
         if (pl->ipc_sig[i]) cudaIpcCloseMemHandle(pl->ipc_sig[i]);
     if (pl->sig) cudaFree(pl->sig);
     if (pl->err_host) cudaFreeHost(pl->err_host);
+    for (auto& ch : pl->hchunks)
+        if (ch.sub) bbm_bbb_desc_destroy(ch.sub);
+    for (auto& e : pl->hev)
+        if (e) cudaEventDestroy(e);
+    if (pl->ws_x) cudaFree(pl->ws_x);
+    if (pl->ws_y) cudaFree(pl->ws_y);
+    if (pl->ws_s) cudaFree(pl->ws_s);
     pl->magic = 0;
     delete pl;
     return BBM_OK;
@@ -671,5 +822,9 @@ int32_t bbm_dist_bbb_mul_f32(bbm_dist_bbb_plan_t pl, float alpha, const float* d
                              int64_t nrhs, float beta, float* d_y_own) {
     return dist_mul_impl<float>(pl, alpha, d_data_local, d_x_local, nrhs, beta, d_y_own);
 }
+int32_t bbm_dist_bbb_mul_host_f64(bbm_dist_bbb_plan_t pl, double alpha, const double* d_data_local, const double* h_x_own, double beta,
+                                  double* h_y_own) { return dist_mul_host_impl<double>(pl, alpha, d_data_local, h_x_own, beta, h_y_own); }
+int32_t bbm_dist_bbb_mul_host_f32(bbm_dist_bbb_plan_t pl, float alpha, const float* d_data_local, const float* h_x_own, float beta,
+                                  float* h_y_own) { return dist_mul_host_impl<float>(pl, alpha, d_data_local, h_x_own, beta, h_y_own); }
 
 }  // extern "C"

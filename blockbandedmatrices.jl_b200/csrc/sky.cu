@@ -70,6 +70,13 @@ struct bbm_sky_desc {
         i64 step_ldb = -1, step_nrhs = -1, step_ldx = -1;
         Batch stepA, stepB;            // all block steps; tiles of step K are [ptr[K], ptr[K+1])
         std::vector<int> ptrA, ptrB;
+        // data-flow solve: ONE persistent kernel walks all block steps; tiles in dependency order with counters
+        void* flow_tiles = nullptr;    // FlowTile[flow_ntiles]
+        i64 flow_ntiles = 0;
+        int* flow_ctr = nullptr;       // 2*Nr completion counters (+ 1 error word), zeroed per call
+        i64 flow_ldb = -1, flow_nrhs = -1, flow_ldx = -1;
+        bool flow_ok = false;
+        double* d_cond = nullptr;      // per diagonal block: ||T||_inf, ||inv(T)||_inf (condition guard)
     } tri[2];
     // QR-solve plan (Float64): compact-WY form of every panel's reflectors, built on first use
     struct Qr {
@@ -1047,7 +1054,13 @@ int32_t build_tri_step_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
     return BBM_OK;
 }
 
-int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, const double* d_data, double* d_B, i64 ldb, i64 nrhs) {
+int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb, i64 ldx, i64 nrhs);
+int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const double* d_data, const double* W, double* d_B, double* X);
+int32_t tri_condition(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, const double* d_data, const double* W, double* cond_max);
+
+// returns BBM_OK and *fallback = true (nothing written to B) when the condition guard rejects the inverse-based paths
+int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, const double* d_data, double* d_B, i64 ldb, i64 nrhs, bool* fallback) {
+    *fallback = false;
     bbm_sky_desc::Tri& t = d->tri[upper];
     int32_t rc = build_tri_inverse_plan(h, d, upper);
     if (rc != BBM_OK) return rc;
@@ -1078,6 +1091,39 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
         if (rc == BBM_OK) rc = launch_mm64(h, t.inv_levels[lv + 1], 0, t.inv_levels[lv + 1].ntiles, W, Tw, W, -1.0, 0.0, false);
         if (rc != BBM_OK) return rc;
     }
+    // Condition guard.  X_K = inv(T_KK) B_K is not backward stable: its error grows like cond(T_KK) eps, where the
+    // reference's substitution (trsv) stays at the n eps level.  ||T_KK||_inf ||inv(T_KK)||_inf of every diagonal block is
+    // read back (one synchronisation per solve); beyond "trsm.cond_max" (default 8 x the longest row of T: the inverse path
+    // then still meets 64 eps nnz) the call falls back to the substitution kernels.  "trsm.cond_check" = 0 skips it.
+    if (bbm_opt(h, "trsm.cond_check", 1) != 0) {
+        double cmax = 0.0;
+        rc = tri_condition(h, d, upper, unit, d_data, W, &cmax);
+        if (rc != BBM_OK) return rc;
+        i64 longest = 1;
+        for (i64 K = 0; K < d->Nr; ++K) {
+            i64 len = 0;   // entries of block row K of T (diagonal block + off-diagonal blocks on the triangle's side)
+            for (i64 J = 0; J < d->Nc; ++J) if (sky_has(d, K, J) && (upper ? J >= K : J <= K)) len += d->c[J];
+            longest = std::max(longest, len);
+            if (d->Nr > 4096) break;   // (constant-bandwidth structures: the first rows are representative enough)
+        }
+        const double limit = (double)bbm_opt(h, "trsm.cond_max", 8 * longest);
+        h->last_cond = cmax;
+        h->opts["trsm.last_cond_x1000"] = cmax < 9.0e15 ? (i64)(cmax * 1000.0) : INT64_MAX;   // diagnostics (bbm_get_option)
+        if (!(cmax <= limit)) { *fallback = true; h->opts["trsm.last_path"] = 3; return BBM_OK; }
+    }
+    // the data-flow kernel: the whole chain in one persistent launch ("trsm.kernel" = 3 keeps the launch chain below)
+    if (bbm_opt(h, "trsm.kernel", 0) != 3) {
+        rc = build_tri_flow_plan(h, d, upper, ldb, ldx, nrhs);
+        if (rc != BBM_OK) return rc;
+        if (t.flow_ok && (reinterpret_cast<uintptr_t>(d_data) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_B) % 16 == 0)) {
+            rc = launch_trsm_flow(h, d, upper, d_data, W, d_B, X);
+            if (rc != BBM_OK) return rc;
+            h->opts["trsm.last_path"] = 1;
+            BBM_CUDA(h, cudaMemcpy2DAsync(d_B, (size_t)ldb * sizeof(double), X, (size_t)ldx * sizeof(double), (size_t)d->m * sizeof(double),
+                                          (size_t)nrhs, cudaMemcpyDeviceToDevice, h->stream));
+            return BBM_OK;
+        }
+    }
     // the sequential chain: two split-k tensor-core products per block; the next block column's panel and
     // inverse are pulled into L2 on a low-priority side stream one step ahead
     // (measured on cfg5: 27.1 us per block step without, 27.8 us with the prefetch -- off by default here)
@@ -1092,6 +1138,7 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
         BBM_CUDA(h, cudaEventRecord(h->side_ev[0], h->stream));
         BBM_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->side_ev[0], 0));
     }
+    h->opts["trsm.last_path"] = 2;
     for (i64 s = 0; s < d->Nr; ++s) {
         const i64 K = upper ? d->Nr - 1 - s : s;
         if (prefetch && s + 1 < d->Nr) {
@@ -1125,6 +1172,272 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
     }
     BBM_CUDA(h, cudaMemcpy2DAsync(d_B, (size_t)ldb * sizeof(double), X, (size_t)ldx * sizeof(double), (size_t)d->m * sizeof(double),
                                   (size_t)nrhs, cudaMemcpyDeviceToDevice, h->stream));
+    return BBM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Data-flow block triangular solve (Float64, >= 16 right-hand sides): the whole chain in ONE persistent kernel.
+// The launch-per-link chain above spends most of a block step in launch gaps, cold prologues and HBM latency
+// (22 us per step on cfg5 for ~3 us of tensor work).  Here every 64 x 32 x 64 piece of the two products of a step
+//     X_K  += inv(T_KK)[i-tile, k-slice] * B_K[k-slice, j-tile]            ("X tile", waits until B_K is complete)
+//     B_Kr -= A[Kr-tile, K][:, k-slice]  * X_K[k-slice, j-tile]            ("update tile", waits until X_K is complete)
+// is a tile of one global list in dependency order.  Resident CTAs (cooperative launch: all of them are co-resident) take
+// the tiles round-robin; each tile first prefetches its STATIC operand (a piece of the matrix or of an inverse -- neither
+// depends on the chain) into shared memory, then waits for its completion counter in L2 (acquire), loads the 16 KB of
+// right-hand-side data that do depend on the chain, multiplies on the FP64 tensor cores, accumulates with red.add and
+// bumps the counter of its target (release).  Launch gaps and HBM latency leave the critical path; the two far updates
+// of a step (2/3 of the flops) overlap the next steps' critical tiles instead of delaying them.  Summation order of the
+// split-k partial sums is not deterministic ("trsm.kernel" = 3 keeps the launch chain, 2 the substitution kernels).
+// ------------------------------------------------------------------------------------------------
+struct FlowTile {
+    i64 astart, lda;      // static operand: rows x kc, element (i,k) at astart + i + k*lda
+    i64 bstart, ldb;      // dynamic operand: kc x cols, element (k,j) at bstart + k + j*ldb
+    i64 cstart, ldc;      // destination tile, element (i,j) at cstart + i + j*ldc
+    int32_t rows, cols, kc, kind;          // kind 0: X tile (inverse * B -> X, +), 1: update tile (matrix * X -> B, -)
+    int32_t wait_ctr, wait_val, sig_ctr, pad;
+};
+
+constexpr int kFlowBM = 64, kFlowBN = 32, kFlowBK = 64;
+constexpr int kFlowLDA = kFlowBM + 4, kFlowLDB = kFlowBK + 4;
+constexpr size_t kFlowSmem = ((size_t)kFlowBK * kFlowLDA + (size_t)kFlowBN * kFlowLDB) * sizeof(double);
+
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __restrict__ tiles, i64 ntiles, const double* __restrict__ data,
+                                                            const double* __restrict__ W, double* __restrict__ Bm, double* __restrict__ X,
+                                                            int* __restrict__ ctr, int err_idx) {
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    double* As = reinterpret_cast<double*>(mm_smem);          // As[k][i]
+    double* Bs = As + (size_t)kFlowBK * kFlowLDA;              // Bs[j][k]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;
+    const int ar = lane >> 2, ac = lane & 3;
+    for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const FlowTile ft = tiles[t];
+        const double* __restrict__ Ap = ft.kind == 0 ? W : data;
+        const double* __restrict__ Bp = ft.kind == 0 ? Bm : X;
+        double* __restrict__ Cp = ft.kind == 0 ? X : Bm;
+        // 1. the static operand (independent of the chain): prefetch while the predecessors still run
+        for (int v = tid; v < (kFlowBM / 2) * kFlowBK; v += 128) {
+            const int kk = v / (kFlowBM / 2), i = 2 * (v % (kFlowBM / 2));
+            int nv = ft.rows - i; nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+            const int bytes = kk < ft.kc ? 8 * nv : 0;
+            cp_async16(As + kk * kFlowLDA + i, bytes ? Ap + ft.astart + i + (i64)kk * ft.lda : Ap, bytes);
+        }
+        cp_async_commit();
+        // 2. wait until every contribution to the dynamic operand has landed (counter in L2)
+        if (tid == 0 && ft.wait_val > 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                __nanosleep(32);
+                if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + err_idx, 1); break; }   // never hang the device
+            }
+        }
+        __syncthreads();
+        // 3. the dynamic operand (right-hand-side data written by red.add in L2: .cg loads bypass L1)
+        for (int v = tid; v < kFlowBN * (kFlowBK / 2); v += 128) {
+            const int j = v / (kFlowBK / 2), kk = 2 * (v % (kFlowBK / 2));
+            int nv = ft.kc - kk; nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+            const int bytes = j < ft.cols ? 8 * nv : 0;
+            cp_async16(Bs + j * kFlowLDB + kk, bytes ? Bp + ft.bstart + kk + (i64)j * ft.ldb : Bp, bytes);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // 4. 64 x 32 x kc on the FP64 tensor cores: 4 warps, warp tile 32 x 16
+        double acc[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int ksteps = (ft.kc + 3) >> 2;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int k4 = ks * 4;
+            double af[4], bf[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[(k4 + ac) * kFlowLDA + wm0 + i * 8 + ar];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = Bs[(wn0 + j * 8 + ar) * kFlowLDB + k4 + ac];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        // 5. accumulate into the destination and publish
+        const double sgn = ft.kind == 0 ? 1.0 : -1.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = wm0 + i * 8 + ar;
+            if (row >= ft.rows) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int col = wn0 + j * 8 + 2 * ac + q;
+                    if (col < ft.cols) atomicAdd(Cp + ft.cstart + row + (i64)col * ft.ldc, sgn * acc[i][j][q]);
+                }
+        }
+        __threadfence();
+        __syncthreads();   // also: nobody still reads As / Bs when the next tile's prefetch overwrites them
+        if (tid == 0) atomicAdd(ctr + ft.sig_ctr, 1);
+    }
+}
+
+int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb, i64 ldx, i64 nrhs) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    if (t.flow_ldb == ldb && t.flow_nrhs == nrhs && t.flow_ldx == ldx && t.flow_ctr) return BBM_OK;
+    const i64 N = d->Nr;
+    std::vector<FlowTile> tiles;
+    std::vector<int> nA(N, 0), nB(N, 0);
+    bool even = !(ldb & 1) && !(ldx & 1);
+    // pass 1 builds the tiles with the counters' indices, pass 2 fills in the target values
+    for (i64 s = 0; s < N; ++s) {
+        const i64 K = upper ? N - 1 - s : s;
+        const i64 rK = d->r[K];
+        if (rK == 0) continue;
+        const i64 wo = t.woff[K], wl = t.wld[K];
+        for (i64 i0 = 0; i0 < rK; i0 += kFlowBM) {
+            const i64 nr = std::min<i64>(kFlowBM, rK - i0);
+            const i64 klo = upper ? i0 : 0, khi = upper ? rK : std::min<i64>(rK, i0 + kFlowBM);   // skip the zero triangle of the inverse
+            for (i64 k0 = klo; k0 < khi; k0 += kFlowBK) {
+                const i64 kc = std::min<i64>(kFlowBK, khi - k0);
+                for (i64 j0 = 0; j0 < nrhs; j0 += kFlowBN) {
+                    FlowTile ft{wo + i0 + k0 * wl, wl, d->R[K] + k0 + j0 * ldb, ldb, d->R[K] + i0 + j0 * ldx, ldx,
+                                (int32_t)nr, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kc, 0, (int32_t)K, 0, (int32_t)(N + K), 0};
+                    even = even && !(ft.astart & 1) && !(ft.lda & 1) && !(ft.bstart & 1);
+                    tiles.push_back(ft);
+                    ++nA[K];
+                }
+            }
+        }
+        // update tiles, nearest block row first (it is the one the next step waits for)
+        const i64 Kfirst = upper ? K - 1 : K + 1, Klast = upper ? d->klo[K] : d->khi[K];
+        for (i64 Kr = Kfirst; upper ? Kr >= Klast : Kr <= Klast; Kr += upper ? -1 : 1) {
+            const i64 rr = d->r[Kr];
+            if (rr == 0) continue;
+            const i64 bs = sky_start(d, Kr, K);
+            for (i64 i0 = 0; i0 < rr; i0 += kFlowBM) {
+                const i64 nr = std::min<i64>(kFlowBM, rr - i0);
+                for (i64 k0 = 0; k0 < rK; k0 += kFlowBK) {
+                    const i64 kc = std::min<i64>(kFlowBK, rK - k0);
+                    for (i64 j0 = 0; j0 < nrhs; j0 += kFlowBN) {
+                        FlowTile ft{bs + i0 + k0 * d->S[K], d->S[K], d->R[K] + k0 + j0 * ldx, ldx, d->R[Kr] + i0 + j0 * ldb, ldb,
+                                    (int32_t)nr, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kc, 1, (int32_t)(N + K), 0, (int32_t)Kr, 0};
+                        even = even && !(ft.astart & 1) && !(ft.lda & 1) && !(ft.bstart & 1);
+                        tiles.push_back(ft);
+                        ++nB[Kr];
+                    }
+                }
+            }
+        }
+    }
+    for (FlowTile& ft : tiles) ft.wait_val = ft.kind == 0 ? nB[ft.wait_ctr] : nA[ft.wait_ctr - N];
+    if (t.flow_tiles) { cudaFree(t.flow_tiles); t.flow_tiles = nullptr; }
+    if (t.flow_ctr) { cudaFree(t.flow_ctr); t.flow_ctr = nullptr; }
+    t.flow_ok = even && !tiles.empty() && tiles.size() < (size_t)INT32_MAX;
+    t.flow_ntiles = (i64)tiles.size();
+    if (t.flow_ok) {
+        FlowTile* dt = nullptr;
+        int32_t rc = upload(h, tiles, &dt);
+        if (rc != BBM_OK) return rc;
+        t.flow_tiles = dt;
+    }
+    cudaError_t e = cudaMalloc(&t.flow_ctr, sizeof(int) * (size_t)(2 * N + 1));
+    if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
+    t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx;
+    return BBM_OK;
+}
+
+// ||T_KK||_inf and ||inv(T_KK)||_inf per diagonal block (one CTA each): the condition guard of the inverse-based paths.
+// blk holds 5 entries per block: offset of T_KK in `data`, its leading dimension, offset of the inverse in W, its
+// leading dimension, rows.
+__global__ void __launch_bounds__(256) sky_tri_cond_kernel(const double* __restrict__ data, const double* __restrict__ W, const i64* __restrict__ blk,
+                                                           int upper, int unit, double* __restrict__ out) {
+    const i64 K = blockIdx.x;
+    const i64 ds = blk[5 * K], ld = blk[5 * K + 1], wo = blk[5 * K + 2], wld = blk[5 * K + 3];
+    const int r = (int)blk[5 * K + 4];
+    __shared__ double red[2][256];
+    double mt = 0.0, mw = 0.0;
+    for (int i = threadIdx.x; i < r; i += 256) {
+        double st = 0.0, sw = 0.0;
+        const int jlo = upper ? i : 0, jhi = upper ? r : i + 1;
+        for (int j = jlo; j < jhi; ++j) {
+            const double tv = (unit && j == i) ? 1.0 : data[ds + i + (i64)j * ld];
+            st += fabs(tv);
+            sw += fabs(W[wo + i + (i64)j * wld]);
+        }
+        mt = fmax(mt, st); mw = fmax(mw, sw);
+    }
+    red[0][threadIdx.x] = mt; red[1][threadIdx.x] = mw;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + o]);
+            red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * K] = red[0][0]; out[2 * K + 1] = red[1][0]; }
+}
+
+int32_t tri_condition(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, const double* d_data, const double* W, double* cond_max) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    const i64 N = d->Nr;
+    *cond_max = 0.0;
+    if (N == 0) return BBM_OK;
+    if (!t.d_cond) {
+        std::vector<i64> blk(5 * N);
+        for (i64 K = 0; K < N; ++K) {
+            blk[5 * K] = d->r[K] ? sky_start(d, K, K) : 0; blk[5 * K + 1] = d->S[K];
+            blk[5 * K + 2] = t.woff[K]; blk[5 * K + 3] = t.wld[K]; blk[5 * K + 4] = d->r[K];
+        }
+        // one allocation: [2N doubles of results | 5N table entries]
+        cudaError_t e = cudaMalloc(&t.d_cond, sizeof(double) * (size_t)(2 * N) + sizeof(i64) * (size_t)(5 * N));
+        if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(condition table): %s", cudaGetErrorString(e)); }
+        BBM_CUDA(h, cudaMemcpy(t.d_cond + 2 * N, blk.data(), sizeof(i64) * (size_t)(5 * N), cudaMemcpyHostToDevice));
+    }
+    sky_tri_cond_kernel<<<(unsigned)N, 256, 0, h->stream>>>(d_data, W, reinterpret_cast<const i64*>(t.d_cond + 2 * N), upper, unit, t.d_cond);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_tri_cond_kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    std::vector<double> out(2 * N);
+    BBM_CUDA(h, cudaMemcpyAsync(out.data(), t.d_cond, sizeof(double) * (size_t)(2 * N), cudaMemcpyDeviceToHost, h->stream));
+    BBM_CUDA(h, cudaStreamSynchronize(h->stream));
+    double c = 0.0;
+    for (i64 K = 0; K < N; ++K) {
+        const double v = out[2 * K] * out[2 * K + 1];
+        if (!(v == v)) { c = INFINITY; break; }   // NaN (a zero on a diagonal): not for the inverse path
+        c = std::max(c, v);
+    }
+    *cond_max = c;
+    return BBM_OK;
+}
+
+int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const double* d_data, const double* W, double* d_B, double* X) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    const i64 N = d->Nr;
+    cudaError_t e = cudaFuncSetAttribute(sky_trsm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
+    int occ = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sky_trsm_flow_kernel, 128, kFlowSmem);
+    if (e != cudaSuccess || occ < 1) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "data-flow solve: occupancy query failed"); }
+    const i64 cap = bbm_opt(h, "trsm.flow_ctas_per_sm", 0);
+    if (cap > 0) occ = (int)std::min<i64>(occ, cap);
+    const i64 grid = std::min<i64>(t.flow_ntiles, (i64)occ * h->num_sms);
+    BBM_CUDA(h, cudaMemsetAsync(t.flow_ctr, 0, sizeof(int) * (size_t)(2 * N + 1), h->stream));
+    const FlowTile* tiles = static_cast<const FlowTile*>(t.flow_tiles);
+    i64 ntiles = t.flow_ntiles;
+    int* ctr = t.flow_ctr;
+    int err_idx = (int)(2 * N);
+    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&d_data, (void*)&W, (void*)&d_B, (void*)&X, (void*)&ctr, (void*)&err_idx};
+    // cooperative launch: the runtime guarantees that all CTAs are co-resident (the tiles wait for one another)
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(sky_trsm_flow_kernel), dim3((unsigned)grid), dim3(128), args, kFlowSmem, h->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "sky_trsm_flow_kernel launch: %s", cudaGetErrorString(e)); }
+    h->launches += 1;
     return BBM_OK;
 }
 
@@ -1755,8 +2068,12 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
         size_t free_b = 0, total_b = 0;
         const size_t have = h->ws_z_bytes + h->ws_w_bytes + h->ws_y_bytes;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
-        if (wbytes <= 0.5 * ((double)free_b + (double)have))
-            return sky_trsm_gemm(h, d, upper, unit ? 1 : 0, reinterpret_cast<const double*>(d_data), reinterpret_cast<double*>(d_B), ldb, nrhs);
+        if (wbytes <= 0.5 * ((double)free_b + (double)have)) {
+            bool fallback = false;
+            rc = sky_trsm_gemm(h, d, upper, unit ? 1 : 0, reinterpret_cast<const double*>(d_data), reinterpret_cast<double*>(d_B), ldb, nrhs, &fallback);
+            if (rc != BBM_OK || !fallback) return rc;
+            // ill-conditioned diagonal blocks: substitution below (backward stable like the reference's trsv)
+        }
     }
     // pass 0: inverses of the 32x32 diagonal sub-blocks (workspace: 1024 entries per sub-block)
     rc = bbm_ws_reserve(h, &h->ws_x, &h->ws_x_bytes, (size_t)t.nsub * 1024 * sizeof(T));
@@ -1958,6 +2275,9 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         for (auto& b : d->tri[t].inv_levels) free_batch(b);
         free_batch(d->tri[t].stepA);
         free_batch(d->tri[t].stepB);
+        if (d->tri[t].flow_tiles) cudaFree(d->tri[t].flow_tiles);
+        if (d->tri[t].flow_ctr) cudaFree(d->tri[t].flow_ctr);
+        if (d->tri[t].d_cond) cudaFree(d->tri[t].d_cond);
     }
     if (d->rev) { bbm_sky_desc_destroy(d->rev); d->rev = nullptr; }
     if (d->d_titems) cudaFree(d->d_titems);

@@ -145,6 +145,21 @@ class DistBandedBlockBandedMatrix:
                    C.c_void_p(y_own.ptr)), h.h, "bbm_dist_bbb_mul")
         return y_own
 
+    def mul_host_(self, y_own: np.ndarray, x_own: np.ndarray, alpha=1.0, beta=0.0):
+        """y_own <- alpha*A[K0:K1,:]*x + beta*y_own with the rank's vectors on the host (pinned arrays for full PCIe
+        speed): ``bbm_dist_bbb_mul_host_*`` -- upload, halo exchange, product and download pipelined over block-row
+        chunks.  Collective and synchronous."""
+        h = self.comm.handle
+        if x_own.shape != (self.layout["n_own"],) or y_own.shape != (self.layout["m_own"],):
+            raise L.DimensionMismatch(f"x_own must have {self.layout['n_own']} entries and y_own {self.layout['m_own']}")
+        if np.dtype(x_own.dtype) != self.dtype or np.dtype(y_own.dtype) != self.dtype:
+            raise TypeError("eltype mismatch")
+        suf, ct = ("f64", C.c_double) if self.dtype == np.float64 else ("f32", C.c_float)
+        fn = getattr(h._lib, f"bbm_dist_bbb_mul_host_{suf}")
+        L.check(fn(self.plan, ct(alpha), C.c_void_p(self.data.ptr), x_own.ctypes.data_as(C.c_void_p), ct(beta),
+                   y_own.ctypes.data_as(C.c_void_p)), h.h, "bbm_dist_bbb_mul_host")
+        return y_own
+
     def enable_peer(self) -> bool:
         """Collective.  Switch the halo exchange to the fused peer-memory push inside the band-walk
         kernel (``bbm_dist_bbb_enable_peer``); returns False if the partition does not qualify and

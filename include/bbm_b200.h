@@ -367,6 +367,16 @@ int32_t bbm_dist_bbb_mul_f64(bbm_dist_bbb_plan_t p, double alpha, const double* 
 int32_t bbm_dist_bbb_mul_f32(bbm_dist_bbb_plan_t p, float alpha, const float* d_data_local, float* d_x_local,
                              int64_t nrhs, float beta, float* d_y_own);
 
+/* The same product with the rank's vectors on the HOST (the reference-facing call when x and y live in Julia Arrays):
+ * h_x_own (n_own entries) is uploaded, the halo blocks travel over NCCL, the owned rows are multiplied and h_y_own
+ * (m_own entries) comes back -- pipelined over block-row chunks (upload of chunk i+1, product of chunk i, download of
+ * chunk i-1 and the halo exchange all overlap), synchronous like bbm_bbb_mul_host_*.  One right-hand side.  The device
+ * workspaces belong to the plan.  Pinned host memory (bbm_host_alloc) for full PCIe speed.  Collective.            */
+int32_t bbm_dist_bbb_mul_host_f64(bbm_dist_bbb_plan_t p, double alpha, const double* d_data_local, const double* h_x_own, double beta,
+                                  double* h_y_own);
+int32_t bbm_dist_bbb_mul_host_f32(bbm_dist_bbb_plan_t p, float alpha, const float* d_data_local, const float* h_x_own, float beta,
+                                  float* h_y_own);
+
 /* ---- several GPUs: row-block-partitioned BlockBandedMatrix (matvec and A*B, cfg4) -----------------------------
  * Block rows are split exactly like the banded-block-banded case (bbm_bbb_partition_rows; x / the block rows of a
  * right factor B are owned like y).  A block-row range [S0,S1) of a BlockBandedMatrix(rows, cols, (l,u)) is a

@@ -23,6 +23,7 @@ using BlockBandedMatrices
 using BlockBandedMatrices: BandedBlockBandedMatrix, BlockSkylineMatrix, BandedBlockBandedColumns,
                            BlockBandedColumns, blockbandwidths, subblockbandwidths, colblockbandwidths
 using BlockBandedMatrices.ArrayLayouts: MulAdd, Ldiv, TriangularLayout, MemoryLayout, DenseColumnMajor
+using LinearAlgebra: UniformScaling
 import BlockBandedMatrices.ArrayLayouts: materialize!, triangulardata
 using BlockBandedMatrices.BlockArrays: BlockedMatrix, blocklengths, blocksize
 using BlockBandedMatrices.BandedMatrices: BandError
@@ -60,13 +61,24 @@ end
 mutable struct B200Array{T,N} <: DenseArray{T,N}
     ptr::Ptr{T}
     dims::NTuple{N,Int}
+    # descriptors of the matrix structures laid over this buffer (structure key => (kind, bbm_*_desc_t)); they live and
+    # die with the buffer -- the containers themselves are immutable structs and cannot carry finalizers
+    descs::Dict{Any,Tuple{Symbol,Ptr{Cvoid}}}
     function B200Array{T,N}(::UndefInitializer, dims::NTuple{N,Int}) where {T,N}
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:bbm_malloc, libbbm), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Csize_t), handle().ptr, r, sizeof(T) * prod(dims)))
-        a = new{T,N}(Ptr{T}(r[]), dims)
-        finalizer(x -> ccall((:bbm_free, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), handle().ptr, x.ptr), a)
+        a = new{T,N}(Ptr{T}(r[]), dims, Dict{Any,Tuple{Symbol,Ptr{Cvoid}}}())
+        finalizer(a) do x
+            for (kind, p) in values(x.descs)
+                kind === :bbb ? ccall((:bbm_bbb_desc_destroy, libbbm), Int32, (Ptr{Cvoid},), p) :
+                                ccall((:bbm_sky_desc_destroy, libbbm), Int32, (Ptr{Cvoid},), p)
+            end
+            ccall((:bbm_free, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), handle().ptr, x.ptr)
+        end
     end
 end
+B200Array{T}(::UndefInitializer, dims::Integer...) where T = B200Array{T,length(dims)}(undef, map(Int, dims))
+B200Array{T}(::UndefInitializer, dims::NTuple{N,Integer}) where {T,N} = B200Array{T,N}(undef, map(Int, dims))
 const B200Vector{T} = B200Array{T,1}
 const B200Matrix{T} = B200Array{T,2}
 Base.size(a::B200Array) = a.dims
@@ -103,29 +115,36 @@ b200(A::BlockSkylineMatrix{T}) where T<:Union{Float32,Float64} =
 const B200BBB{T} = BandedBlockBandedMatrix{T,<:BlockedMatrix{T,<:B200Matrix{T}}}
 const B200Sky{T} = BlockSkylineMatrix{T,<:B200Vector{T}}
 
-# ---- descriptors (cached per matrix structure) -----------------------------------------------
-const desc_cache = IdDict{Any,Ptr{Cvoid}}()
+# ---- descriptors ------------------------------------------------------------------------------
+# A descriptor depends on the block structure only and is cached in the device buffer it is used with (no global table:
+# nothing keeps a dropped matrix alive, and its descriptors are destroyed by the buffer's finalizer).  Sub-views over the
+# same buffer get their own entry (different structure key).
+desc_table(buf::B200Array) = buf.descs
+
 function descriptor(A::B200BBB)
-    get!(desc_cache, A) do
-        r = Int64.(blocklengths(axes(A, 1))); c = Int64.(blocklengths(axes(A, 2)))
-        l, u = blockbandwidths(A); λ, μ = subblockbandwidths(A)
+    r = Int64.(blocklengths(axes(A, 1))); c = Int64.(blocklengths(axes(A, 2)))
+    l, u = blockbandwidths(A); λ, μ = subblockbandwidths(A)
+    tab = desc_table(parent(A.data))
+    last(get!(tab, (:bbb, r, c, l, u, λ, μ)) do
         d = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:bbm_bbb_desc_create, libbbm), Int32,
                     (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Int64, Int64, Ref{Ptr{Cvoid}}),
                     handle().ptr, length(r), length(c), r, c, l, u, λ, μ, d))
-        d[]
-    end
+        (:bbb, d[])
+    end)
 end
 function descriptor(A::B200Sky)
-    get!(desc_cache, A) do
-        r = Int64.(blocklengths(axes(A, 1))); c = Int64.(blocklengths(axes(A, 2)))
-        l, u = colblockbandwidths(A)
+    r = Int64.(blocklengths(axes(A, 1))); c = Int64.(blocklengths(axes(A, 2)))
+    l, u = colblockbandwidths(A)
+    lv, uv = Vector{Int64}(l), Vector{Int64}(u)
+    tab = desc_table(A.data)
+    last(get!(tab, (:sky, r, c, lv, uv)) do
         d = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:bbm_sky_desc_create, libbbm), Int32,
                     (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
-                    handle().ptr, length(r), length(c), r, c, Vector{Int64}(l), Vector{Int64}(u), d))
-        d[]
-    end
+                    handle().ptr, length(r), length(c), r, c, lv, uv, d))
+        (:sky, d[])
+    end)
 end
 
 suffix(::Type{Float64}) = :f64
@@ -178,9 +197,11 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
         A, x, y = triangulardata(M.A), M.B, M.C
         size(A, 2) == size(x, 1) && size(A, 1) == size(y, 1) && size(x, 2) == size(y, 2) ||
             throw(DimensionMismatch("A has size $(size(A)), x has size $(size(x)), y has size $(size(y))"))
-        check(ccall(($(QuoteNode(Symbol("bbm_bbb_trimul_", suf))), libbbm), Int32,
-                    (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
-                    handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
+        rc = ccall(($(QuoteNode(Symbol("bbm_bbb_trimul_", suf))), libbbm), Int32,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
+                   handle().ptr, descriptor(A), Int32(UPLO), Int32(UNIT == 'U'), M.α, parent(A.data).ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y))
+        rc == BBM_ERR_UNSUPPORTED && return invoke(materialize!, Tuple{MulAdd}, M)   # blocks that do not match: the reference's generic path
+        check(rc)
         y
     end
     # mul!(y, A', x) / transpose(A)*x for real T: the adjoint's Rows layout (src/adjtransblockbanded.jl:2-7)
@@ -298,6 +319,100 @@ function LinearAlgebra.lmul!(adjQ::Adjoint{Float64,<:MatrixFactorizations.QRPack
     check(ccall((:bbm_sky_qr_lmul_adj_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
                 handle().ptr, descriptor(Q.factors), Q.factors.data.ptr, Q.τ.ptr, B.ptr, ld(B), size(B, 2)))
     B
+end
+
+# ---- structured +, -, alpha*A + B and A +- (I | Diagonal | Bidiagonal | Tridiagonal) on the device -------------------
+# The result STRUCTURE stays with the reference (`similar(bc)`: src/broadcast.jl:107-131, 391-411 -- `similar` of a
+# B200-backed matrix is B200-backed; copy_accommodating_diagonals: src/BlockSkylineMatrix.jl:502-531); these methods
+# replace the per-block copyto! loops of src/broadcast.jl:317-388 and the element loops of src/BlockSkylineMatrix.jl:535-638.
+skyptr(A::B200Sky) = A.data.ptr
+bbbptr(A::B200BBB) = parent(A.data).ptr
+for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
+    @eval function b200_axpby!(C::B200BBB{$T}, α::$T, A::B200BBB{$T}, β::$T, B::Union{Nothing,B200BBB{$T}})
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_add_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, $T, Ptr{$T}, Ptr{$T}),
+                    handle().ptr, descriptor(A), B === nothing ? C_NULL : descriptor(B), descriptor(C), α, bbbptr(A), β,
+                    B === nothing ? Ptr{$T}(C_NULL) : bbbptr(B), bbbptr(C)))
+        C
+    end
+    @eval function b200_axpby!(C::B200Sky{$T}, α::$T, A::Union{B200Sky{$T},B200BBB{$T}}, β::$T, B::Union{Nothing,B200Sky{$T},B200BBB{$T}})
+        sky(X) = X isa B200Sky ? descriptor(X) : C_NULL
+        bbb(X) = X isa B200BBB ? descriptor(X) : C_NULL
+        ptr(X) = X === nothing ? Ptr{$T}(C_NULL) : (X isa B200Sky ? skyptr(X) : bbbptr(X))
+        check(ccall(($(QuoteNode(Symbol("bbm_sky_add_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, $T, Ptr{$T}, Ptr{$T}),
+                    handle().ptr, sky(A), bbb(A), sky(B), bbb(B), descriptor(C), α, ptr(A), β, ptr(B), skyptr(C)))
+        C
+    end
+    # C .= A .+ B / C .= A .- B (src/broadcast.jl:317-372) and C .= α .* A .+ B (:379-388)
+    for (op, β) in ((:+, 1), (:-, -1))
+        @eval function Base.copyto!(C::Union{B200Sky{$T},B200BBB{$T}}, bc::Base.Broadcast.Broadcasted{<:BlockBandedMatrices.AbstractBlockBandedStyle,<:Any,typeof($op),
+                                    <:Tuple{<:Union{B200Sky{$T},B200BBB{$T}},<:Union{B200Sky{$T},B200BBB{$T}}}})
+            A, B = bc.args
+            b200_axpby!(C, one($T), A, $T($β), B)
+        end
+    end
+    @eval function Base.copyto!(C::Union{B200Sky{$T},B200BBB{$T}}, bc::Base.Broadcast.Broadcasted{<:BlockBandedMatrices.AbstractBlockBandedStyle,<:Any,typeof(+),
+                                <:Tuple{<:Base.Broadcast.Broadcasted{<:BlockBandedMatrices.AbstractBlockBandedStyle,<:Any,typeof(*),<:Tuple{<:Number,<:Union{B200Sky{$T},B200BBB{$T}}}},
+                                        <:Union{B200Sky{$T},B200BBB{$T}}}})
+        αA, B = bc.args
+        α, A = αA.args
+        b200_axpby!(C, $T(α), A, one($T), B)
+    end
+    # in place: A[i,i] += α(λ + d[i]), A[i,i+1] += α du[i], A[i+1,i] += α dl[i]
+    @eval function b200_add_diags!(A::B200Sky{$T}, α::$T, λ::$T, dl, d, du)
+        dev(v) = v === nothing ? Ptr{$T}(C_NULL) : v.ptr
+        check(ccall(($(QuoteNode(Symbol("bbm_sky_add_diags_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, $T, $T, Ptr{$T}, Ptr{$T}, Ptr{$T}),
+                    handle().ptr, descriptor(A), skyptr(A), α, λ, dev(dl), dev(d), dev(du)))
+        A
+    end
+    @eval function b200_add_diags!(A::B200BBB{$T}, α::$T, λ::$T, dl, d, du)
+        dev(v) = v === nothing ? Ptr{$T}(C_NULL) : v.ptr
+        check(ccall(($(QuoteNode(Symbol("bbm_bbb_add_diags_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, $T, $T, Ptr{$T}, Ptr{$T}, Ptr{$T}),
+                    handle().ptr, descriptor(A), bbbptr(A), α, λ, dev(dl), dev(d), dev(du)))
+        A
+    end
+    # A ± λI and λI ± A (src/BlockSkylineMatrix.jl:535-549); the Diagonal / Bidiagonal / Tridiagonal methods (:551-638)
+    # follow the same two calls with their diagonals uploaded as B200Vectors
+    for (op, s) in ((:+, 1), (:-, -1))
+        @eval function Base.$op(A::B200Sky{$T}, J::UniformScaling)
+            B = BlockBandedMatrices.copy_accommodating_diagonals(A, 0:0)      # `similar` keeps the B200 buffer type; the copy is b200_axpby!
+            b200_add_diags!(B, $T($s), $T(J.λ), nothing, nothing, nothing)
+        end
+        @eval function Base.$op(J::UniformScaling, A::B200Sky{$T})
+            B = BlockBandedMatrices.copy_accommodating_diagonals(A, 0:0)
+            $s == -1 && LinearAlgebra.lmul!(-one($T), B.data)
+            b200_add_diags!(B, one($T), $T(J.λ), nothing, nothing, nothing)
+        end
+    end
+    @eval function BlockBandedMatrices.BlockSkylineMatrix{$T}(A::B200Sky{$T}, sizes::BlockBandedMatrices.BlockSkylineSizes)
+        B = BlockBandedMatrices._BlockSkylineMatrix(B200Array{$T}(undef, BlockBandedMatrices.bb_numentries(sizes)), sizes)
+        b200_axpby!(B, one($T), A, zero($T), nothing)                        # copy into the wider structure (:530)
+    end
+    @eval function LinearAlgebra.lmul!(a::$T, x::B200Array{$T})
+        check(ccall(($(QuoteNode(Symbol("bbm_scal_", suf))), libbbm), Int32, (Ptr{Cvoid}, Int64, $T, Ptr{$T}), handle().ptr, length(x), a, x.ptr))
+        x
+    end
+end
+
+# ---- several GPUs (one Julia process per GPU, MPI.jl / Distributed ships the 128-byte NCCL id) --------------------------
+# bbm_comm_unique_id / bbm_comm_create, then per matrix structure one plan:
+#   banded-block-banded matvec        bbm_dist_bbb_plan_create / bbm_dist_bbb_enable_peer / bbm_dist_bbb_mul_f64
+#   block-banded matvec               bbm_dist_sky_plan_create / bbm_dist_sky_mul_f64
+#   block-banded x block-banded       bbm_dist_sky_mm_plan_create / bbm_dist_sky_matmul_f64   (cfg4: row blocks over 8 GPUs)
+# The local structures are ordinary B200Sky / B200BBB matrices built from bbm_dist_sky_plan_layout /
+# bbm_dist_sky_mm_plan_info + *_bandwidths (INTEGRATION.md shows the calls).
+function dist_sky_mul!(plan::Ptr{Cvoid}, y::B200Array{Float64}, Aloc::B200Sky{Float64}, xlocal::B200Array{Float64}, α=1.0, β=0.0)
+    check(ccall((:bbm_dist_sky_mul_f64, libbbm), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Int64, Float64, Ptr{Float64}),
+                plan, α, skyptr(Aloc), xlocal.ptr, size(xlocal, 2), β, y.ptr))
+    y
+end
+function dist_sky_matmul!(plan::Ptr{Cvoid}, Cloc::B200Sky{Float64}, Aloc::B200Sky{Float64}, Bloc::B200Sky{Float64}, α=1.0, β=0.0)
+    check(ccall((:bbm_dist_sky_matmul_f64, libbbm), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                plan, α, skyptr(Aloc), skyptr(Bloc), β, skyptr(Cloc)))
+    Cloc
 end
 
 synchronize() = check(ccall((:bbm_synchronize, libbbm), Int32, (Ptr{Cvoid},), handle().ptr))

@@ -66,6 +66,19 @@ def main():
                 if lay["m_own"] and (np.isnan(got).any() or relerr(got, want) > tol(np.float64, nnz)):
                     failures.append((ci, use_peer, epoch, "mismatch", relerr(got, want)))
                 dist.barrier()
+            # the host-vector call (pipelined upload / exchange / product / download) on the same operands
+            if not use_peer:
+                for beta in (0.0, 0.5):
+                    x = rng.standard_normal(sum(cols))
+                    xo = np.ascontiguousarray(x[c0 + o:c0 + o + lay["n_own"]])
+                    yo = np.ascontiguousarray(y0[lay["row_offset"]:lay["row_offset"] + lay["m_own"]])
+                    dist.barrier()
+                    A.mul_host_(yo, xo, 1.5, beta)
+                    ref = y0.copy()
+                    O.bbb_mul(rows, cols, *lu, *lm, 1.5, data, x, beta, ref)
+                    want = ref[lay["row_offset"]:lay["row_offset"] + lay["m_own"]]
+                    if lay["m_own"] and (np.isnan(yo).any() or relerr(yo, want) > tol(np.float64, F.bbb_nnz_per_row_max(*lu, *lm) + 1)):
+                        failures.append((ci, "host-vector product", beta, relerr(yo, want)))
             active, timed_out = A.peer_status()
             if timed_out:
                 failures.append((ci, use_peer, "peer wait timed out"))

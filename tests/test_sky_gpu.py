@@ -224,6 +224,99 @@ def test_sky_trsm_matches_oracle(handle, case, uplo, unit, dtype):
         assert relerr(Tm @ X, B0.astype(np.float64)) <= tol(dtype, m) * 4
 
 
+@pytest.mark.parametrize("uplo", ["U", "L"])
+@pytest.mark.parametrize("kernel,path", [(0, 1), (3, 2), (2, 0)])
+def test_sky_trsm_many_rhs_every_path(handle, uplo, kernel, path):
+    """64 right-hand sides, aligned block sizes: the data-flow kernel (one persistent launch, default), the launch chain
+    ("trsm.kernel" = 3) and the substitution kernels (= 2) against the oracle; several block steps deep so that every
+    counter of the data-flow kernel is exercised (far updates of 3 block columns, ragged multiples of 2)."""
+    rows = [128, 64, 192, 66, 0, 130, 64, 256, 32, 96, 64, 128]
+    l, u = (0, 3) if uplo == "U" else (3, 0)
+    rng = np.random.default_rng(81)
+    m = sum(rows)
+    data = rng.standard_normal(B.BlockSkylineMatrix.numentries(rows, rows, l, u)) / np.sqrt(m)
+    A = B.BlockSkylineMatrix(data, rows, rows, l, u)
+    for K in range(len(rows)):
+        if rows[K]:
+            s, ld = A.block_start(K, K), int(A.block_strides[K])
+            i = np.arange(rows[K])
+            data[s + i + i * ld] += 10
+    Ad = A.to_device(handle)
+    T = (B.UpperTriangular if uplo == "U" else B.LowerTriangular)(Ad)
+    handle.set_option("trsm.kernel", kernel)
+    try:
+        for nrhs in (64, 40, 16):
+            B0 = np.asfortranarray(rng.standard_normal((m, nrhs)))
+            dB = handle.to_device(B0)
+            handle.set_option("trsm.last_path", 0)
+            B.ldiv_(T, dB)
+            got = dB.to_host()
+            assert handle.get_option("trsm.last_path") == path
+            ref = B0.copy(order="F")
+            O.sky_trsm(rows, l, u, uplo, False, data, ref)
+            assert not np.isnan(got).any()
+            assert relerr(got, ref) <= tol(np.float64, 4 * 256)
+    finally:
+        handle.set_option("trsm.kernel", 0)
+
+
+def test_sky_trsm_condition_guard(handle):
+    """Ill-conditioned diagonal blocks (cond about 1e7): the inverse-based paths are not backward stable, so the solve must
+    fall back to substitution -- like the reference's trsv -- and leave a residual at the n*eps level; with the guard
+    switched off the explicit inverses show the cond*eps residual the guard exists to avoid."""
+    rows = [64] * 8
+    l, u = 0, 2
+    rng = np.random.default_rng(82)
+    m = sum(rows)
+    data = rng.standard_normal(B.BlockSkylineMatrix.numentries(rows, rows, l, u)) / np.sqrt(m)
+    A = B.BlockSkylineMatrix(data, rows, rows, l, u)
+    for K in range(len(rows)):
+        s, ld = A.block_start(K, K), int(A.block_strides[K])
+        Q1, _ = np.linalg.qr(rng.standard_normal((64, 64)))
+        R = np.triu(Q1 @ np.diag(np.logspace(0, -7, 64)) @ Q1.T + 0.0)      # upper triangle of a matrix with cond 1e7
+        R[np.arange(64), np.arange(64)] = np.where(np.abs(np.diag(R)) < 1e-6, 1e-6, np.diag(R))
+        for j in range(64):
+            data[s + j * ld:s + j * ld + 64] = R[:, j]
+    D = np.triu(A.to_dense())
+    cond = max(np.linalg.cond(D[64 * K:64 * K + 64, 64 * K:64 * K + 64], np.inf) for K in range(8))
+    assert cond > 1e5
+    Ad = A.to_device(handle)
+    T = B.UpperTriangular(Ad)
+    B0 = np.asfortranarray(rng.standard_normal((m, 32)))
+
+    def residual(X):
+        return np.linalg.norm(D @ X - B0) / (np.linalg.norm(D, 2) * np.linalg.norm(X) + np.linalg.norm(B0))
+    dB = handle.to_device(B0)
+    B.ldiv_(T, dB)
+    assert handle.get_option("trsm.last_path") == 3                      # substitution
+    assert handle.get_option("trsm.last_cond_x1000") / 1000.0 >= 0.01 * cond
+    X = dB.to_host()
+    assert residual(X) <= 64 * 2.22e-16 * 192
+    ref = B0.copy(order="F")
+    O.sky_trsm(rows, l, u, "U", False, data, ref)
+    assert relerr(X, ref) <= 64 * 2.22e-16 * 192 * cond                  # forward error: cond-scaled, as for any backward-stable solve
+    # the guard off: the explicit-inverse path still runs (and is what the guard protects against)
+    handle.set_option("trsm.cond_check", 0)
+    try:
+        dB2 = handle.to_device(B0)
+        B.ldiv_(T, dB2)
+        assert handle.get_option("trsm.last_path") == 1
+        assert np.isfinite(dB2.to_host()).all()
+    finally:
+        handle.set_option("trsm.cond_check", 1)
+    # a well-conditioned matrix keeps the fast path
+    data2 = data.copy()
+    A2 = B.BlockSkylineMatrix(data2, rows, rows, l, u)
+    for K in range(len(rows)):
+        s, ld = A2.block_start(K, K), int(A2.block_strides[K])
+        for j in range(64):
+            data2[s + j * ld:s + j * ld + 64] = (rng.standard_normal(64) / 8) * (np.arange(64) <= j)
+            data2[s + j * ld + j] += 10
+    dB3 = handle.to_device(B0)
+    B.ldiv_(B.UpperTriangular(A2.to_device(handle)), dB3)
+    assert handle.get_option("trsm.last_path") == 1
+
+
 def test_sky_trsm_errors(handle):
     A = B.BlockSkylineMatrix.zeros(np.float64, [3, 4], [4, 3], 1, 1).to_device(handle)
     with pytest.raises(B.BBMError):   # no matching square diagonal blocks: not taken by the device path
