@@ -216,6 +216,19 @@ def run_ours(args):
         k, v = kv.split("=")
         h.set_option(k, int(v))
 
+    if args.workload == "cfg4":
+        # secondary workload (not the driver's default): the sharded block-banded x block-banded product of cfg4
+        from benchmarks import dist_cfg4
+        result = dist_cfg4.run(args, torch, dist, B, h, stream, rank, world, local_rank)
+        if rank == 0:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            print(json.dumps(result), flush=True)
+            os.dup2(2, 1)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if world == 1:
         result = bench_single(args, torch, B, h, stream, nb, n, rank)
     else:
@@ -576,6 +589,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=BLOCK, help="number of blocks (default 4096 = cfg2; smaller only for debugging)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"], help="cfg2 (default, BASELINE.json's metric) or the sharded cfg4 product")
+    ap.add_argument("--cfg4-blocks", type=int, default=2048, help="--workload cfg4: number of 256-row blocks (2048 = cfg4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the full-size cfg3/cfg4/cfg5 lines of `extra` (profiling runs)")
     ap.add_argument("--e2e-serial", action="store_true", help="N > 1: time the serial copy / product / copy end-to-end step instead of the pipelined host call")

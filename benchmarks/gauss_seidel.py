@@ -24,7 +24,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def heat_step_matrix(B, n, dtype=np.float64):
-    """A = I - dt*Laplacian with dt = (1/n^2)/4 (examples/finitedifference_2d.jl:53-55), band storage."""
+    """A = I - dt*Laplacian with dt = (1/n^2)/4 (examples/finitedifference_2d.jl:53-55), band storage, on the host
+    (the check's reference; the timed run assembles the same operator on the device)."""
     A = B.BandedBlockBandedMatrix.finitedifference_2d(n, dtype=dtype)
     dt = (1.0 / n ** 2) / 4
     A.data *= -dt
@@ -32,8 +33,19 @@ def heat_step_matrix(B, n, dtype=np.float64):
     return A
 
 
-def gauss_seidel_device(B, h, Ad, db, sweeps):
-    """returns the device vector x after `sweeps` sweeps started from x = b (the reference's copy(b))"""
+def heat_step_matrix_device(B, h, n, dtype=np.float64):
+    """`A = I - dt*Delta` (examples/finitedifference_2d.jl:50-51) assembled on the device from the device-resident
+    Laplacian: dt*Delta by the structured add (bbm_bbb_add_*), then I - (.) (scale by -1 + bbm_bbb_add_diags_*)."""
+    Lap = B.BandedBlockBandedMatrix.finitedifference_2d(n, dtype=dtype).to_device(h)
+    dt = (1.0 / n ** 2) / 4
+    scaled = B.BandedBlockBandedMatrix(h.empty(Lap.data.shape, dtype), Lap.rows, Lap.cols, (1, 1), (1, 1))
+    B.axpby_(scaled, dt, Lap, 0.0, None)
+    return B.sub(B.UniformScaling(1.0), scaled)
+
+
+def gauss_seidel_device(B, h, Ad, db, sweeps, prepared=None):
+    """returns the device vector x after `sweeps` sweeps started from x = b (the reference's copy(b)); `prepared`: a
+    PreparedTriangular of LowerTriangular(Ad) (the matrix does not change between sweeps)"""
     from bbm_b200 import _lib as L
     m = db.shape[0]
     x = h.empty(m, db.dtype)
@@ -45,7 +57,10 @@ def gauss_seidel_device(B, h, Ad, db, sweeps):
         d2d(r, db)
         B.mul_(r, UU, x, -1.0, 1.0)     # r = b - (x + U x)
         B.axpy_(1.0, x, r)              # r = b - U x
-        B.ldiv_(LL, r)                  # r = L \ r
+        if prepared is not None:
+            prepared.ldiv_(r)           # r = L \ r with the wave-ordered planes of L kept across sweeps
+        else:
+            B.ldiv_(LL, r)
         x, r = r, x
     return x
 
@@ -74,20 +89,36 @@ def main():
     A = heat_step_matrix(B, n)
     rng = np.random.default_rng(7)
     b = rng.standard_normal(n * n)
-    Ad, db = A.to_device(h), h.to_device(b)
-    gauss_seidel_device(B, h, Ad, db, 2)      # warm-up (workspace allocation)
+    t0 = time.perf_counter()
+    Ad = heat_step_matrix_device(B, h, n)
     h.synchronize()
-    dt = float("inf")
-    for _ in range(3):                         # best of 3: the loop is short enough for host jitter to show
-        t0 = time.perf_counter()
-        x = gauss_seidel_device(B, h, Ad, db, args.sweeps)
-        h.synchronize()
-        dt = min(dt, time.perf_counter() - t0)
-    xh = x.to_host()
-    res = A.to_device(h) @ x
+    t_assemble = time.perf_counter() - t0
+    assembled_equal = bool(np.array_equal(Ad.data.to_host(), A.data)) if n <= 2048 else None
+    db = h.to_device(b)
     out = {"example": "examples/finitedifference_2d.jl Gauss-Seidel", "n": n, "unknowns": n * n, "sweeps": args.sweeps,
-           "seconds": dt, "ms_per_sweep": dt / args.sweeps * 1e3, "reference_comment_seconds_n1000_20sweeps": 0.4,
-           "residual_rel": float(np.linalg.norm(res.to_host() - b) / np.linalg.norm(b))}
+           "reference_comment_seconds_n1000_20sweeps": 0.4, "device_assembly_seconds": t_assemble,
+           "device_assembly_equals_host": assembled_equal}
+    for name, prep in (("one_call_ldiv", False), ("prepared", True)):
+        t0 = time.perf_counter()
+        prepared = B.prepare_ldiv(B.LowerTriangular(Ad)) if prep else None
+        h.synchronize()
+        t_prep = time.perf_counter() - t0
+        gauss_seidel_device(B, h, Ad, db, 2, prepared)      # warm-up (workspace allocation)
+        h.synchronize()
+        dt = float("inf")
+        for _ in range(3):                         # best of 3: the loop is short enough for host jitter to show
+            t0 = time.perf_counter()
+            x = gauss_seidel_device(B, h, Ad, db, args.sweeps, prepared)
+            h.synchronize()
+            dt = min(dt, time.perf_counter() - t0)
+        out[name] = {"seconds": dt, "ms_per_sweep": dt / args.sweeps * 1e3, "prepare_seconds": t_prep if prep else 0.0}
+        if prepared is not None:
+            prepared.close()
+    xh = x.to_host()
+    res = Ad @ x
+    out["seconds"] = out["prepared"]["seconds"]
+    out["ms_per_sweep"] = out["prepared"]["ms_per_sweep"]
+    out["residual_rel"] = float(np.linalg.norm(res.to_host() - b) / np.linalg.norm(b))
     if args.check and n <= 200:
         ref = gauss_seidel_host(A, b, args.sweeps)
         out["rel_err_vs_scipy"] = float(np.linalg.norm(xh - ref) / np.linalg.norm(ref))

@@ -10,7 +10,7 @@ from ._lib import BandError, BBMError, DimensionMismatch, build_library, LIB_PAT
 from .broadcast import (Bidiagonal, Diagonal, SymTridiagonal, Tridiagonal, UniformScaling, accommodating_bandwidths, add, add_diags_,  # noqa: F401
                         axpby_, scaled_add, similar_sum, sub)
 from .device import DeviceArray, Handle, PinnedArray  # noqa: F401
-from .linalg import add_bandwidths, axpy_, ldiv, ldiv_, lmul_, lmul_adj_, mul, ql_, qr_, mul_, muladd_, sparse  # noqa: F401
+from .linalg import PreparedTriangular, add_bandwidths, axpy_, ldiv, ldiv_, prepare_ldiv, lmul_, lmul_adj_, mul, ql_, qr_, mul_, muladd_, sparse  # noqa: F401
 from .matrices import (Adjoint, BandedBlockBandedMatrix, BlockBandedMatrix, BlockBandedQL, BlockBandedQR, BlockSkylineMatrix, LowerTriangular,  # noqa: F401
                        UnitLowerTriangular, UnitUpperTriangular, UpperTriangular)
 

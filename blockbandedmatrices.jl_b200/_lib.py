@@ -79,6 +79,11 @@ SIGNATURES = {
     "bbm_sky_qr_ldiv_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
     "bbm_bbb_trsv_f64": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_bbb_trsv_f32": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
+    "bbm_bbb_trsv_prepare_f64": (i32, [vp, vp, i32, i32, vp, pp]),
+    "bbm_bbb_trsv_prepare_f32": (i32, [vp, vp, i32, i32, vp, pp]),
+    "bbm_bbb_trsv_solve_f64": (i32, [vp, vp, i64, i64]),
+    "bbm_bbb_trsv_solve_f32": (i32, [vp, vp, i64, i64]),
+    "bbm_bbb_tri_plan_destroy": (i32, [vp]),
     "bbm_bbb_sparse_colptr": (i32, [vp, vp, i32, vp, C.POINTER(i64)]),
     "bbm_bbb_sparse_fill_f64": (i32, [vp, vp, vp, vp, i32, vp, vp]),
     "bbm_bbb_sparse_fill_f32": (i32, [vp, vp, vp, vp, i32, vp, vp]),

@@ -271,7 +271,12 @@ struct TriWaveParams {
     int N, maxr, iters;
     int l, u, lam, mu, w, P;
     int upper, unit, passes, D, nc, relaxed, what, push;
-    int* status;       // set to 1 if a halo value never arrived (lean kernel; the result is then invalid)
+    int* status;       // [right-hand side] set to 1 if a halo value never arrived (lean kernel; the result is then invalid)
+    // Right-hand-side planes live apart from the matrix planes (plane 0 of `packed` is unused): the plane of right-hand
+    // side q is packed + xoff + q*total.  Pack / unpack take q from blockIdx.z, the solve kernels from their cluster's
+    // index -- several right-hand sides are solved concurrently, one 8-CTA cluster each -- and a prepared plan keeps
+    // its matrix planes in a buffer of its own across calls (bbm_bbb_trsv_prepare_*).
+    i64 xoff, ldb;
 };
 
 constexpr int kTriGroup = 128;                      // lanes dealt to one CTA at a time
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) bbb_tri_pack_kernel(const TriWaveParams<T
                 const int c = cg0 + cc;
                 T v;
                 if (c == 0) {
-                    v = p.x[r0 + k];
+                    v = p.x[(i64)blockIdx.z * p.ldb + r0 + k];
                 } else if (c == 1) {
                     v = p.unit ? T(1) : dcol[mu + (i64)p.P * (r0 + k)];
                 } else if (c < 2 + nd * w) {
@@ -345,7 +350,10 @@ __global__ void __launch_bounds__(256) bbb_tri_pack_kernel(const TriWaveParams<T
             const int Kl = Kl0 + lane;
             if (ok[lane][b]) {
                 T* out = p.packed + (s0 + b) * p.Wd + Kl % p.Wd;
-                for (int cc = 0; cc < ncg; ++cc) out[(i64)(cg0 + cc) * p.total] = stage[cc][lane][b];
+                for (int cc = 0; cc < ncg; ++cc) {
+                    const int c = cg0 + cc;
+                    out[c == 0 ? p.xoff + (i64)blockIdx.z * p.total : (i64)c * p.total] = stage[cc][lane][b];
+                }
             }
         }
         __syncthreads();
@@ -360,7 +368,8 @@ __global__ void __launch_bounds__(256) bbb_tri_unpack_kernel(const TriWaveParams
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
     const int Kl0 = blockIdx.y * 32;
     const i64 s0 = (i64)delta * Kl0 + (i64)blockIdx.x * 32;
-    const bool poison = *p.status != 0;   // a halo value never arrived inside the solve kernel: NaN instead of a wrong answer
+    const bool poison = p.status[blockIdx.z] != 0;   // a halo value never arrived inside the solve kernel: NaN instead of a wrong answer
+    const T* __restrict__ xplane = p.packed + p.xoff + (i64)blockIdx.z * p.total;
     // wave-ordered side: warp = step, lanes = consecutive block rows
     for (int b = warp; b < 32; b += 8) {
         const int Kl = Kl0 + lane;
@@ -368,7 +377,7 @@ __global__ void __launch_bounds__(256) bbb_tri_unpack_kernel(const TriWaveParams
         const i64 kk = s - (i64)delta * Kl;
         const bool in = Kl < p.N && kk >= 0 && kk < p.maxr && s < p.iters;
         ok[lane][b] = in ? 1 : 0;
-        if (in) stage[lane][b] = p.packed[s * p.Wd + Kl % p.Wd];
+        if (in) stage[lane][b] = xplane[s * p.Wd + Kl % p.Wd];
     }
     __syncthreads();
     // x side: warp = block row, lanes = consecutive steps = consecutive entries of x
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(256) bbb_tri_unpack_kernel(const TriWaveParams
         const int k = p.upper ? p.maxr - 1 - (int)kk : (int)kk;
         const i64 r0 = p.R[K], rK = p.R[K + 1] - r0;
         if (k >= rK) continue;
-        p.x[r0 + k] = poison ? T(NAN) : stage[a][lane];
+        p.x[(i64)blockIdx.z * p.ldb + r0 + k] = poison ? T(NAN) : stage[a][lane];
     }
 }
 
@@ -396,6 +405,7 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
     const int rank = (int)cluster.block_rank();
     const int grp = tid / kTriGroup, lid = tid % kTriGroup;
     const int g = (grp * kTriCtas + rank) * kTriGroup + lid;   // lane in solve order (block row g + kTriLanes*pass)
+    const i64 xq = p.xoff + (i64)(blockIdx.x / kTriCtas) * p.total;   // this cluster's right-hand-side plane
     const int D = p.D, w = p.w, NC = p.nc, mu = p.mu, maxr = p.maxr, iters = p.iters;
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
     const int nd = p.upper ? p.u : p.l;
@@ -443,7 +453,7 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
                 if (k >= rnme[pass * kTriGroups * gw]) continue;
                 const T* src = p.packed + ((i64)st * p.Wd + klm[pass * kTriThreads + tid]);
                 T* cb = coef + (size_t)((pass * PF + (st & (PF - 1))) * NC) * kTriThreads + tid;
-                tri_cp_async(cb, src);
+                tri_cp_async(cb, src + xq);
                 if (!p.unit) tri_cp_async(cb + kTriThreads, src + p.total);
                 for (int c = 2; c < NC; ++c) tri_cp_async(cb + (size_t)c * kTriThreads, src + (i64)c * p.total);
             }
@@ -477,7 +487,7 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
                 acc = fma(-cd[t * kTriThreads], mine[((km - ii0 - t) & (D - 1)) * kTriThreads], acc);
             const T xk = p.unit ? acc : acc / cb[kTriThreads];
             mine[(k & (D - 1)) * kTriThreads] = xk;
-            p.packed[(i64)s * p.Wd + klm[pass * kTriThreads + tid]] = xk;
+            p.packed[xq + (i64)s * p.Wd + klm[pass * kTriThreads + tid]] = xk;
         }
         if (p.relaxed) {
             // Step boundary without the cluster-scope release: that fence (MEMBAR.ALL.GPU + ERRBAR in SASS) also
@@ -544,6 +554,8 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
     const int delta = p.upper ? p.lam + 1 : p.mu + 1;
     const int ii0 = p.upper ? 0 : p.mu + 1;
     const i64 tot = p.total, Wd = p.Wd;
+    const int rhs = blockIdx.x / kTriCtas;                    // this cluster's right-hand side
+    const i64 xq = p.xoff + (i64)rhs * tot;
     T* ring = reinterpret_cast<T*>(tri_ring_smem);            // [D][kTriThreads]
     T* coef = ring + (size_t)p.D * kTriThreads;               // [PF][NC][kTriThreads]
     T* halo = coef + (size_t)PF * NC * kTriThreads;           // [kTriGroups][ND][D]: rings of the previous group's last ND lanes
@@ -616,7 +628,7 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
     auto issue = [&](int st, int krs, const T* sp) {
         if ((unsigned)krs < (unsigned)rK) {
             T* cb = cmine + (size_t)((st & (PF - 1)) * NC) * kTriThreads;
-            tri_cp_async(cb, sp);
+            tri_cp_async(cb, sp + xq);
             if (!unit) tri_cp_async(cb + kTriThreads, sp + tot);
 #pragma unroll
             for (int c = 2; c < NC; ++c) tri_cp_async(cb + c * kTriThreads, sp + c * tot);
@@ -687,36 +699,42 @@ __global__ void __cluster_dims__(kTriCtas, 1, 1) __launch_bounds__(kTriThreads) 
         // only the shared-memory ring has to be ordered across the step boundary (see the generic kernel)
         asm volatile("fence.acq_rel.cta;" ::: "memory");
         asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-        if (active) *src = xk;
+        if (active) src[xq] = xk;
         ++kr;
 #pragma unroll
         for (int q = 0; q < ND; ++q) ++krP[q];
         src += Wd;
     }
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (failed) *p.status = 1;
+    if (failed) p.status[rhs] = 1;
     cluster.sync();  // nothing may leave while a neighbour could still read its ring
 }
 
 template <typename T, int PF, int ND, int W, int NDIAG>
-cudaError_t launch_lean(const TriWaveParams<T>& p, size_t smem, cudaStream_t stream) {
+cudaError_t launch_lean(const TriWaveParams<T>& p, size_t smem, cudaStream_t stream, int nq) {
     cudaError_t e = cudaFuncSetAttribute(bbb_trisolve_lean_kernel<T, PF, ND, W, NDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bbb_trisolve_lean_kernel<T, PF, ND, W, NDIAG><<<kTriCtas, kTriThreads, smem, stream>>>(p);
+    bbb_trisolve_lean_kernel<T, PF, ND, W, NDIAG><<<kTriCtas * nq, kTriThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <typename T, int PF>
-cudaError_t launch_wave(const TriWaveParams<T>& p, size_t smem, cudaStream_t stream) {
+cudaError_t launch_wave(const TriWaveParams<T>& p, size_t smem, cudaStream_t stream, int nq) {
     cudaError_t e = cudaFuncSetAttribute(bbb_trisolve_wave_kernel<T, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bbb_trisolve_wave_kernel<T, PF><<<kTriCtas, kTriThreads, smem, stream>>>(p);
+    bbb_trisolve_wave_kernel<T, PF><<<kTriCtas * nq, kTriThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-// Returns BBM_OK when the solve was enqueued, 1 when this variant does not apply (caller falls back).
+// mode 0: pack the matrix planes into the handle's workspace, then solve (the one-call path)
+// mode 1: only pack the matrix planes into a buffer of the caller's (*ext, allocated here): bbm_bbb_trsv_prepare_*
+// mode 2: solve with the matrix planes already in *ext: bbm_bbb_trsv_solve_*  (a Gauss-Seidel sweep re-uses them: the matrix
+//         does not change between sweeps, and packing it is 1.2 GB written + read per solve at cfg2's size)
+// Right-hand sides are packed, solved and unpacked in batches of up to "tri.rhs_batch" (default 16): one 8-CTA cluster
+// each, concurrently on different SMs.  Returns BBM_OK when done, 1 when this variant does not apply (caller falls back).
 template <typename T>
-int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams<T>& sp, T* d_B, i64 ldb, i64 nrhs) {
+int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams<T>& sp, T* d_B, i64 ldb, i64 nrhs, int mode = 0,
+                      void** ext = nullptr, size_t* ext_bytes = nullptr) {
     const int upper = sp.upper;
     const i64 delta = upper ? v.lam + 1 : v.mu + 1;
     const i64 nd = upper ? v.u : v.l;
@@ -737,13 +755,44 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     Wd = (Wd + 15) / 16 * 16;
     p.Wd = Wd;
     p.total = (i64)p.iters * Wd;
-    const size_t need = ((size_t)p.total * p.nc * sizeof(T) + 255) / 256 * 256;
-    if (need > (size_t)bbm_opt(h, "tri.ws_max_mb", 16384) * 1048576) return 1;
-    if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, need + 256) != BBM_OK) return 1;
-    p.packed = static_cast<T*>(h->ws_w);
-    p.status = reinterpret_cast<int*>(static_cast<char*>(h->ws_w) + need);
+    const size_t plane = ((size_t)p.total * sizeof(T) + 255) / 256 * 256;
+    const size_t need = plane * (size_t)(p.nc - 1);                  // matrix planes 1 .. nc-1 (plane 0 is the right-hand side's)
+    const int batch = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(nrhs, bbm_opt(h, "tri.rhs_batch", 16)), 64));
+    const size_t xneed = 256 + plane * (size_t)batch;                // status words + right-hand-side planes
+    if (need + xneed > (size_t)bbm_opt(h, "tri.ws_max_mb", 16384) * 1048576) return 1;
+    T* mat = nullptr;
+    char* xws = nullptr;
+    if (mode == 1) {
+        cudaError_t e = cudaMalloc(ext, need + 256);
+        if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(%zu) for the wave-ordered matrix planes: %s", need, cudaGetErrorString(e)); }
+        *ext_bytes = need;
+        mat = static_cast<T*>(*ext);
+    } else if (mode == 2) {
+        if (!ext || !*ext || *ext_bytes != need) return bbm_fail(h, BBM_ERR_ARG, "prepared plan does not match this solve");
+        if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, xneed + 256) != BBM_OK) return 1;
+        mat = static_cast<T*>(*ext);
+        xws = static_cast<char*>(h->ws_w);
+    } else {
+        if (bbm_ws_reserve(h, &h->ws_w, &h->ws_w_bytes, need + xneed + 256) != BBM_OK) return 1;
+        mat = static_cast<T*>(h->ws_w);
+        xws = static_cast<char*>(h->ws_w) + need;
+    }
+    p.packed = mat - plane / sizeof(T);          // plane c of the matrix is packed + c*total', c >= 1 (plane 0 is never addressed)
+    p.total = (i64)(plane / sizeof(T));          // plane stride in elements (rounded to 256 bytes)
     p.push = bbm_opt(h, "tri.push", 1) != 0 ? 1 : 0;
-    BBM_CUDA(h, cudaMemsetAsync(p.status, 0, sizeof(int), h->stream));
+    p.ldb = ldb;
+    // transposing tiles of 32 block rows x 32 steps; a block-row tile is active for maxr + 31*delta steps
+    const dim3 grid((unsigned)((p.maxr + 31 * delta + 31) / 32), (unsigned)((p.N + 31) / 32));
+    if (mode != 2) {
+        p.x = nullptr; p.what = 2; p.xoff = 0; p.status = nullptr;
+        bbb_tri_pack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_tri_pack_kernel launch: %s", cudaGetErrorString(e));
+        h->launches += 1;
+        if (mode == 1) return BBM_OK;
+    }
+    p.status = reinterpret_cast<int*>(xws);
+    p.xoff = (reinterpret_cast<T*>(xws + 256) - p.packed);
     const size_t smem = fixed + (size_t)p.passes * pf * kTriThreads * p.nc * sizeof(T);
     // lean instantiations: one pass, the two common shapes (l or u = 1 with 3 sub-block bands, 2 with 5)
     int lean = 0;
@@ -753,19 +802,19 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
         if (nd == 1 && p.w == 3 && ndiag == 1) lean = 13;
         if (nd == 2 && p.w == 5 && ndiag == 2) lean = 25;
     }
-    // transposing tiles of 32 block rows x 32 steps; a block-row tile is active for maxr + 31*delta steps
-    const dim3 grid((unsigned)((p.maxr + 31 * delta + 31) / 32), (unsigned)((p.N + 31) / 32));
-    for (i64 q = 0; q < nrhs; ++q) {
-        p.x = d_B + q * ldb;
-        p.what = q == 0 ? 3 : 1;
-        bbb_tri_pack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
+    for (i64 q0 = 0; q0 < nrhs; q0 += batch) {
+        const int nq = (int)std::min<i64>(batch, nrhs - q0);
+        p.x = d_B + q0 * ldb;
+        p.what = 1;
+        BBM_CUDA(h, cudaMemsetAsync(p.status, 0, sizeof(int) * 64, h->stream));
+        bbb_tri_pack_kernel<T><<<dim3(grid.x, grid.y, (unsigned)nq), 256, 0, h->stream>>>(p);
         cudaError_t e;
         const size_t lsmem = (size_t)kTriThreads * (p.D + 4 * p.nc) * sizeof(T) + (size_t)kTriGroups * nd * (p.D * sizeof(T) + 2 * sizeof(uint64_t));
-        if (lean == 13) e = launch_lean<T, 4, 1, 3, 1>(p, lsmem, h->stream);
-        else if (lean == 25) e = launch_lean<T, 4, 2, 5, 2>(p, lsmem, h->stream);
-        else e = pf == 8 ? launch_wave<T, 8>(p, smem, h->stream) : pf == 4 ? launch_wave<T, 4>(p, smem, h->stream) : launch_wave<T, 2>(p, smem, h->stream);
+        if (lean == 13) e = launch_lean<T, 4, 1, 3, 1>(p, lsmem, h->stream, nq);
+        else if (lean == 25) e = launch_lean<T, 4, 2, 5, 2>(p, lsmem, h->stream, nq);
+        else e = pf == 8 ? launch_wave<T, 8>(p, smem, h->stream, nq) : pf == 4 ? launch_wave<T, 4>(p, smem, h->stream, nq) : launch_wave<T, 2>(p, smem, h->stream, nq);
         if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_trisolve_wave_kernel launch: %s", cudaGetErrorString(e));
-        bbb_tri_unpack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
+        bbb_tri_unpack_kernel<T><<<dim3(grid.x, grid.y, (unsigned)nq), 256, 0, h->stream>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_tri_unpack_kernel launch: %s", cudaGetErrorString(e));
         h->launches += 3;
@@ -774,7 +823,8 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
 }
 
 template <typename T>
-int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs) {
+int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs, int mode = 0,
+                      void** ext = nullptr, size_t* ext_bytes = nullptr) {
     BBM_REQUIRE_HANDLE(h);
     BbbDescView v;
     if (!bbm_bbb_desc_view(d, &v)) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BandedBlockBandedMatrix descriptor");
@@ -786,9 +836,9 @@ int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t un
     for (i64 K = 0; match && K < v.Nr; ++K) match = v.r[K] == v.c[K];
     if (!match) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "triangular solve needs matching square diagonal blocks (the reference falls back to a generic solve)");
     if (nrhs > 0 && ldb < std::max<i64>(1, v.m)) return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: T is %lld x %lld, ldb=%lld", (long long)v.m, (long long)v.m, (long long)ldb);
-    if (v.m == 0 || nrhs == 0) return BBM_OK;
+    if (v.m == 0 || (nrhs == 0 && mode != 1)) return BBM_OK;
     if (v.P == 0 || v.l < 0 || v.u < 0 || v.lam < 0 || v.mu < 0) return bbm_fail(h, BBM_ERR_BAND, "BandError: the diagonal is outside the bands");
-    if (!d_data || !d_B) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if ((mode != 2 && !d_data) || (mode != 1 && !d_B)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
     BBM_CUDA(h, cudaSetDevice(h->device));
     TriSolveParams<T> p{};
     p.data = d_data; p.R = v.dR; p.N = v.Nr; p.maxr = v.maxr;
@@ -809,9 +859,10 @@ int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t un
     const size_t meta = (size_t)p.passes * (kTriThreads + nd) * (sizeof(i64) + sizeof(int)) + 16;
     p.relaxed = bbm_opt(h, "tri.sync", 1) != 0 ? 1 : 0;  // 0 = cluster.sync(), 1 = CTA fence + relaxed arrive (staged / generic wave kernels)
     const int which = (int)bbm_opt(h, "tri.kernel", 0);  // 0 = wave-ordered, 1 = staged, 2 = direct
-    if (which == 0) {
-        const int32_t rc = bbb_trsv_wave<T>(h, v, p, d_B, ldb, nrhs);
+    if (which == 0 || mode != 0) {
+        const int32_t rc = bbb_trsv_wave<T>(h, v, p, d_B, ldb, nrhs, mode, ext, ext_bytes);
         if (rc != 1) return rc;
+        if (mode != 0) return bbm_fail(h, BBM_ERR_UNSUPPORTED, "the wave-ordered solve does not apply to this structure: use bbm_bbb_trsv_* directly");
     }
     int pf = 0;
     const int want_pf = which == 2 ? 0 : (int)bbm_opt(h, "tri.pf", 4);
@@ -845,7 +896,55 @@ int32_t bbb_trsv_impl(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t un
 
 }  // namespace
 
+struct bbm_bbb_tri_plan {
+    uint32_t magic = 0x7B1A50F1u;
+    bbm_handle_t h = nullptr;
+    bbm_bbb_desc_t d = nullptr;
+    int uplo = 'L', unit = 0, elem = 8;
+    void* packed = nullptr;      // wave-ordered matrix planes
+    size_t bytes = 0;
+};
+
+namespace {
+template <typename T>
+int32_t tri_prepare(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const T* d_data, bbm_bbb_tri_plan_t* out) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!out) return bbm_fail(h, BBM_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    bbm_bbb_tri_plan* pl = new (std::nothrow) bbm_bbb_tri_plan();
+    if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
+    pl->h = h; pl->d = d; pl->uplo = uplo; pl->unit = unit ? 1 : 0; pl->elem = (int)sizeof(T);
+    int32_t rc = bbb_trsv_impl<T>(h, d, uplo, unit, d_data, nullptr, 1, 0, 1, &pl->packed, &pl->bytes);
+    if (rc != BBM_OK) { if (pl->packed) cudaFree(pl->packed); delete pl; return rc; }
+    *out = pl;
+    return BBM_OK;
+}
+template <typename T>
+int32_t tri_solve(bbm_bbb_tri_plan_t pl, T* d_B, i64 ldb, i64 nrhs) {
+    if (!pl || pl->magic != 0x7B1A50F1u || !bbm_valid(pl->h)) return BBM_ERR_HANDLE;
+    if (pl->elem != (int)sizeof(T)) return bbm_fail(pl->h, BBM_ERR_ARG, "the plan was prepared for another element type");
+    if (!pl->packed) return BBM_OK;   // empty matrix
+    return bbb_trsv_impl<T>(pl->h, pl->d, pl->uplo, pl->unit, nullptr, d_B, ldb, nrhs, 2, &pl->packed, &pl->bytes);
+}
+}  // namespace
+
 extern "C" {
+int32_t bbm_bbb_trsv_prepare_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const double* d_data, bbm_bbb_tri_plan_t* out) {
+    return tri_prepare<double>(h, d, uplo, unit, d_data, out);
+}
+int32_t bbm_bbb_trsv_prepare_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const float* d_data, bbm_bbb_tri_plan_t* out) {
+    return tri_prepare<float>(h, d, uplo, unit, d_data, out);
+}
+int32_t bbm_bbb_trsv_solve_f64(bbm_bbb_tri_plan_t p, double* d_B, int64_t ldb, int64_t nrhs) { return tri_solve<double>(p, d_B, ldb, nrhs); }
+int32_t bbm_bbb_trsv_solve_f32(bbm_bbb_tri_plan_t p, float* d_B, int64_t ldb, int64_t nrhs) { return tri_solve<float>(p, d_B, ldb, nrhs); }
+int32_t bbm_bbb_tri_plan_destroy(bbm_bbb_tri_plan_t p) {
+    if (!p || p->magic != 0x7B1A50F1u) return BBM_ERR_HANDLE;
+    if (bbm_valid(p->h)) cudaSetDevice(p->h->device);
+    if (p->packed) cudaFree(p->packed);
+    p->magic = 0;
+    delete p;
+    return BBM_OK;
+}
 int32_t bbm_bbb_trsv_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const double* d_data, double* d_B, int64_t ldb,
                          int64_t nrhs) {
     return bbb_trsv_impl<double>(h, d, uplo, unit, d_data, d_B, ldb, nrhs);

@@ -363,6 +363,51 @@ def ldiv_(T, B):
     return B
 
 
+class PreparedTriangular:
+    """``ldiv!`` with one triangular BandedBlockBandedMatrix many times (the Gauss-Seidel loop of
+    examples/finitedifference_2d.jl:17-47): ``bbm_bbb_trsv_prepare_*`` gathers the matrix into the solve kernel's
+    wave-ordered planes once, ``ldiv_`` (``bbm_bbb_trsv_solve_*``) then only moves right-hand sides.  Valid while the
+    matrix storage is unchanged."""
+
+    def __init__(self, T):
+        if not isinstance(T, _Triangular) or not isinstance(T.parent, BandedBlockBandedMatrix):
+            raise TypeError("prepare_ldiv takes Upper/LowerTriangular wrappers of a BandedBlockBandedMatrix")
+        A = T.parent
+        self.T, self.h = T, _require_device(A)
+        dt = A.dtype
+        if dt not in _SUF:
+            raise TypeError("device path takes Float32/Float64 only")
+        self.suf = _SUF[dt][0]
+        p = C.c_void_p()
+        fn = getattr(self.h._lib, f"bbm_bbb_trsv_prepare_{self.suf}")
+        L.check(fn(self.h.h, A.descriptor(self.h), ord(T.uplo), 1 if T.unit else 0, C.c_void_p(A.data.ptr), C.byref(p)), self.h.h, "prepare")
+        self.plan = p
+
+    def ldiv_(self, B):
+        A = self.T.parent
+        br, bc = _vec_dims(B, "B")
+        if not isinstance(B, DeviceArray) or br != A.shape[0] or np.dtype(B.dtype) != A.dtype:
+            raise L.DimensionMismatch(f"T is {A.shape}, B is {getattr(B, 'shape', None)}")
+        fn = getattr(self.h._lib, f"bbm_bbb_trsv_solve_{self.suf}")
+        L.check(fn(self.plan, C.c_void_p(B.ptr), _ld(B), bc), self.h.h, "ldiv!")
+        return B
+
+    def close(self):
+        if getattr(self, "plan", None) and self.h.h:
+            self.h._lib.bbm_bbb_tri_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prepare_ldiv(T):
+    return PreparedTriangular(T)
+
+
 def ldiv(T, B):
     """``T \\ B``: solves into a copy of B."""
     h = _require_device(T.factors if isinstance(T, BlockBandedQR) else T.parent)

@@ -187,11 +187,23 @@ int32_t bbm_bbb_matmul_f32(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, b
  * banded tbsv per diagonal block and a gbmv per off-diagonal block).  One thread-block cluster runs a systolic
  * level schedule with the recent solution values in (distributed) shared memory.  Needs matching square
  * diagonal blocks and non-negative bandwidths; BBM_ERR_UNSUPPORTED beyond about 24k block rows x small bands.
- * d_B: m x nrhs, ldb >= m; right-hand sides are solved one after the other.                            */
+ * d_B: m x nrhs, ldb >= m; right-hand sides are solved concurrently, one thread-block cluster each (batches of 16).  */
 int32_t bbm_bbb_trsv_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const double* d_data,
                          double* d_B, int64_t ldb, int64_t nrhs);
 int32_t bbm_bbb_trsv_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const float* d_data,
                          float* d_B, int64_t ldb, int64_t nrhs);
+
+/* The same solve split in two for repeated use with ONE matrix -- the Gauss-Seidel loop of examples/finitedifference_2d.jl:17-47
+ * solves with the same LowerTriangular(A) in every sweep: prepare gathers the matrix entries into the wave-ordered planes the
+ * solve kernel streams (a plan-owned buffer of about (1 + (l or u)(lam+mu+1) + (lam or mu)) x 1.5 x m entries), solve only moves
+ * the right-hand sides.  Several right-hand sides run concurrently, one thread-block cluster each.  The plan stays valid while
+ * d_data is unchanged; BBM_ERR_UNSUPPORTED if the wave-ordered kernels do not apply (use bbm_bbb_trsv_* then).             */
+typedef struct bbm_bbb_tri_plan* bbm_bbb_tri_plan_t;
+int32_t bbm_bbb_trsv_prepare_f64(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const double* d_data, bbm_bbb_tri_plan_t* out);
+int32_t bbm_bbb_trsv_prepare_f32(bbm_handle_t h, bbm_bbb_desc_t d, int32_t uplo, int32_t unit, const float* d_data, bbm_bbb_tri_plan_t* out);
+int32_t bbm_bbb_trsv_solve_f64(bbm_bbb_tri_plan_t p, double* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_bbb_trsv_solve_f32(bbm_bbb_tri_plan_t p, float* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_bbb_tri_plan_destroy(bbm_bbb_tri_plan_t p);
 
 /* sparse(A) (ext/BlockBandedMatricesSparseArraysExt.jl:10-27) as CSC arrays built on the device: every in-band entry
  * of every in-band block, explicit zeros included, rows ascending within a column.  Two calls, like any CSC build:

@@ -71,7 +71,7 @@ def main():
                 for beta in (0.0, 0.5):
                     x = rng.standard_normal(sum(cols))
                     xo = np.ascontiguousarray(x[c0 + o:c0 + o + lay["n_own"]])
-                    yo = np.ascontiguousarray(y0[lay["row_offset"]:lay["row_offset"] + lay["m_own"]])
+                    yo = y0[lay["row_offset"]:lay["row_offset"] + lay["m_own"]].copy()
                     dist.barrier()
                     A.mul_host_(yo, xo, 1.5, beta)
                     ref = y0.copy()
@@ -109,7 +109,7 @@ def main():
             o, c0 = lay["own_offset"], lay["col_offset"]
             xl[o:o + lay["n_own"], :] = X[c0 + o:c0 + o + lay["n_own"], :]
             dxs = h.to_device(xl)
-            y0 = rng.standard_normal((mo, nrhs))
+            y0 = np.random.default_rng(5000 + rank).standard_normal((mo, nrhs))   # (rank-local sizes: must not advance the shared generator)
             dys = h.to_device(np.asfortranarray(y0))
             for epoch in range(2):
                 dist.barrier()

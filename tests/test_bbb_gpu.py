@@ -361,6 +361,34 @@ def test_bbb_triangular_ldiv_more_block_rows_than_lanes(handle, uplo, kernel):
     assert relerr(got, ref) <= tol(np.float64, 10)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("uplo,unit", [("U", False), ("L", False), ("L", True)])
+def test_bbb_triangular_prepared_plan_and_many_rhs(handle, uplo, unit, dtype):
+    """bbm_bbb_trsv_prepare_* / _solve_*: the matrix planes are gathered once and re-used by every later solve (the
+    Gauss-Seidel loop); 20 right-hand sides = two batches of concurrently running clusters.  Bit-equal to the one-call
+    solve, within tolerance of the oracle's substitution."""
+    for rows, lu, lm in [([40] * 9, (2, 1), (2, 3)), ([300, 17, 64], (1, 1), (1, 1)), ([5, 3] * 200, (2, 2), (2, 2)), ([64] * 40, (1, 1), (1, 1))]:
+        rng = np.random.default_rng(47)
+        data = _well_conditioned_tri(rng, rows, lu, lm, dtype)
+        m = sum(rows)
+        Ad = B.BandedBlockBandedMatrix(np.nan_to_num(data), rows, rows, lu, lm).to_device(handle)
+        T = {"U": B.UpperTriangular, "L": (B.UnitLowerTriangular if unit else B.LowerTriangular)}[uplo](Ad)
+        plan = B.prepare_ldiv(T)
+        nnz = F.bbb_nnz_per_row_max(*lu, *lm) + 1
+        for nrhs in (1, 20):
+            Bm = np.asfortranarray(rng.standard_normal((m, nrhs)).astype(dtype))
+            d1, d2 = handle.to_device(Bm), handle.to_device(Bm)
+            plan.ldiv_(d1)
+            B.ldiv_(T, d2)
+            X1, X2 = d1.to_host(), d2.to_host()
+            assert np.array_equal(X1, X2)
+            for q in (0, nrhs - 1, nrhs // 2):
+                refq = Bm[:, q].copy()
+                O.bbb_trsm(rows, *lu, *lm, uplo, unit, np.nan_to_num(data), refq)
+                assert relerr(X1[:, q], refq) <= tol(dtype, nnz)
+        plan.close()
+
+
 def test_bbb_triangular_ldiv_gauss_seidel_sweep(handle):
     """examples/finitedifference_2d.jl:17-47 flavour: (D+L) \\ b on the 2-D Laplacian, 200 x 200 blocks."""
     n = 200
