@@ -70,6 +70,9 @@ struct bbm_bbb_desc {
         const void* func = nullptr;
     };
     std::vector<WalkPlan> plans;
+    // column tiles (block column, first column, count <= 256) of the staged product kernel with this matrix as C
+    i64* d_mm_items = nullptr;
+    i64 n_mm_items = 0;
     // block-row chunks of the pipelined host-vector product (sub-view descriptors, built on first use)
     struct HostChunk { i64 Ka, Kb, Jl, Jh; bbm_bbb_desc_t sub; };
     std::vector<HostChunk> chunks;
@@ -1420,6 +1423,100 @@ __global__ void __launch_bounds__(256) bbb_matmul_col_fixed_kernel(const BbbMmPa
     }
 }
 
+
+// Staged variant of the fixed-shape column kernel.  The column kernels above read A with a stride of P_A entries across
+// the lanes of a warp (one column each): every load instruction touches 18 cache lines for 32 useful values, and those L1
+// wavefronts -- 25 x more than the data needs -- bound the kernel (0.70 ms = 0.32 of HBM for the 2048^2 Laplacian squared).
+// Here a CTA owns up to 256 consecutive columns j0.. of ONE block column J of C and first copies, fully coalesced, the
+// contiguous column ranges it needs -- its own columns of B, and for each of the NSB block columns N = J-uB.. of A the columns
+// j0-muB .. j0+nj-1+lamB -- into shared memory; the product then reads shared memory with an odd stride of P entries per lane
+// (conflict-free for 8-byte words, one wavefront per instruction for 4-byte ones) and the 256 x P_C result slab is turned
+// through shared memory for a coalesced write-back as before.  HBM traffic = every byte of A, B, C once (+ (wB-1)/256 halo).
+// Same ascending (N, i) summation order per entry as the other kernels: results are bit-identical.
+template <typename T, int NSA, int WA, int NSB, int WB>
+__global__ void __launch_bounds__(256) bbb_matmul_staged_kernel(const BbbMmParams<T> p, const i64* __restrict__ items, i64 nitems) {
+    extern __shared__ __align__(16) unsigned char mmc_smem[];
+    constexpr int PA = NSA * WA, PB = NSB * WB, NS = NSA + NSB - 1, NW = WA + WB - 1, TW = 256 + WB - 1;
+    T* As = reinterpret_cast<T*>(mmc_smem);            // As[sB][(i - ibase) * PA + rho], ibase = j0 - muB
+    T* Bs = As + (size_t)NSB * TW * PA;                // Bs[t * PB + rho]
+    T* acc = reinterpret_cast<T*>(mmc_smem);           // acc[rho * 257 + t]: re-uses the staging area after the product
+    const int tid = threadIdx.x;
+    const int s0 = p.uC - p.uA - p.uB, i0 = p.muC - p.muA - p.muB;   // >= 0 (BandError otherwise)
+    for (i64 it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const i64 J = items[3 * it], j0 = items[3 * it + 1];
+        const int nj = (int)items[3 * it + 2];
+        const i64 col0 = p.CB[J] + j0;
+        const i64 ibase = j0 - p.muB;
+        // 1. stage: B's columns [col0, col0+nj) and, per block column N of A, the columns i in [ibase, ibase + nj + WB - 1)
+        for (int idx = tid; idx < nj * PB; idx += 256) Bs[idx] = p.B[(i64)PB * col0 + idx];
+#pragma unroll
+        for (int sB = 0; sB < NSB; ++sB) {
+            const i64 N = J + sB - p.uB;
+            if (N < 0 || N >= p.NcA) continue;
+            const i64 cN0 = p.CA[N], cN = p.CA[N + 1] - cN0;
+            const i64 ilo = max(ibase, (i64)0), ihi = min(ibase + nj + WB - 1, cN);
+            if (ihi <= ilo) continue;
+            const T* __restrict__ src = p.A + (i64)PA * (cN0 + ilo);
+            T* dst = As + (size_t)sB * TW * PA + (size_t)(ilo - ibase) * PA;
+            const int cnt = (int)(ihi - ilo) * PA;
+            for (int idx = tid; idx < cnt; idx += 256) dst[idx] = src[idx];
+        }
+        __syncthreads();
+        // 2. product: thread t owns column j0 + t
+        T r[NS][NW];
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int b = 0; b < NW; ++b) r[a][b] = T(0);
+        if (tid < nj) {
+            const i64 j = j0 + tid;
+            i64 rK[NS];   // sizes of the block rows K = J - uA - uB + a of A (0 outside the matrix)
+#pragma unroll
+            for (int a = 0; a < NS; ++a) {
+                const i64 K = J - p.uA - p.uB + a;
+                rK[a] = (K >= 0 && K < p.NrA) ? p.RA[K + 1] - p.RA[K] : 0;
+            }
+            const T* bcol = Bs + tid * PB;
+#pragma unroll
+            for (int sB = 0; sB < NSB; ++sB) {
+                const i64 N = J + sB - p.uB;
+                if (N < 0 || N >= p.NcA) continue;
+                const i64 cN = p.CA[N + 1] - p.CA[N];
+#pragma unroll
+                for (int iB = 0; iB < WB; ++iB) {
+                    const i64 i = j - p.muB + iB;
+                    if (i < 0 || i >= cN) continue;
+                    const T b = bcol[sB * WB + iB];
+                    const T* acol = As + (size_t)sB * TW * PA + (size_t)(tid + iB) * PA;   // column i = ibase + tid + iB
+#pragma unroll
+                    for (int sA = 0; sA < NSA; ++sA) {
+#pragma unroll
+                        for (int iA = 0; iA < WA; ++iA) {
+                            const i64 k = i - p.muA + iA;
+                            if (k >= 0 && k < rK[sA + sB]) r[sA + sB][iA + iB] = fma(acol[sA * WA + iA], b, r[sA + sB][iA + iB]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everybody is done with the staged operands: the area becomes the result slab
+        for (int rho = 0; rho < p.PC; ++rho) acc[rho * 257 + tid] = T(0);
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int b = 0; b < NW; ++b) acc[((s0 + a) * p.wC + i0 + b) * 257 + tid] = r[a][b];
+        __syncthreads();
+        T* __restrict__ cslab = p.C + (i64)p.PC * col0;
+        for (i64 idx = tid; idx < (i64)nj * p.PC; idx += 256) {
+            const int t = (int)(idx / p.PC), rho = (int)(idx - (i64)t * p.PC);
+            T v = p.alpha * acc[rho * 257 + t];
+            if (p.beta != T(0)) v = fma(p.beta, cslab[idx], v);
+            cslab[idx] = v;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_bbb_desc_t Cd, T alpha, const T* dA, const T* dB, T beta, T* dC) {
     BBM_REQUIRE_HANDLE(h);
@@ -1447,6 +1544,30 @@ int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_
     if (smem <= std::min<size_t>(h->smem_optin, 200 * 1024) && bbm_opt(h, "bbb.mm_kernel", 0) != 2) {
         const i64 blocks = std::min<i64>((Cd->n + 255) / 256, (i64)h->num_sms * 8);
         const bool fixed33 = bbm_opt(h, "bbb.mm_kernel", 0) == 0 && A->P == 9 && B->P == 9 && p.wA == 3 && p.wB == 3;   // (1,1),(1,1) x (1,1),(1,1) and kin
+        // staged kernel: operands through shared memory; it wants block columns wide enough to fill a 256-column tile
+        const bool staged = fixed33 && bbm_opt(h, "bbb.mm_staged", 1) != 0 && Cd->n >= 64 * Cd->Nc;
+        if (staged) {
+            if (!Cd->d_mm_items) {
+                std::vector<i64> items;
+                for (i64 J = 0; J < Cd->Nc; ++J)
+                    for (i64 j0 = 0; j0 < Cd->c[J]; j0 += 256) { items.push_back(J); items.push_back(j0); items.push_back(std::min<i64>(256, Cd->c[J] - j0)); }
+                Cd->n_mm_items = (i64)items.size() / 3;
+                cudaError_t em = cudaMalloc(&Cd->d_mm_items, std::max<size_t>(8, items.size() * sizeof(i64)));
+                if (em == cudaSuccess && !items.empty()) em = cudaMemcpy(Cd->d_mm_items, items.data(), items.size() * sizeof(i64), cudaMemcpyHostToDevice);
+                if (em != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "column tiles: %s", cudaGetErrorString(em)); }
+            }
+            const size_t stage = sizeof(T) * ((size_t)3 * 258 * 9 + (size_t)256 * 9);
+            const size_t sm = std::max(stage, smem);
+            if (sm <= std::min<size_t>(h->smem_optin, 200 * 1024)) {
+                const unsigned grid = (unsigned)std::min<i64>(Cd->n_mm_items, (i64)h->num_sms * 8);
+                e = cudaFuncSetAttribute(bbb_matmul_staged_kernel<T, 3, 3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                if (e == cudaSuccess) bbb_matmul_staged_kernel<T, 3, 3, 3, 3><<<grid, 256, sm, h->stream>>>(p, Cd->d_mm_items, Cd->n_mm_items);
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_matmul_staged_kernel launch: %s", cudaGetErrorString(e));
+                h->launches += 1;
+                return BBM_OK;
+            }
+        }
         if (fixed33) {
             e = cudaFuncSetAttribute(bbb_matmul_col_fixed_kernel<T, 3, 3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) bbb_matmul_col_fixed_kernel<T, 3, 3, 3, 3><<<(unsigned)blocks, 256, smem, h->stream>>>(p);
@@ -1531,6 +1652,7 @@ int32_t bbm_bbb_desc_destroy(bbm_bbb_desc_t d) {
         if (e) cudaEventDestroy(e);
     if (d->dR) cudaFree(d->dR);
     if (d->dC) cudaFree(d->dC);
+    if (d->d_mm_items) cudaFree(d->d_mm_items);
     d->magic = 0;
     delete d;
     return BBM_OK;

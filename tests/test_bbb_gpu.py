@@ -465,6 +465,8 @@ BBB_MM_CASES = [
     ([7, 3, 12, 5, 9], (2, 1), (1, 2), (0, 2), (2, 0)),
     ([40] * 6, (1, 1), (2, 2), (1, 0), (0, 3)),
     ([3, 0, 4, 2], (1, 1), (1, 1), (1, 1), (1, 1)),                 # zero-size block
+    ([300, 70, 513, 64, 129], (1, 1), (1, 1), (1, 1), (1, 1)),      # wide ragged blocks: the staged (shared-memory) kernel, several tiles per block
+    ([256] * 5, (1, 1), (1, 1), (1, 1), (1, 1)),                    # exactly one full tile per block column
 ]
 
 
@@ -504,6 +506,31 @@ def test_bbb_matmul_matches_oracle(handle, case, dtype, kernel):
             assert relerr(got2[~mask], -0.5 * c0[~mask]) <= tol(dtype, 1)   # _fill_lmul! scales every stored slot
     finally:
         handle.set_option("bbb.mm_kernel", 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_bbb_matmul_staged_kernel_is_bit_equal(handle, dtype):
+    """The staged kernel keeps the ascending (N, i) summation order of the column kernels: identical bits, also into a
+    wider C with beta != 0 and NaN in the unused slots of the operands."""
+    rows = [300, 70, 513, 64, 129, 1000]
+    rng = np.random.default_rng(65)
+    adata = random_bbb(rng, rows, rows, 1, 1, 1, 1, dtype)
+    bdata = random_bbb(rng, rows, rows, 1, 1, 1, 1, dtype)
+    Ad = B.BandedBlockBandedMatrix(adata, rows, rows, (1, 1), (1, 1)).to_device(handle)
+    Bd = B.BandedBlockBandedMatrix(bdata, rows, rows, (1, 1), (1, 1)).to_device(handle)
+    for luC, lmC in (((2, 2), (2, 2)), ((3, 2), (2, 4))):
+        shape = B.BandedBlockBandedMatrix.data_shape(rows, luC, lmC)
+        c0 = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+        out = []
+        for staged in (1, 0):
+            handle.set_option("bbb.mm_staged", staged)
+            Cd = B.BandedBlockBandedMatrix(c0.copy(order="F"), rows, rows, luC, lmC).to_device(handle)
+            B.mul_(Cd, Ad, Bd, 1.5, -0.5)
+            out.append(Cd.data.to_host())
+        handle.set_option("bbb.mm_staged", 1)
+        assert np.array_equal(out[0], out[1], equal_nan=True)
+        mask = F.bbb_valid_mask(rows, rows, *luC, *lmC)
+        assert not np.isnan(out[0][mask]).any()
 
 
 def test_bbb_matmul_errors(handle):
