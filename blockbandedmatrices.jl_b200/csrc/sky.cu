@@ -15,6 +15,7 @@
 #include <new>
 
 #include "bbm_internal.h"
+#include "ptx.cuh"
 
 namespace {
 
@@ -479,6 +480,114 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_ker
     }
 }
 
+
+// Warp-specialised variant for full tiles (every block a multiple of 128 x 128 with inner dimensions a multiple of 32, 16-byte
+// aligned operands -- cfg4): eight DMMA warps consume a 3-stage ring that ONE producer thread fills with 1-D bulk copies
+// (cp.async.bulk, SASS UBLKCP: 32 copies of 1 KB for the A chunk -- a k-column of the tile is contiguous in the column-major
+// panel -- and 128 copies of 256 B for the B chunk), completion counted in bytes on the stage's `full` mbarrier; a warp hands a
+// stage back with one arrive on its `empty` mbarrier.  No thread of the DMMA warps computes a global address, and there is no
+// CTA-wide barrier inside the k loop: warps drift apart by up to a stage instead of meeting twice per chunk.  2-D tensor maps
+// (cp.async.bulk.tensor) would need one descriptor per panel (every panel has its own leading dimension); the padded shared-memory
+// rows the fragments want (LDA = 132, LDB = 36 doubles: bank-conflict-free) are 16-byte multiples, which is all the 1-D copies need.
+template <int BM, int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(288, 1) sky_dgemm_dmma_ws_kernel(const MmParams<double> p) {
+    constexpr int WM = 64, WN = 32, MF = WM / 8, NF = WN / 8;
+    constexpr int LDA = BM + 4, LDB = BK + 4;
+    extern __shared__ __align__(128) unsigned char mm_smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(mm_smem);            // [STAGES]
+    uint64_t* empty = full + STAGES;                                  // [STAGES]
+    double* As = reinterpret_cast<double*>(mm_smem + 128);
+    double* Bs = As + (size_t)STAGES * BK * LDA;
+    const MmTile tile = p.tiles[blockIdx.x];
+    const MmCBlk cb = p.cblks[tile.cblk];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 8); }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int row0 = tile.ti * BM, col0 = tile.tj * BN;
+    int total = 0;
+    for (int s = cb.seg_begin; s < cb.seg_end; ++s) total += (int)(p.segs[s].kc / BK);
+
+    if (warp == 8) {
+        // ---- producer: one thread feeds the ring ----
+        if (lane == 0) {
+            int seg = cb.seg_begin;
+            i64 k0 = 0;
+            constexpr uint32_t kBytes = (uint32_t)((BM * BK + BN * BK) * sizeof(double));
+            for (int c = 0; c < total; ++c) {
+                const int st = c % STAGES;
+                if (c >= STAGES) ptx::mbar_wait(&empty[st], (uint32_t)(((c / STAGES) - 1) & 1));
+                const MmSeg sg = p.segs[seg];
+                double* as = As + (size_t)st * BK * LDA;
+                double* bs = Bs + (size_t)st * BN * LDB;
+                ptx::mbar_arrive_expect_tx(&full[st], kBytes);
+                const double* ag = p.A + sg.astart + row0 + k0 * sg.lda;
+#pragma unroll 4
+                for (int kk = 0; kk < BK; ++kk) ptx::bulk_g2s(as + kk * LDA, ag + (i64)kk * sg.lda, BM * sizeof(double), &full[st]);
+                const double* bg = p.B + sg.bstart + k0 + (i64)col0 * sg.ldb;
+#pragma unroll 4
+                for (int j = 0; j < BN; ++j) ptx::bulk_g2s(bs + j * LDB, bg + (i64)j * sg.ldb, BK * sizeof(double), &full[st]);
+                k0 += BK;
+                if (k0 >= sg.kc) { k0 = 0; ++seg; }
+            }
+        }
+        return;
+    }
+    // ---- consumers: 8 warps (2 x 4), warp tile 64 x 32 ----
+    const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+    const int ar = lane >> 2, ac = lane & 3;
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int c = 0; c < total; ++c) {
+        const int st = c % STAGES;
+        ptx::mbar_wait(&full[st], (uint32_t)((c / STAGES) & 1));
+        const double* as = As + (size_t)st * BK * LDA;
+        const double* bs = Bs + (size_t)st * BN * LDB;
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double af[MF], bf[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) af[i] = as[(k4 + ac) * LDA + wm0 + i * 8 + ar];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) bf[j] = bs[(wn0 + j * 8 + ar) * LDB + k4 + ac];
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[st]);   // this warp is done with the stage
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+        const int row = row0 + wm0 + i * 8 + ar;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int col = col0 + wn0 + j * 8 + 2 * ac + t;
+                double* cp = p.C + cb.cstart + row + (i64)col * cb.ldc;
+                double v = alpha * acc[i][j][t];
+                if (beta != 0.0) v = fma(beta, *cp, v);
+                *cp = v;
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int BK, int STAGES>
+constexpr size_t mm_ws_smem_bytes() {
+    return 128 + (size_t)STAGES * ((size_t)BK * (BM + 4) + (size_t)BN * (BK + 4)) * sizeof(double);
+}
+
 // SIMT tile kernel: Float32 (tcgen05 kind::tf32 would drop 13 mantissa bits, outside the
 // 64*eps tolerance) and a cross-check path for Float64 ("sky.mm_kernel" = 2).
 template <typename T>
@@ -550,6 +659,7 @@ struct bbm_sky_desc::MmPlan {
     int ntiles[2] = {0, 0};
     int ninterior[2] = {0, 0};                // leading tiles whose product segments only use owned block rows of B
     bool aligned = false;
+    bool full128 = false;                     // every C block a multiple of 128 x 128, inner dimensions multiples of 32, 16-byte strides
     double flops = 0;
 };
 
@@ -584,7 +694,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
     std::vector<MmSeg> segs;
     std::vector<MmTile> tiles[2], btiles[2];
     const int tsz[2] = {128, 64};
-    bool aligned = true;
+    bool aligned = true, full128 = true;
     double flops = 0;
     for (i64 J = 0; J < Cd->Nc; ++J) {
         if (Cd->c[J] == 0) continue;
@@ -600,6 +710,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
                 interior = interior && N >= own_lo && N < own_hi;
                 MmSeg sg{sky_start(A, K, N), A->S[N], sky_start(B, N, J), B->S[J], A->c[N]};
                 aligned = aligned && !(sg.astart & 1) && !(sg.lda & 1) && !(sg.bstart & 1) && !(sg.ldb & 1);
+                full128 = full128 && sg.kc % 32 == 0 && cb.rK % 128 == 0 && cb.cJ % 128 == 0;
                 flops += 2.0 * (double)cb.rK * (double)cb.cJ * (double)sg.kc;
                 segs.push_back(sg);
             }
@@ -620,7 +731,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "product plan too large");
     auto* pl = new (std::nothrow) bbm_sky_desc::MmPlan();
     if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
-    pl->aligned = aligned; pl->flops = flops;
+    pl->aligned = aligned; pl->flops = flops; pl->full128 = full128 && aligned;
     pl->ninterior[0] = ninterior[0]; pl->ninterior[1] = ninterior[1];
     int32_t rc = upload(h, cblks, &pl->d_cblks);
     if (rc == BBM_OK) rc = upload(h, segs, &pl->d_segs);
@@ -668,7 +779,13 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
         };
         // k-chunk depth 32 halves the per-chunk barrier/issue bubble of the DMMA pipe (207 KB of smem)
         const bool bk32 = bbm_opt(h, "sky.mm_bk", 32) >= 32 && h->smem_optin >= mm_smem_bytes<128, 128, 32>();
-        if (al && bk32) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 32, true>, mm_smem_bytes<128, 128, 32>());
+        // warp-specialised bulk-copy pipeline for full tiles ("sky.mm_ws" = 0 keeps the cp.async kernel)
+        const bool ws = al && pl->full128 && bbm_opt(h, "sky.mm_ws", 1) != 0 && h->smem_optin >= mm_ws_smem_bytes<128, 128, 32, 3>();
+        if (ws) {
+            constexpr size_t smem = mm_ws_smem_bytes<128, 128, 32, 3>();
+            e = cudaFuncSetAttribute(sky_dgemm_dmma_ws_kernel<128, 128, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { sky_dgemm_dmma_ws_kernel<128, 128, 32, 3><<<nt[0], 288, smem, h->stream>>>(pd); e = cudaGetLastError(); }
+        } else if (al && bk32) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 32, true>, mm_smem_bytes<128, 128, 32>());
         else if (al) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, true>, mm_smem_bytes<128, 128, 16>());
         else go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, false>, mm_smem_bytes<128, 128, 16>());
     } else {

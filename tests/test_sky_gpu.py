@@ -143,6 +143,40 @@ def test_sky_matmul_matches_oracle(handle, case, dtype, kernel):
         handle.set_option("sky.mm_kernel", 0)
 
 
+@pytest.mark.parametrize("ws", [1, 0], ids=["bulk-copy-pipeline", "cp.async"])
+def test_sky_matmul_full_tiles_warp_specialised(handle, ws):
+    """Blocks that are multiples of 128 with 16-byte-aligned panels take the warp-specialised DMMA kernel (one producer thread
+    feeding a bulk-copy ring, "sky.mm_ws"); same oracle, alpha/beta, a wider C and ragged per-column bandwidths."""
+    rows = [128, 256, 384, 128, 256, 128]
+    cases = [((1, 2), (2, 1), None), ((1, 1), (1, 1), (3, 3)), (([1, 0, 2, 1, 0, 1], [0, 1, 1, 2, 1, 0]), ([0, 1, 1, 0, 2, 1], [1, 1, 0, 1, 1, 2]), None)]
+    handle.set_option("sky.mm_ws", ws)
+    try:
+        for (la, ua), (lb, ub), wide in cases:
+            rng = np.random.default_rng(14)
+            adata, bdata = random_sky(rng, rows, rows, la, ua), random_sky(rng, rows, rows, lb, ub)
+            A = B.BlockSkylineMatrix(adata, rows, rows, la, ua)
+            Bm = B.BlockSkylineMatrix(bdata, rows, rows, lb, ub)
+            if wide is None:
+                ol, ou = F.add_bandwidths(A.l, A.u, Bm.l, Bm.u, constant=A.constant_bandwidths and Bm.constant_bandwidths)
+            else:
+                ol, ou = wide
+            n = B.BlockSkylineMatrix.numentries(rows, rows, ol, ou)
+            c0 = rng.standard_normal(n)
+            for alpha, beta in ((1.0, 0.0), (-1.5, 0.75)):
+                cin = c0.copy()
+                if beta == 0:
+                    cin[:] = np.nan
+                Cd = B.BlockSkylineMatrix(handle.to_device(cin), rows, rows, ol, ou)
+                B.mul_(Cd, A.to_device(handle), Bm.to_device(handle), alpha, beta)
+                ref = c0.copy()
+                O.sky_matmul((rows, rows, la, ua), (rows, rows, lb, ub), (rows, rows, ol, ou), alpha, adata, bdata, beta, ref)
+                got = Cd.data.to_host()
+                assert not np.isnan(got).any()
+                assert relerr(got, ref) <= tol(np.float64, 3 * 384)
+    finally:
+        handle.set_option("sky.mm_ws", 1)
+
+
 def test_sky_matmul_into_wider_c_and_band_error(handle):
     """test/test_blockbanded.jl:213-221: mul!(C, A, B) into a preallocated wider-banded C; a C that is
     too narrow is a BandError (src/BlockSkylineMatrix.jl:491)."""
