@@ -104,7 +104,10 @@ int32_t bbm_malloc(bbm_handle_t h, void** d_ptr, size_t bytes) {
     if (!d_ptr) return bbm_fail(h, BBM_ERR_ARG, "null argument");
     *d_ptr = nullptr;
     BBM_CUDA(h, cudaSetDevice(h->device));
-    if (bytes == 0) bytes = 16;  // always hand back a valid, 16-byte-granular allocation
+    // The band-walk kernel moves `data` and `x` with 16-byte-granular bulk copies: it may read up to 15 bytes past the last
+    // element it addresses.  Every bbm_malloc allocation therefore ends with 32 bytes of readable padding of its own (cudaMalloc's
+    // 256-byte granularity already guarantees it today; a sub-allocating pool behind this call would not).
+    bytes = ((bytes + 15) & ~size_t(15)) + 32;
     cudaError_t e = cudaMalloc(d_ptr, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
     return BBM_OK;

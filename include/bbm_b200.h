@@ -29,8 +29,10 @@
  *   - a handle is not thread-safe; distinct handles are independent.  Every call does its own
  *     cudaSetDevice, so calls may come from any host thread / Julia task.
  *   - the band-walk matvec moves `data` and `x` with 16-byte-granular bulk copies: the 16-byte-aligned
- *     windows around the addressed ranges must be readable (true for cudaMalloc / bbm_malloc memory, whose
- *     allocations are padded to at least 256 bytes; bytes outside the addressed range are never used).
+ *     windows around the addressed ranges must be readable, i.e. up to 15 bytes before the first and after the
+ *     last addressed element (bytes outside the addressed range are never used).  bbm_malloc pads every
+ *     allocation by 32 bytes for this; cudaMalloc memory satisfies it through its 256-byte granularity; a buffer
+ *     carved out of a caller's own pool must leave 16 readable bytes on either side of `data` and `x`.
  *   - there is NO CPU fallback: without a usable CUDA device bbm_create fails with BBM_ERR_CUDA.
  */
 #ifndef BBM_B200_H
