@@ -93,7 +93,8 @@ def main():
     Ad = heat_step_matrix_device(B, h, n)
     h.synchronize()
     t_assemble = time.perf_counter() - t0
-    assembled_equal = bool(np.array_equal(Ad.data.to_host(), A.data)) if n <= 2048 else None
+    mask = A.valid_mask() if n <= 1024 else None     # unused storage slots differ (the device add zeroes them)
+    assembled_equal = bool(np.array_equal(Ad.data.to_host()[mask], A.data[mask])) if mask is not None else None
     db = h.to_device(b)
     out = {"example": "examples/finitedifference_2d.jl Gauss-Seidel", "n": n, "unknowns": n * n, "sweeps": args.sweeps,
            "reference_comment_seconds_n1000_20sweeps": 0.4, "device_assembly_seconds": t_assemble,

@@ -783,7 +783,8 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     p.ldb = ldb;
     // transposing tiles of 32 block rows x 32 steps; a block-row tile is active for maxr + 31*delta steps
     const dim3 grid((unsigned)((p.maxr + 31 * delta + 31) / 32), (unsigned)((p.N + 31) / 32));
-    if (mode != 2) {
+    const bool fused_pack = mode == 0 && nrhs == 1;   // one launch packs the matrix planes and the right-hand side together
+    if (mode != 2 && !fused_pack) {
         p.x = nullptr; p.what = 2; p.xoff = 0; p.status = nullptr;
         bbb_tri_pack_kernel<T><<<grid, 256, 0, h->stream>>>(p);
         cudaError_t e = cudaGetLastError();
@@ -805,7 +806,7 @@ int32_t bbb_trsv_wave(bbm_handle_t h, const BbbDescView& v, const TriSolveParams
     for (i64 q0 = 0; q0 < nrhs; q0 += batch) {
         const int nq = (int)std::min<i64>(batch, nrhs - q0);
         p.x = d_B + q0 * ldb;
-        p.what = 1;
+        p.what = fused_pack ? 3 : 1;
         BBM_CUDA(h, cudaMemsetAsync(p.status, 0, sizeof(int) * 64, h->stream));
         bbb_tri_pack_kernel<T><<<dim3(grid.x, grid.y, (unsigned)nq), 256, 0, h->stream>>>(p);
         cudaError_t e;

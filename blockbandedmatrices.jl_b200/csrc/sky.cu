@@ -61,6 +61,8 @@ struct bbm_sky_desc {
         std::vector<i64> sub_ptr;      // prefix of 32-row sub-blocks per diagonal block
         i64* d_sub = nullptr;          // per sub-block: (data offset of its top-left, ld, size)
         i64* d_place = nullptr;        // per sub-block: (offset in the dense inverse block storage, ld, size)
+        i64* d_zero = nullptr;         // rectangles on the zero side of the inverses' triangles: (offset, ld, rows, cols)
+        i64 nzero = 0;
         i64 nsub = 0;
         // GEMM-based solve (Float64, many right-hand sides): explicit inverses of the diagonal blocks
         struct Batch { void* cblks = nullptr; void* segs = nullptr; void* tiles = nullptr; int ntiles = 0; bool aligned = false; };
@@ -75,7 +77,7 @@ struct bbm_sky_desc {
         void* flow_tiles = nullptr;    // FlowTile[flow_ntiles]
         i64 flow_ntiles = 0;
         int* flow_ctr = nullptr;       // 2*Nr completion counters (+ 1 error word), zeroed per call
-        i64 flow_ldb = -1, flow_nrhs = -1, flow_ldx = -1;
+        i64 flow_ldb = -1, flow_nrhs = -1, flow_ldx = -1, flow_bk = 0;
         bool flow_ok = false;
         double* d_cond = nullptr;      // per diagonal block: ||T||_inf, ||inv(T)||_inf (condition guard)
     } tri[2];
@@ -482,9 +484,9 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) sky_dgemm_dmma_ker
 
 
 // Warp-specialised variant for full tiles (every block a multiple of 128 x 128 with inner dimensions a multiple of 32, 16-byte
-// aligned operands -- cfg4): eight DMMA warps consume a 3-stage ring that ONE producer thread fills with 1-D bulk copies
+// aligned operands -- cfg4): eight DMMA warps consume a 3-stage ring that one producer WARP fills with 1-D bulk copies
 // (cp.async.bulk, SASS UBLKCP: 32 copies of 1 KB for the A chunk -- a k-column of the tile is contiguous in the column-major
-// panel -- and 128 copies of 256 B for the B chunk), completion counted in bytes on the stage's `full` mbarrier; a warp hands a
+// panel -- and 128 copies of 256 B for the B chunk, five per lane), completion counted in bytes on the stage's `full` mbarrier; a warp hands a
 // stage back with one arrive on its `empty` mbarrier.  No thread of the DMMA warps computes a global address, and there is no
 // CTA-wide barrier inside the k loop: warps drift apart by up to a stage instead of meeting twice per chunk.  2-D tensor maps
 // (cp.async.bulk.tensor) would need one descriptor per panel (every panel has its own leading dimension); the padded shared-memory
@@ -512,27 +514,26 @@ __global__ void __launch_bounds__(288, 1) sky_dgemm_dmma_ws_kernel(const MmParam
     for (int s = cb.seg_begin; s < cb.seg_end; ++s) total += (int)(p.segs[s].kc / BK);
 
     if (warp == 8) {
-        // ---- producer: one thread feeds the ring ----
-        if (lane == 0) {
-            int seg = cb.seg_begin;
-            i64 k0 = 0;
-            constexpr uint32_t kBytes = (uint32_t)((BM * BK + BN * BK) * sizeof(double));
-            for (int c = 0; c < total; ++c) {
-                const int st = c % STAGES;
-                if (c >= STAGES) ptx::mbar_wait(&empty[st], (uint32_t)(((c / STAGES) - 1) & 1));
-                const MmSeg sg = p.segs[seg];
-                double* as = As + (size_t)st * BK * LDA;
-                double* bs = Bs + (size_t)st * BN * LDB;
-                ptx::mbar_arrive_expect_tx(&full[st], kBytes);
-                const double* ag = p.A + sg.astart + row0 + k0 * sg.lda;
-#pragma unroll 4
-                for (int kk = 0; kk < BK; ++kk) ptx::bulk_g2s(as + kk * LDA, ag + (i64)kk * sg.lda, BM * sizeof(double), &full[st]);
-                const double* bg = p.B + sg.bstart + k0 + (i64)col0 * sg.ldb;
-#pragma unroll 4
-                for (int j = 0; j < BN; ++j) ptx::bulk_g2s(bs + j * LDB, bg + (i64)j * sg.ldb, BK * sizeof(double), &full[st]);
-                k0 += BK;
-                if (k0 >= sg.kc) { k0 = 0; ++seg; }
-            }
+        // ---- producer warp: lane 0 arms the stage's barrier, then all 32 lanes issue their share of the 160 bulk copies
+        // (a single issuing thread was the bottleneck of the first version: 79 ms against 54 ms for the cp.async kernel) ----
+        int seg = cb.seg_begin;
+        i64 k0 = 0;
+        constexpr uint32_t kBytes = (uint32_t)((BM * BK + BN * BK) * sizeof(double));
+        for (int c = 0; c < total; ++c) {
+            const int st = c % STAGES;
+            if (c >= STAGES) ptx::mbar_wait(&empty[st], (uint32_t)(((c / STAGES) - 1) & 1));
+            const MmSeg sg = p.segs[seg];
+            double* as = As + (size_t)st * BK * LDA;
+            double* bs = Bs + (size_t)st * BN * LDB;
+            if (lane == 0) ptx::mbar_arrive_expect_tx(&full[st], kBytes);
+            __syncwarp();
+            const double* ag = p.A + sg.astart + row0 + k0 * sg.lda;
+            for (int kk = lane; kk < BK; kk += 32) ptx::bulk_g2s(as + kk * LDA, ag + (i64)kk * sg.lda, BM * sizeof(double), &full[st]);
+            const double* bg = p.B + sg.bstart + k0 + (i64)col0 * sg.ldb;
+#pragma unroll
+            for (int j = lane; j < BN; j += 32) ptx::bulk_g2s(bs + j * LDB, bg + (i64)j * sg.ldb, BK * sizeof(double), &full[st]);
+            k0 += BK;
+            if (k0 >= sg.kc) { k0 = 0; ++seg; }
         }
         return;
     }
@@ -1087,6 +1088,25 @@ int32_t build_tri_inverse_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
         if (t.d_place) { cudaFree(t.d_place); t.d_place = nullptr; }
         int32_t rcp = upload(h, place, &t.d_place);
         if (rcp != BBM_OK) return rcp;
+        std::vector<i64> zero;
+        for (i64 K = 0; K < N; ++K) {
+            const i64 rK = d->r[K], wl = t.wld[K];
+            const i64 rpad = (rK + 1) & ~i64(1);   // the storage of an odd block has one padding row / column
+            for (i64 j0 = 0; j0 < rpad; j0 += 32) {
+                const i64 nc = std::min<i64>(32, rpad - j0);
+                // upper triangle: rows below the strip's diagonal sub-block; lower triangle: rows above it
+                const i64 i0 = upper ? j0 + nc : 0, nr = upper ? rpad - (j0 + nc) : j0;
+                if (nr > 0) { zero.push_back(t.woff[K] + i0 + j0 * wl); zero.push_back(wl); zero.push_back(nr); zero.push_back(nc); }
+            }
+            if (rpad > rK) {   // the padding row and column themselves (read by 2-element vector loads at the edge)
+                zero.push_back(t.woff[K] + rK); zero.push_back(wl); zero.push_back(1); zero.push_back(rpad);
+                zero.push_back(t.woff[K] + rK * wl); zero.push_back(wl); zero.push_back(rpad); zero.push_back(1);
+            }
+        }
+        if (t.d_zero) { cudaFree(t.d_zero); t.d_zero = nullptr; }
+        t.nzero = (i64)zero.size() / 4;
+        rcp = upload(h, zero, &t.d_zero);
+        if (rcp != BBM_OK) return rcp;
     }
     for (auto& b : t.inv_levels) free_batch(b);
     t.inv_levels.clear();
@@ -1128,6 +1148,20 @@ __global__ void __launch_bounds__(256) sky_tri_scatter_kernel(const double* __re
     for (int idx = threadIdx.x; idx < 1024; idx += 256) {
         const int i = idx & 31, j = idx >> 5;
         if (i < nb && j < nb) W[dst + i + (i64)j * ld] = W32[sb * 1024 + idx];
+    }
+}
+
+// Zero the zero side of the triangle of every inverse block (one rectangle per 32-column strip): the doubling levels and the
+// chain's products read the inverses as dense operands, and every other entry of W is written by the scatter above or by a
+// doubling level -- half the bytes of the memset of all of W that this replaces.
+__global__ void __launch_bounds__(256) sky_tri_zero_kernel(const i64* __restrict__ zt, i64 nz, double* __restrict__ W) {
+    const i64 z = blockIdx.x;
+    if (z >= nz) return;
+    const i64 dst = zt[4 * z], ld = zt[4 * z + 1];
+    const int nr = (int)zt[4 * z + 2], nc = (int)zt[4 * z + 3];
+    for (int idx = threadIdx.x; idx < nr * nc; idx += 256) {
+        const int i = idx % nr, j = idx / nr;
+        W[dst + i + (i64)j * ld] = 0.0;
     }
 }
 
@@ -1194,7 +1228,10 @@ int32_t sky_trsm_gemm(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
     double* X = static_cast<double*>(h->ws_y);
     double* W = static_cast<double*>(h->ws_z);
     double* Tw = static_cast<double*>(h->ws_w);
-    BBM_CUDA(h, cudaMemsetAsync(W, 0, (size_t)t.wtotal * sizeof(double), h->stream));
+    if (t.nzero > 0) {
+        sky_tri_zero_kernel<<<(unsigned)t.nzero, 256, 0, h->stream>>>(t.d_zero, t.nzero, W);
+        h->launches += 1;
+    }
     BBM_CUDA(h, cudaMemsetAsync(X, 0, (size_t)ldx * nrhs * sizeof(double), h->stream));
     // level 0: 32x32 inverses by substitution, scattered onto the diagonals of the dense inverse blocks
     sky_tri_invdiag_kernel<double><<<(unsigned)((t.nsub + 3) / 4), 128, 0, h->stream>>>(d_data, t.d_sub, t.nsub, upper, unit ? 1 : 0, W32);
@@ -1315,19 +1352,24 @@ struct FlowTile {
     int32_t wait_ctr, wait_val, sig_ctr, pad;
 };
 
-constexpr int kFlowBM = 64, kFlowBN = 32, kFlowBK = 64;
-constexpr int kFlowLDA = kFlowBM + 4, kFlowLDB = kFlowBK + 4;
-constexpr size_t kFlowSmem = ((size_t)kFlowBK * kFlowLDA + (size_t)kFlowBN * kFlowLDB) * sizeof(double);
+constexpr int kFlowBM = 64, kFlowBN = 32;
+constexpr int kFlowLDA = kFlowBM + 4;
+template <int BK>
+constexpr size_t flow_smem_bytes() { return ((size_t)BK * kFlowLDA + (size_t)kFlowBN * (BK + 4)) * sizeof(double); }
 
-__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+// Polling load: relaxed at gpu scope (served by L2, no L1 invalidation per iteration -- an acquire in the loop costs a CCTL.IVALL
+// every time, 8.5 % of all stall samples in the first version); the acquire fence follows once, after the value has arrived.
+__device__ __forceinline__ int ld_relaxed_gpu_s32(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
+template <int kFlowBK>
 __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __restrict__ tiles, i64 ntiles, const double* __restrict__ data,
                                                             const double* __restrict__ W, double* __restrict__ Bm, double* __restrict__ X,
-                                                            int* __restrict__ ctr, int err_idx) {
+                                                            int* __restrict__ ctr, int err_idx, int sleep_ns) {
+    constexpr int kFlowLDB = kFlowBK + 4;
     extern __shared__ __align__(16) unsigned char mm_smem[];
     double* As = reinterpret_cast<double*>(mm_smem);          // As[k][i]
     double* Bs = As + (size_t)kFlowBK * kFlowLDA;              // Bs[j][k]
@@ -1349,11 +1391,14 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
         cp_async_commit();
         // 2. wait until every contribution to the dynamic operand has landed (counter in L2)
         if (tid == 0 && ft.wait_val > 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
-                __nanosleep(32);
-                if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + err_idx, 1); break; }   // never hang the device
+            if (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                const long long t0 = clock64();
+                while (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                    if (sleep_ns > 0) __nanosleep(sleep_ns);
+                    if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + err_idx, 1); break; }   // never hang the device
+                }
             }
+            asm volatile("fence.acquire.gpu;" ::: "memory");
         }
         __syncthreads();
         // 3. the dynamic operand (right-hand-side data written by red.add in L2: .cg loads bypass L1)
@@ -1407,7 +1452,8 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
 
 int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb, i64 ldx, i64 nrhs) {
     bbm_sky_desc::Tri& t = d->tri[upper];
-    if (t.flow_ldb == ldb && t.flow_nrhs == nrhs && t.flow_ldx == ldx && t.flow_ctr) return BBM_OK;
+    const i64 kFlowBK = bbm_opt(h, "trsm.flow_bk", 64) >= 128 ? 128 : 64;   // k-slice per tile: 64 (more tiles, shorter) or 128 (half the atomics)
+    if (t.flow_ldb == ldb && t.flow_nrhs == nrhs && t.flow_ldx == ldx && t.flow_bk == kFlowBK && t.flow_ctr) return BBM_OK;
     const i64 N = d->Nr;
     std::vector<FlowTile> tiles;
     std::vector<int> nA(N, 0), nB(N, 0);
@@ -1466,7 +1512,7 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
     }
     cudaError_t e = cudaMalloc(&t.flow_ctr, sizeof(int) * (size_t)(2 * N + 1));
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
-    t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx;
+    t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx; t.flow_bk = kFlowBK;
     return BBM_OK;
 }
 
@@ -1538,9 +1584,12 @@ int32_t tri_condition(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
 int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const double* d_data, const double* W, double* d_B, double* X) {
     bbm_sky_desc::Tri& t = d->tri[upper];
     const i64 N = d->Nr;
-    cudaError_t e = cudaFuncSetAttribute(sky_trsm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
+    const bool bk128 = t.flow_bk == 128;
+    const void* func = bk128 ? reinterpret_cast<const void*>(sky_trsm_flow_kernel<128>) : reinterpret_cast<const void*>(sky_trsm_flow_kernel<64>);
+    const size_t smem = bk128 ? flow_smem_bytes<128>() : flow_smem_bytes<64>();
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sky_trsm_flow_kernel, 128, kFlowSmem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, 128, smem);
     if (e != cudaSuccess || occ < 1) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "data-flow solve: occupancy query failed"); }
     const i64 cap = bbm_opt(h, "trsm.flow_ctas_per_sm", 0);
     if (cap > 0) occ = (int)std::min<i64>(occ, cap);
@@ -1550,9 +1599,10 @@ int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const doub
     i64 ntiles = t.flow_ntiles;
     int* ctr = t.flow_ctr;
     int err_idx = (int)(2 * N);
-    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&d_data, (void*)&W, (void*)&d_B, (void*)&X, (void*)&ctr, (void*)&err_idx};
+    int sleep_ns = (int)std::max<i64>(0, bbm_opt(h, "trsm.flow_sleep_ns", 32));
+    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&d_data, (void*)&W, (void*)&d_B, (void*)&X, (void*)&ctr, (void*)&err_idx, (void*)&sleep_ns};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident (the tiles wait for one another)
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(sky_trsm_flow_kernel), dim3((unsigned)grid), dim3(128), args, kFlowSmem, h->stream);
+    e = cudaLaunchCooperativeKernel(func, dim3((unsigned)grid), dim3(128), args, smem, h->stream);
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "sky_trsm_flow_kernel launch: %s", cudaGetErrorString(e)); }
     h->launches += 1;
     return BBM_OK;
@@ -2176,7 +2226,7 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     int32_t rc = build_tri(h, d, upper);
     if (rc != BBM_OK) return rc;
     bbm_sky_desc::Tri& t = d->tri[upper];
-    if (sizeof(T) == 8 && nrhs >= 16 && bbm_opt(h, "trsm.kernel", 0) == 0) {
+    if (sizeof(T) == 8 && nrhs >= 16 && (bbm_opt(h, "trsm.kernel", 0) == 0 || bbm_opt(h, "trsm.kernel", 0) == 3)) {
         // the GEMM path stores an explicit inverse (and a level temporary) per diagonal block: take it only if
         // that workspace is a modest share of the free device memory, else solve by substitution
         double wbytes = 0;
@@ -2389,6 +2439,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
         if (d->tri[t].d_items) cudaFree(d->tri[t].d_items);
         if (d->tri[t].d_sub) cudaFree(d->tri[t].d_sub);
         if (d->tri[t].d_place) cudaFree(d->tri[t].d_place);
+        if (d->tri[t].d_zero) cudaFree(d->tri[t].d_zero);
         for (auto& b : d->tri[t].inv_levels) free_batch(b);
         free_batch(d->tri[t].stepA);
         free_batch(d->tri[t].stepB);
