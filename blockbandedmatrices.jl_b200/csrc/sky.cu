@@ -65,7 +65,7 @@ struct bbm_sky_desc {
         i64 nzero = 0;
         i64 nsub = 0;
         // GEMM-based solve (Float64, many right-hand sides): explicit inverses of the diagonal blocks
-        struct Batch { void* cblks = nullptr; void* segs = nullptr; void* tiles = nullptr; int ntiles = 0; bool aligned = false; };
+        struct Batch { void* cblks = nullptr; void* segs = nullptr; void* tiles = nullptr; int ntiles = 0; bool aligned = false; int tile = 64; };
         bool inv_built = false;
         std::vector<i64> woff, wld;    // inverse of diagonal block K: W + woff[K], leading dimension wld[K]
         i64 wtotal = 0;
@@ -780,8 +780,9 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
         };
         // k-chunk depth 32 halves the per-chunk barrier/issue bubble of the DMMA pipe (207 KB of smem)
         const bool bk32 = bbm_opt(h, "sky.mm_bk", 32) >= 32 && h->smem_optin >= mm_smem_bytes<128, 128, 32>();
-        // warp-specialised bulk-copy pipeline for full tiles ("sky.mm_ws" = 0 keeps the cp.async kernel)
-        const bool ws = al && pl->full128 && bbm_opt(h, "sky.mm_ws", 1) != 0 && h->smem_optin >= mm_ws_smem_bytes<128, 128, 32, 3>();
+        // warp-specialised bulk-copy pipeline for full tiles: opt-in ("sky.mm_ws" = 1) -- measured SLOWER than the cp.async kernel
+        // on cfg4 (56.8 vs 54.0 ms): 160 bulk copies of 256 B - 1 KB per chunk keep the copy engine busier than the DMMA pipe
+        const bool ws = al && pl->full128 && bbm_opt(h, "sky.mm_ws", 0) != 0 && h->smem_optin >= mm_ws_smem_bytes<128, 128, 32, 3>();
         if (ws) {
             constexpr size_t smem = mm_ws_smem_bytes<128, 128, 32, 3>();
             e = cudaFuncSetAttribute(sky_dgemm_dmma_ws_kernel<128, 128, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -995,7 +996,8 @@ struct MmBatchHost {
     std::vector<MmSeg> segs;
     std::vector<MmTile> tiles;
     bool aligned = true;
-    // one C block of rows x cols at (cstart, ldc) with a single product segment, cut into 64x64 tiles
+    int tile = 64;   // output tile edge: 64 (4-warp kernel, split-k chain links) or 128 (8-warp kernel, the large inversion levels)
+    // one C block of rows x cols at (cstart, ldc) with a single product segment, cut into tile x tile pieces
     void add(i64 cstart, i64 ldc, i64 rows, i64 cols, const MmSeg& sg) {
         if (rows <= 0 || cols <= 0 || sg.kc <= 0) return;
         MmCBlk cb{cstart, ldc, (int32_t)rows, (int32_t)cols, (int32_t)segs.size(), (int32_t)segs.size() + 1};
@@ -1003,8 +1005,25 @@ struct MmBatchHost {
         segs.push_back(sg);
         const int32_t ci = (int32_t)cblks.size();
         cblks.push_back(cb);
-        for (int tj = 0; tj * 64 < cols; ++tj)
-            for (int ti = 0; ti * 64 < rows; ++ti) tiles.push_back(MmTile{ci, ti, tj, 0});
+        for (int tj = 0; tj * tile < cols; ++tj)
+            for (int ti = 0; ti * tile < rows; ++ti) tiles.push_back(MmTile{ci, ti, tj, 0});
+    }
+    // C (rows x cols) = A (rows x kdim) * B (kdim x cols) where one factor is TRIANGULAR (its zero triangle is skipped):
+    // tri = 1: B upper triangular (output columns [c0, c0+nc) need k < c0+nc); 2: B lower triangular (k >= c0);
+    //       3: A upper triangular (output rows [r0, r0+nr) need k >= r0);       4: A lower triangular (k < r0+nr).
+    // Every tile x tile piece of C becomes a block of its own with its own trimmed k range.
+    void add_tri(i64 cstart, i64 ldc, i64 rows, i64 cols, i64 astart, i64 lda, i64 bstart, i64 ldb, i64 kdim, int tri) {
+        for (i64 c0 = 0; c0 < cols; c0 += tile)
+            for (i64 r0 = 0; r0 < rows; r0 += tile) {
+                const i64 nr = std::min<i64>(tile, rows - r0), nc = std::min<i64>(tile, cols - c0);
+                i64 klo = 0, khi = kdim;
+                if (tri == 1) khi = std::min(kdim, c0 + nc);
+                else if (tri == 2) klo = std::min(kdim, c0);
+                else if (tri == 3) klo = std::min(kdim, r0);
+                else if (tri == 4) khi = std::min(kdim, r0 + nr);
+                klo &= ~i64(1);   // keep 16-byte alignment of the operands' k offsets
+                add(cstart + r0 + c0 * ldc, ldc, nr, nc, MmSeg{astart + r0 + klo * lda, lda, bstart + klo + c0 * ldb, ldb, khi - klo});
+            }
     }
 };
 
@@ -1024,6 +1043,7 @@ int32_t upload_batch(bbm_handle_t h, const MmBatchHost& hb, bbm_sky_desc::Tri::B
     out->cblks = c; out->segs = sgs; out->tiles = t;
     out->ntiles = (int)hb.tiles.size();
     out->aligned = hb.aligned;
+    out->tile = hb.tile;
     return rc;
 }
 
@@ -1033,6 +1053,21 @@ int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, i
     if (nt <= 0) return BBM_OK;
     MmParams<double> p{A, Bm, Cm, (const MmCBlk*)b.cblks, (const MmSeg*)b.segs, (const MmTile*)b.tiles + t0, alpha, beta};
     const bool al = b.aligned && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(Bm) % 16 == 0);
+    if (b.tile == 128) {
+        // the large levels of the inversion: the 8-warp 128 x 128 kernels of the block-banded product
+        if (atomic) return bbm_fail(h, BBM_ERR_ARG, "internal: 128-tiles are not split");
+        cudaError_t e2 = cudaSuccess;
+        auto run = [&](auto kern, size_t sm) {
+            e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e2 == cudaSuccess) { kern<<<nt, 256, sm, h->stream>>>(p); e2 = cudaGetLastError(); }
+        };
+        if (al && h->smem_optin >= mm_smem_bytes<128, 128, 32>()) run(sky_dgemm_dmma_kernel<128, 128, 64, 32, 32, true>, mm_smem_bytes<128, 128, 32>());
+        else if (al) run(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, true>, mm_smem_bytes<128, 128, 16>());
+        else run(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, false>, mm_smem_bytes<128, 128, 16>());
+        if (e2 != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "triangular-solve inversion product: %s", cudaGetErrorString(e2));
+        h->launches += 1;
+        return BBM_OK;
+    }
     constexpr size_t smem = mm_smem_bytes<64, 64, 16, 4>();  // 4 stages: a 64-deep k-slice is requested at once
     cudaError_t e = cudaSuccess;
     const char* where = "";
@@ -1112,6 +1147,9 @@ int32_t build_tri_inverse_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
     t.inv_levels.clear();
     for (i64 sz = 32; sz < maxr; sz *= 2) {
         MmBatchHost g1, g2;  // g1: T = offdiag * X22 (upper) / offdiag * X11 (lower);  g2: X12 = -X11 * T / X21 = -X22 * T
+        // the inverses of the sub-blocks are triangular: their zero triangle is skipped tile by tile (37 % of the flops of the
+        // largest level), and the two large levels use 128 x 128 tiles (the 8-warp kernel: 31 instead of 23 TFLOP/s)
+        g1.tile = g2.tile = sz >= 128 ? 128 : 64;
         for (i64 K = 0; K < N; ++K) {
             const i64 rK = d->r[K];
             if (rK <= sz) continue;
@@ -1119,13 +1157,13 @@ int32_t build_tri_inverse_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper) {
             for (i64 base = 0; base + sz < rK; base += 2 * sz) {
                 const i64 s1 = sz, s2 = std::min<i64>(sz, rK - base - sz), mid = base + s1;
                 if (upper) {
-                    // T12 (s1 x s2) = U12 * X22 ;  X12 = -X11 * T12
-                    g1.add(wo + base + mid * wl, wl, s1, s2, MmSeg{ds + base + mid * ld, ld, wo + mid + mid * wl, wl, s2});
-                    g2.add(wo + base + mid * wl, wl, s1, s2, MmSeg{wo + base + base * wl, wl, wo + base + mid * wl, wl, s1});
+                    // T12 (s1 x s2) = U12 * X22 (upper triangular) ;  X12 = -X11 (upper triangular) * T12
+                    g1.add_tri(wo + base + mid * wl, wl, s1, s2, ds + base + mid * ld, ld, wo + mid + mid * wl, wl, s2, 1);
+                    g2.add_tri(wo + base + mid * wl, wl, s1, s2, wo + base + base * wl, wl, wo + base + mid * wl, wl, s1, 3);
                 } else {
-                    // T21 (s2 x s1) = L21 * X11 ;  X21 = -X22 * T21
-                    g1.add(wo + mid + base * wl, wl, s2, s1, MmSeg{ds + mid + base * ld, ld, wo + base + base * wl, wl, s1});
-                    g2.add(wo + mid + base * wl, wl, s2, s1, MmSeg{wo + mid + mid * wl, wl, wo + mid + base * wl, wl, s2});
+                    // T21 (s2 x s1) = L21 * X11 (lower triangular) ;  X21 = -X22 (lower triangular) * T21
+                    g1.add_tri(wo + mid + base * wl, wl, s2, s1, ds + mid + base * ld, ld, wo + base + base * wl, wl, s1, 2);
+                    g2.add_tri(wo + mid + base * wl, wl, s2, s1, wo + mid + mid * wl, wl, wo + mid + base * wl, wl, s2, 4);
                 }
             }
         }
