@@ -1474,38 +1474,38 @@ __global__ void __launch_bounds__(256) bbb_matmul_staged_kernel(const BbbMmParam
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // 2. product: thread t owns column j0 + t
+        // 2. product: thread t owns column j0 + t (32-bit index arithmetic: block sizes are < 2^30)
         T r[NS][NW];
 #pragma unroll
         for (int a = 0; a < NS; ++a)
 #pragma unroll
             for (int b = 0; b < NW; ++b) r[a][b] = T(0);
         if (tid < nj) {
-            const i64 j = j0 + tid;
-            i64 rK[NS];   // sizes of the block rows K = J - uA - uB + a of A (0 outside the matrix)
+            const int j = (int)j0 + tid;
+            int rK[NS];   // sizes of the block rows K = J - uA - uB + a of A (0 outside the matrix)
 #pragma unroll
             for (int a = 0; a < NS; ++a) {
                 const i64 K = J - p.uA - p.uB + a;
-                rK[a] = (K >= 0 && K < p.NrA) ? p.RA[K + 1] - p.RA[K] : 0;
+                rK[a] = (K >= 0 && K < p.NrA) ? (int)(p.RA[K + 1] - p.RA[K]) : 0;
             }
             const T* bcol = Bs + tid * PB;
 #pragma unroll
             for (int sB = 0; sB < NSB; ++sB) {
                 const i64 N = J + sB - p.uB;
                 if (N < 0 || N >= p.NcA) continue;
-                const i64 cN = p.CA[N + 1] - p.CA[N];
+                const int cN = (int)(p.CA[N + 1] - p.CA[N]);
 #pragma unroll
                 for (int iB = 0; iB < WB; ++iB) {
-                    const i64 i = j - p.muB + iB;
-                    if (i < 0 || i >= cN) continue;
+                    const int i = j - p.muB + iB;
+                    if ((unsigned)i >= (unsigned)cN) continue;
                     const T b = bcol[sB * WB + iB];
                     const T* acol = As + (size_t)sB * TW * PA + (size_t)(tid + iB) * PA;   // column i = ibase + tid + iB
 #pragma unroll
                     for (int sA = 0; sA < NSA; ++sA) {
 #pragma unroll
                         for (int iA = 0; iA < WA; ++iA) {
-                            const i64 k = i - p.muA + iA;
-                            if (k >= 0 && k < rK[sA + sB]) r[sA + sB][iA + iB] = fma(acol[sA * WA + iA], b, r[sA + sB][iA + iB]);
+                            const int k = i - p.muA + iA;
+                            if ((unsigned)k < (unsigned)rK[sA + sB]) r[sA + sB][iA + iB] = fma(acol[sA * WA + iA], b, r[sA + sB][iA + iB]);
                         }
                     }
                 }
@@ -1518,12 +1518,17 @@ __global__ void __launch_bounds__(256) bbb_matmul_staged_kernel(const BbbMmParam
 #pragma unroll
             for (int b = 0; b < NW; ++b) acc[((s0 + a) * p.wC + i0 + b) * 257 + tid] = r[a][b];
         __syncthreads();
+        // coalesced write-back of the nj x P_C slab; (t, rho) advance without a division: idx += 256 is t += 256 / P_C,
+        // rho += 256 % P_C with one carry
         T* __restrict__ cslab = p.C + (i64)p.PC * col0;
-        for (i64 idx = tid; idx < (i64)nj * p.PC; idx += 256) {
-            const int t = (int)(idx / p.PC), rho = (int)(idx - (i64)t * p.PC);
+        const int PC = p.PC, dt = 256 / PC, dr = 256 % PC, total = nj * PC;
+        int t = tid / PC, rho = tid % PC;
+        for (int idx = tid; idx < total; idx += 256) {
             T v = p.alpha * acc[rho * 257 + t];
             if (p.beta != T(0)) v = fma(p.beta, cslab[idx], v);
             cslab[idx] = v;
+            t += dt; rho += dr;
+            if (rho >= PC) { rho -= PC; ++t; }
         }
         __syncthreads();
     }
@@ -1573,6 +1578,8 @@ int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_
             if (sm <= std::min<size_t>(h->smem_optin, 200 * 1024)) {
                 const unsigned grid = (unsigned)std::min<i64>(Cd->n_mm_items, (i64)h->num_sms * 8);
                 e = cudaFuncSetAttribute(bbb_matmul_staged_kernel<T, 3, 3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                // three CTAs of 74 KB only fit with the largest shared-memory carve-out (the default left room for two)
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(bbb_matmul_staged_kernel<T, 3, 3, 3, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
                 if (e == cudaSuccess) bbb_matmul_staged_kernel<T, 3, 3, 3, 3><<<grid, 256, sm, h->stream>>>(p, Cd->d_mm_items, Cd->n_mm_items);
                 if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_matmul_staged_kernel launch: %s", cudaGetErrorString(e));

@@ -77,7 +77,7 @@ struct bbm_sky_desc {
         void* flow_tiles = nullptr;    // FlowTile[flow_ntiles]
         i64 flow_ntiles = 0;
         int* flow_ctr = nullptr;       // 2*Nr completion counters (+ 1 error word), zeroed per call
-        i64 flow_ldb = -1, flow_nrhs = -1, flow_ldx = -1, flow_bk = 0;
+        i64 flow_ldb = -1, flow_nrhs = -1, flow_ldx = -1, flow_bk = 0, flow_nctr = 0;
         bool flow_ok = false;
         double* d_cond = nullptr;      // per diagonal block: ||T||_inf, ||inv(T)||_inf (condition guard)
     } tri[2];
@@ -1494,9 +1494,15 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
     if (t.flow_ldb == ldb && t.flow_nrhs == nrhs && t.flow_ldx == ldx && t.flow_bk == kFlowBK && t.flow_ctr) return BBM_OK;
     const i64 N = d->Nr;
     std::vector<FlowTile> tiles;
-    std::vector<int> nA(N, 0), nB(N, 0);
-    bool even = !(ldb & 1) && !(ldx & 1);
-    // pass 1 builds the tiles with the counters' indices, pass 2 fills in the target values
+    // Completion counters per 64-row tile of every block: cB[K][c] counts the update tiles that have landed in rows
+    // [64c, 64c+64) of B_K, cX[K][i] the partial products of rows [64i, 64i+64) of X_K.  A tile waits only for the one
+    // 64-row slice it reads (its k-slice), not for the whole block: no tile waits for the slowest of several hundred.
+    std::vector<i64> toff(N + 1, 0);
+    for (i64 K = 0; K < N; ++K) toff[K + 1] = toff[K] + (d->r[K] + kFlowBM - 1) / kFlowBM;
+    const i64 nctr = toff[N];
+    if (2 * nctr + 1 >= (i64)INT32_MAX) { t.flow_ok = false; t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx; t.flow_bk = kFlowBK; return BBM_OK; }
+    std::vector<int> nA(nctr, 0), nB(nctr, 0);   // targets: cX / cB
+    bool even = !(ldb & 1) && !(ldx & 1) && kFlowBK == kFlowBM;   // (k-slices must coincide with the 64-row tiles)
     for (i64 s = 0; s < N; ++s) {
         const i64 K = upper ? N - 1 - s : s;
         const i64 rK = d->r[K];
@@ -1509,10 +1515,11 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
                 const i64 kc = std::min<i64>(kFlowBK, khi - k0);
                 for (i64 j0 = 0; j0 < nrhs; j0 += kFlowBN) {
                     FlowTile ft{wo + i0 + k0 * wl, wl, d->R[K] + k0 + j0 * ldb, ldb, d->R[K] + i0 + j0 * ldx, ldx,
-                                (int32_t)nr, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kc, 0, (int32_t)K, 0, (int32_t)(N + K), 0};
+                                (int32_t)nr, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kc, 0,
+                                (int32_t)(toff[K] + k0 / kFlowBM), 0, (int32_t)(nctr + toff[K] + i0 / kFlowBM), 0};
                     even = even && !(ft.astart & 1) && !(ft.lda & 1) && !(ft.bstart & 1);
                     tiles.push_back(ft);
-                    ++nA[K];
+                    ++nA[toff[K] + i0 / kFlowBM];
                 }
             }
         }
@@ -1528,16 +1535,17 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
                     const i64 kc = std::min<i64>(kFlowBK, rK - k0);
                     for (i64 j0 = 0; j0 < nrhs; j0 += kFlowBN) {
                         FlowTile ft{bs + i0 + k0 * d->S[K], d->S[K], d->R[K] + k0 + j0 * ldx, ldx, d->R[Kr] + i0 + j0 * ldb, ldb,
-                                    (int32_t)nr, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kc, 1, (int32_t)(N + K), 0, (int32_t)Kr, 0};
+                                    (int32_t)nr, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kc, 1,
+                                    (int32_t)(nctr + toff[K] + k0 / kFlowBM), 0, (int32_t)(toff[Kr] + i0 / kFlowBM), 0};
                         even = even && !(ft.astart & 1) && !(ft.lda & 1) && !(ft.bstart & 1);
                         tiles.push_back(ft);
-                        ++nB[Kr];
+                        ++nB[toff[Kr] + i0 / kFlowBM];
                     }
                 }
             }
         }
     }
-    for (FlowTile& ft : tiles) ft.wait_val = ft.kind == 0 ? nB[ft.wait_ctr] : nA[ft.wait_ctr - N];
+    for (FlowTile& ft : tiles) ft.wait_val = ft.kind == 0 ? nB[ft.wait_ctr] : nA[ft.wait_ctr - nctr];
     if (t.flow_tiles) { cudaFree(t.flow_tiles); t.flow_tiles = nullptr; }
     if (t.flow_ctr) { cudaFree(t.flow_ctr); t.flow_ctr = nullptr; }
     t.flow_ok = even && !tiles.empty() && tiles.size() < (size_t)INT32_MAX;
@@ -1548,7 +1556,8 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
         if (rc != BBM_OK) return rc;
         t.flow_tiles = dt;
     }
-    cudaError_t e = cudaMalloc(&t.flow_ctr, sizeof(int) * (size_t)(2 * N + 1));
+    t.flow_nctr = 2 * nctr;
+    cudaError_t e = cudaMalloc(&t.flow_ctr, sizeof(int) * (size_t)(2 * nctr + 1));
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
     t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx; t.flow_bk = kFlowBK;
     return BBM_OK;
@@ -1632,11 +1641,11 @@ int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const doub
     const i64 cap = bbm_opt(h, "trsm.flow_ctas_per_sm", 0);
     if (cap > 0) occ = (int)std::min<i64>(occ, cap);
     const i64 grid = std::min<i64>(t.flow_ntiles, (i64)occ * h->num_sms);
-    BBM_CUDA(h, cudaMemsetAsync(t.flow_ctr, 0, sizeof(int) * (size_t)(2 * N + 1), h->stream));
+    BBM_CUDA(h, cudaMemsetAsync(t.flow_ctr, 0, sizeof(int) * (size_t)(t.flow_nctr + 1), h->stream));
     const FlowTile* tiles = static_cast<const FlowTile*>(t.flow_tiles);
     i64 ntiles = t.flow_ntiles;
     int* ctr = t.flow_ctr;
-    int err_idx = (int)(2 * N);
+    int err_idx = (int)t.flow_nctr;
     int sleep_ns = (int)std::max<i64>(0, bbm_opt(h, "trsm.flow_sleep_ns", 32));
     void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&d_data, (void*)&W, (void*)&d_B, (void*)&X, (void*)&ctr, (void*)&err_idx, (void*)&sleep_ns};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident (the tiles wait for one another)
