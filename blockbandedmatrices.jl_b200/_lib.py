@@ -77,6 +77,12 @@ SIGNATURES = {
     "bbm_sky_qr_f64": (i32, [vp, vp, vp, vp]),
     "bbm_sky_qr_lmul_adj_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
     "bbm_sky_qr_ldiv_f64": (i32, [vp, vp, vp, vp, vp, i64, i64]),
+    "bbm_sky_ql_f32": (i32, [vp, vp, vp, vp]),
+    "bbm_sky_ql_lmul_adj_f32": (i32, [vp, vp, vp, vp, vp, i64, i64]),
+    "bbm_sky_ql_ldiv_f32": (i32, [vp, vp, vp, vp, vp, i64, i64]),
+    "bbm_sky_qr_f32": (i32, [vp, vp, vp, vp]),
+    "bbm_sky_qr_lmul_adj_f32": (i32, [vp, vp, vp, vp, vp, i64, i64]),
+    "bbm_sky_qr_ldiv_f32": (i32, [vp, vp, vp, vp, vp, i64, i64]),
     "bbm_bbb_trsv_f64": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_bbb_trsv_f32": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_bbb_trsv_prepare_f64": (i32, [vp, vp, i32, i32, vp, pp]),

@@ -2374,6 +2374,88 @@ int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t un
     return BBM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Float32 QR / QL (src/blockskylineqr.jl:17-67 is generic in T): the factorisation and its solves run in Float64 on the
+// FP64 tensor-core pipeline above -- the operands are widened into stream-ordered scratch buffers, the Float64 kernels run
+// unchanged, and the results are rounded to Float32 ONCE at the end.  Every intermediate carries 29 more bits than the
+// reference's Float32 arithmetic, so factors, tau and solutions agree with it to Float32 rounding (the parity tests apply
+// the Float32 tolerance against a Float32 restatement of the reference's loops).
+// ------------------------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) sky_convert_kernel(const S* __restrict__ src, i64 lds, D* __restrict__ dst, i64 ldd, i64 rows, i64 cols) {
+    for (i64 c = blockIdx.y; c < cols; c += gridDim.y)
+        for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < rows; i += (i64)gridDim.x * 256) dst[i + c * ldd] = static_cast<D>(src[i + c * lds]);
+}
+template <typename S, typename D>
+void sky_convert(bbm_handle_t h, const S* src, i64 lds, D* dst, i64 ldd, i64 rows, i64 cols) {
+    if (rows <= 0 || cols <= 0) return;
+    const dim3 grid((unsigned)std::min<i64>((rows + 255) / 256, 4096), (unsigned)std::min<i64>(cols, 65535));
+    sky_convert_kernel<S, D><<<grid, 256, 0, h->stream>>>(src, lds, dst, ldd, rows, cols);
+    h->launches += 1;
+}
+
+struct ScratchF64 {   // stream-ordered Float64 scratch, released behind the work that uses it
+    bbm_handle_t h;
+    std::vector<void*> bufs;
+    explicit ScratchF64(bbm_handle_t hh) : h(hh) {}
+    double* get(i64 n) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, sizeof(double) * (size_t)std::max<i64>(n, 1), h->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        bufs.push_back(p);
+        return static_cast<double*>(p);
+    }
+    ~ScratchF64() { for (void* p : bufs) cudaFreeAsync(p, h->stream); }
+};
+
+// which: 0 qr!, 1 ql!
+int32_t sky_fact_f32(bbm_handle_t h, bbm_sky_desc_t d, float* d_data, float* d_tau, int which) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (!d_data || !d_tau) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const i64 ntau = d->Nr >= d->Nc ? d->n : d->m;
+    ScratchF64 ws(h);
+    double* D = ws.get(d->numel);
+    double* Tau = ws.get(ntau);
+    if (!D || !Tau) return bbm_fail(h, BBM_ERR_ALLOC, "Float64 scratch for the Float32 factorisation");
+    sky_convert<float, double>(h, d_data, d->numel, D, d->numel, d->numel, 1);
+    BBM_CUDA(h, cudaMemsetAsync(Tau, 0, sizeof(double) * (size_t)std::max<i64>(ntau, 1), h->stream));
+    int32_t rc = which == 0 ? sky_qr_fact_impl(h, d, D, Tau) : sky_ql_fact_impl(h, d, D, Tau);
+    if (rc != BBM_OK) return rc;
+    sky_convert<double, float>(h, D, d->numel, d_data, d->numel, d->numel, 1);
+    sky_convert<double, float>(h, Tau, ntau, d_tau, ntau, ntau, 1);
+    return BBM_OK;
+}
+
+// which: 0 lmul!(Q', B) of a QR, 1 F \ B of a QR, 2 lmul!(Q', B) of a QL, 3 F \ B of a QL
+int32_t sky_apply_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_fac, const float* d_tau, float* d_B, i64 ldb, i64 nrhs, int which) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (nrhs < 0) return bbm_fail(h, BBM_ERR_ARG, "nrhs < 0");
+    if (nrhs > 0 && ldb < std::max<i64>(1, d->m)) return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: Q is %lld x %lld, ldb=%lld", (long long)d->m, (long long)d->m, (long long)ldb);
+    if (d->m == 0 || d->n == 0 || nrhs == 0) return BBM_OK;
+    if (!d_fac || !d_tau || !d_B) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    const i64 ntau = d->Nr >= d->Nc ? d->n : d->m;
+    const i64 ldd = std::max<i64>(2, (d->m + 1) & ~i64(1));
+    ScratchF64 ws(h);
+    double* D = ws.get(d->numel);
+    double* Tau = ws.get(ntau);
+    double* Bd = ws.get(ldd * nrhs);
+    if (!D || !Tau || !Bd) return bbm_fail(h, BBM_ERR_ALLOC, "Float64 scratch for the Float32 solve");
+    sky_convert<float, double>(h, d_fac, d->numel, D, d->numel, d->numel, 1);
+    sky_convert<float, double>(h, d_tau, ntau, Tau, ntau, ntau, 1);
+    sky_convert<float, double>(h, d_B, ldb, Bd, ldd, d->m, nrhs);
+    int32_t rc;
+    if (which == 0) rc = bbm_sky_qr_lmul_adj_f64(h, d, D, Tau, Bd, ldd, nrhs);
+    else if (which == 1) rc = bbm_sky_qr_ldiv_f64(h, d, D, Tau, Bd, ldd, nrhs);
+    else rc = sky_ql_apply_impl(h, d, D, Tau, Bd, ldd, nrhs, which == 3 ? 1 : 0);
+    if (rc != BBM_OK) return rc;
+    sky_convert<double, float>(h, Bd, ldd, d_B, ldb, d->m, nrhs);
+    return BBM_OK;
+}
+
 }  // namespace
 
 int32_t bbm_sky_mul_rows(bbm_handle_t h, bbm_sky_desc_t d, int elem, double alpha, const void* data, const void* X, i64 ldx, i64 nrhs, double beta,
@@ -2575,6 +2657,20 @@ int32_t bbm_sky_qr_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_fa
     int32_t rc = sky_qr_lmul_adj_impl(h, d, d_factors, d_tau, d_B, ldb, nrhs);
     if (rc != BBM_OK) return rc;
     return sky_trsm_impl<double>(h, d, 'U', 0, d_factors, d_B, ldb, nrhs);
+}
+int32_t bbm_sky_qr_f32(bbm_handle_t h, bbm_sky_desc_t d, float* d_data, float* d_tau) { return sky_fact_f32(h, d, d_data, d_tau, 0); }
+int32_t bbm_sky_ql_f32(bbm_handle_t h, bbm_sky_desc_t d, float* d_data, float* d_tau) { return sky_fact_f32(h, d, d_data, d_tau, 1); }
+int32_t bbm_sky_qr_lmul_adj_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs) {
+    return sky_apply_f32(h, d, d_factors, d_tau, d_B, ldb, nrhs, 0);
+}
+int32_t bbm_sky_qr_ldiv_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs) {
+    return sky_apply_f32(h, d, d_factors, d_tau, d_B, ldb, nrhs, 1);
+}
+int32_t bbm_sky_ql_lmul_adj_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs) {
+    return sky_apply_f32(h, d, d_factors, d_tau, d_B, ldb, nrhs, 2);
+}
+int32_t bbm_sky_ql_ldiv_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs) {
+    return sky_apply_f32(h, d, d_factors, d_tau, d_B, ldb, nrhs, 3);
 }
 int32_t bbm_sky_trsm_f64(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const double* d_data, double* d_B,
                          int64_t ldb, int64_t nrhs) {

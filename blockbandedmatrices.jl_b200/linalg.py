@@ -261,8 +261,9 @@ def _qr_call(name, F, B):
     br, _bc = _vec_dims(B, "B")
     if br != A.shape[0]:
         raise L.DimensionMismatch(f"Q is {A.shape[0]} x {A.shape[0]}, B is {B.shape}")
-    if A.dtype != np.float64 or np.dtype(B.dtype) != np.float64 or np.dtype(F.tau.dtype) != np.float64:
-        raise TypeError("the device QR solve takes Float64 operands only")
+    if A.dtype not in _SUF or np.dtype(B.dtype) != A.dtype or np.dtype(F.tau.dtype) != A.dtype:
+        raise TypeError("the device QR solve takes matching Float32 / Float64 operands")
+    name = name.replace("_f64", "_" + _SUF[A.dtype][0])
     rc = getattr(h._lib, name)(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(F.tau.ptr), C.c_void_p(B.ptr), _ld(B), _bc)
     L.check(rc, h.h, name)
     return B
@@ -298,16 +299,16 @@ def qr_(A):
     if not isinstance(A, BlockSkylineMatrix):
         raise TypeError("qr! takes a BlockBandedMatrix")
     h = _require_device(A)
-    if A.dtype != np.float64:
-        raise TypeError("the device qr! takes Float64 only")
+    if A.dtype not in _SUF:
+        raise TypeError("the device qr! takes Float32 / Float64")
     n_tau = A.shape[1] if len(A.rows) >= len(A.cols) else A.shape[0]
-    tau = h.empty(max(n_tau, 1), np.float64)
-    rc = h._lib.bbm_sky_qr_f64(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(tau.ptr))
+    tau = h.empty(max(n_tau, 1), A.dtype)
+    rc = getattr(h._lib, f"bbm_sky_qr_{_SUF[A.dtype][0]}")(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(tau.ptr))
     L.check(rc, h.h, "qr!")
     if n_tau == 0:
-        tau = DeviceArray(h, (0,), np.float64, ptr=tau.ptr)
+        tau = DeviceArray(h, (0,), A.dtype, ptr=tau.ptr)
     elif tau.shape[0] != n_tau:
-        tau = DeviceArray(h, (n_tau,), np.float64, ptr=tau.ptr)
+        tau = DeviceArray(h, (n_tau,), A.dtype, ptr=tau.ptr)
     return BlockBandedQR(A, tau)
 
 
@@ -317,16 +318,16 @@ def ql_(A):
     if not isinstance(A, BlockSkylineMatrix):
         raise TypeError("ql! takes a BlockBandedMatrix")
     h = _require_device(A)
-    if A.dtype != np.float64:
-        raise TypeError("the device ql! takes Float64 only")
+    if A.dtype not in _SUF:
+        raise TypeError("the device ql! takes Float32 / Float64")
     if len(A.rows) < len(A.cols):
         raise ValueError("Wide block-QL not implemented")      # ArgumentError, src/blockskylineqr.jl:56
     n_tau = A.shape[1]
-    tau = h.empty(max(n_tau, 1), np.float64)
-    rc = h._lib.bbm_sky_ql_f64(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(tau.ptr))
+    tau = h.empty(max(n_tau, 1), A.dtype)
+    rc = getattr(h._lib, f"bbm_sky_ql_{_SUF[A.dtype][0]}")(h.h, A.descriptor(h), C.c_void_p(A.data.ptr), C.c_void_p(tau.ptr))
     L.check(rc, h.h, "ql!")
     if tau.shape[0] != n_tau:
-        tau = DeviceArray(h, (n_tau,), np.float64, ptr=tau.ptr)
+        tau = DeviceArray(h, (n_tau,), A.dtype, ptr=tau.ptr)
     return BlockBandedQL(A, tau)
 
 

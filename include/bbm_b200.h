@@ -309,6 +309,15 @@ int32_t bbm_sky_ql_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_fa
                             double* d_B, int64_t ldb, int64_t nrhs);
 int32_t bbm_sky_qr_ldiv_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau,
                             double* d_B, int64_t ldb, int64_t nrhs);
+/* The Float32 counterparts of the six calls above (src/blockskylineqr.jl:17-67 is generic in T).  They run the Float64
+ * kernels on widened copies (stream-ordered scratch: 2 x the factors' storage) and round once at the end, so factors, tau
+ * and solutions agree with the reference's Float32 arithmetic to Float32 rounding; same status codes.                  */
+int32_t bbm_sky_qr_f32(bbm_handle_t h, bbm_sky_desc_t d, float* d_data, float* d_tau);
+int32_t bbm_sky_ql_f32(bbm_handle_t h, bbm_sky_desc_t d, float* d_data, float* d_tau);
+int32_t bbm_sky_qr_lmul_adj_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_sky_qr_ldiv_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_sky_ql_lmul_adj_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs);
+int32_t bbm_sky_ql_ldiv_f32(bbm_handle_t h, bbm_sky_desc_t d, const float* d_factors, const float* d_tau, float* d_B, int64_t ldb, int64_t nrhs);
 
 /* ---- several GPUs: row-block partition + halo exchange ------------------------------------
  * One process per GPU.  Block rows are split into contiguous ranges (the reference's one

@@ -273,53 +273,58 @@ function b200_sparse_arrays(A::B200BBB{T}) where {T<:Union{Float32,Float64}}
 end
 
 # ldiv!(F, B) / lmul!(F.Q', B) for F = qr(A) computed by the reference on the host and moved with b200(F):
-# src/blockskylineqr.jl:77-127 (Q'B panel by panel) and :131-145 (then the triangular solve).  Float64.
-b200(F::MatrixFactorizations.QR{Float64,<:BlockSkylineMatrix}) = MatrixFactorizations.QR(b200(F.factors), B200Array(F.τ))
+# src/blockskylineqr.jl:77-127 (Q'B panel by panel) and :131-145 (then the triangular solve).  Float64 and Float32
+# (the Float32 entry points run the Float64 kernels on widened copies and round once at the end).
+b200(F::MatrixFactorizations.QR{T,<:BlockSkylineMatrix}) where T<:Union{Float32,Float64} = MatrixFactorizations.QR(b200(F.factors), B200Array(F.τ))
+for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
+@eval begin
 # qr!(A) on the device (src/blockskylineqr.jl:45-49); `_qr` (:75) has already widened A to (l, l+u) with similar/copyto!
-function BlockBandedMatrices.qr!(A::B200Sky{Float64})
+function BlockBandedMatrices.qr!(A::B200Sky{$T})
     M, N = blocksize(A)
-    τ = B200Array{Float64}(undef, M < N ? size(A, 1) : size(A, 2))
-    check(ccall((:bbm_sky_qr_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+    τ = B200Array{$T}(undef, M < N ? size(A, 1) : size(A, 2))
+    check(ccall(($(QuoteNode(Symbol("bbm_sky_qr_", suf))), libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, Ptr{$T}),
                 handle().ptr, descriptor(A), A.data.ptr, τ.ptr))
     MatrixFactorizations.QR(A, τ)
 end
-function LinearAlgebra.ldiv!(F::MatrixFactorizations.QR{Float64,<:B200Sky{Float64}}, B::B200Array{Float64})
+function LinearAlgebra.ldiv!(F::MatrixFactorizations.QR{$T,<:B200Sky{$T}}, B::B200Array{$T})
     A = F.factors
-    size(A, 1) == size(B, 1) || throw(DimensionMismatch("F has size $(size(A)), B has size $(size(B))"))
-    rc = ccall((:bbm_sky_qr_ldiv_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+    size(A, 1) == size(B, 1) || throw(DimensionMismatch(string("F has size ", size(A), ", B has size ", size(B))))
+    rc = ccall(($(QuoteNode(Symbol("bbm_sky_qr_ldiv_", suf))), libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64),
                handle().ptr, descriptor(A), A.data.ptr, F.τ.ptr, B.ptr, ld(B), size(B, 2))
     rc == BBM_ERR_UNSUPPORTED && error("thin/wide block-banded QR solves stay on the host: use Array(B)")
     check(rc)
     B
 end
 # the QL counterparts (src/blockskylineqr.jl:51-72, 96-111, 149-157); `_ql` (:76) has widened A to (l+u, u)
-function BlockBandedMatrices.ql!(A::B200Sky{Float64})
+function BlockBandedMatrices.ql!(A::B200Sky{$T})
     M, N = blocksize(A)
     M < N && throw(ArgumentError("Wide block-QL not implented"))
-    τ = B200Array{Float64}(undef, size(A, 2))
-    check(ccall((:bbm_sky_ql_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+    τ = B200Array{$T}(undef, size(A, 2))
+    check(ccall(($(QuoteNode(Symbol("bbm_sky_ql_", suf))), libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, Ptr{$T}),
                 handle().ptr, descriptor(A), A.data.ptr, τ.ptr))
     MatrixFactorizations.QL(A, τ)
 end
-function LinearAlgebra.ldiv!(F::MatrixFactorizations.QL{Float64,<:B200Sky{Float64}}, B::B200Array{Float64})
+function LinearAlgebra.ldiv!(F::MatrixFactorizations.QL{$T,<:B200Sky{$T}}, B::B200Array{$T})
     A = F.factors
-    size(A, 1) == size(B, 1) || throw(DimensionMismatch("F has size $(size(A)), B has size $(size(B))"))
-    check(ccall((:bbm_sky_ql_ldiv_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+    size(A, 1) == size(B, 1) || throw(DimensionMismatch(string("F has size ", size(A), ", B has size ", size(B))))
+    check(ccall(($(QuoteNode(Symbol("bbm_sky_ql_ldiv_", suf))), libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64),
                 handle().ptr, descriptor(A), A.data.ptr, F.τ.ptr, B.ptr, ld(B), size(B, 2)))
     B
 end
-function LinearAlgebra.lmul!(adjQ::Adjoint{Float64,<:MatrixFactorizations.QLPackedQ{Float64,<:B200Sky{Float64}}}, B::B200Array{Float64})
+function LinearAlgebra.lmul!(adjQ::Adjoint{$T,<:MatrixFactorizations.QLPackedQ{$T,<:B200Sky{$T}}}, B::B200Array{$T})
     Q = parent(adjQ)
-    check(ccall((:bbm_sky_ql_lmul_adj_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+    check(ccall(($(QuoteNode(Symbol("bbm_sky_ql_lmul_adj_", suf))), libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64),
                 handle().ptr, descriptor(Q.factors), Q.factors.data.ptr, Q.τ.ptr, B.ptr, ld(B), size(B, 2)))
     B
 end
-function LinearAlgebra.lmul!(adjQ::Adjoint{Float64,<:MatrixFactorizations.QRPackedQ{Float64,<:B200Sky{Float64}}}, B::B200Array{Float64})
+function LinearAlgebra.lmul!(adjQ::Adjoint{$T,<:MatrixFactorizations.QRPackedQ{$T,<:B200Sky{$T}}}, B::B200Array{$T})
     Q = parent(adjQ)
-    check(ccall((:bbm_sky_qr_lmul_adj_f64, libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+    check(ccall(($(QuoteNode(Symbol("bbm_sky_qr_lmul_adj_", suf))), libbbm), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64),
                 handle().ptr, descriptor(Q.factors), Q.factors.data.ptr, Q.τ.ptr, B.ptr, ld(B), size(B, 2)))
     B
 end
+end # @eval
+end # for T
 
 # ---- structured +, -, alpha*A + B and A +- (I | Diagonal | Bidiagonal | Tridiagonal) on the device -------------------
 # The result STRUCTURE stays with the reference (`similar(bc)`: src/broadcast.jl:107-131, 391-411 -- `similar` of a

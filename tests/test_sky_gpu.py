@@ -514,6 +514,39 @@ def test_block_banded_ql_on_device(handle, rows, l, u):
         assert relerr(x, rs) <= tol(np.float64, nnz) * cond
 
 
+@pytest.mark.parametrize("rows,l,u", [([4] * 6, 1, 1), ([3, 5, 2, 6, 4], 2, 1), ([40, 33, 64, 17], 1, 2)])
+def test_block_banded_qr_ql_float32(handle, rows, l, u):
+    """The factorisations and their solves for Float32 (src/blockskylineqr.jl:17-67 is generic in T): qr! / ql!, lmul!(Q', B) and
+    F \\ B through bbm_sky_q{r,l}_*_f32 against the Float32 restatement of the reference's loops, Float32 tolerance."""
+    rng = np.random.default_rng(93)
+    m = sum(rows)
+    f32 = np.float32
+    Ad = (F.sky_to_dense(F.sky_from_dense(rng.standard_normal((m, m)) + 3.0 * np.eye(m), rows, rows, l, u), rows, rows, l, u)).astype(f32)
+    nnz = max(rows) * (l + u + 1)
+    B0 = np.asfortranarray(rng.standard_normal((m, 5)).astype(f32))
+    for kind in ("qr", "ql"):
+        lw, uw = (l, l + u) if kind == "qr" else (l + u, u)
+        Aw = B.BlockSkylineMatrix(F.sky_from_dense(Ad, rows, rows, lw, uw).astype(f32), rows, rows, lw, uw)
+        ref = Aw.data.copy()
+        tau_ref = (O.sky_qr if kind == "qr" else O.sky_ql)(rows, rows, lw, uw, ref)
+        Fd = (B.qr_ if kind == "qr" else B.ql_)(Aw.to_device(handle))
+        got, tau = Fd.factors.data.to_host(), Fd.tau.to_host()
+        assert got.dtype == f32 and tau.dtype == f32
+        assert np.abs(got - ref).max() <= tol(f32, nnz) * np.abs(ref).max()
+        assert np.abs(tau - tau_ref).max() <= tol(f32, nnz)
+        dB = handle.to_device(B0)
+        B.lmul_adj_(Fd, dB)
+        r2 = np.asfortranarray(B0.copy())
+        if kind == "qr":
+            O.sky_qr_lmul_adj(rows, rows, lw, uw, ref, tau_ref, r2)
+        else:
+            O.sky_ql_lmul_adj(rows, lw, uw, ref, tau_ref, r2)
+        assert relerr(dB.to_host(), r2) <= tol(f32, nnz)
+        dX = B.ldiv(Fd, handle.to_device(B0))
+        cond = np.linalg.cond(Ad.astype(np.float64))
+        assert relerr(Ad.astype(np.float64) @ dX.to_host().astype(np.float64), B0) <= tol(f32, nnz) * max(1.0, cond)
+
+
 def test_block_banded_ql_wide_is_an_argument_error(handle):
     A = B.BlockSkylineMatrix(np.zeros(F.sky_numentries([3, 3], [3, 3, 3], 2, 1)), [3, 3], [3, 3, 3], 2, 1).to_device(handle)
     with pytest.raises(ValueError):            # test/test_blockskylineqr.jl:121-123 "Wide QL"
