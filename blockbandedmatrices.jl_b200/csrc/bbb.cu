@@ -21,6 +21,8 @@
 // src/AbstractBlockBandedMatrix.jl:90-104).
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "bbm_internal.h"
@@ -886,6 +888,20 @@ const void* walk_kernel(int NS, int w, int nr) {
     }
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (context, function) pair, not to a launch plan: plans of
+// several descriptors share one kernel instantiation, and a later plan with a smaller footprint must not lower the
+// limit under an earlier, cached one ("invalid argument" at its next launch).  The limit is therefore only ever raised.
+cudaError_t ensure_dyn_smem(int device, const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> have;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = have[std::make_pair(device, func)];
+    if (bytes <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
+
 // Builds the launch plan of the band-walk kernel for (descriptor, T, nr, options, fused-halo geometry); plan->walk
 // stays false when the generic kernel has to take the product.
 template <typename T>
@@ -949,7 +965,7 @@ int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::
     int occ = 1;
     {
         const size_t smem_cap = walk_tab_bytes(maxseg_cap, (int)NS) + (size_t)stages * ((size_t)dbytes + (size_t)nr * xbytes);
-        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+        cudaError_t e = ensure_dyn_smem(h->device, func, smem_cap);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, tile, smem_cap);
         if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
         occ = std::max(1, occ);
@@ -988,7 +1004,7 @@ int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::
     // Measured (back-to-back products, one event at either end): 34.4 -> 31.2 us at 512 block rows, 27.2 us together
     // with the third CTA per SM; 231.1 -> 228.2 us at 4096 block rows.
     plan->pdl = (int)bbm_opt(h, "bbb.pdl", 2);
-    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem);
+    cudaError_t e = ensure_dyn_smem(h->device, func, plan->smem);
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "cudaFuncSetAttribute(bbb_walk_kernel): %s", cudaGetErrorString(e));
     plan->walk = true;
     return BBM_OK;

@@ -105,7 +105,7 @@ struct bbm_sky_desc {
     // qr! plan (Float64): sub-panels of nb reflectors; tiles of step t are [ptr[t], ptr[t+1])
     struct QrFact {
         bool built = false;
-        int nb = 32;
+        int nb = 32, variant = 0;
         i64 nsteps = 0, maxrows = 0, ws_total = 0, wlen = 0;
         i64 slotV[2] = {0, 0}, slotY[2] = {0, 0}, slotW[2] = {0, 0};
         i64* d_steps = nullptr;              // per step: slab start, ld, rows, width, tau offset, parity
@@ -2058,6 +2058,208 @@ __global__ void __launch_bounds__(kQrThreads) sky_qr_panel_kernel(double* __rest
     }
 }
 
+// Register-resident variant of the panel step (the default when a slab has at most 1024 rows).  Warp c keeps slab
+// column c in registers for the whole step (lane owns rows lane, lane+32, ...: NR values), so a reflector step is
+//   warp jj   : |x| by shuffles, nu / tau, x scaled, x published in shared memory (double-buffered)
+//   one CTA barrier
+//   warp != jj: one pass over its registers for v'a, one shuffle reduction, one pass for a -= tau (v'a) v
+// -- 1 barrier and ~4 NR + 30 instructions per warp instead of 4 barriers and shared-memory traffic for every element.
+// Column jj-1 of T (larft recurrence) is computed by warp jj-1 during step jj, where it only has a dot product to do.
+// The tail writes R / v / tau and V from the registers and forms YT = T'V' from V in shared memory: lane = slab row,
+// a warp task = 32 rows x 16 columns of YT, staged through shared memory for contiguous stores.
+template <int NR, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 1) sky_qr_panel_reg_kernel(double* __restrict__ data, double* __restrict__ tau, const i64* __restrict__ steps,
+                                                                       i64 step, double* __restrict__ ws, i64 slotV0, i64 slotV1, i64 slotY0, i64 slotY1,
+                                                                       i64 slotW0, i64 slotW1, i64 wlen) {
+    extern __shared__ __align__(16) unsigned char qr_smem[];
+    constexpr int NT = NWARP * 32, RMAX = NR * 32, TW = 34, NH = NWARP / 16, TPW = NR * NH / NWARP, SB = NWARP + 1;
+    static_assert(NR % 16 == 0 && (NWARP == 16 || NWARP == 32) && TPW >= 1, "slab shape");
+    const i64* st = steps + step * 6;
+    const i64 a0 = st[0], ld = st[1];
+    const int rows = (int)st[2], w = (int)st[3];
+    const i64 tau0 = st[4];
+    const int par = (int)st[5];
+    const int lds = rows | 1;
+    double* xs = reinterpret_cast<double*>(qr_smem);            // [2][RMAX] the current reflector (0 above, 1 on the diagonal)
+    double* Ts = xs + 2 * RMAX;                                  // [32][TW]  T (upper)
+    double* Gs = Ts + 32 * TW;                                   // [32][33]  V'V (upper)
+    double* sc = Gs + 32 * 33;                                   // [32] tau, padded to 40
+    double* As = sc + 40;                                        // [w][lds] V, later [rows][SB] YT'
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a[NR];
+    if (warp < w) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int r = lane + 32 * i;
+            a[i] = r < rows ? data[a0 + r + (i64)warp * ld] : 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) a[i] = 0.0;
+    }
+    for (int idx = tid; idx < 32 * TW; idx += NT) Ts[idx] = 0.0;
+    for (int idx = tid; idx < 32 * 33; idx += NT) Gs[idx] = 0.0;
+    {   // the split-k products of this step accumulate into a zeroed W
+        double* W = ws + (par ? slotW1 : slotW0);
+        for (i64 idx = tid; idx < wlen; idx += NT) W[idx] = 0.0;
+    }
+    __syncthreads();
+    auto t_column = [&](int j) {     // T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j], T[j, j] = tau_j; lane = row of T
+        const double tj = sc[j];
+        double s0 = 0.0, s1 = 0.0;
+        if (lane < j) {
+            int k = lane;
+            for (; k + 1 < j; k += 2) {
+                s0 = fma(Ts[lane * TW + k], Gs[k * 33 + j], s0);
+                s1 = fma(Ts[lane * TW + k + 1], Gs[(k + 1) * 33 + j], s1);
+            }
+            if (k < j) s0 = fma(Ts[lane * TW + k], Gs[k * 33 + j], s0);
+        }
+        __syncwarp();
+        if (lane < j) Ts[lane * TW + j] = -tj * (s0 + s1);
+        if (lane == j) Ts[j * TW + j] = tj;
+    };
+    for (int jj = 0; jj < w; ++jj) {
+        double* xb = xs + (jj & 1) * RMAX;
+        if (warp == jj) {
+            double tj = 0.0;
+            if (rows - jj > 1) {                     // real element type: nothing to annihilate in the last row
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NR; i += 2) {
+                    if (lane + 32 * i >= jj) s0 = fma(a[i], a[i], s0);
+                    if (lane + 32 * (i + 1) >= jj) s1 = fma(a[i + 1], a[i + 1], s1);
+                }
+                double ss = s0 + s1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                const double normu = sqrt(ss);
+                double mine = 0.0;
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    if (i == (jj >> 5)) mine = a[i];
+                double xi1 = __shfl_sync(0xffffffffu, mine, jj & 31);
+                if (normu != 0.0) {
+                    const double nu = copysign(normu, xi1);
+                    xi1 += nu;
+                    tj = xi1 / nu;
+                    const double rinv = 1.0 / xi1;
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int r = lane + 32 * i;
+                        if (r > jj) {                // a / xi1, correctly rounded from the reciprocal
+                            const double q = a[i] * rinv;
+                            a[i] = fma(fma(-q, xi1, a[i]), rinv, q);
+                        } else if (r == jj) {
+                            a[i] = -nu;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int r = lane + 32 * i;
+                xb[r] = r < jj ? 0.0 : r == jj ? 1.0 : a[i];
+            }
+            if (lane == 0) { sc[jj] = tj; tau[tau0 + jj] = tj; }
+        }
+        __syncthreads();
+        const double tj = sc[jj];
+        if (tj != 0.0 && warp != jj && warp < w) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NR; i += 2) {
+                v0 = fma(xb[lane + 32 * i], a[i], v0);
+                v1 = fma(xb[lane + 32 * (i + 1)], a[i + 1], v1);
+            }
+            double v = v0 + v1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (warp > jj) {                         // reflectorApply! on the columns to the right
+                v *= tj;
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    if (lane + 32 * i >= jj) a[i] = fma(-xb[lane + 32 * i], v, a[i]);
+            } else if (lane == 0) {                  // to the left: v_t'v_jj for the T factor
+                Gs[warp * 33 + jj] = v;
+            }
+        }
+        if (jj > 0 && warp == jj - 1) t_column(jj - 1);
+    }
+    __syncthreads();
+    if (warp == w - 1) t_column(w - 1);
+    // R and the Householder vectors go back in place; V (zeros above, ones on the diagonal) to the workspace and to
+    // shared memory
+    double* Vout = ws + (par ? slotV1 : slotV0);   // rows x w, ld = rows
+    double* Yout = ws + (par ? slotY1 : slotY0);   // w x rows, ld = w
+    if (warp < w) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int r = lane + 32 * i;
+            if (r < rows) {
+                data[a0 + r + (i64)warp * ld] = a[i];
+                const double vc = r < warp ? 0.0 : r == warp ? 1.0 : a[i];
+                Vout[r + (i64)warp * rows] = vc;
+                As[r + warp * lds] = vc;
+            }
+        }
+    }
+    __syncthreads();
+    // YT[i, r] = sum_{k <= i} T[k, i] V[r, k]: lane = r inside a group of 32 rows, a task = (row group, 16 values of i)
+    double acc[TPW][16];
+#pragma unroll
+    for (int tt = 0; tt < TPW; ++tt) {
+        const int task = warp + tt * NWARP;
+        const int hh = NH == 2 ? (task >> 2) & 1 : 0;
+        const int g = NH == 2 ? (task & 3) | ((task >> 3) << 2) : task;
+        const int r = g * 32 + lane;
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) acc[tt][ii] = 0.0;
+        if (hh == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < w) {
+                    const double v = r < rows ? As[r + k * lds] : 0.0;
+#pragma unroll
+                    for (int i2 = (k & ~1); i2 < 16; i2 += 2) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(Ts + k * TW + i2);
+                        if (i2 >= k) acc[tt][i2] = fma(t2.x, v, acc[tt][i2]);
+                        acc[tt][i2 + 1] = fma(t2.y, v, acc[tt][i2 + 1]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k < w) {
+                    const double v = r < rows ? As[r + k * lds] : 0.0;
+#pragma unroll
+                    for (int i2 = (k < 16 ? 16 : (k & ~1)); i2 < 32; i2 += 2) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(Ts + k * TW + i2);
+                        if (i2 >= k) acc[tt][i2 - 16] = fma(t2.x, v, acc[tt][i2 - 16]);
+                        acc[tt][i2 - 15] = fma(t2.y, v, acc[tt][i2 - 15]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();                                 // every V value has been read: the buffer now takes YT' ([row][i])
+#pragma unroll
+    for (int tt = 0; tt < TPW; ++tt) {
+        const int task = warp + tt * NWARP;
+        const int hh = NH == 2 ? (task >> 2) & 1 : 0;
+        const int g = NH == 2 ? (task & 3) | ((task >> 3) << 2) : task;
+        const int r = g * 32 + lane;
+        if (r < rows) {
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) As[r * SB + hh * 16 + ii] = acc[tt][ii];
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < rows; r += NWARP)
+        if (lane < w) Yout[lane + (i64)r * w] = As[r * SB + lane];
+}
+
 int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
     bbm_sky_desc::QrFact& q = d->qrf;
     if (q.built) return BBM_OK;
@@ -2074,8 +2276,11 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
         for (i64 J = K; J <= std::min(K + U, d->Nc - 1); ++J) cols += d->c[J];
         maxcols = std::max(maxcols, cols);
     }
-    q.nb = maxS <= 704 ? 32 : maxS <= 1472 ? 16 : 8;
-    if ((size_t)q.nb * (maxS | 1) * 8 + 2 * 32 * 33 * 8 + 1024 > std::min<size_t>(h->smem_optin, 220 * 1024))
+    // variant 1 / 2: the register-resident slab kernel with 32 warps x 16 rows per lane / 16 warps x 32 rows per lane;
+    // 0: the shared-memory slab kernel (taller panels, or qr.panel = 1)
+    q.variant = bbm_opt(h, "qr.panel", 0) == 1 ? 0 : maxS <= 512 ? 1 : maxS <= 1024 ? 2 : 0;
+    q.nb = q.variant == 1 ? 32 : q.variant == 2 ? 16 : maxS <= 704 ? 32 : maxS <= 1472 ? 16 : 8;
+    if (q.variant == 0 && (size_t)q.nb * (maxS | 1) * 8 + 2 * 32 * 33 * 8 + 1024 > std::min<size_t>(h->smem_optin, 220 * 1024))
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "qr!: panels of %lld rows exceed the shared-memory slab", (long long)maxS);
     q.maxrows = maxS;
     auto even = [](i64 v) { return (v + 1) & ~i64(1); };
@@ -2144,12 +2349,17 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
     if (rc != BBM_OK) return rc;
     double* WS = static_cast<double*>(h->ws_w);
     BBM_CUDA(h, cudaMemsetAsync(d_tau, 0, (size_t)ntau * sizeof(double), h->stream));
-    const size_t smem = ((size_t)q.nb * (q.maxrows | 1) + 2 * 32 * 33 + 32 + 2 + 32 + 2) * sizeof(double);
-    BBM_CUDA(h, cudaFuncSetAttribute(sky_qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = ((size_t)q.nb * (q.maxrows | 1) + 2 * 32 * 33 + 32 + 2 + 32 + 2) * sizeof(double);
+    if (q.variant != 0) {
+        const size_t rmax = q.variant == 1 ? 512 : 1024;
+        smem = (2 * rmax + 32 * 34 + 32 * 33 + 40 + std::max<size_t>((size_t)q.nb * (q.maxrows | 1), (size_t)q.maxrows * (q.nb + 1))) * sizeof(double);
+    }
+    auto kern = q.variant == 1 ? sky_qr_panel_reg_kernel<16, 32> : q.variant == 2 ? sky_qr_panel_reg_kernel<32, 16> : sky_qr_panel_kernel;
+    BBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
+    const unsigned nthreads = q.variant == 2 ? 512 : kQrThreads;
     for (i64 t = 0; t < q.nsteps; ++t) {
-        sky_qr_panel_kernel<<<1, kQrThreads, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1],
-                                                               q.slotW[0], q.slotW[1], q.wlen);
+        kern<<<1, nthreads, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1], q.slotW[0], q.slotW[1], q.wlen);
         h->launches += 1;
         rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
         if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);

@@ -28,6 +28,20 @@ def main():
     from tests.helpers import random_bbb, relerr, tol
 
     world, rank, local_rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    import faulthandler
+    import time as _time
+    _t0 = _time.time()
+    # a rank that is still here after this long dumps its Python stack and leaves: a hang names itself
+    import threading
+    _deadline = float(os.environ.get("BBM_DIST_TEST_DEADLINE_S", "200"))
+    faulthandler.dump_traceback_later(_deadline, exit=False)
+    _killer = threading.Timer(_deadline + 5.0, lambda: os._exit(3))     # every rank has had time to print its stack
+    _killer.daemon = True
+    _killer.start()
+
+    def trace(*what):
+        if os.environ.get("BBM_DIST_TRACE"):
+            print(f"[rank {rank} +{_time.time() - _t0:6.1f}s]", *what, file=sys.stderr, flush=True)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -36,6 +50,7 @@ def main():
     failures = []
     for ci, (rows, cols, lu, lm, want_fused) in enumerate(CASES):
         for use_peer in (False, True):
+            trace("bbb case", ci, "peer", use_peer)
             rng = np.random.default_rng(500 + ci)
             data = random_bbb(rng, rows, cols, *lu, *lm)
             A = D.DistBandedBlockBandedMatrix(comm, rows, cols, lu, lm)
@@ -68,6 +83,7 @@ def main():
                 dist.barrier()
             # the host-vector call (pipelined upload / exchange / product / download) on the same operands
             if not use_peer:
+                trace("bbb case", ci, "host vectors")
                 for beta in (0.0, 0.5):
                     x = rng.standard_normal(sum(cols))
                     xo = np.ascontiguousarray(x[c0 + o:c0 + o + lay["n_own"]])
@@ -90,6 +106,7 @@ def main():
     from tests.helpers import random_sky
     for ci, (rows, l, u) in enumerate([([16] * 12, 2, 2), ([5, 9, 4, 12, 7, 3, 8, 6], 1, 2), ([64] * 9, 0, 3), ([130] * 11, 2, 1)]):
         rng = np.random.default_rng(900 + ci)
+        trace("sky case", ci)
         adata = random_sky(rng, rows, rows, l, u)
         bdata = random_sky(rng, rows, rows, u, l)
         Ah = B.BlockSkylineMatrix(adata, rows, rows, l, u)
@@ -121,6 +138,7 @@ def main():
                 if lay["m_own"] and (np.isnan(got).any() or relerr(got, want) > tol(np.float64, 64)):
                     failures.append(("sky matvec", ci, nrhs, epoch, relerr(got, want)))
             mv.close()
+        trace("sky product", ci)
         prod = D.DistBlockBandedMatmul(comm, rows, rows, rows, (l, u), (u, l), Kbounds=kb)
         P = prod.ranges
         locA, _, _ = D.sky_cut_rows(Ah, P["K0"], P["K1"])
@@ -161,6 +179,7 @@ def main():
     rng = np.random.default_rng(77)
     data = random_bbb(rng, rows, rows, 1, 1, 1, 1)
     for timeout_ms, delay_s, expect_ok in ((30000, 1.5, True), (200, 1.0, False)):
+        trace("late rank", timeout_ms, delay_s)
         A = D.DistBandedBlockBandedMatrix(comm, rows, rows, (1, 1), (1, 1))
         lay = A.layout
         A.set_local_data(A.local_data(data))
@@ -205,6 +224,7 @@ def main():
         A.close()
     h.set_option("dist.peer_timeout_ms", 30000)
 
+    trace("done, failures:", failures)
     flag = torch.tensor([len(failures)], device=f"cuda:{local_rank}")
     dist.all_reduce(flag)
     if failures:
@@ -214,6 +234,8 @@ def main():
     comm.close()
     dist.barrier()
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
+    _killer.cancel()
     sys.exit(0 if int(flag.item()) == 0 else 1)
 
 

@@ -586,3 +586,22 @@ def test_bbb_adjoint_mul_matches_oracle(handle, case, dtype):
             assert relerr(got, dense) <= tol(dtype, nnz)
     with pytest.raises(B.DimensionMismatch):
         B.mul_(handle.empty(n + 1, dtype), At, handle.empty(m, dtype))
+
+
+def test_bbb_mul_cached_plans_of_two_descriptors(handle):
+    """Two matrices with the same bandwidths (one kernel instantiation) but different block sizes (different launch
+    plans, different shared-memory footprints), multiplied alternately: the later plan must not invalidate the earlier
+    one (the dynamic shared-memory limit is a per-kernel attribute)."""
+    rng = np.random.default_rng(321)
+    mats = []
+    for rows in ([2048] * 6, [40] * 12, list(range(20, 60))):
+        data = random_bbb(rng, rows, rows, 1, 1, 1, 1)
+        A = B.BandedBlockBandedMatrix(data, rows, rows, (1, 1), (1, 1)).to_device(handle)
+        mats.append((rows, data, A))
+    for _ in range(3):
+        for rows, data, A in mats:
+            x = rng.standard_normal(sum(rows))
+            y = B.mul(A, handle.to_device(x)).to_host()
+            ref = np.zeros(sum(rows))
+            O.bbb_mul(rows, rows, 1, 1, 1, 1, 1.0, data, x, 0.0, ref)
+            assert relerr(y, ref) <= tol(np.float64, 9)

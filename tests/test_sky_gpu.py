@@ -465,6 +465,33 @@ def test_block_banded_qr_factorisation_on_device(handle, rows, cols, l, u):
         assert relerr(Ad @ x, b) <= tol(np.float64, max(rows) * (2 * l + u + 1)) * max(1.0, np.linalg.cond(Ad))
 
 
+@pytest.mark.parametrize("panel", [0, 1])
+@pytest.mark.parametrize("rows,l,u", [([256] * 4, 1, 1),              # 512-row slabs: 32 warps x 16 rows per lane
+                                      ([280, 260, 300], 2, 1),        # 840-row slabs: 16 warps x 32 rows per lane
+                                      ([600, 500, 90], 1, 1),         # 1100-row slabs: shared-memory slab kernel
+                                      ([37, 5, 64, 129], 1, 2)])
+def test_block_banded_qr_panel_kernels(handle, rows, l, u, panel):
+    """Every panel-step kernel of qr! (register-resident slabs of <= 512 / <= 1024 rows, shared-memory slab; option
+    qr.panel = 1 forces the latter) gives LAPACK's factors and tau (test/test_blockskylineqr.jl:19-20)."""
+    rng = np.random.default_rng(74)
+    m = sum(rows)
+    A = B.BlockSkylineMatrix(F.sky_from_dense(rng.standard_normal((m, m)) + 3.0 * np.eye(m), rows, rows, l, u), rows, rows, l, u)
+    Aw = A.with_bandwidths(l, l + u)
+    handle.set_option("qr.panel", panel)
+    try:
+        Fd = B.qr_(Aw.to_device(handle))
+        got, tau = Fd.factors.data.to_host(), Fd.tau.to_host()
+    finally:
+        handle.set_option("qr.panel", 0)
+    h, t = np.linalg.qr(A.to_dense(), mode="raw")
+    fac = F.sky_to_dense(got, rows, rows, l, l + u)
+    assert np.abs(fac - h.T).max() <= 1e-12 * np.abs(h).max()
+    assert np.abs(tau - t).max() <= 1e-12
+    b = rng.standard_normal(m)
+    x = B.ldiv(Fd, handle.to_device(b)).to_host()
+    assert relerr(A.to_dense() @ x, b) <= tol(np.float64, max(rows) * (2 * l + u + 1)) * max(1.0, np.linalg.cond(A.to_dense()))
+
+
 QL_GPU_CASES = [
     (list(range(1, 6)), 2, 1),                  # test/test_blockskylineqr.jl:81-100 "Square QL"
     ([3, 2, 1, 3], 1, 1),                       # :125-140 "Off-diagonals"
