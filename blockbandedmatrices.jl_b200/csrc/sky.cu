@@ -2058,22 +2058,102 @@ __global__ void __launch_bounds__(kQrThreads) sky_qr_panel_kernel(double* __rest
     }
 }
 
-// Register-resident variant of the panel step (the default when a slab has at most 1024 rows).  Warp c keeps slab
-// column c in registers for the whole step (lane owns rows lane, lane+32, ...: NR values), so a reflector step is
-//   warp jj   : |x| by shuffles, nu / tau, x scaled, x published in shared memory (double-buffered)
+// Helpers of the register-resident panel step.  A slab column lives in the registers of one warp (lane owns rows lane,
+// lane+32, ...); a slab has at most 32 columns, so row jj is element 0 of lane jj and only element 0 can lie above it.
+//
+// The reflector's scalars sit on the critical path of every step (all lanes compute them redundantly): square root,
+// quotient and reciprocal come from the hardware's 20-bit seeds with two Newton steps and one residual correction each
+// (the quotient-from-reciprocal sequence of the IEEE routines without their special-case branches: ~12 dependent
+// instructions instead of ~35).  Arguments outside [1e-280, 1e280] take the library routines.
+__device__ __forceinline__ double qr_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double qr_sqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double sq = a * y;
+    return fma(fma(-sq, sq, a), 0.5 * y, sq);
+}
+// One Householder reflector on a slab column, convention of LinearAlgebra.reflector!: nu = copysign(|x|, x_jj),
+// x_jj <- -nu, x[jj+1:] scaled by 1 / (x_jj + nu) (a multiplication by the reciprocal, as LAPACK's dlarfg scales),
+// tau = (x_jj + nu) / nu.  Publishes v (0 above row jj, 1 in row jj) in xb and tau in sc[jj] / tau_out[jj].
+template <int NR>
+__device__ __forceinline__ void qr_reflect(double (&col)[NR], int jj, int rows, int lane, double* __restrict__ xb, double* __restrict__ sc,
+                                           double* __restrict__ tau_out) {
+    double tj = 0.0;
+    if (rows - jj > 1) {                 // real element type: nothing to annihilate in the last row
+        double s0 = lane >= jj ? col[0] * col[0] : 0.0, s1 = col[1] * col[1], s2 = col[2] * col[2], s3 = col[3] * col[3];
+#pragma unroll
+        for (int i = 4; i < NR; i += 4) {
+            s0 = fma(col[i], col[i], s0);
+            s1 = fma(col[i + 1], col[i + 1], s1);
+            s2 = fma(col[i + 2], col[i + 2], s2);
+            s3 = fma(col[i + 3], col[i + 3], s3);
+        }
+        double ss = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        double xi1 = __shfl_sync(0xffffffffu, col[0], jj);
+        if (ss != 0.0) {
+            const bool fast = ss > 1e-280 && ss < 1e280;
+            const double normu = fast ? qr_sqrt(ss) : sqrt(ss);
+            const double nu = copysign(normu, xi1);
+            xi1 += nu;                   // same sign: |xi1| >= |nu| > 0
+            double rinv;
+            if (fast && fabs(xi1) < 1e280) {
+                const double rnu = qr_rcp(nu);
+                rinv = qr_rcp(xi1);
+                const double q = xi1 * rnu;
+                tj = fma(fma(-q, nu, xi1), rnu, q);
+            } else {
+                tj = xi1 / nu;
+                rinv = 1.0 / xi1;
+            }
+            if (lane > jj) col[0] *= rinv;
+            else if (lane == jj) col[0] = -nu;
+#pragma unroll
+            for (int i = 1; i < NR; ++i) col[i] *= rinv;
+        }
+    }
+    xb[lane] = lane < jj ? 0.0 : lane == jj ? 1.0 : col[0];
+#pragma unroll
+    for (int i = 1; i < NR; ++i) xb[lane + 32 * i] = col[i];
+    if (lane == 0) { sc[jj] = tj; tau_out[jj] = tj; }
+}
+
+// Register-resident variant of the panel step (the default when a slab has at most 1024 rows).  A warp keeps CPW slab
+// columns in registers for the whole step (lane owns rows lane, lane+32, ...: NR values per column), so a reflector
+// step is
+//   owner warp : |x| by shuffles, nu / tau, x scaled, v published in shared memory (double-buffered)
 //   one CTA barrier
-//   warp != jj: one pass over its registers for v'a, one shuffle reduction, one pass for a -= tau (v'a) v
-// -- 1 barrier and ~4 NR + 30 instructions per warp instead of 4 barriers and shared-memory traffic for every element.
-// Column jj-1 of T (larft recurrence) is computed by warp jj-1 during step jj, where it only has a dot product to do.
+//   every warp : v into registers once, then per column v'a (one pass over registers, one shuffle reduction) and
+//                a -= tau (v'a) v (one more pass)
+// -- 1 barrier, NR shared-memory loads and ~4 NR FP64 instructions per warp instead of 4 barriers and shared-memory
+// traffic for every element.  The step is a chain of dependent FP64 instructions (ncu: ~13 cycles per issued
+// instruction and warp, FP64 pipe 17 % busy), so what counts is the NUMBER of instructions on the owner -> barrier ->
+// update -> next owner path.  History on a 512 x 32 slab: shared-memory slab kernel 140 us; one column per warp, v
+// re-read for the update, spills: 122 us (LSU queue; profiles/r02_sky_qr_panel_reg_v1_ncu_details.txt); two columns
+// per warp, v in registers: 62 us; a two-barrier variant that overlaps the owner's scalar chain with everybody's dot
+// products on the raw column was SLOWER (70 us: more instructions per step than the overlap saved).
+// Column jj-1 of T (larft recurrence) is computed during step jj by a warp that is half a panel away from the owner.
 // The tail writes R / v / tau and V from the registers and forms YT = T'V' from V in shared memory: lane = slab row,
 // a warp task = 32 rows x 16 columns of YT, staged through shared memory for contiguous stores.
-template <int NR, int NWARP>
+template <int NR, int NWARP, int CPW>
 __global__ void __launch_bounds__(NWARP * 32, 1) sky_qr_panel_reg_kernel(double* __restrict__ data, double* __restrict__ tau, const i64* __restrict__ steps,
                                                                        i64 step, double* __restrict__ ws, i64 slotV0, i64 slotV1, i64 slotY0, i64 slotY1,
                                                                        i64 slotW0, i64 slotW1, i64 wlen) {
     extern __shared__ __align__(16) unsigned char qr_smem[];
-    constexpr int NT = NWARP * 32, RMAX = NR * 32, TW = 34, NH = NWARP / 16, TPW = NR * NH / NWARP, SB = NWARP + 1;
-    static_assert(NR % 16 == 0 && (NWARP == 16 || NWARP == 32) && TPW >= 1, "slab shape");
+    constexpr int NT = NWARP * 32, RMAX = NR * 32, TW = 34, NB = NWARP * CPW, NH = NB / 16, TPW = NR * NH / NWARP, SB = NB + 1;
+    static_assert(NR % 16 == 0 && (NB == 16 || NB == 32) && TPW >= 1 && (NR * NH) % NWARP == 0, "slab shape");
     const i64* st = steps + step * 6;
     const i64 a0 = st[0], ld = st[1];
     const int rows = (int)st[2], w = (int)st[3];
@@ -2083,19 +2163,18 @@ __global__ void __launch_bounds__(NWARP * 32, 1) sky_qr_panel_reg_kernel(double*
     double* xs = reinterpret_cast<double*>(qr_smem);            // [2][RMAX] the current reflector (0 above, 1 on the diagonal)
     double* Ts = xs + 2 * RMAX;                                  // [32][TW]  T (upper)
     double* Gs = Ts + 32 * TW;                                   // [32][33]  V'V (upper)
-    double* sc = Gs + 32 * 33;                                   // [32] tau, padded to 40
-    double* As = sc + 40;                                        // [w][lds] V, later [rows][SB] YT'
+    double* sc = Gs + 32 * 33;                                   // [32] tau | [32] 1 / (x_jj + nu), padded to 72
+    double* As = sc + 72;                                        // [w][lds] V, later [rows][SB] YT'
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double a[NR];
-    if (warp < w) {
+    double a[CPW][NR];
+#pragma unroll
+    for (int s = 0; s < CPW; ++s) {
+        const int c = warp * CPW + s;
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             const int r = lane + 32 * i;
-            a[i] = r < rows ? data[a0 + r + (i64)warp * ld] : 0.0;
+            a[s][i] = (c < w && r < rows) ? data[a0 + r + (i64)c * ld] : 0.0;
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < NR; ++i) a[i] = 0.0;
     }
     for (int idx = tid; idx < 32 * TW; idx += NT) Ts[idx] = 0.0;
     for (int idx = tid; idx < 32 * 33; idx += NT) Gs[idx] = 0.0;
@@ -2121,86 +2200,80 @@ __global__ void __launch_bounds__(NWARP * 32, 1) sky_qr_panel_reg_kernel(double*
     };
     for (int jj = 0; jj < w; ++jj) {
         double* xb = xs + (jj & 1) * RMAX;
-        if (warp == jj) {
-            double tj = 0.0;
-            if (rows - jj > 1) {                     // real element type: nothing to annihilate in the last row
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int i = 0; i < NR; i += 2) {
-                    if (lane + 32 * i >= jj) s0 = fma(a[i], a[i], s0);
-                    if (lane + 32 * (i + 1) >= jj) s1 = fma(a[i + 1], a[i + 1], s1);
-                }
-                double ss = s0 + s1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                const double normu = sqrt(ss);
-                double mine = 0.0;
-#pragma unroll
-                for (int i = 0; i < NR; ++i)
-                    if (i == (jj >> 5)) mine = a[i];
-                double xi1 = __shfl_sync(0xffffffffu, mine, jj & 31);
-                if (normu != 0.0) {
-                    const double nu = copysign(normu, xi1);
-                    xi1 += nu;
-                    tj = xi1 / nu;
-                    const double rinv = 1.0 / xi1;
-#pragma unroll
-                    for (int i = 0; i < NR; ++i) {
-                        const int r = lane + 32 * i;
-                        if (r > jj) {                // a / xi1, correctly rounded from the reciprocal
-                            const double q = a[i] * rinv;
-                            a[i] = fma(fma(-q, xi1, a[i]), rinv, q);
-                        } else if (r == jj) {
-                            a[i] = -nu;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                const int r = lane + 32 * i;
-                xb[r] = r < jj ? 0.0 : r == jj ? 1.0 : a[i];
-            }
-            if (lane == 0) { sc[jj] = tj; tau[tau0 + jj] = tj; }
+        if (warp == jj / CPW) {                      // (explicit branches: the column array must stay in registers)
+            if (CPW == 1 || jj % CPW == 0) qr_reflect<NR>(a[0], jj, rows, lane, xb, sc, tau + tau0);
+            else qr_reflect<NR>(a[CPW - 1], jj, rows, lane, xb, sc, tau + tau0);
         }
         __syncthreads();
         const double tj = sc[jj];
-        if (tj != 0.0 && warp != jj && warp < w) {
-            double v0 = 0.0, v1 = 0.0;
+        if (tj != 0.0 && warp * CPW < w) {
+            constexpr bool kKeepX = (CPW + 1) * NR * 2 <= 100;   // v stays in registers between the two passes if it fits
+            double xv[kKeepX ? NR : 1];
+            if constexpr (kKeepX) {
 #pragma unroll
-            for (int i = 0; i < NR; i += 2) {
-                v0 = fma(xb[lane + 32 * i], a[i], v0);
-                v1 = fma(xb[lane + 32 * (i + 1)], a[i + 1], v1);
+                for (int i = 0; i < NR; ++i) xv[i] = xb[lane + 32 * i];
             }
-            double v = v0 + v1;
+            double v[CPW];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (warp > jj) {                         // reflectorApply! on the columns to the right
-                v *= tj;
+            for (int s = 0; s < CPW; ++s) {
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll
-                for (int i = 0; i < NR; ++i)
-                    if (lane + 32 * i >= jj) a[i] = fma(-xb[lane + 32 * i], v, a[i]);
-            } else if (lane == 0) {                  // to the left: v_t'v_jj for the T factor
-                Gs[warp * 33 + jj] = v;
+                for (int i = 0; i < NR; i += 4) {
+                    if constexpr (kKeepX) {
+                        v0 = fma(xv[i], a[s][i], v0);
+                        v1 = fma(xv[i + 1], a[s][i + 1], v1);
+                        v2 = fma(xv[i + 2], a[s][i + 2], v2);
+                        v3 = fma(xv[i + 3], a[s][i + 3], v3);
+                    } else {
+                        v0 = fma(xb[lane + 32 * i], a[s][i], v0);
+                        v1 = fma(xb[lane + 32 * (i + 1)], a[s][i + 1], v1);
+                        v2 = fma(xb[lane + 32 * (i + 2)], a[s][i + 2], v2);
+                        v3 = fma(xb[lane + 32 * (i + 3)], a[s][i + 3], v3);
+                    }
+                }
+                v[s] = (v0 + v1) + (v2 + v3);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int s = 0; s < CPW; ++s) v[s] += __shfl_xor_sync(0xffffffffu, v[s], o);
+            }
+#pragma unroll
+            for (int s = 0; s < CPW; ++s) {
+                const int c = warp * CPW + s;
+                if (c >= w || c == jj) continue;
+                if (c > jj) {                        // reflectorApply! on the columns to the right
+                    const double vt = v[s] * tj;         // (v is zero above row jj: those entries keep their value)
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        if constexpr (kKeepX) a[s][i] = fma(-xv[i], vt, a[s][i]);
+                        else a[s][i] = fma(-xb[lane + 32 * i], vt, a[s][i]);
+                    }
+                } else if (lane == 0) {              // to the left: v_t'v_jj for the T factor
+                    Gs[c * 33 + jj] = v[s];
+                }
             }
         }
-        if (jj > 0 && warp == jj - 1) t_column(jj - 1);
+        if (jj > 0 && warp == ((jj / CPW) ^ (NWARP / 2))) t_column(jj - 1);
     }
     __syncthreads();
-    if (warp == w - 1) t_column(w - 1);
+    if (warp == 0) t_column(w - 1);
     // R and the Householder vectors go back in place; V (zeros above, ones on the diagonal) to the workspace and to
     // shared memory
     double* Vout = ws + (par ? slotV1 : slotV0);   // rows x w, ld = rows
     double* Yout = ws + (par ? slotY1 : slotY0);   // w x rows, ld = w
-    if (warp < w) {
+#pragma unroll
+    for (int s = 0; s < CPW; ++s) {
+        const int c = warp * CPW + s;
+        if (c >= w) continue;
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             const int r = lane + 32 * i;
             if (r < rows) {
-                data[a0 + r + (i64)warp * ld] = a[i];
-                const double vc = r < warp ? 0.0 : r == warp ? 1.0 : a[i];
-                Vout[r + (i64)warp * rows] = vc;
-                As[r + warp * lds] = vc;
+                data[a0 + r + (i64)c * ld] = a[s][i];
+                const double vc = r < c ? 0.0 : r == c ? 1.0 : a[s][i];
+                Vout[r + (i64)c * rows] = vc;
+                As[r + c * lds] = vc;
             }
         }
     }
@@ -2276,7 +2349,7 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
         for (i64 J = K; J <= std::min(K + U, d->Nc - 1); ++J) cols += d->c[J];
         maxcols = std::max(maxcols, cols);
     }
-    // variant 1 / 2: the register-resident slab kernel with 32 warps x 16 rows per lane / 16 warps x 32 rows per lane;
+    // variant 1 / 2: the register-resident slab kernel, 16 warps x 2 columns x 16 rows per lane / 16 warps x 1 column x 32 rows per lane;
     // 0: the shared-memory slab kernel (taller panels, or qr.panel = 1)
     q.variant = bbm_opt(h, "qr.panel", 0) == 1 ? 0 : maxS <= 512 ? 1 : maxS <= 1024 ? 2 : 0;
     q.nb = q.variant == 1 ? 32 : q.variant == 2 ? 16 : maxS <= 704 ? 32 : maxS <= 1472 ? 16 : 8;
@@ -2352,12 +2425,12 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
     size_t smem = ((size_t)q.nb * (q.maxrows | 1) + 2 * 32 * 33 + 32 + 2 + 32 + 2) * sizeof(double);
     if (q.variant != 0) {
         const size_t rmax = q.variant == 1 ? 512 : 1024;
-        smem = (2 * rmax + 32 * 34 + 32 * 33 + 40 + std::max<size_t>((size_t)q.nb * (q.maxrows | 1), (size_t)q.maxrows * (q.nb + 1))) * sizeof(double);
+        smem = (2 * rmax + 32 * 34 + 32 * 33 + 72 + std::max<size_t>((size_t)q.nb * (q.maxrows | 1), (size_t)q.maxrows * (q.nb + 1))) * sizeof(double);
     }
-    auto kern = q.variant == 1 ? sky_qr_panel_reg_kernel<16, 32> : q.variant == 2 ? sky_qr_panel_reg_kernel<32, 16> : sky_qr_panel_kernel;
+    auto kern = q.variant == 1 ? sky_qr_panel_reg_kernel<16, 16, 2> : q.variant == 2 ? sky_qr_panel_reg_kernel<32, 16, 1> : sky_qr_panel_kernel;
     BBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
-    const unsigned nthreads = q.variant == 2 ? 512 : kQrThreads;
+    const unsigned nthreads = q.variant != 0 ? 512 : kQrThreads;
     for (i64 t = 0; t < q.nsteps; ++t) {
         kern<<<1, nthreads, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1], q.slotW[0], q.slotW[1], q.wlen);
         h->launches += 1;
