@@ -72,6 +72,7 @@ struct bbm_context {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // pipelined host-vector product
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_ev[2] = {nullptr, nullptr};
+    cudaEvent_t qr_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // qr! look-ahead: panel done x2, rest-of-update done x2
 };
 
 inline bool bbm_valid(bbm_handle_t h) { return h != nullptr && h->magic == 0xBB200C0Du; }

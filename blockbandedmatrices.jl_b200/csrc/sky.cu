@@ -109,8 +109,10 @@ struct bbm_sky_desc {
         i64 nsteps = 0, maxrows = 0, ws_total = 0, wlen = 0;
         i64 slotV[2] = {0, 0}, slotY[2] = {0, 0}, slotW[2] = {0, 0};
         i64* d_steps = nullptr;              // per step: slab start, ld, rows, width, tau offset, parity
-        Tri::Batch bW, bC;
+        Tri::Batch bW, bC;                   // tiles of W = YT C and C -= V W on everything but the next slab's columns
         std::vector<int> ptrW, ptrC;
+        Tri::Batch bWn, bCn;                 // the same on the columns the NEXT step factorises (look-ahead)
+        std::vector<int> ptrWn, ptrCn;
     } qrf;
     // device copy of the structure tables [off(Nc+1) | S(Nc) | klo(Nc) | khi(Nc) | R(Nr+1) | C(Nc+1)] for the
     // element-wise kernels of csrc/structadd.cu, uploaded on first use
@@ -1049,8 +1051,9 @@ int32_t upload_batch(bbm_handle_t h, const MmBatchHost& hb, bbm_sky_desc::Tri::B
 
 // C (+)= alpha * A * B over the tiles [t0, t0+nt) of a batch; 64x64 DMMA tiles, 4 warps
 int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, int nt, const double* A, const double* Bm,
-                    double* Cm, double alpha, double beta, bool atomic, bool set_attr = true, bool pdl = false) {
+                    double* Cm, double alpha, double beta, bool atomic, bool set_attr = true, bool pdl = false, cudaStream_t st = nullptr) {
     if (nt <= 0) return BBM_OK;
+    if (!st) st = h->stream;
     MmParams<double> p{A, Bm, Cm, (const MmCBlk*)b.cblks, (const MmSeg*)b.segs, (const MmTile*)b.tiles + t0, alpha, beta};
     const bool al = b.aligned && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(Bm) % 16 == 0);
     if (b.tile == 128) {
@@ -1080,7 +1083,7 @@ int32_t launch_mm64(bbm_handle_t h, const bbm_sky_desc::Tri::Batch& b, int t0, i
             // programmatic dependent launch: the kernel's launch latency and prologue overlap the predecessor's
             // tail; griddepcontrol.wait inside the kernel still orders all operand accesses after it
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)nt); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+            cfg.gridDim = dim3((unsigned)nt); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -2366,43 +2369,62 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
     q.wlen = (i64)q.nb * maxcols;
     q.ws_total = off;
     std::vector<i64> steps;
-    MmBatchHost bw, bc;
-    q.ptrW.clear(); q.ptrC.clear();
-    i64 nsteps = 0;
+    MmBatchHost bw, bc, bwn, bcn;
+    q.ptrW.clear(); q.ptrC.clear(); q.ptrWn.clear(); q.ptrCn.clear();
+    struct Slab { i64 K, j0, w; };
+    std::vector<Slab> slabs;
     for (i64 K = 0; K < P; ++K) {
         const i64 K1 = std::min(K + L, d->Nr - 1);
         const i64 S = d->R[K1 + 1] - d->R[K], c = d->c[K];
         if (S == 0 || c == 0) continue;
+        for (i64 j0 = 0; j0 < std::min(S, c); j0 += q.nb) slabs.push_back(Slab{K, j0, std::min<i64>(q.nb, std::min(S, c) - j0)});
+    }
+    i64 nsteps = 0;
+    for (size_t si = 0; si < slabs.size(); ++si) {
+        const i64 K = slabs[si].K, j0 = slabs[si].j0, w = slabs[si].w;
+        const i64 K1 = std::min(K + L, d->Nr - 1);
+        const i64 S = d->R[K1 + 1] - d->R[K], c = d->c[K];
         const i64 vstart = sky_start(d, K, K), ld = d->S[K];
-        for (i64 j0 = 0; j0 < std::min(S, c); j0 += q.nb) {
-            const i64 w = std::min<i64>(q.nb, std::min(S, c) - j0), rows = S - j0;
-            const int par = (int)(nsteps & 1);
-            steps.insert(steps.end(), {vstart + j0 + j0 * ld, ld, rows, w, d->C[K] + j0, (i64)par});
-            q.ptrW.push_back((int)bw.tiles.size());
-            q.ptrC.push_back((int)bc.tiles.size());
-            i64 woff = q.slotW[par];
-            auto piece = [&](i64 cstart, i64 ldc, i64 cols) {   // rows x cols target with top-left at data[cstart]
-                if (cols <= 0) return;
-                for (i64 k0 = 0; k0 < rows; k0 += 64)                                           // W += YT[:, k-slice] C[k-slice, :]
-                    bw.add(woff, w, w, cols, MmSeg{q.slotY[par] + k0 * w, w, cstart + k0, ldc, std::min<i64>(64, rows - k0)});
-                bc.add(cstart, ldc, rows, cols, MmSeg{q.slotV[par], rows, woff, w, w});       // C -= V W
-                woff += w * cols;
-            };
-            piece(vstart + j0 + (j0 + w) * ld, ld, c - j0 - w);                              // rest of the panel
-            for (i64 J = K + 1; J <= std::min(K + U, d->Nc - 1); ++J) {
-                if (d->c[J] == 0) continue;
-                if (!sky_has(d, K, J) || !sky_has(d, K1, J)) return bbm_fail(h, BBM_ERR_BAND, "BandError: the factors structure must have upper block bandwidth l+u");
-                piece(sky_start(d, K, J) + j0, d->S[J], d->c[J]);
-            }
-            ++nsteps;
+        const i64 rows = S - j0;
+        // the columns the next step factorises: block column Kn, [j0n, j0n + wn) -- always a prefix of one piece below
+        const i64 Kn = si + 1 < slabs.size() ? slabs[si + 1].K : -1, wn = si + 1 < slabs.size() ? slabs[si + 1].w : 0;
+        const int par = (int)(nsteps & 1);
+        steps.insert(steps.end(), {vstart + j0 + j0 * ld, ld, rows, w, d->C[K] + j0, (i64)par});
+        q.ptrW.push_back((int)bw.tiles.size());
+        q.ptrC.push_back((int)bc.tiles.size());
+        q.ptrWn.push_back((int)bwn.tiles.size());
+        q.ptrCn.push_back((int)bcn.tiles.size());
+        i64 woff = q.slotW[par];
+        auto part = [&](MmBatchHost& pw, MmBatchHost& pc, i64 cstart, i64 ldc, i64 cols) {   // rows x cols target with top-left at data[cstart]
+            if (cols <= 0) return;
+            for (i64 k0 = 0; k0 < rows; k0 += 64)                                           // W += YT[:, k-slice] C[k-slice, :]
+                pw.add(woff, w, w, cols, MmSeg{q.slotY[par] + k0 * w, w, cstart + k0, ldc, std::min<i64>(64, rows - k0)});
+            pc.add(cstart, ldc, rows, cols, MmSeg{q.slotV[par], rows, woff, w, w});       // C -= V W
+            woff += w * cols;
+        };
+        auto piece = [&](i64 J, i64 cstart, i64 ldc, i64 cols) {
+            const i64 ncols = J == Kn ? std::min(wn, cols) : 0;
+            part(bwn, bcn, cstart, ldc, ncols);
+            part(bw, bc, cstart + ncols * ldc, ldc, cols - ncols);
+        };
+        piece(K, vstart + j0 + (j0 + w) * ld, ld, c - j0 - w);                              // rest of the panel
+        for (i64 J = K + 1; J <= std::min(K + U, d->Nc - 1); ++J) {
+            if (d->c[J] == 0) continue;
+            if (!sky_has(d, K, J) || !sky_has(d, K1, J)) return bbm_fail(h, BBM_ERR_BAND, "BandError: the factors structure must have upper block bandwidth l+u");
+            piece(J, sky_start(d, K, J) + j0, d->S[J], d->c[J]);
         }
+        ++nsteps;
     }
     q.ptrW.push_back((int)bw.tiles.size());
     q.ptrC.push_back((int)bc.tiles.size());
+    q.ptrWn.push_back((int)bwn.tiles.size());
+    q.ptrCn.push_back((int)bcn.tiles.size());
     q.nsteps = nsteps;
     int32_t rc = upload(h, steps, &q.d_steps);
     if (rc == BBM_OK) rc = upload_batch(h, bw, &q.bW);
     if (rc == BBM_OK) rc = upload_batch(h, bc, &q.bC);
+    if (rc == BBM_OK) rc = upload_batch(h, bwn, &q.bWn);
+    if (rc == BBM_OK) rc = upload_batch(h, bcn, &q.bCn);
     if (rc != BBM_OK) return rc;
     q.built = true;
     return BBM_OK;
@@ -2431,13 +2453,41 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
     BBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
     const unsigned nthreads = q.variant != 0 ? 512 : kQrThreads;
+    // Look-ahead ("qr.lookahead", default on): only the columns the NEXT step factorises are updated on the main
+    // stream, in front of that step; the rest of the update (two launches over all the trailing blocks) runs on a second
+    // stream beside the next panel step, which occupies one SM.
+    //   main  : P(t) ........ wait R(t-1) . Wn(t) Cn(t) . P(t+1) ...
+    //   side  :      wait P(t) . Wr(t) Cr(t) -> R(t)
+    // R(t-1) updated the columns Wn(t)/Cn(t) touch, hence the wait; P(t+2) reuses the workspace slots R(t) reads and
+    // is ordered behind it through the same wait one step later.
+    const bool look = bbm_opt(h, "qr.lookahead", 1) != 0;
+    if (look) {
+        if (!h->side_stream) {
+            int lo = 0, hi = 0;
+            BBM_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            BBM_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo));
+            for (int i = 0; i < 2; ++i) BBM_CUDA(h, cudaEventCreateWithFlags(&h->side_ev[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < 4; ++i)
+            if (!h->qr_ev[i]) BBM_CUDA(h, cudaEventCreateWithFlags(&h->qr_ev[i], cudaEventDisableTiming));
+    }
     for (i64 t = 0; t < q.nsteps; ++t) {
         kern<<<1, nthreads, smem, h->stream>>>(d_data, d_tau, q.d_steps, t, WS, q.slotV[0], q.slotV[1], q.slotY[0], q.slotY[1], q.slotW[0], q.slotW[1], q.wlen);
         h->launches += 1;
-        rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
-        if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
+        if (look) {
+            BBM_CUDA(h, cudaEventRecord(h->qr_ev[t & 1], h->stream));
+            if (t > 0) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->qr_ev[2 + ((t - 1) & 1)], 0));
+        }
+        rc = launch_mm64(h, q.bWn, q.ptrWn[t], q.ptrWn[t + 1] - q.ptrWn[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bCn, q.ptrCn[t], q.ptrCn[t + 1] - q.ptrCn[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
+        cudaStream_t rs = look ? h->side_stream : h->stream;
+        if (look) BBM_CUDA(h, cudaStreamWaitEvent(rs, h->qr_ev[t & 1], 0));
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl, rs);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl, rs);
+        if (look) BBM_CUDA(h, cudaEventRecord(h->qr_ev[2 + (t & 1)], rs));
         if (rc != BBM_OK) return rc;
     }
+    if (look && q.nsteps > 0) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->qr_ev[2 + ((q.nsteps - 1) & 1)], 0));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "sky_qr_panel_kernel: %s", cudaGetErrorString(e));
     return BBM_OK;
@@ -2863,7 +2913,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
     if (d->d_titems) cudaFree(d->d_titems);
     if (d->d_struct) cudaFree(d->d_struct);
     if (d->qrf.d_steps) cudaFree(d->qrf.d_steps);
-    free_batch(d->qrf.bW); free_batch(d->qrf.bC);
+    free_batch(d->qrf.bW); free_batch(d->qrf.bC); free_batch(d->qrf.bWn); free_batch(d->qrf.bCn);
     if (d->qr.d_pan) cudaFree(d->qr.d_pan);
     if (d->qr.d_blk) cudaFree(d->qr.d_blk);
     free_batch(d->qr.gram); free_batch(d->qr.ytb); free_batch(d->qr.stepW); free_batch(d->qr.stepB);

@@ -465,24 +465,27 @@ def test_block_banded_qr_factorisation_on_device(handle, rows, cols, l, u):
         assert relerr(Ad @ x, b) <= tol(np.float64, max(rows) * (2 * l + u + 1)) * max(1.0, np.linalg.cond(Ad))
 
 
-@pytest.mark.parametrize("panel", [0, 1])
+@pytest.mark.parametrize("panel,lookahead", [(0, 1), (0, 0), (1, 1)])
 @pytest.mark.parametrize("rows,l,u", [([256] * 4, 1, 1),              # 512-row slabs: 32 warps x 16 rows per lane
                                       ([280, 260, 300], 2, 1),        # 840-row slabs: 16 warps x 32 rows per lane
                                       ([600, 500, 90], 1, 1),         # 1100-row slabs: shared-memory slab kernel
                                       ([37, 5, 64, 129], 1, 2)])
-def test_block_banded_qr_panel_kernels(handle, rows, l, u, panel):
+def test_block_banded_qr_panel_kernels(handle, rows, l, u, panel, lookahead):
     """Every panel-step kernel of qr! (register-resident slabs of <= 512 / <= 1024 rows, shared-memory slab; option
-    qr.panel = 1 forces the latter) gives LAPACK's factors and tau (test/test_blockskylineqr.jl:19-20)."""
+    qr.panel = 1 forces the latter), with and without the look-ahead split of the trailing update (qr.lookahead), gives
+    LAPACK's factors and tau (test/test_blockskylineqr.jl:19-20)."""
     rng = np.random.default_rng(74)
     m = sum(rows)
     A = B.BlockSkylineMatrix(F.sky_from_dense(rng.standard_normal((m, m)) + 3.0 * np.eye(m), rows, rows, l, u), rows, rows, l, u)
     Aw = A.with_bandwidths(l, l + u)
     handle.set_option("qr.panel", panel)
+    handle.set_option("qr.lookahead", lookahead)
     try:
         Fd = B.qr_(Aw.to_device(handle))
         got, tau = Fd.factors.data.to_host(), Fd.tau.to_host()
     finally:
         handle.set_option("qr.panel", 0)
+        handle.set_option("qr.lookahead", 1)
     h, t = np.linalg.qr(A.to_dense(), mode="raw")
     fac = F.sky_to_dense(got, rows, rows, l, l + u)
     assert np.abs(fac - h.T).max() <= 1e-12 * np.abs(h).max()
