@@ -247,6 +247,82 @@ def run_cfg4(torch, B, h, stream, reps, oracle, nblk=2048, bs=256, peak_tf=None,
     return out
 
 
+def sgemm_simt_peak(torch, n=8192, reps=5):
+    """cuBLAS FP32 GEMM with TF32 switched off (FFMA, exact single-precision products) = what a Float32 block product
+    that has to agree with the reference's sgemm can be compared with."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        a = torch.randn(n, n, device="cuda", dtype=torch.float32)
+        b = torch.randn(n, n, device="cuda", dtype=torch.float32)
+        c = torch.empty_like(a)
+        for _ in range(2):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_cfg4_f32(torch, B, h, stream, reps, nblk=2048, bs=256):
+    """cfg4's structure in Float32 (`sky_gemm_simt_kernel<float>`: FFMA, no tensor cores -- single-precision products
+    are exact only on the SIMT pipe or through a 3 x TF32 split): throughput against the same-run cuBLAS SGEMM (TF32 off)
+    and the nominal FP32 FFMA peak; sampled blocks against float64 block products."""
+    rows = [bs] * nblk
+    gen = torch.Generator(device="cuda").manual_seed(1004)
+    nA = B.BlockSkylineMatrix.numentries(rows, rows, 2, 2)
+    nC = B.BlockSkylineMatrix.numentries(rows, rows, 4, 4)
+    a_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float32) / 16
+    b_t = torch.randn(nA, generator=gen, device="cuda", dtype=torch.float32) / 16
+    c_t = torch.full((nC,), float("nan"), device="cuda", dtype=torch.float32)
+    A = B.BlockSkylineMatrix(wrap(B, h, a_t), rows, rows, 2, 2)
+    Bm = B.BlockSkylineMatrix(wrap(B, h, b_t), rows, rows, 2, 2)
+    Cm = B.BlockSkylineMatrix(wrap(B, h, c_t), rows, rows, 4, 4)
+    avg, best = time_gpu(torch, stream, lambda: B.mul_(Cm, A, Bm), reps, warm=2)
+    triples = 0
+    for J in range(nblk):
+        for N in range(max(0, J - 2), min(nblk - 1, J + 2) + 1):
+            triples += min(nblk - 1, N + 2) - max(0, N - 2) + 1
+    flops = 2.0 * bs ** 3 * triples
+    peak = sgemm_simt_peak(torch)
+    props = torch.cuda.get_device_properties(0)
+    nominal = props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
+    tf = flops / (avg * 1e-3) / 1e12
+    out = {"config": f"cfg4 in Float32: BlockBandedMatrix {nblk} blocks of {bs}, (2,2) x (2,2) -> (4,4)", "ms_avg": avg, "ms_min": best,
+           "TFLOPs": tf, "tolerance": 64 * EPS[4] * 5 * bs,
+           "roofline": {"bound": "fp32 simt", "peak_TFLOPs": peak, "peak_source": "torch.matmul float32 8192^3 with allow_tf32 = False (cuBLAS SGEMM) measured in this run",
+                        "frac": tf / peak, "nominal_ffma_TFLOPs": nominal, "frac_of_nominal": tf / nominal}}
+    rng = np.random.default_rng(7)
+    h.synchronize()
+    worst = 0.0
+    for _ in range(6):
+        J = int(rng.integers(0, nblk))
+        K = int(rng.integers(max(0, J - 4), min(nblk - 1, J + 4) + 1))
+        ref = np.zeros((bs, bs))
+        for N in range(max(0, J - 2), min(nblk - 1, J + 2) + 1):
+            if abs(K - N) <= 2:
+                sa, la = A.block_start(K, N), int(A.block_strides[N])
+                sb, lb = Bm.block_start(N, J), int(Bm.block_strides[J])
+                Ab = a_t[sa:sa + la * bs].cpu().numpy().astype(np.float64).reshape((la, bs), order="F")[:bs]
+                Bb = b_t[sb:sb + lb * bs].cpu().numpy().astype(np.float64).reshape((lb, bs), order="F")[:bs]
+                ref += Ab @ Bb
+        sc, lc = Cm.block_start(K, J), int(Cm.block_strides[J])
+        got = c_t[sc:sc + lc * bs].cpu().numpy().astype(np.float64).reshape((lc, bs), order="F")[:bs]
+        worst = max(worst, relerr(got, ref) if np.linalg.norm(ref) else float(np.abs(got).max()))
+    out["rel_err_sampled_blocks_vs_float64"] = worst
+    out["nan_in_C"] = bool(torch.isnan(c_t).any().item())
+    out["parity_ok"] = bool(worst <= out["tolerance"] and not out["nan_in_C"])
+    return out
+
+
 def run_bbb_mm(torch, B, h, stream, reps, oracle, n=2048):
     """A*A for the 2-D Laplacian BandedBlockBandedMatrix (n blocks of size n): (1,1),(1,1)^2 -> (2,2),(2,2)."""
     rows = [n] * n
@@ -559,6 +635,8 @@ def main():
             print(json.dumps(run_bbb(torch, B, h, stream, "cfg3: BBB rows=cols=1:4000, (2,2),(2,2)", r, r, (2, 2), (2, 2), dt, args.reps, oracle)), flush=True)
     if "4" in want:
         print(json.dumps(run_cfg4(torch, B, h, stream, max(2, args.reps // 3), oracle, peak_tf=peak_tf)), flush=True)
+    if "4f32" in want:
+        print(json.dumps(run_cfg4_f32(torch, B, h, stream, max(2, args.reps // 3))), flush=True)
     if "bbbmm" in want:
         print(json.dumps(run_bbb_mm(torch, B, h, stream, args.reps, oracle)), flush=True)
     if "qr" in want:

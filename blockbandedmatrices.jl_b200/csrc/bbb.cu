@@ -1592,10 +1592,16 @@ int32_t bbb_matmul_impl(bbm_handle_t h, bbm_bbb_desc_t A, bbm_bbb_desc_t B, bbm_
             const size_t stage = sizeof(T) * ((size_t)3 * 258 * 9 + (size_t)256 * 9);
             const size_t sm = std::max(stage, smem);
             if (sm <= std::min<size_t>(h->smem_optin, 200 * 1024)) {
-                const unsigned grid = (unsigned)std::min<i64>(Cd->n_mm_items, (i64)h->num_sms * 8);
                 e = cudaFuncSetAttribute(bbb_matmul_staged_kernel<T, 3, 3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 // three CTAs of 74 KB only fit with the largest shared-memory carve-out (the default left room for two)
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(bbb_matmul_staged_kernel<T, 3, 3, 3, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                // exactly one wave of resident CTAs, each looping over its share of the column tiles: a grid of 8 CTAs per
+                // SM ran 2.67 waves of the 3 that fit, the last one a third empty ("bbb.mm_ctas_per_sm" overrides)
+                int occ = 0;
+                if (e == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bbb_matmul_staged_kernel<T, 3, 3, 3, 3>, 256, sm) != cudaSuccess) { cudaGetLastError(); occ = 0; }
+                const i64 cps = bbm_opt(h, "bbb.mm_ctas_per_sm", 0);
+                const i64 per_sm = cps > 0 ? cps : (occ > 0 ? occ : 8);
+                const unsigned grid = (unsigned)std::min<i64>(Cd->n_mm_items, (i64)h->num_sms * per_sm);
                 if (e == cudaSuccess) bbb_matmul_staged_kernel<T, 3, 3, 3, 3><<<grid, 256, sm, h->stream>>>(p, Cd->d_mm_items, Cd->n_mm_items);
                 if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "bbb_matmul_staged_kernel launch: %s", cudaGetErrorString(e));

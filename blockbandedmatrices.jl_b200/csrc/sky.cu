@@ -109,10 +109,9 @@ struct bbm_sky_desc {
         i64 nsteps = 0, maxrows = 0, ws_total = 0, wlen = 0;
         i64 slotV[2] = {0, 0}, slotY[2] = {0, 0}, slotW[2] = {0, 0};
         i64* d_steps = nullptr;              // per step: slab start, ld, rows, width, tau offset, parity
-        Tri::Batch bW, bC;                   // tiles of W = YT C and C -= V W on everything but the next slab's columns
-        std::vector<int> ptrW, ptrC;
-        Tri::Batch bWn, bCn;                 // the same on the columns the NEXT step factorises (look-ahead)
-        std::vector<int> ptrWn, ptrCn;
+        Tri::Batch bW, bC;                   // tiles of W = YT C and C -= V W; step t: [ptr[t], mid[t]) on the columns the NEXT
+        std::vector<int> ptrW, ptrC;         // step factorises (look-ahead), [mid[t], ptr[t+1]) on everything else
+        std::vector<int> midW, midC;
     } qrf;
     // device copy of the structure tables [off(Nc+1) | S(Nc) | klo(Nc) | khi(Nc) | R(Nr+1) | C(Nc+1)] for the
     // element-wise kernels of csrc/structadd.cu, uploaded on first use
@@ -2369,8 +2368,8 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
     q.wlen = (i64)q.nb * maxcols;
     q.ws_total = off;
     std::vector<i64> steps;
-    MmBatchHost bw, bc, bwn, bcn;
-    q.ptrW.clear(); q.ptrC.clear(); q.ptrWn.clear(); q.ptrCn.clear();
+    MmBatchHost bw, bc;
+    q.ptrW.clear(); q.ptrC.clear(); q.midW.clear(); q.midC.clear();
     struct Slab { i64 K, j0, w; };
     std::vector<Slab> slabs;
     for (i64 K = 0; K < P; ++K) {
@@ -2390,41 +2389,40 @@ int32_t build_qr_fact_plan(bbm_handle_t h, bbm_sky_desc_t d) {
         const i64 Kn = si + 1 < slabs.size() ? slabs[si + 1].K : -1, wn = si + 1 < slabs.size() ? slabs[si + 1].w : 0;
         const int par = (int)(nsteps & 1);
         steps.insert(steps.end(), {vstart + j0 + j0 * ld, ld, rows, w, d->C[K] + j0, (i64)par});
-        q.ptrW.push_back((int)bw.tiles.size());
-        q.ptrC.push_back((int)bc.tiles.size());
-        q.ptrWn.push_back((int)bwn.tiles.size());
-        q.ptrCn.push_back((int)bcn.tiles.size());
-        i64 woff = q.slotW[par];
-        auto part = [&](MmBatchHost& pw, MmBatchHost& pc, i64 cstart, i64 ldc, i64 cols) {   // rows x cols target with top-left at data[cstart]
-            if (cols <= 0) return;
-            for (i64 k0 = 0; k0 < rows; k0 += 64)                                           // W += YT[:, k-slice] C[k-slice, :]
-                pw.add(woff, w, w, cols, MmSeg{q.slotY[par] + k0 * w, w, cstart + k0, ldc, std::min<i64>(64, rows - k0)});
-            pc.add(cstart, ldc, rows, cols, MmSeg{q.slotV[par], rows, woff, w, w});       // C -= V W
-            woff += w * cols;
-        };
-        auto piece = [&](i64 J, i64 cstart, i64 ldc, i64 cols) {
-            const i64 ncols = J == Kn ? std::min(wn, cols) : 0;
-            part(bwn, bcn, cstart, ldc, ncols);
-            part(bw, bc, cstart + ncols * ldc, ldc, cols - ncols);
-        };
-        piece(K, vstart + j0 + (j0 + w) * ld, ld, c - j0 - w);                              // rest of the panel
-        for (i64 J = K + 1; J <= std::min(K + U, d->Nc - 1); ++J) {
-            if (d->c[J] == 0) continue;
-            if (!sky_has(d, K, J) || !sky_has(d, K1, J)) return bbm_fail(h, BBM_ERR_BAND, "BandError: the factors structure must have upper block bandwidth l+u");
-            piece(J, sky_start(d, K, J) + j0, d->S[J], d->c[J]);
+        // tiles of this step: first the part on the next slab's columns ([ptr[t], mid[t])), then the rest ([mid[t], ptr[t+1]))
+        for (int pass = 0; pass < 2; ++pass) {
+            (pass == 0 ? q.ptrW : q.midW).push_back((int)bw.tiles.size());
+            (pass == 0 ? q.ptrC : q.midC).push_back((int)bc.tiles.size());
+            i64 woff = q.slotW[par];
+            auto part = [&](bool emit, i64 cstart, i64 ldc, i64 cols) {   // rows x cols target with top-left at data[cstart]
+                if (cols <= 0) return;
+                if (emit) {
+                    for (i64 k0 = 0; k0 < rows; k0 += 64)                                       // W += YT[:, k-slice] C[k-slice, :]
+                        bw.add(woff, w, w, cols, MmSeg{q.slotY[par] + k0 * w, w, cstart + k0, ldc, std::min<i64>(64, rows - k0)});
+                    bc.add(cstart, ldc, rows, cols, MmSeg{q.slotV[par], rows, woff, w, w});   // C -= V W
+                }
+                woff += w * cols;
+            };
+            auto piece = [&](i64 J, i64 cstart, i64 ldc, i64 cols) {
+                const i64 ncols = J == Kn ? std::min(wn, cols) : 0;
+                part(pass == 0, cstart, ldc, ncols);
+                part(pass == 1, cstart + ncols * ldc, ldc, cols - ncols);
+            };
+            piece(K, vstart + j0 + (j0 + w) * ld, ld, c - j0 - w);                          // rest of the panel
+            for (i64 J = K + 1; J <= std::min(K + U, d->Nc - 1); ++J) {
+                if (d->c[J] == 0) continue;
+                if (!sky_has(d, K, J) || !sky_has(d, K1, J)) return bbm_fail(h, BBM_ERR_BAND, "BandError: the factors structure must have upper block bandwidth l+u");
+                piece(J, sky_start(d, K, J) + j0, d->S[J], d->c[J]);
+            }
         }
         ++nsteps;
     }
     q.ptrW.push_back((int)bw.tiles.size());
     q.ptrC.push_back((int)bc.tiles.size());
-    q.ptrWn.push_back((int)bwn.tiles.size());
-    q.ptrCn.push_back((int)bcn.tiles.size());
     q.nsteps = nsteps;
     int32_t rc = upload(h, steps, &q.d_steps);
     if (rc == BBM_OK) rc = upload_batch(h, bw, &q.bW);
     if (rc == BBM_OK) rc = upload_batch(h, bc, &q.bC);
-    if (rc == BBM_OK) rc = upload_batch(h, bwn, &q.bWn);
-    if (rc == BBM_OK) rc = upload_batch(h, bcn, &q.bCn);
     if (rc != BBM_OK) return rc;
     q.built = true;
     return BBM_OK;
@@ -2453,14 +2451,17 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
     BBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
     const unsigned nthreads = q.variant != 0 ? 512 : kQrThreads;
-    // Look-ahead ("qr.lookahead", default on): only the columns the NEXT step factorises are updated on the main
+    // Look-ahead ("qr.lookahead" = 1; default OFF): only the columns the NEXT step factorises are updated on the main
     // stream, in front of that step; the rest of the update (two launches over all the trailing blocks) runs on a second
     // stream beside the next panel step, which occupies one SM.
     //   main  : P(t) ........ wait R(t-1) . Wn(t) Cn(t) . P(t+1) ...
     //   side  :      wait P(t) . Wr(t) Cr(t) -> R(t)
     // R(t-1) updated the columns Wn(t)/Cn(t) touch, hence the wait; P(t+2) reuses the workspace slots R(t) reads and
-    // is ordered behind it through the same wait one step later.
-    const bool look = bbm_opt(h, "qr.lookahead", 1) != 0;
+    // is ordered behind it through the same wait one step later.  Measured (512 blocks of 256, (1,1)): 345 ms with,
+    // 336 ms without: a dependent launch costs ~10 us whether it carries 4 tiles or 90, so the two small launches left
+    // on the critical path cost what the two big ones did, and the events add host work.  Kept for wider trailing
+    // updates (large l + u), where the rest of the update is no longer launch-bound.
+    const bool look = bbm_opt(h, "qr.lookahead", 0) != 0;
     if (look) {
         if (!h->side_stream) {
             int lo = 0, hi = 0;
@@ -2478,13 +2479,19 @@ int32_t sky_qr_fact_impl(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, doubl
             BBM_CUDA(h, cudaEventRecord(h->qr_ev[t & 1], h->stream));
             if (t > 0) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->qr_ev[2 + ((t - 1) & 1)], 0));
         }
-        rc = launch_mm64(h, q.bWn, q.ptrWn[t], q.ptrWn[t + 1] - q.ptrWn[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
-        if (rc == BBM_OK) rc = launch_mm64(h, q.bCn, q.ptrCn[t], q.ptrCn[t + 1] - q.ptrCn[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
-        cudaStream_t rs = look ? h->side_stream : h->stream;
-        if (look) BBM_CUDA(h, cudaStreamWaitEvent(rs, h->qr_ev[t & 1], 0));
-        if (rc == BBM_OK) rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl, rs);
-        if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl, rs);
-        if (look) BBM_CUDA(h, cudaEventRecord(h->qr_ev[2 + (t & 1)], rs));
+        if (!look) {                                 // one W launch and one C launch over all the tiles of the step
+            rc = launch_mm64(h, q.bW, q.ptrW[t], q.ptrW[t + 1] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
+            if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.ptrC[t + 1] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
+            if (rc != BBM_OK) return rc;
+            continue;
+        }
+        rc = launch_mm64(h, q.bW, q.ptrW[t], q.midW[t] - q.ptrW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.ptrC[t], q.midC[t] - q.ptrC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl);
+        cudaStream_t rs = h->side_stream;
+        BBM_CUDA(h, cudaStreamWaitEvent(rs, h->qr_ev[t & 1], 0));
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bW, q.midW[t], q.ptrW[t + 1] - q.midW[t], WS, d_data, WS, 1.0, 1.0, true, t < 2, pdl, rs);
+        if (rc == BBM_OK) rc = launch_mm64(h, q.bC, q.midC[t], q.ptrC[t + 1] - q.midC[t], WS, WS, d_data, -1.0, 1.0, false, t < 2, pdl, rs);
+        BBM_CUDA(h, cudaEventRecord(h->qr_ev[2 + (t & 1)], rs));
         if (rc != BBM_OK) return rc;
     }
     if (look && q.nsteps > 0) BBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->qr_ev[2 + ((q.nsteps - 1) & 1)], 0));
@@ -2913,7 +2920,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
     if (d->d_titems) cudaFree(d->d_titems);
     if (d->d_struct) cudaFree(d->d_struct);
     if (d->qrf.d_steps) cudaFree(d->qrf.d_steps);
-    free_batch(d->qrf.bW); free_batch(d->qrf.bC); free_batch(d->qrf.bWn); free_batch(d->qrf.bCn);
+    free_batch(d->qrf.bW); free_batch(d->qrf.bC);
     if (d->qr.d_pan) cudaFree(d->qr.d_pan);
     if (d->qr.d_blk) cudaFree(d->qr.d_blk);
     free_batch(d->qr.gram); free_batch(d->qr.ytb); free_batch(d->qr.stepW); free_batch(d->qr.stepB);
