@@ -652,6 +652,144 @@ __global__ void __launch_bounds__(256) sky_gemm_simt_kernel(const MmParams<T> p)
     }
 }
 
+// Float32 product kernel.  Single-precision products that have to agree with the reference's sgemm need the FP32 FMA pipe
+// (tcgen05 kind::tf32 drops 13 mantissa bits; a 3 x TF32 split triples the tensor work and still differs in the last
+// bits), so this is a register-tiled SIMT GEMM: 128 x 128 tile, 256 threads x (8 x 8) accumulators, operands through a
+// 3-stage cp.async ring in the layouts global memory already has (A: rows contiguous, B: k contiguous), both read from
+// shared memory as float4 -- 16 LDS.128 per 256 FFMA.  The first version (64 x 64 tile, 4 x 4 per thread, synchronous
+// scalar loads: `sky_gemm_simt_kernel` above) ran cfg4's structure at 24.0 TFLOP/s = 0.375 of cuBLAS SGEMM.
+constexpr int kSgBM = 128, kSgBN = 128, kSgBK = 16, kSgStages = 3, kSgLDA = kSgBM + 4, kSgLDB = kSgBK + 4;
+constexpr size_t kSgSmem = (size_t)kSgStages * ((size_t)kSgBK * kSgLDA + (size_t)kSgBN * kSgLDB) * sizeof(float);
+
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes) : "memory");
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256, 2) sky_sgemm_simt_kernel(const MmParams<float> p) {
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    float* As = reinterpret_cast<float*>(mm_smem);                        // [stage][k][LDA]  (row index contiguous)
+    float* Bs = As + (size_t)kSgStages * kSgBK * kSgLDA;                  // [stage][n][LDB]  (k index contiguous)
+    const MmTile tile = p.tiles[blockIdx.x];
+    const MmCBlk cb = p.cblks[tile.cblk];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int row0 = tile.ti * kSgBM, col0 = tile.tj * kSgBN;
+    int pseg = cb.seg_begin;
+    i64 pk0 = 0;
+    int total = 0;
+    for (int s = cb.seg_begin; s < cb.seg_end; ++s) total += (int)((p.segs[s].kc + kSgBK - 1) / kSgBK);
+
+    auto load_chunk = [&](int stage) {
+        const MmSeg sg = p.segs[pseg];
+        float* as = As + (size_t)stage * kSgBK * kSgLDA;
+        float* bs = Bs + (size_t)stage * kSgBN * kSgLDB;
+        if (ALIGNED) {
+            for (int v = tid; v < (kSgBM / 4) * kSgBK; v += 256) {          // A: 4 consecutive rows of one k
+                const int kk = v / (kSgBM / 4), i = 4 * (v % (kSgBM / 4));
+                const int row = row0 + i;
+                int nv = cb.rK - row; nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
+                const int bytes = pk0 + kk < sg.kc ? 4 * nv : 0;
+                const float* src = bytes ? p.A + sg.astart + row + (pk0 + kk) * sg.lda : p.A;
+                cp_async16(as + kk * kSgLDA + i, src, bytes);
+            }
+            for (int v = tid; v < kSgBN * (kSgBK / 4); v += 256) {          // B: 4 consecutive k of one column
+                const int j = v / (kSgBK / 4), kk = 4 * (v % (kSgBK / 4));
+                const int col = col0 + j;
+                i64 nv = sg.kc - (pk0 + kk); nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
+                const int bytes = col < cb.cJ ? 4 * (int)nv : 0;
+                const float* src = bytes ? p.B + sg.bstart + (pk0 + kk) + (i64)col * sg.ldb : p.B;
+                cp_async16(bs + j * kSgLDB + kk, src, bytes);
+            }
+        } else {
+            for (int v = tid; v < kSgBM * kSgBK; v += 256) {
+                const int kk = v / kSgBM, i = v % kSgBM;
+                const int row = row0 + i;
+                const int bytes = (row < cb.rK && pk0 + kk < sg.kc) ? 4 : 0;
+                const float* src = bytes ? p.A + sg.astart + row + (pk0 + kk) * sg.lda : p.A;
+                cp_async4(as + kk * kSgLDA + i, src, bytes);
+            }
+            for (int v = tid; v < kSgBN * kSgBK; v += 256) {
+                const int j = v / kSgBK, kk = v % kSgBK;
+                const int col = col0 + j;
+                const int bytes = (col < cb.cJ && pk0 + kk < sg.kc) ? 4 : 0;
+                const float* src = bytes ? p.B + sg.bstart + (pk0 + kk) + (i64)col * sg.ldb : p.B;
+                cp_async4(bs + j * kSgLDB + kk, src, bytes);
+            }
+        }
+        pk0 += kSgBK;
+        if (pk0 >= sg.kc) { pk0 = 0; ++pseg; }
+    };
+
+    // thread (tx, ty): rows {4 tx .. 4 tx + 3} and {64 + 4 tx ..}, columns {4 ty ..} and {64 + 4 ty ..}
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    int issued = 0;
+    for (; issued < kSgStages - 1; ++issued) {
+        if (issued < total) load_chunk(issued % kSgStages);
+        cp_async_commit();
+    }
+    for (int c = 0; c < total; ++c) {
+        cp_async_wait<kSgStages - 2>();
+        __syncthreads();
+        if (issued < total) load_chunk(issued % kSgStages);    // refills the stage everybody left before this barrier
+        cp_async_commit();
+        ++issued;
+        const float* as = As + (size_t)(c % kSgStages) * kSgBK * kSgLDA;
+        const float* bs = Bs + (size_t)(c % kSgStages) * kSgBN * kSgLDB;
+#pragma unroll
+        for (int k4 = 0; k4 < kSgBK; k4 += 4) {
+            float4 b4[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b4[j] = *reinterpret_cast<const float4*>(bs + ((j < 4 ? 0 : 64) + 4 * ty + (j & 3)) * kSgLDB + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(as + (k4 + kk) * kSgLDA + 4 * tx);
+                const float4 a1 = *reinterpret_cast<const float4*>(as + (k4 + kk) * kSgLDA + 64 + 4 * tx);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float b = kk == 0 ? b4[j].x : kk == 1 ? b4[j].y : kk == 2 ? b4[j].z : b4[j].w;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(a[i], b, acc[i][j]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    const float alpha = p.alpha, beta = p.beta;
+    const bool vec = ((cb.cstart | cb.ldc) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = col0 + (j < 4 ? 0 : 64) + 4 * ty + (j & 3);
+        if (col >= cb.cJ) continue;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = row0 + 64 * h2 + 4 * tx;
+            float* cp = p.C + cb.cstart + row + (i64)col * cb.ldc;
+            if (vec && row + 3 < cb.rK) {
+                float4 v = make_float4(alpha * acc[4 * h2][j], alpha * acc[4 * h2 + 1][j], alpha * acc[4 * h2 + 2][j], alpha * acc[4 * h2 + 3][j]);
+                if (beta != 0.0f) {
+                    const float4 o = *reinterpret_cast<const float4*>(cp);
+                    v.x = fmaf(beta, o.x, v.x); v.y = fmaf(beta, o.y, v.y); v.z = fmaf(beta, o.z, v.z); v.w = fmaf(beta, o.w, v.w);
+                }
+                *reinterpret_cast<float4*>(cp) = v;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (row + i < cb.rK) {
+                        float v = alpha * acc[4 * h2 + i][j];
+                        if (beta != 0.0f) v = fmaf(beta, cp[i], v);
+                        cp[i] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 struct bbm_sky_desc::MmPlan {
@@ -661,6 +799,7 @@ struct bbm_sky_desc::MmPlan {
     int ntiles[2] = {0, 0};
     int ninterior[2] = {0, 0};                // leading tiles whose product segments only use owned block rows of B
     bool aligned = false;
+    bool aligned4 = false;                    // all operand offsets and strides multiples of 4 elements (16 bytes of Float32)
     bool full128 = false;                     // every C block a multiple of 128 x 128, inner dimensions multiples of 32, 16-byte strides
     double flops = 0;
 };
@@ -696,7 +835,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
     std::vector<MmSeg> segs;
     std::vector<MmTile> tiles[2], btiles[2];
     const int tsz[2] = {128, 64};
-    bool aligned = true, full128 = true;
+    bool aligned = true, aligned4 = true, full128 = true;
     double flops = 0;
     for (i64 J = 0; J < Cd->Nc; ++J) {
         if (Cd->c[J] == 0) continue;
@@ -712,6 +851,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
                 interior = interior && N >= own_lo && N < own_hi;
                 MmSeg sg{sky_start(A, K, N), A->S[N], sky_start(B, N, J), B->S[J], A->c[N]};
                 aligned = aligned && !(sg.astart & 1) && !(sg.lda & 1) && !(sg.bstart & 1) && !(sg.ldb & 1);
+                aligned4 = aligned4 && !(sg.astart & 3) && !(sg.lda & 3) && !(sg.bstart & 3) && !(sg.ldb & 3);
                 full128 = full128 && sg.kc % 32 == 0 && cb.rK % 128 == 0 && cb.cJ % 128 == 0;
                 flops += 2.0 * (double)cb.rK * (double)cb.cJ * (double)sg.kc;
                 segs.push_back(sg);
@@ -733,7 +873,7 @@ int32_t build_mm_plan(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_sk
         return bbm_fail(h, BBM_ERR_UNSUPPORTED, "product plan too large");
     auto* pl = new (std::nothrow) bbm_sky_desc::MmPlan();
     if (!pl) return bbm_fail(h, BBM_ERR_ALLOC, "out of host memory");
-    pl->aligned = aligned; pl->flops = flops; pl->full128 = full128 && aligned;
+    pl->aligned = aligned; pl->aligned4 = aligned4; pl->flops = flops; pl->full128 = full128 && aligned;
     pl->ninterior[0] = ninterior[0]; pl->ninterior[1] = ninterior[1];
     int32_t rc = upload(h, cblks, &pl->d_cblks);
     if (rc == BBM_OK) rc = upload(h, segs, &pl->d_segs);
@@ -791,6 +931,15 @@ int32_t sky_matmul_impl(bbm_handle_t h, bbm_sky_desc_t A, bbm_sky_desc_t B, bbm_
         } else if (al && bk32) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 32, true>, mm_smem_bytes<128, 128, 32>());
         else if (al) go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, true>, mm_smem_bytes<128, 128, 16>());
         else go(sky_dgemm_dmma_kernel<128, 128, 64, 32, 16, false>, mm_smem_bytes<128, 128, 16>());
+    } else if (sizeof(T) == 4 && force != 2 && bbm_opt(h, "sky.mm_f32_kernel", 0) == 0) {
+        MmParams<float> pf{(const float*)dA, (const float*)dB, (float*)dC, pl->d_cblks, pl->d_segs, pl->d_tiles[0] + t0[0], (float)alpha, (float)beta};
+        const bool al = pl->aligned4 && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % 16 == 0);
+        auto go = [&](auto kern) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSgSmem);
+            if (e == cudaSuccess) { kern<<<nt[0], 256, kSgSmem, h->stream>>>(pf); e = cudaGetLastError(); }
+        };
+        if (al) go(sky_sgemm_simt_kernel<true>);
+        else go(sky_sgemm_simt_kernel<false>);
     } else {
         p.tiles = pl->d_tiles[1] + t0[1];
         sky_gemm_simt_kernel<T><<<nt[1], 256, 0, h->stream>>>(p);

@@ -143,6 +143,41 @@ def test_sky_matmul_matches_oracle(handle, case, dtype, kernel):
         handle.set_option("sky.mm_kernel", 0)
 
 
+@pytest.mark.parametrize("f32_kernel", [0, 1], ids=["register-tiled", "first-version"])
+@pytest.mark.parametrize("rows", [[128, 256, 384, 128, 256, 128], [132, 60, 260, 4, 96, 200], [100, 37, 250, 129, 3, 64]],
+                         ids=["full-tiles", "16-byte-aligned-ragged", "unaligned-ragged"])
+def test_sky_matmul_float32_kernels(handle, rows, f32_kernel):
+    """Float32 products (both SIMT kernels; 16-byte cp.async path and element-wise path; tiles cut by the block edges; several
+    k-chunks and product segments per tile; alpha/beta; a wider C; ragged per-column bandwidths) against the oracle."""
+    cases = [((1, 2), (2, 1), None), ((1, 1), (1, 1), (3, 3)), (([1, 0, 2, 1, 0, 1], [0, 1, 1, 2, 1, 0]), ([0, 1, 1, 0, 2, 1], [1, 1, 0, 1, 1, 2]), None)]
+    handle.set_option("sky.mm_f32_kernel", f32_kernel)
+    try:
+        for (la, ua), (lb, ub), wide in cases:
+            rng = np.random.default_rng(15)
+            adata, bdata = random_sky(rng, rows, rows, la, ua, np.float32), random_sky(rng, rows, rows, lb, ub, np.float32)
+            A = B.BlockSkylineMatrix(adata, rows, rows, la, ua)
+            Bm = B.BlockSkylineMatrix(bdata, rows, rows, lb, ub)
+            if wide is None:
+                ol, ou = F.add_bandwidths(A.l, A.u, Bm.l, Bm.u, constant=A.constant_bandwidths and Bm.constant_bandwidths)
+            else:
+                ol, ou = wide
+            n = B.BlockSkylineMatrix.numentries(rows, rows, ol, ou)
+            c0 = rng.standard_normal(n).astype(np.float32)
+            for alpha, beta in ((1.0, 0.0), (-1.5, 0.75)):
+                cin = c0.copy()
+                if beta == 0:
+                    cin[:] = np.nan
+                Cd = B.BlockSkylineMatrix(handle.to_device(cin), rows, rows, ol, ou)
+                B.mul_(Cd, A.to_device(handle), Bm.to_device(handle), alpha, beta)
+                ref = c0.copy()
+                O.sky_matmul((rows, rows, la, ua), (rows, rows, lb, ub), (rows, rows, ol, ou), alpha, adata, bdata, beta, ref)
+                got = Cd.data.to_host()
+                assert not np.isnan(got).any()
+                assert relerr(got, ref) <= tol(np.float32, 3 * max(rows))
+    finally:
+        handle.set_option("sky.mm_f32_kernel", 0)
+
+
 @pytest.mark.parametrize("ws", [1, 0], ids=["bulk-copy-pipeline", "cp.async"])
 def test_sky_matmul_full_tiles_warp_specialised(handle, ws):
     """Blocks that are multiples of 128 with 16-byte-aligned panels take the warp-specialised DMMA kernel (one producer thread
