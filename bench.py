@@ -183,6 +183,29 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def bind_near_gpu(torch, local_rank):
+    """N > 1: keep this rank's host threads -- and, through first-touch page placement, its pinned staging buffers -- on
+    the CPUs NVML reports as nearest to the rank's GPU (what `numactl --cpunodebind --membind` per rank does on a
+    multi-socket box: without it the pinned buffers of all ranks may sit on one socket and every copy of the other
+    socket's GPUs crosses the inter-socket link).  Best effort: returns the CPU list, or None if anything is missing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        hdl = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        ncpu = os.cpu_count() or 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        near = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus = sorted(near & os.sched_getaffinity(0))
+        if not cpus or len(cpus) == len(os.sched_getaffinity(0)):
+            return None          # one NUMA node (or a cpuset that hides the topology): nothing to do
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def run_ours(args):
     # Libraries (NCCL's version banner, for one) write to fd 1: keep stdout for the ONE JSON line by
     # pointing fd 1 at stderr until the result is printed.
@@ -202,6 +225,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    args.near_cpus = bind_near_gpu(torch, local_rank) if world > 1 else None
     if world > 1:
         # NCCL_DEBUG=VERSION/INFO banners go to stdout by default: keep stdout for the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -573,7 +597,9 @@ def bench_distributed(args, torch, dist, B, h, stream, nb, block, rank, world, l
         "e2e": {"value": nbytes / e2e_s / 1e9, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "steps": Ke,
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                 "call": ("bbm_dist_bbb_mul_host_f64 (pinned x_own up, halo exchange, product and y_own down pipelined over block-row chunks), per rank"
-                         if host_call else "bbm_memcpy_h2d(x_own) + bbm_dist_bbb_mul_f64 + bbm_memcpy_d2h(y_own), per rank")},
+                         if host_call else "bbm_memcpy_h2d(x_own) + bbm_dist_bbb_mul_f64 + bbm_memcpy_d2h(y_own), per rank"),
+                "host_affinity": (f"rank 0 bound to the {len(args.near_cpus)} CPUs NVML reports nearest to its GPU (pinned buffers first-touched there); every rank does the same"
+                                  if getattr(args, "near_cpus", None) else "none (one NUMA node, or the topology is not visible)")},
         "gpu_launches": int(lt.item()),
         "roofline": {"bound": "hbm", "kernel": "bbb_walk_kernel<double,3,3> (per rank, incl. halo push / exchange)",
                      "achieved": value, "peak": None, "unit": UNIT, "frac": None, "traffic": None,
