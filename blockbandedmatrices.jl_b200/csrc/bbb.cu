@@ -66,6 +66,7 @@ struct bbm_bbb_desc {
         int elem = 0, nr = 0, peer = 0, own_J0 = 0, own_J1 = 0, force = 0;
         bool walk = false;
         int tile = 0, stages = 0, dbytes = 0, xbytes = 0, maxseg = 0, nitems = 0, pdl = 0, l2hint = 1;
+        float l2keep = 0.0f;
         const BbbItem* d_items = nullptr;
         size_t smem = 0;
         int consumers[2] = {0, 0};
@@ -107,6 +108,7 @@ struct BbbParams {
     int nrhs;              // right-hand sides (multi-vector kernel); keep new fields at the END: ptxas' code for the
                            // single-vector kernel proved sensitive to the parameter layout (5 % on cfg2)
     int pdl_early;         // != 0: release the dependent launch at the first step instead of the last one
+    float l2keep;          // > 0: this fraction of the matrix lines is kept in L2 with priority ("bbb.l2keep_pct")
 };
 
 template <typename T> __device__ __forceinline__ T bbm_nan();
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256) bbb_walk_kernel(const BbbParams<T> p) {
 
     uint64_t pol_stream = 0, pol_keep = 0;
     if (tid == 0 && p.l2hint) {
-        pol_stream = ptx::policy_evict_first();
+        pol_stream = p.l2keep > 0.0f ? ptx::policy_keep_fraction(p.l2keep) : ptx::policy_evict_first();
         pol_keep = ptx::policy_evict_last();
     }
 
@@ -911,6 +913,9 @@ int32_t build_walk_plan(bbm_handle_t h, bbm_bbb_desc_t d, int nr, bbm_bbb_desc::
     const i64 force = bbm_opt(h, "bbb.kernel", 0);
     plan->walk = false;
     plan->l2hint = (int)bbm_opt(h, "bbb.l2hint", 1);
+    // "bbb.l2keep_pct" (default 0 = stream the matrix): for back-to-back products with a matrix not much larger than L2
+    // (an iterative solver on one rank's shard), keep that percentage of its lines resident across products
+    plan->l2keep = (float)std::min<i64>(100, std::max<i64>(0, bbm_opt(h, "bbb.l2keep_pct", 0))) / 100.0f;
     bool walk = d->P > 0 && NS >= 1 && NS <= kMaxNS && force != 2;
     // tiny blocks leave the 32..256-row tiles mostly idle: use the per-row kernel
     if (walk && force != 1 && d->m < 16 * d->Nr && !h->peer) walk = false;
@@ -1067,6 +1072,7 @@ int32_t bbb_mul_impl(bbm_handle_t h, bbm_bbb_desc_t d, T alpha, const T* d_data,
         p.stage_data_bytes = plan->dbytes;
         p.stage_x_bytes = nr * plan->xbytes;
         p.pdl_early = plan->pdl == 2 ? 1 : 0;
+        p.l2keep = plan->l2keep;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)plan->nitems + (h->peer ? 1u : 0u), (unsigned)((nrhs + nr - 1) / nr), 1);
         cfg.blockDim = dim3((unsigned)plan->tile);

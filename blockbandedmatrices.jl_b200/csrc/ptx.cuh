@@ -49,6 +49,13 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// a fixed, address-selected fraction of the lines is kept with priority (evict_last), the rest is streamed (evict_first):
+// the part of a matrix that fits L2 stays there across back-to-back products
+__device__ __forceinline__ uint64_t policy_keep_fraction(float fraction) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(fraction));
+    return pol;
+}
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
