@@ -96,6 +96,11 @@ struct bbm_sky_desc {
         i64 step_ldb = -1, step_nrhs = -1, step_ldw = -1;
         Tri::Batch stepW, stepB;             // the sweep; tiles of panel K are [ptr[K], ptr[K+1])
         std::vector<int> ptrW, ptrB;
+        // data-flow sweep: the same two products per panel as tiles of ONE persistent kernel (the solve's sky_trsm_flow_kernel)
+        void* flow_tiles = nullptr;
+        i64 flow_ntiles = 0, flow_nctr = 0, flow_ldb = -1, flow_nrhs = -1, flow_ldw = -1;
+        int* flow_ctr = nullptr;
+        bool flow_ok = false;
     } qr;
     // descriptor of the row-and-column reversed matrix (its storage is the reversed `data`), for the QL calls
     bbm_sky_desc* rev = nullptr;
@@ -1779,10 +1784,10 @@ int32_t tri_condition(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
     return BBM_OK;
 }
 
-int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const double* d_data, const double* W, double* d_B, double* X) {
-    bbm_sky_desc::Tri& t = d->tri[upper];
-    const i64 N = d->Nr;
-    const bool bk128 = t.flow_bk == 128;
+// One cooperative launch of the data-flow kernel over a tile list: static operands of kind-0 / kind-1 tiles from A0 / A1,
+// dynamic operands and destinations Bm and X (kind 0: A0 * Bm -> X, +; kind 1: A1 * X -> Bm, -).
+int32_t launch_flow(bbm_handle_t h, const void* flow_tiles, i64 flow_ntiles, int* flow_ctr, i64 flow_nctr, bool bk128,
+                    const double* A1, const double* A0, double* Bm, double* X) {
     const void* func = bk128 ? reinterpret_cast<const void*>(sky_trsm_flow_kernel<128>) : reinterpret_cast<const void*>(sky_trsm_flow_kernel<64>);
     const size_t smem = bk128 ? flow_smem_bytes<128>() : flow_smem_bytes<64>();
     cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1791,19 +1796,24 @@ int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const doub
     if (e != cudaSuccess || occ < 1) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "data-flow solve: occupancy query failed"); }
     const i64 cap = bbm_opt(h, "trsm.flow_ctas_per_sm", 0);
     if (cap > 0) occ = (int)std::min<i64>(occ, cap);
-    const i64 grid = std::min<i64>(t.flow_ntiles, (i64)occ * h->num_sms);
-    BBM_CUDA(h, cudaMemsetAsync(t.flow_ctr, 0, sizeof(int) * (size_t)(t.flow_nctr + 1), h->stream));
-    const FlowTile* tiles = static_cast<const FlowTile*>(t.flow_tiles);
-    i64 ntiles = t.flow_ntiles;
-    int* ctr = t.flow_ctr;
-    int err_idx = (int)t.flow_nctr;
+    const i64 grid = std::min<i64>(flow_ntiles, (i64)occ * h->num_sms);
+    BBM_CUDA(h, cudaMemsetAsync(flow_ctr, 0, sizeof(int) * (size_t)(flow_nctr + 1), h->stream));
+    const FlowTile* tiles = static_cast<const FlowTile*>(flow_tiles);
+    i64 ntiles = flow_ntiles;
+    int* ctr = flow_ctr;
+    int err_idx = (int)flow_nctr;
     int sleep_ns = (int)std::max<i64>(0, bbm_opt(h, "trsm.flow_sleep_ns", 32));
-    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&d_data, (void*)&W, (void*)&d_B, (void*)&X, (void*)&ctr, (void*)&err_idx, (void*)&sleep_ns};
+    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&A1, (void*)&A0, (void*)&Bm, (void*)&X, (void*)&ctr, (void*)&err_idx, (void*)&sleep_ns};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident (the tiles wait for one another)
     e = cudaLaunchCooperativeKernel(func, dim3((unsigned)grid), dim3(128), args, smem, h->stream);
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "sky_trsm_flow_kernel launch: %s", cudaGetErrorString(e)); }
     h->launches += 1;
     return BBM_OK;
+}
+
+int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const double* d_data, const double* W, double* d_B, double* X) {
+    bbm_sky_desc::Tri& t = d->tri[upper];
+    return launch_flow(h, t.flow_tiles, t.flow_ntiles, t.flow_ctr, t.flow_nctr, t.flow_bk == 128, d_data, W, d_B, X);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2022,6 +2032,70 @@ int32_t build_qr_step_plan(bbm_handle_t h, bbm_sky_desc_t d, i64 ldb, i64 ldw, i
     return BBM_OK;
 }
 
+// The sweep of lmul!(Q', B) as a tile list for the data-flow kernel (see sky_trsm_flow_kernel): per panel K
+//     W_K        += YT_K[i-tile, k-slice] * B[R_K + k-slice, j-tile]      (kind 0; waits until that 64-row slice of B has
+//                                                                          received every update of the panels before K)
+//     B[R_K + i] -= V_K[i-tile, k-slice]  * W_K[k-slice, j-tile]          (kind 1; waits until ALL of W_K is complete: the
+//                                                                          panel's rows of B are both read by its W tiles
+//                                                                          and written by its update tiles)
+// A 64-row slice of B is read by up to l+1 panels, each after a different number of updates: the counters are cumulative and
+// every tile carries its own threshold.  Needs block sizes that are multiples of 64 (slices = tiles) and even strides.
+int32_t build_qr_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, i64 ldb, i64 ldw, i64 nrhs) {
+    bbm_sky_desc::Qr& q = d->qr;
+    if (q.flow_ldb == ldb && q.flow_nrhs == nrhs && q.flow_ldw == ldw && q.flow_ctr) return BBM_OK;
+    if (q.flow_tiles) { cudaFree(q.flow_tiles); q.flow_tiles = nullptr; }
+    if (q.flow_ctr) { cudaFree(q.flow_ctr); q.flow_ctr = nullptr; }
+    q.flow_ldb = ldb; q.flow_nrhs = nrhs; q.flow_ldw = ldw; q.flow_ok = false;
+    bool ok = !(ldb & 1) && !(ldw & 1);
+    for (i64 K = 0; K < d->Nr && ok; ++K) ok = d->r[K] % kFlowBM == 0;
+    for (i64 J = 0; J < d->Nc && ok; ++J) ok = d->c[J] % kFlowBM == 0;
+    const i64 P = q.ncols;
+    const i64 nrow = d->m / kFlowBM;                            // counters: 64-row slices of B, then one per panel (W_K complete)
+    if (!ok || nrow + P + 1 >= (i64)INT32_MAX) {
+        cudaError_t e0 = cudaMalloc(&q.flow_ctr, sizeof(int));   // (marks the plan as built for these strides)
+        if (e0 != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e0)); }
+        return BBM_OK;
+    }
+    std::vector<FlowTile> tiles;
+    std::vector<int> landed(nrow, 0);                           // update tiles that target a slice of B so far
+    const i64 njt = (nrhs + kFlowBN - 1) / kFlowBN;
+    for (i64 K = 0; K < P; ++K) {
+        const i64 c = d->c[K], S = q.srows[K];
+        if (c == 0 || S == 0) continue;
+        const i64 r0 = d->R[K] / kFlowBM;
+        for (i64 i0 = 0; i0 < c; i0 += kFlowBM)
+            for (i64 k0 = 0; k0 < S; k0 += kFlowBM)
+                for (i64 j0 = 0; j0 < nrhs; j0 += kFlowBN)
+                    tiles.push_back(FlowTile{q.yt[K] + i0 + k0 * c, c, d->R[K] + k0 + j0 * ldb, ldb, d->C[K] + i0 + j0 * ldw, ldw,
+                                             (int32_t)kFlowBM, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kFlowBM, 0,
+                                             (int32_t)(r0 + k0 / kFlowBM), landed[r0 + k0 / kFlowBM], (int32_t)(nrow + K), 0});
+        const int wdone = (int)((c / kFlowBM) * (S / kFlowBM) * njt);   // all W tiles of the panel
+        for (i64 i0 = 0; i0 < S; i0 += kFlowBM) {
+            for (i64 k0 = 0; k0 < c; k0 += kFlowBM)
+                for (i64 j0 = 0; j0 < nrhs; j0 += kFlowBN)
+                    tiles.push_back(FlowTile{q.vc[K] + i0 + k0 * S, S, d->C[K] + k0 + j0 * ldw, ldw, d->R[K] + i0 + j0 * ldb, ldb,
+                                             (int32_t)kFlowBM, (int32_t)std::min<i64>(kFlowBN, nrhs - j0), (int32_t)kFlowBM, 1,
+                                             (int32_t)(nrow + K), wdone, (int32_t)(r0 + i0 / kFlowBM), 0});
+            landed[r0 + i0 / kFlowBM] += (int)((c / kFlowBM) * njt);
+        }
+    }
+    if (tiles.empty() || tiles.size() >= (size_t)INT32_MAX) {
+        cudaError_t e0 = cudaMalloc(&q.flow_ctr, sizeof(int));
+        if (e0 != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e0)); }
+        return BBM_OK;
+    }
+    FlowTile* dt = nullptr;
+    int32_t rc = upload(h, tiles, &dt);
+    if (rc != BBM_OK) return rc;
+    q.flow_tiles = dt;
+    q.flow_ntiles = (i64)tiles.size();
+    q.flow_nctr = nrow + P;
+    cudaError_t e = cudaMalloc(&q.flow_ctr, sizeof(int) * (size_t)(q.flow_nctr + 1));
+    if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
+    q.flow_ok = true;
+    return BBM_OK;
+}
+
 int32_t sky_qr_lmul_adj_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_fac, const double* d_tau, double* d_B, i64 ldb, i64 nrhs) {
     BBM_REQUIRE_HANDLE(h);
     if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
@@ -2061,7 +2135,13 @@ int32_t sky_qr_lmul_adj_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_f
     }
     rc = launch_mm64(h, q.ytb, 0, q.ytb.ntiles, WS, WS, WS, 1.0, 0.0, false);
     if (rc != BBM_OK) return rc;
-    // the sequential sweep over the panels
+    // the sweep over the panels: one persistent data-flow kernel ("qr.flow", default on; many right-hand sides, block
+    // sizes multiples of 64), else two dependent launches per panel
+    if (bbm_opt(h, "qr.flow", 1) != 0 && nrhs >= 8 && (reinterpret_cast<uintptr_t>(d_B) % 16 == 0)) {
+        rc = build_qr_flow_plan(h, d, ldb, ldw, nrhs);
+        if (rc != BBM_OK) return rc;
+        if (q.flow_ok) return launch_flow(h, q.flow_tiles, q.flow_ntiles, q.flow_ctr, q.flow_nctr, false, WS, WS, d_B, W);
+    }
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
     for (i64 K = 0; K < q.ncols; ++K) {
         rc = launch_mm64(h, q.stepW, q.ptrW[K], q.ptrW[K + 1] - q.ptrW[K], WS, d_B, W, 1.0, 1.0, true, K < 2, pdl);
@@ -3072,6 +3152,8 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
     free_batch(d->qrf.bW); free_batch(d->qrf.bC);
     if (d->qr.d_pan) cudaFree(d->qr.d_pan);
     if (d->qr.d_blk) cudaFree(d->qr.d_blk);
+    if (d->qr.flow_tiles) cudaFree(d->qr.flow_tiles);
+    if (d->qr.flow_ctr) cudaFree(d->qr.flow_ctr);
     free_batch(d->qr.gram); free_batch(d->qr.ytb); free_batch(d->qr.stepW); free_batch(d->qr.stepB);
     for (auto& b : d->qr.levels) free_batch(b);
     for (auto& kv : d->plans) free_plan(kv.second);

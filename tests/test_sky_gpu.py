@@ -461,6 +461,37 @@ def test_block_banded_qr_lmul_adj_and_ldiv(handle, rows, cols, l, u, nrhs):
         assert relerr(Ad @ dX.to_host(), B0) <= tol(np.float64, nnz) * max(1.0, cond)
 
 
+@pytest.mark.parametrize("flow", [1, 0], ids=["data-flow", "launch-chain"])
+@pytest.mark.parametrize("rows,cols,l,u", [([64] * 12, [64] * 12, 1, 2), ([128, 64, 192, 64, 128], [128, 64, 192, 64, 128], 2, 1),
+                                           ([64, 128, 64, 64], [64, 128, 64], 1, 1), ([192] * 6, [192] * 6, 3, 0)])
+@pytest.mark.parametrize("nrhs", [8, 33, 64])
+def test_block_banded_qr_sweep_kernels(handle, rows, cols, l, u, nrhs, flow):
+    """The sweep of lmul!(F.Q', B) as one persistent data-flow kernel (block sizes multiples of 64, >= 8 right-hand sides;
+    option qr.flow) and as the launch chain: same oracle, partial column tiles, thin factors, several block rows per panel."""
+    rng = np.random.default_rng(75)
+    Ad, data, tau = _factor_on_host(rng, rows, cols, l, u)
+    m = sum(rows)
+    Fd = B.BlockBandedQR(B.BlockSkylineMatrix(data, rows, cols, l, l + u), tau).to_device(handle)
+    B0 = np.asfortranarray(rng.standard_normal((m, nrhs)))
+    handle.set_option("qr.flow", flow)
+    try:
+        for _ in range(2):                                  # the second call re-uses the plan and re-zeroes the counters
+            dB = handle.to_device(B0)
+            B.lmul_adj_(Fd, dB)
+            got = dB.to_host()
+        if rows == cols:
+            dX = B.ldiv(Fd, handle.to_device(B0)).to_host()
+    finally:
+        handle.set_option("qr.flow", 1)
+    ref = np.asfortranarray(B0.copy())
+    O.sky_qr_lmul_adj(rows, cols, l, l + u, data, tau, ref)
+    nnz = max(rows) * (l + 1) + max(cols)
+    assert not np.isnan(got).any()
+    assert relerr(got, ref) <= tol(np.float64, nnz)
+    if rows == cols:
+        assert relerr(Ad @ dX, B0) <= tol(np.float64, nnz) * max(1.0, np.linalg.cond(Ad))
+
+
 def test_block_banded_qr_errors(handle):
     rng = np.random.default_rng(72)
     rows, cols = [3, 3], [3, 3, 3]
