@@ -1567,6 +1567,8 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
     extern __shared__ __align__(16) unsigned char mm_smem[];
     double* As = reinterpret_cast<double*>(mm_smem);          // As[k][i]
     double* Bs = As + (size_t)kFlowBK * kFlowLDA;              // Bs[j][k]
+    __shared__ int bad_flag;
+    int* bad = &bad_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;
     const int ar = lane >> 2, ac = lane & 3;
@@ -1584,15 +1586,19 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
         }
         cp_async_commit();
         // 2. wait until every contribution to the dynamic operand has landed (counter in L2)
-        if (tid == 0 && ft.wait_val > 0) {
-            if (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
-                const long long t0 = clock64();
-                while (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
-                    if (sleep_ns > 0) __nanosleep(sleep_ns);
-                    if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + err_idx, 1); break; }   // never hang the device
+        if (tid == 0) {
+            int timed_out = 0;
+            if (ft.wait_val > 0) {
+                if (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                    const long long t0 = clock64();
+                    while (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                        if (sleep_ns > 0) __nanosleep(sleep_ns);
+                        if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + err_idx, 1); timed_out = 1; break; }   // never hang the device
+                    }
                 }
+                asm volatile("fence.acquire.gpu;" ::: "memory");
             }
-            asm volatile("fence.acquire.gpu;" ::: "memory");
+            *bad = timed_out;   // a tile that gave up poisons its destination: everything downstream turns NaN, never silently wrong
         }
         __syncthreads();
         // 3. the dynamic operand (right-hand-side data written by red.add in L2: .cg loads bypass L1)
@@ -1625,7 +1631,7 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
                 for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         // 5. accumulate into the destination and publish
-        const double sgn = ft.kind == 0 ? 1.0 : -1.0;
+        const double sgn = *bad ? __longlong_as_double(0x7ff8000000000000LL) : (ft.kind == 0 ? 1.0 : -1.0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int row = wm0 + i * 8 + ar;
