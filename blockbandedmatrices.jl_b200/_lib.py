@@ -105,6 +105,8 @@ SIGNATURES = {
     "bbm_sky_mul_f32": (i32, [vp, vp, f32, vp, vp, i64, i64, f32, vp, i64]),
     "bbm_sky_matmul_f64": (i32, [vp, vp, vp, vp, f64, vp, vp, f64, vp]),
     "bbm_sky_matmul_f32": (i32, [vp, vp, vp, vp, f32, vp, vp, f32, vp]),
+    "bbm_sky_rmul_f64": (i32, [vp, vp, f64, vp, i64, i64, vp, f64, vp, i64]),
+    "bbm_sky_rmul_f32": (i32, [vp, vp, f32, vp, i64, i64, vp, f32, vp, i64]),
     "bbm_sky_trsm_f64": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_sky_trsm_f32": (i32, [vp, vp, i32, i32, vp, vp, i64, i64]),
     "bbm_bbb_partition_rows": (i32, [i64, vp, i32, vp]),

@@ -102,6 +102,8 @@ struct bbm_sky_desc {
         int* flow_ctr = nullptr;
         bool flow_ok = false;
     } qr;
+    // X*A (dense times block-banded): one C block per block column of A; cached for the last (rows of X, ldx, ldy, eltype)
+    struct Rmul { i64 p = -1, ldx = -1, ldy = -1; int elem = 0; bool aligned4 = false; Tri::Batch batch; } rmul;
     // descriptor of the row-and-column reversed matrix (its storage is the reversed `data`), for the QL calls
     bbm_sky_desc* rev = nullptr;
     // transposed matvec: one item per group of up to 8 columns of a panel (start, ld = rows, x row start, y row start, columns)
@@ -1160,6 +1162,14 @@ struct MmBatchHost {
         segs.push_back(sg);
         const int32_t ci = (int32_t)cblks.size();
         cblks.push_back(cb);
+        for (int tj = 0; tj * tile < cols; ++tj)
+            for (int ti = 0; ti * tile < rows; ++ti) tiles.push_back(MmTile{ci, ti, tj, 0});
+    }
+    // a C block with an empty product: it only gets its beta scaling (or zeros)
+    void add_empty(i64 cstart, i64 ldc, i64 rows, i64 cols) {
+        if (rows <= 0 || cols <= 0) return;
+        const int32_t ci = (int32_t)cblks.size();
+        cblks.push_back(MmCBlk{cstart, ldc, (int32_t)rows, (int32_t)cols, (int32_t)segs.size(), (int32_t)segs.size()});
         for (int tj = 0; tj * tile < cols; ++tj)
             for (int ti = 0; ti * tile < rows; ++ti) tiles.push_back(MmTile{ci, ti, tj, 0});
     }
@@ -2739,6 +2749,60 @@ template <typename T>
 int32_t sky_trsm_impl(bbm_handle_t h, bbm_sky_desc_t d, int32_t uplo, int32_t unit, const T* d_data, T* d_B, i64 ldb, i64 nrhs);
 
 // ------------------------------------------------------------------------------------------------
+// Y <- alpha * X * A + beta * Y for a dense column-major X (p x m) and a block-skyline A (`X*A`, `MulAdd(X, A)`,
+// test/test_linalg.jl:56-57; [upstream] the block loop Y[:, J] += X[:, K] A_KJ over K in blockcolsupport(A, J)).
+// The in-band blocks of block column J are ONE contiguous column-major panel, so the whole column is a single dense
+// product Y[:, C_J : C_J+c_J) = X[:, R_klo : R_khi+1) * panel_J: the panel is the k-contiguous operand the tile kernels
+// want for "B", X the row-contiguous one for "A".  One batched launch (FP64: DMMA; FP32: the register-tiled SIMT kernel).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int32_t sky_rmul_impl(bbm_handle_t h, bbm_sky_desc_t d, T alpha, const T* d_X, i64 ldx, i64 p, const T* d_data, T beta, T* d_Y, i64 ldy) {
+    BBM_REQUIRE_HANDLE(h);
+    if (!sky_valid(d) || d->h != h) return bbm_fail(h, BBM_ERR_HANDLE, "invalid BlockSkylineMatrix descriptor");
+    if (p < 0) return bbm_fail(h, BBM_ERR_ARG, "negative row count");
+    if (p > 0 && (ldx < p || ldy < p)) return bbm_fail(h, BBM_ERR_DIM, "DimensionMismatch: X is %lld x %lld, ldx=%lld, ldy=%lld", (long long)p, (long long)d->m, (long long)ldx, (long long)ldy);
+    if (p == 0 || d->n == 0) return BBM_OK;
+    if (!d_Y || (d->m > 0 && !d_X) || (d->numel > 0 && !d_data)) return bbm_fail(h, BBM_ERR_ARG, "null device pointer");
+    if ((const void*)d_Y == (const void*)d_X) return bbm_fail(h, BBM_ERR_ARG, "mul!: destination must not alias an operand");
+    BBM_CUDA(h, cudaSetDevice(h->device));
+    bbm_sky_desc::Rmul& r = d->rmul;
+    if (r.p != p || r.ldx != ldx || r.ldy != ldy || r.elem != (int)sizeof(T)) {
+        MmBatchHost b;
+        b.tile = sizeof(T) == 8 ? 64 : 128;
+        bool a4 = true;
+        for (i64 J = 0; J < d->Nc; ++J) {
+            if (d->c[J] == 0) continue;
+            const i64 S = d->S[J];
+            if (S == 0) { b.add_empty(d->C[J] * ldy, ldy, p, d->c[J]); continue; }
+            const MmSeg sg{d->R[d->klo[J]] * ldx, ldx, d->off[J], S, S};
+            a4 = a4 && !(sg.astart & 3) && !(sg.lda & 3) && !(sg.bstart & 3) && !(sg.ldb & 3);
+            b.add(d->C[J] * ldy, ldy, p, d->c[J], sg);
+        }
+        int32_t rc = upload_batch(h, b, &r.batch);
+        if (rc != BBM_OK) { r.p = -1; return rc; }
+        r.p = p; r.ldx = ldx; r.ldy = ldy; r.elem = (int)sizeof(T); r.aligned4 = a4;
+    }
+    if (r.batch.ntiles == 0) return BBM_OK;
+    if constexpr (sizeof(T) == 8) {
+        return launch_mm64(h, r.batch, 0, r.batch.ntiles, (const double*)d_X, (const double*)d_data, (double*)d_Y, (double)alpha, (double)beta, false);
+    } else {
+        MmParams<float> pf{(const float*)d_X, (const float*)d_data, (float*)d_Y, (const MmCBlk*)r.batch.cblks, (const MmSeg*)r.batch.segs,
+                           (const MmTile*)r.batch.tiles, (float)alpha, (float)beta};
+        const bool al = r.aligned4 && (reinterpret_cast<uintptr_t>(d_X) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_data) % 16 == 0);
+        cudaError_t e = cudaSuccess;
+        auto go = [&](auto kern) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSgSmem);
+            if (e == cudaSuccess) { kern<<<r.batch.ntiles, 256, kSgSmem, h->stream>>>(pf); e = cudaGetLastError(); }
+        };
+        if (al) go(sky_sgemm_simt_kernel<true>);
+        else go(sky_sgemm_simt_kernel<false>);
+        if (e != cudaSuccess) return bbm_fail(h, BBM_ERR_CUDA, "X*A product launch: %s", cudaGetErrorString(e));
+        h->launches += 1;
+        return BBM_OK;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // QL (ql!, lmul!(F.Q', B), ldiv!(F::QL, B); src/blockskylineqr.jl:51-72, 96-111, 149-157) by reversal.
 // LAPACK's geqlf/ormql are geqrf/ormqr on the matrix with rows and columns reversed, and for block-skyline
 // storage that reversed matrix is simply the flat `data` vector read backwards (panels in reverse order, every
@@ -3161,6 +3225,7 @@ int32_t bbm_sky_desc_destroy(bbm_sky_desc_t d) {
     if (d->qr.flow_tiles) cudaFree(d->qr.flow_tiles);
     if (d->qr.flow_ctr) cudaFree(d->qr.flow_ctr);
     free_batch(d->qr.gram); free_batch(d->qr.ytb); free_batch(d->qr.stepW); free_batch(d->qr.stepB);
+    free_batch(d->rmul.batch);
     for (auto& b : d->qr.levels) free_batch(b);
     for (auto& kv : d->plans) free_plan(kv.second);
     d->magic = 0;
@@ -3218,6 +3283,14 @@ int32_t bbm_sky_mul_t_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const 
 int32_t bbm_sky_mul_t_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X, int64_t ldx,
                           int64_t nrhs, float beta, float* d_Y, int64_t ldy) {
     return sky_mul_t_impl<float>(h, d, alpha, d_data, d_X, ldx, nrhs, beta, d_Y, ldy);
+}
+int32_t bbm_sky_rmul_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_X, int64_t ldx, int64_t p, const double* d_data,
+                         double beta, double* d_Y, int64_t ldy) {
+    return sky_rmul_impl<double>(h, d, alpha, d_X, ldx, p, d_data, beta, d_Y, ldy);
+}
+int32_t bbm_sky_rmul_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_X, int64_t ldx, int64_t p, const float* d_data,
+                         float beta, float* d_Y, int64_t ldy) {
+    return sky_rmul_impl<float>(h, d, alpha, d_X, ldx, p, d_data, beta, d_Y, ldy);
 }
 int32_t bbm_sky_qr_f64(bbm_handle_t h, bbm_sky_desc_t d, double* d_data, double* d_tau) { return sky_qr_fact_impl(h, d, d_data, d_tau); }
 int32_t bbm_sky_qr_lmul_adj_f64(bbm_handle_t h, bbm_sky_desc_t d, const double* d_factors, const double* d_tau, double* d_B, int64_t ldb,

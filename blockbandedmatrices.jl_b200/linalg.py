@@ -53,6 +53,8 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
     (host vectors: copied through the C ABI's *_host_* call, synchronous)."""
     if isinstance(A, BlockSkylineMatrix) and isinstance(x, BlockSkylineMatrix):
         return _sky_matmul_(y, A, x, alpha, beta)
+    if isinstance(A, DeviceArray) and isinstance(x, BlockSkylineMatrix):
+        return _sky_rmul_(y, A, x, alpha, beta)
     if isinstance(A, _Triangular):
         return _bbb_trimul_(y, A, x, alpha, beta)
     if isinstance(A, Adjoint):
@@ -95,6 +97,27 @@ def mul_(y, A, x, alpha=1.0, beta=0.0):
                 y.ctypes.data_as(C.c_void_p), _ld(y))
     L.check(rc, h.h, "mul!")
     return y
+
+
+def _sky_rmul_(Y, X, A, alpha=1.0, beta=0.0):
+    """``mul!(Y, X, A, alpha, beta)`` for a dense device matrix X (column-major) times a device-resident BlockSkylineMatrix
+    (`X*A`, test/test_linalg.jl:56-57)."""
+    h = _require_device(A)
+    m, n = A.shape
+    if not isinstance(Y, DeviceArray):
+        raise TypeError("X and Y must both be device arrays")
+    xr, xc = _vec_dims(X, "X")
+    yr, yc = _vec_dims(Y, "Y")
+    if xc != m or yc != n or xr != yr:
+        raise L.DimensionMismatch(f"X is {X.shape}, A is {m}x{n}, Y is {Y.shape}")
+    dt = A.dtype
+    if dt not in _SUF or np.dtype(X.dtype) != dt or np.dtype(Y.dtype) != dt:
+        raise TypeError("device path takes matching Float32/Float64 operands only")
+    suf, ct = _SUF[dt]
+    fn = getattr(h._lib, f"bbm_sky_rmul_{suf}")
+    rc = fn(h.h, A.descriptor(h), ct(alpha), C.c_void_p(X.ptr), _ld(X), xr, C.c_void_p(A.data.ptr), ct(beta), C.c_void_p(Y.ptr), _ld(Y))
+    L.check(rc, h.h, "mul!")
+    return Y
 
 
 def _bbb_matmul_(Cm, A, B, alpha=1.0, beta=0.0):
@@ -420,6 +443,12 @@ def ldiv(T, B):
 def mul(A, x):
     """``A*x``: allocates the result where x lives (``similar`` + ``mul!``).  For two
     BlockSkylineMatrix operands the result structure is ``similar(::MulAdd)`` of src/linalg.jl:32-48."""
+    if isinstance(A, DeviceArray) and isinstance(x, BlockSkylineMatrix):
+        # X*A: dense times block-banded (test/test_linalg.jl:56-57); the result is dense like X
+        h = _require_device(x)
+        if len(A.shape) != 2:
+            raise L.DimensionMismatch("X*A needs a matrix X")
+        return _sky_rmul_(h.empty((A.shape[0], x.shape[1]), x.dtype), A, x, 1.0, 0.0)
     if isinstance(A, Adjoint):
         h = _require_device(A.parent)
         n = A.parent.shape[1]

@@ -259,6 +259,15 @@ int32_t bbm_sky_mul_t_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const 
 int32_t bbm_sky_mul_t_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_data, const float* d_X,
                           int64_t ldx, int64_t nrhs, float beta, float* d_Y, int64_t ldy);
 
+/* Y <- alpha * X * A + beta * Y: `X*A` / `similar(X) .= MulAdd(X, A)` for a dense column-major X (p x m, ldx >= p) and a
+ * BlockSkylineMatrix A (test/test_linalg.jl:56-57; [upstream] block loop Y[:,J] += X[:,K] * A_KJ with one gemm per block).
+ * d_Y: p x n (ldy >= p); beta == 0 never reads Y.  One dense product per block COLUMN of A (its in-band blocks are one
+ * contiguous panel), batched into one launch.                                                              */
+int32_t bbm_sky_rmul_f64(bbm_handle_t h, bbm_sky_desc_t d, double alpha, const double* d_X, int64_t ldx, int64_t p,
+                         const double* d_data, double beta, double* d_Y, int64_t ldy);
+int32_t bbm_sky_rmul_f32(bbm_handle_t h, bbm_sky_desc_t d, float alpha, const float* d_X, int64_t ldx, int64_t p,
+                         const float* d_data, float beta, float* d_Y, int64_t ldy);
+
 /* C <- alpha*A*B + beta*C, all three block-skyline (replaces [upstream] _block_muladd! + one BLAS
  * gemm per block triple; C's structure is the caller's: src/linalg.jl:27-48 for A*B, a wider C is
  * allowed, test/test_blockbanded.jl:213-221).  BBM_ERR_DIM if the block axes are incompatible,

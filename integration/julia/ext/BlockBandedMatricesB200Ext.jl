@@ -22,7 +22,7 @@ module BlockBandedMatricesB200Ext
 using BlockBandedMatrices
 using BlockBandedMatrices: BandedBlockBandedMatrix, BlockSkylineMatrix, BandedBlockBandedColumns,
                            BlockBandedColumns, blockbandwidths, subblockbandwidths, colblockbandwidths
-using BlockBandedMatrices.ArrayLayouts: MulAdd, Ldiv, TriangularLayout, MemoryLayout, DenseColumnMajor
+using BlockBandedMatrices.ArrayLayouts: MulAdd, Ldiv, TriangularLayout, MemoryLayout, DenseColumnMajor, AbstractColumnMajor
 using LinearAlgebra: UniformScaling
 import BlockBandedMatrices.ArrayLayouts: materialize!, triangulardata
 using BlockBandedMatrices.BlockArrays: BlockedMatrix, blocklengths, blocksize
@@ -183,6 +183,16 @@ for (T, suf) in ((Float64, "f64"), (Float32, "f32"))
                     (Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Ptr{$T}, Int64, Int64, $T, Ptr{$T}, Int64),
                     handle().ptr, descriptor(A), M.α, A.data.ptr, x.ptr, ld(x), size(x, 2), M.β, y.ptr, ld(y)))
         y
+    end
+    # Y <- α X A + β Y for a dense device matrix X: `X*A`, `similar(X) .= MulAdd(X, A)` (test/test_linalg.jl:56-57)
+    @eval function materialize!(M::MulAdd{<:AbstractColumnMajor,<:BlockBandedColumns,<:AbstractColumnMajor,$T,<:B200Array{$T,2},<:B200Sky{$T},<:B200Array{$T,2}})
+        X, A, Y = M.A, M.B, M.C
+        size(X, 2) == size(A, 1) && size(X, 1) == size(Y, 1) && size(A, 2) == size(Y, 2) ||
+            throw(DimensionMismatch("X has size $(size(X)), A has size $(size(A)), Y has size $(size(Y))"))
+        check(ccall(($(QuoteNode(Symbol("bbm_sky_rmul_", suf))), libbbm), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, $T, Ptr{$T}, Int64, Int64, Ptr{$T}, $T, Ptr{$T}, Int64),
+                    handle().ptr, descriptor(A), M.α, X.ptr, ld(X), size(X, 1), A.data.ptr, M.β, Y.ptr, ld(Y)))
+        Y
     end
     # C <- α A B + β C, all block-skyline (result structure from similar(::MulAdd), src/linalg.jl:32-48,
     # which returns a B200-backed BlockSkylineMatrix because `similar(::B200Vector)` is a B200Vector)

@@ -321,3 +321,31 @@ def sky_numentries(rows, cols, l, u) -> int:
     c, cp = _ia(cols)
     lv, uv = _vecbw(l, len(c)), _vecbw(u, len(c))
     return int(lib().oracle_sky_numentries(i64(len(r)), i64(len(c)), rp, cp, lv.ctypes.data_as(_p), uv.ctypes.data_as(_p)))
+
+
+def sky_rmul(rows, cols, l, u, alpha, X, data, beta, Y):
+    """Y <- alpha*X*A + beta*Y in place for a dense X (p x sum(rows)) and a block-skyline A: `X*A` / `MulAdd(X, A)`
+    (test/test_linalg.jl:56-57).  [upstream] BlockArrays' block loop with X as a single block row: for every block column J
+    and every K in blockcolsupport(A, J) (src/AbstractBlockBandedMatrix.jl:90-104), Y[:, J] += alpha * X[:, K] * A[K, J]
+    (one gemm per block on the (ptr, ld) view of src/BlockSkylineMatrix.jl:459-465); beta == 0 overwrites Y without reading it.
+    Plain numpy, per block -- small cases only."""
+    from . import formats as F
+    r, c = [int(v) for v in rows], [int(v) for v in cols]
+    off, S, klo, khi = F.sky_layout(r, c, l, u)
+    R = np.concatenate([[0], np.cumsum(r)]).astype(np.int64)
+    Cc = np.concatenate([[0], np.cumsum(c)]).astype(np.int64)
+    if X.shape[1] != R[-1] or Y.shape[1] != Cc[-1] or X.shape[0] != Y.shape[0]:
+        raise ValueError("DimensionMismatch")
+    if beta == 0:
+        Y[...] = 0
+    else:
+        Y *= beta
+    for J in range(len(c)):
+        ld = int(S[J])
+        if ld == 0 or c[J] == 0:
+            continue
+        pan = data[int(off[J]):int(off[J]) + ld * c[J]].reshape((ld, c[J]), order="F")
+        for K in range(int(klo[J]), int(khi[J]) + 1):
+            r0 = int(R[K] - R[int(klo[J])])
+            Y[:, Cc[J]:Cc[J + 1]] += alpha * (X[:, R[K]:R[K + 1]] @ pan[r0:r0 + r[K], :])
+    return Y

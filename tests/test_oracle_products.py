@@ -238,6 +238,24 @@ def test_oracle_sky_mul_t_vs_dense():
         assert relerr(Y, ref) <= 1e-14
 
 
+def test_oracle_sky_rmul_vs_dense():
+    """`X*A` (test/test_linalg.jl:56-57): the restated block loop against dense `X @ Matrix(A)`, incl. beta = 0 with a NaN destination,
+    rectangular and ragged structures and an empty block column."""
+    rng = np.random.default_rng(29)
+    for rows, cols, l, u in [([5, 3, 7, 2, 6], [4, 6, 2, 5, 3, 7], 1, 2), ([3] * 7, [3] * 7, [2, 1, 2, 3, 1, 0, 0], [0, 1, 1, 2, 3, 1, 2]),
+                             (list(range(1, 5)), list(range(1, 5)), 1, 1), ([2, 2, 2], [2, 2, 2], [0, -1, 0], [0, -1, 0])]:
+        data = random_sky(rng, rows, cols, l, u)
+        Dn = F.sky_to_dense(data, rows, cols, l, u)
+        X = np.asfortranarray(rng.standard_normal((4, sum(rows))))
+        Y0 = np.asfortranarray(rng.standard_normal((4, sum(cols))))
+        Y = Y0.copy(order="F")
+        O.sky_rmul(rows, cols, l, u, 2.0, X, data, -0.5, Y)
+        assert relerr(Y, 2.0 * X @ Dn - 0.5 * Y0) <= 1e-14
+        Y = np.full_like(Y0, np.nan)
+        O.sky_rmul(rows, cols, l, u, 1.0, X, data, 0.0, Y)
+        assert relerr(Y, X @ Dn) <= 1e-14 if np.linalg.norm(X @ Dn) else not np.isnan(Y).any()
+
+
 def test_oracle_bbb_sparse_matches_dense():
     import scipy.sparse as sp
     rng = np.random.default_rng(29)

@@ -143,6 +143,42 @@ def test_sky_matmul_matches_oracle(handle, case, dtype, kernel):
         handle.set_option("sky.mm_kernel", 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("rows,cols,l,u", [(list(range(1, 5)), list(range(1, 5)), 1, 1),          # test/test_linalg.jl:38-57
+                                           ([5, 3, 7, 2, 6], [4, 6, 2, 5, 3, 7], 1, 2),
+                                           ([3] * 7, [3] * 7, [2, 1, 2, 3, 1, 0, 0], [0, 1, 1, 2, 3, 1, 2]),
+                                           ([2, 2, 2], [2, 2, 2], [0, -1, 0], [0, -1, 0]),        # an empty block column
+                                           ([128, 64, 200, 36], [128, 64, 200, 36], 1, 1),
+                                           ([256] * 5, [256] * 5, 2, 2)])
+@pytest.mark.parametrize("p", [1, 10, 150])
+def test_sky_rmul_dense_times_block_banded(handle, rows, cols, l, u, dtype, p):
+    """`X*A` and `mul!(Y, X, A, alpha, beta)` for a dense X (test/test_linalg.jl:56-57: `X*A ≈ (similar(X) .= MulAdd(X,A)) ≈ Matrix(X)*A`)
+    against the restated block loop; beta = 0 never reads the NaN-filled destination."""
+    rng = np.random.default_rng(31)
+    data = random_sky(rng, rows, cols, l, u, dtype)
+    A = B.BlockSkylineMatrix(data, rows, cols, l, u).to_device(handle)
+    m, n = sum(rows), sum(cols)
+    X = np.asfortranarray(rng.standard_normal((p, m)).astype(dtype))
+    dX = handle.to_device(X)
+    nnz = int(max(A.block_strides.max() if len(cols) else 0, 1))
+    got = B.mul(dX, A).to_host()
+    ref = np.zeros((p, n), dtype=dtype, order="F")
+    O.sky_rmul(rows, cols, l, u, 1.0, X, data, 0.0, ref)
+    assert got.shape == (p, n) and not np.isnan(got).any()
+    assert relerr(got, ref) <= tol(dtype, nnz)
+    Y0 = np.asfortranarray(rng.standard_normal((p, n)).astype(dtype))
+    dY = handle.to_device(Y0)
+    B.mul_(dY, dX, A, 2.5, -0.5)
+    ref = Y0.copy(order="F")
+    O.sky_rmul(rows, cols, l, u, 2.5, X, data, -0.5, ref)
+    assert relerr(dY.to_host(), ref) <= tol(dtype, nnz + 1)
+    dY = handle.to_device(np.full((p, n), np.nan, dtype=dtype, order="F"))
+    B.mul_(dY, dX, A, 1.0, 0.0)
+    assert not np.isnan(dY.to_host()).any()
+    with pytest.raises(B.DimensionMismatch):
+        B.mul_(handle.empty((p, n + 1), dtype), dX, A)
+
+
 @pytest.mark.parametrize("f32_kernel", [0, 1], ids=["register-tiled", "first-version"])
 @pytest.mark.parametrize("rows", [[128, 256, 384, 128, 256, 128], [132, 60, 260, 4, 96, 200], [100, 37, 250, 129, 3, 64]],
                          ids=["full-tiles", "16-byte-aligned-ragged", "unaligned-ragged"])
