@@ -5,7 +5,7 @@
 
 static const char* const kOptionKeys[] = {
     "bbb.tile", "bbb.stages", "bbb.items_per_sm", "bbb.kernel", "bbb.maxseg", "bbb.l2hint", "bbb.l2keep_pct", "bbb.waves", "bbb.host_chunks", "bbb.ovh", "bbb.mm_kernel", "bbb.mm_staged", "bbb.pdl", "bbb.ctas_per_sm",
-    "sky.kernel", "sky.mv_split", "sky.mm_kernel", "sky.mm_bk", "sky.mm_ws", "sky.mm_f32_kernel", "bbb.mm_ctas_per_sm", "qr.panel", "qr.flow", "qr.lookahead", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "trsm.cond_check", "trsm.cond_max", "trsm.flow_ctas_per_sm", "trsm.flow_bk", "trsm.flow_sleep_ns", "trsm.last_cond_x1000", "trsm.last_path", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "tri.rhs_batch", "dist.graph", "dist.peer", "dist.lead_steps", "dist.peer_timeout_ms", nullptr};
+    "sky.kernel", "sky.mv_split", "sky.mm_kernel", "sky.mm_bk", "sky.mm_ws", "sky.mm_f32_kernel", "bbb.mm_ctas_per_sm", "qr.panel", "qr.flow", "qr.lookahead", "trsm.kernel", "trsm.prefetch", "trsm.pdl", "trsm.cond_check", "trsm.cond_max", "trsm.flow_ctas_per_sm", "trsm.flow_bk", "trsm.flow_ctr_stride", "trsm.flow_sleep_ns", "trsm.last_cond_x1000", "trsm.last_path", "tri.pf", "tri.sync", "tri.kernel", "tri.lean", "tri.push", "tri.ws_max_mb", "tri.rhs_batch", "dist.graph", "dist.peer", "dist.lead_steps", "dist.peer_timeout_ms", nullptr};
 
 extern "C" {
 

@@ -1557,6 +1557,7 @@ struct FlowTile {
 };
 
 constexpr int kFlowBM = 64, kFlowBN = 32;
+constexpr int kFlowCtrStride = 32;   // ints between two completion counters: one 128-byte line per counter
 constexpr int kFlowLDA = kFlowBM + 4;
 template <int BK>
 constexpr size_t flow_smem_bytes() { return ((size_t)BK * kFlowLDA + (size_t)kFlowBN * (BK + 4)) * sizeof(double); }
@@ -1572,7 +1573,8 @@ __device__ __forceinline__ int ld_relaxed_gpu_s32(const int* p) {
 template <int kFlowBK>
 __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __restrict__ tiles, i64 ntiles, const double* __restrict__ data,
                                                             const double* __restrict__ W, double* __restrict__ Bm, double* __restrict__ X,
-                                                            int* __restrict__ ctr, int err_idx, int sleep_ns) {
+                                                            int* __restrict__ ctr, int err_idx, int sleep_ns, int cs) {
+    // cs: stride between counters in ints (32 = one 128-byte line each: waiting tiles of one step poll different L2 lines)
     constexpr int kFlowLDB = kFlowBK + 4;
     extern __shared__ __align__(16) unsigned char mm_smem[];
     double* As = reinterpret_cast<double*>(mm_smem);          // As[k][i]
@@ -1599,11 +1601,12 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
         if (tid == 0) {
             int timed_out = 0;
             if (ft.wait_val > 0) {
-                if (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                const int* wp = ctr + (i64)ft.wait_ctr * cs;
+                if (ld_relaxed_gpu_s32(wp) < ft.wait_val) {
                     const long long t0 = clock64();
-                    while (ld_relaxed_gpu_s32(ctr + ft.wait_ctr) < ft.wait_val) {
+                    while (ld_relaxed_gpu_s32(wp) < ft.wait_val) {
                         if (sleep_ns > 0) __nanosleep(sleep_ns);
-                        if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + err_idx, 1); timed_out = 1; break; }   // never hang the device
+                        if (clock64() - t0 > 4000000000LL) { atomicExch(ctr + (i64)err_idx * cs, 1); timed_out = 1; break; }   // never hang the device
                     }
                 }
                 asm volatile("fence.acquire.gpu;" ::: "memory");
@@ -1656,13 +1659,14 @@ __global__ void __launch_bounds__(128) sky_trsm_flow_kernel(const FlowTile* __re
         }
         __threadfence();
         __syncthreads();   // also: nobody still reads As / Bs when the next tile's prefetch overwrites them
-        if (tid == 0) atomicAdd(ctr + ft.sig_ctr, 1);
+        if (tid == 0) atomicAdd(ctr + (i64)ft.sig_ctr * cs, 1);
     }
 }
 
 int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb, i64 ldx, i64 nrhs) {
     bbm_sky_desc::Tri& t = d->tri[upper];
-    const i64 kFlowBK = bbm_opt(h, "trsm.flow_bk", 64) >= 128 ? 128 : 64;   // k-slice per tile: 64 (more tiles, shorter) or 128 (half the atomics)
+    const i64 fbk = bbm_opt(h, "trsm.flow_bk", 64);
+    const i64 kFlowBK = fbk >= 128 ? 128 : (fbk <= 32 ? 32 : 64);   // k-slice per tile: 64; 32 = twice the tiles, each half as long; 128 falls back to the launch chain
     if (t.flow_ldb == ldb && t.flow_nrhs == nrhs && t.flow_ldx == ldx && t.flow_bk == kFlowBK && t.flow_ctr) return BBM_OK;
     const i64 N = d->Nr;
     std::vector<FlowTile> tiles;
@@ -1674,7 +1678,7 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
     const i64 nctr = toff[N];
     if (2 * nctr + 1 >= (i64)INT32_MAX) { t.flow_ok = false; t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx; t.flow_bk = kFlowBK; return BBM_OK; }
     std::vector<int> nA(nctr, 0), nB(nctr, 0);   // targets: cX / cB
-    bool even = !(ldb & 1) && !(ldx & 1) && kFlowBK == kFlowBM;   // (k-slices must coincide with the 64-row tiles)
+    bool even = !(ldb & 1) && !(ldx & 1) && kFlowBK <= kFlowBM;   // (a k-slice must lie inside one 64-row slice: one counter to wait for)
     for (i64 s = 0; s < N; ++s) {
         const i64 K = upper ? N - 1 - s : s;
         const i64 rK = d->r[K];
@@ -1729,7 +1733,7 @@ int32_t build_tri_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, int upper, i64 ldb
         t.flow_tiles = dt;
     }
     t.flow_nctr = 2 * nctr;
-    cudaError_t e = cudaMalloc(&t.flow_ctr, sizeof(int) * (size_t)(2 * nctr + 1));
+    cudaError_t e = cudaMalloc(&t.flow_ctr, sizeof(int) * (size_t)(2 * nctr + 1) * kFlowCtrStride);
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
     t.flow_ldb = ldb; t.flow_nrhs = nrhs; t.flow_ldx = ldx; t.flow_bk = kFlowBK;
     return BBM_OK;
@@ -1802,10 +1806,10 @@ int32_t tri_condition(bbm_handle_t h, bbm_sky_desc_t d, int upper, int unit, con
 
 // One cooperative launch of the data-flow kernel over a tile list: static operands of kind-0 / kind-1 tiles from A0 / A1,
 // dynamic operands and destinations Bm and X (kind 0: A0 * Bm -> X, +; kind 1: A1 * X -> Bm, -).
-int32_t launch_flow(bbm_handle_t h, const void* flow_tiles, i64 flow_ntiles, int* flow_ctr, i64 flow_nctr, bool bk128,
+int32_t launch_flow(bbm_handle_t h, const void* flow_tiles, i64 flow_ntiles, int* flow_ctr, i64 flow_nctr, int bk,
                     const double* A1, const double* A0, double* Bm, double* X) {
-    const void* func = bk128 ? reinterpret_cast<const void*>(sky_trsm_flow_kernel<128>) : reinterpret_cast<const void*>(sky_trsm_flow_kernel<64>);
-    const size_t smem = bk128 ? flow_smem_bytes<128>() : flow_smem_bytes<64>();
+    const void* func = bk == 32 ? reinterpret_cast<const void*>(sky_trsm_flow_kernel<32>) : reinterpret_cast<const void*>(sky_trsm_flow_kernel<64>);
+    const size_t smem = bk == 32 ? flow_smem_bytes<32>() : flow_smem_bytes<64>();
     cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, 128, smem);
@@ -1813,13 +1817,14 @@ int32_t launch_flow(bbm_handle_t h, const void* flow_tiles, i64 flow_ntiles, int
     const i64 cap = bbm_opt(h, "trsm.flow_ctas_per_sm", 0);
     if (cap > 0) occ = (int)std::min<i64>(occ, cap);
     const i64 grid = std::min<i64>(flow_ntiles, (i64)occ * h->num_sms);
-    BBM_CUDA(h, cudaMemsetAsync(flow_ctr, 0, sizeof(int) * (size_t)(flow_nctr + 1), h->stream));
+    int cs = (int)std::min<i64>(kFlowCtrStride, std::max<i64>(1, bbm_opt(h, "trsm.flow_ctr_stride", kFlowCtrStride)));
+    BBM_CUDA(h, cudaMemsetAsync(flow_ctr, 0, sizeof(int) * (size_t)(flow_nctr + 1) * cs, h->stream));
     const FlowTile* tiles = static_cast<const FlowTile*>(flow_tiles);
     i64 ntiles = flow_ntiles;
     int* ctr = flow_ctr;
     int err_idx = (int)flow_nctr;
     int sleep_ns = (int)std::max<i64>(0, bbm_opt(h, "trsm.flow_sleep_ns", 32));
-    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&A1, (void*)&A0, (void*)&Bm, (void*)&X, (void*)&ctr, (void*)&err_idx, (void*)&sleep_ns};
+    void* args[] = {(void*)&tiles, (void*)&ntiles, (void*)&A1, (void*)&A0, (void*)&Bm, (void*)&X, (void*)&ctr, (void*)&err_idx, (void*)&sleep_ns, (void*)&cs};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident (the tiles wait for one another)
     e = cudaLaunchCooperativeKernel(func, dim3((unsigned)grid), dim3(128), args, smem, h->stream);
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_CUDA, "sky_trsm_flow_kernel launch: %s", cudaGetErrorString(e)); }
@@ -1829,7 +1834,7 @@ int32_t launch_flow(bbm_handle_t h, const void* flow_tiles, i64 flow_ntiles, int
 
 int32_t launch_trsm_flow(bbm_handle_t h, bbm_sky_desc_t d, int upper, const double* d_data, const double* W, double* d_B, double* X) {
     bbm_sky_desc::Tri& t = d->tri[upper];
-    return launch_flow(h, t.flow_tiles, t.flow_ntiles, t.flow_ctr, t.flow_nctr, t.flow_bk == 128, d_data, W, d_B, X);
+    return launch_flow(h, t.flow_tiles, t.flow_ntiles, t.flow_ctr, t.flow_nctr, (int)t.flow_bk, d_data, W, d_B, X);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2106,7 +2111,7 @@ int32_t build_qr_flow_plan(bbm_handle_t h, bbm_sky_desc_t d, i64 ldb, i64 ldw, i
     q.flow_tiles = dt;
     q.flow_ntiles = (i64)tiles.size();
     q.flow_nctr = nrow + P;
-    cudaError_t e = cudaMalloc(&q.flow_ctr, sizeof(int) * (size_t)(q.flow_nctr + 1));
+    cudaError_t e = cudaMalloc(&q.flow_ctr, sizeof(int) * (size_t)(q.flow_nctr + 1) * kFlowCtrStride);
     if (e != cudaSuccess) { cudaGetLastError(); return bbm_fail(h, BBM_ERR_ALLOC, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
     q.flow_ok = true;
     return BBM_OK;
@@ -2156,7 +2161,7 @@ int32_t sky_qr_lmul_adj_impl(bbm_handle_t h, bbm_sky_desc_t d, const double* d_f
     if (bbm_opt(h, "qr.flow", 1) != 0 && nrhs >= 8 && (reinterpret_cast<uintptr_t>(d_B) % 16 == 0)) {
         rc = build_qr_flow_plan(h, d, ldb, ldw, nrhs);
         if (rc != BBM_OK) return rc;
-        if (q.flow_ok) return launch_flow(h, q.flow_tiles, q.flow_ntiles, q.flow_ctr, q.flow_nctr, false, WS, WS, d_B, W);
+        if (q.flow_ok) return launch_flow(h, q.flow_tiles, q.flow_ntiles, q.flow_ctr, q.flow_nctr, 64, WS, WS, d_B, W);
     }
     const bool pdl = bbm_opt(h, "trsm.pdl", 1) != 0;
     for (i64 K = 0; K < q.ncols; ++K) {

@@ -330,8 +330,8 @@ def test_sky_trsm_matches_oracle(handle, case, uplo, unit, dtype):
 
 
 @pytest.mark.parametrize("uplo", ["U", "L"])
-@pytest.mark.parametrize("kernel,path", [(0, 1), (3, 2), (2, 0)])
-def test_sky_trsm_many_rhs_every_path(handle, uplo, kernel, path):
+@pytest.mark.parametrize("kernel,path,flow_bk", [(0, 1, 64), (0, 1, 32), (3, 2, 64), (2, 0, 64)])
+def test_sky_trsm_many_rhs_every_path(handle, uplo, kernel, path, flow_bk):
     """64 right-hand sides, aligned block sizes: the data-flow kernel (one persistent launch, default), the launch chain
     ("trsm.kernel" = 3) and the substitution kernels (= 2) against the oracle; several block steps deep so that every
     counter of the data-flow kernel is exercised (far updates of 3 block columns, ragged multiples of 2)."""
@@ -349,6 +349,7 @@ def test_sky_trsm_many_rhs_every_path(handle, uplo, kernel, path):
     Ad = A.to_device(handle)
     T = (B.UpperTriangular if uplo == "U" else B.LowerTriangular)(Ad)
     handle.set_option("trsm.kernel", kernel)
+    handle.set_option("trsm.flow_bk", flow_bk)
     try:
         for nrhs in (64, 40, 16):
             B0 = np.asfortranarray(rng.standard_normal((m, nrhs)))
@@ -363,6 +364,7 @@ def test_sky_trsm_many_rhs_every_path(handle, uplo, kernel, path):
             assert relerr(got, ref) <= tol(np.float64, 4 * 256)
     finally:
         handle.set_option("trsm.kernel", 0)
+        handle.set_option("trsm.flow_bk", 64)
 
 
 def test_sky_trsm_condition_guard(handle):
